@@ -1,0 +1,94 @@
+"""ctypes binding of liba3d.so (the C-ABI declared in include/a3d.h).
+
+The library is built in-tree by `__graft_entry__.build()` (nvcc, sm_100a).  There is NO fallback:
+if the shared object is missing, or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liba3d.so")
+
+A3D_F32, A3D_BF16 = 0, 1
+IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
+EPI_RELU, EPI_SIGMOID = 1, 2
+OP_FWD, OP_DGRAD, OP_WGRAD = 0, 1, 2
+
+
+class A3DError(RuntimeError):
+    pass
+
+
+class ConvDesc(C.Structure):
+    """Mirror of `a3d_conv_desc` (include/a3d.h)."""
+    _fields_ = [(n, C.c_int) for n in
+                ("N", "H", "W", "C", "K", "R", "S", "stride_h", "stride_w", "pad_t", "pad_l", "P", "Q", "ldy", "impl")]
+
+
+_vp, _i, _f, _sz, _u = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_uint
+
+# name -> (restype, argtypes); every symbol include/a3d.h declares
+SIGNATURES = {
+    "a3d_version": (_i, []),
+    "a3d_last_error": (C.c_char_p, []),
+    "a3d_create": (_i, [_i, C.POINTER(_vp)]),
+    "a3d_destroy": (_i, [_vp]),
+    "a3d_sm_count": (_i, [_vp]),
+    "a3d_launch_count": (C.c_uint64, [_vp]),
+    "a3d_resize_bilinear_tf1": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp]),
+    "a3d_conv2d_ws_bytes": (_sz, [_vp, C.POINTER(ConvDesc), _i]),
+    "a3d_conv2d_fwd": (_i, [_vp, C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _i, _u, _vp, _sz, _vp]),
+    "a3d_conv2d_dgrad": (_i, [_vp, C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _sz, _vp]),
+    "a3d_conv2d_wgrad": (_i, [_vp, C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "a3d_dense_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _i, _vp, _i, _i, _i, _u, _i, _vp]),
+    "a3d_dense_dgrad": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "a3d_dense_wgrad": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "a3d_dense_epilogue_bwd": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _sz, _u, _vp]),
+    "a3d_maxpool2x2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
+    "a3d_maxpool2x2_relu_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "a3d_relu_bwd": (_i, [_vp, _vp, _vp, _i, _vp, _sz, _i, _vp]),
+    "a3d_silog_loss": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
+    "a3d_adam_tf": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _vp]),
+    "a3d_sgd": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _vp]),
+    "a3d_cast_f32_bf16": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "a3d_scatter_channel_bf16": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp]),
+    "a3d_fill_zero": (_i, [_vp, _vp, _sz, _vp]),
+    "a3d_crf_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "a3d_pairwise_features": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _f, _vp, _vp, _vp]),
+    "a3d_pairwise_ws_bytes": (_sz, [_i, _i, _i]),
+    "a3d_tile_means": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "a3d_extract_patches": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "a3d_comm_unique_id": (_i, [C.c_char_p, _vp]),
+    "a3d_comm_init": (_i, [_vp, C.c_char_p, _vp, _i, _i]),
+    "a3d_comm_destroy": (_i, [_vp]),
+    "a3d_allreduce_sum": (_i, [_vp, _vp, _sz, _i, _vp]),
+    # engine unit-test hook (not part of the drop-in surface)
+    "a3d_debug_tc_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen liba3d.so and bind every declared symbol.  Raises A3DError if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise A3DError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU or PyTorch fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().a3d_last_error().decode(errors="replace")
+        raise A3DError(f"liba3d {what} failed (rc={rc}): {msg}")

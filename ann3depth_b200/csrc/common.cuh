@@ -1,0 +1,88 @@
+// common.cuh -- context, error plumbing and small device helpers shared by all liba3d sources.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/a3d.h"
+
+struct a3d_ctx {
+  int device;
+  int sm_count;
+  uint64_t launches;
+  // driver entry points (resolved with cudaGetDriverEntryPoint; no link-time libcuda dependency)
+  void* fn_encode_tiled;
+  void* fn_encode_im2col;
+  int driver_version;
+  // NCCL (dlopen)
+  void* nccl_lib;
+  void* nccl_comm;
+  int nranks;
+};
+
+void a3d_set_error(const char* fmt, ...);
+
+#define A3D_CHECK_CUDA(expr)                                                            \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      a3d_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return (int)_e;                                                                   \
+    }                                                                                   \
+  } while (0)
+
+#define A3D_REQUIRE(cond, ...)                                                          \
+  do {                                                                                  \
+    if (!(cond)) {                                                                      \
+      a3d_set_error(__VA_ARGS__);                                                       \
+      return A3D_EINVAL;                                                                \
+    }                                                                                   \
+  } while (0)
+
+// after a kernel launch
+#define A3D_LAUNCH_OK(ctx)                                                              \
+  do {                                                                                  \
+    (ctx)->launches++;                                                                  \
+    cudaError_t _e = cudaGetLastError();                                                \
+    if (_e != cudaSuccess) {                                                            \
+      a3d_set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return (int)_e;                                                                   \
+    }                                                                                   \
+  } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return (cudaStream_t)s; }
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float bf16_bits_to_f32(uint16_t b) {
+  return __uint_as_float(((uint32_t)b) << 16);
+}
+__device__ __forceinline__ uint16_t f32_to_bf16_bits(float f) {
+  __nv_bfloat16 h = __float2bfloat16_rn(f);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  return (uint32_t)f32_to_bf16_bits(lo) | ((uint32_t)f32_to_bf16_bits(hi) << 16);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// internal cross-file entry points
+int a3d_tc_conv_fwd_supported(const a3d_conv_desc* d);
+int a3d_simt_conv_fwd(a3d_ctx*, const a3d_conv_desc*, const uint16_t* x, const uint16_t* w, const float* bias,
+                      void* y, int y_dtype, unsigned flags, cudaStream_t st);
+int a3d_simt_conv_dgrad(a3d_ctx*, const a3d_conv_desc*, const uint16_t* dy, const uint16_t* w, uint16_t* dx,
+                        cudaStream_t st);
+int a3d_simt_conv_wgrad(a3d_ctx*, const a3d_conv_desc*, const uint16_t* x, const uint16_t* dy, float* dw,
+                        cudaStream_t st);
+int a3d_colsum_bf16(a3d_ctx*, const uint16_t* a, size_t rows, int C, int ld, float* out, cudaStream_t st);
+int a3d_simt_dense_fwd(a3d_ctx*, const uint16_t* x, int ldx, const uint16_t* w, const float* bias, const uint8_t* mask,
+                       float drop_rate, void* y, int y_dtype, int M, int N, int K, unsigned flags, cudaStream_t st);
+int a3d_simt_dense_dgrad(a3d_ctx*, const uint16_t* dy, const uint16_t* w, uint16_t* dx, int M, int N, int K,
+                         cudaStream_t st);
+int a3d_simt_dense_wgrad(a3d_ctx*, const uint16_t* x, int ldx, const uint16_t* dy, float* dw, int M, int N, int K,
+                         cudaStream_t st);

@@ -1,0 +1,298 @@
+// crf.cu -- DCNF structured part (src/models.py:95-177): fused pairwise features, tile means,
+// patch gather and the batched closed-form CRF (Cholesky in shared memory, one CTA per graph).
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace {
+
+constexpr int CRF_THREADS = 256;
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  float s = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+  return s;
+}
+
+// A (n x n, row-major, pitch n+1 to dodge bank conflicts) lives in dynamic smem.
+__global__ void __launch_bounds__(CRF_THREADS)
+crf_kernel(const float* __restrict__ z_, const float* __restrict__ y_, const float* __restrict__ r_,
+           const int32_t* __restrict__ pl, const int32_t* __restrict__ pr, int n, int n_pairs, float grad_scale,
+           float* __restrict__ ystar_, float* __restrict__ nll_, float* __restrict__ logdet_, float* __restrict__ dz_,
+           float* __restrict__ dr_, int32_t* __restrict__ status_) {
+  extern __shared__ float sm[];
+  const int ld = n + 1;
+  float* A = sm;                       // n*ld
+  float* z = A + (size_t)n * ld;       // n
+  float* y = z + n;                    // n
+  float* w = y + n;                    // n   (L w = z)
+  float* ys = w + n;                   // n   (L^T ys = w)
+  float* red = ys + n;                 // 32
+  float* tmp = red + 32;               // (warps) * n scratch for dr solves
+  __shared__ int s_status;
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const float* r = r_ + (size_t)b * n_pairs;
+
+  for (int i = tid; i < n * ld; i += nt) A[i] = 0.f;
+  for (int i = tid; i < n; i += nt) { z[i] = z_[(size_t)b * n + i]; y[i] = y_[(size_t)b * n + i]; }
+  if (tid == 0) s_status = 0;
+  __syncthreads();
+  // R[l][r] = R[r][l] = r_k  (scatter *update* semantics of src/models.py:138-141: last write wins)
+  if (tid == 0)
+    for (int k = 0; k < n_pairs; ++k) {
+      int l = pl[k], q = pr[k];
+      A[l * ld + q] = r[k];
+      A[q * ld + l] = r[k];
+    }
+  __syncthreads();
+  // A = I + diag(R 1) - R
+  for (int i = tid; i < n; i += nt) {
+    float s = 0.f;
+    for (int j = 0; j < n; ++j) s += A[i * ld + j];
+    w[i] = s;                          // row sums (A still holds R)
+  }
+  __syncthreads();
+  for (int idx = tid; idx < n * n; idx += nt) {
+    int i = idx / n, j = idx - i * n;
+    float v = -A[i * ld + j];
+    if (i == j) v += 1.f + w[i];
+    A[i * ld + j] = v;
+  }
+  __syncthreads();
+  // energy = y^T A y - 2 z^T y + z^T z
+  float e = 0.f, zz = 0.f;
+  for (int i = tid; i < n; i += nt) {
+    float s = 0.f;
+    for (int j = 0; j < n; ++j) s += A[i * ld + j] * y[j];
+    e += y[i] * s - 2.f * z[i] * y[i] + z[i] * z[i];
+    zz += z[i] * z[i];
+  }
+  const float energy = block_sum(e, red);
+  const float ztz = block_sum(zz, red);
+
+  // in-place right-looking Cholesky (lower triangle): A = L L^T
+  for (int k = 0; k < n; ++k) {
+    if (tid == 0) {
+      float d = A[k * ld + k];
+      if (!(d > 0.f)) { if (s_status == 0) s_status = k + 1; d = 1.f; }
+      A[k * ld + k] = sqrtf(d);
+    }
+    __syncthreads();
+    const float dk = A[k * ld + k];
+    for (int i = k + 1 + tid; i < n; i += nt) A[i * ld + k] /= dk;
+    __syncthreads();
+    const int rem = n - k - 1;
+    for (int idx = tid; idx < rem * rem; idx += nt) {
+      int i = k + 1 + idx / rem, j = k + 1 + idx % rem;
+      if (j <= i) A[i * ld + j] -= A[i * ld + k] * A[j * ld + k];
+    }
+    __syncthreads();
+  }
+  float ldsum = 0.f;
+  for (int i = tid; i < n; i += nt) ldsum += logf(A[i * ld + i]);
+  const float logdet = 2.f * block_sum(ldsum, red);
+
+  // forward / backward substitution by warp 0 (dot products via shuffles)
+  if (tid < 32) {
+    for (int i = 0; i < n; ++i) {
+      float s = 0.f;
+      for (int j = tid; j < i; j += 32) s += A[i * ld + j] * w[j];
+      s = warp_sum(s);
+      if (tid == 0) w[i] = (z[i] - s) / A[i * ld + i];
+      __syncwarp();
+    }
+    for (int i = n - 1; i >= 0; --i) {
+      float s = 0.f;
+      for (int j = i + 1 + tid; j < n; j += 32) s += A[j * ld + i] * ys[j];
+      s = warp_sum(s);
+      if (tid == 0) ys[i] = (w[i] - s) / A[i * ld + i];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  float q = 0.f;
+  for (int i = tid; i < n; i += nt) q += w[i] * w[i];
+  const float quad = block_sum(q, red);
+  const bool ok = (s_status == 0);
+  if (tid == 0) {
+    status_[b] = s_status;
+    nll_[b] = ok ? energy + 0.5f * n * logf(CUDART_PI_F) - 0.5f * logdet + quad - ztz : 0.f;
+    if (logdet_) logdet_[b] = ok ? logdet : 0.f;
+  }
+  for (int i = tid; i < n; i += nt) {
+    if (ystar_) ystar_[(size_t)b * n + i] = ok ? ys[i] : 0.f;
+    if (dz_) dz_[(size_t)b * n + i] = ok ? grad_scale * 2.f * (ys[i] - y[i]) : 0.f;
+  }
+  if (dr_) {
+    // d nll / d r_k = (y_l-y_r)^2 - (y*_l-y*_r)^2 - 0.5 * || L^-1 (e_l - e_r) ||^2
+    const int wid = tid >> 5, lane = tid & 31, nw = nt >> 5;
+    float* t = tmp + (size_t)wid * n;
+    for (int k = wid; k < n_pairs; k += nw) {
+      int l = pl[k], rr = pr[k];
+      float nrm = 0.f;
+      for (int i = 0; i < n; ++i) {
+        float s = 0.f;
+        for (int j = lane; j < i; j += 32) s += A[i * ld + j] * t[j];
+        s = warp_sum(s);
+        float rhs = (i == l ? 1.f : 0.f) - (i == rr ? 1.f : 0.f);
+        float ti = (rhs - s) / A[i * ld + i];
+        if (lane == 0) t[i] = ti;
+        nrm += ti * ti;
+        __syncwarp();
+      }
+      if (lane == 0) {
+        float dy = y[l] - y[rr], ds = ys[l] - ys[rr];
+        dr_[(size_t)b * n_pairs + k] = ok ? grad_scale * (dy * dy - ds * ds - 0.5f * nrm) : 0.f;
+      }
+    }
+  }
+}
+
+// ---- pairwise features ---------------------------------------------------------------------
+constexpr int TILE = 40, TPIX = TILE * TILE, NBINS = 256, FEAT = TPIX + NBINS;
+
+// one CTA per (image, tile): channel-mean vector [1600] and 256-bin colour histogram
+__global__ void tile_features_kernel(const float* __restrict__ img, int H, int W, int cols, int n_tiles,
+                                     float* __restrict__ feat) {
+  __shared__ unsigned int hist[NBINS];
+  const int b = blockIdx.x / n_tiles, t = blockIdx.x % n_tiles;
+  const int tr = t / cols, tcol = t % cols;
+  for (int i = threadIdx.x; i < NBINS; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  float* f = feat + (size_t)blockIdx.x * FEAT;
+  for (int i = threadIdx.x; i < TPIX; i += blockDim.x) {
+    int py = tr * TILE + i / TILE, px = tcol * TILE + i % TILE;
+    float r = 0.f, g = 0.f, bl = 0.f;
+    if (py < H && px < W) {       // SAME padding of extract_image_patches: zeros outside
+      const float* p = img + (((size_t)b * H + py) * W + px) * 3;
+      r = p[0]; g = p[1]; bl = p[2];
+    }
+    f[i] = (r + g + bl) / 3.f;
+    // src/models.py:97-99: v = R*2^24 + G*2^16 + B*2^8 ; bin = clip(floor(256 * v / 2^24), 0, 255)
+    float v = r * 16777216.f + g * 65536.f + bl * 256.f;
+    float scaled = v / 16777216.f;
+    int bin = (int)floorf(scaled * (float)NBINS);
+    bin = max(0, min(NBINS - 1, bin));
+    atomicAdd(&hist[bin], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NBINS; i += blockDim.x) f[TPIX + i] = (float)hist[i];
+}
+
+// one warp per (image, pair)
+__global__ void pair_similarity_kernel(const float* __restrict__ feat, const int32_t* __restrict__ pl,
+                                       const int32_t* __restrict__ pr, int n_tiles, int n_pairs, int total, float gamma,
+                                       float* __restrict__ sims) {
+  int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= total) return;
+  int b = gw / n_pairs, k = gw % n_pairs;
+  const float* fl = feat + ((size_t)b * n_tiles + pl[k]) * FEAT;
+  const float* fr = feat + ((size_t)b * n_tiles + pr[k]) * FEAT;
+  float s0 = 0.f, s1 = 0.f;
+  for (int i = lane; i < TPIX; i += 32) { float d = fl[i] - fr[i]; s0 += d * d; }
+  for (int i = lane; i < NBINS; i += 32) { float d = fl[TPIX + i] - fr[TPIX + i]; s1 += d * d; }
+  s0 = warp_sum(s0);
+  s1 = warp_sum(s1);
+  if (lane == 0) {
+    sims[(size_t)gw * 2 + 0] = expf(-gamma * sqrtf(s0));
+    sims[(size_t)gw * 2 + 1] = expf(-gamma * sqrtf(s1));
+  }
+}
+
+__global__ void tile_means_kernel(const float* __restrict__ depth, int H, int W, int cols, int n_tiles,
+                                  float* __restrict__ y) {
+  __shared__ float red[32];
+  const int b = blockIdx.x / n_tiles, t = blockIdx.x % n_tiles;
+  const int tr = t / cols, tcol = t % cols;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < TPIX; i += blockDim.x) {
+    int py = tr * TILE + i / TILE, px = tcol * TILE + i % TILE;
+    if (py < H && px < W) s += depth[((size_t)b * H + py) * W + px];
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) y[blockIdx.x] = s / (float)TPIX;
+}
+
+// 100x100 patches, stride 40, SAME (30 px zero border) -> bf16 NHWC with dstC channels
+__global__ void extract_patches_kernel(const float* __restrict__ img, int B, int H, int W, int rows, int cols,
+                                       uint16_t* __restrict__ out, int dstC) {
+  const int PS = 100, PAD = 30;
+  size_t total = (size_t)B * rows * cols * PS * PS;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int px = (int)(i % PS);
+    size_t t = i / PS;
+    int py = (int)(t % PS);
+    t /= PS;
+    int pc = (int)(t % cols);
+    t /= cols;
+    int prow = (int)(t % rows);
+    int b = (int)(t / rows);
+    int iy = prow * TILE - PAD + py, ix = pc * TILE - PAD + px;
+    float v[3] = {0.f, 0.f, 0.f};
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      const float* p = img + (((size_t)b * H + iy) * W + ix) * 3;
+      v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
+    }
+    uint16_t* o = out + i * dstC;
+    for (int c = 0; c < dstC; ++c) o[c] = c < 3 ? f32_to_bf16_bits(v[c]) : (uint16_t)0;
+  }
+}
+
+}  // namespace
+
+extern "C" int a3d_crf_fwd_bwd(a3d_ctx* ctx, const float* z, const float* y, const float* r, const int32_t* pl,
+                               const int32_t* pr, int B, int n, int n_pairs, float grad_scale, float* ystar, float* nll,
+                               float* logdet, float* dz, float* dr, int32_t* status, void* stream) {
+  A3D_REQUIRE(ctx && z && y && r && pl && pr && nll && status, "crf: null argument");
+  A3D_REQUIRE(B > 0 && n > 0 && n <= 192 && n_pairs >= 0, "crf: n must be in 1..192");
+  size_t smem = ((size_t)n * (n + 1) + 4 * (size_t)n + 32 + (size_t)(CRF_THREADS / 32) * n) * sizeof(float);
+  if (smem > 48 * 1024)
+    A3D_CHECK_CUDA(cudaFuncSetAttribute(crf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  crf_kernel<<<B, CRF_THREADS, smem, as_stream(stream)>>>(z, y, r, pl, pr, n, n_pairs, grad_scale, ystar, nll, logdet, dz,
+                                                         dr, status);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
+extern "C" size_t a3d_pairwise_ws_bytes(int B, int H, int W) {
+  int rows = (H + TILE - 1) / TILE, cols = (W + TILE - 1) / TILE;
+  return (size_t)B * rows * cols * FEAT * sizeof(float);
+}
+
+extern "C" int a3d_pairwise_features(a3d_ctx* ctx, const float* images, int B, int H, int W, const int32_t* pl,
+                                     const int32_t* pr, int n_pairs, float gamma, float* tile_feat_ws, float* sims,
+                                     void* stream) {
+  A3D_REQUIRE(ctx && images && pl && pr && tile_feat_ws && sims, "pairwise_features: null argument");
+  int rows = (H + TILE - 1) / TILE, cols = (W + TILE - 1) / TILE, n_tiles = rows * cols;
+  tile_features_kernel<<<B * n_tiles, 256, 0, as_stream(stream)>>>(images, H, W, cols, n_tiles, tile_feat_ws);
+  A3D_LAUNCH_OK(ctx);
+  int total = B * n_pairs;
+  pair_similarity_kernel<<<ceil_div((long long)total * 32, 256), 256, 0, as_stream(stream)>>>(
+      tile_feat_ws, pl, pr, n_tiles, n_pairs, total, gamma, sims);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
+extern "C" int a3d_tile_means(a3d_ctx* ctx, const float* depth, int B, int H, int W, float* y, void* stream) {
+  A3D_REQUIRE(ctx && depth && y, "tile_means: null argument");
+  int rows = (H + TILE - 1) / TILE, cols = (W + TILE - 1) / TILE, n_tiles = rows * cols;
+  tile_means_kernel<<<B * n_tiles, 256, 0, as_stream(stream)>>>(depth, H, W, cols, n_tiles, y);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
+extern "C" int a3d_extract_patches(a3d_ctx* ctx, const float* images, int B, int H, int W, uint16_t* patches, int dstC,
+                                   void* stream) {
+  A3D_REQUIRE(ctx && images && patches && dstC >= 3, "extract_patches: bad argument");
+  int rows = (H + TILE - 1) / TILE, cols = (W + TILE - 1) / TILE;
+  size_t total = (size_t)B * rows * cols * 100 * 100;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > (size_t)ctx->sm_count * 32) blocks = (size_t)ctx->sm_count * 32;
+  extract_patches_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(images, B, H, W, rows, cols, patches, dstC);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}

@@ -1,0 +1,417 @@
+// elementwise.cu -- the HBM-bound kernels of the MSDN/DCNF step: bilinear resize, 2x2 max-pool
+// (fwd / bwd fused with ReLU-grad), scale-invariant log loss (+grad), TF-Adam / SGD, casts.
+// All are coalesced, 128-bit vectorised where the layout allows, and sized as grid-stride loops
+// over a multiple of the SM count.
+#include "common.cuh"
+
+static inline int grid_for(a3d_ctx* ctx, size_t work_items, int block, int max_waves = 8) {
+  size_t blocks = (work_items + block - 1) / block;
+  size_t cap = (size_t)ctx->sm_count * max_waves * (2048 / block);
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ------------------------------------------------------------------------------------ resize
+// TF1 legacy bilinear: src = dst * (in/out); lo = floor(src); hi = min(lo+1, in-1); lerp = src-lo.
+// One thread per output pixel; the <= 4 channels of a pixel are adjacent so a warp reads a
+// contiguous strip of each of the two source rows.
+template <bool OUT_BF16>
+__global__ void resize_bilinear_tf1_kernel(const float* __restrict__ src, int B, int H, int W, int C,
+                                           void* __restrict__ dst, int OH, int OW, int dstC, float sy, float sx) {
+  size_t total = (size_t)B * OH * OW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int ox = (int)(i % OW);
+    size_t t = i / OW;
+    int oy = (int)(t % OH);
+    int b = (int)(t / OH);
+    float fy = oy * sy, fx = ox * sx;
+    int y0 = (int)floorf(fy), x0 = (int)floorf(fx);
+    int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    float ly = fy - y0, lx = fx - x0;
+    const float* r0 = src + ((size_t)b * H + y0) * W * C;
+    const float* r1 = src + ((size_t)b * H + y1) * W * C;
+    for (int c = 0; c < dstC; ++c) {
+      float v = 0.f;
+      if (c < C) {
+        float tl = __ldg(r0 + (size_t)x0 * C + c), tr = __ldg(r0 + (size_t)x1 * C + c);
+        float bl = __ldg(r1 + (size_t)x0 * C + c), br = __ldg(r1 + (size_t)x1 * C + c);
+        float top = tl + (tr - tl) * lx;
+        float bot = bl + (br - bl) * lx;
+        v = top + (bot - top) * ly;
+      }
+      if (OUT_BF16) reinterpret_cast<uint16_t*>(dst)[i * dstC + c] = f32_to_bf16_bits(v);
+      else reinterpret_cast<float*>(dst)[i * dstC + c] = v;
+    }
+  }
+}
+
+extern "C" int a3d_resize_bilinear_tf1(a3d_ctx* ctx, const float* src, int B, int H, int W, int C, void* dst,
+                                       int OH, int OW, int dstC, int dst_dtype, void* stream) {
+  A3D_REQUIRE(ctx && src && dst, "resize: null argument");
+  A3D_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && OH > 0 && OW > 0 && dstC >= C, "resize: bad shape");
+  size_t total = (size_t)B * OH * OW;
+  int block = 256, grid = grid_for(ctx, total, block);
+  // the scale is formed in float like TF's CalculateResizeScale (in/out as float division)
+  float sy = (float)H / (float)OH, sx = (float)W / (float)OW;
+  if (dst_dtype == A3D_BF16)
+    resize_bilinear_tf1_kernel<true><<<grid, block, 0, as_stream(stream)>>>(src, B, H, W, C, dst, OH, OW, dstC, sy, sx);
+  else
+    resize_bilinear_tf1_kernel<false><<<grid, block, 0, as_stream(stream)>>>(src, B, H, W, C, dst, OH, OW, dstC, sy, sx);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ max-pool
+__device__ __forceinline__ uint4 max_bf16x8(uint4 a, uint4 b) {
+  uint4 r;
+  __nv_bfloat162* ra = reinterpret_cast<__nv_bfloat162*>(&a);
+  __nv_bfloat162* rb = reinterpret_cast<__nv_bfloat162*>(&b);
+  __nv_bfloat162* rr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) rr[i] = __hmax2(ra[i], rb[i]);
+  return r;
+}
+
+// one thread = one output pixel x 8 channels (16 B loads/stores)
+__global__ void maxpool2x2_fwd_kernel(const uint4* __restrict__ x, int N, int H, int W, int C8, uint4* __restrict__ y,
+                                      int ldy8) {
+  int OH = H / 2, OW = W / 2;
+  size_t total = (size_t)N * OH * OW * C8;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C8);
+    size_t t = i / C8;
+    int ow = (int)(t % OW);
+    t /= OW;
+    int oh = (int)(t % OH);
+    int n = (int)(t / OH);
+    const uint4* p = x + (((size_t)n * H + 2 * oh) * W + 2 * ow) * C8 + c;
+    uint4 a = __ldg(p), b = __ldg(p + C8), d = __ldg(p + (size_t)W * C8), e = __ldg(p + (size_t)W * C8 + C8);
+    y[(((size_t)n * OH + oh) * OW + ow) * ldy8 + c] = max_bf16x8(max_bf16x8(a, b), max_bf16x8(d, e));
+  }
+}
+
+extern "C" int a3d_maxpool2x2_fwd(a3d_ctx* ctx, const uint16_t* x, int N, int H, int W, int C, uint16_t* y, int ldy,
+                                  void* stream) {
+  A3D_REQUIRE(ctx && x && y, "maxpool: null argument");
+  A3D_REQUIRE(C % 8 == 0 && ldy % 8 == 0 && ldy >= C && H >= 2 && W >= 2, "maxpool: C and ldy must be multiples of 8");
+  size_t total = (size_t)N * (H / 2) * (W / 2) * (C / 8);
+  int block = 256, grid = grid_for(ctx, total, block);
+  maxpool2x2_fwd_kernel<<<grid, block, 0, as_stream(stream)>>>(reinterpret_cast<const uint4*>(x), N, H, W, C / 8,
+                                                             reinterpret_cast<uint4*>(y), ldy / 8);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
+// one thread = one 2x2 window (or an uncovered edge cell group) x 8 channels.
+// Gradient goes to the FIRST arg-max in (0,0),(0,1),(1,0),(1,1) order and only where x > 0 (ReLU).
+__global__ void maxpool2x2_relu_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, int lddy8, int N,
+                                           int H, int W, int C8, uint4* __restrict__ dx) {
+  int OH = H / 2, OW = W / 2;
+  int GH = (H + 1) / 2, GW = (W + 1) / 2;   // windows incl. the partial ones on the odd edge
+  size_t total = (size_t)N * GH * GW * C8;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C8);
+    size_t t = i / C8;
+    int gw = (int)(t % GW);
+    t /= GW;
+    int gh = (int)(t % GH);
+    int n = (int)(t / GH);
+    int h0 = 2 * gh, w0 = 2 * gw;
+    bool covered = (gh < OH) && (gw < OW);
+    size_t base = (((size_t)n * H + h0) * W + w0) * C8 + c;
+    uint4 zero = make_uint4(0, 0, 0, 0);
+    if (!covered) {
+      dx[base] = zero;
+      if (w0 + 1 < W) dx[base + C8] = zero;
+      if (h0 + 1 < H) {
+        dx[base + (size_t)W * C8] = zero;
+        if (w0 + 1 < W) dx[base + (size_t)W * C8 + C8] = zero;
+      }
+      continue;
+    }
+    uint4 xv[4] = {__ldg(x + base), __ldg(x + base + C8), __ldg(x + base + (size_t)W * C8),
+                   __ldg(x + base + (size_t)W * C8 + C8)};
+    uint4 g = __ldg(dy + (((size_t)n * OH + gh) * OW + gw) * lddy8 + c);
+    uint4 out[4];
+    const uint16_t* gv = reinterpret_cast<const uint16_t*>(&g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = bf16_bits_to_f32(reinterpret_cast<const uint16_t*>(&xv[k])[e]);
+      int arg = 0;
+      float m = v[0];
+#pragma unroll
+      for (int k = 1; k < 4; ++k)
+        if (v[k] > m) { m = v[k]; arg = k; }
+      uint16_t gg = (m > 0.f) ? gv[e] : (uint16_t)0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) reinterpret_cast<uint16_t*>(&out[k])[e] = (k == arg) ? gg : (uint16_t)0;
+    }
+    dx[base] = out[0];
+    dx[base + C8] = out[1];
+    dx[base + (size_t)W * C8] = out[2];
+    dx[base + (size_t)W * C8 + C8] = out[3];
+  }
+}
+
+extern "C" int a3d_maxpool2x2_relu_bwd(a3d_ctx* ctx, const uint16_t* x, const uint16_t* dy, int lddy, int N, int H,
+                                       int W, int C, uint16_t* dx, void* stream) {
+  A3D_REQUIRE(ctx && x && dy && dx, "maxpool_bwd: null argument");
+  A3D_REQUIRE(C % 8 == 0 && lddy % 8 == 0 && lddy >= C, "maxpool_bwd: C and lddy must be multiples of 8");
+  size_t total = (size_t)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+  int block = 256, grid = grid_for(ctx, total, block);
+  maxpool2x2_relu_bwd_kernel<<<grid, block, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(dy), lddy / 8, N, H, W, C / 8,
+      reinterpret_cast<uint4*>(dx));
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
+__global__ void relu_bwd_kernel(const uint4* __restrict__ y, const uint4* __restrict__ dy, int lddy8, uint4* __restrict__ dx,
+                                size_t rows, int C8) {
+  size_t total = rows * C8;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t r = i / C8;
+    int c = (int)(i % C8);
+    uint4 yv = __ldg(y + i), g = __ldg(dy + r * lddy8 + c), o;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = bf16_bits_to_f32(reinterpret_cast<const uint16_t*>(&yv)[e]);
+      reinterpret_cast<uint16_t*>(&o)[e] = v > 0.f ? reinterpret_cast<const uint16_t*>(&g)[e] : (uint16_t)0;
+    }
+    dx[i] = o;
+  }
+}
+
+extern "C" int a3d_relu_bwd(a3d_ctx* ctx, const uint16_t* y, const uint16_t* dy, int lddy, uint16_t* dx, size_t rows,
+                            int C, void* stream) {
+  A3D_REQUIRE(ctx && y && dy && dx, "relu_bwd: null argument");
+  A3D_REQUIRE(C % 8 == 0 && lddy % 8 == 0, "relu_bwd: C and lddy must be multiples of 8");
+  int block = 256, grid = grid_for(ctx, rows * (C / 8), block);
+  relu_bwd_kernel<<<grid, block, 0, as_stream(stream)>>>(reinterpret_cast<const uint4*>(y),
+                                                       reinterpret_cast<const uint4*>(dy), lddy / 8,
+                                                       reinterpret_cast<uint4*>(dx), rows, C / 8);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
+__global__ void dense_epilogue_bwd_kernel(const uint16_t* __restrict__ g_post, const uint16_t* __restrict__ y,
+                                          const uint8_t* __restrict__ mask, float scale, uint16_t* __restrict__ g_pre,
+                                          size_t n, unsigned flags) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float g = bf16_bits_to_f32(g_post[i]);
+    if (mask) g = mask[i] ? g * scale : 0.f;
+    float yv = bf16_bits_to_f32(y[i]);
+    if (flags & A3D_EPI_RELU) g = yv > 0.f ? g : 0.f;
+    if (flags & A3D_EPI_SIGMOID) g = g * yv * (1.f - yv);
+    g_pre[i] = f32_to_bf16_bits(g);
+  }
+}
+
+extern "C" int a3d_dense_epilogue_bwd(a3d_ctx* ctx, const uint16_t* g_post, const uint16_t* y, const uint8_t* keep_mask,
+                                      float drop_rate, uint16_t* g_pre, size_t n, unsigned flags, void* stream) {
+  A3D_REQUIRE(ctx && g_post && y && g_pre, "dense_epilogue_bwd: null argument");
+  int block = 256, grid = grid_for(ctx, n, block);
+  dense_epilogue_bwd_kernel<<<grid, block, 0, as_stream(stream)>>>(g_post, y, keep_mask, 1.f / (1.f - drop_rate), g_pre,
+                                                                 n, flags);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ loss
+// One CTA per sample.  Pass 1: d_i = nan0(log(out+eps)) - nan0(log(tar+eps)), block-reduce sum d and
+// sum d^2 with warp shuffles.  Pass 2: gradient (2 d_i - 2*lon*sum d) / (out_i+eps) / B, 0 on the NaN branch.
+__global__ void silog_loss_kernel(const float* __restrict__ out, const float* __restrict__ tar, int n, int B,
+                                  float lambda_over_n, float* __restrict__ loss_ps, float* __restrict__ dout_f32,
+                                  uint16_t* __restrict__ dout_bf16) {
+  extern __shared__ float sd[];          // n floats: cached d_i
+  __shared__ float red[2][32];
+  const float eps = 1e-8f;
+  int b = blockIdx.x;
+  const float* o = out + (size_t)b * n;
+  const float* t = tar + (size_t)b * n;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float lo = logf(o[i] + eps);
+    lo = isnan(lo) ? 0.f : lo;
+    float lt = logf(t[i] + eps);
+    lt = isnan(lt) ? 0.f : lt;
+    float d = lo - lt;
+    sd[i] = d;
+    s1 += d;
+    s2 += d * d;
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane == 0) { red[0][wid] = s1; red[1][wid] = s2; }
+  __syncthreads();
+  if (wid == 0) {
+    s1 = lane < nw ? red[0][lane] : 0.f;
+    s2 = lane < nw ? red[1][lane] : 0.f;
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) { red[0][0] = s1; red[1][0] = s2; }
+  }
+  __syncthreads();
+  s1 = red[0][0];
+  s2 = red[1][0];
+  if (threadIdx.x == 0) loss_ps[b] = s2 - lambda_over_n * s1 * s1;
+  if (dout_f32 || dout_bf16) {
+    float invB = 1.f / (float)B;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      float arg = o[i] + eps;
+      float g = 0.f;
+      if (!isnan(logf(arg))) g = (2.f * sd[i] - 2.f * lambda_over_n * s1) / arg * invB;
+      if (dout_f32) dout_f32[(size_t)b * n + i] = g;
+      if (dout_bf16) dout_bf16[(size_t)b * n + i] = f32_to_bf16_bits(g);
+    }
+  }
+}
+
+__global__ void mean_kernel(const float* __restrict__ v, int n, float* __restrict__ out) {
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 32) s += v[i];
+  s = warp_sum(s);
+  if (threadIdx.x == 0) *out = s / (float)n;
+}
+
+extern "C" int a3d_silog_loss(a3d_ctx* ctx, const float* out, const float* tar, int B, int n, float lambda_over_n,
+                              float* loss_per_sample, float* loss, float* dout_f32, uint16_t* dout_bf16, void* stream) {
+  A3D_REQUIRE(ctx && out && tar && loss_per_sample && loss, "silog_loss: null argument");
+  A3D_REQUIRE(B > 0 && n > 0 && (size_t)n * sizeof(float) <= 200 * 1024, "silog_loss: bad shape");
+  size_t smem = (size_t)n * sizeof(float);
+  if (smem > 48 * 1024)
+    A3D_CHECK_CUDA(cudaFuncSetAttribute(silog_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  silog_loss_kernel<<<B, 512, smem, as_stream(stream)>>>(out, tar, n, B, lambda_over_n, loss_per_sample, dout_f32,
+                                                        dout_bf16);
+  A3D_LAUNCH_OK(ctx);
+  mean_kernel<<<1, 32, 0, as_stream(stream)>>>(loss_per_sample, B, loss);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ optimizers
+// TF1 ApplyAdam; one pass, 128-bit loads/stores: 16 B read + 12 B written per parameter (+2 B bf16 mirror).
+__global__ void adam_tf_kernel(float4* __restrict__ w, const float4* __restrict__ g, float4* __restrict__ m,
+                               float4* __restrict__ v, uint2* __restrict__ wb, size_t n4, float lr_t, float b1, float b2,
+                               float eps, float gs) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 W = w[i], G = __ldg(g + i), M = m[i], V = v[i];
+    float* pw = &W.x; float* pg = &G.x; float* pm = &M.x; float* pv = &V.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float gk = pg[k] * gs;
+      pm[k] = b1 * pm[k] + (1.f - b1) * gk;
+      pv[k] = b2 * pv[k] + (1.f - b2) * gk * gk;
+      pw[k] = pw[k] - lr_t * pm[k] / (sqrtf(pv[k]) + eps);
+    }
+    w[i] = W; m[i] = M; v[i] = V;
+    if (wb) wb[i] = make_uint2(pack_bf16x2(W.x, W.y), pack_bf16x2(W.z, W.w));
+  }
+}
+__global__ void adam_tf_tail_kernel(float* w, const float* g, float* m, float* v, uint16_t* wb, size_t start, size_t n,
+                                    float lr_t, float b1, float b2, float eps, float gs) {
+  size_t i = start + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) {
+    float gk = g[i] * gs;
+    float mm = b1 * m[i] + (1.f - b1) * gk;
+    float vv = b2 * v[i] + (1.f - b2) * gk * gk;
+    float ww = w[i] - lr_t * mm / (sqrtf(vv) + eps);
+    m[i] = mm; v[i] = vv; w[i] = ww;
+    if (wb) wb[i] = f32_to_bf16_bits(ww);
+  }
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int a3d_adam_tf(a3d_ctx* ctx, float* w, const float* g, float* m, float* v, uint16_t* w_bf16, size_t n,
+                           float lr_t, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  A3D_REQUIRE(ctx && w && g && m && v, "adam: null argument");
+  if (n == 0) return 0;
+  bool vec = aligned16(w) && aligned16(g) && aligned16(m) && aligned16(v) &&
+             (!w_bf16 || (reinterpret_cast<uintptr_t>(w_bf16) & 7) == 0);
+  size_t n4 = vec ? n / 4 : 0;
+  if (n4) {
+    int block = 256, grid = grid_for(ctx, n4, block);
+    adam_tf_kernel<<<grid, block, 0, as_stream(stream)>>>(reinterpret_cast<float4*>(w), reinterpret_cast<const float4*>(g),
+                                                        reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v),
+                                                        reinterpret_cast<uint2*>(w_bf16), n4, lr_t, beta1, beta2, eps,
+                                                        grad_scale);
+    A3D_LAUNCH_OK(ctx);
+  }
+  size_t done = n4 * 4;
+  if (done < n) {
+    size_t rem = n - done;
+    adam_tf_tail_kernel<<<ceil_div(rem, 256), 256, 0, as_stream(stream)>>>(w, g, m, v, w_bf16, done, n, lr_t, beta1, beta2,
+                                                                          eps, grad_scale);
+    A3D_LAUNCH_OK(ctx);
+  }
+  return 0;
+}
+
+__global__ void sgd_kernel(float* __restrict__ w, const float* __restrict__ g, uint16_t* __restrict__ wb, size_t n, float lr,
+                           float gs) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float ww = w[i] - lr * (g[i] * gs);
+    w[i] = ww;
+    if (wb) wb[i] = f32_to_bf16_bits(ww);
+  }
+}
+extern "C" int a3d_sgd(a3d_ctx* ctx, float* w, const float* g, uint16_t* w_bf16, size_t n, float lr, float grad_scale,
+                       void* stream) {
+  A3D_REQUIRE(ctx && w && g, "sgd: null argument");
+  if (n == 0) return 0;
+  int block = 256, grid = grid_for(ctx, n, block);
+  sgd_kernel<<<grid, block, 0, as_stream(stream)>>>(w, g, w_bf16, n, lr, grad_scale);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ s, uint16_t* __restrict__ d, size_t n) {
+  size_t n4 = n / 4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 f = __ldg(reinterpret_cast<const float4*>(s) + i);
+    reinterpret_cast<uint2*>(d)[i] = make_uint2(pack_bf16x2(f.x, f.y), pack_bf16x2(f.z, f.w));
+  }
+  size_t i = n4 * 4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) d[i] = f32_to_bf16_bits(s[i]);
+}
+__global__ void cast_f32_bf16_scalar_kernel(const float* __restrict__ s, uint16_t* __restrict__ d, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    d[i] = f32_to_bf16_bits(s[i]);
+}
+extern "C" int a3d_cast_f32_bf16(a3d_ctx* ctx, const float* src, uint16_t* dst, size_t n, void* stream) {
+  A3D_REQUIRE(ctx && src && dst, "cast: null argument");
+  if (n == 0) return 0;
+  int block = 256;
+  if (aligned16(src) && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+    int grid = grid_for(ctx, n / 4 + 1, block);
+    cast_f32_bf16_kernel<<<grid, block, 0, as_stream(stream)>>>(src, dst, n);
+  } else {
+    cast_f32_bf16_scalar_kernel<<<grid_for(ctx, n, block), block, 0, as_stream(stream)>>>(src, dst, n);
+  }
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
+__global__ void scatter_channel_kernel(const float* __restrict__ s, uint16_t* __restrict__ d, size_t rows, int ld, int ch) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < rows; i += (size_t)gridDim.x * blockDim.x)
+    d[i * ld + ch] = f32_to_bf16_bits(s[i]);
+}
+extern "C" int a3d_scatter_channel_bf16(a3d_ctx* ctx, const float* src, uint16_t* dst, size_t rows, int ld, int ch,
+                                        void* stream) {
+  A3D_REQUIRE(ctx && src && dst && ch >= 0 && ch < ld, "scatter_channel: bad argument");
+  int block = 256, grid = grid_for(ctx, rows, block);
+  scatter_channel_kernel<<<grid, block, 0, as_stream(stream)>>>(src, dst, rows, ld, ch);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
+extern "C" int a3d_fill_zero(a3d_ctx* ctx, void* p, size_t bytes, void* stream) {
+  A3D_REQUIRE(ctx && p, "fill_zero: null argument");
+  A3D_CHECK_CUDA(cudaMemsetAsync(p, 0, bytes, as_stream(stream)));
+  return 0;
+}

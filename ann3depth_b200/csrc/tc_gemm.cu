@@ -1,0 +1,284 @@
+// tc_gemm.cu -- host side of the tcgen05 GEMM engine: tensor-map construction, tile/split selection
+// and the launchers used by the convolution / dense entry points.
+#include "tc_gemm.cuh"
+#include <cuda.h>
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+
+CUtensorMapSwizzle swizzle_for(int row_bytes) {
+  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+         : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+         : row_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                           : CU_TENSOR_MAP_SWIZZLE_NONE;
+}
+
+// bf16 2-D tensor [rows][cols] (cols contiguous, row pitch ld elements); box = box_cols x box_rows.
+int make_tmap_2d(a3d_ctx* ctx, CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                 uint32_t box_cols, uint32_t box_rows) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides[0] & 15)) {
+    a3d_set_error("tensor map: base %p / row pitch %llu B not 16-byte aligned", base, (unsigned long long)strides[0]);
+    return A3D_EINVAL;
+  }
+  CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->fn_encode_tiled)(
+      tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(box_cols * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    a3d_set_error("cuTensorMapEncodeTiled failed (%d): rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r,
+                  (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_cols, box_rows);
+    return A3D_ETMAP;
+  }
+  return 0;
+}
+
+// bf16 NHWC activation tensor in im2col mode.  Base pixels run over lower + {0..P-1} * stride per axis.
+int make_tmap_im2col(a3d_ctx* ctx, CUtensorMap* tm, const void* base, int N, int H, int W, int C, int lower_h,
+                     int lower_w, int P, int Q, int sh, int sw, uint32_t chan_box, uint32_t pixels) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  // tightest bounding box that still contains the last base pixel (see DESIGN.md "im2col corners")
+  int upper_w = lower_w + (Q - 1) * sw + 1 - W;
+  int upper_h = lower_h + (P - 1) * sh + 1 - H;
+  int lower[2] = {lower_w, lower_h};
+  int upper[2] = {upper_w, upper_h};
+  cuuint32_t estr[4] = {1, (cuuint32_t)sw, (cuuint32_t)sh, 1};
+  for (int i = 0; i < 2; ++i)
+    if (lower[i] < -128 || lower[i] > 127 || upper[i] < -128 || upper[i] > 127) {
+      a3d_set_error("im2col tensor map: corner out of [-128,127] (lower %d,%d upper %d,%d)", lower_w, lower_h, upper_w,
+                    upper_h);
+      return A3D_ENOTSUP;
+    }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides[0] & 15)) {
+    a3d_set_error("im2col tensor map: base/pixel pitch not 16-byte aligned (C=%d)", C);
+    return A3D_EINVAL;
+  }
+  CUresult r = reinterpret_cast<EncodeIm2colFn>(ctx->fn_encode_im2col)(
+      tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, lower, upper, chan_box, pixels,
+      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(chan_box * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    a3d_set_error("cuTensorMapEncodeIm2col failed (%d): NHWC=%d,%d,%d,%d lower=%d,%d upper=%d,%d box=%u x %u", (int)r, N,
+                  H, W, C, lower_w, lower_h, upper_w, upper_h, chan_box, pixels);
+    return A3D_ETMAP;
+  }
+  // Driver quirk also worked around by CUTLASS (copy_traits_sm90_im2col.hpp): for tensors smaller
+  // than 128 KiB, drivers <= 13.1 set a descriptor bit that makes im2col loads fault.
+  if (ctx->driver_version <= 13010) {
+    size_t bytes = (size_t)N * H * W * C * 2;
+    if (bytes < 131072) reinterpret_cast<uint64_t*>(tm)[1] &= ~(1ull << 21);
+  }
+  return 0;
+}
+
+template <class C>
+int launch_cfg(a3d_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const tc::Params& p, int splits,
+               cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    A3D_CHECK_CUDA(cudaFuncSetAttribute(tc::gemm_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(p.M, C::BM), ceil_div(p.N, C::BN), splits);
+  tc::gemm_kernel<C><<<grid, 192, C::SMEM_BYTES, st>>>(tmA, tmB, p);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
+// K-major x K-major dispatch over (BN, KCB)
+int launch_kk(a3d_ctx* ctx, int bn, int kcb, const CUtensorMap& tmA, const CUtensorMap& tmB, const tc::Params& p,
+              int splits, cudaStream_t st) {
+#define A3D_CASE(BN, KCB) \
+  if (bn == BN && kcb == KCB) return launch_cfg<tc::Cfg<BN, KCB, false, false>>(ctx, tmA, tmB, p, splits, st);
+  A3D_CASE(32, 128) A3D_CASE(64, 128) A3D_CASE(96, 128) A3D_CASE(128, 128) A3D_CASE(192, 128) A3D_CASE(256, 128)
+  A3D_CASE(32, 64) A3D_CASE(64, 64) A3D_CASE(96, 64) A3D_CASE(128, 64) A3D_CASE(192, 64) A3D_CASE(256, 64)
+  A3D_CASE(32, 32) A3D_CASE(64, 32) A3D_CASE(96, 32) A3D_CASE(128, 32) A3D_CASE(256, 32)
+#undef A3D_CASE
+  a3d_set_error("tc gemm: no kernel for BN=%d KCB=%d", bn, kcb);
+  return A3D_ENOTSUP;
+}
+
+int pick_bn(int n) {
+  if (n <= 32) return 32;
+  if (n <= 64) return 64;
+  if (n <= 96) return 96;
+  if (n <= 128) return 128;
+  if (n % 192 == 0 && n % 128 != 0) return 192;
+  return 128;
+}
+
+// how many K splits give roughly >= 1 wave of CTAs without starving each split
+int pick_splits(a3d_ctx* ctx, int tiles, int num_kb, int min_kb_per_split) {
+  if (tiles >= ctx->sm_count * 3 / 4) return 1;
+  int s = (ctx->sm_count + tiles - 1) / tiles;
+  int max_s = num_kb / min_kb_per_split;
+  if (max_s < 1) max_s = 1;
+  if (s > max_s) s = max_s;
+  return s < 1 ? 1 : s;
+}
+
+__global__ void bias_act_cast_kernel(const float* __restrict__ acc, const float* __restrict__ bias,
+                                     const uint8_t* __restrict__ mask, float drop_scale, void* __restrict__ y, int y_f32,
+                                     size_t rows, int n, long long ldy, unsigned flags) {
+  size_t total = rows * n;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t r = i / n;
+    int c = (int)(i - r * n);
+    float v = acc[i];
+    if (bias) v += bias[c];
+    if (flags & A3D_EPI_RELU) v = fmaxf(v, 0.f);
+    if (flags & A3D_EPI_SIGMOID) v = 1.f / (1.f + expf(-v));
+    if (mask) v = mask[i] ? v * drop_scale : 0.f;
+    if (y_f32) reinterpret_cast<float*>(y)[r * ldy + c] = v;
+    else reinterpret_cast<uint16_t*>(y)[r * ldy + c] = f32_to_bf16_bits(v);
+  }
+}
+
+int finish(a3d_ctx* ctx, const float* acc, const float* bias, const uint8_t* mask, float drop_rate, void* y, int y_f32,
+           size_t rows, int n, long long ldy, unsigned flags, cudaStream_t st) {
+  size_t total = rows * n;
+  int block = 256;
+  size_t blocks = (total + block - 1) / block;
+  if (blocks > (size_t)ctx->sm_count * 16) blocks = (size_t)ctx->sm_count * 16;
+  bias_act_cast_kernel<<<(int)blocks, block, 0, st>>>(acc, bias, mask, 1.f / (1.f - drop_rate), y, y_f32, rows, n, ldy,
+                                                     flags);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// convolution forward as an implicit GEMM: M = N*P*Q output pixels, N = K filters, K = R*S*C
+int a3d_tc_conv_fwd_supported(const a3d_conv_desc* d) {
+  if (d->C % 16) return 0;                       // im2col box needs >= 32 B of channels per pixel
+  if (d->stride_h > 8 || d->stride_w > 8) return 0;
+  if (d->R > 256 || d->S > 256) return 0;
+  if (d->ldy % 8) return 0;
+  return 1;
+}
+
+size_t a3d_tc_conv_fwd_ws_bytes(a3d_ctx* ctx, const a3d_conv_desc* d) {
+  // split-K accumulation buffer (only used when the tile count is far below one wave)
+  return (size_t)d->N * d->P * d->Q * d->K * sizeof(float);
+}
+
+int a3d_tc_conv_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, const uint16_t* w, const float* bias,
+                    void* y, int y_dtype, unsigned flags, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!a3d_tc_conv_fwd_supported(d)) {
+    a3d_set_error("tc conv fwd: unsupported shape (C=%d must be a multiple of 16)", d->C);
+    return A3D_ENOTSUP;
+  }
+  const int kc = d->C % 64 == 0 ? 64 : d->C % 32 == 0 ? 32 : 16;   // channels per k-block
+  const int kcb = kc * 2;
+  const int cblocks = d->C / kc;
+  const int num_kb = d->R * d->S * cblocks;
+  const long long M = (long long)d->N * d->P * d->Q;
+  const int bn = pick_bn(d->K);
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_im2col(ctx, &tmA, x, d->N, d->H, d->W, d->C, -d->pad_t, -d->pad_l, d->P, d->Q, d->stride_h,
+                            d->stride_w, kc, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d(ctx, &tmB, w, d->K, (uint64_t)d->R * d->S * d->C, (uint64_t)d->R * d->S * d->C, kc, bn);
+  if (rc) return rc;
+  tc::Params p{};
+  p.M = (int)M; p.N = d->K; p.num_kb = num_kb;
+  p.a_mode = tc::A_IM2COL; p.a_k0 = 0;
+  p.PQ = d->P * d->Q; p.Q = d->Q; p.sh = d->stride_h; p.sw = d->stride_w; p.lower_h = -d->pad_t; p.lower_w = -d->pad_l;
+  p.S = d->S; p.cblocks = cblocks;
+  const int tiles = ceil_div(M, 128) * ceil_div(d->K, bn);
+  int splits = pick_splits(ctx, tiles, num_kb, 8);
+  if (splits > 1 && (!ws || ws_bytes < (size_t)M * d->K * sizeof(float))) splits = 1;
+  p.kb_per_split = ceil_div(num_kb, splits);
+  splits = ceil_div(num_kb, p.kb_per_split);
+  if (splits == 1) {
+    p.epi = y_dtype == A3D_F32 ? tc::EPI_ROW_F32 : tc::EPI_ROW_BF16;
+    p.out = y; p.ldo = d->ldy; p.bias = bias; p.flags = flags; p.atomic = 0;
+    return launch_kk(ctx, bn, kcb, tmA, tmB, p, 1, st);
+  }
+  A3D_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)M * d->K * sizeof(float), st));
+  p.epi = tc::EPI_ROW_F32; p.out = ws; p.ldo = d->K; p.bias = nullptr; p.flags = 0; p.atomic = 1;
+  rc = launch_kk(ctx, bn, kcb, tmA, tmB, p, splits, st);
+  if (rc) return rc;
+  return finish(ctx, reinterpret_cast<const float*>(ws), bias, nullptr, 0.f, y, y_dtype == A3D_F32, (size_t)M, d->K,
+                d->ldy, flags, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// dense forward: the weight matrix [N_out][K] is the 128-row operand (it is the one that has to be
+// streamed from HBM exactly once); the activations [M_batch][K] are the UMMA N operand.
+// acc_ws f32 [M_batch][N_out] receives the split-K partial sums; `finish` applies bias/act/dropout.
+int a3d_tc_dense_fwd(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t* w, const float* bias,
+                     const uint8_t* mask, float drop_rate, void* y, int y_dtype, float* acc_ws, int M, int N, int K,
+                     unsigned flags, cudaStream_t st) {
+  if (K % 64 || ldx % 8 || M > 256 || !acc_ws) {
+    a3d_set_error("tc dense fwd: needs K %% 64 == 0, batch <= 256 and an accumulation workspace (K=%d M=%d)", K, M);
+    return A3D_ENOTSUP;
+  }
+  int bn = M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d(ctx, &tmA, w, N, K, K, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d(ctx, &tmB, x, M, K, ldx, 64, bn);
+  if (rc) return rc;
+  tc::Params p{};
+  p.M = N; p.N = M; p.num_kb = K / 64; p.a_mode = tc::A_TILED; p.a_k0 = 0;
+  const int tiles = ceil_div(N, 128);
+  int splits = pick_splits(ctx, tiles, p.num_kb, 4);
+  // weight streaming is HBM-bound: two CTAs' worth of loads in flight per SM helps, so oversubscribe
+  if (splits * tiles < 2 * ctx->sm_count && p.num_kb / (splits * 2) >= 4) splits *= 2;
+  p.kb_per_split = ceil_div(p.num_kb, splits);
+  splits = ceil_div(p.num_kb, p.kb_per_split);
+  A3D_CHECK_CUDA(cudaMemsetAsync(acc_ws, 0, (size_t)M * N * sizeof(float), st));
+  p.epi = tc::EPI_COL_F32; p.out = acc_ws; p.ldo = N; p.bias = nullptr; p.flags = 0; p.atomic = 1;
+  rc = launch_kk(ctx, bn, 128, tmA, tmB, p, splits, st);
+  if (rc) return rc;
+  return finish(ctx, acc_ws, bias, mask, drop_rate, y, y_dtype == A3D_F32, (size_t)M, N, N, flags, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Raw GEMM for unit tests of the engine: D[M][N] (f32, row-major) = A * B^T with every combination
+// of operand majors.  K-major operand: [rows][K]; MN-major operand: [K][rows].
+extern "C" int a3d_debug_tc_gemm(a3d_ctx* ctx, const uint16_t* A, const uint16_t* B, float* D, int M, int N, int K,
+                                 int bn, int kcb, int a_mn, int b_mn, int splits, void* stream) {
+  A3D_REQUIRE(ctx && A && B && D, "debug gemm: null argument");
+  cudaStream_t st = as_stream(stream);
+  CUtensorMap tmA, tmB;
+  int rc;
+  const int kelems = (a_mn || b_mn) ? 64 : kcb / 2;
+  A3D_REQUIRE(K % kelems == 0, "debug gemm: K must be a multiple of %d", kelems);
+  if (a_mn) rc = make_tmap_2d(ctx, &tmA, A, K, M, M, 64, 64);
+  else rc = make_tmap_2d(ctx, &tmA, A, M, K, K, kelems, 128);
+  if (rc) return rc;
+  if (b_mn) rc = make_tmap_2d(ctx, &tmB, B, K, N, N, 64, 64);
+  else rc = make_tmap_2d(ctx, &tmB, B, N, K, K, kelems, bn);
+  if (rc) return rc;
+  tc::Params p{};
+  p.M = M; p.N = N; p.num_kb = K / kelems; p.a_mode = tc::A_TILED;
+  if (splits < 1) splits = 1;
+  p.kb_per_split = ceil_div(p.num_kb, splits);
+  splits = ceil_div(p.num_kb, p.kb_per_split);
+  p.epi = tc::EPI_ROW_F32; p.out = D; p.ldo = N; p.atomic = splits > 1;
+  if (splits > 1) A3D_CHECK_CUDA(cudaMemsetAsync(D, 0, (size_t)M * N * sizeof(float), st));
+  if (!a_mn && !b_mn) return launch_kk(ctx, bn, kcb, tmA, tmB, p, splits, st);
+#define A3D_MN_CASE(BN, AM, BM_) \
+  if (bn == BN && (bool)a_mn == AM && (bool)b_mn == BM_) \
+    return launch_cfg<tc::Cfg<BN, 128, AM, BM_>>(ctx, tmA, tmB, p, splits, st);
+  A3D_MN_CASE(64, true, true) A3D_MN_CASE(128, true, true) A3D_MN_CASE(256, true, true)
+  A3D_MN_CASE(32, true, false) A3D_MN_CASE(64, true, false) A3D_MN_CASE(128, true, false)
+  A3D_MN_CASE(64, false, true) A3D_MN_CASE(128, false, true) A3D_MN_CASE(256, false, true)
+#undef A3D_MN_CASE
+  a3d_set_error("debug gemm: no kernel for BN=%d a_mn=%d b_mn=%d", bn, a_mn, b_mn);
+  return A3D_ENOTSUP;
+}

@@ -1,0 +1,261 @@
+// tc_gemm.cuh -- the tcgen05 / TMEM / TMA GEMM engine of liba3d (sm_100a only).
+//
+// One CTA computes one 128 x BN tile of  D[m][n] = sum_k A[m][k] * B[n][k]  with bf16 operands and
+// fp32 accumulation in tensor memory:
+//   warp 0     : TMA producer (one elected lane) -- tiled 2-D loads, or im2col-mode loads of an NHWC
+//                activation tensor so that the convolution never materialises its im2col matrix
+//   warp 1     : TMEM allocator + single-thread tcgen05.mma issuer
+//   warps 2..5 : epilogue -- tcgen05.ld the accumulator (32 lanes per warp), bias / ReLU / cast, store
+// Producer and issuer are decoupled by a STAGES-deep ring of shared-memory stages guarded by
+// full/empty mbarriers; the issuer hands a stage back with tcgen05.commit.
+//
+// Operand layouts in shared memory are the canonical UMMA layouts that TMA produces directly:
+//   K-major  : tile rows = M (or N) index, each row KCB bytes of K (128/64/32 -> SWIZZLE_128B/64B/32B)
+//   MN-major : tile rows = K index (64 per stage), each row 128 B = 64 consecutive M (or N) elements,
+//              one 8 KB block per 64 columns (SWIZZLE_128B)
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace tc {
+
+enum AMode : int { A_TILED = 0, A_IM2COL = 1 };
+enum Epi : int {
+  EPI_ROW_BF16 = 0,       // out_bf16[row*ldo + col] = act(acc + bias[col])
+  EPI_ROW_F32 = 1,        // out_f32 [row*ldo + col] = act(acc + bias[col])   (atomicAdd when split-K)
+  EPI_COL_F32 = 2,        // out_f32 [col*ldo + row] (+)= acc                  (transposed; dense layers)
+};
+
+struct Params {
+  int M, N;                 // valid rows of A / rows of B (GEMM M, N)
+  int num_kb;               // k-blocks in total
+  int kb_per_split;         // k-blocks handled by one blockIdx.z
+  // A operand addressing
+  int a_mode;
+  int a_k0;                 // tiled: first K coordinate
+  int PQ, Q, sh, sw, lower_h, lower_w, S, cblocks;   // im2col
+  // B operand addressing: coords (kb*KC, n0) for K-major, (n0, kb*64) for MN-major
+  // epilogue
+  int epi;
+  void* out;
+  long long ldo;
+  const float* bias;
+  unsigned flags;
+  int atomic;               // accumulate with atomicAdd (split-K)
+};
+
+template <int BN_, int KCB_, bool A_MN_, bool B_MN_>
+struct Cfg {
+  static constexpr int BM = 128;
+  static constexpr int BN = BN_;
+  static constexpr int KCB = KCB_;                       // K-major: bytes of K per row per stage
+  static constexpr bool A_MN = A_MN_, B_MN = B_MN_;
+  static constexpr int KELEMS = (A_MN_ || B_MN_) ? 64 : KCB_ / 2;   // K elements per stage
+  static constexpr int A_BYTES = A_MN_ ? 2 * 8192 : BM * KCB_;
+  static constexpr int B_BYTES = B_MN_ ? (BN_ / 64) * 8192 : BN_ * KCB_;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = BN_ <= 32 ? 32 : BN_ <= 64 ? 64 : BN_ <= 128 ? 128 : 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(!(A_MN_ || B_MN_) || KCB_ == 128, "MN-major operands use 128-byte rows");
+  static_assert(!B_MN_ || BN_ % 64 == 0, "MN-major B needs BN % 64 == 0");
+  static_assert(BN_ % 16 == 0 && BN_ >= 16 && BN_ <= 256, "UMMA N");
+};
+
+template <class C>
+__global__ void __launch_bounds__(192, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment: required by the 128-byte swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + C::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * C::BM;
+  const int n0 = blockIdx.y * C::BN;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  int kb_end = kb_begin + p.kb_per_split;
+  if (kb_end > p.num_kb) kb_end = p.num_kb;
+  const int nkb = kb_end - kb_begin;      // host guarantees nkb >= 1
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    for (int s = 0; s < C::STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int n_img = 0, h0 = 0, w0 = 0;
+      if (p.a_mode == A_IM2COL) {
+        // first output pixel of this tile -> base coordinates in input space
+        n_img = m0 / p.PQ;
+        int rem = m0 - n_img * p.PQ;
+        int p0 = rem / p.Q, q0 = rem - p0 * p.Q;
+        h0 = p.lower_h + p0 * p.sh;
+        w0 = p.lower_w + q0 * p.sw;
+      }
+      for (int i = 0; i < nkb; ++i) {
+        const int kb = kb_begin + i;
+        const int stage = i % C::STAGES;
+        const uint32_t phase = (i / C::STAGES) & 1;
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sA = smem + stage * C::STAGE_BYTES;
+        uint8_t* sB = sA + C::A_BYTES;
+        ptx::mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+        // ---- A
+        if constexpr (!C::A_MN) {
+          if (p.a_mode == A_TILED) {
+            ptx::tma_load_2d(sA, &tmA, &full_bar[stage], p.a_k0 + kb * C::KELEMS, m0);
+          } else {
+            int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+            int r = tap / p.S, s = tap - r * p.S;
+            ptx::tma_load_im2col_4d(sA, &tmA, &full_bar[stage], cb * C::KELEMS, w0, h0, n_img, (uint16_t)s,
+                                    (uint16_t)r);
+          }
+        } else {
+          // MN-major A: global [K rows][M cols]; two 64-column boxes of 64 K-rows
+          ptx::tma_load_2d(sA, &tmA, &full_bar[stage], m0, kb * 64);
+          ptx::tma_load_2d(sA + 8192, &tmA, &full_bar[stage], m0 + 64, kb * 64);
+        }
+        // ---- B
+        if constexpr (!C::B_MN) {
+          ptx::tma_load_2d(sB, &tmB, &full_bar[stage], kb * C::KELEMS, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < C::BN / 64; ++j)
+            ptx::tma_load_2d(sB + j * 8192, &tmB, &full_bar[stage], n0 + j * 64, kb * 64);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(C::BM, C::BN, C::A_MN ? 1 : 0, C::B_MN ? 1 : 0);
+      constexpr uint32_t k_layout =
+          C::KCB == 128 ? ptx::LAYOUT_SW128 : C::KCB == 64 ? ptx::LAYOUT_SW64 : ptx::LAYOUT_SW32;
+      for (int i = 0; i < nkb; ++i) {
+        const int stage = i % C::STAGES;
+        const uint32_t phase = (i / C::STAGES) & 1;
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after_sync();
+        const uint32_t sA = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
+        const uint32_t sB = sA + C::A_BYTES;
+        // K-major : SBO = 8 rows * KCB bytes, LBO unused (1) ; K step = 32 B inside the swizzled row
+        // MN-major: SBO = 1024 (next 8 K-rows), LBO = 8192 (next 64 MN elements) ; K step = 16 rows = 2048 B
+        const uint64_t a_desc = C::A_MN ? ptx::make_smem_desc(sA, 8192, 1024, ptx::LAYOUT_SW128)
+                                        : ptx::make_smem_desc(sA, 16, 8 * C::KCB, k_layout);
+        const uint64_t b_desc = C::B_MN ? ptx::make_smem_desc(sB, 8192, 1024, ptx::LAYOUT_SW128)
+                                        : ptx::make_smem_desc(sB, 16, 8 * C::KCB, k_layout);
+        constexpr uint32_t a_step = C::A_MN ? (2048 >> 4) : (32 >> 4);
+        constexpr uint32_t b_step = C::B_MN ? (2048 >> 4) : (32 >> 4);
+#pragma unroll
+        for (int k = 0; k < C::KELEMS / 16; ++k)
+          ptx::umma_bf16(tmem_base, a_desc + (uint64_t)(k * a_step), b_desc + (uint64_t)(k * b_step), idesc,
+                         (uint32_t)((i | k) != 0));
+        ptx::umma_commit(&empty_bar[stage]);       // frees the smem stage when these MMAs retire
+      }
+      ptx::umma_commit(tmem_full_bar);             // accumulator complete
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
+    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::tc_fence_after_sync();
+    const int row = m0 + quarter * 32 + lane;
+    const bool row_ok = row < p.M;
+#pragma unroll 1
+    for (int c0 = 0; c0 < C::BN; c0 += 16) {
+      const int col0 = n0 + c0;
+      if (col0 >= p.N) break;                      // warp-uniform
+      __syncwarp();                                // tcgen05.ld is .sync.aligned: reconverge first
+      uint32_t r[16];
+      ptx::tmem_ld_x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+      ptx::tmem_ld_wait();
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+      if (p.epi == EPI_COL_F32) {
+        float* o = reinterpret_cast<float*>(p.out);
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (col0 + j < p.N) {
+              float* dst = o + (long long)(col0 + j) * p.ldo + row;
+              if (p.atomic) atomicAdd(dst, v[j]); else *dst = v[j];
+            }
+          }
+        }
+      } else {
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+        }
+        if (p.flags & A3D_EPI_RELU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (row_ok && p.epi == EPI_ROW_BF16) {
+          uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + (long long)row * p.ldo + col0;
+          const bool vec = (col0 + 16 <= p.N) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
+          if (vec) {
+            uint4 q0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                  pack_bf16x2(v[6], v[7]));
+            uint4 q1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                                  pack_bf16x2(v[14], v[15]));
+            reinterpret_cast<uint4*>(o)[0] = q0;
+            reinterpret_cast<uint4*>(o)[1] = q1;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (col0 + j < p.N) o[j] = f32_to_bf16_bits(v[j]);
+          }
+        } else if (row_ok) {  // EPI_ROW_F32
+          float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0;
+          if (p.atomic) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (col0 + j < p.N) atomicAdd(o + j, v[j]);
+          } else {
+            const bool vec = (col0 + 16 <= p.N) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
+            if (vec) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (col0 + j < p.N) o[j] = v[j];
+            }
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace tc

@@ -1,0 +1,301 @@
+"""Torch-tensor front end of the liba3d C-ABI: one thin method per entry point of include/a3d.h.
+
+Tensors are only carriers of device memory (`data_ptr()`); all arithmetic happens in liba3d.so.
+Every method launches on torch's current CUDA stream, so callers can wrap a whole step in a
+`torch.cuda.graph` capture.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib as L
+from ._lib import ConvDesc
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def conv_desc(N, H, W, Cin, K, R, S, stride=1, padding="valid", ldy=None, impl=L.IMPL_AUTO):
+    """Build an `a3d_conv_desc` with TF padding rules (src/models.py conv2d call sites)."""
+    if isinstance(stride, int):
+        stride = (stride, stride)
+    sh, sw = stride
+    if isinstance(padding, str):
+        if padding.lower() == "same":
+            P, Q = -(-H // sh), -(-W // sw)
+            pt = max((P - 1) * sh + R - H, 0) // 2
+            pl = max((Q - 1) * sw + S - W, 0) // 2
+        else:
+            P, Q = (H - R) // sh + 1, (W - S) // sw + 1
+            pt = pl = 0
+    else:
+        pt, pl = padding
+        P, Q = (H + 2 * pt - R) // sh + 1, (W + 2 * pl - S) // sw + 1
+    d = ConvDesc()
+    d.N, d.H, d.W, d.C, d.K, d.R, d.S = N, H, W, Cin, K, R, S
+    d.stride_h, d.stride_w, d.pad_t, d.pad_l, d.P, d.Q = sh, sw, pt, pl, P, Q
+    d.ldy = ldy if ldy is not None else K
+    d.impl = impl
+    return d
+
+
+class Context:
+    """Owns one `a3d_ctx` (one per device / rank)."""
+
+    def __init__(self, device: int = 0):
+        if not torch.cuda.is_available():
+            raise L.A3DError("ann3depth_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = L.load()
+        self.device = device
+        torch.cuda.set_device(device)
+        h = C.c_void_p()
+        L.check(self.lib.a3d_create(device, C.byref(h)), "a3d_create")
+        self.h = h
+        self._ws = {}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.a3d_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def sm_count(self):
+        return self.lib.a3d_sm_count(self.h)
+
+    @property
+    def launches(self):
+        return int(self.lib.a3d_launch_count(self.h))
+
+    def workspace(self, key, nbytes):
+        """Persistent scratch buffers (allocated once, so steps stay CUDA-graph capturable)."""
+        nbytes = max(int(nbytes), 256)
+        t = self._ws.get(key)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{self.device}")
+            self._ws[key] = t
+        return t
+
+    # ------------------------------------------------------------------ elementwise
+    def resize_bilinear_tf1(self, src, OH, OW, dstC=None, dtype=torch.float32, out=None):
+        B, H, W, Cc = src.shape
+        dstC = dstC or Cc
+        if out is None:
+            out = torch.empty(B, OH, OW, dstC, dtype=dtype, device=src.device)
+        code = L.A3D_BF16 if out.dtype == torch.bfloat16 else L.A3D_F32
+        L.check(self.lib.a3d_resize_bilinear_tf1(self.h, _ptr(src), B, H, W, Cc, _ptr(out), OH, OW, dstC, code,
+                                                 _stream()), "resize")
+        return out
+
+    def maxpool2x2_fwd(self, x, out=None, ldy=None):
+        N, H, W, Cc = x.shape
+        ldy = ldy or Cc
+        if out is None:
+            out = torch.empty(N, H // 2, W // 2, ldy, dtype=torch.bfloat16, device=x.device)
+        L.check(self.lib.a3d_maxpool2x2_fwd(self.h, _ptr(x), N, H, W, Cc, _ptr(out), ldy, _stream()), "maxpool")
+        return out
+
+    def maxpool2x2_relu_bwd(self, x, dy, lddy=None, out=None):
+        N, H, W, Cc = x.shape
+        lddy = lddy or dy.shape[-1]
+        if out is None:
+            out = torch.empty_like(x)
+        L.check(self.lib.a3d_maxpool2x2_relu_bwd(self.h, _ptr(x), _ptr(dy), lddy, N, H, W, Cc, _ptr(out), _stream()),
+                "maxpool_bwd")
+        return out
+
+    def relu_bwd(self, y, dy, lddy=None, out=None):
+        Cc = y.shape[-1]
+        rows = y.numel() // Cc
+        lddy = lddy or dy.shape[-1]
+        if out is None:
+            out = torch.empty_like(y)
+        L.check(self.lib.a3d_relu_bwd(self.h, _ptr(y), _ptr(dy), lddy, _ptr(out), rows, Cc, _stream()), "relu_bwd")
+        return out
+
+    def dense_epilogue_bwd(self, g_post, y, keep_mask, drop_rate, flags, out=None):
+        if out is None:
+            out = torch.empty_like(g_post)
+        L.check(self.lib.a3d_dense_epilogue_bwd(self.h, _ptr(g_post), _ptr(y), _ptr(keep_mask), drop_rate, _ptr(out),
+                                                g_post.numel(), flags, _stream()), "dense_epilogue_bwd")
+        return out
+
+    def silog_loss(self, out, tar, lambda_over_n=0.5 / 4070, want_grad=True, grad_bf16=False,
+                   loss_ps=None, loss=None, dout=None, dout_bf16=None):
+        B = out.shape[0]
+        n = out.numel() // B
+        dev = out.device
+        loss_ps = loss_ps if loss_ps is not None else torch.empty(B, dtype=torch.float32, device=dev)
+        loss = loss if loss is not None else torch.empty(1, dtype=torch.float32, device=dev)
+        if want_grad and dout is None and not grad_bf16:
+            dout = torch.empty(B, n, dtype=torch.float32, device=dev)
+        if want_grad and grad_bf16 and dout_bf16 is None:
+            dout_bf16 = torch.empty(B, n, dtype=torch.bfloat16, device=dev)
+        L.check(self.lib.a3d_silog_loss(self.h, _ptr(out), _ptr(tar), B, n, lambda_over_n, _ptr(loss_ps), _ptr(loss),
+                                        _ptr(dout), _ptr(dout_bf16), _stream()), "silog_loss")
+        return loss, loss_ps, dout, dout_bf16
+
+    def adam_tf(self, w, g, m, v, w_bf16, lr, beta1, beta2, eps, t, grad_scale=1.0, n=None):
+        lr_t = lr * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
+        n = n if n is not None else w.numel()
+        L.check(self.lib.a3d_adam_tf(self.h, _ptr(w), _ptr(g), _ptr(m), _ptr(v), _ptr(w_bf16), n, lr_t, beta1, beta2,
+                                     eps, grad_scale, _stream()), "adam")
+
+    def sgd(self, w, g, w_bf16, lr, grad_scale=1.0, n=None):
+        n = n if n is not None else w.numel()
+        L.check(self.lib.a3d_sgd(self.h, _ptr(w), _ptr(g), _ptr(w_bf16), n, lr, grad_scale, _stream()), "sgd")
+
+    def cast_f32_bf16(self, src, dst=None):
+        if dst is None:
+            dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+        L.check(self.lib.a3d_cast_f32_bf16(self.h, _ptr(src), _ptr(dst), src.numel(), _stream()), "cast")
+        return dst
+
+    def scatter_channel_bf16(self, src, dst, ch):
+        ld = dst.shape[-1]
+        L.check(self.lib.a3d_scatter_channel_bf16(self.h, _ptr(src), _ptr(dst), src.numel(), ld, ch, _stream()),
+                "scatter_channel")
+
+    def fill_zero(self, t):
+        L.check(self.lib.a3d_fill_zero(self.h, _ptr(t), t.numel() * t.element_size(), _stream()), "fill_zero")
+
+    # ------------------------------------------------------------------ conv / dense
+    def conv_ws(self, d, op):
+        nbytes = self.lib.a3d_conv2d_ws_bytes(self.h, C.byref(d), op)
+        return self.workspace(("conv", op), nbytes), nbytes
+
+    def conv2d_fwd(self, d, x, w, bias, relu=False, out=None, out_dtype=torch.bfloat16):
+        if out is None:
+            out = torch.empty(d.N, d.P, d.Q, d.ldy, dtype=out_dtype, device=x.device)
+        ws, nb = self.conv_ws(d, L.OP_FWD)
+        code = L.A3D_BF16 if out.dtype == torch.bfloat16 else L.A3D_F32
+        L.check(self.lib.a3d_conv2d_fwd(self.h, C.byref(d), _ptr(x), _ptr(w), _ptr(bias), _ptr(out), code,
+                                        L.EPI_RELU if relu else 0, _ptr(ws), ws.numel(), _stream()), "conv2d_fwd")
+        return out
+
+    def conv2d_dgrad(self, d, dy, w, out=None):
+        if out is None:
+            out = torch.empty(d.N, d.H, d.W, d.C, dtype=torch.bfloat16, device=dy.device)
+        ws, nb = self.conv_ws(d, L.OP_DGRAD)
+        L.check(self.lib.a3d_conv2d_dgrad(self.h, C.byref(d), _ptr(dy), _ptr(w), _ptr(out), _ptr(ws), ws.numel(),
+                                          _stream()), "conv2d_dgrad")
+        return out
+
+    def conv2d_wgrad(self, d, x, dy, dw=None, db=None):
+        if dw is None:
+            dw = torch.empty(d.K, d.R, d.S, d.C, dtype=torch.float32, device=x.device)
+        ws, nb = self.conv_ws(d, L.OP_WGRAD)
+        L.check(self.lib.a3d_conv2d_wgrad(self.h, C.byref(d), _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), _ptr(ws),
+                                          ws.numel(), _stream()), "conv2d_wgrad")
+        return dw, db
+
+    def dense_fwd(self, x, w, bias, flags=0, keep_mask=None, drop_rate=0.0, out=None, out_dtype=torch.bfloat16,
+                  impl=L.IMPL_AUTO, ldx=None):
+        M = x.shape[0]
+        N, K = w.shape
+        ldx = ldx or x.shape[1]
+        if out is None:
+            out = torch.empty(M, N, dtype=out_dtype, device=x.device)
+        acc = self.workspace(("dense_acc", M, N), M * N * 4)
+        code = L.A3D_BF16 if out.dtype == torch.bfloat16 else L.A3D_F32
+        L.check(self.lib.a3d_dense_fwd(self.h, _ptr(x), ldx, _ptr(w), _ptr(bias), _ptr(keep_mask), drop_rate,
+                                       _ptr(out), code, _ptr(acc), M, N, K, flags, impl, _stream()), "dense_fwd")
+        return out
+
+    def dense_dgrad(self, dy, w, out=None, impl=L.IMPL_AUTO):
+        M = dy.shape[0]
+        N, K = w.shape
+        if out is None:
+            out = torch.empty(M, K, dtype=torch.bfloat16, device=dy.device)
+        acc = self.workspace(("dense_dacc", M, K), M * K * 4)
+        L.check(self.lib.a3d_dense_dgrad(self.h, _ptr(dy), _ptr(w), _ptr(out), _ptr(acc), M, N, K, impl, _stream()),
+                "dense_dgrad")
+        return out
+
+    def dense_wgrad(self, x, dy, dw=None, db=None, impl=L.IMPL_AUTO, ldx=None):
+        M, N = dy.shape
+        K = x.shape[1] if ldx is None else dw.shape[1]
+        ldx = ldx or x.shape[1]
+        if dw is None:
+            dw = torch.empty(N, K, dtype=torch.float32, device=x.device)
+        L.check(self.lib.a3d_dense_wgrad(self.h, _ptr(x), ldx, _ptr(dy), _ptr(dw), _ptr(db), M, N, K, impl, _stream()),
+                "dense_wgrad")
+        return dw, db
+
+    def debug_tc_gemm(self, A, B, M, N, K, bn, kcb=128, a_mn=False, b_mn=False, splits=1):
+        D = torch.empty(M, N, dtype=torch.float32, device=A.device)
+        L.check(self.lib.a3d_debug_tc_gemm(self.h, _ptr(A), _ptr(B), _ptr(D), M, N, K, bn, kcb, int(a_mn), int(b_mn),
+                                           splits, _stream()), "debug_tc_gemm")
+        return D
+
+    # ------------------------------------------------------------------ DCNF
+    def crf(self, z, y, r, pl, pr, grad_scale=1.0, want_dz=True, want_dr=False):
+        B, n = z.shape[0], z.shape[1]
+        n_pairs = r.shape[1]
+        dev = z.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        ystar = torch.empty(B, n, **f32)
+        nll = torch.empty(B, **f32)
+        logdet = torch.empty(B, **f32)
+        dz = torch.empty(B, n, **f32) if want_dz else None
+        dr = torch.empty(B, n_pairs, **f32) if want_dr else None
+        status = torch.empty(B, dtype=torch.int32, device=dev)
+        L.check(self.lib.a3d_crf_fwd_bwd(self.h, _ptr(z), _ptr(y), _ptr(r), _ptr(pl), _ptr(pr), B, n, n_pairs,
+                                         grad_scale, _ptr(ystar), _ptr(nll), _ptr(logdet), _ptr(dz), _ptr(dr),
+                                         _ptr(status), _stream()), "crf")
+        return dict(ystar=ystar, nll=nll, logdet=logdet, dz=dz, dr=dr, status=status)
+
+    def pairwise_features(self, images, pl, pr, gamma=1.0):
+        B, H, W, _ = images.shape
+        n_pairs = pl.numel()
+        ws = self.workspace(("pairwise", B, H, W), self.lib.a3d_pairwise_ws_bytes(B, H, W))
+        sims = torch.empty(B, n_pairs, 2, dtype=torch.float32, device=images.device)
+        L.check(self.lib.a3d_pairwise_features(self.h, _ptr(images), B, H, W, _ptr(pl), _ptr(pr), n_pairs, gamma,
+                                               _ptr(ws), _ptr(sims), _stream()), "pairwise_features")
+        return sims
+
+    def tile_means(self, depth):
+        B, H, W = depth.shape[:3]
+        n = math.ceil(H / 40) * math.ceil(W / 40)
+        y = torch.empty(B, n, dtype=torch.float32, device=depth.device)
+        L.check(self.lib.a3d_tile_means(self.h, _ptr(depth), B, H, W, _ptr(y), _stream()), "tile_means")
+        return y
+
+    def extract_patches(self, images, dstC=16):
+        B, H, W, _ = images.shape
+        n = math.ceil(H / 40) * math.ceil(W / 40)
+        out = torch.empty(B * n, 100, 100, dstC, dtype=torch.bfloat16, device=images.device)
+        L.check(self.lib.a3d_extract_patches(self.h, _ptr(images), B, H, W, _ptr(out), dstC, _stream()),
+                "extract_patches")
+        return out
+
+    # ------------------------------------------------------------------ data parallel
+    def comm_init(self, id_bytes: bytes, rank: int, nranks: int, nccl_path: str | None = None):
+        buf = C.create_string_buffer(id_bytes, 128)
+        L.check(self.lib.a3d_comm_init(self.h, nccl_path.encode() if nccl_path else None, buf, rank, nranks),
+                "comm_init")
+
+    def allreduce_sum(self, t, count=None):
+        code = L.A3D_BF16 if t.dtype == torch.bfloat16 else L.A3D_F32
+        L.check(self.lib.a3d_allreduce_sum(self.h, _ptr(t), count if count is not None else t.numel(), code,
+                                           _stream()), "allreduce")
+
+
+def comm_unique_id(nccl_path: str | None = None) -> bytes:
+    lib = L.load()
+    buf = C.create_string_buffer(128)
+    L.check(lib.a3d_comm_unique_id(nccl_path.encode() if nccl_path else None, buf), "comm_unique_id")
+    return buf.raw

@@ -1,0 +1,205 @@
+/*
+ * a3d.h -- C-ABI of liba3d.so, the B200 (sm_100a) compute library behind ann3depth_b200.
+ *
+ * The reference (shoeffner/ann3depth) has no native code: its hot path is the set of TensorFlow
+ * 1.3 ops that `src/models.py` invokes through `session.run(model_op)` (src/ann3depth.py:126-127).
+ * Each entry point below replaces one of those implicit TF kernels; the comment above each
+ * function names the reference call sites (file:line under /root/reference) it stands in for.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes.  Every data pointer is a CALLER-OWNED DEVICE pointer
+ *    (e.g. torch `tensor.data_ptr()`); the library never allocates device memory.
+ *  - Every launch takes an explicit `cudaStream_t` passed as `void*` (0 = legacy default stream).
+ *    All entry points are asynchronous and CUDA-graph capturable (no host sync, no allocation).
+ *  - Return value: 0 on success; >0 a cudaError_t; <0 an A3D_E* code.  `a3d_last_error()` returns a
+ *    thread-local message for the last failure.
+ *  - Activations are NHWC.  "bf16" pointers are `uint16_t*` holding bfloat16 bit patterns.
+ *  - Convolution kernels are stored OHWI ("packed"): W[Cout][R][S][Cin], i.e. the GEMM K index is
+ *    (r*S+s)*Cin+ci.  Dense kernels are stored [out][in].  The TF layouts of the reference
+ *    (HWIO and [in,out]) are converted at the Python boundary (ann3depth_b200/params.py).
+ *  - No CPU fallback exists: without a CUDA device every launch returns an error.
+ */
+#ifndef A3D_H_
+#define A3D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define A3D_VERSION 100
+
+/* negative error codes */
+#define A3D_EINVAL   (-1)   /* bad argument / unsupported shape */
+#define A3D_ENODEV   (-2)   /* no CUDA device / driver entry point missing */
+#define A3D_ETMAP    (-3)   /* cuTensorMapEncode* failed */
+#define A3D_ENCCL    (-4)   /* NCCL failure / libnccl not loadable */
+#define A3D_ENOTSUP  (-5)   /* configuration not supported by the selected implementation */
+
+/* element types */
+#define A3D_F32  0
+#define A3D_BF16 1
+
+/* conv / gemm implementation selector */
+#define A3D_IMPL_AUTO 0     /* tcgen05 tensor-core kernels wherever the shape allows */
+#define A3D_IMPL_SIMT 1     /* CUDA-core implicit GEMM (debug / shapes tcgen05 cannot take) */
+#define A3D_IMPL_TC   2     /* tcgen05 only: error if the shape is not supported */
+
+/* epilogue flags */
+#define A3D_EPI_RELU     1u
+#define A3D_EPI_SIGMOID  2u
+
+typedef struct a3d_ctx a3d_ctx;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int  a3d_version(void);
+const char* a3d_last_error(void);
+/* One context per device / rank.  Not thread-safe per context. */
+int  a3d_create(int device, a3d_ctx** out);
+int  a3d_destroy(a3d_ctx* ctx);
+int  a3d_sm_count(a3d_ctx* ctx);
+/* Number of kernels this context has launched since creation (bench.py's "gpu_launches"). */
+uint64_t a3d_launch_count(a3d_ctx* ctx);
+
+/* ---- tf.image.resize_images, BILINEAR, TF1 legacy mapping ---------------------------------- */
+/* Replaces: src/models.py:282-283 (MSDN preprocessing), :180-181,189-191 (DCNF).
+ * src f32 [B,H,W,C] -> dst [B,OH,OW,dstC] (channels >= C are written as zero), dst_dtype F32|BF16. */
+int a3d_resize_bilinear_tf1(a3d_ctx*, const float* src, int B, int H, int W, int C,
+                            void* dst, int OH, int OW, int dstC, int dst_dtype, void* stream);
+
+/* ---- convolution --------------------------------------------------------------------------- */
+typedef struct a3d_conv_desc {
+  int N, H, W, C;          /* input  [N,H,W,C]  (C = channels as stored, incl. padding)        */
+  int K, R, S;             /* filter [K,R,S,C]  (K = output channels)                           */
+  int stride_h, stride_w;
+  int pad_t, pad_l;        /* zero padding top/left (bottom/right implied by P,Q)               */
+  int P, Q;                /* output [N,P,Q,K]                                                  */
+  int ldy;                 /* channel stride of the output tensor (>= K; lets conv write into a
+                              wider concat buffer, src/models.py:246)                           */
+  int impl;                /* A3D_IMPL_*                                                        */
+} a3d_conv_desc;
+
+/* Scratch requirements.  op: 0 = fwd (split-K accumulator), 1 = dgrad (repacked filter + accumulator),
+ * 2 = wgrad.  A launch given less scratch than this falls back to a configuration that needs none,
+ * or fails with A3D_EINVAL where none exists. */
+#define A3D_OP_FWD   0
+#define A3D_OP_DGRAD 1
+#define A3D_OP_WGRAD 2
+size_t a3d_conv2d_ws_bytes(a3d_ctx*, const a3d_conv_desc*, int op);
+
+/* Replaces tf.layers.conv2d forward = Conv2D + BiasAdd [+ Relu]:
+ * src/models.py:211-223,241-251 (MSDN), :64-72 (DCNF).  x bf16, w bf16 OHWI, bias f32 (nullable),
+ * y bf16 [N,P,Q,ldy] (or f32 when y_dtype == A3D_F32). */
+int a3d_conv2d_fwd(a3d_ctx*, const a3d_conv_desc*, const uint16_t* x, const uint16_t* w,
+                   const float* bias, void* y, int y_dtype, unsigned flags,
+                   void* ws, size_t ws_bytes, void* stream);
+/* Replaces Conv2DBackpropInput (autodiff of the above via compute_gradients, src/models.py:314,199).
+ * dy bf16 [N,P,Q,ldy], w bf16 OHWI -> dx bf16 [N,H,W,C]. */
+int a3d_conv2d_dgrad(a3d_ctx*, const a3d_conv_desc*, const uint16_t* dy, const uint16_t* w,
+                     uint16_t* dx, void* ws, size_t ws_bytes, void* stream);
+/* Replaces Conv2DBackpropFilter + BiasAddGrad.  dw f32 OHWI, db f32 [K] (nullable).
+ * Both are OVERWRITTEN (not accumulated). */
+int a3d_conv2d_wgrad(a3d_ctx*, const a3d_conv_desc*, const uint16_t* x, const uint16_t* dy,
+                     float* dw, float* db, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- dense (tf.layers.dense) --------------------------------------------------------------- */
+/* Replaces src/models.py:228-232 (MSDN dense_0/1), :80-82,93 (DCNF).
+ * x bf16 [M,K] (row stride ldx), w bf16 [N,K] ("[out][in]"), bias f32 [N] (nullable),
+ * keep_mask u8 [M,N] (nullable; dropout keep-mask, y *= mask/(1-rate), src/models.py:230),
+ * y [M,N] bf16 or f32, acc_ws f32 [M,N] scratch (split-K accumulation). */
+int a3d_dense_fwd(a3d_ctx*, const uint16_t* x, int ldx, const uint16_t* w, const float* bias,
+                  const uint8_t* keep_mask, float drop_rate, void* y, int y_dtype, float* acc_ws,
+                  int M, int N, int K, unsigned flags, int impl, void* stream);
+/* dx[M,K] = dy[M,N] . w[N,K]   (MatMul grad wrt input).  dx bf16, acc_ws f32 [M,K]. */
+int a3d_dense_dgrad(a3d_ctx*, const uint16_t* dy, const uint16_t* w, uint16_t* dx, float* acc_ws,
+                    int M, int N, int K, int impl, void* stream);
+/* dw[N,K] = dy[M,N]^T . x[M,K] ; db[N] = sum_M dy.   dw/db f32, overwritten. */
+int a3d_dense_wgrad(a3d_ctx*, const uint16_t* x, int ldx, const uint16_t* dy, float* dw, float* db,
+                    int M, int N, int K, int impl, void* stream);
+/* Elementwise backward of the dense epilogue: g_pre = g_post * mask/(1-rate) * act'(y).
+ * y is the stored post-activation (pre-dropout) output; used between dense_1 dgrad and dense_0. */
+int a3d_dense_epilogue_bwd(a3d_ctx*, const uint16_t* g_post, const uint16_t* y, const uint8_t* keep_mask,
+                           float drop_rate, uint16_t* g_pre, size_t n, unsigned flags, void* stream);
+
+/* ---- max-pool 2x2/2 VALID (tf.layers.max_pooling2d) ---------------------------------------- */
+/* Replaces src/models.py:213,216,243 (MSDN), :65,68,73 (DCNF).  x bf16 [N,H,W,C] ->
+ * y bf16 [N,H/2,W/2,ldy] (channel stride ldy >= C). */
+int a3d_maxpool2x2_fwd(a3d_ctx*, const uint16_t* x, int N, int H, int W, int C,
+                       uint16_t* y, int ldy, void* stream);
+/* MaxPoolGrad fused with the ReluGrad of the conv that produced x (x is post-ReLU):
+ * dx[n,h,w,c] = (x > 0 && (h,w) is the first arg-max of its window) ? dy[n,h/2,w/2,c] : 0.
+ * dy has channel stride lddy. Rows/cols not covered by a window get 0. */
+int a3d_maxpool2x2_relu_bwd(a3d_ctx*, const uint16_t* x, const uint16_t* dy, int lddy,
+                            int N, int H, int W, int C, uint16_t* dx, void* stream);
+/* ReluGrad alone: dx = (y > 0) ? dy : 0 (dy channel stride lddy, y/dx dense [rows,C]). */
+int a3d_relu_bwd(a3d_ctx*, const uint16_t* y, const uint16_t* dy, int lddy, uint16_t* dx,
+                 size_t rows, int C, void* stream);
+
+/* ---- scale-invariant log loss (src/models.py:255-275) + its gradient ------------------------ */
+/* out,tar f32 [B,n]; loss_per_sample f32 [B]; loss f32 [1] (batch mean);
+ * dout (nullable) = d loss / d out, written as f32 and/or bf16 (either pointer may be null).
+ * lambda_over_n is the constant `lambd / (74*55)` of the reference. */
+int a3d_silog_loss(a3d_ctx*, const float* out, const float* tar, int B, int n, float lambda_over_n,
+                   float* loss_per_sample, float* loss, float* dout_f32, uint16_t* dout_bf16,
+                   void* stream);
+
+/* ---- optimizers (src/models.py:307-345 Adam x4, :198-200 SGD) ------------------------------- */
+/* TF1 ApplyAdam on a flat segment: m = b1*m+(1-b1)*g ; v = b2*v+(1-b2)*g^2 ;
+ * w -= lr_t*m/(sqrt(v)+eps), lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed by the caller in double.
+ * g is multiplied by grad_scale first (1/world_size after a sum-allreduce).
+ * w_bf16 (nullable) receives the bf16 copy of the updated weights. */
+int a3d_adam_tf(a3d_ctx*, float* w, const float* g, float* m, float* v, uint16_t* w_bf16, size_t n,
+                float lr_t, float beta1, float beta2, float eps, float grad_scale, void* stream);
+int a3d_sgd(a3d_ctx*, float* w, const float* g, uint16_t* w_bf16, size_t n, float lr,
+            float grad_scale, void* stream);
+/* f32 -> bf16 cast of a flat segment (weight mirror refresh). */
+int a3d_cast_f32_bf16(a3d_ctx*, const float* src, uint16_t* dst, size_t n, void* stream);
+
+/* ---- small glue kernels -------------------------------------------------------------------- */
+/* Write src f32 [rows] into channel `ch` of a bf16 NHWC buffer with channel stride ld
+ * (tf.concat of the coarse map, src/models.py:246). */
+int a3d_scatter_channel_bf16(a3d_ctx*, const float* src, uint16_t* dst, size_t rows, int ld, int ch,
+                             void* stream);
+int a3d_fill_zero(a3d_ctx*, void* p, size_t bytes, void* stream);
+
+/* ---- DCNF CRF (src/models.py:129-177) ------------------------------------------------------ */
+/* Batched closed-form CRF on the static pair graph.  For each of B graphs with n nodes and
+ * n_pairs undirected edges (pl[k], pr[k]) with weights r[b,k]:
+ *   A = I + diag(R 1) - R ;  y* = A^-1 z (MAP) ;  logdet = log det A ;  quad = z^T A^-1 z ;
+ *   energy = y^T A y - 2 z^T y + z^T z ;
+ *   nll = energy + n/2 log(pi) - logdet/2 + quad - z^T z          (stable closed form)
+ *   dz  = grad_scale * d nll / d z = grad_scale * 2 (y* - y)   ... when dz != NULL (unary gradient)
+ *   dr  = grad_scale * d nll / d r[b,k]   ... when dr != NULL (beyond-reference)
+ * status[b] = 0 ok, k+1 if pivot k of the Cholesky factorisation was not positive (outputs of
+ * that graph are then zero, never NaN).  n <= 192.  f32 arrays; pl/pr/status int32. */
+int a3d_crf_fwd_bwd(a3d_ctx*, const float* z, const float* y, const float* r, const int32_t* pl,
+                    const int32_t* pr, int B, int n, int n_pairs, float grad_scale, float* ystar,
+                    float* nll, float* logdet, float* dz, float* dr, int32_t* status, void* stream);
+
+/* Fused pairwise features (src/models.py:95-127): images f32 [B,H,W,3] (H,W multiples of 40) ->
+ * sims f32 [B,n_pairs,2] = (exp(-g*||mean-colour tile l - tile r||), exp(-g*||hist_l - hist_r||)). */
+int a3d_pairwise_features(a3d_ctx*, const float* images, int B, int H, int W, const int32_t* pl,
+                          const int32_t* pr, int n_pairs, float gamma, float* tile_feat_ws,
+                          float* sims, void* stream);
+size_t a3d_pairwise_ws_bytes(int B, int H, int W);
+/* Tile means of a 1-channel map (src/models.py:131-132): depth f32 [B,H,W] -> y f32 [B,n]. */
+int a3d_tile_means(a3d_ctx*, const float* depth, int B, int H, int W, float* y, void* stream);
+/* Gather 100x100 stride-40 SAME patches (src/models.py:50-59) as bf16 NHWC with dstC channels:
+ * images f32 [B,H,W,3] -> patches bf16 [B*rows*cols,100,100,dstC]. */
+int a3d_extract_patches(a3d_ctx*, const float* images, int B, int H, int W, uint16_t* patches,
+                        int dstC, void* stream);
+
+/* ---- data parallelism (replaces the PS/gRPC replication of src/ann3depth.py:78-92) ---------- */
+/* NCCL is dlopen()ed at first use (path = NULL -> "libnccl.so.2"). */
+int a3d_comm_unique_id(const char* nccl_path, void* id128);              /* 128-byte ncclUniqueId */
+int a3d_comm_init(a3d_ctx*, const char* nccl_path, const void* id128, int rank, int nranks);
+int a3d_comm_destroy(a3d_ctx*);
+/* In-place sum-allreduce of a flat gradient bucket on `stream`. */
+int a3d_allreduce_sum(a3d_ctx*, void* buf, size_t count, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* A3D_H_ */

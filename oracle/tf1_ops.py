@@ -30,11 +30,13 @@ def resize_bilinear_tf1(x: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor
     dt = x.dtype
 
     def axis(n_in, n_out):
-        scale = n_in / n_out
-        src = torch.arange(n_out, dtype=torch.float64) * scale
+        # TF computes the scale and the source coordinate in float32 (CalculateResizeScale,
+        # `in = dst * scale`), whatever the image dtype: mirror that so floor()/lerp agree bit-wise.
+        scale = torch.tensor(float(n_in), dtype=torch.float32) / torch.tensor(float(n_out), dtype=torch.float32)
+        src = torch.arange(n_out, dtype=torch.float32) * scale
         lo = torch.floor(src).to(torch.long)
         hi = torch.clamp(lo + 1, max=n_in - 1)
-        lerp = (src - lo.to(torch.float64)).to(dt)
+        lerp = (src - lo.to(torch.float32)).to(dt)
         return lo, hi, lerp
 
     ylo, yhi, yl = axis(h, out_h)

@@ -1,0 +1,54 @@
+"""CPU-side checks of the drop-in boundary: liba3d.so loads and exports every symbol that
+include/a3d.h declares, and the ctypes table in ann3depth_b200/_lib.py covers all of them."""
+import ctypes
+import os
+import re
+
+import pytest
+
+
+def declared_symbols(root):
+    text = open(os.path.join(root, "include", "a3d.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(a3d_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(repo_root):
+    import __graft_entry__ as g
+    g.build()
+    lib = ctypes.CDLL(os.path.join(repo_root, "ann3depth_b200", "liba3d.so"))
+    names = declared_symbols(repo_root)
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/a3d.h but not exported"
+
+
+def test_ctypes_table_matches_header(repo_root):
+    from ann3depth_b200 import _lib
+    names = set(declared_symbols(repo_root))
+    table = set(_lib.SIGNATURES) - {"a3d_debug_tc_gemm"}
+    assert names == table, (names - table, table - names)
+    lib = _lib.load()
+    assert lib.a3d_version() == 100
+
+
+def test_no_device_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    from ann3depth_b200 import _lib, ops
+    with pytest.raises(_lib.A3DError):
+        ops.Context(0)
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    assert lib.a3d_create(0, ctypes.byref(h)) != 0
+    assert b"no CUDA device" in lib.a3d_last_error() or b"CPU fallback" in lib.a3d_last_error()
+
+
+def test_product_never_imports_oracle(repo_root):
+    pkg = os.path.join(repo_root, "ann3depth_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M) or f == "selfcheck.py", f

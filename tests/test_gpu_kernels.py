@@ -1,0 +1,345 @@
+"""GPU parity tests of the individual liba3d kernels (called through the C-ABI via ctypes).
+
+Dense contractions are checked against an fp32 evaluation of the same bf16 operands (tolerance
+2e-3 relative to the output scale: fp32 accumulation-order differences only); elementwise / loss /
+optimizer / CRF kernels are checked against the CPU oracle (`oracle/`).
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from ann3depth_b200 import _lib as L
+    from ann3depth_b200 import ops
+
+from oracle import dcnf as OD
+from oracle import msdn as OM
+from oracle import tf1_ops as T
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = ops.Context(0)
+    yield c
+    torch.cuda.synchronize()
+    c.close()
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-20))
+
+
+def bf16_rand(*shape, seed=0, scale=1.0, shift=0.0):
+    g = torch.Generator().manual_seed(seed)
+    return ((torch.rand(*shape, generator=g) * 2 - 1) * scale + shift).to(torch.bfloat16).to(DEV)
+
+
+# ----------------------------------------------------------------------------- tcgen05 engine
+@pytest.mark.parametrize("bn,kcb", [(32, 128), (64, 128), (96, 128), (128, 128), (192, 128), (256, 128),
+                                    (64, 64), (128, 64), (256, 64), (32, 32), (128, 32)])
+def test_tc_gemm_kmajor(ctx, bn, kcb):
+    M, N, K = 300, bn + (16 if bn < 256 else 0) - 8, 512
+    A = bf16_rand(M, K, seed=1)
+    B = bf16_rand(N, K, seed=2)
+    D = ctx.debug_tc_gemm(A, B, M, N, K, bn, kcb)
+    ref = A.float() @ B.float().t()
+    assert rel_err(D, ref) < 2e-3
+
+
+def test_tc_gemm_kmajor_splitk_long(ctx):
+    M, N, K = 260, 128, 64 * 50          # 50 k-blocks > ring depth: exercises phase wrap-around
+    A = bf16_rand(M, K, seed=3)
+    B = bf16_rand(N, K, seed=4)
+    ref = A.float() @ B.float().t()
+    assert rel_err(ctx.debug_tc_gemm(A, B, M, N, K, 128, 128, splits=1), ref) < 2e-3
+    assert rel_err(ctx.debug_tc_gemm(A, B, M, N, K, 128, 128, splits=5), ref) < 2e-3
+
+
+@pytest.mark.parametrize("a_mn,b_mn,bn", [(True, True, 128), (True, True, 64), (True, True, 256),
+                                          (True, False, 32), (True, False, 128), (False, True, 128)])
+def test_tc_gemm_mn_major(ctx, a_mn, b_mn, bn):
+    M, N, K = 256, bn, 192
+    A = bf16_rand(M, K, seed=5)
+    B = bf16_rand(N, K, seed=6)
+    ref = A.float() @ B.float().t()
+    Ain = A.t().contiguous() if a_mn else A          # MN-major operand is stored [K][rows]
+    Bin = B.t().contiguous() if b_mn else B
+    D = ctx.debug_tc_gemm(Ain, Bin, M, N, K, bn, 128, a_mn=a_mn, b_mn=b_mn)
+    assert rel_err(D, ref) < 2e-3
+
+
+# ----------------------------------------------------------------------------- convolution
+def torch_conv_ref(x_nhwc, w_ohwi, bias, stride, pad_t, pad_l, P, Q, relu):
+    """fp32 evaluation of the same bf16 operands on the GPU."""
+    x = x_nhwc.float().permute(0, 3, 1, 2)
+    w = w_ohwi.float().permute(0, 3, 1, 2)
+    R, S = w.shape[2], w.shape[3]
+    H, W = x.shape[2], x.shape[3]
+    pb = max((P - 1) * stride + R - H - pad_t, 0)
+    pr = max((Q - 1) * stride + S - W - pad_l, 0)
+    y = F.conv2d(F.pad(x, (pad_l, pr, pad_t, pb)), w, bias, stride=stride)[:, :, :P, :Q]
+    if relu:
+        y = torch.relu(y)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+# (name, H, W, C, K, R, S, stride, padding) -- the MSDN layers (src/models.py:211-251), channel
+# counts as stored by the B200 path, plus DCNF-style VALID layers (src/models.py:64-72)
+LAYERS = [
+    ("conv2d_1", 27, 37, 96, 256, 5, 5, 1, "same"),
+    ("conv2d_2", 13, 18, 256, 384, 3, 3, 1, "same"),
+    ("conv2d_3", 13, 18, 384, 384, 3, 3, 1, "same"),
+    ("conv2d_4", 13, 18, 384, 256, 3, 3, 2, "valid"),
+    ("fine_second", 55, 74, 64, 64, 5, 5, 1, "same"),
+    ("dcnf_conv2d_1", 45, 45, 64, 256, 5, 5, 1, "valid"),
+    ("dcnf_conv2d_2", 20, 20, 256, 256, 3, 3, 1, "valid"),
+    ("c16_k32", 17, 19, 16, 32, 3, 3, 1, "same"),
+]
+SMALL_C_LAYERS = [
+    ("conv2d_0", 228, 304, 3, 96, 11, 11, 4, "valid"),
+    ("fine_first", 228, 304, 3, 63, 9, 9, 2, "valid"),
+    ("fine_third", 55, 74, 64, 1, 5, 5, 1, "same"),
+]
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("layer", LAYERS, ids=[l[0] for l in LAYERS])
+def test_conv_fwd(ctx, layer, impl):
+    name, H, W, Cc, K, R, S, stride, padding = layer
+    N = 3
+    d = ops.conv_desc(N, H, W, Cc, K, R, S, stride, padding, impl=L.IMPL_SIMT if impl == "simt" else L.IMPL_TC)
+    x = bf16_rand(N, H, W, Cc, seed=10)
+    w = bf16_rand(K, R, S, Cc, seed=11, scale=1.0 / math.sqrt(R * S * Cc))
+    bias = (torch.rand(K, generator=torch.Generator().manual_seed(12)) - 0.5).to(DEV)
+    y = ctx.conv2d_fwd(d, x, w, bias, relu=True)
+    ref = torch_conv_ref(x, w, bias, stride, d.pad_t, d.pad_l, d.P, d.Q, True)
+    assert y.shape == ref.shape
+    assert rel_err(y, ref) < 1e-2          # output is rounded to bf16 (2^-8 relative)
+    yf = ctx.conv2d_fwd(d, x, w, bias, relu=False, out_dtype=torch.float32)
+    ref = torch_conv_ref(x, w, bias, stride, d.pad_t, d.pad_l, d.P, d.Q, False)
+    assert rel_err(yf, ref) < 2e-3
+
+
+@pytest.mark.parametrize("layer", SMALL_C_LAYERS, ids=[l[0] for l in SMALL_C_LAYERS])
+def test_conv_fwd_small_channels(ctx, layer):
+    name, H, W, Cc, K, R, S, stride, padding = layer
+    N = 2
+    d = ops.conv_desc(N, H, W, Cc, K, R, S, stride, padding, impl=L.IMPL_AUTO)
+    x = bf16_rand(N, H, W, Cc, seed=13)
+    w = bf16_rand(K, R, S, Cc, seed=14, scale=1.0 / math.sqrt(R * S * Cc))
+    yf = ctx.conv2d_fwd(d, x, w, None, relu=False, out_dtype=torch.float32)
+    ref = torch_conv_ref(x, w, None, stride, d.pad_t, d.pad_l, d.P, d.Q, False)
+    assert rel_err(yf, ref) < 2e-3
+
+
+def test_conv_fwd_concat_stride(ctx):
+    """Output written into a wider NHWC buffer (ldy > K): the concat of src/models.py:246."""
+    N, H, W, Cc, K = 2, 20, 24, 32, 48
+    d = ops.conv_desc(N, H, W, Cc, K, 3, 3, 1, "same", ldy=64, impl=L.IMPL_TC)
+    x = bf16_rand(N, H, W, Cc, seed=15)
+    w = bf16_rand(K, 3, 3, Cc, seed=16, scale=0.1)
+    out = torch.full((N, H, W, 64), 7.0, dtype=torch.bfloat16, device=DEV)
+    ctx.conv2d_fwd(d, x, w, None, relu=False, out=out)
+    ref = torch_conv_ref(x, w, None, 1, d.pad_t, d.pad_l, d.P, d.Q, False)
+    assert rel_err(out[..., :K], ref) < 1e-2
+    assert float((out[..., K:] - 7.0).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("impl", ["simt", "auto"])
+@pytest.mark.parametrize("layer", LAYERS, ids=[l[0] for l in LAYERS])
+def test_conv_dgrad_wgrad(ctx, layer, impl):
+    name, H, W, Cc, K, R, S, stride, padding = layer
+    N = 2
+    d = ops.conv_desc(N, H, W, Cc, K, R, S, stride, padding, impl=L.IMPL_SIMT if impl == "simt" else L.IMPL_AUTO)
+    x = bf16_rand(N, H, W, Cc, seed=20)
+    w = bf16_rand(K, R, S, Cc, seed=21, scale=1.0 / math.sqrt(R * S * Cc))
+    dy = bf16_rand(N, d.P, d.Q, K, seed=22)
+    xr = x.float().requires_grad_(True)
+    wr = w.float().requires_grad_(True)
+    pb = max((d.P - 1) * stride + R - H - d.pad_t, 0)
+    pr = max((d.Q - 1) * stride + S - W - d.pad_l, 0)
+    yr = F.conv2d(F.pad(xr.permute(0, 3, 1, 2), (d.pad_l, pr, d.pad_t, pb)), wr.permute(0, 3, 1, 2), None,
+                  stride=stride)[:, :, :d.P, :d.Q]
+    gx, gw = torch.autograd.grad(yr, (xr, wr), dy.float().permute(0, 3, 1, 2))
+    dx = ctx.conv2d_dgrad(d, dy, w)
+    assert rel_err(dx, gx) < 1e-2
+    db = torch.empty(K, dtype=torch.float32, device=DEV)
+    dw, _ = ctx.conv2d_wgrad(d, x, dy, db=db)
+    assert rel_err(dw, gw) < 2e-3
+    assert rel_err(db, dy.float().sum((0, 1, 2))) < 2e-3
+
+
+# ----------------------------------------------------------------------------- dense
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("M,N,K", [(32, 4096, 12288), (32, 4070, 4096), (8, 128, 12544), (5, 200, 256)])
+def test_dense_fwd(ctx, impl, M, N, K):
+    x = bf16_rand(M, K, seed=30)
+    w = bf16_rand(N, K, seed=31, scale=1.0 / math.sqrt(K))
+    bias = (torch.rand(N, generator=torch.Generator().manual_seed(32)) - 0.5).to(DEV)
+    mask = (torch.rand(M, N, generator=torch.Generator().manual_seed(33)) < 0.5).to(torch.uint8).to(DEV)
+    code = L.IMPL_SIMT if impl == "simt" else L.IMPL_TC
+    y = ctx.dense_fwd(x, w, bias, flags=L.EPI_RELU, keep_mask=mask, drop_rate=0.5, out_dtype=torch.float32, impl=code)
+    ref = torch.relu(x.float() @ w.float().t() + bias) * mask.float() * 2.0
+    assert rel_err(y, ref) < 2e-3
+    y2 = ctx.dense_fwd(x, w, bias, flags=0, out_dtype=torch.float32, impl=code)
+    assert rel_err(y2, x.float() @ w.float().t() + bias) < 2e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(32, 4070, 4096), (6, 130, 200)])
+def test_dense_bwd(ctx, M, N, K):
+    x = bf16_rand(M, K, seed=34)
+    w = bf16_rand(N, K, seed=35, scale=1.0 / math.sqrt(K))
+    dy = bf16_rand(M, N, seed=36)
+    dx = ctx.dense_dgrad(dy, w)
+    assert rel_err(dx, dy.float() @ w.float()) < 1e-2
+    db = torch.empty(N, dtype=torch.float32, device=DEV)
+    dw, _ = ctx.dense_wgrad(x, dy, db=db)
+    assert rel_err(dw, dy.float().t() @ x.float()) < 2e-3
+    assert rel_err(db, dy.float().sum(0)) < 2e-3
+
+
+# ----------------------------------------------------------------------------- elementwise
+@pytest.mark.parametrize("shape,out", [((2, 480, 640, 3), (228, 304)), ((2, 55, 73, 1), (55, 74)),
+                                       ((1, 6, 8, 1), (240, 320)), ((1, 48, 64, 3), (48, 64))])
+def test_resize_vs_oracle(ctx, shape, out):
+    g = torch.Generator().manual_seed(40)
+    x = torch.rand(*shape, generator=g)
+    ref = T.resize_bilinear_tf1(x.double(), *out).float()
+    y = ctx.resize_bilinear_tf1(x.to(DEV), out[0], out[1])
+    assert float((y.cpu() - ref).abs().max()) < 1e-5
+    yb = ctx.resize_bilinear_tf1(x.to(DEV), out[0], out[1], dstC=shape[3] + 1, dtype=torch.bfloat16)
+    assert float((yb[..., :shape[3]].float().cpu() - ref).abs().max()) < 5e-3
+    assert float(yb[..., shape[3]:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("N,H,W,C", [(2, 55, 74, 96), (2, 27, 37, 256), (1, 110, 148, 64), (1, 4, 4, 8)])
+def test_maxpool_fwd_bwd(ctx, N, H, W, C):
+    x = torch.relu(bf16_rand(N, H, W, C, seed=41))
+    y = ctx.maxpool2x2_fwd(x)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    yr = F.max_pool2d(xr, 2, 2)
+    assert torch.equal(y.float(), yr.permute(0, 2, 3, 1))
+    dy = bf16_rand(N, H // 2, W // 2, C, seed=42)
+    # reference: MaxPoolGrad to the first arg-max, then ReluGrad (x > 0). Ties only occur at x == 0.
+    (gx,) = torch.autograd.grad(yr, xr, dy.float().permute(0, 3, 1, 2))
+    gx = gx.permute(0, 2, 3, 1) * (x.float() > 0)
+    dx = ctx.maxpool2x2_relu_bwd(x, dy)
+    assert torch.equal(dx.float(), gx)
+    # concat-buffer stride
+    yw = torch.zeros(N, H // 2, W // 2, C + 8, dtype=torch.bfloat16, device=DEV)
+    ctx.maxpool2x2_fwd(x, out=yw, ldy=C + 8)
+    assert torch.equal(yw[..., :C], y) and float(yw[..., C:].abs().max()) == 0.0
+
+
+def test_relu_bwd_and_dense_epilogue_bwd(ctx):
+    y = torch.relu(bf16_rand(70, 64, seed=43))
+    dy = bf16_rand(70, 64, seed=44)
+    assert torch.equal(ctx.relu_bwd(y, dy).float(), dy.float() * (y.float() > 0))
+    mask = (torch.rand(70, 64) < 0.5).to(torch.uint8).to(DEV)
+    g = ctx.dense_epilogue_bwd(dy, y, mask, 0.5, L.EPI_RELU)
+    ref = (dy.float() * 2.0 * mask.float() * (y.float() > 0)).to(torch.bfloat16)
+    assert torch.equal(g, ref)
+
+
+@pytest.mark.parametrize("quantised", [False, True])
+def test_silog_loss_vs_oracle(ctx, quantised):
+    g = torch.Generator().manual_seed(45)
+    B, n = 8, 4070
+    out = torch.rand(B, n, generator=g) * 1.4 - 0.4           # ~30 % negative -> NaN branch
+    tar = torch.rand(B, n, generator=g) * 0.95 + 0.05
+    if quantised:                                              # depth PNGs are k/255 incl. zeros
+        tar = torch.round(torch.rand(B, n, generator=g) * 255) / 255
+    o64 = out.double().requires_grad_(True)
+    ref = OM.silog_loss(o64, tar.double())
+    (gref,) = torch.autograd.grad(ref, o64)
+    loss, lps, dout, _ = ctx.silog_loss(out.to(DEV), tar.to(DEV))
+    assert abs(float(loss) - float(ref)) / abs(float(ref)) < 1e-4
+    denom = float(gref.abs().max())
+    assert float((dout.cpu().double() - gref).abs().max()) / denom < 1e-4
+    _, _, _, db = ctx.silog_loss(out.to(DEV), tar.to(DEV), grad_bf16=True)
+    assert float((db.float().cpu().double() - gref).abs().max()) / denom < 1e-2
+
+
+@pytest.mark.parametrize("beta2", [1.0, 0.999])
+def test_adam_vs_oracle(ctx, beta2):
+    g = torch.Generator().manual_seed(46)
+    n = 100003                                                 # odd: exercises the scalar tail
+    w = torch.randn(n, generator=g)
+    gr = torch.randn(n, generator=g) * 1e-2
+    m = torch.randn(n, generator=g) * 1e-3
+    v = torch.rand(n, generator=g) * 1e-4
+    wr, mr, vr = T.tf_adam_update(w.double(), gr.double() * 0.5, m.double(), v.double(), 3, 0.1, 0.9, beta2, 1e-8)
+    wd, gd, md, vd = (t.to(DEV).clone() for t in (w, gr, m, v))
+    wb = torch.empty(n, dtype=torch.bfloat16, device=DEV)
+    ctx.adam_tf(wd, gd, md, vd, wb, 0.1, 0.9, beta2, 1e-8, 3, grad_scale=0.5)
+    assert float((wd.cpu().double() - wr).abs().max()) < 1e-5
+    assert float((md.cpu().double() - mr).abs().max()) < 1e-7
+    assert float((vd.cpu().double() - vr).abs().max()) < 1e-9
+    assert torch.equal(wb, wd.to(torch.bfloat16))
+    if beta2 == 1.0:                                           # the reference's configuration: weights frozen
+        assert torch.equal(wd.cpu(), w)
+    w2 = w.to(DEV).clone()
+    ctx.sgd(w2, gd, None, 0.1)
+    assert float((w2.cpu() - (w - 0.1 * gr)).abs().max()) < 1e-6
+
+
+def test_cast_and_scatter(ctx):
+    x = torch.randn(12345, device=DEV)
+    assert torch.equal(ctx.cast_f32_bf16(x), x.to(torch.bfloat16))
+    buf = torch.zeros(10, 7, 64, dtype=torch.bfloat16, device=DEV)
+    src = torch.randn(70, device=DEV)
+    ctx.scatter_channel_bf16(src, buf, 63)
+    assert torch.equal(buf[..., 63].reshape(-1), src.to(torch.bfloat16)) and float(buf[..., :63].abs().max()) == 0
+
+
+# ----------------------------------------------------------------------------- DCNF pieces
+def test_crf_vs_oracle(ctx):
+    g = torch.Generator().manual_seed(47)
+    B, n = 16, 48
+    z = torch.rand(B, n, 1, generator=g, dtype=torch.float64)
+    y = torch.rand(B, n, 1, generator=g, dtype=torch.float64)
+    r = torch.rand(B, 48, 1, generator=g, dtype=torch.float64)
+    pl, pr = OD.pair_indices()
+    zl = z.clone().requires_grad_(True)
+    rl = r.clone().requires_grad_(True)
+    A = OD.build_A(rl)
+    nll = torch.stack([OD.nll_stable(A[i:i + 1], y[i:i + 1], zl[i:i + 1]) for i in range(B)])
+    gz, gr = torch.autograd.grad(nll.sum(), (zl, rl))
+    ystar = OD.crf_map(A.detach(), z)
+    res = ctx.crf(z.float().reshape(B, n).to(DEV), y.float().reshape(B, n).to(DEV), r.float().reshape(B, 48).to(DEV),
+                  torch.tensor(pl, dtype=torch.int32, device=DEV), torch.tensor(pr, dtype=torch.int32, device=DEV),
+                  want_dr=True)
+    assert int(res["status"].abs().max()) == 0
+    assert float((res["ystar"].cpu().double() - ystar.reshape(B, n)).abs().max()) < 1e-5      # north-star: 1e-5
+    assert float((res["nll"].cpu().double() - nll.detach()).abs().max()) < 1e-3
+    assert float((res["logdet"].cpu().double() - torch.linalg.slogdet(A.detach())[1]).abs().max()) < 1e-4
+    assert float((res["dz"].cpu().double() - gz.reshape(B, n)).abs().max()) < 1e-4
+    assert float((res["dr"].cpu().double() - gr.reshape(B, 48)).abs().max()) < 1e-4
+    # not SPD -> status, zeros instead of NaNs
+    rbad = -torch.ones(2, 48)
+    res = ctx.crf(z.float().reshape(B, n)[:2].to(DEV), y.float().reshape(B, n)[:2].to(DEV), rbad.to(DEV),
+                  torch.tensor(pl, dtype=torch.int32, device=DEV), torch.tensor(pr, dtype=torch.int32, device=DEV))
+    assert int(res["status"].min()) > 0 and bool(torch.isfinite(res["ystar"]).all())
+
+
+def test_pairwise_features_tile_means_patches(ctx):
+    g = torch.Generator().manual_seed(48)
+    im = torch.rand(2, 240, 320, 3, generator=g)
+    dp = torch.rand(2, 240, 320, 1, generator=g)
+    pl, pr = OD.pair_indices()
+    ref = OD.pairwise_features(im.double())
+    sims = ctx.pairwise_features(im.to(DEV), torch.tensor(pl, dtype=torch.int32, device=DEV),
+                                 torch.tensor(pr, dtype=torch.int32, device=DEV))
+    assert float((sims.cpu().double() - ref).abs().max()) < 1e-5
+    ym = ctx.tile_means(dp.to(DEV))
+    assert float((ym.cpu().double() - OD.tile_means(dp.double()).reshape(2, 48)).abs().max()) < 1e-6
+    pt = ctx.extract_patches(im.to(DEV), dstC=16)
+    refp = OD.patches(im).reshape(96, 100, 100, 3).to(torch.bfloat16)
+    assert torch.equal(pt[..., :3].cpu(), refp) and float(pt[..., 3:].abs().max()) == 0
