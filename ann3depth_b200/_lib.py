@@ -48,13 +48,18 @@ SIGNATURES = {
     "a3d_dense_epilogue_bwd": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _sz, _u, _vp]),
     "a3d_maxpool2x2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "a3d_maxpool2x2_relu_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "a3d_maxpool2x2_fwd_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
+    "a3d_maxpool2x2_idx_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "a3d_relu_bwd": (_i, [_vp, _vp, _vp, _i, _vp, _sz, _i, _vp]),
     "a3d_silog_loss": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
-    "a3d_adam_tf": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _vp]),
+    "a3d_adam_tf": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _vp, _vp]),
     "a3d_sgd": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _vp]),
+    "a3d_bernoulli_mask": (_i, [_vp, _vp, _sz, _f, C.c_uint64, _vp, _vp]),
+    "a3d_increment_i64": (_i, [_vp, _vp, _vp]),
     "a3d_cast_f32_bf16": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "a3d_scatter_channel_bf16": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp]),
     "a3d_fill_zero": (_i, [_vp, _vp, _sz, _vp]),
+    "a3d_apply_mask_f32": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "a3d_crf_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "a3d_pairwise_features": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _f, _vp, _vp, _vp]),
     "a3d_pairwise_ws_bytes": (_sz, [_i, _i, _i]),

@@ -297,7 +297,8 @@ extern "C" int a3d_silog_loss(a3d_ctx* ctx, const float* out, const float* tar, 
 // TF1 ApplyAdam; one pass, 128-bit loads/stores: 16 B read + 12 B written per parameter (+2 B bf16 mirror).
 __global__ void adam_tf_kernel(float4* __restrict__ w, const float4* __restrict__ g, float4* __restrict__ m,
                                float4* __restrict__ v, uint2* __restrict__ wb, size_t n4, float lr_t, float b1, float b2,
-                               float eps, float gs) {
+                               float eps, float gs, const float* __restrict__ lr_dev) {
+  if (lr_dev) lr_t = __ldg(lr_dev);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 W = w[i], G = __ldg(g + i), M = m[i], V = v[i];
     float* pw = &W.x; float* pg = &G.x; float* pm = &M.x; float* pv = &V.x;
@@ -313,7 +314,8 @@ __global__ void adam_tf_kernel(float4* __restrict__ w, const float4* __restrict_
   }
 }
 __global__ void adam_tf_tail_kernel(float* w, const float* g, float* m, float* v, uint16_t* wb, size_t start, size_t n,
-                                    float lr_t, float b1, float b2, float eps, float gs) {
+                                    float lr_t, float b1, float b2, float eps, float gs, const float* lr_dev) {
+  if (lr_dev) lr_t = __ldg(lr_dev);
   size_t i = start + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i < n) {
     float gk = g[i] * gs;
@@ -328,7 +330,8 @@ __global__ void adam_tf_tail_kernel(float* w, const float* g, float* m, float* v
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 extern "C" int a3d_adam_tf(a3d_ctx* ctx, float* w, const float* g, float* m, float* v, uint16_t* w_bf16, size_t n,
-                           float lr_t, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+                           float lr_t, float beta1, float beta2, float eps, float grad_scale, const float* lr_t_dev,
+                           void* stream) {
   A3D_REQUIRE(ctx && w && g && m && v, "adam: null argument");
   if (n == 0) return 0;
   bool vec = aligned16(w) && aligned16(g) && aligned16(m) && aligned16(v) &&
@@ -339,14 +342,14 @@ extern "C" int a3d_adam_tf(a3d_ctx* ctx, float* w, const float* g, float* m, flo
     adam_tf_kernel<<<grid, block, 0, as_stream(stream)>>>(reinterpret_cast<float4*>(w), reinterpret_cast<const float4*>(g),
                                                         reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v),
                                                         reinterpret_cast<uint2*>(w_bf16), n4, lr_t, beta1, beta2, eps,
-                                                        grad_scale);
+                                                        grad_scale, lr_t_dev);
     A3D_LAUNCH_OK(ctx);
   }
   size_t done = n4 * 4;
   if (done < n) {
     size_t rem = n - done;
     adam_tf_tail_kernel<<<ceil_div(rem, 256), 256, 0, as_stream(stream)>>>(w, g, m, v, w_bf16, done, n, lr_t, beta1, beta2,
-                                                                          eps, grad_scale);
+                                                                          eps, grad_scale, lr_t_dev);
     A3D_LAUNCH_OK(ctx);
   }
   return 0;
@@ -413,5 +416,146 @@ extern "C" int a3d_scatter_channel_bf16(a3d_ctx* ctx, const float* src, uint16_t
 extern "C" int a3d_fill_zero(a3d_ctx* ctx, void* p, size_t bytes, void* stream) {
   A3D_REQUIRE(ctx && p, "fill_zero: null argument");
   A3D_CHECK_CUDA(cudaMemsetAsync(p, 0, bytes, as_stream(stream)));
+  return 0;
+}
+
+__global__ void apply_mask_kernel(float* __restrict__ g, const uint8_t* __restrict__ keep, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    if (!keep[i]) g[i] = 0.f;
+}
+extern "C" int a3d_apply_mask_f32(a3d_ctx* ctx, float* g, const uint8_t* keep, size_t n, void* stream) {
+  A3D_REQUIRE(ctx && g && keep, "apply_mask: null argument");
+  if (n == 0) return 0;
+  int block = 256, grid = grid_for(ctx, n, block);
+  apply_mask_kernel<<<grid, block, 0, as_stream(stream)>>>(g, keep, n);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {   // splitmix64 finaliser
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__global__ void bernoulli_mask_kernel(uint8_t* __restrict__ keep, size_t n, float keep_prob, uint64_t seed,
+                                      const int64_t* __restrict__ counter) {
+  uint64_t base = mix64(seed ^ mix64((uint64_t)(counter ? *counter : 0)));
+  uint32_t thresh = (uint32_t)fminf(keep_prob * 4294967296.f, 4294967295.f);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    keep[i] = ((uint32_t)(mix64(base + i) >> 32) < thresh) ? 1 : 0;
+}
+extern "C" int a3d_bernoulli_mask(a3d_ctx* ctx, uint8_t* keep, size_t n, float keep_prob, uint64_t seed,
+                                  const int64_t* counter_dev, void* stream) {
+  A3D_REQUIRE(ctx && keep, "bernoulli_mask: null argument");
+  if (n == 0) return 0;
+  int block = 256, grid = grid_for(ctx, n, block);
+  bernoulli_mask_kernel<<<grid, block, 0, as_stream(stream)>>>(keep, n, keep_prob, seed, counter_dev);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+__global__ void increment_i64_kernel(int64_t* p) { *p += 1; }
+extern "C" int a3d_increment_i64(a3d_ctx* ctx, int64_t* p, void* stream) {
+  A3D_REQUIRE(ctx && p, "increment: null argument");
+  increment_i64_kernel<<<1, 1, 0, as_stream(stream)>>>(p);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ f32 pool + routing index
+// one thread = one output pixel x 4 channels (16 B f32 loads, 8 B bf16 store, 4 B index store)
+__global__ void maxpool2x2_fwd_f32_kernel(const float4* __restrict__ x, int N, int H, int W, int C4,
+                                          uint2* __restrict__ y, int ldy4, uint32_t* __restrict__ idx) {
+  int OH = H / 2, OW = W / 2;
+  size_t total = (size_t)N * OH * OW * C4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4);
+    size_t t = i / C4;
+    int ow = (int)(t % OW);
+    t /= OW;
+    int oh = (int)(t % OH);
+    int n = (int)(t / OH);
+    const float4* p = x + (((size_t)n * H + 2 * oh) * W + 2 * ow) * C4 + c;
+    float4 v[4] = {__ldg(p), __ldg(p + C4), __ldg(p + (size_t)W * C4), __ldg(p + (size_t)W * C4 + C4)};
+    float m[4];
+    uint32_t packed = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float best = (&v[0].x)[e];
+      int arg = 0;
+#pragma unroll
+      for (int k = 1; k < 4; ++k) {
+        float val = (&v[k].x)[e];
+        if (val > best) { best = val; arg = k; }
+      }
+      m[e] = best;
+      packed |= (uint32_t)(best > 0.f ? arg : 4) << (8 * e);
+    }
+    size_t o = ((size_t)n * OH + oh) * OW + ow;
+    y[o * ldy4 + c] = make_uint2(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]));
+    if (idx) idx[o * C4 + c] = packed;
+  }
+}
+
+extern "C" int a3d_maxpool2x2_fwd_f32(a3d_ctx* ctx, const float* x, int N, int H, int W, int C, uint16_t* y, int ldy,
+                                      uint8_t* idx, void* stream) {
+  A3D_REQUIRE(ctx && x && y, "maxpool_f32: null argument");
+  A3D_REQUIRE(C % 4 == 0 && ldy % 4 == 0 && ldy >= C && H >= 2 && W >= 2, "maxpool_f32: C and ldy must be multiples of 4");
+  size_t total = (size_t)N * (H / 2) * (W / 2) * (C / 4);
+  int block = 256, grid = grid_for(ctx, total, block);
+  maxpool2x2_fwd_f32_kernel<<<grid, block, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(x), N, H, W, C / 4,
+                                                                 reinterpret_cast<uint2*>(y), ldy / 4,
+                                                                 reinterpret_cast<uint32_t*>(idx));
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
+// one thread = one (possibly partial) 2x2 window x 4 channels
+__global__ void maxpool2x2_idx_bwd_kernel(const uint32_t* __restrict__ idx, const uint2* __restrict__ dy, int lddy4, int N,
+                                          int H, int W, int C4, uint2* __restrict__ dx) {
+  int OH = H / 2, OW = W / 2;
+  int GH = (H + 1) / 2, GW = (W + 1) / 2;
+  size_t total = (size_t)N * GH * GW * C4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4);
+    size_t t = i / C4;
+    int gw = (int)(t % GW);
+    t /= GW;
+    int gh = (int)(t % GH);
+    int n = (int)(t / GH);
+    int h0 = 2 * gh, w0 = 2 * gw;
+    bool covered = (gh < OH) && (gw < OW);
+    size_t base = (((size_t)n * H + h0) * W + w0) * C4 + c;
+    uint2 out[4] = {make_uint2(0, 0), make_uint2(0, 0), make_uint2(0, 0), make_uint2(0, 0)};
+    if (covered) {
+      size_t o = ((size_t)n * OH + gh) * OW + gw;
+      uint32_t packed = __ldg(idx + o * C4 + c);
+      uint2 g = __ldg(dy + o * lddy4 + c);
+      const uint16_t* gv = reinterpret_cast<const uint16_t*>(&g);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        uint32_t a = (packed >> (8 * e)) & 0xff;
+        if (a < 4) reinterpret_cast<uint16_t*>(&out[a])[e] = gv[e];
+      }
+    }
+    dx[base] = out[0];
+    if (w0 + 1 < W) dx[base + C4] = out[1];
+    if (h0 + 1 < H) {
+      dx[base + (size_t)W * C4] = out[2];
+      if (w0 + 1 < W) dx[base + (size_t)W * C4 + C4] = out[3];
+    }
+  }
+}
+
+extern "C" int a3d_maxpool2x2_idx_bwd(a3d_ctx* ctx, const uint8_t* idx, const uint16_t* dy, int lddy, int N, int H, int W,
+                                      int C, uint16_t* dx, void* stream) {
+  A3D_REQUIRE(ctx && idx && dy && dx, "maxpool_idx_bwd: null argument");
+  A3D_REQUIRE(C % 4 == 0 && lddy % 4 == 0 && lddy >= C, "maxpool_idx_bwd: C and lddy must be multiples of 4");
+  size_t total = (size_t)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4);
+  int block = 256, grid = grid_for(ctx, total, block);
+  maxpool2x2_idx_bwd_kernel<<<grid, block, 0, as_stream(stream)>>>(reinterpret_cast<const uint32_t*>(idx),
+                                                                 reinterpret_cast<const uint2*>(dy), lddy / 4, N, H, W,
+                                                                 C / 4, reinterpret_cast<uint2*>(dx));
+  A3D_LAUNCH_OK(ctx);
   return 0;
 }

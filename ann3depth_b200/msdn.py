@@ -1,0 +1,293 @@
+"""MSDN (Eigen et al. 2014) train / inference step on liba3d -- host-side orchestration.
+
+Mirrors `_MultiScaleDeepNetwork` of the reference (src/models.py:203-367): preprocessing resize,
+coarse stack, fine stack, two scale-invariant log losses, and the three-phase schedule with four
+TF-Adam instances.  Every arithmetic operation is a liba3d kernel launched on the current CUDA
+stream; PyTorch only owns the buffers.  The whole step is captured in a CUDA graph per phase.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+from . import ops
+from .params import Arena, msdn_specs
+
+IN_H, IN_W = 228, 304          # src/models.py:282
+OUT_H, OUT_W = 55, 74          # src/models.py:283
+N_PIX = OUT_H * OUT_W          # 4070 == the 74*55 of src/models.py:269
+LAMBDA_OVER_N = 0.5 / (74 * 55)
+
+# src/models.py:318-345 -- (learning rate) per Adam instance; beta1 = 0.9 ('momentum'), eps = 1e-8
+ADAM_LR = {"CoarseConv": 0.001, "CoarseDense": 0.1, "FineA": 0.001, "FineB": 0.01}
+ADAM_BETA1, ADAM_EPS = 0.9, 1e-8
+ADAM_BETA2_REFERENCE = 1.0     # third positional argument of AdamOptimizer, src/models.py:309
+
+
+def phase_of(global_step: int, batchsize: int) -> int:
+    """src/models.py:301-305,347-364 (batchsize is the per-replica batch, as in the reference)."""
+    steps_coarse = 2000000 // batchsize
+    steps_fine = 1500000 // batchsize
+    if global_step < steps_coarse:
+        return 1
+    if global_step < steps_coarse + steps_fine:
+        return 2
+    return 3
+
+
+class MSDNNet:
+    """Buffers + launch sequence for one replica with a static batch size (the reference requires a
+    static batch dimension too: `int(images.shape[0])`, src/models.py:225,256,299)."""
+
+    def __init__(self, ctx: ops.Context, batch: int, in_hw=(480, 640), depth_hw=(55, 73), train=True,
+                 beta2=ADAM_BETA2_REFERENCE, impl=L.IMPL_AUTO, dropout_seed=2, comm=None, grad_dtype=torch.float32):
+        self.ctx, self.B, self.train, self.beta2, self.impl = ctx, batch, train, beta2, impl
+        self.dev = torch.device(f"cuda:{ctx.device}")
+        self.in_hw, self.depth_hw = in_hw, depth_hw
+        self.comm = comm                      # data-parallel hook (ann3depth_b200.dp.DataParallel) or None
+        self.arena = Arena(msdn_specs(), self.dev)
+        self.global_step = 0
+        self.adam_t = {g: 0 for g in ADAM_LR}
+        self.dropout_seed = dropout_seed
+        B = batch
+        bf, f32 = dict(dtype=torch.bfloat16, device=self.dev), dict(dtype=torch.float32, device=self.dev)
+        z = torch.zeros
+        # ---- static input buffers (the "placeholders" the driver refills each step)
+        self.images = z(B, in_hw[0], in_hw[1], 3, **f32)
+        self.depths = z(B, depth_hw[0], depth_hw[1], 1, **f32)
+        self.keep_mask = torch.ones(B, 4096, dtype=torch.uint8, device=self.dev)
+        self.external_mask = False
+        # ---- forward activations
+        self.img = z(B, IN_H, IN_W, 4, **bf)           # resized image, channel-padded to 4 (8-byte pixels)
+        self.tar = z(B, OUT_H, OUT_W, 1, **f32)         # resized target
+        # conv outputs that feed a max-pool stay f32 and the pool records its routing (see a3d.h)
+        self.c0 = z(B, 55, 74, 96, **f32)
+        self.p0 = z(B, 27, 37, 96, **bf)
+        self.i0 = torch.zeros(B, 27, 37, 96, dtype=torch.uint8, device=self.dev)
+        self.c1 = z(B, 27, 37, 256, **f32)
+        self.p1 = z(B, 13, 18, 256, **bf)
+        self.i1 = torch.zeros(B, 13, 18, 256, dtype=torch.uint8, device=self.dev)
+        self.c2 = z(B, 13, 18, 384, **bf)
+        self.c3 = z(B, 13, 18, 384, **bf)
+        self.c4 = z(B, 6, 8, 256, **bf)
+        self.d0 = z(B, 4096, **bf)                      # relu + dropout applied
+        self.coarse = z(B, N_PIX, **f32)
+        self.f1 = z(B, 110, 148, 64, **f32)
+        self.if1 = torch.zeros(B, 55, 74, 64, dtype=torch.uint8, device=self.dev)
+        self.cat = z(B, 55, 74, 64, **bf)               # pool(f1)[...,:63] ++ coarse  (src/models.py:246)
+        self.f2 = z(B, 55, 74, 64, **bf)
+        self.fine = z(B, N_PIX, **f32)
+        self.loss_coarse, self.loss_fine = z(1, **f32), z(1, **f32)
+        self.lps_coarse, self.lps_fine = z(B, **f32), z(B, **f32)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.lr_dev = {g: z(1, **f32) for g in ADAM_LR}
+        # ---- conv descriptors (src/models.py:211-223, 241-251)
+        cd = ops.conv_desc
+        self.d_c0 = cd(B, IN_H, IN_W, 4, 96, 11, 12, 4, "valid", impl=impl)     # 11x11x3 stored 11x12x4
+        self.d_c1 = cd(B, 27, 37, 96, 256, 5, 5, 1, "same", impl=impl)
+        self.d_c2 = cd(B, 13, 18, 256, 384, 3, 3, 1, "same", impl=impl)
+        self.d_c3 = cd(B, 13, 18, 384, 384, 3, 3, 1, "same", impl=impl)
+        self.d_c4 = cd(B, 13, 18, 384, 256, 3, 3, 2, "valid", impl=impl)
+        self.d_f1 = cd(B, IN_H, IN_W, 4, 64, 9, 10, 2, "valid", impl=impl)       # 9x9x3->63 stored 9x10x4->64
+        self.d_f2 = cd(B, 55, 74, 64, 64, 5, 5, 1, "same", impl=impl)
+        self.d_f3 = cd(B, 55, 74, 64, 1, 5, 5, 1, "same", impl=impl)
+        assert (self.d_c0.P, self.d_c0.Q) == (55, 74) and (self.d_f1.P, self.d_f1.Q) == (110, 148)
+        assert (self.d_c4.P, self.d_c4.Q) == (6, 8)
+        if train:
+            self.g_coarse = z(B, N_PIX, **bf)
+            self.g_fine = z(B, N_PIX, **bf)
+            self.g_d0a, self.g_d0 = z(B, 4096, **bf), z(B, 4096, **bf)
+            self.g_c4a, self.g_c4 = z(B, 6, 8, 256, **bf), z(B, 6, 8, 256, **bf)
+            self.g_c3a, self.g_c3 = z(B, 13, 18, 384, **bf), z(B, 13, 18, 384, **bf)
+            self.g_c2a, self.g_c2 = z(B, 13, 18, 384, **bf), z(B, 13, 18, 384, **bf)
+            self.g_p1 = z(B, 13, 18, 256, **bf)
+            self.g_c1 = z(B, 27, 37, 256, **bf)
+            self.g_p0 = z(B, 27, 37, 96, **bf)
+            self.g_c0 = z(B, 55, 74, 96, **bf)
+            self.g_f2a, self.g_f2 = z(B, 55, 74, 64, **bf), z(B, 55, 74, 64, **bf)
+            self.g_cat = z(B, 55, 74, 64, **bf)
+            self.g_f1 = z(B, 110, 148, 64, **bf)
+        self._graphs = {}
+
+    # ------------------------------------------------------------------ parameters
+    def w(self, name):
+        return self.arena.view(self.arena.wb, name)
+
+    def bias(self, name):
+        return self.arena.view(self.arena.w, name + "/bias")
+
+    def gw(self, name):
+        return self.arena.view(self.arena.g, name)
+
+    def load_params(self, tf_params):
+        self.arena.load_tf(tf_params)
+
+    def export_params(self):
+        return self.arena.export_tf()
+
+    def export_grads(self):
+        return self.arena.export_tf(self.arena.g)
+
+    def set_dropout_mask(self, mask):
+        """Parity hook: use an externally supplied keep-mask [B,4096] instead of the device RNG."""
+        self.keep_mask.copy_(mask.to(torch.uint8))
+        self.external_mask = True
+
+    # ------------------------------------------------------------------ forward
+    def forward(self):
+        """src/models.py:281-290.  Reads self.images / self.depths, fills self.coarse / self.fine / losses."""
+        c, B = self.ctx, self.B
+        K = "/kernel"
+        c.resize_bilinear_tf1(self.images, IN_H, IN_W, out=self.img)
+        c.resize_bilinear_tf1(self.depths, OUT_H, OUT_W, out=self.tar)
+        # coarse (src/models.py:208-236)
+        n = "coarse/conv/conv2d_"
+        c.conv2d_fwd(self.d_c0, self.img, self.w(n + "0" + K), self.bias(n + "0"), relu=True, out=self.c0)
+        c.maxpool2x2_fwd_f32(self.c0, out=self.p0, idx=self.i0)
+        c.conv2d_fwd(self.d_c1, self.p0, self.w(n + "1" + K), self.bias(n + "1"), relu=True, out=self.c1)
+        c.maxpool2x2_fwd_f32(self.c1, out=self.p1, idx=self.i1)
+        c.conv2d_fwd(self.d_c2, self.p1, self.w(n + "2" + K), self.bias(n + "2"), relu=True, out=self.c2)
+        c.conv2d_fwd(self.d_c3, self.c2, self.w(n + "3" + K), self.bias(n + "3"), relu=True, out=self.c3)
+        c.conv2d_fwd(self.d_c4, self.c3, self.w(n + "4" + K), self.bias(n + "4"), relu=True, out=self.c4)
+        mask = None
+        if self.train:
+            if not self.external_mask:
+                c.bernoulli_mask(self.keep_mask, 0.5, self.dropout_seed, self.step_dev)
+            mask = self.keep_mask
+        n = "coarse/dense/dense_"
+        c.dense_fwd(self.c4.view(B, 12288), self.w(n + "0" + K), self.bias(n + "0"), flags=L.EPI_RELU, keep_mask=mask,
+                    drop_rate=0.5, out=self.d0, impl=self.impl)
+        c.dense_fwd(self.d0, self.w(n + "1" + K), self.bias(n + "1"), flags=0, out=self.coarse, impl=self.impl)
+        # fine (src/models.py:238-253)
+        c.conv2d_fwd(self.d_f1, self.img, self.w("fine/first/conv2d" + K), self.bias("fine/first/conv2d"), relu=True,
+                     out=self.f1)
+        c.maxpool2x2_fwd_f32(self.f1, out=self.cat, ldy=64, idx=self.if1)
+        c.scatter_channel_bf16(self.coarse, self.cat, 63)
+        c.conv2d_fwd(self.d_f2, self.cat, self.w("fine/second/conv2d" + K), self.bias("fine/second/conv2d"), relu=True,
+                     out=self.f2)
+        c.conv2d_fwd(self.d_f3, self.f2, self.w("fine/third" + K), self.bias("fine/third"), relu=False,
+                     out=self.fine.view(B, 55, 74, 1))
+        # losses (src/models.py:288-290); the gradient of the active branch is produced in the same pass
+        c.silog_loss(self.coarse, self.tar, LAMBDA_OVER_N, want_grad=False, loss_ps=self.lps_coarse,
+                     loss=self.loss_coarse, dout_bf16=self.g_coarse if self.train else None)
+        c.silog_loss(self.fine, self.tar, LAMBDA_OVER_N, want_grad=False, loss_ps=self.lps_fine, loss=self.loss_fine,
+                     dout_bf16=self.g_fine if self.train else None)
+
+    # ------------------------------------------------------------------ backward
+    def backward_coarse(self):
+        """d loss_coarse / d coarse variables (compute_gradients of src/models.py:319-324)."""
+        c, B, K = self.ctx, self.B, "/kernel"
+        hook = self.comm.bucket_ready if self.comm else (lambda *_: None)
+        n = "coarse/dense/dense_"
+        c.dense_wgrad(self.d0, self.g_coarse, dw=self.gw(n + "1" + K), db=self.gw(n + "1/bias"), impl=self.impl)
+        hook(self, "dense_1")
+        c.dense_dgrad(self.g_coarse, self.w(n + "1" + K), out=self.g_d0a, impl=self.impl)
+        # dropout grad (mask * 1/(1-rate)) and relu grad (d0 > 0) in one pass
+        c.dense_epilogue_bwd(self.g_d0a, self.d0, self.keep_mask, 0.5, L.EPI_RELU, out=self.g_d0)
+        c.dense_wgrad(self.c4.view(B, 12288), self.g_d0, dw=self.gw(n + "0" + K), db=self.gw(n + "0/bias"),
+                      impl=self.impl)
+        hook(self, "dense_0")
+        c.dense_dgrad(self.g_d0, self.w(n + "0" + K), out=self.g_c4a.view(B, 12288), impl=self.impl)
+        c.relu_bwd(self.c4, self.g_c4a, out=self.g_c4)
+        n = "coarse/conv/conv2d_"
+        c.conv2d_wgrad(self.d_c4, self.c3, self.g_c4, dw=self.gw(n + "4" + K), db=self.gw(n + "4/bias"))
+        c.conv2d_dgrad(self.d_c4, self.g_c4, self.w(n + "4" + K), out=self.g_c3a)
+        c.relu_bwd(self.c3, self.g_c3a, out=self.g_c3)
+        c.conv2d_wgrad(self.d_c3, self.c2, self.g_c3, dw=self.gw(n + "3" + K), db=self.gw(n + "3/bias"))
+        c.conv2d_dgrad(self.d_c3, self.g_c3, self.w(n + "3" + K), out=self.g_c2a)
+        c.relu_bwd(self.c2, self.g_c2a, out=self.g_c2)
+        c.conv2d_wgrad(self.d_c2, self.p1, self.g_c2, dw=self.gw(n + "2" + K), db=self.gw(n + "2/bias"))
+        c.conv2d_dgrad(self.d_c2, self.g_c2, self.w(n + "2" + K), out=self.g_p1)
+        c.maxpool2x2_idx_bwd(self.i1, self.g_p1, (self.B, 27, 37, 256), out=self.g_c1)
+        c.conv2d_wgrad(self.d_c1, self.p0, self.g_c1, dw=self.gw(n + "1" + K), db=self.gw(n + "1/bias"))
+        c.conv2d_dgrad(self.d_c1, self.g_c1, self.w(n + "1" + K), out=self.g_p0)
+        c.maxpool2x2_idx_bwd(self.i0, self.g_p0, (self.B, 55, 74, 96), out=self.g_c0)
+        c.conv2d_wgrad(self.d_c0, self.img, self.g_c0, dw=self.gw(n + "0" + K), db=self.gw(n + "0/bias"))
+        self._mask_padding("coarse/conv/conv2d_0/kernel")
+        hook(self, "coarse_conv")
+
+    def backward_fine(self):
+        """d loss_fine / d fine variables (src/models.py:334-338); the coarse map is a constant input."""
+        c, K = self.ctx, "/kernel"
+        hook = self.comm.bucket_ready if self.comm else (lambda *_: None)
+        c.conv2d_wgrad(self.d_f3, self.f2, self.g_fine.view(self.B, 55, 74, 1), dw=self.gw("fine/third" + K),
+                       db=self.gw("fine/third/bias"))
+        c.conv2d_dgrad(self.d_f3, self.g_fine.view(self.B, 55, 74, 1), self.w("fine/third" + K), out=self.g_f2a)
+        c.relu_bwd(self.f2, self.g_f2a, out=self.g_f2)
+        c.conv2d_wgrad(self.d_f2, self.cat, self.g_f2, dw=self.gw("fine/second/conv2d" + K),
+                       db=self.gw("fine/second/conv2d/bias"))
+        c.conv2d_dgrad(self.d_f2, self.g_f2, self.w("fine/second/conv2d" + K), out=self.g_cat)
+        c.maxpool2x2_idx_bwd(self.if1, self.g_cat, (self.B, 110, 148, 64), lddy=64, out=self.g_f1)
+        c.conv2d_wgrad(self.d_f1, self.img, self.g_f1, dw=self.gw("fine/first/conv2d" + K),
+                       db=self.gw("fine/first/conv2d/bias"))
+        self._mask_padding("fine/first/conv2d/kernel")
+        self._mask_padding("fine/first/conv2d/bias")
+        hook(self, "fine")
+
+    def _mask_padding(self, name):
+        m = self.arena.masks.get(name)
+        if m is not None:
+            s = self.arena.specs[name]
+            self.ctx.apply_mask_f32(self.arena.g[s.offset:s.offset + s.numel], m)
+
+    # ------------------------------------------------------------------ optimizer
+    def apply_adam(self, groups, grad_scale=1.0):
+        """apply_gradients of the two Adam instances of the active branch (src/models.py:326-331,340-345)."""
+        a = self.arena
+        for g in groups:
+            lo, hi = a.group_range(g)
+            self.ctx.adam_tf(a.w[lo:hi], a.g[lo:hi], a.m[lo:hi], a.v[lo:hi], a.wb[lo:hi], ADAM_LR[g], ADAM_BETA1,
+                             self.beta2, ADAM_EPS, max(self.adam_t[g], 1), grad_scale, lr_t_dev=self.lr_dev[g])
+
+    # ------------------------------------------------------------------ one session.run(model_op)
+    def _enqueue_step(self, phase):
+        self.forward()
+        if phase == 1:
+            self.backward_coarse()
+            groups = ("CoarseDense", "CoarseConv")
+        elif phase == 2:
+            self.backward_fine()
+            groups = ("FineA", "FineB")
+        else:
+            groups = ()
+        if groups:
+            scale = 1.0
+            if self.comm:
+                self.comm.wait_all(self)
+                scale = 1.0 / self.comm.world
+            self.apply_adam(groups, scale)
+        self.ctx.increment_i64(self.step_dev)            # global_step += 1 (src/models.py:329,343,356)
+
+    def train_step(self, use_graph=True):
+        """One `session.run(model_op)` of the reference loop (src/ann3depth.py:126-127)."""
+        assert self.train
+        phase = phase_of(self.global_step, self.B)
+        groups = {1: ("CoarseDense", "CoarseConv"), 2: ("FineA", "FineB"), 3: ()}[phase]
+        for g in groups:                                   # each Adam instance owns its beta-power state
+            self.adam_t[g] += 1
+            self.lr_dev[g].fill_(ops.adam_lr_t(ADAM_LR[g], ADAM_BETA1, self.beta2, self.adam_t[g]))
+        if use_graph:
+            gr = self._graphs.get(phase)
+            if gr is None:
+                # warm-up launch outside capture (sets func attributes, allocates workspaces), then capture
+                saved = (self.arena.w.clone(), self.arena.m.clone(), self.arena.v.clone(), self.arena.wb.clone(),
+                         self.step_dev.clone())
+                self._enqueue_step(phase)
+                torch.cuda.synchronize()
+                self.arena.w.copy_(saved[0]); self.arena.m.copy_(saved[1]); self.arena.v.copy_(saved[2])
+                self.arena.wb.copy_(saved[3]); self.step_dev.copy_(saved[4])
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    self._enqueue_step(phase)
+                self._graphs[phase] = gr
+                # the capture itself does not execute; fall through to the replay below
+            gr.replay()
+        else:
+            self._enqueue_step(phase)
+        self.global_step += 1
+        return phase
+
+    def infer(self):
+        """Inference = coarse + fine with train=False (dropout off), src/models.py:230,278,286."""
+        self.forward()
+        return self.fine.view(self.B, OUT_H, OUT_W, 1)

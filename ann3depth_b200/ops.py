@@ -23,6 +23,11 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def adam_lr_t(lr, beta1, beta2, t):
+    """lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t)  (TF1 AdamOptimizer; t >= 1)."""
+    return lr * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
+
+
 def conv_desc(N, H, W, Cin, K, R, S, stride=1, padding="valid", ldy=None, impl=L.IMPL_AUTO):
     """Build an `a3d_conv_desc` with TF padding rules (src/models.py conv2d call sites)."""
     if isinstance(stride, int):
@@ -92,9 +97,9 @@ class Context:
     # ------------------------------------------------------------------ elementwise
     def resize_bilinear_tf1(self, src, OH, OW, dstC=None, dtype=torch.float32, out=None):
         B, H, W, Cc = src.shape
-        dstC = dstC or Cc
         if out is None:
-            out = torch.empty(B, OH, OW, dstC, dtype=dtype, device=src.device)
+            out = torch.empty(B, OH, OW, dstC or Cc, dtype=dtype, device=src.device)
+        dstC = out.shape[-1]
         code = L.A3D_BF16 if out.dtype == torch.bfloat16 else L.A3D_F32
         L.check(self.lib.a3d_resize_bilinear_tf1(self.h, _ptr(src), B, H, W, Cc, _ptr(out), OH, OW, dstC, code,
                                                  _stream()), "resize")
@@ -115,6 +120,24 @@ class Context:
             out = torch.empty_like(x)
         L.check(self.lib.a3d_maxpool2x2_relu_bwd(self.h, _ptr(x), _ptr(dy), lddy, N, H, W, Cc, _ptr(out), _stream()),
                 "maxpool_bwd")
+        return out
+
+    def maxpool2x2_fwd_f32(self, x, out=None, ldy=None, idx=None):
+        N, H, W, Cc = x.shape
+        ldy = ldy or (out.shape[-1] if out is not None else Cc)
+        if out is None:
+            out = torch.empty(N, H // 2, W // 2, ldy, dtype=torch.bfloat16, device=x.device)
+        L.check(self.lib.a3d_maxpool2x2_fwd_f32(self.h, _ptr(x), N, H, W, Cc, _ptr(out), ldy, _ptr(idx), _stream()),
+                "maxpool_f32")
+        return out
+
+    def maxpool2x2_idx_bwd(self, idx, dy, shape, lddy=None, out=None):
+        N, H, W, Cc = shape
+        lddy = lddy or dy.shape[-1]
+        if out is None:
+            out = torch.empty(N, H, W, Cc, dtype=torch.bfloat16, device=dy.device)
+        L.check(self.lib.a3d_maxpool2x2_idx_bwd(self.h, _ptr(idx), _ptr(dy), lddy, N, H, W, Cc, _ptr(out), _stream()),
+                "maxpool_idx_bwd")
         return out
 
     def relu_bwd(self, y, dy, lddy=None, out=None):
@@ -148,15 +171,23 @@ class Context:
                                         _ptr(dout), _ptr(dout_bf16), _stream()), "silog_loss")
         return loss, loss_ps, dout, dout_bf16
 
-    def adam_tf(self, w, g, m, v, w_bf16, lr, beta1, beta2, eps, t, grad_scale=1.0, n=None):
-        lr_t = lr * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
+    def adam_tf(self, w, g, m, v, w_bf16, lr, beta1, beta2, eps, t, grad_scale=1.0, n=None, lr_t_dev=None):
+        """TF1 ApplyAdam.  `lr_t_dev` (1-element f32 device tensor) overrides the host-computed lr_t."""
+        lr_t = adam_lr_t(lr, beta1, beta2, t)
         n = n if n is not None else w.numel()
         L.check(self.lib.a3d_adam_tf(self.h, _ptr(w), _ptr(g), _ptr(m), _ptr(v), _ptr(w_bf16), n, lr_t, beta1, beta2,
-                                     eps, grad_scale, _stream()), "adam")
+                                     eps, grad_scale, _ptr(lr_t_dev), _stream()), "adam")
 
     def sgd(self, w, g, w_bf16, lr, grad_scale=1.0, n=None):
         n = n if n is not None else w.numel()
         L.check(self.lib.a3d_sgd(self.h, _ptr(w), _ptr(g), _ptr(w_bf16), n, lr, grad_scale, _stream()), "sgd")
+
+    def bernoulli_mask(self, keep, keep_prob, seed, counter_dev=None):
+        L.check(self.lib.a3d_bernoulli_mask(self.h, _ptr(keep), keep.numel(), keep_prob, seed, _ptr(counter_dev),
+                                            _stream()), "bernoulli_mask")
+
+    def increment_i64(self, p):
+        L.check(self.lib.a3d_increment_i64(self.h, _ptr(p), _stream()), "increment")
 
     def cast_f32_bf16(self, src, dst=None):
         if dst is None:
@@ -171,6 +202,10 @@ class Context:
 
     def fill_zero(self, t):
         L.check(self.lib.a3d_fill_zero(self.h, _ptr(t), t.numel() * t.element_size(), _stream()), "fill_zero")
+
+    def apply_mask_f32(self, g, keep, n=None):
+        L.check(self.lib.a3d_apply_mask_f32(self.h, _ptr(g), _ptr(keep), n if n is not None else g.numel(), _stream()),
+                "apply_mask")
 
     # ------------------------------------------------------------------ conv / dense
     def conv_ws(self, d, op):

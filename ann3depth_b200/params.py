@@ -1,0 +1,176 @@
+"""Parameter layouts: conversion between the reference's TensorFlow variable layouts and the packed
+layouts liba3d computes on, and the flat parameter arena (weights / grads / Adam slots / bf16 mirror).
+
+TF side (src/models.py): conv kernels HWIO `[kh, kw, in, out]`, dense kernels `[in, out]`,
+variable names `<scope>/kernel`, `<scope>/bias`.
+Packed side: conv kernels OHWI `[out][kh][kw'][in']`, dense kernels `[out][in]`; kw'/in'/out may be
+zero-padded so the first (3-channel) layers map onto 16-byte pixels groups.
+The arena orders variables in BACKWARD order inside each optimizer group, so gradient buckets
+become ready front-to-back during the backward pass and each Adam group is one contiguous range.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from dataclasses import dataclass
+
+import torch
+
+
+@dataclass
+class VarSpec:
+    name: str            # TF variable name
+    tf_shape: tuple
+    packed_shape: tuple
+    kind: str            # 'conv_kernel' | 'dense_kernel' | 'bias'
+    group: str           # optimizer group
+    offset: int = 0      # element offset in the arena
+    size: int = 0        # padded element count (multiple of 8)
+
+    @property
+    def numel(self):
+        n = 1
+        for s in self.packed_shape:
+            n *= s
+        return n
+
+
+def pack(spec: VarSpec, t: torch.Tensor) -> torch.Tensor:
+    """TF layout -> packed layout (zero padding where the packed shape is larger)."""
+    if spec.kind == "conv_kernel":
+        kh, kw, ci, co = spec.tf_shape
+        K, R, S, Cp = spec.packed_shape
+        out = torch.zeros(spec.packed_shape, dtype=t.dtype)
+        out[:co, :kh, :kw, :ci] = t.permute(3, 0, 1, 2)
+        return out
+    if spec.kind == "dense_kernel":
+        return t.t().contiguous()
+    out = torch.zeros(spec.packed_shape, dtype=t.dtype)
+    out[:t.numel()] = t
+    return out
+
+
+def unpack(spec: VarSpec, p: torch.Tensor) -> torch.Tensor:
+    """packed layout -> TF layout."""
+    p = p.reshape(spec.packed_shape)
+    if spec.kind == "conv_kernel":
+        kh, kw, ci, co = spec.tf_shape
+        return p[:co, :kh, :kw, :ci].permute(1, 2, 3, 0).contiguous()
+    if spec.kind == "dense_kernel":
+        return p.t().contiguous()
+    return p[:spec.tf_shape[0]].contiguous()
+
+
+def keep_mask(spec: VarSpec) -> torch.Tensor | None:
+    """uint8 mask of the real (non-padding) entries of a packed variable, or None if unpadded."""
+    ones = torch.ones(spec.tf_shape, dtype=torch.uint8)
+    m = pack(spec, ones)
+    return None if bool(m.all()) else m
+
+
+def _conv(name, tf_shape, packed, group):
+    return [VarSpec(name + "/kernel", tf_shape, packed, "conv_kernel", group),
+            VarSpec(name + "/bias", (tf_shape[-1],), (packed[0],), "bias", group)]
+
+
+def _dense(name, n_in, n_out, group):
+    return [VarSpec(name + "/kernel", (n_in, n_out), (n_out, n_in), "dense_kernel", group),
+            VarSpec(name + "/bias", (n_out,), (n_out,), "bias", group)]
+
+
+def msdn_specs():
+    """MSDN variables (src/models.py:208-251) in arena order."""
+    v = []
+    # CoarseDense (lr 0.1, src/models.py:322-324), backward order
+    v += _dense("coarse/dense/dense_1", 4096, 4070, "CoarseDense")
+    v += _dense("coarse/dense/dense_0", 12288, 4096, "CoarseDense")
+    # CoarseConv (lr 1e-3, :319-321)
+    v += _conv("coarse/conv/conv2d_4", (3, 3, 384, 256), (256, 3, 3, 384), "CoarseConv")
+    v += _conv("coarse/conv/conv2d_3", (3, 3, 384, 384), (384, 3, 3, 384), "CoarseConv")
+    v += _conv("coarse/conv/conv2d_2", (3, 3, 256, 384), (384, 3, 3, 256), "CoarseConv")
+    v += _conv("coarse/conv/conv2d_1", (5, 5, 96, 256), (256, 5, 5, 96), "CoarseConv")
+    # 11x11x3 stored as 11x12x4: four 4-channel pixels = one 32-byte group for the stride-4 layer
+    v += _conv("coarse/conv/conv2d_0", (11, 11, 3, 96), (96, 11, 12, 4), "CoarseConv")
+    # FineA (lr 1e-3, :334-336): fine/third, fine/first
+    v += _conv("fine/third", (5, 5, 64, 1), (1, 5, 5, 64), "FineA")
+    # 9x9x3 -> 63 stored as 9x10x4 -> 64: two 4-channel pixels = one 16-byte group for the stride-2 layer
+    v += _conv("fine/first/conv2d", (9, 9, 3, 63), (64, 9, 10, 4), "FineA")
+    # FineB (lr 0.01, :337-338)
+    v += _conv("fine/second/conv2d", (5, 5, 64, 64), (64, 5, 5, 64), "FineB")
+    return v
+
+
+def dcnf_specs():
+    """DCNF variables (src/models.py:61-93); one SGD group (src/models.py:198)."""
+    v = []
+    g = "SGD"
+    v += _dense("unary/unary_layers/dense_2", 16, 1, g)
+    v += _dense("unary/unary_layers/dense_1", 128, 16, g)
+    v += _dense("unary/unary_layers/dense", 12544, 128, g)
+    v += _conv("unary/unary_layers/conv2d_4", (3, 3, 256, 256), (256, 3, 3, 256), g)
+    v += _conv("unary/unary_layers/conv2d_3", (3, 3, 256, 256), (256, 3, 3, 256), g)
+    v += _conv("unary/unary_layers/conv2d_2", (3, 3, 256, 256), (256, 3, 3, 256), g)
+    v += _conv("unary/unary_layers/conv2d_1", (5, 5, 64, 256), (256, 5, 5, 64), g)
+    v += _conv("unary/unary_layers/conv2d", (11, 11, 3, 64), (64, 11, 11, 16), g)
+    v += _dense("pairwise/pairwise_layers/dense", 2, 1, "Pairwise")
+    return v
+
+
+class Arena:
+    """Flat device buffers holding every variable: f32 master `w`, f32 grads `g`, Adam slots `m`,`v`,
+    and the bf16 mirror `wb` the kernels read.  Segment starts are multiples of 8 elements, so both
+    the f32 and the bf16 views of a segment are 16-byte aligned (TMA base alignment)."""
+
+    def __init__(self, specs, device, with_adam=True):
+        off = 0
+        self.specs = OrderedDict()
+        self.groups = OrderedDict()
+        for s in specs:
+            s.offset = off
+            s.size = (s.numel + 7) // 8 * 8
+            off += s.size
+            self.specs[s.name] = s
+            lo, hi = self.groups.get(s.group, (s.offset, s.offset))
+            self.groups[s.group] = (min(lo, s.offset), s.offset + s.size)
+        self.total = off
+        f32 = dict(dtype=torch.float32, device=device)
+        self.w = torch.zeros(off, **f32)
+        self.g = torch.zeros(off, **f32)
+        self.m = torch.zeros(off, **f32) if with_adam else None
+        self.v = torch.zeros(off, **f32) if with_adam else None
+        self.wb = torch.zeros(off, dtype=torch.bfloat16, device=device)
+        self.masks = {}
+        for s in specs:
+            km = keep_mask(s)
+            if km is not None:
+                self.masks[s.name] = km.reshape(-1).to(device)
+
+    def view(self, buf, name):
+        s = self.specs[name]
+        return buf[s.offset:s.offset + s.numel].view(s.packed_shape)
+
+    def group_range(self, group):
+        return self.groups[group]
+
+    def num_real_params(self):
+        tot = 0
+        for s in self.specs.values():
+            n = 1
+            for d in s.tf_shape:
+                n *= d
+            tot += n
+        return tot
+
+    def load_tf(self, tf_params: dict):
+        """Copy TF-layout tensors (any float dtype, CPU or GPU) into the arena and refresh the mirror."""
+        for name, s in self.specs.items():
+            t = tf_params[name].detach().to("cpu", torch.float32)
+            assert tuple(t.shape) == tuple(s.tf_shape), (name, t.shape, s.tf_shape)
+            self.view(self.w, name).copy_(pack(s, t))
+        self.wb.copy_(self.w)       # load-time only; the step itself refreshes the mirror in liba3d
+
+    def export_tf(self, buf=None):
+        buf = self.w if buf is None else buf
+        out = OrderedDict()
+        for name, s in self.specs.items():
+            out[name] = unpack(s, self.view(buf, name).detach().cpu())
+        return out

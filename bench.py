@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- MSDN train images/s (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (liba3d, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...   # restated reference on the host CPU cores
+
+A "step" is one `session.run(model_op)` of the reference loop (src/ann3depth.py:126-127) at the
+default schedule position (phase 1, src/models.py:301-305): forward of the coarse and fine stacks on
+a batch of 32 synthetic 640x480 RGB images (+55x73 depth targets), both scale-invariant losses,
+backward through the coarse stack and the two TF-Adam groups.  For N > 1 the driver launches one
+rank per GPU with torch.distributed.run; every rank holds a replica and its own batch of 32 (weak
+scaling), gradients are sum-allreduced with NCCL.  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 32
+FLOP_PER_IMAGE_PHASE1 = 9.357e9          # BASELINE.md section 4 (2*MAC, unpadded dims)
+H2D_BYTES = BATCH * (480 * 640 * 3 + 55 * 73) * 4
+D2H_BYTES = 8
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons (NVML) during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def synthetic_batch(rank, torch):
+    g = torch.Generator().manual_seed(100 + rank)
+    images = torch.rand(BATCH, 480, 640, 3, generator=g)
+    depths = torch.rand(BATCH, 55, 73, 1, generator=g) * 0.95 + 0.05
+    return images, depths
+
+
+# --------------------------------------------------------------------------------------- CPU arm
+def cpu_train_step_rate(steps, warmup, budget_s=150.0):
+    """Times the CPU restatement of the reference step (oracle/, float32, all host threads).
+    Returns (images_per_s, cores, sample description, ms_per_step)."""
+    import torch
+    from oracle import msdn as OM
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    p = OM.init_params(1, torch.float32)
+    images, depths = synthetic_batch(0, torch)
+    mask = (torch.rand(BATCH, 4096, generator=torch.Generator().manual_seed(2)) < 0.5).float()
+
+    def run(b):
+        st = OM.TrainState(p)
+        t0 = time.perf_counter()
+        OM.train_step(st, images[:b], depths[:b], mask[:b])
+        return time.perf_counter() - t0
+
+    run(2)                                    # page-in / oneDNN primitive cache
+    per_img = run(4) / 4
+    b = BATCH
+    while b > 4 and (steps + warmup) * b * per_img > budget_s:
+        b //= 2
+    for _ in range(warmup):
+        run(b)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run(b)
+    dt = time.perf_counter() - t0
+    sample = (f"{steps} phase-1 train steps of {b} images each (of the 32-image batch), float32 PyTorch-CPU "
+              f"restatement of src/models.py (TensorFlow 1.3 is not installable here), {cores} threads")
+    return steps * b / dt, cores, sample, dt / steps * 1e3
+
+
+def reference_arm(args, rank):
+    if rank != 0:
+        return
+    v, cores, sample, ms = cpu_train_step_rate(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": "MSDN train images/s (bs32/GPU, phase-1 step)", "value": v,
+            "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "msdn phase-1 train step, batch 32, 640x480 RGB -> 55x73 depth"},
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------- GPU arm
+def per_op_profile(op, torch, reps=3):
+    """Times every liba3d call of one (non-graph) step with CUDA events on the launching stream."""
+    ctx = op.net.ctx
+    records = []
+    lib = ctx.lib
+    from ann3depth_b200 import _lib as L
+    wrapped = {}
+    stream = torch.cuda.current_stream()
+    for name in L.SIGNATURES:
+        fn = getattr(lib, name)
+        if name in ("a3d_last_error", "a3d_version", "a3d_launch_count", "a3d_sm_count", "a3d_conv2d_ws_bytes",
+                    "a3d_pairwise_ws_bytes", "a3d_create", "a3d_destroy"):
+            continue
+
+        def make(fn, name):
+            def w(*a):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                rc = fn(*a)
+                e1.record(stream)
+                detail = ""
+                if name.startswith("a3d_conv2d"):
+                    d = a[1]._obj
+                    detail = f"N{d.N} {d.H}x{d.W}x{d.C}->{d.P}x{d.Q}x{d.K} k{d.R}x{d.S} s{d.stride_h}"
+                elif name in ("a3d_dense_fwd", "a3d_dense_dgrad", "a3d_dense_wgrad"):
+                    i0 = {"a3d_dense_fwd": 10, "a3d_dense_dgrad": 5, "a3d_dense_wgrad": 6}[name]
+                    detail = "MNK=" + "x".join(str(int(x)) for x in a[i0:i0 + 3])
+                records.append((name, detail, e0, e1))
+                return rc
+            return w
+        wrapped[name] = fn
+        setattr(lib, name, make(fn, name))
+    try:
+        agg = {}
+        for r in range(reps):
+            records.clear()
+            op.net.global_step = 0
+            op.run(use_graph=False)
+            torch.cuda.synchronize()
+            for i, (name, detail, e0, e1) in enumerate(records):
+                key = (i, name, detail)
+                agg.setdefault(key, []).append(e0.elapsed_time(e1))
+    finally:
+        for name, fn in wrapped.items():
+            setattr(lib, name, fn)
+    rows = [{"seq": k[0], "op": k[1], "detail": k[2], "ms": min(v)} for k, v in sorted(agg.items())]
+    return rows
+
+
+def conv_flops(detail):
+    try:
+        left, right = detail.split("->")
+        n = int(left.split()[0][1:])
+        c = int(left.split()[1].split("x")[2])
+        p, q, k = (int(x) for x in right.split()[0].split("x"))
+        r, s = (int(x) for x in right.split()[1][1:].split("x"))
+        return 2.0 * n * p * q * k * r * s * c
+    except Exception:
+        return 0.0
+
+
+def gpu_arm(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from ann3depth_b200 import models, ops
+    from ann3depth_b200.dp import DataParallel
+    from ann3depth_b200.init import glorot_params
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    comm = None
+    ctx = models.get_context(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        ids = [ops.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        comm = DataParallel(ctx, rank, world, ids[0])
+
+    images_h, depths_h = synthetic_batch(rank, torch)
+    images_h, depths_h = images_h.pin_memory(), depths_h.pin_memory()
+    images, depths = images_h.to(dev), depths_h.to(dev)
+    op = models.msdn(images, depths, train=True, comm=comm)
+    op.net.load_params(glorot_params(seed=1))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident inputs: value
+    launches0 = ctx.launches
+    op.run(use_graph=False)
+    launches_per_step = ctx.launches - launches0
+    for _ in range(max(args.warmup, 3)):
+        op.run()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        op.run()
+    e1.record()
+    barrier()
+    sampler.stop_flag = True
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t)
+    value = BATCH * world * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end: pinned host batch -> H2D (prefetched on a copy stream) -> step -> loss D2H
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage = [(torch.empty_like(images), torch.empty_like(depths)) for _ in range(2)]
+    loss_h = torch.empty(2, dtype=torch.float32).pin_memory()
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    freed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[i % 2])
+            stage[i % 2][0].copy_(images_h, non_blocking=True)
+            stage[i % 2][1].copy_(depths_h, non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
+    def e2e_loop(n):
+        cur = torch.cuda.current_stream()
+        for f in freed:
+            f.record(cur)
+        prefetch(0)
+        for i in range(n):
+            if i + 1 < n:
+                prefetch(i + 1)
+            cur.wait_event(ready[i % 2])
+            images.copy_(stage[i % 2][0], non_blocking=True)
+            depths.copy_(stage[i % 2][1], non_blocking=True)
+            freed[i % 2].record(cur)
+            op.run()
+            loss_h[0:1].copy_(op.losses["loss/coarse_loss"], non_blocking=True)
+            loss_h[1:2].copy_(op.losses["loss/fine_loss"], non_blocking=True)
+            cur.synchronize()                       # the driver reads the loss every step
+        return float(loss_h[0])
+
+    e2e_loop(3)
+    barrier()
+    t0 = time.perf_counter()
+    last_loss = e2e_loop(args.steps)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = BATCH * world * args.steps / float(t)
+
+    if rank == 0:
+        pk, pk_kind = peaks()
+        rows = per_op_profile(op, torch)
+        step_ms = ms_total / args.steps
+        # dominant kernel of the step, and the conv/FC tensor-pipe aggregate
+        top = max(rows, key=lambda r: r["ms"])
+        tensor_ops = [r for r in rows if r["op"].startswith("a3d_conv2d")]
+        tflops = sum(conv_flops(r["detail"]) for r in tensor_ops)
+        tms = sum(r["ms"] for r in tensor_ops)
+        if top["op"].startswith("a3d_conv2d"):
+            fl = conv_flops(top["detail"])
+            ach = fl / (top["ms"] * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": f'{top["op"]} {top["detail"]}', "achieved": ach,
+                    "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": None,
+                    "peak_kind": pk_kind + " burst", "share_of_step": top["ms"] / sum(r["ms"] for r in rows)}
+        else:
+            roof = {"bound": "hbm", "kernel": f'{top["op"]} {top["detail"]}', "achieved": None, "peak": pk["hbm_gbs"],
+                    "unit": "GB/s", "frac": None, "traffic": None, "peak_kind": pk_kind,
+                    "share_of_step": top["ms"] / sum(r["ms"] for r in rows)}
+        roof["conv_tensor_tflops"] = tflops / (tms * 1e-3) / 1e12 if tms else None
+        roof["conv_tensor_frac_of_burst"] = roof["conv_tensor_tflops"] / pk["bf16_tflops"] if tms else None
+        roof["step_tflops_algorithmic"] = FLOP_PER_IMAGE_PHASE1 * BATCH / (step_ms * 1e-3) / 1e12
+        os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+        for d in ("profiles", "gpurun_out"):
+            if os.path.isdir(os.path.join(ROOT, d)):
+                with open(os.path.join(ROOT, d, "bench_ops_latest.json"), "w") as f:
+                    json.dump({"step_ms_graph": step_ms, "ops": rows}, f, indent=1)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, sample, _ = cpu_train_step_rate(2, 1, budget_s=25.0)
+            cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
+        line = {"metric": "MSDN train images/s (bs32/GPU, phase-1 step)", "value": value, "unit": "images/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic",
+                "config": {"workload": "msdn phase-1 train step (fwd coarse+fine, 2 losses, coarse bwd, 2 TF-Adam "
+                                       "groups), batch 32/GPU, 640x480 RGB -> 55x73 depth, glorot init seed 1",
+                           "parallelism": f"dp{world}", "global_batch": BATCH * world,
+                           "l2": "working set per step (~2.6 GB: activations + 283 MB weights + Adam slots) >> 126 MB L2",
+                           "adam": "reference TF-Adam(beta1=0.9, beta2=1, eps=1e-8)", "cuda_graph": True},
+                "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": H2D_BYTES,
+                        "d2h_bytes_per_step": D2H_BYTES, "last_loss": last_loss},
+                "gpu_launches": launches_per_step * args.steps,
+                "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="a3d", choices=["a3d", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+    gpu_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -133,6 +133,16 @@ int a3d_maxpool2x2_fwd(a3d_ctx*, const uint16_t* x, int N, int H, int W, int C,
  * dy has channel stride lddy. Rows/cols not covered by a window get 0. */
 int a3d_maxpool2x2_relu_bwd(a3d_ctx*, const uint16_t* x, const uint16_t* dy, int lddy,
                             int N, int H, int W, int C, uint16_t* dx, void* stream);
+/* Same pool, but on the f32 conv output and recording the routing decision: idx[n,oh,ow,c] in 0..3 is
+ * the first arg-max of the window (row-major), 4 means "blocked" (max <= 0, i.e. the ReLU was inactive).
+ * Deciding on f32 values avoids the arg-max ties that bf16-rounded activations produce (about 1 % of
+ * windows), which would mis-route gradients relative to the reference's f32 MaxPoolGrad. */
+int a3d_maxpool2x2_fwd_f32(a3d_ctx*, const float* x, int N, int H, int W, int C,
+                           uint16_t* y, int ldy, uint8_t* idx, void* stream);
+/* MaxPoolGrad + ReluGrad from the recorded routing: dx[n,2oh+i/2,2ow+i%2,c] = dy[n,oh,ow,c] where
+ * i = idx < 4, zero everywhere else (including the odd trailing row / column). dx bf16 [N,H,W,C]. */
+int a3d_maxpool2x2_idx_bwd(a3d_ctx*, const uint8_t* idx, const uint16_t* dy, int lddy,
+                           int N, int H, int W, int C, uint16_t* dx, void* stream);
 /* ReluGrad alone: dx = (y > 0) ? dy : 0 (dy channel stride lddy, y/dx dense [rows,C]). */
 int a3d_relu_bwd(a3d_ctx*, const uint16_t* y, const uint16_t* dy, int lddy, uint16_t* dx,
                  size_t rows, int C, void* stream);
@@ -151,9 +161,19 @@ int a3d_silog_loss(a3d_ctx*, const float* out, const float* tar, int B, int n, f
  * g is multiplied by grad_scale first (1/world_size after a sum-allreduce).
  * w_bf16 (nullable) receives the bf16 copy of the updated weights. */
 int a3d_adam_tf(a3d_ctx*, float* w, const float* g, float* m, float* v, uint16_t* w_bf16, size_t n,
-                float lr_t, float beta1, float beta2, float eps, float grad_scale, void* stream);
+                float lr_t, float beta1, float beta2, float eps, float grad_scale,
+                const float* lr_t_dev /* nullable: device scalar that overrides lr_t, so a captured
+                                         CUDA graph can follow the bias-correction schedule */,
+                void* stream);
 int a3d_sgd(a3d_ctx*, float* w, const float* g, uint16_t* w_bf16, size_t n, float lr,
             float grad_scale, void* stream);
+/* Dropout keep-mask (tf.layers.dropout, src/models.py:230; unseeded in the reference): keep[i] = 1 with
+ * probability keep_prob, from a counter-based hash of (seed, *counter_dev, i).  counter_dev is a device
+ * int64 (e.g. the global step) so that a captured CUDA graph draws a fresh mask on every replay. */
+int a3d_bernoulli_mask(a3d_ctx*, uint8_t* keep, size_t n, float keep_prob, uint64_t seed,
+                       const int64_t* counter_dev, void* stream);
+/* *p += 1 (device-resident global_step, src/models.py:279,329,343,356). */
+int a3d_increment_i64(a3d_ctx*, int64_t* p, void* stream);
 /* f32 -> bf16 cast of a flat segment (weight mirror refresh). */
 int a3d_cast_f32_bf16(a3d_ctx*, const float* src, uint16_t* dst, size_t n, void* stream);
 
@@ -163,6 +183,9 @@ int a3d_cast_f32_bf16(a3d_ctx*, const float* src, uint16_t* dst, size_t n, void*
 int a3d_scatter_channel_bf16(a3d_ctx*, const float* src, uint16_t* dst, size_t rows, int ld, int ch,
                              void* stream);
 int a3d_fill_zero(a3d_ctx*, void* p, size_t bytes, void* stream);
+/* g[i] = keep[i] ? g[i] : 0 -- clears the gradient of layout-padding entries (zero taps / channels
+ * added so that the 3-channel first layers fit the tensor-core path) before the optimizer runs. */
+int a3d_apply_mask_f32(a3d_ctx*, float* g, const uint8_t* keep, size_t n, void* stream);
 
 /* ---- DCNF CRF (src/models.py:129-177) ------------------------------------------------------ */
 /* Batched closed-form CRF on the static pair graph.  For each of B graphs with n nodes and

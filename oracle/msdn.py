@@ -98,10 +98,12 @@ def coarse(p, images, dropout_mask=None, train=True, q=_ident):
 
     def b(n):
         return p[n + "/bias"]
-    t = q(T.conv2d(images, k("coarse/conv/conv2d_0"), b("coarse/conv/conv2d_0"), 4, "valid", True))
-    t = T.max_pool_2x2(t)
-    t = q(T.conv2d(t, k("coarse/conv/conv2d_1"), b("coarse/conv/conv2d_1"), 1, "same", True))
-    t = T.max_pool_2x2(t)
+    # where a pool follows, q() is applied after it: rounding is monotone so the forward value is the
+    # same, and the arg-max routing is decided on unrounded values as in the CUDA path
+    t = T.conv2d(images, k("coarse/conv/conv2d_0"), b("coarse/conv/conv2d_0"), 4, "valid", True)
+    t = q(T.max_pool_2x2(t))
+    t = T.conv2d(t, k("coarse/conv/conv2d_1"), b("coarse/conv/conv2d_1"), 1, "same", True)
+    t = q(T.max_pool_2x2(t))
     t = q(T.conv2d(t, k("coarse/conv/conv2d_2"), b("coarse/conv/conv2d_2"), 1, "same", True))
     t = q(T.conv2d(t, k("coarse/conv/conv2d_3"), b("coarse/conv/conv2d_3"), 1, "same", True))
     t = q(T.conv2d(t, k("coarse/conv/conv2d_4"), b("coarse/conv/conv2d_4"), 2, "valid", True))
@@ -122,8 +124,8 @@ def fine(p, images, coarse_map, q=_ident):
 
     def b(n):
         return p[n + "/bias"]
-    t = q(T.conv2d(images, k("fine/first/conv2d"), b("fine/first/conv2d"), 2, "valid", True))
-    t = T.max_pool_2x2(t)
+    t = T.conv2d(images, k("fine/first/conv2d"), b("fine/first/conv2d"), 2, "valid", True)
+    t = q(T.max_pool_2x2(t))
     t = torch.cat([t, q(coarse_map)], dim=-1)                         # :246
     t = q(T.conv2d(t, k("fine/second/conv2d"), b("fine/second/conv2d"), 1, "same", True))
     t = T.conv2d(t, k("fine/third"), b("fine/third"), 1, "same", False)

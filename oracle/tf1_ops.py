@@ -71,7 +71,7 @@ def conv2d(x, kernel, bias=None, stride=1, padding="valid", relu=False):
         _, pt, pb = same_pad(x.shape[1], kh, stride)
         _, pl, pr = same_pad(x.shape[2], kw, stride)
         xn = F.pad(xn, (pl, pr, pt, pb))
-    w = kernel.permute(3, 2, 0, 1)
+    w = kernel.permute(3, 2, 0, 1).contiguous()
     y = F.conv2d(xn, w, bias, stride=stride)
     if relu:
         y = torch.relu(y)

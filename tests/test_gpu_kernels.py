@@ -343,3 +343,19 @@ def test_pairwise_features_tile_means_patches(ctx):
     pt = ctx.extract_patches(im.to(DEV), dstC=16)
     refp = OD.patches(im).reshape(96, 100, 100, 3).to(torch.bfloat16)
     assert torch.equal(pt[..., :3].cpu(), refp) and float(pt[..., 3:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("N,H,W,C", [(2, 55, 74, 96), (1, 27, 37, 256), (1, 110, 148, 64)])
+def test_maxpool_f32_routing(ctx, N, H, W, C):
+    g = torch.Generator().manual_seed(50)
+    x = torch.relu(torch.randn(N, H, W, C, generator=g)).to(DEV)
+    idx = torch.empty(N, H // 2, W // 2, C, dtype=torch.uint8, device=DEV)
+    y = ctx.maxpool2x2_fwd_f32(x, idx=idx)
+    xr = x.permute(0, 3, 1, 2).clone().requires_grad_(True)
+    yr = F.max_pool2d(xr, 2, 2)
+    assert torch.equal(y, yr.permute(0, 2, 3, 1).to(torch.bfloat16))
+    dy = bf16_rand(N, H // 2, W // 2, C, seed=51)
+    (gx,) = torch.autograd.grad(yr, xr, dy.float().permute(0, 3, 1, 2))
+    gx = gx.permute(0, 2, 3, 1) * (x > 0)
+    dx = ctx.maxpool2x2_idx_bwd(idx, dy, (N, H, W, C))
+    assert torch.equal(dx.float(), gx)
