@@ -1,13 +1,20 @@
 // conv.cu -- public convolution / dense entry points: argument checks and implementation dispatch
-// (tcgen05 engine in tc_gemm.cu where the shape allows, CUDA-core implicit GEMM otherwise).
+// (tcgen05 engine in tc_gemm.cu where the shape allows, CUDA-core kernels otherwise), plus the small
+// helper kernels around them (filter flip for dgrad, col2im, single-filter convolution).
 #include "common.cuh"
 
 int a3d_tc_conv_fwd(a3d_ctx*, const a3d_conv_desc*, const uint16_t* x, const uint16_t* w, const float* bias, void* y,
                     int y_dtype, unsigned flags, void* ws, size_t ws_bytes, cudaStream_t st);
-size_t a3d_tc_conv_fwd_ws_bytes(a3d_ctx*, const a3d_conv_desc*);
+int a3d_tc_conv_wgrad_supported(const a3d_conv_desc* d);
+int a3d_tc_conv_wgrad(a3d_ctx*, const a3d_conv_desc*, const uint16_t* x, const uint16_t* dy, float* dw, cudaStream_t st);
+int a3d_tc_dgrad_cols(a3d_ctx*, const a3d_conv_desc*, const uint16_t* dy, const uint16_t* w, float* col, cudaStream_t st);
 int a3d_tc_dense_fwd(a3d_ctx*, const uint16_t* x, int ldx, const uint16_t* w, const float* bias, const uint8_t* mask,
                      float drop_rate, void* y, int y_dtype, float* acc_ws, int M, int N, int K, unsigned flags,
                      cudaStream_t st);
+int a3d_tc_dense_dgrad(a3d_ctx*, const uint16_t* dy, int lddy, const uint16_t* w, uint16_t* dx, float* acc_ws, int M,
+                       int N, int K, cudaStream_t st);
+int a3d_tc_dense_wgrad(a3d_ctx*, const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, int M, int N, int K,
+                       cudaStream_t st);
 
 static int check_desc(const a3d_conv_desc* d) {
   A3D_REQUIRE(d, "conv: null descriptor");
@@ -20,10 +27,26 @@ static int check_desc(const a3d_conv_desc* d) {
   return 0;
 }
 
+// A layer with fewer than 16 channels cannot feed the im2col TMA (>= 32 B per pixel for UMMA K = 16).
+// If the horizontal stride is a multiple of g = 16/C pixels, g adjacent pixels can be read as ONE
+// pixel of g*C channels of a [N, H, W/g, g*C] tensor: the filter [K,R,S,C] is then the same memory
+// as [K,R,S/g,g*C] and the stride becomes stride_w/g.  (MSDN conv2d_0: 11x12x4 s4 -> 11x3x16 s1.)
+static bool virtualize(const a3d_conv_desc* d, a3d_conv_desc* v) {
+  if (d->C >= 16 || 16 % d->C) return false;
+  int g = 16 / d->C;
+  if (d->stride_w % g || d->W % g || d->S % g || d->pad_l != 0) return false;
+  *v = *d;
+  v->C = d->C * g; v->W = d->W / g; v->S = d->S / g; v->stride_w = d->stride_w / g;
+  return true;
+}
+
 // dgrad of a stride-1 conv == forward conv of dy with the spatially flipped, channel-transposed filter
 static bool dgrad_as_fwd_ok(const a3d_conv_desc* d) {
   return d->stride_h == 1 && d->stride_w == 1 && d->ldy == d->K && d->K % 16 == 0 && d->C % 8 == 0 &&
          d->R - 1 - d->pad_t >= 0 && d->S - 1 - d->pad_l >= 0;
+}
+static bool dgrad_as_cols_ok(const a3d_conv_desc* d) {
+  return d->K % 64 == 0 && (d->R * d->S * d->C) % 64 == 0 && d->ldy % 8 == 0 && d->C % 8 == 0;
 }
 
 __global__ void flip_filter_kernel(const uint16_t* __restrict__ w, uint16_t* __restrict__ wd, int K, int RS, int C) {
@@ -38,11 +61,98 @@ __global__ void flip_filter_kernel(const uint16_t* __restrict__ w, uint16_t* __r
   }
 }
 
+// dx[n,ih,iw,c8] = sum over taps (r,s) with (ih+pt-r) % sh == 0 ... of col[(n,p,q)][(r,s,c8)]
+__global__ void col2im_kernel(const float* __restrict__ col, uint16_t* __restrict__ dx, int N, int H, int W, int C, int R,
+                              int S, int sh, int sw, int pt, int pl, int P, int Q) {
+  const int C8 = C / 8;
+  const size_t J = (size_t)R * S * C;
+  size_t total = (size_t)N * H * W * C8;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int c8 = (int)(i % C8);
+    size_t t = i / C8;
+    int iw = (int)(t % W);
+    t /= W;
+    int ih = (int)(t % H);
+    int n = (int)(t / H);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int r = 0; r < R; ++r) {
+      int ph = ih + pt - r;
+      if (ph < 0 || ph % sh) continue;
+      int p = ph / sh;
+      if (p >= P) continue;
+      for (int s = 0; s < S; ++s) {
+        int qw = iw + pl - s;
+        if (qw < 0 || qw % sw) continue;
+        int q = qw / sw;
+        if (q >= Q) continue;
+        const float4* src =
+            reinterpret_cast<const float4*>(col + (((size_t)n * P + p) * Q + q) * J + (size_t)(r * S + s) * C + c8 * 8);
+        float4 a = __ldg(src), b = __ldg(src + 1);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+        acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+      }
+    }
+    uint4 o = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                         pack_bf16x2(acc[6], acc[7]));
+    reinterpret_cast<uint4*>(dx)[i] = o;
+  }
+}
+
+// Single-filter convolution (K == 1, C % 64 == 0): one warp per output pixel, lanes split the channels
+// (coalesced 128 B per tap), warp-shuffle reduction.  HBM/L2-bound; used for MSDN fine/third
+// (src/models.py:250: 5x5x64 -> 1) where a 128-row tensor-core tile would be 127/128 padding.
+__global__ void conv_k1_fwd_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ w,
+                                   const float* __restrict__ bias, void* __restrict__ y, int y_f32, int N, int H, int W,
+                                   int C, int R, int S, int sh, int sw, int pt, int pl, int P, int Q, int ldy,
+                                   unsigned flags) {
+  extern __shared__ float wsm[];           // R*S*C filter as f32
+  for (int i = threadIdx.x; i < R * S * C; i += blockDim.x) wsm[i] = bf16_bits_to_f32(w[i]);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const long long total = (long long)N * P * Q;
+  for (long long m = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); m < total;
+       m += (long long)gridDim.x * warps_per_block) {
+    int q = (int)(m % Q);
+    long long t = m / Q;
+    int p = (int)(t % P);
+    int n = (int)(t / P);
+    float acc = 0.f;
+    for (int r = 0; r < R; ++r) {
+      int ih = p * sh - pt + r;
+      if (ih < 0 || ih >= H) continue;
+      for (int s = 0; s < S; ++s) {
+        int iw = q * sw - pl + s;
+        if (iw < 0 || iw >= W) continue;
+        const uint16_t* px = x + (((size_t)n * H + ih) * W + iw) * C;
+        const float* wf = wsm + (r * S + s) * C;
+        for (int c = lane * 2; c < C; c += 64) {
+          uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(px + c));
+          acc = fmaf(__uint_as_float(v << 16), wf[c], acc);
+          acc = fmaf(__uint_as_float(v & 0xffff0000u), wf[c + 1], acc);
+        }
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      if (bias) acc += bias[0];
+      if (flags & A3D_EPI_RELU) acc = fmaxf(acc, 0.f);
+      if (y_f32) reinterpret_cast<float*>(y)[(size_t)m * ldy] = acc;
+      else reinterpret_cast<uint16_t*>(y)[(size_t)m * ldy] = f32_to_bf16_bits(acc);
+    }
+  }
+}
+
+static size_t filt_bytes(const a3d_conv_desc* d) { return ((size_t)d->K * d->R * d->S * d->C * 2 + 255) & ~(size_t)255; }
+
 extern "C" size_t a3d_conv2d_ws_bytes(a3d_ctx* ctx, const a3d_conv_desc* d, int op) {
   if (!d) return 0;
-  size_t filt = ((size_t)d->K * d->R * d->S * d->C * 2 + 255) & ~(size_t)255;
   if (op == A3D_OP_FWD) return (size_t)d->N * d->P * d->Q * d->K * sizeof(float);
-  if (op == A3D_OP_DGRAD) return filt + (size_t)d->N * d->H * d->W * d->C * sizeof(float);
+  if (op == A3D_OP_DGRAD) {
+    size_t a = filt_bytes(d) + (size_t)d->N * d->H * d->W * d->C * sizeof(float);          // stride-1 path
+    size_t b = (size_t)d->N * d->P * d->Q * d->R * d->S * d->C * sizeof(float);            // cols path
+    return a > b ? a : b;
+  }
   return 0;
 }
 
@@ -54,7 +164,19 @@ extern "C" int a3d_conv2d_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
   if (d->impl == A3D_IMPL_SIMT) return a3d_simt_conv_fwd(ctx, d, x, w, bias, y, y_dtype, flags, st);
-  if (a3d_tc_conv_fwd_supported(d)) return a3d_tc_conv_fwd(ctx, d, x, w, bias, y, y_dtype, flags, ws, ws_bytes, st);
+  if (d->K == 1 && d->C % 64 == 0 && (size_t)d->R * d->S * d->C * 4 <= 48 * 1024) {
+    long long pixels = (long long)d->N * d->P * d->Q;
+    int block = 256, grid = (int)((pixels + 7) / 8);
+    if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+    conv_k1_fwd_kernel<<<grid, block, (size_t)d->R * d->S * d->C * 4, st>>>(
+        x, w, bias, y, y_dtype == A3D_F32, d->N, d->H, d->W, d->C, d->R, d->S, d->stride_h, d->stride_w, d->pad_t,
+        d->pad_l, d->P, d->Q, d->ldy, flags);
+    A3D_LAUNCH_OK(ctx);
+    return 0;
+  }
+  a3d_conv_desc v;
+  const a3d_conv_desc* e = virtualize(d, &v) ? &v : d;
+  if (a3d_tc_conv_fwd_supported(e)) return a3d_tc_conv_fwd(ctx, e, x, w, bias, y, y_dtype, flags, ws, ws_bytes, st);
   if (d->impl == A3D_IMPL_TC) {
     a3d_set_error("conv fwd: shape not supported by the tcgen05 path (C=%d K=%d)", d->C, d->K);
     return A3D_ENOTSUP;
@@ -68,7 +190,7 @@ extern "C" int a3d_conv2d_dgrad(a3d_ctx* ctx, const a3d_conv_desc* d, const uint
   int rc = check_desc(d);
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
-  size_t filt = ((size_t)d->K * d->R * d->S * d->C * 2 + 255) & ~(size_t)255;
+  const size_t filt = filt_bytes(d);
   if (d->impl != A3D_IMPL_SIMT && dgrad_as_fwd_ok(d) && ws && ws_bytes >= filt) {
     uint16_t* wd = reinterpret_cast<uint16_t*>(ws);
     size_t total = (size_t)d->K * d->R * d->S * d->C;
@@ -83,6 +205,20 @@ extern "C" int a3d_conv2d_dgrad(a3d_ctx* ctx, const a3d_conv_desc* d, const uint
     e.stride_h = e.stride_w = 1;
     return a3d_tc_conv_fwd(ctx, &e, dy, wd, nullptr, dx, A3D_BF16, 0, reinterpret_cast<uint8_t*>(ws) + filt,
                            ws_bytes - filt, st);
+  }
+  const size_t col_bytes = (size_t)d->N * d->P * d->Q * d->R * d->S * d->C * sizeof(float);
+  if (d->impl != A3D_IMPL_SIMT && dgrad_as_cols_ok(d) && ws && ws_bytes >= col_bytes) {
+    // strided conv: GEMM into per-output-pixel columns, then gather them back (col2im)
+    float* col = reinterpret_cast<float*>(ws);
+    rc = a3d_tc_dgrad_cols(ctx, d, dy, w, col, st);
+    if (rc) return rc;
+    size_t total = (size_t)d->N * d->H * d->W * (d->C / 8);
+    int grid = (int)((total + 255) / 256);
+    if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
+    col2im_kernel<<<grid, 256, 0, st>>>(col, dx, d->N, d->H, d->W, d->C, d->R, d->S, d->stride_h, d->stride_w, d->pad_t,
+                                       d->pad_l, d->P, d->Q);
+    A3D_LAUNCH_OK(ctx);
+    return 0;
   }
   if (d->impl == A3D_IMPL_TC) {
     a3d_set_error("conv dgrad: shape not supported by the tcgen05 path (stride %d, K=%d, ws=%zu)", d->stride_h, d->K,
@@ -102,9 +238,14 @@ extern "C" int a3d_conv2d_wgrad(a3d_ctx* ctx, const a3d_conv_desc* d, const uint
     rc = a3d_colsum_bf16(ctx, dy, (size_t)d->N * d->P * d->Q, d->K, d->ldy, db, st);
     if (rc) return rc;
   }
-  if (d->impl == A3D_IMPL_TC) {
-    a3d_set_error("conv wgrad: tcgen05 path not available for this shape");
-    return A3D_ENOTSUP;
+  if (d->impl != A3D_IMPL_SIMT) {
+    a3d_conv_desc v;
+    const a3d_conv_desc* e = virtualize(d, &v) ? &v : d;
+    if (a3d_tc_conv_wgrad_supported(e)) return a3d_tc_conv_wgrad(ctx, e, x, dy, dw, st);
+    if (d->impl == A3D_IMPL_TC) {
+      a3d_set_error("conv wgrad: shape not supported by the tcgen05 path (C=%d ldy=%d)", d->C, d->ldy);
+      return A3D_ENOTSUP;
+    }
   }
   return a3d_simt_conv_wgrad(ctx, d, x, dy, dw, st);
 }
@@ -125,27 +266,32 @@ extern "C" int a3d_dense_fwd(a3d_ctx* ctx, const uint16_t* x, int ldx, const uin
   return a3d_simt_dense_fwd(ctx, x, ldx, w, bias, keep_mask, drop_rate, y, y_dtype, M, N, K, flags, st);
 }
 
-extern "C" int a3d_dense_dgrad(a3d_ctx* ctx, const uint16_t* dy, const uint16_t* w, uint16_t* dx, float* acc_ws, int M,
-                               int N, int K, int impl, void* stream) {
-  A3D_REQUIRE(ctx && dy && w && dx && M > 0 && N > 0 && K > 0, "dense dgrad: bad argument");
+extern "C" int a3d_dense_dgrad(a3d_ctx* ctx, const uint16_t* dy, int lddy, const uint16_t* w, uint16_t* dx,
+                               float* acc_ws, int M, int N, int K, int impl, void* stream) {
+  A3D_REQUIRE(ctx && dy && w && dx && M > 0 && N > 0 && K > 0 && lddy >= N, "dense dgrad: bad argument");
+  cudaStream_t st = as_stream(stream);
+  bool tc_ok = (K % 8 == 0) && (lddy % 8 == 0) && M <= 128 && acc_ws;
+  if (impl != A3D_IMPL_SIMT && tc_ok) return a3d_tc_dense_dgrad(ctx, dy, lddy, w, dx, acc_ws, M, N, K, st);
   if (impl == A3D_IMPL_TC) {
-    a3d_set_error("dense dgrad: tcgen05 path not available");
+    a3d_set_error("dense dgrad: shape not supported by the tcgen05 path (M=%d N=%d K=%d lddy=%d)", M, N, K, lddy);
     return A3D_ENOTSUP;
   }
-  return a3d_simt_dense_dgrad(ctx, dy, w, dx, M, N, K, as_stream(stream));
+  return a3d_simt_dense_dgrad(ctx, dy, lddy, w, dx, M, N, K, st);
 }
 
-extern "C" int a3d_dense_wgrad(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t* dy, float* dw, float* db, int M,
-                               int N, int K, int impl, void* stream) {
-  A3D_REQUIRE(ctx && x && dy && dw && M > 0 && N > 0 && K > 0, "dense wgrad: bad argument");
+extern "C" int a3d_dense_wgrad(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw,
+                               float* db, int M, int N, int K, int impl, void* stream) {
+  A3D_REQUIRE(ctx && x && dy && dw && M > 0 && N > 0 && K > 0 && lddy >= N && ldx >= K, "dense wgrad: bad argument");
   cudaStream_t st = as_stream(stream);
   if (db) {
-    int rc = a3d_colsum_bf16(ctx, dy, (size_t)M, N, N, db, st);
+    int rc = a3d_colsum_bf16(ctx, dy, (size_t)M, N, lddy, db, st);
     if (rc) return rc;
   }
+  bool tc_ok = (K % 64 == 0) && (ldx % 8 == 0) && (lddy % 8 == 0);
+  if (impl != A3D_IMPL_SIMT && tc_ok) return a3d_tc_dense_wgrad(ctx, x, ldx, dy, lddy, dw, M, N, K, st);
   if (impl == A3D_IMPL_TC) {
-    a3d_set_error("dense wgrad: tcgen05 path not available");
+    a3d_set_error("dense wgrad: shape not supported by the tcgen05 path (M=%d N=%d K=%d)", M, N, K);
     return A3D_ENOTSUP;
   }
-  return a3d_simt_dense_wgrad(ctx, x, ldx, dy, dw, M, N, K, st);
+  return a3d_simt_dense_wgrad(ctx, x, ldx, dy, lddy, dw, M, N, K, st);
 }

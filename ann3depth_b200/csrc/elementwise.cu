@@ -225,7 +225,7 @@ extern "C" int a3d_dense_epilogue_bwd(a3d_ctx* ctx, const uint16_t* g_post, cons
 // sum d^2 with warp shuffles.  Pass 2: gradient (2 d_i - 2*lon*sum d) / (out_i+eps) / B, 0 on the NaN branch.
 __global__ void silog_loss_kernel(const float* __restrict__ out, const float* __restrict__ tar, int n, int B,
                                   float lambda_over_n, float* __restrict__ loss_ps, float* __restrict__ dout_f32,
-                                  uint16_t* __restrict__ dout_bf16) {
+                                  uint16_t* __restrict__ dout_bf16, int ld) {
   extern __shared__ float sd[];          // n floats: cached d_i
   __shared__ float red[2][32];
   const float eps = 1e-8f;
@@ -265,8 +265,8 @@ __global__ void silog_loss_kernel(const float* __restrict__ out, const float* __
       float arg = o[i] + eps;
       float g = 0.f;
       if (!isnan(logf(arg))) g = (2.f * sd[i] - 2.f * lambda_over_n * s1) / arg * invB;
-      if (dout_f32) dout_f32[(size_t)b * n + i] = g;
-      if (dout_bf16) dout_bf16[(size_t)b * n + i] = f32_to_bf16_bits(g);
+      if (dout_f32) dout_f32[(size_t)b * ld + i] = g;
+      if (dout_bf16) dout_bf16[(size_t)b * ld + i] = f32_to_bf16_bits(g);
     }
   }
 }
@@ -279,14 +279,17 @@ __global__ void mean_kernel(const float* __restrict__ v, int n, float* __restric
 }
 
 extern "C" int a3d_silog_loss(a3d_ctx* ctx, const float* out, const float* tar, int B, int n, float lambda_over_n,
-                              float* loss_per_sample, float* loss, float* dout_f32, uint16_t* dout_bf16, void* stream) {
+                              float* loss_per_sample, float* loss, float* dout_f32, uint16_t* dout_bf16, int dout_ld,
+                              void* stream) {
   A3D_REQUIRE(ctx && out && tar && loss_per_sample && loss, "silog_loss: null argument");
   A3D_REQUIRE(B > 0 && n > 0 && (size_t)n * sizeof(float) <= 200 * 1024, "silog_loss: bad shape");
   size_t smem = (size_t)n * sizeof(float);
   if (smem > 48 * 1024)
     A3D_CHECK_CUDA(cudaFuncSetAttribute(silog_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (dout_ld <= 0) dout_ld = n;
+  A3D_REQUIRE(dout_ld >= n, "silog_loss: dout_ld < n");
   silog_loss_kernel<<<B, 512, smem, as_stream(stream)>>>(out, tar, n, B, lambda_over_n, loss_per_sample, dout_f32,
-                                                        dout_bf16);
+                                                        dout_bf16, dout_ld);
   A3D_LAUNCH_OK(ctx);
   mean_kernel<<<1, 32, 0, as_stream(stream)>>>(loss_per_sample, B, loss);
   A3D_LAUNCH_OK(ctx);

@@ -89,21 +89,21 @@ struct DenseFwdProb {   // y[m][n] = act(sum_k x[m][k] w[n][k] + bias[n]) * mask
 };
 
 struct DenseDgradProb {  // dx[m][k] = sum_n dy[m][n] w[n][k]
-  const uint16_t* dy; const uint16_t* w; uint16_t* dx; int M, N, K;
+  const uint16_t* dy; const uint16_t* w; uint16_t* dx; int M, N, K, lddy;
   __device__ int dimM() const { return M; }
   __device__ int dimN() const { return K; }
   __device__ int dimK() const { return N; }
-  __device__ float a(int m, int j) const { return bf16_bits_to_f32(dy[(size_t)m * N + j]); }
+  __device__ float a(int m, int j) const { return bf16_bits_to_f32(dy[(size_t)m * lddy + j]); }
   __device__ float b(int kin, int j) const { return bf16_bits_to_f32(w[(size_t)j * K + kin]); }
   __device__ void store(int m, int kin, float acc) const { dx[(size_t)m * K + kin] = f32_to_bf16_bits(acc); }
 };
 
 struct DenseWgradProb {  // dw[n][k] = sum_m dy[m][n] x[m][k]
-  const uint16_t* x; const uint16_t* dy; float* dw; int M, N, K, ldx;
+  const uint16_t* x; const uint16_t* dy; float* dw; int M, N, K, ldx, lddy;
   __device__ int dimM() const { return N; }
   __device__ int dimN() const { return K; }
   __device__ int dimK() const { return M; }
-  __device__ float a(int n, int m) const { return bf16_bits_to_f32(dy[(size_t)m * N + n]); }
+  __device__ float a(int n, int m) const { return bf16_bits_to_f32(dy[(size_t)m * lddy + n]); }
   __device__ float b(int k, int m) const { return bf16_bits_to_f32(x[(size_t)m * ldx + k]); }
   __device__ void store(int n, int k, float acc) const { dw[(size_t)n * K + k] = acc; }
 };
@@ -208,14 +208,14 @@ int a3d_simt_dense_fwd(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t*
   return launch(ctx, p, M, N, st);
 }
 
-int a3d_simt_dense_dgrad(a3d_ctx* ctx, const uint16_t* dy, const uint16_t* w, uint16_t* dx, int M, int N, int K,
-                         cudaStream_t st) {
-  DenseDgradProb p{dy, w, dx, M, N, K};
+int a3d_simt_dense_dgrad(a3d_ctx* ctx, const uint16_t* dy, int lddy, const uint16_t* w, uint16_t* dx, int M, int N,
+                         int K, cudaStream_t st) {
+  DenseDgradProb p{dy, w, dx, M, N, K, lddy};
   return launch(ctx, p, M, K, st);
 }
 
-int a3d_simt_dense_wgrad(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t* dy, float* dw, int M, int N, int K,
-                         cudaStream_t st) {
-  DenseWgradProb p{x, dy, dw, M, N, K, ldx};
+int a3d_simt_dense_wgrad(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, int M,
+                         int N, int K, cudaStream_t st) {
+  DenseWgradProb p{x, dy, dw, M, N, K, ldx, lddy};
   return launch(ctx, p, N, K, st);
 }

@@ -248,6 +248,147 @@ int a3d_tc_dense_fwd(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t* w
 }
 
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// convolution weight gradient:  dW[co][(tap,ci)] = sum_m dY[m][co] * im2col(X)[m][(tap,ci)]
+// Both operands are MN-major (the reduction index m = output pixel is the slow one in memory):
+//   A = dY  [m][co]   tiled loads of 64 pixels x 64 channels
+//   B = X in im2col mode, 64 pixels x BW channels per (tap, channel-block)
+// split-K over the pixel range with fp32 atomics into the (zeroed) dW.
+namespace {
+template <int BW, int NBLK>
+int launch_wgrad(a3d_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const tc::Params& p, int splits,
+                 cudaStream_t st) {
+  return launch_cfg<tc::Cfg<BW * NBLK, 128, true, true, BW>>(ctx, tmA, tmB, p, splits, st);
+}
+int pick_nblk(int bw, int total_blocks) {
+  static const int c64[] = {4, 3, 2, 1, 0}, c32[] = {6, 5, 4, 3, 0}, c16[] = {16, 11, 8, 0};
+  const int* cand = bw == 64 ? c64 : bw == 32 ? c32 : c16;
+  int best = cand[0], best_pad = 1 << 30;
+  for (int i = 0; cand[i]; ++i) {
+    int padded = (total_blocks + cand[i] - 1) / cand[i] * cand[i];
+    if (padded < best_pad) { best_pad = padded; best = cand[i]; }
+  }
+  return best;
+}
+}  // namespace
+
+int a3d_tc_conv_wgrad_supported(const a3d_conv_desc* d) {
+  return d->C % 16 == 0 && d->ldy % 8 == 0 && d->stride_h <= 8 && d->stride_w <= 8 && d->R <= 256 && d->S <= 256;
+}
+
+int a3d_tc_conv_wgrad(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, const uint16_t* dy, float* dw,
+                      cudaStream_t st) {
+  if (!a3d_tc_conv_wgrad_supported(d)) {
+    a3d_set_error("tc conv wgrad: unsupported shape (C=%d ldy=%d)", d->C, d->ldy);
+    return A3D_ENOTSUP;
+  }
+  const int bw = d->C % 64 == 0 ? 64 : d->C % 32 == 0 ? 32 : 16;
+  const int cblocks = d->C / bw;
+  const int RS = d->R * d->S;
+  const int total_blocks = RS * cblocks;
+  const int nblk = pick_nblk(bw, total_blocks);
+  const long long Mpix = (long long)d->N * d->P * d->Q;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d(ctx, &tmA, dy, Mpix, d->K, d->ldy, 64, 64);
+  if (rc) return rc;
+  rc = make_tmap_im2col(ctx, &tmB, x, d->N, d->H, d->W, d->C, -d->pad_t, -d->pad_l, d->P, d->Q, d->stride_h,
+                        d->stride_w, bw, 64);
+  if (rc) return rc;
+  tc::Params p{};
+  p.M = d->K; p.N = RS * d->C; p.num_kb = ceil_div(Mpix, 64);
+  p.a_mode = tc::A_TILED; p.b_im2col = 1; p.RS = RS;
+  p.PQ = d->P * d->Q; p.Q = d->Q; p.sh = d->stride_h; p.sw = d->stride_w; p.lower_h = -d->pad_t; p.lower_w = -d->pad_l;
+  p.S = d->S; p.cblocks = cblocks;
+  const int tiles = ceil_div(d->K, 128) * ceil_div(total_blocks, nblk);
+  int splits = pick_splits(ctx, tiles, p.num_kb, 4);
+  p.kb_per_split = ceil_div(p.num_kb, splits);
+  splits = ceil_div(p.num_kb, p.kb_per_split);
+  p.epi = tc::EPI_ROW_F32; p.out = dw; p.ldo = (long long)RS * d->C; p.atomic = splits > 1;
+  if (splits > 1) A3D_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)d->K * RS * d->C * sizeof(float), st));
+#define A3D_WG(BW, NB) if (bw == BW && nblk == NB) return launch_wgrad<BW, NB>(ctx, tmA, tmB, p, splits, st);
+  A3D_WG(64, 4) A3D_WG(64, 3) A3D_WG(64, 2) A3D_WG(64, 1)
+  A3D_WG(32, 6) A3D_WG(32, 5) A3D_WG(32, 4) A3D_WG(32, 3)
+  A3D_WG(16, 16) A3D_WG(16, 11) A3D_WG(16, 8)
+#undef A3D_WG
+  a3d_set_error("tc conv wgrad: no kernel for BW=%d NBLK=%d", bw, nblk);
+  return A3D_ENOTSUP;
+}
+
+// ------------------------------------------------------------------------------------------------
+// strided dgrad, GEMM half:  col[m][(tap,ci)] = sum_co dY[m][co] * W[co][(tap,ci)]   (f32, then col2im)
+int a3d_tc_dgrad_cols(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* dy, const uint16_t* w, float* col,
+                      cudaStream_t st) {
+  const long long Mpix = (long long)d->N * d->P * d->Q;
+  const int J = d->R * d->S * d->C;
+  if (d->K % 64 || J % 64 || d->ldy % 8) {
+    a3d_set_error("tc dgrad cols: needs K %% 64 == 0 and R*S*C %% 64 == 0");
+    return A3D_ENOTSUP;
+  }
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d(ctx, &tmA, dy, Mpix, d->K, d->ldy, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d(ctx, &tmB, w, d->K, J, J, 64, 64);
+  if (rc) return rc;
+  tc::Params p{};
+  p.M = (int)Mpix; p.N = J; p.num_kb = d->K / 64; p.kb_per_split = p.num_kb; p.a_mode = tc::A_TILED;
+  p.epi = tc::EPI_ROW_F32; p.out = col; p.ldo = J; p.atomic = 0;
+  const int bn = J % 256 == 0 ? 256 : J % 192 == 0 ? 192 : J % 128 == 0 ? 128 : 64;
+  if (bn == 256) return launch_cfg<tc::Cfg<256, 128, false, true, 64>>(ctx, tmA, tmB, p, 1, st);
+  if (bn == 192) return launch_cfg<tc::Cfg<192, 128, false, true, 64>>(ctx, tmA, tmB, p, 1, st);
+  if (bn == 128) return launch_cfg<tc::Cfg<128, 128, false, true, 64>>(ctx, tmA, tmB, p, 1, st);
+  return launch_cfg<tc::Cfg<64, 128, false, true, 64>>(ctx, tmA, tmB, p, 1, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// dense backward.  dgrad: dx[b][k] = sum_n dy[b][n] w[n][k]  -> D^T[k][b], A = w MN-major, B = dy K-major.
+int a3d_tc_dense_dgrad(a3d_ctx* ctx, const uint16_t* dy, int lddy, const uint16_t* w, uint16_t* dx, float* acc_ws,
+                       int M, int N, int K, cudaStream_t st) {
+  if (K % 8 || lddy % 8 || M > 128 || !acc_ws) {
+    a3d_set_error("tc dense dgrad: needs K %% 8 == 0, lddy %% 8 == 0, batch <= 128, workspace");
+    return A3D_ENOTSUP;
+  }
+  const int bn = M <= 32 ? 32 : M <= 64 ? 64 : 128;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d(ctx, &tmA, w, N, K, K, 64, 64);
+  if (rc) return rc;
+  rc = make_tmap_2d(ctx, &tmB, dy, M, N, lddy, 64, bn);
+  if (rc) return rc;
+  tc::Params p{};
+  p.M = K; p.N = M; p.num_kb = ceil_div(N, 64); p.a_mode = tc::A_TILED;
+  const int tiles = ceil_div(K, 128);
+  int splits = pick_splits(ctx, tiles, p.num_kb, 4);
+  if (splits * tiles < 2 * ctx->sm_count && p.num_kb / (splits * 2) >= 4) splits *= 2;
+  p.kb_per_split = ceil_div(p.num_kb, splits);
+  splits = ceil_div(p.num_kb, p.kb_per_split);
+  A3D_CHECK_CUDA(cudaMemsetAsync(acc_ws, 0, (size_t)M * K * sizeof(float), st));
+  p.epi = tc::EPI_COL_F32; p.out = acc_ws; p.ldo = K; p.atomic = 1;
+  if (bn == 32) rc = launch_cfg<tc::Cfg<32, 128, true, false>>(ctx, tmA, tmB, p, splits, st);
+  else if (bn == 64) rc = launch_cfg<tc::Cfg<64, 128, true, false>>(ctx, tmA, tmB, p, splits, st);
+  else rc = launch_cfg<tc::Cfg<128, 128, true, false>>(ctx, tmA, tmB, p, splits, st);
+  if (rc) return rc;
+  return finish(ctx, acc_ws, nullptr, nullptr, 0.f, dx, 0, (size_t)M, K, K, 0, st);
+}
+
+// wgrad: dw[n][k] = sum_b dy[b][n] x[b][k]; both operands MN-major with the batch as the reduction index.
+int a3d_tc_dense_wgrad(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, int M, int N,
+                       int K, cudaStream_t st) {
+  if (K % 64 || ldx % 8 || lddy % 8) {
+    a3d_set_error("tc dense wgrad: needs K %% 64 == 0 and 16-byte aligned row pitches");
+    return A3D_ENOTSUP;
+  }
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d(ctx, &tmA, dy, M, N, lddy, 64, 64);
+  if (rc) return rc;
+  rc = make_tmap_2d(ctx, &tmB, x, M, K, ldx, 64, 64);
+  if (rc) return rc;
+  tc::Params p{};
+  p.M = N; p.N = K; p.num_kb = ceil_div(M, 64); p.kb_per_split = p.num_kb; p.a_mode = tc::A_TILED;
+  p.epi = tc::EPI_ROW_F32; p.out = dw; p.ldo = K; p.atomic = 0;
+  if (K % 256 == 0) return launch_cfg<tc::Cfg<256, 128, true, true, 64>>(ctx, tmA, tmB, p, 1, st);
+  if (K % 128 == 0) return launch_cfg<tc::Cfg<128, 128, true, true, 64>>(ctx, tmA, tmB, p, 1, st);
+  return launch_cfg<tc::Cfg<64, 128, true, true, 64>>(ctx, tmA, tmB, p, 1, st);
+}
+
 // Raw GEMM for unit tests of the engine: D[M][N] (f32, row-major) = A * B^T with every combination
 // of operand majors.  K-major operand: [rows][K]; MN-major operand: [K][rows].
 extern "C" int a3d_debug_tc_gemm(a3d_ctx* ctx, const uint16_t* A, const uint16_t* B, float* D, int M, int N, int K,

@@ -34,7 +34,11 @@ struct Params {
   int a_mode;
   int a_k0;                 // tiled: first K coordinate
   int PQ, Q, sh, sw, lower_h, lower_w, S, cblocks;   // im2col
-  // B operand addressing: coords (kb*KC, n0) for K-major, (n0, kb*64) for MN-major
+  // B operand addressing: coords (kb*KC, n0) for K-major, (n0, kb*64) for MN-major.
+  // b_im2col (wgrad): B is the im2col view of an NHWC tensor, MN-major: K rows = 64 consecutive output
+  // pixels, N blocks of BW channels; block jb <-> (tap = jb / cblocks, channel block jb % cblocks).
+  int b_im2col;
+  int RS;                   // number of filter taps (b_im2col)
   // epilogue
   int epi;
   void* out;
@@ -44,22 +48,26 @@ struct Params {
   int atomic;               // accumulate with atomicAdd (split-K)
 };
 
-template <int BN_, int KCB_, bool A_MN_, bool B_MN_>
+template <int BN_, int KCB_, bool A_MN_, bool B_MN_, int B_BW_ = 64>
 struct Cfg {
+  static constexpr int B_BW = B_BW_;                     // MN-major B: elements per block (64/32/16)
+  static constexpr int B_BLK_BYTES = 64 * B_BW_ * 2;     // 64 K-rows x BW elements
+  static constexpr int B_NBLK = BN_ / B_BW_;
   static constexpr int BM = 128;
   static constexpr int BN = BN_;
   static constexpr int KCB = KCB_;                       // K-major: bytes of K per row per stage
   static constexpr bool A_MN = A_MN_, B_MN = B_MN_;
   static constexpr int KELEMS = (A_MN_ || B_MN_) ? 64 : KCB_ / 2;   // K elements per stage
   static constexpr int A_BYTES = A_MN_ ? 2 * 8192 : BM * KCB_;
-  static constexpr int B_BYTES = B_MN_ ? (BN_ / 64) * 8192 : BN_ * KCB_;
+  static constexpr int B_BYTES = B_MN_ ? B_NBLK * B_BLK_BYTES : BN_ * KCB_;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = BN_ <= 32 ? 32 : BN_ <= 64 ? 64 : BN_ <= 128 ? 128 : 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(!(A_MN_ || B_MN_) || KCB_ == 128, "MN-major operands use 128-byte rows");
-  static_assert(!B_MN_ || BN_ % 64 == 0, "MN-major B needs BN % 64 == 0");
+  static_assert(!B_MN_ || BN_ % B_BW_ == 0, "MN-major B needs BN % BW == 0");
+  static_assert(B_BW_ == 64 || B_BW_ == 32 || B_BW_ == 16, "MN-major block width");
   static_assert(BN_ % 16 == 0 && BN_ >= 16 && BN_ <= 256, "UMMA N");
 };
 
@@ -137,10 +145,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // ---- B
         if constexpr (!C::B_MN) {
           ptx::tma_load_2d(sB, &tmB, &full_bar[stage], kb * C::KELEMS, n0);
-        } else {
+        } else if (!p.b_im2col) {
 #pragma unroll
-          for (int j = 0; j < C::BN / 64; ++j)
-            ptx::tma_load_2d(sB + j * 8192, &tmB, &full_bar[stage], n0 + j * 64, kb * 64);
+          for (int j = 0; j < C::B_NBLK; ++j)
+            ptx::tma_load_2d(sB + j * C::B_BLK_BYTES, &tmB, &full_bar[stage], n0 + j * C::B_BW, kb * 64);
+        } else {
+          // 64 consecutive output pixels starting at kb*64 -> base coordinates in input space
+          const int mk = kb * 64;
+          const int ni = mk / p.PQ;
+          const int rem = mk - ni * p.PQ;
+          const int pp = rem / p.Q, qq = rem - pp * p.Q;
+          const int hh = p.lower_h + pp * p.sh, ww = p.lower_w + qq * p.sw;
+#pragma unroll 1
+          for (int j = 0; j < C::B_NBLK; ++j) {
+            int jb = blockIdx.y * C::B_NBLK + j;
+            int tap = jb / p.cblocks, cb = jb - tap * p.cblocks;
+            if (tap >= p.RS) tap = p.RS - 1;              // columns beyond N: loaded but never stored
+            int r = tap / p.S, sx = tap - r * p.S;
+            ptx::tma_load_im2col_4d(sB + j * C::B_BLK_BYTES, &tmB, &full_bar[stage], cb * C::B_BW, ww, hh, ni,
+                                    (uint16_t)sx, (uint16_t)r);
+          }
         }
       }
     }
@@ -161,10 +185,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // MN-major: SBO = 1024 (next 8 K-rows), LBO = 8192 (next 64 MN elements) ; K step = 16 rows = 2048 B
         const uint64_t a_desc = C::A_MN ? ptx::make_smem_desc(sA, 8192, 1024, ptx::LAYOUT_SW128)
                                         : ptx::make_smem_desc(sA, 16, 8 * C::KCB, k_layout);
-        const uint64_t b_desc = C::B_MN ? ptx::make_smem_desc(sB, 8192, 1024, ptx::LAYOUT_SW128)
+        // MN-major B with block width BW: row pitch BW*2 bytes, 8-row atom = 16*BW bytes (SBO),
+        // next block of BW columns at 64 rows * BW*2 bytes (LBO), swizzle = row pitch
+        constexpr uint32_t b_mn_layout =
+            C::B_BW == 64 ? ptx::LAYOUT_SW128 : C::B_BW == 32 ? ptx::LAYOUT_SW64 : ptx::LAYOUT_SW32;
+        const uint64_t b_desc = C::B_MN ? ptx::make_smem_desc(sB, C::B_BLK_BYTES, 16 * C::B_BW, b_mn_layout)
                                         : ptx::make_smem_desc(sB, 16, 8 * C::KCB, k_layout);
         constexpr uint32_t a_step = C::A_MN ? (2048 >> 4) : (32 >> 4);
-        constexpr uint32_t b_step = C::B_MN ? (2048 >> 4) : (32 >> 4);
+        constexpr uint32_t b_step = C::B_MN ? ((16 * C::B_BW * 2) >> 4) : (32 >> 4);
 #pragma unroll
         for (int k = 0; k < C::KELEMS / 16; ++k)
           ptx::umma_bf16(tmem_base, a_desc + (uint64_t)(k * a_step), b_desc + (uint64_t)(k * b_step), idesc,

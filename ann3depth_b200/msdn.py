@@ -94,7 +94,7 @@ class MSDNNet:
         assert (self.d_c0.P, self.d_c0.Q) == (55, 74) and (self.d_f1.P, self.d_f1.Q) == (110, 148)
         assert (self.d_c4.P, self.d_c4.Q) == (6, 8)
         if train:
-            self.g_coarse = z(B, N_PIX, **bf)
+            self.g_coarse = z(B, 4096, **bf)             # row stride padded 4070 -> 4096 (16-byte aligned rows)
             self.g_fine = z(B, N_PIX, **bf)
             self.g_d0a, self.g_d0 = z(B, 4096, **bf), z(B, 4096, **bf)
             self.g_c4a, self.g_c4 = z(B, 6, 8, 256, **bf), z(B, 6, 8, 256, **bf)
@@ -169,7 +169,7 @@ class MSDNNet:
                      out=self.fine.view(B, 55, 74, 1))
         # losses (src/models.py:288-290); the gradient of the active branch is produced in the same pass
         c.silog_loss(self.coarse, self.tar, LAMBDA_OVER_N, want_grad=False, loss_ps=self.lps_coarse,
-                     loss=self.loss_coarse, dout_bf16=self.g_coarse if self.train else None)
+                     loss=self.loss_coarse, dout_bf16=self.g_coarse if self.train else None, dout_ld=4096)
         c.silog_loss(self.fine, self.tar, LAMBDA_OVER_N, want_grad=False, loss_ps=self.lps_fine, loss=self.loss_fine,
                      dout_bf16=self.g_fine if self.train else None)
 

@@ -157,7 +157,7 @@ class Context:
         return out
 
     def silog_loss(self, out, tar, lambda_over_n=0.5 / 4070, want_grad=True, grad_bf16=False,
-                   loss_ps=None, loss=None, dout=None, dout_bf16=None):
+                   loss_ps=None, loss=None, dout=None, dout_bf16=None, dout_ld=0):
         B = out.shape[0]
         n = out.numel() // B
         dev = out.device
@@ -168,7 +168,7 @@ class Context:
         if want_grad and grad_bf16 and dout_bf16 is None:
             dout_bf16 = torch.empty(B, n, dtype=torch.bfloat16, device=dev)
         L.check(self.lib.a3d_silog_loss(self.h, _ptr(out), _ptr(tar), B, n, lambda_over_n, _ptr(loss_ps), _ptr(loss),
-                                        _ptr(dout), _ptr(dout_bf16), _stream()), "silog_loss")
+                                        _ptr(dout), _ptr(dout_bf16), dout_ld, _stream()), "silog_loss")
         return loss, loss_ps, dout, dout_bf16
 
     def adam_tf(self, w, g, m, v, w_bf16, lr, beta1, beta2, eps, t, grad_scale=1.0, n=None, lr_t_dev=None):
@@ -251,23 +251,25 @@ class Context:
         return out
 
     def dense_dgrad(self, dy, w, out=None, impl=L.IMPL_AUTO):
-        M = dy.shape[0]
+        """dy may be wider than N (row stride = dy.shape[1]); only the first N columns are used."""
+        M, lddy = dy.shape
         N, K = w.shape
         if out is None:
             out = torch.empty(M, K, dtype=torch.bfloat16, device=dy.device)
         acc = self.workspace(("dense_dacc", M, K), M * K * 4)
-        L.check(self.lib.a3d_dense_dgrad(self.h, _ptr(dy), _ptr(w), _ptr(out), _ptr(acc), M, N, K, impl, _stream()),
-                "dense_dgrad")
+        L.check(self.lib.a3d_dense_dgrad(self.h, _ptr(dy), lddy, _ptr(w), _ptr(out), _ptr(acc), M, N, K, impl,
+                                         _stream()), "dense_dgrad")
         return out
 
-    def dense_wgrad(self, x, dy, dw=None, db=None, impl=L.IMPL_AUTO, ldx=None):
-        M, N = dy.shape
-        K = x.shape[1] if ldx is None else dw.shape[1]
-        ldx = ldx or x.shape[1]
+    def dense_wgrad(self, x, dy, dw=None, db=None, impl=L.IMPL_AUTO, N=None):
+        """dw[N,K] = dy[:, :N]^T x ; dy row stride = dy.shape[1], x row stride = x.shape[1]."""
+        M, lddy = dy.shape
+        N = N if N is not None else (dw.shape[0] if dw is not None else lddy)
+        K = x.shape[1]
         if dw is None:
             dw = torch.empty(N, K, dtype=torch.float32, device=x.device)
-        L.check(self.lib.a3d_dense_wgrad(self.h, _ptr(x), ldx, _ptr(dy), _ptr(dw), _ptr(db), M, N, K, impl, _stream()),
-                "dense_wgrad")
+        L.check(self.lib.a3d_dense_wgrad(self.h, _ptr(x), K, _ptr(dy), lddy, _ptr(dw), _ptr(db), M, N, K, impl,
+                                         _stream()), "dense_wgrad")
         return dw, db
 
     def debug_tc_gemm(self, A, B, M, N, K, bn, kcb=128, a_mn=False, b_mn=False, splits=1):

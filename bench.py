@@ -154,7 +154,7 @@ def per_op_profile(op, torch, reps=3):
                     d = a[1]._obj
                     detail = f"N{d.N} {d.H}x{d.W}x{d.C}->{d.P}x{d.Q}x{d.K} k{d.R}x{d.S} s{d.stride_h}"
                 elif name in ("a3d_dense_fwd", "a3d_dense_dgrad", "a3d_dense_wgrad"):
-                    i0 = {"a3d_dense_fwd": 10, "a3d_dense_dgrad": 5, "a3d_dense_wgrad": 6}[name]
+                    i0 = {"a3d_dense_fwd": 10, "a3d_dense_dgrad": 6, "a3d_dense_wgrad": 7}[name]
                     detail = "MNK=" + "x".join(str(int(x)) for x in a[i0:i0 + 3])
                 records.append((name, detail, e0, e1))
                 return rc

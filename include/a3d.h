@@ -112,11 +112,12 @@ int a3d_conv2d_wgrad(a3d_ctx*, const a3d_conv_desc*, const uint16_t* x, const ui
 int a3d_dense_fwd(a3d_ctx*, const uint16_t* x, int ldx, const uint16_t* w, const float* bias,
                   const uint8_t* keep_mask, float drop_rate, void* y, int y_dtype, float* acc_ws,
                   int M, int N, int K, unsigned flags, int impl, void* stream);
-/* dx[M,K] = dy[M,N] . w[N,K]   (MatMul grad wrt input).  dx bf16, acc_ws f32 [M,K]. */
-int a3d_dense_dgrad(a3d_ctx*, const uint16_t* dy, const uint16_t* w, uint16_t* dx, float* acc_ws,
+/* dx[M,K] = dy[M,N] . w[N,K]   (MatMul grad wrt input).  dy bf16 with row stride lddy (a multiple of 8
+ * elements for the tensor-core path), dx bf16 [M,K], acc_ws f32 [M,K]. */
+int a3d_dense_dgrad(a3d_ctx*, const uint16_t* dy, int lddy, const uint16_t* w, uint16_t* dx, float* acc_ws,
                     int M, int N, int K, int impl, void* stream);
 /* dw[N,K] = dy[M,N]^T . x[M,K] ; db[N] = sum_M dy.   dw/db f32, overwritten. */
-int a3d_dense_wgrad(a3d_ctx*, const uint16_t* x, int ldx, const uint16_t* dy, float* dw, float* db,
+int a3d_dense_wgrad(a3d_ctx*, const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, float* db,
                     int M, int N, int K, int impl, void* stream);
 /* Elementwise backward of the dense epilogue: g_pre = g_post * mask/(1-rate) * act'(y).
  * y is the stored post-activation (pre-dropout) output; used between dense_1 dgrad and dense_0. */
@@ -149,11 +150,12 @@ int a3d_relu_bwd(a3d_ctx*, const uint16_t* y, const uint16_t* dy, int lddy, uint
 
 /* ---- scale-invariant log loss (src/models.py:255-275) + its gradient ------------------------ */
 /* out,tar f32 [B,n]; loss_per_sample f32 [B]; loss f32 [1] (batch mean);
- * dout (nullable) = d loss / d out, written as f32 and/or bf16 (either pointer may be null).
+ * dout (nullable) = d loss / d out, written as f32 and/or bf16 (either pointer may be null) with row
+ * stride dout_ld elements (0 = n; the padded stride keeps rows 16-byte aligned for TMA consumers).
  * lambda_over_n is the constant `lambd / (74*55)` of the reference. */
 int a3d_silog_loss(a3d_ctx*, const float* out, const float* tar, int B, int n, float lambda_over_n,
                    float* loss_per_sample, float* loss, float* dout_f32, uint16_t* dout_bf16,
-                   void* stream);
+                   int dout_ld, void* stream);
 
 /* ---- optimizers (src/models.py:307-345 Adam x4, :198-200 SGD) ------------------------------- */
 /* TF1 ApplyAdam on a flat segment: m = b1*m+(1-b1)*g ; v = b2*v+(1-b2)*g^2 ;

@@ -102,6 +102,12 @@ LAYERS = [
     ("dcnf_conv2d_2", 20, 20, 256, 256, 3, 3, 1, "valid"),
     ("c16_k32", 17, 19, 16, 32, 3, 3, 1, "same"),
 ]
+# 3-channel first layers as the B200 path stores them: 4-channel pixels, filter width padded so that
+# groups of 16/C pixels can be read as one 16-channel pixel (conv.cu `virtualize`)
+PACKED_LAYERS = [
+    ("conv2d_0_packed", 228, 304, 4, 96, 11, 12, 4, "valid"),
+    ("fine_first_packed", 228, 304, 4, 64, 9, 10, 2, "valid"),
+]
 SMALL_C_LAYERS = [
     ("conv2d_0", 228, 304, 3, 96, 11, 11, 4, "valid"),
     ("fine_first", 228, 304, 3, 63, 9, 9, 2, "valid"),
@@ -137,6 +143,24 @@ def test_conv_fwd_small_channels(ctx, layer):
     yf = ctx.conv2d_fwd(d, x, w, None, relu=False, out_dtype=torch.float32)
     ref = torch_conv_ref(x, w, None, stride, d.pad_t, d.pad_l, d.P, d.Q, False)
     assert rel_err(yf, ref) < 2e-3
+
+
+@pytest.mark.parametrize("layer", PACKED_LAYERS, ids=[l[0] for l in PACKED_LAYERS])
+def test_conv_packed_first_layers(ctx, layer):
+    name, H, W, Cc, K, R, S, stride, padding = layer
+    N = 2
+    d = ops.conv_desc(N, H, W, Cc, K, R, S, stride, padding, impl=L.IMPL_AUTO)
+    x = bf16_rand(N, H, W, Cc, seed=17)
+    w = bf16_rand(K, R, S, Cc, seed=18, scale=1.0 / math.sqrt(R * S * Cc))
+    yf = ctx.conv2d_fwd(d, x, w, None, relu=False, out_dtype=torch.float32)
+    ref = torch_conv_ref(x, w, None, stride, d.pad_t, d.pad_l, d.P, d.Q, False)
+    assert rel_err(yf, ref) < 2e-3
+    dy = bf16_rand(N, d.P, d.Q, K, seed=19)
+    wr = w.float().requires_grad_(True)
+    yr = F.conv2d(x.float().permute(0, 3, 1, 2), wr.permute(0, 3, 1, 2), None, stride=stride)
+    (gw,) = torch.autograd.grad(yr, wr, dy.float().permute(0, 3, 1, 2))
+    dw, _ = ctx.conv2d_wgrad(d, x, dy)
+    assert rel_err(dw, gw) < 2e-3
 
 
 def test_conv_fwd_concat_stride(ctx):
@@ -192,17 +216,29 @@ def test_dense_fwd(ctx, impl, M, N, K):
     assert rel_err(y2, x.float() @ w.float().t() + bias) < 2e-3
 
 
-@pytest.mark.parametrize("M,N,K", [(32, 4070, 4096), (6, 130, 200)])
-def test_dense_bwd(ctx, M, N, K):
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("M,N,K,ld", [(32, 4070, 4096, 4096), (32, 4096, 12288, 4096), (6, 136, 256, 136)])
+def test_dense_bwd(ctx, M, N, K, ld, impl):
+    code = L.IMPL_SIMT if impl == "simt" else L.IMPL_TC
     x = bf16_rand(M, K, seed=34)
     w = bf16_rand(N, K, seed=35, scale=1.0 / math.sqrt(K))
-    dy = bf16_rand(M, N, seed=36)
-    dx = ctx.dense_dgrad(dy, w)
+    dyp = torch.zeros(M, ld, dtype=torch.bfloat16, device=DEV)     # padded row stride
+    dyp[:, :N] = bf16_rand(M, N, seed=36)
+    dy = dyp[:, :N]
+    dx = ctx.dense_dgrad(dyp, w, impl=code)
     assert rel_err(dx, dy.float() @ w.float()) < 1e-2
     db = torch.empty(N, dtype=torch.float32, device=DEV)
-    dw, _ = ctx.dense_wgrad(x, dy, db=db)
+    dw, _ = ctx.dense_wgrad(x, dyp, db=db, N=N, impl=code)
     assert rel_err(dw, dy.float().t() @ x.float()) < 2e-3
     assert rel_err(db, dy.float().sum(0)) < 2e-3
+
+
+def test_dense_bwd_unaligned_falls_back(ctx):
+    M, N, K = 6, 130, 200
+    x, w, dy = bf16_rand(M, K, seed=34), bf16_rand(N, K, seed=35, scale=0.1), bf16_rand(M, N, seed=36)
+    assert rel_err(ctx.dense_dgrad(dy, w), dy.float() @ w.float()) < 1e-2
+    dw, _ = ctx.dense_wgrad(x, dy)
+    assert rel_err(dw, dy.float().t() @ x.float()) < 2e-3
 
 
 # ----------------------------------------------------------------------------- elementwise

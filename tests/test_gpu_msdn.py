@@ -158,16 +158,16 @@ def test_train_step_reference_adam_freezes_weights():
 
 
 def test_train_step_general_adam_matches_oracle():
-    """A sane beta2: weights after two phase-1 steps match the oracle's TF-Adam."""
+    """A sane beta2: Adam slots and weights after one phase-1 step match the oracle's TF-Adam.
+    (One step only: with the reference's lr = 0.1 on the dense group the first sign-like update moves
+    every dense weight by 0.1, after which the trajectory is chaotic in any arithmetic.)"""
     B = 2
     images, depths, mask = make_inputs(B)
     p = conditioned_params()
     op = build(B, p, mask, images, depths, beta2=0.999)
     op.run(use_graph=False)
-    op.run(use_graph=False)
     torch.cuda.synchronize()
     st = OM.TrainState({k: v.double() for k, v in p.items()}, beta2=0.999)
-    OM.train_step(st, images.double(), depths.double(), mask.double(), q=OM.bf16_round)
     OM.train_step(st, images.double(), depths.double(), mask.double(), q=OM.bf16_round)
     got = op.net.export_params()
     got_m = op.net.arena.export_tf(op.net.arena.m)
@@ -179,9 +179,12 @@ def test_train_step_general_adam_matches_oracle():
         cm, cv = cos(got_m[name], st.m[name]), cos(got_v[name], st.v[name])
         print(name, "update cosine", cos(d1, d0), "m cosine", cm, "v cosine", cv, "max |dw|", float(d0.abs().max()))
         assert cm > 0.999 and cv > 0.995, name
-        assert cos(d1, d0) > 0.9, name              # sign-like early Adam updates: element-wise agreement
+        assert cos(d1, d0) > 0.97, name             # first Adam step ~ lr * sign(g): element-wise agreement
         assert abs(float(d1.abs().max()) / float(d0.abs().max()) - 1) < 0.05, name
     assert torch.equal(got["fine/third/kernel"], p["fine/third/kernel"])
+    op.run(use_graph=False)                          # a second step stays finite
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(op.net.arena.w).all()) and op.global_step == 2
 
 
 def test_phase_schedule_and_inference():
