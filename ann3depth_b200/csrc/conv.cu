@@ -31,13 +31,17 @@ static int check_desc(const a3d_conv_desc* d) {
 // If the horizontal stride is a multiple of g = 16/C pixels, g adjacent pixels can be read as ONE
 // pixel of g*C channels of a [N, H, W/g, g*C] tensor: the filter [K,R,S,C] is then the same memory
 // as [K,R,S/g,g*C] and the stride becomes stride_w/g.  (MSDN conv2d_0: 11x12x4 s4 -> 11x3x16 s1.)
+// With stride_w only a multiple of 8/C pixels the group is 8 channels wide (MSDN fine/first:
+// 9x10x4 s2 -> 9x5x8 s1), which the engine takes in its chunked no-swizzle mode.
 static bool virtualize(const a3d_conv_desc* d, a3d_conv_desc* v) {
   if (d->C >= 16 || 16 % d->C) return false;
-  int g = 16 / d->C;
-  if (d->stride_w % g || d->W % g || d->S % g || d->pad_l != 0) return false;
-  *v = *d;
-  v->C = d->C * g; v->W = d->W / g; v->S = d->S / g; v->stride_w = d->stride_w / g;
-  return true;
+  for (int g = 16 / d->C; g * d->C >= 8 && g >= 2; g /= 2) {
+    if (d->stride_w % g || d->W % g || d->S % g || d->pad_l != 0) continue;
+    *v = *d;
+    v->C = d->C * g; v->W = d->W / g; v->S = d->S / g; v->stride_w = d->stride_w / g;
+    return true;
+  }
+  return false;
 }
 
 // dgrad of a stride-1 conv == forward conv of dy with the spatially flipped, channel-transposed filter
@@ -164,7 +168,10 @@ extern "C" int a3d_conv2d_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
   if (d->impl == A3D_IMPL_SIMT) return a3d_simt_conv_fwd(ctx, d, x, w, bias, y, y_dtype, flags, st);
-  if (d->K == 1 && d->C % 64 == 0 && (size_t)d->R * d->S * d->C * 4 <= 48 * 1024) {
+  a3d_conv_desc v;
+  const a3d_conv_desc* e = virtualize(d, &v) ? &v : d;
+  if (a3d_tc_conv_fwd_supported(e)) return a3d_tc_conv_fwd(ctx, e, x, w, bias, y, y_dtype, flags, ws, ws_bytes, st);
+  if (d->K == 1 && d->C % 64 == 0 && d->impl == A3D_IMPL_AUTO && (size_t)d->R * d->S * d->C * 4 <= 48 * 1024) {
     long long pixels = (long long)d->N * d->P * d->Q;
     int block = 256, grid = (int)((pixels + 7) / 8);
     if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
@@ -174,9 +181,6 @@ extern "C" int a3d_conv2d_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16
     A3D_LAUNCH_OK(ctx);
     return 0;
   }
-  a3d_conv_desc v;
-  const a3d_conv_desc* e = virtualize(d, &v) ? &v : d;
-  if (a3d_tc_conv_fwd_supported(e)) return a3d_tc_conv_fwd(ctx, e, x, w, bias, y, y_dtype, flags, ws, ws_bytes, st);
   if (d->impl == A3D_IMPL_TC) {
     a3d_set_error("conv fwd: shape not supported by the tcgen05 path (C=%d K=%d)", d->C, d->K);
     return A3D_ENOTSUP;

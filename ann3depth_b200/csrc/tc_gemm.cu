@@ -43,6 +43,29 @@ int make_tmap_2d(a3d_ctx* ctx, CUtensorMap* tm, const void* base, uint64_t rows,
   return 0;
 }
 
+// Weight matrix [rows][ktot] viewed as {8, rows, ktot/8}: one box = 8 chunks x box_rows rows x 8 elements,
+// landing chunk-major in shared memory (the "chunked" no-swizzle K-major layout of tc_gemm.cuh).
+int make_tmap_chunked(a3d_ctx* ctx, CUtensorMap* tm, const void* base, uint64_t rows, uint64_t ktot, uint32_t box_rows) {
+  cuuint64_t dims[3] = {8, rows, ktot / 8};
+  cuuint64_t strides[2] = {ktot * 2, 16};
+  cuuint32_t box[3] = {8, box_rows, 8};
+  cuuint32_t estr[3] = {1, 1, 1};
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides[0] & 15) || (ktot % 8)) {
+    a3d_set_error("chunked tensor map: base / row pitch not 16-byte aligned (ktot=%llu)", (unsigned long long)ktot);
+    return A3D_EINVAL;
+  }
+  CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->fn_encode_tiled)(
+      tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    a3d_set_error("cuTensorMapEncodeTiled(chunked) failed (%d): rows=%llu ktot=%llu", (int)r, (unsigned long long)rows,
+                  (unsigned long long)ktot);
+    return A3D_ETMAP;
+  }
+  return 0;
+}
+
 // bf16 NHWC activation tensor in im2col mode.  Base pixels run over lower + {0..P-1} * stride per axis.
 int make_tmap_im2col(a3d_ctx* ctx, CUtensorMap* tm, const void* base, int N, int H, int W, int C, int lower_h,
                      int lower_w, int P, int Q, int sh, int sw, uint32_t chan_box, uint32_t pixels) {
@@ -104,12 +127,15 @@ int launch_kk(a3d_ctx* ctx, int bn, int kcb, const CUtensorMap& tmA, const CUten
   A3D_CASE(32, 128) A3D_CASE(64, 128) A3D_CASE(96, 128) A3D_CASE(128, 128) A3D_CASE(192, 128) A3D_CASE(256, 128)
   A3D_CASE(32, 64) A3D_CASE(64, 64) A3D_CASE(96, 64) A3D_CASE(128, 64) A3D_CASE(192, 64) A3D_CASE(256, 64)
   A3D_CASE(32, 32) A3D_CASE(64, 32) A3D_CASE(96, 32) A3D_CASE(128, 32) A3D_CASE(256, 32)
+  A3D_CASE(16, 128) A3D_CASE(16, 64) A3D_CASE(16, 32)
+  A3D_CASE(32, 16) A3D_CASE(64, 16) A3D_CASE(96, 16) A3D_CASE(128, 16)
 #undef A3D_CASE
   a3d_set_error("tc gemm: no kernel for BN=%d KCB=%d", bn, kcb);
   return A3D_ENOTSUP;
 }
 
 int pick_bn(int n) {
+  if (n <= 16) return 16;
   if (n <= 32) return 32;
   if (n <= 64) return 64;
   if (n <= 96) return 96;
@@ -162,10 +188,10 @@ int finish(a3d_ctx* ctx, const float* acc, const float* bias, const uint8_t* mas
 // ------------------------------------------------------------------------------------------------
 // convolution forward as an implicit GEMM: M = N*P*Q output pixels, N = K filters, K = R*S*C
 int a3d_tc_conv_fwd_supported(const a3d_conv_desc* d) {
-  if (d->C % 16) return 0;                       // im2col box needs >= 32 B of channels per pixel
+  if (d->C % 8) return 0;                        // im2col box needs >= 16 B of channels per pixel
+  if (d->C % 16 && d->K > 128) return 0;         // 8-channel "chunked" kernels exist for K <= 128 only
   if (d->stride_h > 8 || d->stride_w > 8) return 0;
   if (d->R > 256 || d->S > 256) return 0;
-  if (d->ldy % 8) return 0;
   return 1;
 }
 
@@ -180,17 +206,20 @@ int a3d_tc_conv_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, con
     a3d_set_error("tc conv fwd: unsupported shape (C=%d must be a multiple of 16)", d->C);
     return A3D_ENOTSUP;
   }
-  const int kc = d->C % 64 == 0 ? 64 : d->C % 32 == 0 ? 32 : 16;   // channels per k-block
+  // channels per TMA load: 64/32/16 -> swizzled rows of 128/64/32 B; 8 -> chunked mode (8 loads per stage)
+  const int kc = d->C % 64 == 0 ? 64 : d->C % 32 == 0 ? 32 : d->C % 16 == 0 ? 16 : 8;
   const int kcb = kc * 2;
   const int cblocks = d->C / kc;
-  const int num_kb = d->R * d->S * cblocks;
+  const int num_kb = kc == 8 ? ceil_div(d->R * d->S * cblocks, 8) : d->R * d->S * cblocks;
   const long long M = (long long)d->N * d->P * d->Q;
-  const int bn = pick_bn(d->K);
+  int bn = pick_bn(d->K);
+  if (kc == 8 && bn < 32) bn = 32;
   CUtensorMap tmA, tmB;
   int rc = make_tmap_im2col(ctx, &tmA, x, d->N, d->H, d->W, d->C, -d->pad_t, -d->pad_l, d->P, d->Q, d->stride_h,
                             d->stride_w, kc, 128);
   if (rc) return rc;
-  rc = make_tmap_2d(ctx, &tmB, w, d->K, (uint64_t)d->R * d->S * d->C, (uint64_t)d->R * d->S * d->C, kc, bn);
+  if (kc == 8) rc = make_tmap_chunked(ctx, &tmB, w, d->K, (uint64_t)d->R * d->S * d->C, bn);
+  else rc = make_tmap_2d(ctx, &tmB, w, d->K, (uint64_t)d->R * d->S * d->C, (uint64_t)d->R * d->S * d->C, kc, bn);
   if (rc) return rc;
   tc::Params p{};
   p.M = (int)M; p.N = d->K; p.num_kb = num_kb;

@@ -13,6 +13,9 @@
 //   K-major  : tile rows = M (or N) index, each row KCB bytes of K (128/64/32 -> SWIZZLE_128B/64B/32B)
 //   MN-major : tile rows = K index (64 per stage), each row 128 B = 64 consecutive M (or N) elements,
 //              one 8 KB block per 64 columns (SWIZZLE_128B)
+//   K-major, KCB = 16 ("chunked", no swizzle): for tensors with only 8 channels per (virtual) pixel.
+//              A stage holds 8 chunks of 8 K-elements; chunk j = rows x 16 B, i.e. contiguous 128-byte
+//              core matrices (8 rows x 16 B).  Two adjacent chunks form one UMMA K = 16 step (LBO = chunk).
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"
@@ -57,9 +60,11 @@ struct Cfg {
   static constexpr int BN = BN_;
   static constexpr int KCB = KCB_;                       // K-major: bytes of K per row per stage
   static constexpr bool A_MN = A_MN_, B_MN = B_MN_;
-  static constexpr int KELEMS = (A_MN_ || B_MN_) ? 64 : KCB_ / 2;   // K elements per stage
-  static constexpr int A_BYTES = A_MN_ ? 2 * 8192 : BM * KCB_;
-  static constexpr int B_BYTES = B_MN_ ? B_NBLK * B_BLK_BYTES : BN_ * KCB_;
+  static constexpr bool CHUNKED = (KCB_ == 16);           // 8 chunks of 16 B per stage, no swizzle
+  static constexpr int KELEMS = (A_MN_ || B_MN_ || CHUNKED) ? 64 : KCB_ / 2;   // K elements per stage
+  static constexpr int A_BYTES = A_MN_ ? 2 * 8192 : CHUNKED ? 8 * BM * 16 : BM * KCB_;
+  static constexpr int B_BYTES = B_MN_ ? B_NBLK * B_BLK_BYTES : CHUNKED ? 8 * BN_ * 16 : BN_ * KCB_;
+  static_assert(!CHUNKED || (!A_MN_ && !B_MN_), "chunked mode is K-major only");
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -128,7 +133,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         uint8_t* sB = sA + C::A_BYTES;
         ptx::mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
         // ---- A
-        if constexpr (!C::A_MN) {
+        if constexpr (C::CHUNKED) {
+          // 8 im2col loads of 128 pixels x 8 channels (one per tap / channel-chunk), one 3-D load of B
+#pragma unroll 1
+          for (int j = 0; j < 8; ++j) {
+            int ch = kb * 8 + j;
+            int tap = ch / p.cblocks, cb = ch - tap * p.cblocks;
+            int r = tap / p.S, sx = tap - r * p.S;      // taps beyond the filter meet zero-filled weights
+            ptx::tma_load_im2col_4d(sA + j * (C::BM * 16), &tmA, &full_bar[stage], cb * 8, w0, h0, n_img, (uint16_t)sx,
+                                    (uint16_t)r);
+          }
+          ptx::tma_load_3d(sB, &tmB, &full_bar[stage], 0, n0, kb * 8);
+        } else if constexpr (!C::A_MN) {
           if (p.a_mode == A_TILED) {
             ptx::tma_load_2d(sA, &tmA, &full_bar[stage], p.a_k0 + kb * C::KELEMS, m0);
           } else {
@@ -143,7 +159,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           ptx::tma_load_2d(sA + 8192, &tmA, &full_bar[stage], m0 + 64, kb * 64);
         }
         // ---- B
-        if constexpr (!C::B_MN) {
+        if constexpr (C::CHUNKED) {
+          // loaded above
+        } else if constexpr (!C::B_MN) {
           ptx::tma_load_2d(sB, &tmB, &full_bar[stage], kb * C::KELEMS, n0);
         } else if (!p.b_im2col) {
 #pragma unroll
@@ -183,16 +201,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const uint32_t sB = sA + C::A_BYTES;
         // K-major : SBO = 8 rows * KCB bytes, LBO unused (1) ; K step = 32 B inside the swizzled row
         // MN-major: SBO = 1024 (next 8 K-rows), LBO = 8192 (next 64 MN elements) ; K step = 16 rows = 2048 B
-        const uint64_t a_desc = C::A_MN ? ptx::make_smem_desc(sA, 8192, 1024, ptx::LAYOUT_SW128)
-                                        : ptx::make_smem_desc(sA, 16, 8 * C::KCB, k_layout);
+        const uint64_t a_desc = C::A_MN      ? ptx::make_smem_desc(sA, 8192, 1024, ptx::LAYOUT_SW128)
+                                : C::CHUNKED ? ptx::make_smem_desc(sA, C::BM * 16, 128, ptx::LAYOUT_NONE)
+                                             : ptx::make_smem_desc(sA, 16, 8 * C::KCB, k_layout);
         // MN-major B with block width BW: row pitch BW*2 bytes, 8-row atom = 16*BW bytes (SBO),
         // next block of BW columns at 64 rows * BW*2 bytes (LBO), swizzle = row pitch
         constexpr uint32_t b_mn_layout =
             C::B_BW == 64 ? ptx::LAYOUT_SW128 : C::B_BW == 32 ? ptx::LAYOUT_SW64 : ptx::LAYOUT_SW32;
-        const uint64_t b_desc = C::B_MN ? ptx::make_smem_desc(sB, C::B_BLK_BYTES, 16 * C::B_BW, b_mn_layout)
-                                        : ptx::make_smem_desc(sB, 16, 8 * C::KCB, k_layout);
-        constexpr uint32_t a_step = C::A_MN ? (2048 >> 4) : (32 >> 4);
-        constexpr uint32_t b_step = C::B_MN ? ((16 * C::B_BW * 2) >> 4) : (32 >> 4);
+        const uint64_t b_desc = C::B_MN      ? ptx::make_smem_desc(sB, C::B_BLK_BYTES, 16 * C::B_BW, b_mn_layout)
+                                : C::CHUNKED ? ptx::make_smem_desc(sB, C::BN * 16, 128, ptx::LAYOUT_NONE)
+                                             : ptx::make_smem_desc(sB, 16, 8 * C::KCB, k_layout);
+        constexpr uint32_t a_step = C::A_MN ? (2048 >> 4) : C::CHUNKED ? ((2 * C::BM * 16) >> 4) : (32 >> 4);
+        constexpr uint32_t b_step =
+            C::B_MN ? ((16 * C::B_BW * 2) >> 4) : C::CHUNKED ? ((2 * C::BN * 16) >> 4) : (32 >> 4);
 #pragma unroll
         for (int k = 0; k < C::KELEMS / 16; ++k)
           ptx::umma_bf16(tmem_base, a_desc + (uint64_t)(k * a_step), b_desc + (uint64_t)(k * b_step), idesc,
