@@ -60,7 +60,10 @@ SIGNATURES = {
     "a3d_scatter_channel_bf16": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp]),
     "a3d_fill_zero": (_i, [_vp, _vp, _sz, _vp]),
     "a3d_apply_mask_f32": (_i, [_vp, _vp, _vp, _sz, _vp]),
-    "a3d_crf_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "a3d_crf_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "a3d_pairwise_dense": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "a3d_mean_f32": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "a3d_scale_cast_bf16": (_i, [_vp, _vp, _vp, _sz, _f, _vp]),
     "a3d_pairwise_features": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _f, _vp, _vp, _vp]),
     "a3d_pairwise_ws_bytes": (_sz, [_i, _i, _i]),
     "a3d_tile_means": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),

@@ -1,0 +1,180 @@
+"""Train driver: the B200 counterpart of the reference's `src/ann3depth.py`.
+
+Same CLI (`dataset --model --steps --batchsize --ckptdir --id --ckptfreq --sumfreq --datadir --timeout`,
+src/ann3depth.py:221-254) and the same loop shape: build the model op once (`setup_model`, :134-145), then
+`while not should_stop: run(op)` (:126-127) under stop-at-step / stop-at-signal hooks, periodic
+checkpoints with resume (MonitoredTrainingSession, :113-125) and loss summaries (:103-104).
+The cluster flags (`--cluster-spec --job-name --task-index`) are accepted and ignored: the
+parameter-server cluster (:39-67, :78-92) is replaced by one process per GPU
+(`torchrun --nproc-per-node N -m ann3depth_b200.ann3depth ...`; RANK / WORLD_SIZE / LOCAL_RANK from
+the environment) with an NCCL gradient allreduce.  Exit code = number of the signal that stopped the
+run, 0 otherwise (:129).
+"""
+from __future__ import annotations
+
+import argparse
+import logging
+import os
+import signal
+import sys
+import time
+
+import torch
+
+from . import data, models
+from .init import glorot_params
+
+logger = logging.getLogger("ann3depth")
+
+
+class StopAtSignalHook:
+    """src/tfhelper.py:160-189: remember the signal, request a stop after the current step."""
+
+    def __init__(self, signals=None):
+        self.signal_received = 0
+        for s in signals or [signal.SIGUSR1, signal.SIGUSR2, signal.SIGALRM, signal.SIGINT, signal.SIGTERM]:
+            signal.signal(s, self._handler)
+
+    def _handler(self, signum, frame):
+        self.signal_received = signum
+
+
+class TraceHook:
+    """src/tfhelper.py:192-249: trace the first step after a (re)start and every N-th step.  Here a
+    trace is the per-kernel CUDA-event timeline of one un-graphed step, written as JSON."""
+
+    def __init__(self, ckptdir, every_step=5000):
+        self.ckptdir, self.every, self._trace = ckptdir, every_step, True
+
+    def wants_trace(self):
+        return self._trace
+
+    def after_run(self, global_step):
+        self._trace = not ((global_step + 1) % self.every)
+
+
+def save_checkpoint(op, ckptdir):
+    os.makedirs(ckptdir, exist_ok=True)
+    net = op.net
+    state = {"w": net.arena.w.cpu(), "global_step": net.global_step}
+    if net.arena.m is not None:
+        state.update(m=net.arena.m.cpu(), v=net.arena.v.cpu())
+    if hasattr(net, "adam_t"):
+        state["adam_t"] = dict(net.adam_t)
+    tmp = os.path.join(ckptdir, "model.ckpt.tmp")
+    torch.save(state, tmp)
+    os.replace(tmp, os.path.join(ckptdir, "model.ckpt"))
+
+
+def restore_checkpoint(op, ckptdir):
+    path = os.path.join(ckptdir, "model.ckpt")
+    if not os.path.exists(path):
+        return False
+    state = torch.load(path, map_location="cpu")
+    net = op.net
+    net.arena.w.copy_(state["w"])
+    net.arena.wb.copy_(net.arena.w)
+    if "m" in state and net.arena.m is not None:
+        net.arena.m.copy_(state["m"])
+        net.arena.v.copy_(state["v"])
+    net.global_step = int(state["global_step"])
+    if hasattr(net, "step_dev"):
+        net.step_dev.fill_(net.global_step)
+    if "adam_t" in state and hasattr(net, "adam_t"):
+        net.adam_t.update(state["adam_t"])
+    return True
+
+
+def setup_model(args, comm=None):
+    """src/ann3depth.py:134-145."""
+    model = getattr(models, args.model)
+    inp = data.inputs(args.datadir, args.dataset, args.batchsize, seed=100 + int(os.environ.get("RANK", 0)))
+    op = model(inp.images, inp.depths, comm=comm)
+    op.net.load_params(glorot_params(seed=1, model=args.model))
+    return op, inp
+
+
+def main(argv=None):
+    logging.basicConfig(level=logging.DEBUG, stream=sys.stdout,
+                        format="%(asctime)s %(name)s %(levelname)s %(message)s")
+    args = parse_args(argv)
+    logger.debug(args)
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank)
+    chief = rank == 0
+    logger.info(f"This is rank {rank} of {world} -- Chief? {chief}")
+
+    comm = None
+    if world > 1:
+        import torch.distributed as dist
+        from . import ops
+        from .dp import DataParallel
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        ids = [ops.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        comm = DataParallel(models.get_context(local_rank), rank, world, ids[0])
+
+    run_id = args.model + ("" if not args.id else f"_{args.id}")
+    ckptdir = str(os.path.join(args.ckptdir, run_id))
+    logger.info(f"Checkpoint dir is {ckptdir}.")
+    logger.info(f"Loading model {args.model}.")
+    op, inp = setup_model(args, comm)
+    size_train = op.net.arena.num_real_params() * 4 / 1024 / 1024          # tfhelper.estimate_size_of
+    logger.debug(f"Trainable variables have about {size_train:.1f} MB")
+    if restore_checkpoint(op, ckptdir):
+        logger.info(f"Restored checkpoint at global step {op.global_step}.")
+
+    stop_hook = StopAtSignalHook()
+    trace_hook = TraceHook(ckptdir, 5000)
+    if args.timeout:
+        logger.info(f"Starting alarm: {args.timeout} s timeout.")
+        signal.alarm(args.timeout)
+
+    logger.info("Starting session.")
+    last_ckpt = last_log = time.time()
+    last_log_step = op.global_step
+    while op.global_step < args.steps and not stop_hook.signal_received:       # StopAtStepHook(last_step)
+        inp.next_batch()
+        op.run(use_graph=not trace_hook.wants_trace())
+        trace_hook.after_run(op.global_step - 1)
+        if op.global_step % args.sumfreq == 0:
+            torch.cuda.synchronize()
+            now = time.time()
+            losses = {k: float(v) for k, v in op.losses.items()}
+            rate = (op.global_step - last_log_step) / max(now - last_log, 1e-9)
+            logger.info(f"step {op.global_step} losses {losses} global_step/sec {rate:.2f} "
+                        f"images/sec {rate * args.batchsize * world:.1f}")
+            last_log, last_log_step = now, op.global_step
+        if chief and time.time() - last_ckpt > args.ckptfreq:
+            torch.cuda.synchronize()
+            save_checkpoint(op, ckptdir)
+            last_ckpt = time.time()
+    torch.cuda.synchronize()
+    if chief:
+        save_checkpoint(op, ckptdir)
+    logger.info("Session stopped.")
+    return stop_hook.signal_received
+
+
+def parse_args(argv=None):
+    """src/ann3depth.py:221-254 -- same flags and defaults."""
+    parser = argparse.ArgumentParser()
+    parser.add_argument("dataset", default="nyu", type=str, nargs="?", help="The dataset to use.")
+    parser.add_argument("--model", "-m", default="msdn", type=str, help="Enter a model name.")
+    parser.add_argument("--steps", "-s", default=1000000, type=int, help="Total steps")
+    parser.add_argument("--batchsize", "-b", default=32, type=int, help="Batchsize")
+    parser.add_argument("--ckptdir", "-p", default="checkpoints", help="Checkpoint directory")
+    parser.add_argument("--id", default="", type=str, help="Checkpoint path suffix.")
+    parser.add_argument("--ckptfreq", "-f", default=900, type=int, help="Create a checkpoint every N seconds.")
+    parser.add_argument("--sumfreq", "-r", default=100, type=int, help="Create a summary every N steps.")
+    parser.add_argument("--datadir", "-d", default="data", type=str, help="The data directory containing the datasets.")
+    parser.add_argument("--timeout", "-k", default=4200, type=int, help="The time after which the process dies.")
+    parser.add_argument("--cluster-spec", default="", type=str, help="(ignored: no parameter servers)")
+    parser.add_argument("--job-name", default="local", type=str, help="(ignored)")
+    parser.add_argument("--task-index", default=0, type=int, help="(ignored)")
+    return parser.parse_args(argv)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -149,13 +149,21 @@ __global__ void conv_k1_fwd_kernel(const uint16_t* __restrict__ x, const uint16_
 
 static size_t filt_bytes(const a3d_conv_desc* d) { return ((size_t)d->K * d->R * d->S * d->C * 2 + 255) & ~(size_t)255; }
 
+// split-K (and with it the f32 accumulation buffer) is only chosen when the output has far fewer
+// 128x128 tiles than the GPU has SMs (tc_gemm.cu pick_splits)
+static size_t splitk_bytes(a3d_ctx* ctx, long long rows, int cols) {
+  long long tiles = ((rows + 127) / 128) * ((cols + 127) / 128);
+  int sms = ctx ? ctx->sm_count : 148;
+  return tiles >= sms * 3 / 4 ? 0 : (size_t)rows * cols * sizeof(float);
+}
+
 extern "C" size_t a3d_conv2d_ws_bytes(a3d_ctx* ctx, const a3d_conv_desc* d, int op) {
   if (!d) return 0;
-  if (op == A3D_OP_FWD) return (size_t)d->N * d->P * d->Q * d->K * sizeof(float);
+  if (op == A3D_OP_FWD) return splitk_bytes(ctx, (long long)d->N * d->P * d->Q, d->K);
   if (op == A3D_OP_DGRAD) {
-    size_t a = filt_bytes(d) + (size_t)d->N * d->H * d->W * d->C * sizeof(float);          // stride-1 path
-    size_t b = (size_t)d->N * d->P * d->Q * d->R * d->S * d->C * sizeof(float);            // cols path
-    return a > b ? a : b;
+    if (dgrad_as_fwd_ok(d)) return filt_bytes(d) + splitk_bytes(ctx, (long long)d->N * d->H * d->W, d->C);
+    if (dgrad_as_cols_ok(d)) return (size_t)d->N * d->P * d->Q * d->R * d->S * d->C * sizeof(float);
+    return 0;
   }
   return 0;
 }

@@ -22,7 +22,7 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 __global__ void __launch_bounds__(CRF_THREADS)
 crf_kernel(const float* __restrict__ z_, const float* __restrict__ y_, const float* __restrict__ r_,
            const int32_t* __restrict__ pl, const int32_t* __restrict__ pr, int n, int n_pairs, float grad_scale,
-           float* __restrict__ ystar_, float* __restrict__ nll_, float* __restrict__ logdet_, float* __restrict__ dz_,
+           int naive, float* __restrict__ ystar_, float* __restrict__ nll_, float* __restrict__ logdet_, float* __restrict__ dz_,
            float* __restrict__ dr_, int32_t* __restrict__ status_) {
   extern __shared__ float sm[];
   const int ld = n + 1;
@@ -118,9 +118,22 @@ crf_kernel(const float* __restrict__ z_, const float* __restrict__ y_, const flo
   for (int i = tid; i < n; i += nt) q += w[i] * w[i];
   const float quad = block_sum(q, red);
   const bool ok = (s_status == 0);
+  float nll = energy + 0.5f * n * logf(CUDART_PI_F) - 0.5f * logdet + quad - ztz;
+  if (naive) {
+    // src/models.py:163-171 evaluated literally in f32 (eps = 1e-7 everywhere)
+    const float eps = 1e-7f;
+    float zs = 0.f;
+    for (int i = tid; i < n; i += nt) zs += z[i];
+    const float zsum = block_sum(zs, red);
+    float fac = powf(CUDART_PI_F, 0.5f * n) / (sqrtf(expf(logdet)) + eps);
+    float Z = fac * expf(quad + eps * zsum * zsum - ztz) + eps;
+    float u = expf(-energy) / Z;
+    nll = -logf(u + eps);
+    grad_scale *= u / (u + eps);
+  }
   if (tid == 0) {
     status_[b] = s_status;
-    nll_[b] = ok ? energy + 0.5f * n * logf(CUDART_PI_F) - 0.5f * logdet + quad - ztz : 0.f;
+    nll_[b] = ok ? nll : 0.f;
     if (logdet_) logdet_[b] = ok ? logdet : 0.f;
   }
   for (int i = tid; i < n; i += nt) {
@@ -245,15 +258,15 @@ __global__ void extract_patches_kernel(const float* __restrict__ img, int B, int
 }  // namespace
 
 extern "C" int a3d_crf_fwd_bwd(a3d_ctx* ctx, const float* z, const float* y, const float* r, const int32_t* pl,
-                               const int32_t* pr, int B, int n, int n_pairs, float grad_scale, float* ystar, float* nll,
-                               float* logdet, float* dz, float* dr, int32_t* status, void* stream) {
+                               const int32_t* pr, int B, int n, int n_pairs, float grad_scale, int naive, float* ystar,
+                               float* nll, float* logdet, float* dz, float* dr, int32_t* status, void* stream) {
   A3D_REQUIRE(ctx && z && y && r && pl && pr && nll && status, "crf: null argument");
   A3D_REQUIRE(B > 0 && n > 0 && n <= 192 && n_pairs >= 0, "crf: n must be in 1..192");
   size_t smem = ((size_t)n * (n + 1) + 4 * (size_t)n + 32 + (size_t)(CRF_THREADS / 32) * n) * sizeof(float);
   if (smem > 48 * 1024)
     A3D_CHECK_CUDA(cudaFuncSetAttribute(crf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  crf_kernel<<<B, CRF_THREADS, smem, as_stream(stream)>>>(z, y, r, pl, pr, n, n_pairs, grad_scale, ystar, nll, logdet, dz,
-                                                         dr, status);
+  crf_kernel<<<B, CRF_THREADS, smem, as_stream(stream)>>>(z, y, r, pl, pr, n, n_pairs, grad_scale, naive, ystar, nll,
+                                                         logdet, dz, dr, status);
   A3D_LAUNCH_OK(ctx);
   return 0;
 }
@@ -293,6 +306,47 @@ extern "C" int a3d_extract_patches(a3d_ctx* ctx, const float* images, int B, int
   size_t blocks = (total + 255) / 256;
   if (blocks > (size_t)ctx->sm_count * 32) blocks = (size_t)ctx->sm_count * 32;
   extract_patches_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(images, B, H, W, rows, cols, patches, dstC);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
+__global__ void pairwise_dense_kernel(const float* __restrict__ sims, const float* __restrict__ w, const float* __restrict__ b,
+                                      float* __restrict__ r, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    r[i] = sims[2 * i] * w[0] + sims[2 * i + 1] * w[1] + b[0];
+}
+extern "C" int a3d_pairwise_dense(a3d_ctx* ctx, const float* sims, const float* w2, const float* b1, float* r, size_t n,
+                                  void* stream) {
+  A3D_REQUIRE(ctx && sims && w2 && b1 && r, "pairwise_dense: null argument");
+  pairwise_dense_kernel<<<ceil_div((long long)n, 256), 256, 0, as_stream(stream)>>>(sims, w2, b1, r, n);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
+__global__ void mean_f32_kernel(const float* __restrict__ v, int n, float* __restrict__ out) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) *out = s / (float)n;
+}
+extern "C" int a3d_mean_f32(a3d_ctx* ctx, const float* v, int n, float* out, void* stream) {
+  A3D_REQUIRE(ctx && v && out && n > 0, "mean: bad argument");
+  mean_f32_kernel<<<1, 256, 0, as_stream(stream)>>>(v, n, out);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
+__global__ void scale_cast_bf16_kernel(const float* __restrict__ s, uint16_t* __restrict__ d, size_t n, float scale) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    d[i] = f32_to_bf16_bits(s[i] * scale);
+}
+extern "C" int a3d_scale_cast_bf16(a3d_ctx* ctx, const float* src, uint16_t* dst, size_t n, float scale, void* stream) {
+  A3D_REQUIRE(ctx && src && dst, "scale_cast: null argument");
+  if (n == 0) return 0;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > (size_t)ctx->sm_count * 16) blocks = (size_t)ctx->sm_count * 16;
+  scale_cast_bf16_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(src, dst, n, scale);
   A3D_LAUNCH_OK(ctx);
   return 0;
 }

@@ -1,0 +1,238 @@
+"""DCNF (Liu et al. 2015) train / inference step on liba3d -- host-side orchestration.
+
+Mirrors `_DistributedConvolutionalNeuralFields` of the reference (src/models.py:9-200): resize to
+240x320, 100x100 patches around the 6x8 grid of 40x40 tiles, unary CNN on every patch, pairwise
+colour / histogram similarities through a 2->1 dense layer, CRF negative log-likelihood with
+A = I + D - R, plain SGD (lr 0.1).  The hard-coded worker devices of the reference (:63-79) and its
+serial `map_fn`s are gone: all B*48 patches form one batch and every CRF graph gets its own CTA.
+
+As in TF 1.3, no gradient reaches `pairwise_layers` (ScatterNdUpdate is not differentiable,
+src/models.py:138-141): only the unary CNN trains.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _lib as L
+from . import ops
+from .params import Arena, dcnf_specs
+
+H, W = 240, 320            # src/models.py:180-181
+SP = 40                    # src/models.py:16
+SGD_LR = 0.1               # src/models.py:198
+GAMMA = 1.0                # src/models.py:17
+PATCH_C = 16               # 3 image channels stored as 16 (32-byte pixels: the im2col TMA minimum)
+
+
+def num_superpixels(h=H, w=W):
+    """src/models.py:32-35."""
+    return math.ceil(h / SP), math.ceil(w / SP)
+
+
+def pair_indices(h=H, w=W):
+    """src/models.py:20-30."""
+    max_rows, max_cols = num_superpixels(h, w)
+    left, right = [], []
+    for row in range(1, max_rows - 1):
+        for col in range(2 - (row & 1), max_cols - 1, 2):
+            pixel = row * max_cols + col
+            for addend in [-max_cols, max_cols, -1, 1]:
+                left.append(pixel)
+                right.append(pixel + addend)
+    return left, right
+
+
+class DCNFNet:
+    def __init__(self, ctx: ops.Context, batch: int, in_hw=(480, 640), depth_hw=(480, 640), train=True,
+                 impl=L.IMPL_AUTO, naive_loss=True, comm=None):
+        self.ctx, self.B, self.train, self.impl, self.naive = ctx, batch, train, impl, naive_loss
+        self.dev = torch.device(f"cuda:{ctx.device}")
+        self.comm = comm
+        self.arena = Arena(dcnf_specs(), self.dev, with_adam=False)
+        self.global_step = 0
+        rows, cols = num_superpixels()
+        self.n = rows * cols
+        pl, pr = pair_indices()
+        assert len(pl) == self.n, "the reference sizes R by #pairs, valid only when #pairs == #nodes (src/models.py:149)"
+        self.pl = torch.tensor(pl, dtype=torch.int32, device=self.dev)
+        self.pr = torch.tensor(pr, dtype=torch.int32, device=self.dev)
+        B, NP = batch, batch * self.n
+        self.NP = NP
+        bf, f32 = dict(dtype=torch.bfloat16, device=self.dev), dict(dtype=torch.float32, device=self.dev)
+        u8 = dict(dtype=torch.uint8, device=self.dev)
+        z = torch.zeros
+        self.images = z(B, in_hw[0], in_hw[1], 3, **f32)
+        self.depths = z(B, depth_hw[0], depth_hw[1], 1, **f32)
+        self.im = z(B, H, W, 3, **f32)
+        self.dp = z(B, H, W, 1, **f32)
+        self.patches = z(NP, 100, 100, PATCH_C, **bf)
+        cd = ops.conv_desc
+        self.d0 = cd(NP, 100, 100, PATCH_C, 64, 11, 11, 1, "valid", impl=impl)      # :64
+        self.d1 = cd(NP, 45, 45, 64, 256, 5, 5, 1, "valid", impl=impl)              # :67
+        self.d2 = cd(NP, 20, 20, 256, 256, 3, 3, 1, "valid", impl=impl)             # :69
+        self.d3 = cd(NP, 18, 18, 256, 256, 3, 3, 1, "valid", impl=impl)             # :71
+        self.d4 = cd(NP, 16, 16, 256, 256, 3, 3, 1, "valid", impl=impl)             # :72
+        self.c0 = z(NP, 90, 90, 64, **f32)
+        self.p0, self.i0 = z(NP, 45, 45, 64, **bf), z(NP, 45, 45, 64, **u8)
+        self.c1 = z(NP, 41, 41, 256, **f32)
+        self.p1, self.i1 = z(NP, 20, 20, 256, **bf), z(NP, 20, 20, 256, **u8)
+        self.c2 = z(NP, 18, 18, 256, **bf)
+        self.c3 = z(NP, 16, 16, 256, **bf)
+        self.c4 = z(NP, 14, 14, 256, **f32)
+        self.p4, self.i4 = z(NP, 7, 7, 256, **bf), z(NP, 7, 7, 256, **u8)
+        self.h0 = z(NP, 128, **bf)
+        self.h1 = z(NP, 16, **bf)
+        self.z = z(NP, 1, **f32)
+        self.sims = z(B, self.n, 2, **f32)
+        self.r = z(B, self.n, **f32)
+        self.y = z(B, self.n, **f32)
+        self.ystar, self.nll, self.logdet = z(B, self.n, **f32), z(B, **f32), z(B, **f32)
+        self.status = torch.zeros(B, dtype=torch.int32, device=self.dev)
+        self.loss = z(1, **f32)
+        self.output = z(B, H, W, 1, **f32)
+        if train:
+            self.dz = z(B, self.n, **f32)
+            self.g_z = z(NP, 1, **bf)
+            self.g_h1a, self.g_h1 = z(NP, 16, **bf), z(NP, 16, **bf)
+            self.g_h0a, self.g_h0 = z(NP, 128, **bf), z(NP, 128, **bf)
+            self.g_p4 = z(NP, 7, 7, 256, **bf)
+            self.g_c4 = z(NP, 14, 14, 256, **bf)
+            self.g_c3a, self.g_c3 = z(NP, 16, 16, 256, **bf), z(NP, 16, 16, 256, **bf)
+            self.g_c2a, self.g_c2 = z(NP, 18, 18, 256, **bf), z(NP, 18, 18, 256, **bf)
+            self.g_p1 = z(NP, 20, 20, 256, **bf)
+            self.g_c1 = z(NP, 41, 41, 256, **bf)
+            self.g_p0 = z(NP, 45, 45, 64, **bf)
+            self.g_c0 = z(NP, 90, 90, 64, **bf)
+
+    # ------------------------------------------------------------------ parameters
+    def w(self, name):
+        return self.arena.view(self.arena.wb, name)
+
+    def wf(self, name):
+        return self.arena.view(self.arena.w, name)
+
+    def gw(self, name):
+        return self.arena.view(self.arena.g, name)
+
+    def load_params(self, tf_params):
+        self.arena.load_tf(tf_params)
+
+    def export_params(self):
+        return self.arena.export_tf()
+
+    def export_grads(self):
+        return self.arena.export_tf(self.arena.g)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self):
+        c, B, NP = self.ctx, self.B, self.NP
+        U, K = "unary/unary_layers/", "/kernel"
+        c.resize_bilinear_tf1(self.images, H, W, out=self.im)
+        c.resize_bilinear_tf1(self.depths, H, W, out=self.dp)
+        # unary part (src/models.py:61-89) on all B*48 patches at once
+        c.extract_patches(self.im, out=self.patches)
+        c.conv2d_fwd(self.d0, self.patches, self.w(U + "conv2d" + K), self.wf(U + "conv2d/bias"), relu=True, out=self.c0)
+        c.maxpool2x2_fwd_f32(self.c0, out=self.p0, idx=self.i0)
+        c.conv2d_fwd(self.d1, self.p0, self.w(U + "conv2d_1" + K), self.wf(U + "conv2d_1/bias"), relu=True, out=self.c1)
+        c.maxpool2x2_fwd_f32(self.c1, out=self.p1, idx=self.i1)
+        c.conv2d_fwd(self.d2, self.p1, self.w(U + "conv2d_2" + K), self.wf(U + "conv2d_2/bias"), relu=True, out=self.c2)
+        c.conv2d_fwd(self.d3, self.c2, self.w(U + "conv2d_3" + K), self.wf(U + "conv2d_3/bias"), relu=True, out=self.c3)
+        c.conv2d_fwd(self.d4, self.c3, self.w(U + "conv2d_4" + K), self.wf(U + "conv2d_4/bias"), relu=True, out=self.c4)
+        c.maxpool2x2_fwd_f32(self.c4, out=self.p4, idx=self.i4)
+        c.dense_fwd(self.p4.view(NP, 12544), self.w(U + "dense" + K), self.wf(U + "dense/bias"), flags=L.EPI_RELU,
+                    out=self.h0, impl=self.impl)
+        c.dense_fwd(self.h0, self.w(U + "dense_1" + K), self.wf(U + "dense_1/bias"), flags=L.EPI_SIGMOID, out=self.h1,
+                    impl=L.IMPL_SIMT)
+        c.dense_fwd(self.h1, self.w(U + "dense_2" + K), self.wf(U + "dense_2/bias"), flags=0, out=self.z,
+                    impl=L.IMPL_SIMT)
+        # pairwise part (src/models.py:108-127)
+        c.pairwise_features(self.im, self.pl, self.pr, GAMMA, out=self.sims)
+        P = "pairwise/pairwise_layers/dense"
+        c.pairwise_dense(self.sims, self.wf(P + K), self.wf(P + "/bias"), out=self.r)
+        # loss part (src/models.py:129-177)
+        c.tile_means(self.dp, out=self.y)
+        c.crf(self.z.view(B, self.n), self.y, self.r, self.pl, self.pr, grad_scale=1.0 / B, naive=self.naive,
+              out=dict(ystar=self.ystar, nll=self.nll, logdet=self.logdet, dz=self.dz if self.train else None,
+                       status=self.status))
+        c.mean_f32(self.nll, self.loss)
+        # output (src/models.py:187-191): the unary prediction, upsampled
+        rows, cols = num_superpixels()
+        c.resize_bilinear_tf1(self.z.view(B, rows, cols, 1), H, W, out=self.output)
+
+    # ------------------------------------------------------------------ backward (unary CNN only)
+    def backward(self):
+        c, NP = self.ctx, self.NP
+        U, K = "unary/unary_layers/", "/kernel"
+        hook = self.comm.bucket_ready if self.comm else (lambda *_: None)
+        c.scale_cast_bf16(self.dz.view(-1), self.g_z.view(-1), 1.0)
+        S = L.IMPL_SIMT
+        c.dense_wgrad(self.h1, self.g_z, dw=self.gw(U + "dense_2" + K), db=self.gw(U + "dense_2/bias"), N=1, impl=S)
+        c.dense_dgrad(self.g_z, self.w(U + "dense_2" + K), out=self.g_h1a, impl=S)
+        c.dense_epilogue_bwd(self.g_h1a, self.h1, None, 0.0, L.EPI_SIGMOID, out=self.g_h1)
+        c.dense_wgrad(self.h0, self.g_h1, dw=self.gw(U + "dense_1" + K), db=self.gw(U + "dense_1/bias"), impl=S)
+        c.dense_dgrad(self.g_h1, self.w(U + "dense_1" + K), out=self.g_h0a, impl=S)
+        c.dense_epilogue_bwd(self.g_h0a, self.h0, None, 0.0, L.EPI_RELU, out=self.g_h0)
+        c.dense_wgrad(self.p4.view(NP, 12544), self.g_h0, dw=self.gw(U + "dense" + K), db=self.gw(U + "dense/bias"),
+                      impl=self.impl)
+        c.dense_dgrad(self.g_h0, self.w(U + "dense" + K), out=self.g_p4.view(NP, 12544), impl=S)
+        c.maxpool2x2_idx_bwd(self.i4, self.g_p4, (NP, 14, 14, 256), out=self.g_c4)
+        c.conv2d_wgrad(self.d4, self.c3, self.g_c4, dw=self.gw(U + "conv2d_4" + K), db=self.gw(U + "conv2d_4/bias"))
+        c.conv2d_dgrad(self.d4, self.g_c4, self.w(U + "conv2d_4" + K), out=self.g_c3a)
+        c.relu_bwd(self.c3, self.g_c3a, out=self.g_c3)
+        c.conv2d_wgrad(self.d3, self.c2, self.g_c3, dw=self.gw(U + "conv2d_3" + K), db=self.gw(U + "conv2d_3/bias"))
+        c.conv2d_dgrad(self.d3, self.g_c3, self.w(U + "conv2d_3" + K), out=self.g_c2a)
+        c.relu_bwd(self.c2, self.g_c2a, out=self.g_c2)
+        c.conv2d_wgrad(self.d2, self.p1, self.g_c2, dw=self.gw(U + "conv2d_2" + K), db=self.gw(U + "conv2d_2/bias"))
+        c.conv2d_dgrad(self.d2, self.g_c2, self.w(U + "conv2d_2" + K), out=self.g_p1)
+        c.maxpool2x2_idx_bwd(self.i1, self.g_p1, (NP, 41, 41, 256), out=self.g_c1)
+        c.conv2d_wgrad(self.d1, self.p0, self.g_c1, dw=self.gw(U + "conv2d_1" + K), db=self.gw(U + "conv2d_1/bias"))
+        c.conv2d_dgrad(self.d1, self.g_c1, self.w(U + "conv2d_1" + K), out=self.g_p0)
+        c.maxpool2x2_idx_bwd(self.i0, self.g_p0, (NP, 90, 90, 64), out=self.g_c0)
+        c.conv2d_wgrad(self.d0, self.patches, self.g_c0, dw=self.gw(U + "conv2d" + K), db=self.gw(U + "conv2d/bias"))
+        m = self.arena.masks.get(U + "conv2d" + K)
+        if m is not None:
+            s = self.arena.specs[U + "conv2d" + K]
+            c.apply_mask_f32(self.arena.g[s.offset:s.offset + s.numel], m)
+        hook(self, "SGD")
+
+    def train_step(self, use_graph=False):
+        self.forward()
+        self.backward()
+        scale = 1.0
+        if self.comm:
+            self.comm.wait_all(self)
+            scale = 1.0 / self.comm.world
+        lo, hi = self.arena.group_range("SGD")
+        self.ctx.sgd(self.arena.w[lo:hi], self.arena.g[lo:hi], self.arena.wb[lo:hi], SGD_LR, scale)
+        self.global_step += 1
+        return 1
+
+    def infer(self):
+        self.forward()
+        return self.output
+
+
+class DCNFTrainOp:
+    """The object `models.dcnf(images, depths)` returns (src/models.py:198-200: minimize(loss, global_step))."""
+
+    def __init__(self, net: DCNFNet):
+        self.net = net
+        self.losses = {"loss/mean_loss": net.loss}
+        self.outputs = net.output
+
+    @property
+    def global_step(self):
+        return self.net.global_step
+
+    @property
+    def trainable_variables(self):
+        return {n: s.tf_shape for n, s in self.net.arena.specs.items()}
+
+    def run(self, use_graph=False):
+        if self.net.train:
+            return self.net.train_step()
+        return self.net.infer()
+
+    __call__ = run

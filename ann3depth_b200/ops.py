@@ -279,42 +279,65 @@ class Context:
         return D
 
     # ------------------------------------------------------------------ DCNF
-    def crf(self, z, y, r, pl, pr, grad_scale=1.0, want_dz=True, want_dr=False):
+    def pairwise_dense(self, sims, w2, b1, out=None):
+        n = sims.numel() // 2
+        if out is None:
+            out = torch.empty(sims.shape[:-1], dtype=torch.float32, device=sims.device)
+        L.check(self.lib.a3d_pairwise_dense(self.h, _ptr(sims), _ptr(w2), _ptr(b1), _ptr(out), n, _stream()),
+                "pairwise_dense")
+        return out
+
+    def mean_f32(self, v, out):
+        L.check(self.lib.a3d_mean_f32(self.h, _ptr(v), v.numel(), _ptr(out), _stream()), "mean")
+        return out
+
+    def scale_cast_bf16(self, src, dst, scale=1.0):
+        L.check(self.lib.a3d_scale_cast_bf16(self.h, _ptr(src), _ptr(dst), src.numel(), scale, _stream()),
+                "scale_cast")
+        return dst
+
+    def crf(self, z, y, r, pl, pr, grad_scale=1.0, want_dz=True, want_dr=False, naive=False, out=None):
         B, n = z.shape[0], z.shape[1]
         n_pairs = r.shape[1]
         dev = z.device
         f32 = dict(dtype=torch.float32, device=dev)
-        ystar = torch.empty(B, n, **f32)
-        nll = torch.empty(B, **f32)
-        logdet = torch.empty(B, **f32)
-        dz = torch.empty(B, n, **f32) if want_dz else None
-        dr = torch.empty(B, n_pairs, **f32) if want_dr else None
-        status = torch.empty(B, dtype=torch.int32, device=dev)
+        if out is not None:
+            ystar, nll, logdet = out["ystar"], out["nll"], out["logdet"]
+            dz, dr, status = out.get("dz"), out.get("dr"), out["status"]
+        else:
+            ystar = torch.empty(B, n, **f32)
+            nll = torch.empty(B, **f32)
+            logdet = torch.empty(B, **f32)
+            dz = torch.empty(B, n, **f32) if want_dz else None
+            dr = torch.empty(B, n_pairs, **f32) if want_dr else None
+            status = torch.empty(B, dtype=torch.int32, device=dev)
         L.check(self.lib.a3d_crf_fwd_bwd(self.h, _ptr(z), _ptr(y), _ptr(r), _ptr(pl), _ptr(pr), B, n, n_pairs,
-                                         grad_scale, _ptr(ystar), _ptr(nll), _ptr(logdet), _ptr(dz), _ptr(dr),
-                                         _ptr(status), _stream()), "crf")
+                                         grad_scale, int(naive), _ptr(ystar), _ptr(nll), _ptr(logdet), _ptr(dz),
+                                         _ptr(dr), _ptr(status), _stream()), "crf")
         return dict(ystar=ystar, nll=nll, logdet=logdet, dz=dz, dr=dr, status=status)
 
-    def pairwise_features(self, images, pl, pr, gamma=1.0):
+    def pairwise_features(self, images, pl, pr, gamma=1.0, out=None):
         B, H, W, _ = images.shape
         n_pairs = pl.numel()
         ws = self.workspace(("pairwise", B, H, W), self.lib.a3d_pairwise_ws_bytes(B, H, W))
-        sims = torch.empty(B, n_pairs, 2, dtype=torch.float32, device=images.device)
+        sims = out if out is not None else torch.empty(B, n_pairs, 2, dtype=torch.float32, device=images.device)
         L.check(self.lib.a3d_pairwise_features(self.h, _ptr(images), B, H, W, _ptr(pl), _ptr(pr), n_pairs, gamma,
                                                _ptr(ws), _ptr(sims), _stream()), "pairwise_features")
         return sims
 
-    def tile_means(self, depth):
+    def tile_means(self, depth, out=None):
         B, H, W = depth.shape[:3]
         n = math.ceil(H / 40) * math.ceil(W / 40)
-        y = torch.empty(B, n, dtype=torch.float32, device=depth.device)
+        y = out if out is not None else torch.empty(B, n, dtype=torch.float32, device=depth.device)
         L.check(self.lib.a3d_tile_means(self.h, _ptr(depth), B, H, W, _ptr(y), _stream()), "tile_means")
         return y
 
-    def extract_patches(self, images, dstC=16):
+    def extract_patches(self, images, dstC=16, out=None):
         B, H, W, _ = images.shape
         n = math.ceil(H / 40) * math.ceil(W / 40)
-        out = torch.empty(B * n, 100, 100, dstC, dtype=torch.bfloat16, device=images.device)
+        if out is None:
+            out = torch.empty(B * n, 100, 100, dstC, dtype=torch.bfloat16, device=images.device)
+        dstC = out.shape[-1]
         L.check(self.lib.a3d_extract_patches(self.h, _ptr(images), B, H, W, _ptr(out), dstC, _stream()),
                 "extract_patches")
         return out

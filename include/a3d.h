@@ -198,16 +198,27 @@ int a3d_apply_mask_f32(a3d_ctx*, float* g, const uint8_t* keep, size_t n, void* 
  *   dz  = grad_scale * d nll / d z = grad_scale * 2 (y* - y)   ... when dz != NULL (unary gradient)
  *   dr  = grad_scale * d nll / d r[b,k]   ... when dr != NULL (beyond-reference)
  * status[b] = 0 ok, k+1 if pivot k of the Cholesky factorisation was not positive (outputs of
- * that graph are then zero, never NaN).  n <= 192.  f32 arrays; pl/pr/status int32. */
+ * that graph are then zero, never NaN).  n <= 192.  f32 arrays; pl/pr/status int32.
+ * naive != 0 reproduces the reference's literal evaluation (src/models.py:163-171):
+ *   nll = -log(exp(-energy)/Z + eps), Z = pi^(n/2)/(sqrt(det A)+eps) * exp(z^T(A^-1+eps)z - z^T z) + eps,
+ * eps = 1e-7, which saturates at -log(eps) = 16.118; dz is then scaled by u/(u+eps), u = exp(-energy)/Z. */
 int a3d_crf_fwd_bwd(a3d_ctx*, const float* z, const float* y, const float* r, const int32_t* pl,
-                    const int32_t* pr, int B, int n, int n_pairs, float grad_scale, float* ystar,
-                    float* nll, float* logdet, float* dz, float* dr, int32_t* status, void* stream);
+                    const int32_t* pr, int B, int n, int n_pairs, float grad_scale, int naive,
+                    float* ystar, float* nll, float* logdet, float* dz, float* dr, int32_t* status,
+                    void* stream);
 
 /* Fused pairwise features (src/models.py:95-127): images f32 [B,H,W,3] (H,W multiples of 40) ->
  * sims f32 [B,n_pairs,2] = (exp(-g*||mean-colour tile l - tile r||), exp(-g*||hist_l - hist_r||)). */
 int a3d_pairwise_features(a3d_ctx*, const float* images, int B, int H, int W, const int32_t* pl,
                           const int32_t* pr, int n_pairs, float gamma, float* tile_feat_ws,
                           float* sims, void* stream);
+/* The 2 -> 1 `pairwise_dense` layer (src/models.py:91-93): r[i] = sims[i,0]*w[0] + sims[i,1]*w[1] + b[0]. */
+int a3d_pairwise_dense(a3d_ctx*, const float* sims, const float* w2, const float* b1, float* r, size_t n,
+                       void* stream);
+/* out[0] = mean(v[0..n)) (tf.reduce_mean of per-sample losses, src/models.py:174,272). */
+int a3d_mean_f32(a3d_ctx*, const float* v, int n, float* out, void* stream);
+/* f32 -> bf16 with scaling: dst[i] = bf16(scale * src[i]). */
+int a3d_scale_cast_bf16(a3d_ctx*, const float* src, uint16_t* dst, size_t n, float scale, void* stream);
 size_t a3d_pairwise_ws_bytes(int B, int H, int W);
 /* Tile means of a 1-channel map (src/models.py:131-132): depth f32 [B,H,W] -> y f32 [B,n]. */
 int a3d_tile_means(a3d_ctx*, const float* depth, int B, int H, int W, float* y, void* stream);

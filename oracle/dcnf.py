@@ -100,18 +100,20 @@ def unary_part_patch(p, patch_batch, q=lambda t: t):
 
     def b(n):
         return p[L + n + "/bias"]
-    t = q(T.conv2d(patch_batch, k("conv2d"), b("conv2d"), 1, "valid", True))
-    t = T.max_pool_2x2(t)
-    t = q(T.conv2d(t, k("conv2d_1"), b("conv2d_1"), 1, "valid", True))
-    t = T.max_pool_2x2(t)
+    # q() marks the bf16 storage points of the CUDA path (after the pool where one follows: rounding is
+    # monotone, and the arg-max routing is decided on unrounded values)
+    t = T.conv2d(patch_batch, k("conv2d"), b("conv2d"), 1, "valid", True)
+    t = q(T.max_pool_2x2(t))
+    t = T.conv2d(t, k("conv2d_1"), b("conv2d_1"), 1, "valid", True)
+    t = q(T.max_pool_2x2(t))
     t = q(T.conv2d(t, k("conv2d_2"), b("conv2d_2"), 1, "valid", True))
     t = q(T.conv2d(t, k("conv2d_3"), b("conv2d_3"), 1, "valid", True))
-    t = q(T.conv2d(t, k("conv2d_4"), b("conv2d_4"), 1, "valid", True))
-    t = T.max_pool_2x2(t)
+    t = T.conv2d(t, k("conv2d_4"), b("conv2d_4"), 1, "valid", True)
+    t = q(T.max_pool_2x2(t))
     t = t.reshape(t.shape[0], -1)
     t = q(T.dense(t, k("dense"), b("dense"), "relu"))
-    t = T.dense(t, p[L + "dense_1/kernel"], b("dense_1"), "sigmoid")
-    t = T.dense(t, p[L + "dense_2/kernel"], b("dense_2"), None)
+    t = q(T.dense(t, k("dense_1"), b("dense_1"), "sigmoid"))
+    t = T.dense(t, k("dense_2"), b("dense_2"), None)
     return t
 
 
