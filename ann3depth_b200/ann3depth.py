@@ -110,7 +110,7 @@ def main(argv=None):
         import torch.distributed as dist
         from . import ops
         from .dp import DataParallel
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        dist.init_process_group("gloo")      # control plane only; gradients go over liba3d's NCCL communicator
         ids = [ops.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         comm = DataParallel(models.get_context(local_rank), rank, world, ids[0])

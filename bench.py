@@ -202,7 +202,10 @@ def gpu_arm(args, rank, world, local_rank):
     comm = None
     ctx = models.get_context(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # torch.distributed (gloo) is control-plane only: rendezvous, barriers, max-over-ranks of the timings.
+        # The data path (gradient allreduce) runs on liba3d's own NCCL communicator; keeping a single NCCL
+        # communicator per process avoids cross-communicator ordering deadlocks.
+        dist.init_process_group("gloo")
         ids = [ops.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         comm = DataParallel(ctx, rank, world, ids[0])
@@ -235,7 +238,7 @@ def gpu_arm(args, rank, world, local_rank):
     barrier()
     sampler.stop_flag = True
     ms_total = e0.elapsed_time(e1)
-    t = torch.tensor([ms_total], device=dev)
+    t = torch.tensor([ms_total])
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t)
@@ -279,14 +282,17 @@ def gpu_arm(args, rank, world, local_rank):
     last_loss = e2e_loop(args.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device=dev)
+    t = torch.tensor([e2e_s])
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = BATCH * world * args.steps / float(t)
 
     if rank == 0:
         pk, pk_kind = peaks()
+        # per-kernel timing pass runs on rank 0 alone: detach the communicator so that it contains no collective
+        saved_comm, op.net.comm = op.net.comm, None
         rows = per_op_profile(op, torch)
+        op.net.comm = saved_comm
         step_ms = ms_total / args.steps
         # dominant kernel of the step, and the conv/FC tensor-pipe aggregate
         top = max(rows, key=lambda r: r["ms"])
@@ -330,7 +336,12 @@ def gpu_arm(args, rank, world, local_rank):
                 "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without running destructors: NCCL communicator teardown at interpreter exit is collective and
+        # its order across ranks is undefined (observed to hang the launcher for minutes).
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

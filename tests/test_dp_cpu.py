@@ -1,0 +1,115 @@
+"""CPU tests (gloo, world_size 2) of the data-parallel protocol and host-side layout logic.
+
+The GPU path sum-allreduces flat gradient buckets with NCCL and folds 1/n into the optimizer
+(ann3depth_b200/dp.py).  Here the same protocol runs over gloo with the CPU oracle as the per-rank
+model: n ranks x batch B must equal one rank x batch n*B."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ann3depth_b200.dp import DataParallel
+from ann3depth_b200.params import Arena, msdn_specs, pack, unpack
+from oracle import msdn as OM
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _batch(n, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    images = torch.rand(n, 480, 640, 3, generator=g)
+    depths = torch.rand(n, 55, 73, 1, generator=g) * 0.95 + 0.05
+    mask = (torch.rand(n, 4096, generator=g) < 0.5).float()
+    return images, depths, mask
+
+
+def _params():
+    p = OM.init_params(1, torch.float32, bias_range=0.05)
+    p["coarse/dense/dense_1/bias"] += 1.0
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    images, depths, mask = _batch(world)
+    p = _params()
+    sl = slice(rank, rank + 1)                                    # shard: one sample per rank
+    g, _ = OM.grads(p, images[sl], depths[sl], mask[sl], "coarse")
+    # flat bucket in arena order, sum-allreduce, then the optimizer's grad_scale = 1/n
+    names = [n for n in g]
+    flat = torch.cat([g[n].reshape(-1) for n in names])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat *= 1.0 / world
+    if rank == 0:
+        torch.save({"names": names, "flat": flat}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dp_mean_of_rank_gradients_equals_big_batch(tmp_path):
+    world, port = 2, 29531
+    out = str(tmp_path / "dp.pt")
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    got = torch.load(out)
+    images, depths, mask = _batch(world)
+    ref, _ = OM.grads(_params(), images, depths, mask, "coarse")
+    flat_ref = torch.cat([ref[n].reshape(-1) for n in got["names"]])
+    cos = float(got["flat"] @ flat_ref / (got["flat"].norm() * flat_ref.norm()))
+    assert cos > 0.99999
+    assert float((got["flat"] - flat_ref).abs().max() / flat_ref.abs().max()) < 1e-3
+
+
+class _Net:
+    def __init__(self):
+        self.arena = Arena(msdn_specs(), "cpu", with_adam=False)
+
+
+def test_arena_layout_and_buckets():
+    net = _Net()
+    a = net.arena
+    assert a.num_real_params() == 70877171                      # KA2
+    # every segment 16-byte aligned in both the f32 and the bf16 view
+    for s in a.specs.values():
+        assert s.offset % 8 == 0
+    # optimizer groups are contiguous, disjoint, and cover the arena in backward order
+    order = ["CoarseDense", "CoarseConv", "FineA", "FineB"]
+    pos = 0
+    for g in order:
+        lo, hi = a.group_range(g)
+        assert lo == pos
+        pos = hi
+    assert pos == a.total
+    br = DataParallel.bucket_range
+    d1, d0, cc = br(net, "dense_1"), br(net, "dense_0"), br(net, "coarse_conv")
+    assert d1[0] == 0 and d1[1] == d0[0] and d0[1] == cc[0]      # buckets become ready front to back
+    assert br(net, "CoarseDense") == (d1[0], d0[1])
+    fa, fb = a.group_range("FineA"), a.group_range("FineB")
+    assert br(net, "fine") == (fa[0], fb[1])
+
+
+def test_pack_unpack_roundtrip_and_masks():
+    a = _Net().arena
+    g = torch.Generator().manual_seed(0)
+    for name in ("coarse/conv/conv2d_0/kernel", "fine/first/conv2d/kernel", "fine/first/conv2d/bias",
+                 "coarse/dense/dense_1/kernel", "coarse/conv/conv2d_3/kernel"):
+        s = a.specs[name]
+        t = torch.rand(s.tf_shape, generator=g)
+        assert torch.equal(unpack(s, pack(s, t)), t)
+    m = a.masks["coarse/conv/conv2d_0/kernel"].view(96, 11, 12, 4)
+    assert int(m.sum()) == 96 * 11 * 11 * 3 and not bool(m[:, :, 11, :].any()) and not bool(m[..., 3].any())
+    m = a.masks["fine/first/conv2d/kernel"].view(64, 9, 10, 4)
+    assert int(m.sum()) == 63 * 9 * 9 * 3 and not bool(m[63].any())
+    assert "coarse/conv/conv2d_1/kernel" not in a.masks
+
+
+def test_bench_reference_arm_other_ranks_are_silent():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+                        "--steps", "1", "--warmup", "0"], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
