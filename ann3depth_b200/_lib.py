@@ -74,6 +74,7 @@ SIGNATURES = {
     "a3d_allreduce_sum": (_i, [_vp, _vp, _sz, _i, _vp]),
     # engine unit-test hook (not part of the drop-in surface)
     "a3d_debug_tc_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "a3d_debug_tc_shift": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
 }
 
 _lib = None

@@ -157,9 +157,44 @@ int launch(a3d_ctx* ctx, const Prob& p, long long M, long long N, cudaStream_t s
   return 0;
 }
 
-// column sums of a bf16 [rows, ld] matrix (first C columns) -> f32[C]; out must be zeroed.
-__global__ void colsum_bf16_kernel(const uint16_t* __restrict__ a, size_t rows, int C, int ld, float* __restrict__ out,
-                                   int rows_per_block) {
+// column sums of a bf16 [rows, ld] matrix (first C columns, C % 8 == 0) -> f32[C]; out must be zeroed.
+// 256 threads = RL row-lanes x C8 column-vectors of 8: 16-byte coalesced loads, per-thread f32
+// accumulation over the block's row range, smem reduction across row-lanes, one atomic per column.
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const uint16_t* __restrict__ a, size_t rows, int C8, int ld8, float* __restrict__ out,
+                   size_t rows_per_block) {
+  extern __shared__ float red[];                     // [RL][C8*8]
+  const int RL = 256 / C8;
+  const int rl = threadIdx.x / C8, cv = threadIdx.x % C8;
+  const bool active = rl < RL;
+  size_t r0 = (size_t)blockIdx.x * rows_per_block;
+  size_t r1 = min(rows, r0 + rows_per_block);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (active) {
+    const uint4* p = reinterpret_cast<const uint4*>(a);
+    for (size_t r = r0 + rl; r < r1; r += RL) {
+      uint4 v = __ldg(p + r * ld8 + cv);
+      const uint32_t* w = &v.x;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        acc[2 * k] += __uint_as_float(w[k] << 16);
+        acc[2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[(size_t)rl * C8 * 8 + cv * 8 + k] = acc[k];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C8 * 8; c += blockDim.x) {
+    float s = 0.f;
+    for (int j = 0; j < RL; ++j) s += red[(size_t)j * C8 * 8 + c];
+    atomicAdd(out + c, s);
+  }
+}
+
+// generic fallback (any C, any ld)
+__global__ void colsum_bf16_scalar_kernel(const uint16_t* __restrict__ a, size_t rows, int C, int ld,
+                                          float* __restrict__ out, int rows_per_block) {
   size_t r0 = (size_t)blockIdx.x * rows_per_block;
   size_t r1 = min(rows, r0 + rows_per_block);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -194,9 +229,20 @@ int a3d_simt_conv_wgrad(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x,
 
 int a3d_colsum_bf16(a3d_ctx* ctx, const uint16_t* a, size_t rows, int C, int ld, float* out, cudaStream_t st) {
   A3D_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, st));
-  int rpb = 256;
-  int grid = ceil_div((long long)rows, rpb);
-  colsum_bf16_kernel<<<grid, 128, 0, st>>>(a, rows, C, ld, out, rpb);
+  const bool vec = C % 8 == 0 && ld % 8 == 0 && C / 8 <= 256 && (reinterpret_cast<uintptr_t>(a) & 15) == 0;
+  if (vec) {
+    const int C8 = C / 8, RL = 256 / C8;
+    size_t blocks = (rows + (size_t)RL * 8 - 1) / ((size_t)RL * 8);        // >= 8 rows per row-lane
+    size_t cap = (size_t)ctx->sm_count * 4;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    size_t rpb = (rows + blocks - 1) / blocks;
+    blocks = (rows + rpb - 1) / rpb;
+    colsum_bf16_kernel<<<(int)blocks, 256, (size_t)RL * C * sizeof(float), st>>>(a, rows, C8, ld / 8, out, rpb);
+  } else {
+    int rpb = 256;
+    colsum_bf16_scalar_kernel<<<ceil_div((long long)rows, rpb), 128, 0, st>>>(a, rows, C, ld, out, rpb);
+  }
   A3D_LAUNCH_OK(ctx);
   return 0;
 }
