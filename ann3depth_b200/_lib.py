@@ -40,7 +40,7 @@ SIGNATURES = {
     "a3d_resize_bilinear_tf1": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp]),
     "a3d_conv2d_ws_bytes": (_sz, [_vp, C.POINTER(ConvDesc), _i]),
     "a3d_conv2d_fwd": (_i, [_vp, C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _i, _u, _vp, _sz, _vp]),
-    "a3d_conv2d_dgrad": (_i, [_vp, C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _sz, _vp]),
+    "a3d_conv2d_dgrad": (_i, [_vp, C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "a3d_conv2d_wgrad": (_i, [_vp, C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "a3d_dense_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _i, _vp, _i, _i, _i, _u, _i, _vp]),
     "a3d_dense_dgrad": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

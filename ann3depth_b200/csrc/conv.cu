@@ -2,6 +2,7 @@
 // (tcgen05 engine in tc_gemm.cu where the shape allows, CUDA-core kernels otherwise), plus the small
 // helper kernels around them (filter flip for dgrad, col2im, single-filter convolution).
 #include "common.cuh"
+#include <stdlib.h>
 
 int a3d_tc_conv_fwd(a3d_ctx*, const a3d_conv_desc*, const uint16_t* x, const uint16_t* w, const float* bias, void* y,
                     int y_dtype, unsigned flags, void* ws, size_t ws_bytes, cudaStream_t st);
@@ -15,6 +16,72 @@ int a3d_tc_dense_dgrad(a3d_ctx*, const uint16_t* dy, int lddy, const uint16_t* w
                        int N, int K, cudaStream_t st);
 int a3d_tc_dense_wgrad(a3d_ctx*, const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, int M, int N, int K,
                        cudaStream_t st);
+
+// tc_halo.cu
+struct HaloGeom { int Hp, Wp, Cp, need_copy; };
+size_t a3d_halo_ws_bytes(int N, int H, int W, int C, int ld, int K, int R, int S, int pt, int pl, int P, int Q, int flip);
+int a3d_halo_conv_run(a3d_ctx* ctx, const uint16_t* xp, int N, int Hp, int Wp, int Cp, const uint16_t* wpk, int Kout, int R,
+                      int S, int P, int Q, void* out, int out_f32, int OH, int OW, int oph, int opw, long long ldo,
+                      const float* bias, unsigned flags, const uint16_t* relu_src, cudaStream_t st);
+int a3d_halo_pad_copy(a3d_ctx* ctx, const uint16_t* src, int N, int H, int W, int C, int ld, uint16_t* dst, int Hp, int Wp,
+                      int Cp, int pt, int pl, cudaStream_t st);
+int a3d_halo_repack_filter(a3d_ctx* ctx, const uint16_t* w, uint16_t* wd, int K, int RS, int C, int Cp, int flip,
+                           cudaStream_t st);
+
+static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// Stride-1 convolution through the shared-memory-halo kernel (tc_halo.cu).  `in` is the tensor the filter
+// slides over ([N,H,W,C], channel stride ld), outputs P x Q, filter [Kout][R][S][C] (flip = 0) or the
+// original OHWI filter of a conv whose dgrad this is (flip = 1: w is [C_conv = Kout][RS][K_conv = C]).
+static int halo_policy() {          // A3D_HALO = 0 never, 1 default (measured wins only), 2 wherever it fits
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("A3D_HALO"); v = e ? atoi(e) : 1; }
+  return v;
+}
+static bool halo_ok(int C, int R, int S, int Wp, bool dgrad) {
+  // needs >= 48 channels (padding to 64 wastes < 1/3) and a window that fits shared memory.  Measured on
+  // B200 (profiles/bench_ops_r01_halo.json): a win for the 5x5 forward layers (25 taps share one window);
+  // for 3x3 layers and for dgrad at these small spatial sizes the padded-grid garbage (20-28 % of the
+  // positions) and the extra pad-copy outweigh the saved L2 traffic, so they stay on the im2col-TMA path.
+  if (!(C >= 48 && (128 + (R - 1) * Wp + S - 1) <= 1024)) return false;
+  if (halo_policy() == 0) return false;
+  if (halo_policy() >= 2) return true;
+  return !dgrad && R * S >= 25;
+}
+
+static int halo_conv(a3d_ctx* ctx, const uint16_t* in, int N, int H, int W, int C, int ld, const uint16_t* w, int Kout,
+                     int R, int S, int pt, int pl, int P, int Q, int flip, void* out, int out_f32, long long ldo,
+                     const float* bias, unsigned flags, const uint16_t* relu_src, void* ws, size_t ws_bytes,
+                     cudaStream_t st) {
+  int Hp = P + R - 1; if (Hp < H + pt) Hp = H + pt;
+  int Wp = Q + S - 1; if (Wp < W + pl) Wp = W + pl;
+  const int Cp = (C + 63) / 64 * 64;
+  const bool need_copy = !(pt == 0 && pl == 0 && Hp == H && Wp == W && Cp == C && ld == C);
+  uint8_t* wsb = reinterpret_cast<uint8_t*>(ws);
+  size_t off = 0;
+  const uint16_t* xp = in;
+  if (need_copy) {
+    size_t bytes = al256((size_t)N * Hp * Wp * Cp * 2);
+    if (off + bytes > ws_bytes) { a3d_set_error("halo conv: workspace too small"); return A3D_EINVAL; }
+    int rc = a3d_halo_pad_copy(ctx, in, N, H, W, C, ld, reinterpret_cast<uint16_t*>(wsb + off), Hp, Wp, Cp, pt, pl, st);
+    if (rc) return rc;
+    xp = reinterpret_cast<const uint16_t*>(wsb + off);
+    off += bytes;
+  }
+  const uint16_t* wpk = w;
+  if (flip || Cp != C) {
+    size_t bytes = al256((size_t)Kout * R * S * Cp * 2);
+    if (off + bytes > ws_bytes) { a3d_set_error("halo conv: workspace too small"); return A3D_EINVAL; }
+    // flip: w is [K_conv = C][RS][C_conv = Kout] -> [Kout][RS][Cp]
+    int rc = flip ? a3d_halo_repack_filter(ctx, w, reinterpret_cast<uint16_t*>(wsb + off), C, R * S, Kout, Cp, 1, st)
+                  : a3d_halo_repack_filter(ctx, w, reinterpret_cast<uint16_t*>(wsb + off), Kout, R * S, C, Cp, 0, st);
+    if (rc) return rc;
+    wpk = reinterpret_cast<const uint16_t*>(wsb + off);
+    off += bytes;
+  }
+  return a3d_halo_conv_run(ctx, xp, N, Hp, Wp, Cp, wpk, Kout, R, S, P, Q, out, out_f32, P, Q, 0, 0, ldo, bias, flags,
+                           relu_src, st);
+}
 
 static int check_desc(const a3d_conv_desc* d) {
   A3D_REQUIRE(d, "conv: null descriptor");
@@ -159,9 +226,19 @@ static size_t splitk_bytes(a3d_ctx* ctx, long long rows, int cols) {
 
 extern "C" size_t a3d_conv2d_ws_bytes(a3d_ctx* ctx, const a3d_conv_desc* d, int op) {
   if (!d) return 0;
-  if (op == A3D_OP_FWD) return splitk_bytes(ctx, (long long)d->N * d->P * d->Q, d->K);
+  const bool s1 = d->stride_h == 1 && d->stride_w == 1;
+  if (op == A3D_OP_FWD) {
+    size_t a = splitk_bytes(ctx, (long long)d->N * d->P * d->Q, d->K);
+    size_t b = s1 ? a3d_halo_ws_bytes(d->N, d->H, d->W, d->C, d->C, d->K, d->R, d->S, d->pad_t, d->pad_l, d->P, d->Q, 0) : 0;
+    return a > b ? a : b;
+  }
   if (op == A3D_OP_DGRAD) {
-    if (dgrad_as_fwd_ok(d)) return filt_bytes(d) + splitk_bytes(ctx, (long long)d->N * d->H * d->W, d->C);
+    if (dgrad_as_fwd_ok(d)) {
+      size_t a = filt_bytes(d) + splitk_bytes(ctx, (long long)d->N * d->H * d->W, d->C);
+      size_t b = a3d_halo_ws_bytes(d->N, d->P, d->Q, d->K, d->ldy, d->C, d->R, d->S, d->R - 1 - d->pad_t,
+                                   d->S - 1 - d->pad_l, d->H, d->W, 1);
+      return a > b ? a : b;
+    }
     if (dgrad_as_cols_ok(d)) return (size_t)d->N * d->P * d->Q * d->R * d->S * d->C * sizeof(float);
     return 0;
   }
@@ -176,6 +253,15 @@ extern "C" int a3d_conv2d_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
   if (d->impl == A3D_IMPL_SIMT) return a3d_simt_conv_fwd(ctx, d, x, w, bias, y, y_dtype, flags, st);
+  {
+    int Wp = d->Q + d->S - 1; if (Wp < d->W + d->pad_l) Wp = d->W + d->pad_l;
+    if (d->stride_h == 1 && d->stride_w == 1 && halo_ok(d->C, d->R, d->S, Wp, false) && ws &&
+        ws_bytes >= a3d_halo_ws_bytes(d->N, d->H, d->W, d->C, d->C, d->K, d->R, d->S, d->pad_t, d->pad_l, d->P, d->Q, 0)) {
+      int rc2 = halo_conv(ctx, x, d->N, d->H, d->W, d->C, d->C, w, d->K, d->R, d->S, d->pad_t, d->pad_l, d->P, d->Q, 0, y,
+                          y_dtype == A3D_F32, d->ldy, bias, flags, nullptr, ws, ws_bytes, st);
+      if (rc2 != A3D_ENOTSUP) return rc2;
+    }
+  }
   a3d_conv_desc v;
   const a3d_conv_desc* e = virtualize(d, &v) ? &v : d;
   if (a3d_tc_conv_fwd_supported(e)) return a3d_tc_conv_fwd(ctx, e, x, w, bias, y, y_dtype, flags, ws, ws_bytes, st);
@@ -196,13 +282,40 @@ extern "C" int a3d_conv2d_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16
   return a3d_simt_conv_fwd(ctx, d, x, w, bias, y, y_dtype, flags, st);
 }
 
+static int dgrad_impl(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* dy, const uint16_t* w, uint16_t* dx,
+                      const uint16_t* relu_src, bool* relu_done, void* ws, size_t ws_bytes, cudaStream_t st);
+
 extern "C" int a3d_conv2d_dgrad(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* dy, const uint16_t* w,
-                                uint16_t* dx, void* ws, size_t ws_bytes, void* stream) {
+                                uint16_t* dx, const uint16_t* relu_src, void* ws, size_t ws_bytes, void* stream) {
   A3D_REQUIRE(ctx && dy && w && dx, "conv dgrad: null argument");
   int rc = check_desc(d);
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
+  bool relu_done = false;
+  rc = dgrad_impl(ctx, d, dy, w, dx, relu_src, &relu_done, ws, ws_bytes, st);
+  if (rc) return rc;
+  if (relu_src && !relu_done) {
+    A3D_REQUIRE(d->C % 8 == 0, "conv dgrad: fused ReluGrad needs C %% 8 == 0");
+    return a3d_relu_bwd(ctx, relu_src, dx, d->C, dx, (size_t)d->N * d->H * d->W, d->C, st);     // in place
+  }
+  return 0;
+}
+
+static int dgrad_impl(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* dy, const uint16_t* w, uint16_t* dx,
+                      const uint16_t* relu_src, bool* relu_done, void* ws, size_t ws_bytes, cudaStream_t st) {
+  int rc = 0;
   const size_t filt = filt_bytes(d);
+  if (d->impl != A3D_IMPL_SIMT && dgrad_as_fwd_ok(d)) {
+    const int pt2 = d->R - 1 - d->pad_t, pl2 = d->S - 1 - d->pad_l;
+    int Wp = d->W + d->S - 1; if (Wp < d->Q + pl2) Wp = d->Q + pl2;
+    if (halo_ok(d->K, d->R, d->S, Wp, true) && ws &&
+        ws_bytes >= a3d_halo_ws_bytes(d->N, d->P, d->Q, d->K, d->ldy, d->C, d->R, d->S, pt2, pl2, d->H, d->W, 1)) {
+      rc = halo_conv(ctx, dy, d->N, d->P, d->Q, d->K, d->ldy, w, d->C, d->R, d->S, pt2, pl2, d->H, d->W, 1, dx, 0, d->C,
+                     nullptr, 0, relu_src, ws, ws_bytes, st);
+      if (rc == 0) { *relu_done = relu_src != nullptr; return 0; }
+      if (rc != A3D_ENOTSUP) return rc;
+    }
+  }
   if (d->impl != A3D_IMPL_SIMT && dgrad_as_fwd_ok(d) && ws && ws_bytes >= filt) {
     uint16_t* wd = reinterpret_cast<uint16_t*>(ws);
     size_t total = (size_t)d->K * d->R * d->S * d->C;

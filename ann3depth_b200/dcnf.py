@@ -179,11 +179,9 @@ class DCNFNet:
         c.dense_dgrad(self.g_h0, self.w(U + "dense" + K), out=self.g_p4.view(NP, 12544), impl=S)
         c.maxpool2x2_idx_bwd(self.i4, self.g_p4, (NP, 14, 14, 256), out=self.g_c4)
         c.conv2d_wgrad(self.d4, self.c3, self.g_c4, dw=self.gw(U + "conv2d_4" + K), db=self.gw(U + "conv2d_4/bias"))
-        c.conv2d_dgrad(self.d4, self.g_c4, self.w(U + "conv2d_4" + K), out=self.g_c3a)
-        c.relu_bwd(self.c3, self.g_c3a, out=self.g_c3)
+        c.conv2d_dgrad(self.d4, self.g_c4, self.w(U + "conv2d_4" + K), out=self.g_c3, relu_src=self.c3)
         c.conv2d_wgrad(self.d3, self.c2, self.g_c3, dw=self.gw(U + "conv2d_3" + K), db=self.gw(U + "conv2d_3/bias"))
-        c.conv2d_dgrad(self.d3, self.g_c3, self.w(U + "conv2d_3" + K), out=self.g_c2a)
-        c.relu_bwd(self.c2, self.g_c2a, out=self.g_c2)
+        c.conv2d_dgrad(self.d3, self.g_c3, self.w(U + "conv2d_3" + K), out=self.g_c2, relu_src=self.c2)
         c.conv2d_wgrad(self.d2, self.p1, self.g_c2, dw=self.gw(U + "conv2d_2" + K), db=self.gw(U + "conv2d_2/bias"))
         c.conv2d_dgrad(self.d2, self.g_c2, self.w(U + "conv2d_2" + K), out=self.g_p1)
         c.maxpool2x2_idx_bwd(self.i1, self.g_p1, (NP, 41, 41, 256), out=self.g_c1)

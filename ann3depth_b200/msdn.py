@@ -191,11 +191,9 @@ class MSDNNet:
         c.relu_bwd(self.c4, self.g_c4a, out=self.g_c4)
         n = "coarse/conv/conv2d_"
         c.conv2d_wgrad(self.d_c4, self.c3, self.g_c4, dw=self.gw(n + "4" + K), db=self.gw(n + "4/bias"))
-        c.conv2d_dgrad(self.d_c4, self.g_c4, self.w(n + "4" + K), out=self.g_c3a)
-        c.relu_bwd(self.c3, self.g_c3a, out=self.g_c3)
+        c.conv2d_dgrad(self.d_c4, self.g_c4, self.w(n + "4" + K), out=self.g_c3, relu_src=self.c3)
         c.conv2d_wgrad(self.d_c3, self.c2, self.g_c3, dw=self.gw(n + "3" + K), db=self.gw(n + "3/bias"))
-        c.conv2d_dgrad(self.d_c3, self.g_c3, self.w(n + "3" + K), out=self.g_c2a)
-        c.relu_bwd(self.c2, self.g_c2a, out=self.g_c2)
+        c.conv2d_dgrad(self.d_c3, self.g_c3, self.w(n + "3" + K), out=self.g_c2, relu_src=self.c2)
         c.conv2d_wgrad(self.d_c2, self.p1, self.g_c2, dw=self.gw(n + "2" + K), db=self.gw(n + "2/bias"))
         c.conv2d_dgrad(self.d_c2, self.g_c2, self.w(n + "2" + K), out=self.g_p1)
         c.maxpool2x2_idx_bwd(self.i1, self.g_p1, (self.B, 27, 37, 256), out=self.g_c1)
@@ -212,8 +210,8 @@ class MSDNNet:
         hook = self.comm.bucket_ready if self.comm else (lambda *_: None)
         c.conv2d_wgrad(self.d_f3, self.f2, self.g_fine.view(self.B, 55, 74, 1), dw=self.gw("fine/third" + K),
                        db=self.gw("fine/third/bias"))
-        c.conv2d_dgrad(self.d_f3, self.g_fine.view(self.B, 55, 74, 1), self.w("fine/third" + K), out=self.g_f2a)
-        c.relu_bwd(self.f2, self.g_f2a, out=self.g_f2)
+        c.conv2d_dgrad(self.d_f3, self.g_fine.view(self.B, 55, 74, 1), self.w("fine/third" + K), out=self.g_f2,
+                       relu_src=self.f2)
         c.conv2d_wgrad(self.d_f2, self.cat, self.g_f2, dw=self.gw("fine/second/conv2d" + K),
                        db=self.gw("fine/second/conv2d/bias"))
         c.conv2d_dgrad(self.d_f2, self.g_f2, self.w("fine/second/conv2d" + K), out=self.g_cat)

@@ -221,12 +221,13 @@ class Context:
                                         L.EPI_RELU if relu else 0, _ptr(ws), ws.numel(), _stream()), "conv2d_fwd")
         return out
 
-    def conv2d_dgrad(self, d, dy, w, out=None):
+    def conv2d_dgrad(self, d, dy, w, out=None, relu_src=None):
+        """relu_src: post-ReLU activation that was the layer's input -> fused ReluGrad of the producer."""
         if out is None:
             out = torch.empty(d.N, d.H, d.W, d.C, dtype=torch.bfloat16, device=dy.device)
         ws, nb = self.conv_ws(d, L.OP_DGRAD)
-        L.check(self.lib.a3d_conv2d_dgrad(self.h, C.byref(d), _ptr(dy), _ptr(w), _ptr(out), _ptr(ws), ws.numel(),
-                                          _stream()), "conv2d_dgrad")
+        L.check(self.lib.a3d_conv2d_dgrad(self.h, C.byref(d), _ptr(dy), _ptr(w), _ptr(out), _ptr(relu_src), _ptr(ws),
+                                          ws.numel(), _stream()), "conv2d_dgrad")
         return out
 
     def conv2d_wgrad(self, d, x, dy, dw=None, db=None):

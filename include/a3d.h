@@ -96,9 +96,11 @@ int a3d_conv2d_fwd(a3d_ctx*, const a3d_conv_desc*, const uint16_t* x, const uint
                    const float* bias, void* y, int y_dtype, unsigned flags,
                    void* ws, size_t ws_bytes, void* stream);
 /* Replaces Conv2DBackpropInput (autodiff of the above via compute_gradients, src/models.py:314,199).
- * dy bf16 [N,P,Q,ldy], w bf16 OHWI -> dx bf16 [N,H,W,C]. */
+ * dy bf16 [N,P,Q,ldy], w bf16 OHWI -> dx bf16 [N,H,W,C].
+ * relu_src (nullable, bf16 [N,H,W,C]): the post-ReLU activation that was this layer's input; when given
+ * the ReluGrad of the producing layer is fused: dx = relu_src > 0 ? dx : 0. */
 int a3d_conv2d_dgrad(a3d_ctx*, const a3d_conv_desc*, const uint16_t* dy, const uint16_t* w,
-                     uint16_t* dx, void* ws, size_t ws_bytes, void* stream);
+                     uint16_t* dx, const uint16_t* relu_src, void* ws, size_t ws_bytes, void* stream);
 /* Replaces Conv2DBackpropFilter + BiasAddGrad.  dw f32 OHWI, db f32 [K] (nullable).
  * Both are OVERWRITTEN (not accumulated). */
 int a3d_conv2d_wgrad(a3d_ctx*, const a3d_conv_desc*, const uint16_t* x, const uint16_t* dy,

@@ -194,6 +194,9 @@ def test_conv_dgrad_wgrad(ctx, layer, impl):
     gx, gw = torch.autograd.grad(yr, (xr, wr), dy.float().permute(0, 3, 1, 2))
     dx = ctx.conv2d_dgrad(d, dy, w)
     assert rel_err(dx, gx) < 1e-2
+    xpos = torch.relu(x)                                     # fused ReluGrad of the producing layer
+    dxr = ctx.conv2d_dgrad(d, dy, w, relu_src=xpos)
+    assert rel_err(dxr, gx * (xpos.float().permute(0, 3, 1, 2).permute(0, 2, 3, 1) > 0)) < 1e-2
     db = torch.empty(K, dtype=torch.float32, device=DEV)
     dw, _ = ctx.conv2d_wgrad(d, x, dy, db=db)
     assert rel_err(dw, gw) < 2e-3
