@@ -40,8 +40,11 @@ class MSDNNet:
     static batch dimension too: `int(images.shape[0])`, src/models.py:225,256,299)."""
 
     def __init__(self, ctx: ops.Context, batch: int, in_hw=(480, 640), depth_hw=(55, 73), train=True,
-                 beta2=ADAM_BETA2_REFERENCE, impl=L.IMPL_AUTO, dropout_seed=2, comm=None, grad_dtype=torch.float32):
+                 beta2=ADAM_BETA2_REFERENCE, impl=L.IMPL_AUTO, dropout_seed=2, comm=None, grad_dtype=torch.float32,
+                 overlap=True):
         self.ctx, self.B, self.train, self.beta2, self.impl = ctx, batch, train, beta2, impl
+        self.overlap = overlap                # phase-1 step on three streams (see _enqueue_phase1_overlapped)
+        self._s_fine = self._s_wgrad = None
         self.dev = torch.device(f"cuda:{ctx.device}")
         self.in_hw, self.depth_hw = in_hw, depth_hw
         self.comm = comm                      # data-parallel hook (ann3depth_b200.dp.DataParallel) or None
@@ -237,8 +240,132 @@ class MSDNNet:
             self.ctx.adam_tf(a.w[lo:hi], a.g[lo:hi], a.m[lo:hi], a.v[lo:hi], a.wb[lo:hi], ADAM_LR[g], ADAM_BETA1,
                              self.beta2, ADAM_EPS, max(self.adam_t[g], 1), grad_scale, lr_t_dev=self.lr_dev[g])
 
+    # ------------------------------------------------------------------ phase-1 step on three streams
+    def _enqueue_phase1_overlapped(self):
+        """Same launches as forward() + backward_coarse() + apply_adam(), arranged by data dependence:
+             main stream : resize, coarse forward, coarse loss, the dgrad chain (the critical path)
+             fine stream : fine forward + fine loss (needs only the image and the coarse map)
+             wgrad stream: every weight/bias gradient as soon as its dY exists, each optimizer group's
+                           gradient allreduce hand-off and TF-Adam right behind its last wgrad
+           so the HBM-bound Adam of the 67 M dense parameters and the small-grid wgrad kernels run under the
+           tensor-bound dgrad chain instead of after it.  Joins back before global_step += 1."""
+        c, B, K = self.ctx, self.B, "/kernel"
+        dev = self.dev
+        if self._s_fine is None:
+            self._s_fine, self._s_wgrad = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        s0, s1, s2 = torch.cuda.current_stream(), self._s_fine, self._s_wgrad
+        if isinstance(self.overlap, str):            # debugging knob: "fine" or "wgrad" overlaps only that part
+            s1 = s1 if "fine" in self.overlap else s0
+            s2 = s2 if "wgrad" in self.overlap else s0
+        hook = self.comm.bucket_ready if self.comm else (lambda *_: None)
+
+        def mark(stream):
+            e = torch.cuda.Event()
+            e.record(stream)
+            return e
+
+        # ---- main: preprocessing
+        c.resize_bilinear_tf1(self.images, IN_H, IN_W, out=self.img)
+        c.resize_bilinear_tf1(self.depths, OUT_H, OUT_W, out=self.tar)
+        e_img = mark(s0)
+        # ---- fine stream, part 1: first conv + pool need only the image
+        with torch.cuda.stream(s1):
+            c.ws_tag = "fine"
+            s1.wait_event(e_img)
+            c.conv2d_fwd(self.d_f1, self.img, self.w("fine/first/conv2d" + K), self.bias("fine/first/conv2d"), relu=True,
+                         out=self.f1)
+            c.maxpool2x2_fwd_f32(self.f1, out=self.cat, ldy=64, idx=self.if1)
+            c.ws_tag = ""
+        # ---- main: coarse forward
+        n = "coarse/conv/conv2d_"
+        c.conv2d_fwd(self.d_c0, self.img, self.w(n + "0" + K), self.bias(n + "0"), relu=True, out=self.c0)
+        c.maxpool2x2_fwd_f32(self.c0, out=self.p0, idx=self.i0)
+        c.conv2d_fwd(self.d_c1, self.p0, self.w(n + "1" + K), self.bias(n + "1"), relu=True, out=self.c1)
+        c.maxpool2x2_fwd_f32(self.c1, out=self.p1, idx=self.i1)
+        c.conv2d_fwd(self.d_c2, self.p1, self.w(n + "2" + K), self.bias(n + "2"), relu=True, out=self.c2)
+        c.conv2d_fwd(self.d_c3, self.c2, self.w(n + "3" + K), self.bias(n + "3"), relu=True, out=self.c3)
+        c.conv2d_fwd(self.d_c4, self.c3, self.w(n + "4" + K), self.bias(n + "4"), relu=True, out=self.c4)
+        if not self.external_mask:
+            c.bernoulli_mask(self.keep_mask, 0.5, self.dropout_seed, self.step_dev)
+        nd = "coarse/dense/dense_"
+        c.dense_fwd(self.c4.view(B, 12288), self.w(nd + "0" + K), self.bias(nd + "0"), flags=L.EPI_RELU,
+                    keep_mask=self.keep_mask, drop_rate=0.5, out=self.d0, impl=self.impl)
+        c.dense_fwd(self.d0, self.w(nd + "1" + K), self.bias(nd + "1"), flags=0, out=self.coarse, impl=self.impl)
+        e_coarse = mark(s0)
+        # ---- fine stream, part 2
+        with torch.cuda.stream(s1):
+            c.ws_tag = "fine"
+            s1.wait_event(e_coarse)
+            c.scatter_channel_bf16(self.coarse, self.cat, 63)
+            c.conv2d_fwd(self.d_f2, self.cat, self.w("fine/second/conv2d" + K), self.bias("fine/second/conv2d"),
+                         relu=True, out=self.f2)
+            c.conv2d_fwd(self.d_f3, self.f2, self.w("fine/third" + K), self.bias("fine/third"), relu=False,
+                         out=self.fine.view(B, 55, 74, 1))
+            c.silog_loss(self.fine, self.tar, LAMBDA_OVER_N, want_grad=False, loss_ps=self.lps_fine, loss=self.loss_fine,
+                         dout_bf16=self.g_fine)
+            c.ws_tag = ""
+            e_fine = mark(s1)
+        # ---- main: coarse loss, then the dgrad chain; wgrad stream follows each dY
+        c.silog_loss(self.coarse, self.tar, LAMBDA_OVER_N, want_grad=False, loss_ps=self.lps_coarse,
+                     loss=self.loss_coarse, dout_bf16=self.g_coarse, dout_ld=4096)
+        e_g = mark(s0)
+
+        def on_wgrad(event, fn):
+            with torch.cuda.stream(s2):
+                c.ws_tag = "wgrad"
+                s2.wait_event(event)
+                fn()
+                c.ws_tag = ""
+
+        on_wgrad(e_g, lambda: (c.dense_wgrad(self.d0, self.g_coarse, dw=self.gw(nd + "1" + K), db=self.gw(nd + "1/bias"),
+                                             impl=self.impl), hook(self, "dense_1")))
+        c.dense_dgrad(self.g_coarse, self.w(nd + "1" + K), out=self.g_d0a, impl=self.impl)
+        c.dense_epilogue_bwd(self.g_d0a, self.d0, self.keep_mask, 0.5, L.EPI_RELU, out=self.g_d0)
+        e_g = mark(s0)
+
+        on_wgrad(e_g, lambda: (c.dense_wgrad(self.c4.view(B, 12288), self.g_d0, dw=self.gw(nd + "0" + K),
+                                             db=self.gw(nd + "0/bias"), impl=self.impl), hook(self, "dense_0")))
+        c.dense_dgrad(self.g_d0, self.w(nd + "0" + K), out=self.g_c4a.view(B, 12288), impl=self.impl)
+        c.relu_bwd(self.c4, self.g_c4a, out=self.g_c4)
+        e_g = mark(s0)
+        if not self.comm:
+            # single GPU: the dense group's Adam runs under the conv backward.  It overwrites the dense weight
+            # mirror, so it waits for e_g: both dense dgrads (the last readers of those weights) are done.
+            on_wgrad(e_g, lambda: self.apply_adam(("CoarseDense",)))
+        on_wgrad(e_g, lambda: c.conv2d_wgrad(self.d_c4, self.c3, self.g_c4, dw=self.gw(n + "4" + K), db=self.gw(n + "4/bias")))
+        c.conv2d_dgrad(self.d_c4, self.g_c4, self.w(n + "4" + K), out=self.g_c3, relu_src=self.c3)
+        e_g = mark(s0)
+        on_wgrad(e_g, lambda: c.conv2d_wgrad(self.d_c3, self.c2, self.g_c3, dw=self.gw(n + "3" + K), db=self.gw(n + "3/bias")))
+        c.conv2d_dgrad(self.d_c3, self.g_c3, self.w(n + "3" + K), out=self.g_c2, relu_src=self.c2)
+        e_g = mark(s0)
+        on_wgrad(e_g, lambda: c.conv2d_wgrad(self.d_c2, self.p1, self.g_c2, dw=self.gw(n + "2" + K), db=self.gw(n + "2/bias")))
+        c.conv2d_dgrad(self.d_c2, self.g_c2, self.w(n + "2" + K), out=self.g_p1)
+        c.maxpool2x2_idx_bwd(self.i1, self.g_p1, (B, 27, 37, 256), out=self.g_c1)
+        e_g = mark(s0)
+        on_wgrad(e_g, lambda: c.conv2d_wgrad(self.d_c1, self.p0, self.g_c1, dw=self.gw(n + "1" + K), db=self.gw(n + "1/bias")))
+        c.conv2d_dgrad(self.d_c1, self.g_c1, self.w(n + "1" + K), out=self.g_p0)
+        c.maxpool2x2_idx_bwd(self.i0, self.g_p0, (B, 55, 74, 96), out=self.g_c0)
+        e_g = mark(s0)
+
+        def conv0_and_adam():
+            c.conv2d_wgrad(self.d_c0, self.img, self.g_c0, dw=self.gw(n + "0" + K), db=self.gw(n + "0/bias"))
+            self._mask_padding("coarse/conv/conv2d_0/kernel")
+            hook(self, "coarse_conv")
+            if self.comm:
+                self.comm.wait_all(self)
+                self.apply_adam(("CoarseDense", "CoarseConv"), 1.0 / self.comm.world)
+            else:
+                self.apply_adam(("CoarseConv",))
+        on_wgrad(e_g, conv0_and_adam)
+        # ---- join
+        s0.wait_event(e_fine)
+        s0.wait_event(mark(s2))
+        c.increment_i64(self.step_dev)
+
     # ------------------------------------------------------------------ one session.run(model_op)
     def _enqueue_step(self, phase):
+        if phase == 1 and self.overlap and self.train:
+            return self._enqueue_phase1_overlapped()
         self.forward()
         if phase == 1:
             self.backward_coarse()

@@ -65,6 +65,7 @@ class Context:
         L.check(self.lib.a3d_create(device, C.byref(h)), "a3d_create")
         self.h = h
         self._ws = {}
+        self.ws_tag = ""          # set per stream by multi-stream callers: concurrent launches must not share scratch
 
     def close(self):
         if getattr(self, "h", None):
@@ -88,6 +89,7 @@ class Context:
     def workspace(self, key, nbytes):
         """Persistent scratch buffers (allocated once, so steps stay CUDA-graph capturable)."""
         nbytes = max(int(nbytes), 256)
+        key = (key, self.ws_tag)
         t = self._ws.get(key)
         if t is None or t.numel() < nbytes:
             t = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{self.device}")
