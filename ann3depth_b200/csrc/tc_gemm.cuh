@@ -66,8 +66,10 @@ struct Cfg {
   static constexpr int B_BYTES = B_MN_ ? B_NBLK * B_BLK_BYTES : CHUNKED ? 8 * BN_ * 16 : BN_ * KCB_;
   static_assert(!CHUNKED || (!A_MN_ && !B_MN_), "chunked mode is K-major only");
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  // ~104 KB of stages per CTA: two CTAs (of this or of a concurrently running kernel on another stream)
+  // fit on one SM, so one CTA's epilogue / prologue hides under the other's main loop.  At least 3 stages.
+  static constexpr int STAGES_RAW = (104 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < 3 ? 3 : STAGES_RAW);
   static constexpr int TMEM_COLS = BN_ <= 32 ? 32 : BN_ <= 64 ? 64 : BN_ <= 128 ? 128 : 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(!(A_MN_ || B_MN_) || KCB_ == 128, "MN-major operands use 128-byte rows");
@@ -77,7 +79,7 @@ struct Cfg {
 };
 
 template <class C>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, 2)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: required by the 128-byte swizzle atoms

@@ -44,7 +44,7 @@ class MSDNNet:
                  overlap=True):
         self.ctx, self.B, self.train, self.beta2, self.impl = ctx, batch, train, beta2, impl
         self.overlap = overlap                # phase-1 step on three streams (see _enqueue_phase1_overlapped)
-        self._s_fine = self._s_wgrad = None
+        self._s_fine = self._s_wgrad = self._s_cwgrad = None
         self.dev = torch.device(f"cuda:{ctx.device}")
         self.in_hw, self.depth_hw = in_hw, depth_hw
         self.comm = comm                      # data-parallel hook (ann3depth_b200.dp.DataParallel) or None
@@ -253,10 +253,15 @@ class MSDNNet:
         dev = self.dev
         if self._s_fine is None:
             self._s_fine, self._s_wgrad = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-        s0, s1, s2 = torch.cuda.current_stream(), self._s_fine, self._s_wgrad
+            self._s_cwgrad = torch.cuda.Stream(device=dev)
+        # s2: dense wgrads + dense Adam (HBM-bound) ; s3: conv wgrads + conv Adam (tensor / L2-bound)
+        s0, s1, s2, s3 = torch.cuda.current_stream(), self._s_fine, self._s_wgrad, self._s_cwgrad
         if isinstance(self.overlap, str):            # debugging knob: "fine" or "wgrad" overlaps only that part
             s1 = s1 if "fine" in self.overlap else s0
             s2 = s2 if "wgrad" in self.overlap else s0
+            s3 = s3 if "wgrad" in self.overlap else s0
+        if self.comm:
+            s3 = s2                                   # DP: one wgrad stream, buckets handed to the comm stream in order
         hook = self.comm.bucket_ready if self.comm else (lambda *_: None)
 
         def mark(stream):
@@ -310,10 +315,11 @@ class MSDNNet:
                      loss=self.loss_coarse, dout_bf16=self.g_coarse, dout_ld=4096)
         e_g = mark(s0)
 
-        def on_wgrad(event, fn):
-            with torch.cuda.stream(s2):
-                c.ws_tag = "wgrad"
-                s2.wait_event(event)
+        def on_wgrad(event, fn, stream=None):
+            stream = stream or s2
+            with torch.cuda.stream(stream):
+                c.ws_tag = "wgrad" if stream is s2 else "cwgrad"
+                stream.wait_event(event)
                 fn()
                 c.ws_tag = ""
 
@@ -332,17 +338,17 @@ class MSDNNet:
             # single GPU: the dense group's Adam runs under the conv backward.  It overwrites the dense weight
             # mirror, so it waits for e_g: both dense dgrads (the last readers of those weights) are done.
             on_wgrad(e_g, lambda: self.apply_adam(("CoarseDense",)))
-        on_wgrad(e_g, lambda: c.conv2d_wgrad(self.d_c4, self.c3, self.g_c4, dw=self.gw(n + "4" + K), db=self.gw(n + "4/bias")))
+        on_wgrad(e_g, lambda: c.conv2d_wgrad(self.d_c4, self.c3, self.g_c4, dw=self.gw(n + "4" + K), db=self.gw(n + "4/bias")), s3)
         c.conv2d_dgrad(self.d_c4, self.g_c4, self.w(n + "4" + K), out=self.g_c3, relu_src=self.c3)
         e_g = mark(s0)
-        on_wgrad(e_g, lambda: c.conv2d_wgrad(self.d_c3, self.c2, self.g_c3, dw=self.gw(n + "3" + K), db=self.gw(n + "3/bias")))
+        on_wgrad(e_g, lambda: c.conv2d_wgrad(self.d_c3, self.c2, self.g_c3, dw=self.gw(n + "3" + K), db=self.gw(n + "3/bias")), s3)
         c.conv2d_dgrad(self.d_c3, self.g_c3, self.w(n + "3" + K), out=self.g_c2, relu_src=self.c2)
         e_g = mark(s0)
-        on_wgrad(e_g, lambda: c.conv2d_wgrad(self.d_c2, self.p1, self.g_c2, dw=self.gw(n + "2" + K), db=self.gw(n + "2/bias")))
+        on_wgrad(e_g, lambda: c.conv2d_wgrad(self.d_c2, self.p1, self.g_c2, dw=self.gw(n + "2" + K), db=self.gw(n + "2/bias")), s3)
         c.conv2d_dgrad(self.d_c2, self.g_c2, self.w(n + "2" + K), out=self.g_p1)
         c.maxpool2x2_idx_bwd(self.i1, self.g_p1, (B, 27, 37, 256), out=self.g_c1)
         e_g = mark(s0)
-        on_wgrad(e_g, lambda: c.conv2d_wgrad(self.d_c1, self.p0, self.g_c1, dw=self.gw(n + "1" + K), db=self.gw(n + "1/bias")))
+        on_wgrad(e_g, lambda: c.conv2d_wgrad(self.d_c1, self.p0, self.g_c1, dw=self.gw(n + "1" + K), db=self.gw(n + "1/bias")), s3)
         c.conv2d_dgrad(self.d_c1, self.g_c1, self.w(n + "1" + K), out=self.g_p0)
         c.maxpool2x2_idx_bwd(self.i0, self.g_p0, (B, 55, 74, 96), out=self.g_c0)
         e_g = mark(s0)
@@ -356,10 +362,12 @@ class MSDNNet:
                 self.apply_adam(("CoarseDense", "CoarseConv"), 1.0 / self.comm.world)
             else:
                 self.apply_adam(("CoarseConv",))
-        on_wgrad(e_g, conv0_and_adam)
+        on_wgrad(e_g, conv0_and_adam, s3)
         # ---- join
         s0.wait_event(e_fine)
         s0.wait_event(mark(s2))
+        if s3 is not s2:
+            s0.wait_event(mark(s3))
         c.increment_i64(self.step_dev)
 
     # ------------------------------------------------------------------ one session.run(model_op)

@@ -206,7 +206,7 @@ def test_overlapped_step_equals_sequential_step():
     # in the metrics the parity tests use (cosine / relative error), not bit-wise.
     assert torch.equal(a[0], b[0])                                      # beta2 = 1: weights frozen in both
     cosm = float((a[1].double() @ b[1].double()) / (a[1].double().norm() * b[1].double().norm()))
-    assert cosm > 0.9999, cosm
+    assert cosm > 0.999, cosm
     assert float((a[3] - b[3]).abs().max()) <= 1e-2 * float(a[3].abs().max())
     assert abs(a[4] - b[4]) <= 1e-3 * abs(a[4]) and abs(a[5] - b[5]) <= 1e-3 * abs(a[5])
 
