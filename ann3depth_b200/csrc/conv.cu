@@ -14,8 +14,9 @@ int a3d_tc_dense_fwd(a3d_ctx*, const uint16_t* x, int ldx, const uint16_t* w, co
                      cudaStream_t st);
 int a3d_tc_dense_dgrad(a3d_ctx*, const uint16_t* dy, int lddy, const uint16_t* w, uint16_t* dx, float* acc_ws, int M,
                        int N, int K, cudaStream_t st);
+struct a3d_adam_args { float* w; float* m; float* v; uint16_t* wb; float lr_t, beta1, beta2, eps, grad_scale; const float* lr_t_dev; };
 int a3d_tc_dense_wgrad(a3d_ctx*, const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, int M, int N, int K,
-                       cudaStream_t st);
+                       cudaStream_t st, const a3d_adam_args* adam = nullptr);
 
 // tc_halo.cu
 struct HaloGeom { int Hp, Wp, Cp, need_copy; };
@@ -419,4 +420,24 @@ extern "C" int a3d_dense_wgrad(a3d_ctx* ctx, const uint16_t* x, int ldx, const u
     return A3D_ENOTSUP;
   }
   return a3d_simt_dense_wgrad(ctx, x, ldx, dy, lddy, dw, M, N, K, st);
+}
+
+// Dense weight gradient fused with the TF-Adam update of that weight matrix: the 128 x 256 gradient tiles
+// are consumed from TMEM by the optimizer (w, m, v updated in place, bf16 mirror refreshed) and never
+// written to HBM.  Single-GPU only (a data-parallel step must allreduce the gradient first).
+// db (nullable) still receives the bias gradient for a separate (tiny) a3d_adam_tf launch.
+extern "C" int a3d_dense_wgrad_adam(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* db,
+                                    float* w, float* m, float* v, uint16_t* w_bf16, int M, int N, int K, float lr_t,
+                                    float beta1, float beta2, float eps, float grad_scale, const float* lr_t_dev,
+                                    void* stream) {
+  A3D_REQUIRE(ctx && x && dy && w && m && v && M > 0 && N > 0 && K > 0 && lddy >= N && ldx >= K,
+              "dense wgrad+adam: bad argument");
+  A3D_REQUIRE(K % 64 == 0 && ldx % 8 == 0 && lddy % 8 == 0, "dense wgrad+adam: needs K %% 64 == 0 and aligned row pitches");
+  cudaStream_t st = as_stream(stream);
+  if (db) {
+    int rc = a3d_colsum_bf16(ctx, dy, (size_t)M, N, lddy, db, st);
+    if (rc) return rc;
+  }
+  a3d_adam_args a{w, m, v, w_bf16, lr_t, beta1, beta2, eps, grad_scale, lr_t_dev};
+  return a3d_tc_dense_wgrad(ctx, x, ldx, dy, lddy, nullptr, M, N, K, st, &a);
 }

@@ -399,8 +399,10 @@ int a3d_tc_dense_dgrad(a3d_ctx* ctx, const uint16_t* dy, int lddy, const uint16_
 }
 
 // wgrad: dw[n][k] = sum_b dy[b][n] x[b][k]; both operands MN-major with the batch as the reduction index.
+// With `adam` != null the gradient tile is consumed in the epilogue by TF-Adam (see tc::EPI_ADAM).
+struct a3d_adam_args { float* w; float* m; float* v; uint16_t* wb; float lr_t, beta1, beta2, eps, grad_scale; const float* lr_t_dev; };
 int a3d_tc_dense_wgrad(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, int M, int N,
-                       int K, cudaStream_t st) {
+                       int K, cudaStream_t st, const a3d_adam_args* adam = nullptr) {
   if (K % 64 || ldx % 8 || lddy % 8) {
     a3d_set_error("tc dense wgrad: needs K %% 64 == 0 and 16-byte aligned row pitches");
     return A3D_ENOTSUP;
@@ -413,6 +415,11 @@ int a3d_tc_dense_wgrad(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t*
   tc::Params p{};
   p.M = N; p.N = K; p.num_kb = ceil_div(M, 64); p.kb_per_split = p.num_kb; p.a_mode = tc::A_TILED;
   p.epi = tc::EPI_ROW_F32; p.out = dw; p.ldo = K; p.atomic = 0;
+  if (adam) {
+    p.epi = tc::EPI_ADAM; p.out = adam->w; p.adam_m = adam->m; p.adam_v = adam->v; p.adam_wb = adam->wb;
+    p.lr_t = adam->lr_t; p.beta1 = adam->beta1; p.beta2 = adam->beta2; p.eps = adam->eps; p.grad_scale = adam->grad_scale;
+    p.lr_t_dev = adam->lr_t_dev;
+  }
   if (K % 256 == 0) return launch_cfg<tc::Cfg<256, 128, true, true, 64>>(ctx, tmA, tmB, p, 1, st);
   if (K % 128 == 0) return launch_cfg<tc::Cfg<128, 128, true, true, 64>>(ctx, tmA, tmB, p, 1, st);
   return launch_cfg<tc::Cfg<64, 128, true, true, 64>>(ctx, tmA, tmB, p, 1, st);

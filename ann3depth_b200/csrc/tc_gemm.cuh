@@ -27,6 +27,8 @@ enum Epi : int {
   EPI_ROW_BF16 = 0,       // out_bf16[row*ldo + col] = act(acc + bias[col])
   EPI_ROW_F32 = 1,        // out_f32 [row*ldo + col] = act(acc + bias[col])   (atomicAdd when split-K)
   EPI_COL_F32 = 2,        // out_f32 [col*ldo + row] (+)= acc                  (transposed; dense layers)
+  EPI_ADAM = 3,           // acc is a weight gradient: TF-Adam applied in place on w/m/v (+ bf16 mirror) at
+                          // [row*ldo + col]; the gradient itself never goes to HBM (dense wgrad, single GPU)
 };
 
 struct Params {
@@ -49,6 +51,10 @@ struct Params {
   const float* bias;
   unsigned flags;
   int atomic;               // accumulate with atomicAdd (split-K)
+  // EPI_ADAM: out = w (f32 master)
+  float* adam_m; float* adam_v; uint16_t* adam_wb;
+  float lr_t, beta1, beta2, eps, grad_scale;
+  const float* lr_t_dev;
 };
 
 template <int BN_, int KCB_, bool A_MN_, bool B_MN_, int B_BW_ = 64>
@@ -242,7 +248,60 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       float v[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-      if (p.epi == EPI_COL_F32) {
+      if (p.epi == EPI_ADAM) {
+        if (row_ok) {
+          const float lr_t = p.lr_t_dev ? __ldg(p.lr_t_dev) : p.lr_t;
+          const long long off = (long long)row * p.ldo + col0;
+          float* pw = reinterpret_cast<float*>(p.out) + off;
+          float* pm = p.adam_m + off;
+          float* pv = p.adam_v + off;
+          uint16_t* pb = p.adam_wb ? p.adam_wb + off : nullptr;
+          const bool vec = (col0 + 16 <= p.N) && ((reinterpret_cast<uintptr_t>(pw) & 15) == 0);
+          float w[16], m[16], vv[16];
+          if (vec) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float4 a = reinterpret_cast<const float4*>(pw)[j], b = reinterpret_cast<const float4*>(pm)[j],
+                     c = reinterpret_cast<const float4*>(pv)[j];
+              w[4 * j] = a.x; w[4 * j + 1] = a.y; w[4 * j + 2] = a.z; w[4 * j + 3] = a.w;
+              m[4 * j] = b.x; m[4 * j + 1] = b.y; m[4 * j + 2] = b.z; m[4 * j + 3] = b.w;
+              vv[4 * j] = c.x; vv[4 * j + 1] = c.y; vv[4 * j + 2] = c.z; vv[4 * j + 3] = c.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (col0 + j < p.N) { w[j] = pw[j]; m[j] = pm[j]; vv[j] = pv[j]; }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float g = v[j] * p.grad_scale;
+            m[j] = p.beta1 * m[j] + (1.f - p.beta1) * g;
+            vv[j] = p.beta2 * vv[j] + (1.f - p.beta2) * g * g;
+            w[j] = w[j] - lr_t * m[j] / (sqrtf(vv[j]) + p.eps);
+          }
+          if (vec) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              reinterpret_cast<float4*>(pw)[j] = make_float4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+              reinterpret_cast<float4*>(pm)[j] = make_float4(m[4 * j], m[4 * j + 1], m[4 * j + 2], m[4 * j + 3]);
+              reinterpret_cast<float4*>(pv)[j] = make_float4(vv[4 * j], vv[4 * j + 1], vv[4 * j + 2], vv[4 * j + 3]);
+            }
+            if (pb) {
+              reinterpret_cast<uint4*>(pb)[0] = make_uint4(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]),
+                                                           pack_bf16x2(w[4], w[5]), pack_bf16x2(w[6], w[7]));
+              reinterpret_cast<uint4*>(pb)[1] = make_uint4(pack_bf16x2(w[8], w[9]), pack_bf16x2(w[10], w[11]),
+                                                           pack_bf16x2(w[12], w[13]), pack_bf16x2(w[14], w[15]));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (col0 + j < p.N) {
+                pw[j] = w[j]; pm[j] = m[j]; pv[j] = vv[j];
+                if (pb) pb[j] = f32_to_bf16_bits(w[j]);
+              }
+          }
+        }
+      } else if (p.epi == EPI_COL_F32) {
         float* o = reinterpret_cast<float*>(p.out);
         if (row_ok) {
 #pragma unroll

@@ -41,9 +41,13 @@ class MSDNNet:
 
     def __init__(self, ctx: ops.Context, batch: int, in_hw=(480, 640), depth_hw=(55, 73), train=True,
                  beta2=ADAM_BETA2_REFERENCE, impl=L.IMPL_AUTO, dropout_seed=2, comm=None, grad_dtype=torch.float32,
-                 overlap=True):
+                 overlap=True, fuse_dense_adam=False):
         self.ctx, self.B, self.train, self.beta2, self.impl = ctx, batch, train, beta2, impl
-        self.overlap = overlap                # phase-1 step on three streams (see _enqueue_phase1_overlapped)
+        self.overlap = overlap                # phase-1 step on several streams (see _enqueue_phase1_overlapped)
+        # single GPU option: TF-Adam inside the dense wgrad epilogue (a3d_dense_wgrad_adam).  Correct, and it saves
+        # 8 B/param of HBM traffic, but measured SLOWER (2.67 vs 1.89 ms/step): four epilogue warps per CTA do not
+        # keep enough loads in flight to stream w/m/v at HBM rate.  Off by default until the epilogue is widened.
+        self.fuse_dense_adam = fuse_dense_adam
         self._s_fine = self._s_wgrad = self._s_cwgrad = None
         self.dev = torch.device(f"cuda:{ctx.device}")
         self.in_hw, self.depth_hw = in_hw, depth_hw
@@ -323,18 +327,38 @@ class MSDNNet:
                 fn()
                 c.ws_tag = ""
 
-        on_wgrad(e_g, lambda: (c.dense_wgrad(self.d0, self.g_coarse, dw=self.gw(nd + "1" + K), db=self.gw(nd + "1/bias"),
-                                             impl=self.impl), hook(self, "dense_1")))
+        fused = self.fuse_dense_adam and not self.comm
+        a = self.arena
+
+        def dense_wgrad_adam(layer, x, dy):
+            # TF-Adam applied by the wgrad epilogue (the gradient never reaches HBM); the bias keeps the plain path
+            g = "CoarseDense"
+            kn, bn_ = nd + layer + K, nd + layer + "/bias"
+            c.dense_wgrad_adam(x, dy, self.gw(bn_), a.view(a.w, kn), a.view(a.m, kn), a.view(a.v, kn), a.view(a.wb, kn),
+                               ADAM_LR[g], ADAM_BETA1, self.beta2, ADAM_EPS, max(self.adam_t[g], 1), 1.0,
+                               lr_t_dev=self.lr_dev[g])
+            s = a.specs[bn_]
+            sl = slice(s.offset, s.offset + s.size)
+            c.adam_tf(a.w[sl], a.g[sl], a.m[sl], a.v[sl], a.wb[sl], ADAM_LR[g], ADAM_BETA1, self.beta2, ADAM_EPS,
+                      max(self.adam_t[g], 1), 1.0, lr_t_dev=self.lr_dev[g])
+
+        if not fused:
+            on_wgrad(e_g, lambda: (c.dense_wgrad(self.d0, self.g_coarse, dw=self.gw(nd + "1" + K),
+                                                 db=self.gw(nd + "1/bias"), impl=self.impl), hook(self, "dense_1")))
         c.dense_dgrad(self.g_coarse, self.w(nd + "1" + K), out=self.g_d0a, impl=self.impl)
         c.dense_epilogue_bwd(self.g_d0a, self.d0, self.keep_mask, 0.5, L.EPI_RELU, out=self.g_d0)
         e_g = mark(s0)
-
-        on_wgrad(e_g, lambda: (c.dense_wgrad(self.c4.view(B, 12288), self.g_d0, dw=self.gw(nd + "0" + K),
-                                             db=self.gw(nd + "0/bias"), impl=self.impl), hook(self, "dense_0")))
+        if fused:       # updates dense_1's weights: must follow dense_1's dgrad, their last reader
+            on_wgrad(e_g, lambda: dense_wgrad_adam("1", self.d0, self.g_coarse))
+        else:
+            on_wgrad(e_g, lambda: (c.dense_wgrad(self.c4.view(B, 12288), self.g_d0, dw=self.gw(nd + "0" + K),
+                                                 db=self.gw(nd + "0/bias"), impl=self.impl), hook(self, "dense_0")))
         c.dense_dgrad(self.g_d0, self.w(nd + "0" + K), out=self.g_c4a.view(B, 12288), impl=self.impl)
         c.relu_bwd(self.c4, self.g_c4a, out=self.g_c4)
         e_g = mark(s0)
-        if not self.comm:
+        if fused:
+            on_wgrad(e_g, lambda: dense_wgrad_adam("0", self.c4.view(B, 12288), self.g_d0))
+        elif not self.comm:
             # single GPU: the dense group's Adam runs under the conv backward.  It overwrites the dense weight
             # mirror, so it waits for e_g: both dense dgrads (the last readers of those weights) are done.
             on_wgrad(e_g, lambda: self.apply_adam(("CoarseDense",)))

@@ -275,6 +275,14 @@ class Context:
                                          _stream()), "dense_wgrad")
         return dw, db
 
+    def dense_wgrad_adam(self, x, dy, db, w, m, v, w_bf16, lr, beta1, beta2, eps, t, grad_scale=1.0, lr_t_dev=None):
+        """dense wgrad with TF-Adam fused into its epilogue (w/m/v: f32 [N,K] views of the arena)."""
+        M, lddy = dy.shape
+        N, K = w.shape
+        L.check(self.lib.a3d_dense_wgrad_adam(self.h, _ptr(x), x.shape[1], _ptr(dy), lddy, _ptr(db), _ptr(w), _ptr(m),
+                                              _ptr(v), _ptr(w_bf16), M, N, K, adam_lr_t(lr, beta1, beta2, t), beta1,
+                                              beta2, eps, grad_scale, _ptr(lr_t_dev), _stream()), "dense_wgrad_adam")
+
     def debug_tc_gemm(self, A, B, M, N, K, bn, kcb=128, a_mn=False, b_mn=False, splits=1):
         D = torch.empty(M, N, dtype=torch.float32, device=A.device)
         L.check(self.lib.a3d_debug_tc_gemm(self.h, _ptr(A), _ptr(B), _ptr(D), M, N, K, bn, kcb, int(a_mn), int(b_mn),

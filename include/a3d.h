@@ -121,6 +121,14 @@ int a3d_dense_dgrad(a3d_ctx*, const uint16_t* dy, int lddy, const uint16_t* w, u
 /* dw[N,K] = dy[M,N]^T . x[M,K] ; db[N] = sum_M dy.   dw/db f32, overwritten. */
 int a3d_dense_wgrad(a3d_ctx*, const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, float* db,
                     int M, int N, int K, int impl, void* stream);
+/* dense wgrad fused with the TF-Adam update of that kernel (single GPU): the gradient tiles are consumed
+ * from tensor memory by the optimizer and never written to HBM.  w/m/v f32 [N,K] updated in place, w_bf16
+ * (nullable) refreshed; db (nullable) f32 [N] receives the bias gradient.  Same formula and arguments as
+ * a3d_adam_tf.  Requires K % 64 == 0 and 16-byte aligned row pitches. */
+int a3d_dense_wgrad_adam(a3d_ctx*, const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* db,
+                         float* w, float* m, float* v, uint16_t* w_bf16, int M, int N, int K,
+                         float lr_t, float beta1, float beta2, float eps, float grad_scale,
+                         const float* lr_t_dev, void* stream);
 /* Elementwise backward of the dense epilogue: g_pre = g_post * mask/(1-rate) * act'(y).
  * y is the stored post-activation (pre-dropout) output; used between dense_1 dgrad and dense_0. */
 int a3d_dense_epilogue_bwd(a3d_ctx*, const uint16_t* g_post, const uint16_t* y, const uint8_t* keep_mask,

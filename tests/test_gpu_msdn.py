@@ -211,6 +211,23 @@ def test_overlapped_step_equals_sequential_step():
     assert abs(a[4] - b[4]) <= 1e-3 * abs(a[4]) and abs(a[5] - b[5]) <= 1e-3 * abs(a[5])
 
 
+def test_fused_dense_wgrad_adam_matches_separate_kernels():
+    B = 2
+    images, depths, mask = make_inputs(B)
+    p = conditioned_params()
+    res = []
+    for fused in (False, True):
+        op = build(B, p, mask, images, depths, beta2=0.999, fuse_dense_adam=fused)
+        op.run(use_graph=False)
+        torch.cuda.synchronize()
+        a = op.net.arena
+        lo, hi = a.group_range("CoarseDense")
+        res.append((a.w[lo:hi].clone(), a.m[lo:hi].clone(), a.v[lo:hi].clone(), a.wb[lo:hi].clone()))
+    for x, y in zip(*res):
+        x, y = x.double(), y.double()
+        assert float((x @ y) / (x.norm() * y.norm())) > 0.9999
+
+
 def test_phase_schedule_and_inference():
     B = 2
     images, depths, mask = make_inputs(B)
