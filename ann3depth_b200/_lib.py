@@ -54,6 +54,7 @@ SIGNATURES = {
     "a3d_relu_bwd": (_i, [_vp, _vp, _vp, _i, _vp, _sz, _i, _vp]),
     "a3d_silog_loss": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp, _i, _vp]),
     "a3d_adam_tf": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _vp, _vp]),
+    "a3d_adam_tf_bf16g": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _vp, _vp]),
     "a3d_sgd": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _vp]),
     "a3d_bernoulli_mask": (_i, [_vp, _vp, _sz, _f, C.c_uint64, _vp, _vp]),
     "a3d_increment_i64": (_i, [_vp, _vp, _vp]),
@@ -73,6 +74,8 @@ SIGNATURES = {
     "a3d_comm_init": (_i, [_vp, C.c_char_p, _vp, _i, _i]),
     "a3d_comm_destroy": (_i, [_vp]),
     "a3d_allreduce_sum": (_i, [_vp, _vp, _sz, _i, _vp]),
+    "a3d_reduce_scatter_sum": (_i, [_vp, _vp, _sz, _i, _vp]),
+    "a3d_allgather": (_i, [_vp, _vp, _sz, _i, _vp]),
     # engine unit-test hook (not part of the drop-in surface)
     "a3d_debug_tc_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "a3d_debug_tc_shift": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -12,6 +12,9 @@ typedef int (*fn_init_rank)(void** comm, int nranks, nccl_uid id, int rank);
 typedef int (*fn_destroy)(void* comm);
 typedef int (*fn_allreduce)(const void* send, void* recv, size_t count, int dtype, int op, void* comm, cudaStream_t st);
 typedef const char* (*fn_errstr)(int);
+typedef int (*fn_reduce_scatter)(const void* send, void* recv, size_t recvcount, int dtype, int op, void* comm, cudaStream_t st);
+typedef int (*fn_allgather)(const void* send, void* recv, size_t sendcount, int dtype, void* comm, cudaStream_t st);
+typedef int (*fn_comm_rank)(void* comm, int* rank);
 
 void* open_nccl(const char* path) {
   void* h = dlopen(path && path[0] ? path : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
@@ -71,5 +74,39 @@ extern "C" int a3d_allreduce_sum(a3d_ctx* ctx, void* buf, size_t count, int dtyp
   int nd = dtype == A3D_BF16 ? 9 : 7;
   int r = f(buf, buf, count, nd, 0, ctx->nccl_comm, as_stream(stream));
   if (r) { a3d_set_error("ncclAllReduce -> %d", r); return A3D_ENCCL; }
+  return 0;
+}
+
+static int comm_rank(a3d_ctx* ctx, int* rank) {
+  fn_comm_rank f = (fn_comm_rank)dlsym(ctx->nccl_lib, "ncclCommUserRank");
+  if (!f || f(ctx->nccl_comm, rank)) { a3d_set_error("ncclCommUserRank failed"); return A3D_ENCCL; }
+  return 0;
+}
+
+extern "C" int a3d_reduce_scatter_sum(a3d_ctx* ctx, void* buf, size_t chunk, int dtype, void* stream) {
+  A3D_REQUIRE(ctx && buf, "reduce_scatter: null argument");
+  if (!ctx->nccl_comm) { a3d_set_error("reduce_scatter: communicator not initialised"); return A3D_ENCCL; }
+  fn_reduce_scatter f = (fn_reduce_scatter)dlsym(ctx->nccl_lib, "ncclReduceScatter");
+  if (!f) { a3d_set_error("ncclReduceScatter not found"); return A3D_ENCCL; }
+  int rank = 0, rc = comm_rank(ctx, &rank);
+  if (rc) return rc;
+  const size_t es = dtype == A3D_BF16 ? 2 : 4;
+  int r = f(buf, reinterpret_cast<char*>(buf) + (size_t)rank * chunk * es, chunk, dtype == A3D_BF16 ? 9 : 7, 0,
+            ctx->nccl_comm, as_stream(stream));
+  if (r) { a3d_set_error("ncclReduceScatter -> %d", r); return A3D_ENCCL; }
+  return 0;
+}
+
+extern "C" int a3d_allgather(a3d_ctx* ctx, void* buf, size_t chunk, int dtype, void* stream) {
+  A3D_REQUIRE(ctx && buf, "allgather: null argument");
+  if (!ctx->nccl_comm) { a3d_set_error("allgather: communicator not initialised"); return A3D_ENCCL; }
+  fn_allgather f = (fn_allgather)dlsym(ctx->nccl_lib, "ncclAllGather");
+  if (!f) { a3d_set_error("ncclAllGather not found"); return A3D_ENCCL; }
+  int rank = 0, rc = comm_rank(ctx, &rank);
+  if (rc) return rc;
+  const size_t es = dtype == A3D_BF16 ? 2 : 4;
+  int r = f(reinterpret_cast<char*>(buf) + (size_t)rank * chunk * es, buf, chunk, dtype == A3D_BF16 ? 9 : 7,
+            ctx->nccl_comm, as_stream(stream));
+  if (r) { a3d_set_error("ncclAllGather -> %d", r); return A3D_ENCCL; }
   return 0;
 }

@@ -562,3 +562,41 @@ extern "C" int a3d_maxpool2x2_idx_bwd(a3d_ctx* ctx, const uint8_t* idx, const ui
   A3D_LAUNCH_OK(ctx);
   return 0;
 }
+
+// TF-Adam with a bf16 gradient (data-parallel exchange dtype): 14 B read + 14 B written per parameter.
+__global__ void adam_tf_bf16g_kernel(float4* __restrict__ w, const uint2* __restrict__ g, float4* __restrict__ m,
+                                     float4* __restrict__ v, uint2* __restrict__ wb, size_t n4, float lr_t, float b1,
+                                     float b2, float eps, float gs, const float* __restrict__ lr_dev) {
+  if (lr_dev) lr_t = __ldg(lr_dev);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 W = w[i], M = m[i], V = v[i];
+    uint2 G = __ldg(g + i);
+    float gk[4] = {__uint_as_float(G.x << 16), __uint_as_float(G.x & 0xffff0000u), __uint_as_float(G.y << 16),
+                   __uint_as_float(G.y & 0xffff0000u)};
+    float* pw = &W.x; float* pm = &M.x; float* pv = &V.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float gg = gk[k] * gs;
+      pm[k] = b1 * pm[k] + (1.f - b1) * gg;
+      pv[k] = b2 * pv[k] + (1.f - b2) * gg * gg;
+      pw[k] = pw[k] - lr_t * pm[k] / (sqrtf(pv[k]) + eps);
+    }
+    w[i] = W; m[i] = M; v[i] = V;
+    if (wb) wb[i] = make_uint2(pack_bf16x2(W.x, W.y), pack_bf16x2(W.z, W.w));
+  }
+}
+extern "C" int a3d_adam_tf_bf16g(a3d_ctx* ctx, float* w, const uint16_t* g, float* m, float* v, uint16_t* w_bf16, size_t n,
+                                 float lr_t, float beta1, float beta2, float eps, float grad_scale, const float* lr_t_dev,
+                                 void* stream) {
+  A3D_REQUIRE(ctx && w && g && m && v, "adam_bf16g: null argument");
+  A3D_REQUIRE(n % 4 == 0 && aligned16(w) && aligned16(m) && aligned16(v) && (reinterpret_cast<uintptr_t>(g) & 7) == 0 &&
+                  (!w_bf16 || (reinterpret_cast<uintptr_t>(w_bf16) & 7) == 0),
+              "adam_bf16g: segment must be a multiple of 4 elements and 16-byte aligned");
+  if (n == 0) return 0;
+  int block = 256, grid = grid_for(ctx, n / 4, block);
+  adam_tf_bf16g_kernel<<<grid, block, 0, as_stream(stream)>>>(
+      reinterpret_cast<float4*>(w), reinterpret_cast<const uint2*>(g), reinterpret_cast<float4*>(m),
+      reinterpret_cast<float4*>(v), reinterpret_cast<uint2*>(w_bf16), n / 4, lr_t, beta1, beta2, eps, grad_scale, lr_t_dev);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}

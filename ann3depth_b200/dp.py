@@ -41,18 +41,67 @@ class DataParallel:
         hi = max(a.specs[k].offset + a.specs[k].size for k in keys)
         return lo, hi
 
-    def bucket_ready(self, net, name):
-        """Called right after the wgrad kernels of a bucket were enqueued on the compute stream."""
+    def bucket_ready(self, net, name, then=None, after=None):
+        """Called right after the wgrad kernels of a bucket were enqueued on the current stream.
+        `then(lo, hi)`: optional work enqueued on the comm stream right behind the allreduce (the bucket's
+        optimizer update); `after`: an extra event that work must wait for (e.g. the last reader of the
+        weights the update overwrites)."""
         lo, hi = self.bucket_range(net, name)
         ready = torch.cuda.Event()
         ready.record(torch.cuda.current_stream())
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ready)
             self.ctx.allreduce_sum(net.arena.g[lo:hi])
+            if then is not None:
+                if after is not None:
+                    self.stream.wait_event(after)
+                then(lo, hi)
             done = torch.cuda.Event()
             done.record(self.stream)
         self._done.append(done)
         self.bytes_per_step += (hi - lo) * 4
+
+    def sharded_adam(self, net, name, group, lr, beta1, eps, after=None):
+        """ZeRO-1 style exchange for one bucket, enqueued on the comm stream behind the bucket's wgrads:
+             f32 grads -> bf16  |  reduce-scatter (sum)  |  TF-Adam on this rank's 1/n slice (grad_scale 1/n)
+             |  all-gather of the bf16 weight mirror.
+        Half the NVLink bytes of an f32 allreduce and 1/n of the optimizer's HBM traffic per rank.  The f32
+        master weights and Adam slots of the other ranks' slices are not kept up to date on this rank
+        (`gather_master` refreshes them, e.g. before a checkpoint)."""
+        a = net.arena
+        lo, hi = self.bucket_range(net, name)
+        n = hi - lo
+        assert n % (self.world * 8) == 0, "bucket must split into 16-byte aligned rank slices"
+        chunk = n // self.world
+        if a.gb is None:
+            a.gb = torch.zeros(a.total, dtype=torch.bfloat16, device=a.w.device)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            self.ctx.cast_f32_bf16(a.g[lo:hi], a.gb[lo:hi])
+            ops.reduce_scatter_sum(self.ctx, a.gb[lo:hi], chunk)
+            if after is not None:
+                self.stream.wait_event(after)
+            s = lo + self.rank * chunk
+            self.ctx.adam_tf_bf16g(a.w[s:s + chunk], a.gb[s:s + chunk], a.m[s:s + chunk], a.v[s:s + chunk],
+                                   a.wb[s:s + chunk], lr, beta1, net.beta2, eps, max(net.adam_t[group], 1),
+                                   1.0 / self.world, lr_t_dev=net.lr_dev[group])
+            ops.allgather(self.ctx, a.wb[lo:hi], chunk)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        self._done.append(done)
+        self.bytes_per_step += n * 2 * 2
+        self._sharded = getattr(self, "_sharded", set()) | {name}
+
+    def gather_master(self, net):
+        """All-gather the f32 master weights and Adam slots of every sharded bucket (checkpoint / export)."""
+        a = net.arena
+        for name in sorted(getattr(self, "_sharded", ())):
+            lo, hi = self.bucket_range(net, name)
+            chunk = (hi - lo) // self.world
+            for buf in (a.w, a.m, a.v):
+                ops.allgather(self.ctx, buf[lo:hi], chunk)
 
     def wait_all(self, net):
         cur = torch.cuda.current_stream()

@@ -244,6 +244,11 @@ class MSDNNet:
             self.ctx.adam_tf(a.w[lo:hi], a.g[lo:hi], a.m[lo:hi], a.v[lo:hi], a.wb[lo:hi], ADAM_LR[g], ADAM_BETA1,
                              self.beta2, ADAM_EPS, max(self.adam_t[g], 1), grad_scale, lr_t_dev=self.lr_dev[g])
 
+    def adam_range(self, group, lo, hi, grad_scale=1.0):
+        a = self.arena
+        self.ctx.adam_tf(a.w[lo:hi], a.g[lo:hi], a.m[lo:hi], a.v[lo:hi], a.wb[lo:hi], ADAM_LR[group], ADAM_BETA1,
+                         self.beta2, ADAM_EPS, max(self.adam_t[group], 1), grad_scale, lr_t_dev=self.lr_dev[group])
+
     # ------------------------------------------------------------------ phase-1 step on three streams
     def _enqueue_phase1_overlapped(self):
         """Same launches as forward() + backward_coarse() + apply_adam(), arranged by data dependence:
@@ -264,8 +269,10 @@ class MSDNNet:
             s1 = s1 if "fine" in self.overlap else s0
             s2 = s2 if "wgrad" in self.overlap else s0
             s3 = s3 if "wgrad" in self.overlap else s0
-        if self.comm:
-            s3 = s2                                   # DP: one wgrad stream, buckets handed to the comm stream in order
+        inv_world = 1.0 / self.comm.world if self.comm else 1.0
+
+        def dp_update(bucket, group, after=None):     # DP: reduce-scatter -> sharded TF-Adam -> all-gather (dp.py)
+            self.comm.sharded_adam(self, bucket, group, ADAM_LR[group], ADAM_BETA1, ADAM_EPS, after)
         hook = self.comm.bucket_ready if self.comm else (lambda *_: None)
 
         def mark(stream):
@@ -342,20 +349,25 @@ class MSDNNet:
             c.adam_tf(a.w[sl], a.g[sl], a.m[sl], a.v[sl], a.wb[sl], ADAM_LR[g], ADAM_BETA1, self.beta2, ADAM_EPS,
                       max(self.adam_t[g], 1), 1.0, lr_t_dev=self.lr_dev[g])
 
-        if not fused:
-            on_wgrad(e_g, lambda: (c.dense_wgrad(self.d0, self.g_coarse, dw=self.gw(nd + "1" + K),
-                                                 db=self.gw(nd + "1/bias"), impl=self.impl), hook(self, "dense_1")))
+        e_loss = e_g
         c.dense_dgrad(self.g_coarse, self.w(nd + "1" + K), out=self.g_d0a, impl=self.impl)
         c.dense_epilogue_bwd(self.g_d0a, self.d0, self.keep_mask, 0.5, L.EPI_RELU, out=self.g_d0)
         e_g = mark(s0)
+        if not fused:
+            # the bucket's Adam overwrites dense_1's weights: it waits for e_g (dense_1's dgrad has read them)
+            on_wgrad(e_loss, lambda: (c.dense_wgrad(self.d0, self.g_coarse, dw=self.gw(nd + "1" + K),
+                                                    db=self.gw(nd + "1/bias"), impl=self.impl),
+                                      self.comm and dp_update("dense_1", "CoarseDense", e_g)))
         if fused:       # updates dense_1's weights: must follow dense_1's dgrad, their last reader
             on_wgrad(e_g, lambda: dense_wgrad_adam("1", self.d0, self.g_coarse))
-        else:
-            on_wgrad(e_g, lambda: (c.dense_wgrad(self.c4.view(B, 12288), self.g_d0, dw=self.gw(nd + "0" + K),
-                                                 db=self.gw(nd + "0/bias"), impl=self.impl), hook(self, "dense_0")))
+        e_d0 = e_g
         c.dense_dgrad(self.g_d0, self.w(nd + "0" + K), out=self.g_c4a.view(B, 12288), impl=self.impl)
         c.relu_bwd(self.c4, self.g_c4a, out=self.g_c4)
         e_g = mark(s0)
+        if not fused:
+            on_wgrad(e_d0, lambda: (c.dense_wgrad(self.c4.view(B, 12288), self.g_d0, dw=self.gw(nd + "0" + K),
+                                                  db=self.gw(nd + "0/bias"), impl=self.impl),
+                                    self.comm and dp_update("dense_0", "CoarseDense", e_g)))
         if fused:
             on_wgrad(e_g, lambda: dense_wgrad_adam("0", self.c4.view(B, 12288), self.g_d0))
         elif not self.comm:
@@ -380,10 +392,9 @@ class MSDNNet:
         def conv0_and_adam():
             c.conv2d_wgrad(self.d_c0, self.img, self.g_c0, dw=self.gw(n + "0" + K), db=self.gw(n + "0/bias"))
             self._mask_padding("coarse/conv/conv2d_0/kernel")
-            hook(self, "coarse_conv")
             if self.comm:
+                dp_update("coarse_conv", "CoarseConv")
                 self.comm.wait_all(self)
-                self.apply_adam(("CoarseDense", "CoarseConv"), 1.0 / self.comm.world)
             else:
                 self.apply_adam(("CoarseConv",))
         on_wgrad(e_g, conv0_and_adam, s3)

@@ -180,6 +180,11 @@ class Context:
         L.check(self.lib.a3d_adam_tf(self.h, _ptr(w), _ptr(g), _ptr(m), _ptr(v), _ptr(w_bf16), n, lr_t, beta1, beta2,
                                      eps, grad_scale, _ptr(lr_t_dev), _stream()), "adam")
 
+    def adam_tf_bf16g(self, w, g_bf16, m, v, w_bf16, lr, beta1, beta2, eps, t, grad_scale=1.0, lr_t_dev=None):
+        L.check(self.lib.a3d_adam_tf_bf16g(self.h, _ptr(w), _ptr(g_bf16), _ptr(m), _ptr(v), _ptr(w_bf16), w.numel(),
+                                           adam_lr_t(lr, beta1, beta2, t), beta1, beta2, eps, grad_scale,
+                                           _ptr(lr_t_dev), _stream()), "adam_bf16g")
+
     def sgd(self, w, g, w_bf16, lr, grad_scale=1.0, n=None):
         n = n if n is not None else w.numel()
         L.check(self.lib.a3d_sgd(self.h, _ptr(w), _ptr(g), _ptr(w_bf16), n, lr, grad_scale, _stream()), "sgd")
@@ -363,6 +368,20 @@ class Context:
         code = L.A3D_BF16 if t.dtype == torch.bfloat16 else L.A3D_F32
         L.check(self.lib.a3d_allreduce_sum(self.h, _ptr(t), count if count is not None else t.numel(), code,
                                            _stream()), "allreduce")
+
+
+def _code(t):
+    return L.A3D_BF16 if t.dtype == torch.bfloat16 else L.A3D_F32
+
+
+def reduce_scatter_sum(ctx, t, chunk):
+    """In place on t (world*chunk elements): afterwards rank r holds the sum in t[r*chunk:(r+1)*chunk]."""
+    L.check(ctx.lib.a3d_reduce_scatter_sum(ctx.h, _ptr(t), chunk, _code(t), _stream()), "reduce_scatter")
+
+
+def allgather(ctx, t, chunk):
+    """In place on t (world*chunk elements): publishes every rank's slice t[r*chunk:(r+1)*chunk]."""
+    L.check(ctx.lib.a3d_allgather(ctx.h, _ptr(t), chunk, _code(t), _stream()), "allgather")
 
 
 def comm_unique_id(nccl_path: str | None = None) -> bytes:

@@ -117,8 +117,9 @@ def dcnf_specs():
 
 class Arena:
     """Flat device buffers holding every variable: f32 master `w`, f32 grads `g`, Adam slots `m`,`v`,
-    and the bf16 mirror `wb` the kernels read.  Segment starts are multiples of 8 elements, so both
-    the f32 and the bf16 views of a segment are 16-byte aligned (TMA base alignment)."""
+    and the bf16 mirror `wb` the kernels read.  Segment starts are multiples of 64 elements: both the f32
+    and the bf16 views of a segment are 16-byte aligned (TMA base alignment), and every bucket splits into
+    8 rank slices that are themselves 16-byte aligned (sharded optimizer, dp.py)."""
 
     def __init__(self, specs, device, with_adam=True):
         off = 0
@@ -126,7 +127,7 @@ class Arena:
         self.groups = OrderedDict()
         for s in specs:
             s.offset = off
-            s.size = (s.numel + 7) // 8 * 8
+            s.size = (s.numel + 63) // 64 * 64
             off += s.size
             self.specs[s.name] = s
             lo, hi = self.groups.get(s.group, (s.offset, s.offset))
@@ -138,6 +139,7 @@ class Arena:
         self.m = torch.zeros(off, **f32) if with_adam else None
         self.v = torch.zeros(off, **f32) if with_adam else None
         self.wb = torch.zeros(off, dtype=torch.bfloat16, device=device)
+        self.gb = None            # bf16 gradient staging for the data-parallel exchange (allocated by dp.py)
         self.masks = {}
         for s in specs:
             km = keep_mask(s)

@@ -206,9 +206,21 @@ def gpu_arm(args, rank, world, local_rank):
         # The data path (gradient allreduce) runs on liba3d's own NCCL communicator; keeping a single NCCL
         # communicator per process avoids cross-communicator ordering deadlocks.
         dist.init_process_group("gloo")
-        ids = [ops.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        comm = DataParallel(ctx, rank, world, ids[0])
+        # NCCL prints its version banner on stdout: keep stdout clean for the single JSON line
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            ids = [ops.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            comm = DataParallel(ctx, rank, world, ids[0])
+            warm = torch.zeros(1024, device=dev)
+            ctx.allreduce_sum(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     images_h, depths_h = synthetic_batch(rank, torch)
     images_h, depths_h = images_h.pin_memory(), depths_h.pin_memory()

@@ -179,6 +179,10 @@ int a3d_adam_tf(a3d_ctx*, float* w, const float* g, float* m, float* v, uint16_t
                 void* stream);
 int a3d_sgd(a3d_ctx*, float* w, const float* g, uint16_t* w_bf16, size_t n, float lr,
             float grad_scale, void* stream);
+/* a3d_adam_tf with the gradient given in bf16 (the dtype of the data-parallel gradient exchange). */
+int a3d_adam_tf_bf16g(a3d_ctx*, float* w, const uint16_t* g_bf16, float* m, float* v, uint16_t* w_bf16, size_t n,
+                      float lr_t, float beta1, float beta2, float eps, float grad_scale,
+                      const float* lr_t_dev, void* stream);
 /* Dropout keep-mask (tf.layers.dropout, src/models.py:230; unseeded in the reference): keep[i] = 1 with
  * probability keep_prob, from a counter-based hash of (seed, *counter_dev, i).  counter_dev is a device
  * int64 (e.g. the global step) so that a captured CUDA graph draws a fresh mask on every replay. */
@@ -244,6 +248,11 @@ int a3d_comm_init(a3d_ctx*, const char* nccl_path, const void* id128, int rank, 
 int a3d_comm_destroy(a3d_ctx*);
 /* In-place sum-allreduce of a flat gradient bucket on `stream`. */
 int a3d_allreduce_sum(a3d_ctx*, void* buf, size_t count, int dtype, void* stream);
+/* Sharded-optimizer exchange (reduce-scatter gradients -> each rank updates its 1/n slice -> all-gather the
+ * bf16 weight mirror).  Both are in place on a buffer of nranks*chunk elements: after the reduce-scatter,
+ * rank r holds the sum in buf[r*chunk, (r+1)*chunk); the all-gather publishes every rank's slice. */
+int a3d_reduce_scatter_sum(a3d_ctx*, void* buf, size_t chunk, int dtype, void* stream);
+int a3d_allgather(a3d_ctx*, void* buf, size_t chunk, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

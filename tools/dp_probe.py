@@ -41,10 +41,35 @@ say("model built")
 op.run(use_graph=False)
 torch.cuda.synchronize()
 say("eager DP step ok")
-gsum = op.net.arena.g[:4096].double().sum().item()
+wsum = op.net.arena.wb.double().sum().item()
 lst = [None] * world
-dist.all_gather_object(lst, gsum)
-say(f"grad checksums equal across ranks: {lst}")
+dist.all_gather_object(lst, wsum)
+say(f"bf16 weight mirror checksums equal across ranks: {lst}")
+# equivalence: n ranks fed the SAME batch must take the single-GPU step (gradients are averaged)
+gs = torch.Generator().manual_seed(7)
+im2 = torch.rand(4, 480, 640, 3, generator=gs).cuda()
+dp2 = (torch.rand(4, 55, 73, 1, generator=gs) * 0.95 + 0.05).cuda()
+mask2 = (torch.rand(4, 4096, generator=gs) < 0.5).cuda()
+pp = glorot_params(seed=1)
+pp["coarse/dense/dense_1/bias"] += 1.0
+outs = []
+for cm in (None, comm):
+    o2 = models.msdn(im2, dp2, train=True, comm=cm, beta2=0.999)
+    o2.net.load_params(pp)
+    o2.net.set_dropout_mask(mask2)
+    w0 = o2.net.arena.wb.float().clone()
+    o2.run(use_graph=False)
+    torch.cuda.synchronize()
+    if cm is not None:
+        cm.gather_master(o2.net)
+        torch.cuda.synchronize()
+    outs.append((o2.net.arena.wb.float() - w0, o2.net.arena.m.clone(), o2.net.arena.w.clone()))
+(d1, m1, w1), (d2, m2, w2) = outs
+lo, hi = o2.net.arena.group_range("CoarseDense")[0], o2.net.arena.group_range("CoarseConv")[1]
+cosd = float((d1[lo:hi].double() @ d2[lo:hi].double()) / (d1[lo:hi].double().norm() * d2[lo:hi].double().norm()))
+cosm = float((m1[lo:hi].double() @ m2[lo:hi].double()) / (m1[lo:hi].double().norm() * m2[lo:hi].double().norm()))
+say(f"DP(same batch) vs single GPU: update cosine {cosd:.6f}  m cosine {cosm:.6f}  max|w diff| {float((w1[lo:hi]-w2[lo:hi]).abs().max()):.3e}")
+assert cosd > 0.98 and cosm > 0.999
 if os.environ.get("A3D_PROBE_GRAPH", "1") == "1":
     op.run(use_graph=True)
     torch.cuda.synchronize()
