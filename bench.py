@@ -302,9 +302,11 @@ def gpu_arm(args, rank, world, local_rank):
     if rank == 0:
         pk, pk_kind = peaks()
         # per-kernel timing pass runs on rank 0 alone: detach the communicator so that it contains no collective
+        # ... and the single-stream schedule, so that each kernel is timed alone on the launching stream
         saved_comm, op.net.comm = op.net.comm, None
+        saved_overlap, op.net.overlap = op.net.overlap, False
         rows = per_op_profile(op, torch)
-        op.net.comm = saved_comm
+        op.net.comm, op.net.overlap = saved_comm, saved_overlap
         step_ms = ms_total / args.steps
         # dominant kernel of the step, and the conv/FC tensor-pipe aggregate
         top = max(rows, key=lambda r: r["ms"])
@@ -321,6 +323,12 @@ def gpu_arm(args, rank, world, local_rank):
             roof = {"bound": "hbm", "kernel": f'{top["op"]} {top["detail"]}', "achieved": None, "peak": pk["hbm_gbs"],
                     "unit": "GB/s", "frac": None, "traffic": None, "peak_kind": pk_kind,
                     "share_of_step": top["ms"] / sum(r["ms"] for r in rows)}
+        # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/), if listed
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            roof["traffic"] = traffic.get(roof["kernel"])
+        except Exception:
+            pass
         roof["conv_tensor_tflops"] = tflops / (tms * 1e-3) / 1e12 if tms else None
         roof["conv_tensor_frac_of_burst"] = roof["conv_tensor_tflops"] / pk["bf16_tflops"] if tms else None
         roof["step_tflops_algorithmic"] = FLOP_PER_IMAGE_PHASE1 * BATCH / (step_ms * 1e-3) / 1e12
@@ -341,7 +349,9 @@ def gpu_arm(args, rank, world, local_rank):
                                        "groups), batch 32/GPU, 640x480 RGB -> 55x73 depth, glorot init seed 1",
                            "parallelism": f"dp{world}", "global_batch": BATCH * world,
                            "l2": "working set per step (~2.6 GB: activations + 283 MB weights + Adam slots) >> 126 MB L2",
-                           "adam": "reference TF-Adam(beta1=0.9, beta2=1, eps=1e-8)", "cuda_graph": True},
+                           "adam": "reference TF-Adam(beta1=0.9, beta2=1, eps=1e-8)", "cuda_graph": True,
+                           "streams": "main + fine-forward + dense-wgrad/Adam + conv-wgrad (+ NCCL comm)",
+                           "dp": "reduce-scatter(bf16) -> sharded Adam -> all-gather(bf16 weights)" if world > 1 else None},
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": H2D_BYTES,
                         "d2h_bytes_per_step": D2H_BYTES, "last_loss": last_loss},
                 "gpu_launches": launches_per_step * args.steps,
