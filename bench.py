@@ -153,6 +153,8 @@ def per_op_profile(op, torch, reps=3):
                 if name.startswith("a3d_conv2d"):
                     d = a[1]._obj
                     detail = f"N{d.N} {d.H}x{d.W}x{d.C}->{d.P}x{d.Q}x{d.K} k{d.R}x{d.S} s{d.stride_h}"
+                elif name == "a3d_adam_tf":
+                    detail = f"n={int(a[6])}"
                 elif name in ("a3d_dense_fwd", "a3d_dense_dgrad", "a3d_dense_wgrad"):
                     i0 = {"a3d_dense_fwd": 10, "a3d_dense_dgrad": 6, "a3d_dense_wgrad": 7}[name]
                     detail = "MNK=" + "x".join(str(int(x)) for x in a[i0:i0 + 3])
@@ -320,8 +322,12 @@ def gpu_arm(args, rank, world, local_rank):
                     "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": None,
                     "peak_kind": pk_kind + " burst", "share_of_step": top["ms"] / sum(r["ms"] for r in rows)}
         else:
-            roof = {"bound": "hbm", "kernel": f'{top["op"]} {top["detail"]}', "achieved": None, "peak": pk["hbm_gbs"],
-                    "unit": "GB/s", "frac": None, "traffic": None, "peak_kind": pk_kind,
+            # algorithmic bytes of the HBM-bound kernels: TF-Adam = 30 B/param
+            ach = None
+            if top["op"] == "a3d_adam_tf" and top["detail"].startswith("n="):
+                ach = 30.0 * int(top["detail"][2:]) / (top["ms"] * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": f'{top["op"]} {top["detail"]}', "achieved": ach, "peak": pk["hbm_gbs"],
+                    "unit": "GB/s", "frac": ach / pk["hbm_gbs"] if ach else None, "traffic": None, "peak_kind": pk_kind,
                     "share_of_step": top["ms"] / sum(r["ms"] for r in rows)}
         # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/), if listed
         try:
