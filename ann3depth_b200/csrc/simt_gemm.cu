@@ -192,6 +192,16 @@ colsum_bf16_kernel(const uint16_t* __restrict__ a, size_t rows, int C8, int ld8,
   }
 }
 
+// few rows, many columns (dense layers: rows = batch): one thread per column, coalesced across the warp,
+// no atomics.  out is fully overwritten.
+__global__ void colsum_bf16_cols_kernel(const uint16_t* __restrict__ a, int rows, int C, int ld, float* __restrict__ out) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int r = 0; r < rows; ++r) s += bf16_bits_to_f32(a[(size_t)r * ld + c]);
+  out[c] = s;
+}
+
 // generic fallback (any C, any ld)
 __global__ void colsum_bf16_scalar_kernel(const uint16_t* __restrict__ a, size_t rows, int C, int ld,
                                           float* __restrict__ out, int rows_per_block) {
@@ -228,6 +238,11 @@ int a3d_simt_conv_wgrad(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x,
 }
 
 int a3d_colsum_bf16(a3d_ctx* ctx, const uint16_t* a, size_t rows, int C, int ld, float* out, cudaStream_t st) {
+  if (rows <= 512 && C >= 1024) {
+    colsum_bf16_cols_kernel<<<ceil_div(C, 128), 128, 0, st>>>(a, (int)rows, C, ld, out);
+    A3D_LAUNCH_OK(ctx);
+    return 0;
+  }
   A3D_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, st));
   const bool vec = C % 8 == 0 && ld % 8 == 0 && C / 8 <= 256 && (reinterpret_cast<uintptr_t>(a) & 15) == 0;
   if (vec) {

@@ -2,6 +2,7 @@
 // and the launchers used by the convolution / dense entry points.
 #include "tc_gemm.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -420,8 +421,12 @@ int a3d_tc_dense_wgrad(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t*
     p.lr_t = adam->lr_t; p.beta1 = adam->beta1; p.beta2 = adam->beta2; p.eps = adam->eps; p.grad_scale = adam->grad_scale;
     p.lr_t_dev = adam->lr_t_dev;
   }
-  if (K % 256 == 0) return launch_cfg<tc::Cfg<256, 128, true, true, 64>>(ctx, tmA, tmB, p, 1, st);
-  if (K % 128 == 0) return launch_cfg<tc::Cfg<128, 128, true, true, 64>>(ctx, tmA, tmB, p, 1, st);
+  // One k-block per CTA: the kernel is all prologue + epilogue.  N tiles of 128 keep the stage ring under
+  // 104 KB so that two CTAs share an SM and one's epilogue hides the other's prologue (A3D_DWGRAD_BN overrides).
+  static int bn_pref = -1;
+  if (bn_pref < 0) { const char* e = getenv("A3D_DWGRAD_BN"); bn_pref = e ? atoi(e) : 128; }
+  if (bn_pref == 256 && K % 256 == 0) return launch_cfg<tc::Cfg<256, 128, true, true, 64>>(ctx, tmA, tmB, p, 1, st);
+  if (bn_pref >= 128 && K % 128 == 0) return launch_cfg<tc::Cfg<128, 128, true, true, 64>>(ctx, tmA, tmB, p, 1, st);
   return launch_cfg<tc::Cfg<64, 128, true, true, 64>>(ctx, tmA, tmB, p, 1, st);
 }
 
