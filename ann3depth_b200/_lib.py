@@ -60,6 +60,7 @@ SIGNATURES = {
     "a3d_increment_i64": (_i, [_vp, _vp, _vp]),
     "a3d_cast_f32_bf16": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "a3d_scatter_channel_bf16": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp]),
+    "a3d_space_to_depth2": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "a3d_fill_zero": (_i, [_vp, _vp, _sz, _vp]),
     "a3d_apply_mask_f32": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "a3d_crf_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

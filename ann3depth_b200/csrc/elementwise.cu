@@ -600,3 +600,29 @@ extern "C" int a3d_adam_tf_bf16g(a3d_ctx* ctx, float* w, const uint16_t* g, floa
   A3D_LAUNCH_OK(ctx);
   return 0;
 }
+
+// one thread = one source pixel of 4 channels (8 bytes)
+__global__ void space_to_depth2_kernel(const uint2* __restrict__ src, int N, int H, int W, int C4, uint2* __restrict__ dst) {
+  size_t total = (size_t)N * H * W * C4;
+  const int H2 = H / 2, W2 = W / 2;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4);
+    size_t t = i / C4;
+    int w = (int)(t % W);
+    t /= W;
+    int h = (int)(t % H);
+    int n = (int)(t / H);
+    size_t o = ((((size_t)n * H2 + h / 2) * W2 + w / 2) * 4 + (h & 1) * 2 + (w & 1)) * C4 + c;
+    dst[o] = __ldg(src + i);
+  }
+}
+extern "C" int a3d_space_to_depth2(a3d_ctx* ctx, const uint16_t* src, int N, int H, int W, int C, uint16_t* dst,
+                                   void* stream) {
+  A3D_REQUIRE(ctx && src && dst && C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "space_to_depth2: bad argument");
+  size_t total = (size_t)N * H * W * (C / 4);
+  int block = 256, grid = grid_for(ctx, total, block);
+  space_to_depth2_kernel<<<grid, block, 0, as_stream(stream)>>>(reinterpret_cast<const uint2*>(src), N, H, W, C / 4,
+                                                              reinterpret_cast<uint2*>(dst));
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}

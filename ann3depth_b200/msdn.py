@@ -66,6 +66,7 @@ class MSDNNet:
         self.external_mask = False
         # ---- forward activations
         self.img = z(B, IN_H, IN_W, 4, **bf)           # resized image, channel-padded to 4 (8-byte pixels)
+        self.img2 = z(B, IN_H // 2, IN_W // 2, 16, **bf)   # space-to-depth copy for the stride-2 fine/first layer
         self.tar = z(B, OUT_H, OUT_W, 1, **f32)         # resized target
         # conv outputs that feed a max-pool stay f32 and the pool records its routing (see a3d.h)
         self.c0 = z(B, 55, 74, 96, **f32)
@@ -95,7 +96,7 @@ class MSDNNet:
         self.d_c2 = cd(B, 13, 18, 256, 384, 3, 3, 1, "same", impl=impl)
         self.d_c3 = cd(B, 13, 18, 384, 384, 3, 3, 1, "same", impl=impl)
         self.d_c4 = cd(B, 13, 18, 384, 256, 3, 3, 2, "valid", impl=impl)
-        self.d_f1 = cd(B, IN_H, IN_W, 4, 64, 9, 10, 2, "valid", impl=impl)       # 9x9x3->63 stored 9x10x4->64
+        self.d_f1 = cd(B, IN_H // 2, IN_W // 2, 16, 64, 5, 5, 1, "valid", impl=impl)   # 9x9x3 s2 -> 63 as 5x5x16 s1 -> 64
         self.d_f2 = cd(B, 55, 74, 64, 64, 5, 5, 1, "same", impl=impl)
         self.d_f3 = cd(B, 55, 74, 64, 1, 5, 5, 1, "same", impl=impl)
         assert (self.d_c0.P, self.d_c0.Q) == (55, 74) and (self.d_f1.P, self.d_f1.Q) == (110, 148)
@@ -166,7 +167,8 @@ class MSDNNet:
                     drop_rate=0.5, out=self.d0, impl=self.impl)
         c.dense_fwd(self.d0, self.w(n + "1" + K), self.bias(n + "1"), flags=0, out=self.coarse, impl=self.impl)
         # fine (src/models.py:238-253)
-        c.conv2d_fwd(self.d_f1, self.img, self.w("fine/first/conv2d" + K), self.bias("fine/first/conv2d"), relu=True,
+        c.space_to_depth2(self.img, self.img2)
+        c.conv2d_fwd(self.d_f1, self.img2, self.w("fine/first/conv2d" + K), self.bias("fine/first/conv2d"), relu=True,
                      out=self.f1)
         c.maxpool2x2_fwd_f32(self.f1, out=self.cat, ldy=64, idx=self.if1)
         c.scatter_channel_bf16(self.coarse, self.cat, 63)
@@ -223,7 +225,7 @@ class MSDNNet:
                        db=self.gw("fine/second/conv2d/bias"))
         c.conv2d_dgrad(self.d_f2, self.g_f2, self.w("fine/second/conv2d" + K), out=self.g_cat)
         c.maxpool2x2_idx_bwd(self.if1, self.g_cat, (self.B, 110, 148, 64), lddy=64, out=self.g_f1)
-        c.conv2d_wgrad(self.d_f1, self.img, self.g_f1, dw=self.gw("fine/first/conv2d" + K),
+        c.conv2d_wgrad(self.d_f1, self.img2, self.g_f1, dw=self.gw("fine/first/conv2d" + K),
                        db=self.gw("fine/first/conv2d/bias"))
         self._mask_padding("fine/first/conv2d/kernel")
         self._mask_padding("fine/first/conv2d/bias")
@@ -288,7 +290,8 @@ class MSDNNet:
         with torch.cuda.stream(s1):
             c.ws_tag = "fine"
             s1.wait_event(e_img)
-            c.conv2d_fwd(self.d_f1, self.img, self.w("fine/first/conv2d" + K), self.bias("fine/first/conv2d"), relu=True,
+            c.space_to_depth2(self.img, self.img2)
+            c.conv2d_fwd(self.d_f1, self.img2, self.w("fine/first/conv2d" + K), self.bias("fine/first/conv2d"), relu=True,
                          out=self.f1)
             c.maxpool2x2_fwd_f32(self.f1, out=self.cat, ldy=64, idx=self.if1)
             c.ws_tag = ""

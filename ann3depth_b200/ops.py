@@ -207,6 +207,11 @@ class Context:
         L.check(self.lib.a3d_scatter_channel_bf16(self.h, _ptr(src), _ptr(dst), src.numel(), ld, ch, _stream()),
                 "scatter_channel")
 
+    def space_to_depth2(self, src, out):
+        N, H, W, Cc = src.shape
+        L.check(self.lib.a3d_space_to_depth2(self.h, _ptr(src), N, H, W, Cc, _ptr(out), _stream()), "space_to_depth2")
+        return out
+
     def fill_zero(self, t):
         L.check(self.lib.a3d_fill_zero(self.h, _ptr(t), t.numel() * t.element_size(), _stream()), "fill_zero")
 

@@ -21,7 +21,7 @@ class VarSpec:
     name: str            # TF variable name
     tf_shape: tuple
     packed_shape: tuple
-    kind: str            # 'conv_kernel' | 'dense_kernel' | 'bias'
+    kind: str            # 'conv_kernel' | 'conv_kernel_s2d' | 'dense_kernel' | 'bias'
     group: str           # optimizer group
     offset: int = 0      # element offset in the arena
     size: int = 0        # padded element count (multiple of 8)
@@ -42,6 +42,15 @@ def pack(spec: VarSpec, t: torch.Tensor) -> torch.Tensor:
         out = torch.zeros(spec.packed_shape, dtype=t.dtype)
         out[:co, :kh, :kw, :ci] = t.permute(3, 0, 1, 2)
         return out
+    if spec.kind == "conv_kernel_s2d":
+        # stride-2 filter [kh,kw,ci,co] as the stride-1 filter over the space-to-depth input:
+        # packed[co][r'][s'][(di*2+dj)*4 + c] = t[2r'+di][2s'+dj][c][co]  (zero beyond kh, kw, ci)
+        kh, kw, ci, co = spec.tf_shape
+        K, R2, S2, C16 = spec.packed_shape
+        full = torch.zeros(2 * R2, 2 * S2, 4, K, dtype=t.dtype)
+        full[:kh, :kw, :ci, :co] = t
+        full = full.view(R2, 2, S2, 2, 4, K).permute(5, 0, 2, 1, 3, 4)       # K, r', s', di, dj, c
+        return full.reshape(K, R2, S2, 16).contiguous()
     if spec.kind == "dense_kernel":
         return t.t().contiguous()
     out = torch.zeros(spec.packed_shape, dtype=t.dtype)
@@ -55,6 +64,11 @@ def unpack(spec: VarSpec, p: torch.Tensor) -> torch.Tensor:
     if spec.kind == "conv_kernel":
         kh, kw, ci, co = spec.tf_shape
         return p[:co, :kh, :kw, :ci].permute(1, 2, 3, 0).contiguous()
+    if spec.kind == "conv_kernel_s2d":
+        kh, kw, ci, co = spec.tf_shape
+        K, R2, S2, C16 = spec.packed_shape
+        full = p.view(K, R2, S2, 2, 2, 4).permute(1, 3, 2, 4, 5, 0).reshape(2 * R2, 2 * S2, 4, K)
+        return full[:kh, :kw, :ci, :co].contiguous()
     if spec.kind == "dense_kernel":
         return p.t().contiguous()
     return p[:spec.tf_shape[0]].contiguous()
@@ -92,8 +106,11 @@ def msdn_specs():
     v += _conv("coarse/conv/conv2d_0", (11, 11, 3, 96), (96, 11, 12, 4), "CoarseConv")
     # FineA (lr 1e-3, :334-336): fine/third, fine/first
     v += _conv("fine/third", (5, 5, 64, 1), (1, 5, 5, 64), "FineA")
-    # 9x9x3 -> 63 stored as 9x10x4 -> 64: two 4-channel pixels = one 16-byte group for the stride-2 layer
-    v += _conv("fine/first/conv2d", (9, 9, 3, 63), (64, 9, 10, 4), "FineA")
+    # 9x9x3 -> 63, stride 2, stored as the equivalent 5x5x16 -> 64 stride-1 filter over the space-to-depth
+    # (2x2 pixel blocks -> 16 channels) image: 32-byte pixels feed the im2col TMA / UMMA K = 16 directly
+    f1 = _conv("fine/first/conv2d", (9, 9, 3, 63), (64, 5, 5, 16), "FineA")
+    f1[0].kind = "conv_kernel_s2d"
+    v += f1
     # FineB (lr 0.01, :337-338)
     v += _conv("fine/second/conv2d", (5, 5, 64, 64), (64, 5, 5, 64), "FineB")
     return v

@@ -193,6 +193,11 @@ int a3d_increment_i64(a3d_ctx*, int64_t* p, void* stream);
 /* f32 -> bf16 cast of a flat segment (weight mirror refresh). */
 int a3d_cast_f32_bf16(a3d_ctx*, const float* src, uint16_t* dst, size_t n, void* stream);
 
+/* Space-to-depth by 2: dst[n,i,j,(di*2+dj)*C + c] = src[n,2i+di,2j+dj,c]  (bf16, C % 4 == 0, H and W even).
+ * Turns a stride-2 convolution over C channels into a stride-1 convolution over 4C channels with half the
+ * filter extent (MSDN fine/first, src/models.py:241: 9x9 stride 2 on 3(4) channels -> 5x5 stride 1 on 16). */
+int a3d_space_to_depth2(a3d_ctx*, const uint16_t* src, int N, int H, int W, int C, uint16_t* dst, void* stream);
+
 /* ---- small glue kernels -------------------------------------------------------------------- */
 /* Write src f32 [rows] into channel `ch` of a bf16 NHWC buffer with channel stride ld
  * (tf.concat of the coarse map, src/models.py:246). */

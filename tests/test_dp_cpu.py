@@ -103,7 +103,7 @@ def test_pack_unpack_roundtrip_and_masks():
         assert torch.equal(unpack(s, pack(s, t)), t)
     m = a.masks["coarse/conv/conv2d_0/kernel"].view(96, 11, 12, 4)
     assert int(m.sum()) == 96 * 11 * 11 * 3 and not bool(m[:, :, 11, :].any()) and not bool(m[..., 3].any())
-    m = a.masks["fine/first/conv2d/kernel"].view(64, 9, 10, 4)
+    m = a.masks["fine/first/conv2d/kernel"].view(64, 5, 5, 16)
     assert int(m.sum()) == 63 * 9 * 9 * 3 and not bool(m[63].any())
     assert "coarse/conv/conv2d_1/kernel" not in a.masks
 
