@@ -27,6 +27,14 @@ H2D_BYTES = BATCH * (480 * 640 * 3 + 55 * 73) * 4
 D2H_BYTES = 8
 
 
+def workload_config(world):
+    return {"workload": "msdn phase-1 train step (fwd coarse+fine, 2 losses, coarse bwd, 2 TF-Adam groups), batch 32/GPU, "
+                        "640x480 RGB -> 55x73 depth, glorot init seed 1",
+            "parallelism": f"dp{world}", "global_batch": BATCH * world,
+            "l2": "working set per step (~2.6 GB: activations + 283 MB weights + Adam slots) >> 126 MB L2",
+            "adam": "reference TF-Adam(beta1=0.9, beta2=1, eps=1e-8)"}
+
+
 def peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
@@ -122,7 +130,7 @@ def reference_arm(args, rank):
     line = {"impl": "reference", "metric": "MSDN train images/s (bs32/GPU, phase-1 step)", "value": v,
             "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "msdn phase-1 train step, batch 32, 640x480 RGB -> 55x73 depth"},
+            "config": workload_config(args.gpus),
             "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -351,11 +359,7 @@ def gpu_arm(args, rank, world, local_rank):
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic",
-                "config": {"workload": "msdn phase-1 train step (fwd coarse+fine, 2 losses, coarse bwd, 2 TF-Adam "
-                                       "groups), batch 32/GPU, 640x480 RGB -> 55x73 depth, glorot init seed 1",
-                           "parallelism": f"dp{world}", "global_batch": BATCH * world,
-                           "l2": "working set per step (~2.6 GB: activations + 283 MB weights + Adam slots) >> 126 MB L2",
-                           "adam": "reference TF-Adam(beta1=0.9, beta2=1, eps=1e-8)", "cuda_graph": True,
+                "config": {**workload_config(world), "cuda_graph": True,
                            "streams": "main + fine-forward + dense-wgrad/Adam + conv-wgrad (+ NCCL comm)",
                            "dp": "reduce-scatter(bf16) -> sharded Adam -> all-gather(bf16 weights)" if world > 1 else None},
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": H2D_BYTES,
