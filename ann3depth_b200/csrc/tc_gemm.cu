@@ -106,16 +106,62 @@ int make_tmap_im2col(a3d_ctx* ctx, CUtensorMap* tm, const void* base, int N, int
   return 0;
 }
 
+// f32 output matrix [rows][cols] (row pitch ld elements) for the TMA epilogue: box = 32 columns x 32 rows,
+// SWIZZLE_128B (the staging slabs of tc::EPI_TMA_F32).
+int make_tmap_out_f32(a3d_ctx* ctx, CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->fn_encode_tiled)(
+      tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    a3d_set_error("cuTensorMapEncodeTiled(out f32) failed (%d): rows=%llu cols=%llu ld=%llu", (int)r,
+                  (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
+    return A3D_ETMAP;
+  }
+  return 0;
+}
+
+// A3D_EPI_TMA=0 keeps the per-thread register epilogue (A/B measurements); default: TMA wherever the
+// output is an f32 row-major matrix with 16-byte aligned rows.
+bool epi_tma_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("A3D_EPI_TMA"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
+bool epi_tma_ok(const void* out, long long ldo) {
+  return epi_tma_enabled() && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ldo % 4) == 0;
+}
+// switch a row-major f32 epilogue to the TMA epilogue when possible; builds the output map
+int maybe_tma_out(a3d_ctx* ctx, tc::Params& p, CUtensorMap* tmC, bool* use) {
+  *use = false;
+  if (p.epi != tc::EPI_ROW_F32 || !epi_tma_ok(p.out, p.ldo)) return 0;
+  int rc = make_tmap_out_f32(ctx, tmC, p.out, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldo);
+  if (rc) return rc;
+  p.epi = tc::EPI_TMA_F32;
+  *use = true;
+  return 0;
+}
+
 template <class C>
-int launch_cfg(a3d_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const tc::Params& p, int splits,
+int launch_cfg(a3d_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const tc::Params& p_in, int splits,
                cudaStream_t st) {
+  static_assert(C::STAGES * C::STAGE_BYTES >= 4 * 8192, "the TMA epilogue stages 4 x 8 KB in the ring");
   static bool attr_set = false;
   if (!attr_set) {
     A3D_CHECK_CUDA(cudaFuncSetAttribute(tc::gemm_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
+  tc::Params p = p_in;
+  CUtensorMap tmC;
+  bool use_c = false;
+  int rc = maybe_tma_out(ctx, p, &tmC, &use_c);
+  if (rc) return rc;
   dim3 grid(ceil_div(p.M, C::BM), ceil_div(p.N, C::BN), splits);
-  tc::gemm_kernel<C><<<grid, 192, C::SMEM_BYTES, st>>>(tmA, tmB, p);
+  tc::gemm_kernel<C><<<grid, 192, C::SMEM_BYTES, st>>>(tmA, tmB, use_c ? tmC : tmA, p);
   A3D_LAUNCH_OK(ctx);
   return 0;
 }

@@ -29,6 +29,9 @@ enum Epi : int {
   EPI_COL_F32 = 2,        // out_f32 [col*ldo + row] (+)= acc                  (transposed; dense layers)
   EPI_ADAM = 3,           // acc is a weight gradient: TF-Adam applied in place on w/m/v (+ bf16 mirror) at
                           // [row*ldo + col]; the gradient itself never goes to HBM (dense wgrad, single GPU)
+  EPI_TMA_F32 = 4,        // out_f32[row*ldo + col] = act(acc + bias[col]) staged through shared memory and written
+                          // with TMA (tmC): whole 128-byte lines per row instead of one 64-byte piece per thread;
+                          // split-K accumulates with cp.reduce.async.bulk (.add.f32, performed in L2)
 };
 
 struct Params {
@@ -86,7 +89,8 @@ struct Cfg {
 
 template <class C>
 __global__ void __launch_bounds__(192, 2)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmC, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: required by the 128-byte swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -237,8 +241,62 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     ptx::tc_fence_after_sync();
     const int row = m0 + quarter * 32 + lane;
     const bool row_ok = row < p.M;
+    int c_begin = 0;
+    if (p.epi == EPI_TMA_F32) {
+      // The accumulator is complete, hence every TMA load has landed and every UMMA has read its stage: the
+      // stage ring is free and serves as staging.  Per warp two 4 KB slabs (32 rows x 32 f32, SWIZZLE_128B:
+      // 16-byte chunk j of row r lives at chunk j ^ (r & 7), which also makes the st.shared conflict-free).
+      // Rows >= M and columns >= N are clipped by TMA.  A trailing 16-column piece (BN % 32) takes the
+      // register path below.
+      uint8_t* slab0 = smem + quarter * 8192;
+      const int row0 = m0 + quarter * 32;
+      constexpr int NCH = C::BN / 32;
+      if (row0 < p.M) {                            // warp-uniform
 #pragma unroll 1
-    for (int c0 = 0; c0 < C::BN; c0 += 16) {
+        for (int ch = 0; ch < NCH; ++ch) {
+          const int col0 = n0 + ch * 32;
+          if (col0 >= p.N) break;                  // warp-uniform
+          uint8_t* slab = slab0 + (ch & 1) * 4096;
+          if (ch >= 2) {                           // the store issued two chunks ago has finished reading this slab
+            if (lane == 0) ptx::bulk_wait_read<1>();
+          }
+          __syncwarp();
+          uint32_t ra[16], rb[16];
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ch * 32);
+          ptx::tmem_ld_x16(taddr, ra);
+          ptx::tmem_ld_x16(taddr + 16, rb);
+          ptx::tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { v[j] = __uint_as_float(ra[j]); v[16 + j] = __uint_as_float(rb[j]); }
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+          }
+          if (p.flags & A3D_EPI_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          const uint32_t srow = ptx::smem_u32(slab) + (uint32_t)lane * 128u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            ptx::st_shared_v4(srow + (uint32_t)((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          ptx::fence_proxy_async_smem();           // generic-proxy writes -> visible to the TMA (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            if (p.atomic) ptx::tma_reduce_add_2d(&tmC, slab, col0, row0);
+            else ptx::tma_store_2d(&tmC, slab, col0, row0);
+            ptx::bulk_commit();
+          }
+        }
+        if (lane == 0) ptx::bulk_wait_all();
+        __syncwarp();
+      }
+      c_begin = NCH * 32;
+    }
+#pragma unroll 1
+    for (int c0 = c_begin; c0 < C::BN; c0 += 16) {
       const int col0 = n0 + c0;
       if (col0 >= p.N) break;                      // warp-uniform
       __syncwarp();                                // tcgen05.ld is .sync.aligned: reconverge first
@@ -337,7 +395,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int j = 0; j < 16; ++j)
               if (col0 + j < p.N) o[j] = f32_to_bf16_bits(v[j]);
           }
-        } else if (row_ok) {  // EPI_ROW_F32
+        } else if (row_ok) {  // EPI_ROW_F32 (and the 16-column tail of EPI_TMA_F32)
           float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0;
           if (p.atomic) {
 #pragma unroll
