@@ -74,6 +74,8 @@ def restore_checkpoint(op, ckptdir):
     net = op.net
     net.arena.w.copy_(state["w"])
     net.arena.wb.copy_(net.arena.w)
+    if hasattr(net, "refresh_derived"):
+        net.refresh_derived()               # filters derived from the arena (MSDN pool-fused fine/first)
     if "m" in state and net.arena.m is not None:
         net.arena.m.copy_(state["m"])
         net.arena.v.copy_(state["v"])

@@ -5,7 +5,7 @@
 #include <stdlib.h>
 
 int a3d_tc_conv_fwd(a3d_ctx*, const a3d_conv_desc*, const uint16_t* x, const uint16_t* w, const float* bias, void* y,
-                    int y_dtype, unsigned flags, void* ws, size_t ws_bytes, cudaStream_t st);
+                    int y_dtype, unsigned flags, void* ws, size_t ws_bytes, cudaStream_t st, uint8_t* pool_idx = nullptr);
 int a3d_tc_conv_wgrad_supported(const a3d_conv_desc* d);
 int a3d_tc_conv_wgrad(a3d_ctx*, const a3d_conv_desc*, const uint16_t* x, const uint16_t* dy, float* dw, cudaStream_t st);
 int a3d_tc_dgrad_cols(a3d_ctx*, const a3d_conv_desc*, const uint16_t* dy, const uint16_t* w, float* col, cudaStream_t st);
@@ -34,9 +34,12 @@ static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 // Stride-1 convolution through the shared-memory-halo kernel (tc_halo.cu).  `in` is the tensor the filter
 // slides over ([N,H,W,C], channel stride ld), outputs P x Q, filter [Kout][R][S][C] (flip = 0) or the
 // original OHWI filter of a conv whose dgrad this is (flip = 1: w is [C_conv = Kout][RS][K_conv = C]).
-static int halo_policy() {          // A3D_HALO = 0 never, 1 default (measured wins only), 2 wherever it fits
+// A3D_HALO = 0 never (default), 1 the 5x5 forward layers, 2 wherever it fits.  With the TMA-store epilogue the
+// im2col-TMA engine is faster than the halo kernel on every MSDN layer (profiles/sweep_r01_halo.txt):
+// conv2d_1 77 vs 122 us, fine/second 67 vs 91 us; the halo kernel stays as an option and a tested path.
+static int halo_policy() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("A3D_HALO"); v = e ? atoi(e) : 1; }
+  if (v < 0) { const char* e = getenv("A3D_HALO"); v = e ? atoi(e) : 0; }
   return v;
 }
 static bool halo_ok(int C, int R, int S, int Wp, bool dgrad) {
@@ -440,4 +443,56 @@ extern "C" int a3d_dense_wgrad_adam(a3d_ctx* ctx, const uint16_t* x, int ldx, co
   }
   a3d_adam_args a{w, m, v, w_bf16, lr_t, beta1, beta2, eps, grad_scale, lr_t_dev};
   return a3d_tc_dense_wgrad(ctx, x, ldx, dy, lddy, nullptr, M, N, K, st, &a);
+}
+
+// Convolution + bias + activation + 2x2/2 max-pool in one tcgen05 GEMM.  The caller supplies the "pool-embedded"
+// filter: for every pooled output pixel the four conv outputs of its window are four groups of Kc = 64 filters
+// (K = 256, filter index g*64 + c, g = 2*a + b for window position (a, b)) over a common receptive field, so
+// that the pool is a max over four accumulator columns of one GEMM row (tc::EPI_POOL4_BF16).
+// y bf16 [N,P,Q,ldy] (64 channels), idx u8 [N,P,Q,64] (nullable): first arg-max group, for a3d_pool4_bwd.
+__global__ void pool4_reduce_kernel(const float* __restrict__ acc, const float* __restrict__ bias, uint16_t* __restrict__ y,
+                                    int ldy, uint8_t* __restrict__ idx, size_t rows, unsigned flags) {
+  const size_t total = rows * 64;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = i >> 6;
+    const int c = (int)(i & 63);
+    const float* a = acc + row * 256 + c;
+    float m = a[0];
+    int g = 0;
+    if (a[64] > m) { m = a[64]; g = 1; }
+    if (a[128] > m) { m = a[128]; g = 2; }
+    if (a[192] > m) { m = a[192]; g = 3; }
+    if (bias) m += bias[c];
+    if (flags & A3D_EPI_RELU) m = fmaxf(m, 0.f);
+    y[row * ldy + c] = f32_to_bf16_bits(m);
+    if (idx) idx[i] = (uint8_t)g;
+  }
+}
+
+extern "C" int a3d_conv2d_pool4_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, const uint16_t* w,
+                                    const float* bias, uint16_t* y, uint8_t* idx, unsigned flags, void* ws,
+                                    size_t ws_bytes, void* stream) {
+  A3D_REQUIRE(ctx && x && w && y && d, "conv pool4 fwd: null argument");
+  A3D_REQUIRE(d->K == 256 && d->ldy >= 64, "conv pool4 fwd: K must be 4 x 64 and ldy >= 64");
+  a3d_conv_desc chk = *d;
+  chk.ldy = d->K;                      // ldy describes the POOLED output (64 channels), not the 256 GEMM columns
+  int rc = check_desc(&chk);
+  if (rc) return rc;
+  cudaStream_t st = as_stream(stream);
+  if (d->impl == A3D_IMPL_SIMT) {
+    // CUDA-core cross-check: plain convolution into an f32 scratch [rows][256], then the group max
+    const size_t rows = (size_t)d->N * d->P * d->Q;
+    A3D_REQUIRE(ws && ws_bytes >= rows * 256 * sizeof(float), "conv pool4 fwd (simt): needs rows*256*4 bytes of scratch");
+    a3d_conv_desc e = *d;
+    e.ldy = 256;
+    rc = a3d_simt_conv_fwd(ctx, &e, x, w, nullptr, ws, A3D_F32, 0, st);
+    if (rc) return rc;
+    size_t total = rows * 64;
+    int grid = (int)((total + 255) / 256);
+    if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
+    pool4_reduce_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(ws), bias, y, d->ldy, idx, rows, flags);
+    A3D_LAUNCH_OK(ctx);
+    return 0;
+  }
+  return a3d_tc_conv_fwd(ctx, d, x, w, bias, y, A3D_BF16, (flags & (A3D_EPI_RELU)) | A3D_EPI_POOL4, nullptr, 0, st, idx);
 }

@@ -626,3 +626,140 @@ extern "C" int a3d_space_to_depth2(a3d_ctx* ctx, const uint16_t* src, int N, int
   A3D_LAUNCH_OK(ctx);
   return 0;
 }
+
+// ------------------------------------------------------------------------------------ resize -> space-to-depth
+// Bilinear resize (TF1 legacy mapping, as above) written directly in space-to-depth layout: an s x s block
+// of resized pixels becomes ONE pixel of s*s*C channels, dst[b][Y][X][(dy*s+dx)*C + c] = resized[b][s*Y+dy][s*X+dx][c],
+// channels >= s*s*C are zero.  One thread writes 8 consecutive bf16 channels (16 bytes), so consecutive
+// threads fill whole 128-byte pixel rows.  (MSDN: 228x304x3 -> 57x76x64, the input of the stride-4 11x11
+// coarse/conv2d_0 and of the pool-fused stride-2 9x9 fine/first, both 3x3 stride-1 convolutions in this layout.)
+__global__ void resize_bilinear_tf1_s2d_kernel(const float* __restrict__ src, int B, int H, int W, int C,
+                                               uint4* __restrict__ dst, int OHs, int OWs, int s, int dstC8, float sy,
+                                               float sx) {
+  const size_t total = (size_t)B * OHs * OWs * dstC8;
+  const int real = s * s * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i % dstC8);
+    size_t t = i / dstC8;
+    const int X = (int)(t % OWs);
+    t /= OWs;
+    const int Y = (int)(t % OHs);
+    const int b = (int)(t / OHs);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = q * 8 + j;
+      float r = 0.f;
+      if (k < real) {
+        const int pix = k / C, c = k - pix * C;
+        const int dy = pix / s, dx = pix - dy * s;
+        const int oy = Y * s + dy, ox = X * s + dx;
+        const float fy = oy * sy, fx = ox * sx;
+        const int y0 = (int)floorf(fy), x0 = (int)floorf(fx);
+        const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+        const float ly = fy - y0, lx = fx - x0;
+        const float* r0 = src + ((size_t)b * H + y0) * W * C;
+        const float* r1 = src + ((size_t)b * H + y1) * W * C;
+        const float tl = __ldg(r0 + (size_t)x0 * C + c), tr = __ldg(r0 + (size_t)x1 * C + c);
+        const float bl = __ldg(r1 + (size_t)x0 * C + c), br = __ldg(r1 + (size_t)x1 * C + c);
+        const float top = tl + (tr - tl) * lx;
+        const float bot = bl + (br - bl) * lx;
+        r = top + (bot - top) * ly;
+      }
+      v[j] = r;
+    }
+    dst[i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+
+extern "C" int a3d_resize_bilinear_tf1_s2d(a3d_ctx* ctx, const float* src, int B, int H, int W, int C, uint16_t* dst,
+                                           int OH, int OW, int s, int dstC, void* stream) {
+  A3D_REQUIRE(ctx && src && dst, "resize_s2d: null argument");
+  A3D_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && s > 0 && OH % s == 0 && OW % s == 0 && dstC % 8 == 0 &&
+                  dstC >= s * s * C && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+              "resize_s2d: bad shape (OH, OW multiples of s; dstC %% 8 == 0 and >= s*s*C)");
+  const size_t total = (size_t)B * (OH / s) * (OW / s) * (dstC / 8);
+  int block = 256, grid = grid_for(ctx, total, block);
+  float sy = (float)H / (float)OH, sx = (float)W / (float)OW;
+  resize_bilinear_tf1_s2d_kernel<<<grid, block, 0, as_stream(stream)>>>(src, B, H, W, C, reinterpret_cast<uint4*>(dst),
+                                                                      OH / s, OW / s, s, dstC / 8, sy, sx);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ pool4 backward
+// Backward of the pool-fused convolution (a3d_conv2d_pool4_fwd): MaxPoolGrad + ReluGrad expressed on the GEMM
+// columns, dybig[row][g*64 + c] = (idx[row][c] == g && y[row][c] > 0) ? dy[row][c] : 0.
+__global__ void pool4_bwd_kernel(const uint16_t* __restrict__ dy, int lddy, const uint16_t* __restrict__ y, int ldy,
+                                 const uint8_t* __restrict__ idx, uint4* __restrict__ dybig, size_t rows) {
+  const size_t total = rows * 32;               // one thread = 8 of the 256 columns
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = i >> 5;
+    const int col = (int)(i & 31) * 8;
+    const int g = col >> 6, c = col & 63;
+    const uint4 d = __ldg(reinterpret_cast<const uint4*>(dy + row * lddy + c));
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(y + row * ldy + c));
+    const uint2 k = __ldg(reinterpret_cast<const uint2*>(idx + row * 64 + c));
+    const uint16_t* dv = reinterpret_cast<const uint16_t*>(&d);
+    const uint16_t* av = reinterpret_cast<const uint16_t*>(&a);
+    const uint8_t* kv = reinterpret_cast<const uint8_t*>(&k);
+    uint16_t o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (kv[j] == g && bf16_bits_to_f32(av[j]) > 0.f) ? dv[j] : (uint16_t)0;
+    dybig[i] = make_uint4(o[0] | ((uint32_t)o[1] << 16), o[2] | ((uint32_t)o[3] << 16), o[4] | ((uint32_t)o[5] << 16),
+                          o[6] | ((uint32_t)o[7] << 16));
+  }
+}
+
+extern "C" int a3d_pool4_bwd(a3d_ctx* ctx, const uint16_t* dy, int lddy, const uint16_t* y, int ldy, const uint8_t* idx,
+                             uint16_t* dybig, size_t rows, void* stream) {
+  A3D_REQUIRE(ctx && dy && y && idx && dybig && rows > 0, "pool4_bwd: null argument");
+  A3D_REQUIRE(lddy % 8 == 0 && ldy % 8 == 0 && lddy >= 64 && ldy >= 64, "pool4_bwd: row pitches must be multiples of 8 elements");
+  int block = 256, grid = grid_for(ctx, rows * 32, block);
+  pool4_bwd_kernel<<<grid, block, 0, as_stream(stream)>>>(dy, lddy, y, ldy, idx, reinterpret_cast<uint4*>(dybig), rows);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ embedded-filter maps
+// A filter that is stored several times inside a larger (derived) filter -- the four shifted copies of the 9x9
+// fine/first filter inside the pool-fused 3x3x64 -> 256 filter -- keeps ONE canonical copy in the parameter arena.
+// idx[g][e] (int32, -1 = none) is the position of canonical element e in copy g of the derived tensor.
+//   gather_sum:   dst[e] = sum_g src[idx[g][e]]              (fold the derived filter's gradient)
+//   scatter_cast: dst[idx[g][e]] = bf16(src[e])              (refresh the derived filter after an update)
+__global__ void gather_sum_f32_kernel(const float* __restrict__ src, const int* __restrict__ idx, int G, size_t n,
+                                      float* __restrict__ dst) {
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int g = 0; g < G; ++g) {
+      const int k = __ldg(idx + (size_t)g * n + e);
+      if (k >= 0) acc += __ldg(src + k);
+    }
+    dst[e] = acc;
+  }
+}
+__global__ void scatter_cast_bf16_kernel(const float* __restrict__ src, const int* __restrict__ idx, int G, size_t n,
+                                         uint16_t* __restrict__ dst) {
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const uint16_t v = f32_to_bf16_bits(__ldg(src + e));
+    for (int g = 0; g < G; ++g) {
+      const int k = __ldg(idx + (size_t)g * n + e);
+      if (k >= 0) dst[k] = v;
+    }
+  }
+}
+extern "C" int a3d_gather_sum_f32(a3d_ctx* ctx, const float* src, const int* idx, int G, size_t n, float* dst, void* stream) {
+  A3D_REQUIRE(ctx && src && idx && dst && G > 0 && n > 0, "gather_sum: bad argument");
+  int block = 256, grid = grid_for(ctx, n, block);
+  gather_sum_f32_kernel<<<grid, block, 0, as_stream(stream)>>>(src, idx, G, n, dst);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+extern "C" int a3d_scatter_cast_bf16(a3d_ctx* ctx, const float* src, const int* idx, int G, size_t n, uint16_t* dst,
+                                     void* stream) {
+  A3D_REQUIRE(ctx && src && idx && dst && G > 0 && n > 0, "scatter_cast: bad argument");
+  int block = 256, grid = grid_for(ctx, n, block);
+  scatter_cast_bf16_kernel<<<grid, block, 0, as_stream(stream)>>>(src, idx, G, n, dst);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}

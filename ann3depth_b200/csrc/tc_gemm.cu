@@ -125,6 +125,24 @@ int make_tmap_out_f32(a3d_ctx* ctx, CUtensorMap* tm, const void* base, uint64_t 
   return 0;
 }
 
+// bf16 output matrix for the TMA epilogue: box = 64 columns (128 bytes) x 32 rows, SWIZZLE_128B
+int make_tmap_out_bf16(a3d_ctx* ctx, CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {64, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->fn_encode_tiled)(
+      tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    a3d_set_error("cuTensorMapEncodeTiled(out bf16) failed (%d): rows=%llu cols=%llu ld=%llu", (int)r,
+                  (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
+    return A3D_ETMAP;
+  }
+  return 0;
+}
+
 // A3D_EPI_TMA=0 keeps the per-thread register epilogue (A/B measurements); default: TMA wherever the
 // output is an f32 row-major matrix with 16-byte aligned rows.
 bool epi_tma_enabled() {
@@ -138,11 +156,24 @@ bool epi_tma_ok(const void* out, long long ldo) {
 // switch a row-major f32 epilogue to the TMA epilogue when possible; builds the output map
 int maybe_tma_out(a3d_ctx* ctx, tc::Params& p, CUtensorMap* tmC, bool* use) {
   *use = false;
-  if (p.epi != tc::EPI_ROW_F32 || !epi_tma_ok(p.out, p.ldo)) return 0;
-  int rc = make_tmap_out_f32(ctx, tmC, p.out, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldo);
-  if (rc) return rc;
-  p.epi = tc::EPI_TMA_F32;
-  *use = true;
+  if (p.epi == tc::EPI_POOL4_BF16) {           // 64 pooled columns; the caller checked alignment
+    int rc = make_tmap_out_bf16(ctx, tmC, p.out, (uint64_t)p.M, 64, (uint64_t)p.ldo);
+    if (rc) return rc;
+    *use = true;
+    return 0;
+  }
+  if (p.epi == tc::EPI_ROW_F32 && epi_tma_ok(p.out, p.ldo)) {
+    int rc = make_tmap_out_f32(ctx, tmC, p.out, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldo);
+    if (rc) return rc;
+    p.epi = tc::EPI_TMA_F32;
+    *use = true;
+  } else if (p.epi == tc::EPI_ROW_BF16 && epi_tma_enabled() && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
+             (p.ldo % 8) == 0) {
+    int rc = make_tmap_out_bf16(ctx, tmC, p.out, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldo);
+    if (rc) return rc;
+    p.epi = tc::EPI_TMA_BF16;
+    *use = true;
+  }
   return 0;
 }
 
@@ -248,7 +279,31 @@ size_t a3d_tc_conv_fwd_ws_bytes(a3d_ctx* ctx, const a3d_conv_desc* d) {
 }
 
 int a3d_tc_conv_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, const uint16_t* w, const float* bias,
-                    void* y, int y_dtype, unsigned flags, void* ws, size_t ws_bytes, cudaStream_t st) {
+                    void* y, int y_dtype, unsigned flags, void* ws, size_t ws_bytes, cudaStream_t st,
+                    uint8_t* pool_idx) {
+  if (flags & A3D_EPI_POOL4) {
+    // conv + bias + act + 2x2 max-pool: the four window positions are four groups of 64 filters (K = 256)
+    if (d->K != 256 || d->C % 64 || y_dtype != A3D_BF16 || d->ldy % 8 || (reinterpret_cast<uintptr_t>(y) & 15)) {
+      a3d_set_error("tc conv pool4 fwd: needs K == 256 (4 x 64), C %% 64 == 0, bf16 output with 16-byte aligned rows");
+      return A3D_ENOTSUP;
+    }
+    const int cblocks = d->C / 64;
+    const long long M = (long long)d->N * d->P * d->Q;
+    CUtensorMap tmA, tmB;
+    int rc = make_tmap_im2col(ctx, &tmA, x, d->N, d->H, d->W, d->C, -d->pad_t, -d->pad_l, d->P, d->Q, d->stride_h,
+                              d->stride_w, 64, 128);
+    if (rc) return rc;
+    rc = make_tmap_2d(ctx, &tmB, w, 256, (uint64_t)d->R * d->S * d->C, (uint64_t)d->R * d->S * d->C, 64, 256);
+    if (rc) return rc;
+    tc::Params p{};
+    p.M = (int)M; p.N = 256; p.num_kb = d->R * d->S * cblocks; p.kb_per_split = p.num_kb;
+    p.a_mode = tc::A_IM2COL;
+    p.PQ = d->P * d->Q; p.Q = d->Q; p.sh = d->stride_h; p.sw = d->stride_w; p.lower_h = -d->pad_t; p.lower_w = -d->pad_l;
+    p.S = d->S; p.cblocks = cblocks;
+    p.epi = tc::EPI_POOL4_BF16; p.out = y; p.ldo = d->ldy; p.bias = bias; p.flags = flags; p.pool_idx = pool_idx;
+    // two stages of 48 KB: two CTAs per SM, one CTA's epilogue runs under the other's main loop
+    return launch_cfg<tc::Cfg<256, 128, false, false, 64, 2>>(ctx, tmA, tmB, p, 1, st);
+  }
   if (!a3d_tc_conv_fwd_supported(d)) {
     a3d_set_error("tc conv fwd: unsupported shape (C=%d must be a multiple of 16)", d->C);
     return A3D_ENOTSUP;
@@ -362,7 +417,11 @@ int a3d_tc_conv_wgrad(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, c
   const int cblocks = d->C / bw;
   const int RS = d->R * d->S;
   const int total_blocks = RS * cblocks;
-  const int nblk = pick_nblk(bw, total_blocks);
+  int nblk = pick_nblk(bw, total_blocks);
+  static int nblk_env = -1, splits_env = -1;       // experiment knobs
+  if (nblk_env < 0) { const char* e = getenv("A3D_WGRAD_NBLK"); nblk_env = e ? atoi(e) : 0; }
+  if (splits_env < 0) { const char* e = getenv("A3D_WGRAD_SPLITS"); splits_env = e ? atoi(e) : 0; }
+  if (nblk_env > 0) nblk = nblk_env;
   const long long Mpix = (long long)d->N * d->P * d->Q;
   CUtensorMap tmA, tmB;
   int rc = make_tmap_2d(ctx, &tmA, dy, Mpix, d->K, d->ldy, 64, 64);
@@ -377,6 +436,7 @@ int a3d_tc_conv_wgrad(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, c
   p.S = d->S; p.cblocks = cblocks;
   const int tiles = ceil_div(d->K, 128) * ceil_div(total_blocks, nblk);
   int splits = pick_splits(ctx, tiles, p.num_kb, 4);
+  if (splits_env > 0) splits = splits_env;
   p.kb_per_split = ceil_div(p.num_kb, splits);
   splits = ceil_div(p.num_kb, p.kb_per_split);
   p.epi = tc::EPI_ROW_F32; p.out = dw; p.ldo = (long long)RS * d->C; p.atomic = splits > 1;

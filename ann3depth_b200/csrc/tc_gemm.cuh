@@ -32,6 +32,10 @@ enum Epi : int {
   EPI_TMA_F32 = 4,        // out_f32[row*ldo + col] = act(acc + bias[col]) staged through shared memory and written
                           // with TMA (tmC): whole 128-byte lines per row instead of one 64-byte piece per thread;
                           // split-K accumulates with cp.reduce.async.bulk (.add.f32, performed in L2)
+  EPI_TMA_BF16 = 5,       // out_bf16[row*ldo + col] = act(acc + bias[col]), 64-column slabs written with TMA
+  EPI_POOL4_BF16 = 6,     // fused 2x2 max-pool of a convolution whose 4 window positions are 4 groups of 64 GEMM
+                          // columns (BN = N = 256): out_bf16[row*ldo + c] = act(max_g acc[g*64 + c] + bias[c]),
+                          // pool_idx[row*64 + c] (nullable) = first arg-max group
 };
 
 struct Params {
@@ -55,12 +59,13 @@ struct Params {
   unsigned flags;
   int atomic;               // accumulate with atomicAdd (split-K)
   // EPI_ADAM: out = w (f32 master)
+  uint8_t* pool_idx;        // EPI_POOL4_BF16: routing record (nullable)
   float* adam_m; float* adam_v; uint16_t* adam_wb;
   float lr_t, beta1, beta2, eps, grad_scale;
   const float* lr_t_dev;
 };
 
-template <int BN_, int KCB_, bool A_MN_, bool B_MN_, int B_BW_ = 64>
+template <int BN_, int KCB_, bool A_MN_, bool B_MN_, int B_BW_ = 64, int MIN_STAGES_ = 3>
 struct Cfg {
   static constexpr int B_BW = B_BW_;                     // MN-major B: elements per block (64/32/16)
   static constexpr int B_BLK_BYTES = 64 * B_BW_ * 2;     // 64 K-rows x BW elements
@@ -78,7 +83,7 @@ struct Cfg {
   // ~104 KB of stages per CTA: two CTAs (of this or of a concurrently running kernel on another stream)
   // fit on one SM, so one CTA's epilogue / prologue hides under the other's main loop.  At least 3 stages.
   static constexpr int STAGES_RAW = (104 * 1024) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < 3 ? 3 : STAGES_RAW);
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < MIN_STAGES_ ? MIN_STAGES_ : STAGES_RAW);
   static constexpr int TMEM_COLS = BN_ <= 32 ? 32 : BN_ <= 64 ? 64 : BN_ <= 128 ? 128 : 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(!(A_MN_ || B_MN_) || KCB_ == 128, "MN-major operands use 128-byte rows");
@@ -295,6 +300,115 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       c_begin = NCH * 32;
     }
+    if (p.epi == EPI_TMA_BF16) {
+      // as above with 64 bf16 columns (= 128 bytes) per slab row; a tail of BN % 64 columns takes the register path
+      uint8_t* slab0 = smem + quarter * 8192;
+      const int row0 = m0 + quarter * 32;
+      constexpr int NCH = C::BN / 64;
+      if (row0 < p.M) {
+#pragma unroll 1
+        for (int ch = 0; ch < NCH; ++ch) {
+          const int col0 = n0 + ch * 64;
+          if (col0 >= p.N) break;
+          uint8_t* slab = slab0 + (ch & 1) * 4096;
+          if (ch >= 2) {
+            if (lane == 0) ptx::bulk_wait_read<1>();
+          }
+          __syncwarp();
+          const uint32_t srow = ptx::smem_u32(slab) + (uint32_t)lane * 128u;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t ra[16], rb[16];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ch * 64 + half * 32);
+            ptx::tmem_ld_x16(taddr, ra);
+            ptx::tmem_ld_x16(taddr + 16, rb);
+            ptx::tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { v[j] = __uint_as_float(ra[j]); v[16 + j] = __uint_as_float(rb[j]); }
+            const int cbase = col0 + half * 32;
+            if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (cbase + j < p.N) v[j] += __ldg(p.bias + cbase + j);
+            }
+            if (p.flags & A3D_EPI_RELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = half * 4 + jj;
+              ptx::st_shared_v4_b32(srow + (uint32_t)((j ^ (lane & 7)) << 4), pack_bf16x2(v[8 * jj], v[8 * jj + 1]),
+                                    pack_bf16x2(v[8 * jj + 2], v[8 * jj + 3]), pack_bf16x2(v[8 * jj + 4], v[8 * jj + 5]),
+                                    pack_bf16x2(v[8 * jj + 6], v[8 * jj + 7]));
+            }
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&tmC, slab, col0, row0);
+            ptx::bulk_commit();
+          }
+        }
+        if (lane == 0) ptx::bulk_wait_all();
+        __syncwarp();
+      }
+      c_begin = NCH * 64;
+    }
+    if constexpr (C::BN == 256) {
+      if (p.epi == EPI_POOL4_BF16) {
+        uint8_t* slab = smem + quarter * 8192;
+        const int row0 = m0 + quarter * 32;
+        if (row0 < p.M) {
+          const uint32_t srow = ptx::smem_u32(slab) + (uint32_t)lane * 128u;
+#pragma unroll 1
+          for (int cc = 0; cc < 4; ++cc) {
+            uint32_t r0[16], r1[16], r2[16], r3[16];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cc * 16);
+            __syncwarp();
+            ptx::tmem_ld_x16(taddr, r0);
+            ptx::tmem_ld_x16(taddr + 64, r1);
+            ptx::tmem_ld_x16(taddr + 128, r2);
+            ptx::tmem_ld_x16(taddr + 192, r3);
+            ptx::tmem_ld_wait();
+            float v[16];
+            uint32_t gi[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float m = __uint_as_float(r0[j]);
+              uint32_t g = 0;
+              const float a1 = __uint_as_float(r1[j]), a2 = __uint_as_float(r2[j]), a3 = __uint_as_float(r3[j]);
+              if (a1 > m) { m = a1; g = 1; }       // strict '>' keeps the FIRST arg-max (TF MaxPoolGrad)
+              if (a2 > m) { m = a2; g = 2; }
+              if (a3 > m) { m = a3; g = 3; }
+              if (p.bias) m += __ldg(p.bias + cc * 16 + j);
+              if (p.flags & A3D_EPI_RELU) m = fmaxf(m, 0.f);
+              v[j] = m;
+              gi[j >> 2] |= g << ((j & 3) * 8);
+            }
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+              const int j = cc * 2 + jj;
+              ptx::st_shared_v4_b32(srow + (uint32_t)((j ^ (lane & 7)) << 4), pack_bf16x2(v[8 * jj], v[8 * jj + 1]),
+                                    pack_bf16x2(v[8 * jj + 2], v[8 * jj + 3]), pack_bf16x2(v[8 * jj + 4], v[8 * jj + 5]),
+                                    pack_bf16x2(v[8 * jj + 6], v[8 * jj + 7]));
+            }
+            if (p.pool_idx && row_ok)
+              *reinterpret_cast<uint4*>(p.pool_idx + (size_t)row * 64 + cc * 16) = make_uint4(gi[0], gi[1], gi[2], gi[3]);
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&tmC, slab, 0, row0);
+            ptx::bulk_commit();
+            ptx::bulk_wait_all();
+          }
+          __syncwarp();
+        }
+        c_begin = C::BN;
+      }
+    }
 #pragma unroll 1
     for (int c0 = c_begin; c0 < C::BN; c0 += 16) {
       const int col0 = n0 + c0;
@@ -380,7 +494,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
         }
-        if (row_ok && p.epi == EPI_ROW_BF16) {
+        if (row_ok && (p.epi == EPI_ROW_BF16 || p.epi == EPI_TMA_BF16)) {
           uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + (long long)row * p.ldo + col0;
           const bool vec = (col0 + 16 <= p.N) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
           if (vec) {

@@ -11,7 +11,7 @@ import torch
 
 from . import _lib as L
 from . import ops
-from .params import Arena, msdn_specs
+from .params import Arena, msdn_specs, fine_first_index_maps, FINE_FIRST_EMBEDDED_SHAPE
 
 IN_H, IN_W = 228, 304          # src/models.py:282
 OUT_H, OUT_W = 55, 74          # src/models.py:283
@@ -65,8 +65,9 @@ class MSDNNet:
         self.keep_mask = torch.ones(B, 4096, dtype=torch.uint8, device=self.dev)
         self.external_mask = False
         # ---- forward activations
-        self.img = z(B, IN_H, IN_W, 4, **bf)           # resized image, channel-padded to 4 (8-byte pixels)
-        self.img2 = z(B, IN_H // 2, IN_W // 2, 16, **bf)   # space-to-depth copy for the stride-2 fine/first layer
+        # resized image in space-to-depth(4) layout: 4x4 pixel blocks -> 48 channels (+16 zero) = 128-byte pixels.
+        # Both first layers are 3x3 stride-1 convolutions on it (coarse 11x11 s4; fine 9x9 s2 + pool = 11x11 s4).
+        self.img4 = z(B, IN_H // 4, IN_W // 4, 64, **bf)
         self.tar = z(B, OUT_H, OUT_W, 1, **f32)         # resized target
         # conv outputs that feed a max-pool stay f32 and the pool records its routing (see a3d.h)
         self.c0 = z(B, 55, 74, 96, **f32)
@@ -80,9 +81,13 @@ class MSDNNet:
         self.c4 = z(B, 6, 8, 256, **bf)
         self.d0 = z(B, 4096, **bf)                      # relu + dropout applied
         self.coarse = z(B, N_PIX, **f32)
-        self.f1 = z(B, 110, 148, 64, **f32)
-        self.if1 = torch.zeros(B, 55, 74, 64, dtype=torch.uint8, device=self.dev)
-        self.cat = z(B, 55, 74, 64, **bf)               # pool(f1)[...,:63] ++ coarse  (src/models.py:246)
+        self.if1 = torch.zeros(B, 55, 74, 64, dtype=torch.uint8, device=self.dev)    # pool routing of fine/first
+        self.cat = z(B, 55, 74, 64, **bf)               # pool(relu(fine/first))[...,:63] ++ coarse  (src/models.py:246)
+        # derived pool-embedded fine/first filter (params.fine_first_embedded) and its index maps
+        self.wbig = z(*FINE_FIRST_EMBEDDED_SHAPE, **bf)
+        km, bm = fine_first_index_maps(self.arena.specs["fine/first/conv2d/kernel"],
+                                       self.arena.specs["fine/first/conv2d/bias"])
+        self.emb_k, self.emb_b = km.to(self.dev), bm.to(self.dev)
         self.f2 = z(B, 55, 74, 64, **bf)
         self.fine = z(B, N_PIX, **f32)
         self.loss_coarse, self.loss_fine = z(1, **f32), z(1, **f32)
@@ -91,15 +96,17 @@ class MSDNNet:
         self.lr_dev = {g: z(1, **f32) for g in ADAM_LR}
         # ---- conv descriptors (src/models.py:211-223, 241-251)
         cd = ops.conv_desc
-        self.d_c0 = cd(B, IN_H, IN_W, 4, 96, 11, 12, 4, "valid", impl=impl)     # 11x11x3 stored 11x12x4
+        self.d_c0 = cd(B, IN_H // 4, IN_W // 4, 64, 96, 3, 3, 1, "valid", impl=impl)   # 11x11x3 s4 as 3x3x64 s1
         self.d_c1 = cd(B, 27, 37, 96, 256, 5, 5, 1, "same", impl=impl)
         self.d_c2 = cd(B, 13, 18, 256, 384, 3, 3, 1, "same", impl=impl)
         self.d_c3 = cd(B, 13, 18, 384, 384, 3, 3, 1, "same", impl=impl)
         self.d_c4 = cd(B, 13, 18, 384, 256, 3, 3, 2, "valid", impl=impl)
-        self.d_f1 = cd(B, IN_H // 2, IN_W // 2, 16, 64, 5, 5, 1, "valid", impl=impl)   # 9x9x3 s2 -> 63 as 5x5x16 s1 -> 64
+        # 9x9x3 s2 -> 63 + pool 2x2 as 3x3x64 s1 -> 4 x 64 with the pool in the GEMM epilogue (writes `cat`)
+        self.d_f1 = cd(B, IN_H // 4, IN_W // 4, 64, 256, 3, 3, 1, "valid", ldy=64, impl=impl)
+        self.d_f1w = cd(B, IN_H // 4, IN_W // 4, 64, 256, 3, 3, 1, "valid", impl=impl)      # its wgrad: dy [.,256]
         self.d_f2 = cd(B, 55, 74, 64, 64, 5, 5, 1, "same", impl=impl)
         self.d_f3 = cd(B, 55, 74, 64, 1, 5, 5, 1, "same", impl=impl)
-        assert (self.d_c0.P, self.d_c0.Q) == (55, 74) and (self.d_f1.P, self.d_f1.Q) == (110, 148)
+        assert (self.d_c0.P, self.d_c0.Q) == (55, 74) and (self.d_f1.P, self.d_f1.Q) == (55, 74)
         assert (self.d_c4.P, self.d_c4.Q) == (6, 8)
         if train:
             self.g_coarse = z(B, 4096, **bf)             # row stride padded 4070 -> 4096 (16-byte aligned rows)
@@ -114,7 +121,8 @@ class MSDNNet:
             self.g_c0 = z(B, 55, 74, 96, **bf)
             self.g_f2a, self.g_f2 = z(B, 55, 74, 64, **bf), z(B, 55, 74, 64, **bf)
             self.g_cat = z(B, 55, 74, 64, **bf)
-            self.g_f1 = z(B, 110, 148, 64, **bf)
+            self.g_f1big = None                          # [B*4070, 256] bf16, allocated on first use (phase 2 only)
+            self.g_wbig = None
         self._graphs = {}
 
     # ------------------------------------------------------------------ parameters
@@ -129,6 +137,14 @@ class MSDNNet:
 
     def load_params(self, tf_params):
         self.arena.load_tf(tf_params)
+        self.refresh_derived()
+
+    def refresh_derived(self):
+        """Re-embed the canonical fine/first filter into the pool-fused filter the kernels read (after a load or a
+        FineA optimizer step).  Entries outside the four embedded copies stay zero."""
+        a = self.arena
+        s = a.specs["fine/first/conv2d/kernel"]
+        self.ctx.scatter_cast_bf16(a.w[s.offset:s.offset + s.numel], self.emb_k, self.wbig)
 
     def export_params(self):
         return self.arena.export_tf()
@@ -146,11 +162,11 @@ class MSDNNet:
         """src/models.py:281-290.  Reads self.images / self.depths, fills self.coarse / self.fine / losses."""
         c, B = self.ctx, self.B
         K = "/kernel"
-        c.resize_bilinear_tf1(self.images, IN_H, IN_W, out=self.img)
+        c.resize_bilinear_tf1_s2d(self.images, IN_H, IN_W, 4, out=self.img4)
         c.resize_bilinear_tf1(self.depths, OUT_H, OUT_W, out=self.tar)
         # coarse (src/models.py:208-236)
         n = "coarse/conv/conv2d_"
-        c.conv2d_fwd(self.d_c0, self.img, self.w(n + "0" + K), self.bias(n + "0"), relu=True, out=self.c0)
+        c.conv2d_fwd(self.d_c0, self.img4, self.w(n + "0" + K), self.bias(n + "0"), relu=True, out=self.c0)
         c.maxpool2x2_fwd_f32(self.c0, out=self.p0, idx=self.i0)
         c.conv2d_fwd(self.d_c1, self.p0, self.w(n + "1" + K), self.bias(n + "1"), relu=True, out=self.c1)
         c.maxpool2x2_fwd_f32(self.c1, out=self.p1, idx=self.i1)
@@ -167,10 +183,8 @@ class MSDNNet:
                     drop_rate=0.5, out=self.d0, impl=self.impl)
         c.dense_fwd(self.d0, self.w(n + "1" + K), self.bias(n + "1"), flags=0, out=self.coarse, impl=self.impl)
         # fine (src/models.py:238-253)
-        c.space_to_depth2(self.img, self.img2)
-        c.conv2d_fwd(self.d_f1, self.img2, self.w("fine/first/conv2d" + K), self.bias("fine/first/conv2d"), relu=True,
-                     out=self.f1)
-        c.maxpool2x2_fwd_f32(self.f1, out=self.cat, ldy=64, idx=self.if1)
+        c.conv2d_pool4_fwd(self.d_f1, self.img4, self.wbig, self.bias("fine/first/conv2d"), relu=True, out=self.cat,
+                           idx=self.if1 if self.train else None)
         c.scatter_channel_bf16(self.coarse, self.cat, 63)
         c.conv2d_fwd(self.d_f2, self.cat, self.w("fine/second/conv2d" + K), self.bias("fine/second/conv2d"), relu=True,
                      out=self.f2)
@@ -209,7 +223,7 @@ class MSDNNet:
         c.conv2d_wgrad(self.d_c1, self.p0, self.g_c1, dw=self.gw(n + "1" + K), db=self.gw(n + "1/bias"))
         c.conv2d_dgrad(self.d_c1, self.g_c1, self.w(n + "1" + K), out=self.g_p0)
         c.maxpool2x2_idx_bwd(self.i0, self.g_p0, (self.B, 55, 74, 96), out=self.g_c0)
-        c.conv2d_wgrad(self.d_c0, self.img, self.g_c0, dw=self.gw(n + "0" + K), db=self.gw(n + "0/bias"))
+        c.conv2d_wgrad(self.d_c0, self.img4, self.g_c0, dw=self.gw(n + "0" + K), db=self.gw(n + "0/bias"))
         self._mask_padding("coarse/conv/conv2d_0/kernel")
         hook(self, "coarse_conv")
 
@@ -224,11 +238,17 @@ class MSDNNet:
         c.conv2d_wgrad(self.d_f2, self.cat, self.g_f2, dw=self.gw("fine/second/conv2d" + K),
                        db=self.gw("fine/second/conv2d/bias"))
         c.conv2d_dgrad(self.d_f2, self.g_f2, self.w("fine/second/conv2d" + K), out=self.g_cat)
-        c.maxpool2x2_idx_bwd(self.if1, self.g_cat, (self.B, 110, 148, 64), lddy=64, out=self.g_f1)
-        c.conv2d_wgrad(self.d_f1, self.img2, self.g_f1, dw=self.gw("fine/first/conv2d" + K),
-                       db=self.gw("fine/first/conv2d/bias"))
-        self._mask_padding("fine/first/conv2d/kernel")
-        self._mask_padding("fine/first/conv2d/bias")
+        # fine/first: MaxPoolGrad + ReluGrad on the 4 x 64 GEMM columns, wgrad of the embedded filter, then fold its
+        # four copies (and the four bias groups) into the canonical variable
+        if self.g_f1big is None:
+            self.g_f1big = torch.zeros(self.B * N_PIX, 256, dtype=torch.bfloat16, device=self.dev)
+            self.g_wbig = torch.zeros(256 * 3 * 3 * 64 + 256, dtype=torch.float32, device=self.dev)
+        c.pool4_bwd(self.g_cat.view(-1, 64), self.cat.view(-1, 64), self.if1, out=self.g_f1big)
+        nk = 256 * 3 * 3 * 64
+        c.conv2d_wgrad(self.d_f1w, self.img4, self.g_f1big.view(self.B, 55, 74, 256),
+                       dw=self.g_wbig[:nk].view(256, 3, 3, 64), db=self.g_wbig[nk:])
+        c.gather_sum_f32(self.g_wbig[:nk], self.emb_k, self.gw("fine/first/conv2d" + K))
+        c.gather_sum_f32(self.g_wbig[nk:], self.emb_b, self.gw("fine/first/conv2d/bias"))
         hook(self, "fine")
 
     def _mask_padding(self, name):
@@ -283,21 +303,19 @@ class MSDNNet:
             return e
 
         # ---- main: preprocessing
-        c.resize_bilinear_tf1(self.images, IN_H, IN_W, out=self.img)
+        c.resize_bilinear_tf1_s2d(self.images, IN_H, IN_W, 4, out=self.img4)
         c.resize_bilinear_tf1(self.depths, OUT_H, OUT_W, out=self.tar)
         e_img = mark(s0)
         # ---- fine stream, part 1: first conv + pool need only the image
         with torch.cuda.stream(s1):
             c.ws_tag = "fine"
             s1.wait_event(e_img)
-            c.space_to_depth2(self.img, self.img2)
-            c.conv2d_fwd(self.d_f1, self.img2, self.w("fine/first/conv2d" + K), self.bias("fine/first/conv2d"), relu=True,
-                         out=self.f1)
-            c.maxpool2x2_fwd_f32(self.f1, out=self.cat, ldy=64, idx=self.if1)
+            c.conv2d_pool4_fwd(self.d_f1, self.img4, self.wbig, self.bias("fine/first/conv2d"), relu=True, out=self.cat,
+                               idx=self.if1)
             c.ws_tag = ""
         # ---- main: coarse forward
         n = "coarse/conv/conv2d_"
-        c.conv2d_fwd(self.d_c0, self.img, self.w(n + "0" + K), self.bias(n + "0"), relu=True, out=self.c0)
+        c.conv2d_fwd(self.d_c0, self.img4, self.w(n + "0" + K), self.bias(n + "0"), relu=True, out=self.c0)
         c.maxpool2x2_fwd_f32(self.c0, out=self.p0, idx=self.i0)
         c.conv2d_fwd(self.d_c1, self.p0, self.w(n + "1" + K), self.bias(n + "1"), relu=True, out=self.c1)
         c.maxpool2x2_fwd_f32(self.c1, out=self.p1, idx=self.i1)
@@ -393,7 +411,7 @@ class MSDNNet:
         e_g = mark(s0)
 
         def conv0_and_adam():
-            c.conv2d_wgrad(self.d_c0, self.img, self.g_c0, dw=self.gw(n + "0" + K), db=self.gw(n + "0/bias"))
+            c.conv2d_wgrad(self.d_c0, self.img4, self.g_c0, dw=self.gw(n + "0" + K), db=self.gw(n + "0/bias"))
             self._mask_padding("coarse/conv/conv2d_0/kernel")
             if self.comm:
                 dp_update("coarse_conv", "CoarseConv")
@@ -427,6 +445,8 @@ class MSDNNet:
                 self.comm.wait_all(self)
                 scale = 1.0 / self.comm.world
             self.apply_adam(groups, scale)
+            if "FineA" in groups:
+                self.refresh_derived()                   # fine/first moved: re-embed it into the pool-fused filter
         self.ctx.increment_i64(self.step_dev)            # global_step += 1 (src/models.py:329,343,356)
 
     def train_step(self, use_graph=True):
@@ -447,6 +467,7 @@ class MSDNNet:
                 torch.cuda.synchronize()
                 self.arena.w.copy_(saved[0]); self.arena.m.copy_(saved[1]); self.arena.v.copy_(saved[2])
                 self.arena.wb.copy_(saved[3]); self.step_dev.copy_(saved[4])
+                self.refresh_derived()
                 gr = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gr):
                     self._enqueue_step(phase)

@@ -107,6 +107,43 @@ class Context:
                                                  _stream()), "resize")
         return out
 
+    def resize_bilinear_tf1_s2d(self, src, OH, OW, s, out):
+        """Resize + space-to-depth(s): out bf16 [B, OH/s, OW/s, dstC >= s*s*C]."""
+        B, H, W, Cc = src.shape
+        L.check(self.lib.a3d_resize_bilinear_tf1_s2d(self.h, _ptr(src), B, H, W, Cc, _ptr(out), OH, OW, s,
+                                                     out.shape[-1], _stream()), "resize_s2d")
+        return out
+
+    def conv2d_pool4_fwd(self, d, x, w, bias, relu=True, out=None, idx=None):
+        """conv + bias + ReLU + 2x2 max-pool as one GEMM over the pool-embedded filter (K = 4 x 64)."""
+        if out is None:
+            out = torch.empty(d.N, d.P, d.Q, d.ldy, dtype=torch.bfloat16, device=x.device)
+        ws = None
+        if d.impl == L.IMPL_SIMT:
+            ws = self.workspace(("pool4_simt",), d.N * d.P * d.Q * 256 * 4)
+        L.check(self.lib.a3d_conv2d_pool4_fwd(self.h, C.byref(d), _ptr(x), _ptr(w), _ptr(bias), _ptr(out), _ptr(idx),
+                                              L.EPI_RELU if relu else 0, _ptr(ws), ws.numel() if ws is not None else 0,
+                                              _stream()), "conv2d_pool4_fwd")
+        return out
+
+    def pool4_bwd(self, dy, y, idx, out=None):
+        rows = idx.numel() // 64
+        if out is None:
+            out = torch.empty(rows, 256, dtype=torch.bfloat16, device=dy.device)
+        L.check(self.lib.a3d_pool4_bwd(self.h, _ptr(dy), dy.shape[-1], _ptr(y), y.shape[-1], _ptr(idx), _ptr(out), rows,
+                                       _stream()), "pool4_bwd")
+        return out
+
+    def gather_sum_f32(self, src, idx, dst):
+        G, n = idx.shape
+        L.check(self.lib.a3d_gather_sum_f32(self.h, _ptr(src), _ptr(idx), G, n, _ptr(dst), _stream()), "gather_sum")
+        return dst
+
+    def scatter_cast_bf16(self, src, idx, dst):
+        G, n = idx.shape
+        L.check(self.lib.a3d_scatter_cast_bf16(self.h, _ptr(src), _ptr(idx), G, n, _ptr(dst), _stream()), "scatter_cast")
+        return dst
+
     def maxpool2x2_fwd(self, x, out=None, ldy=None):
         N, H, W, Cc = x.shape
         ldy = ldy or Cc

@@ -51,10 +51,65 @@ def pack(spec: VarSpec, t: torch.Tensor) -> torch.Tensor:
         full[:kh, :kw, :ci, :co] = t
         full = full.view(R2, 2, S2, 2, 4, K).permute(5, 0, 2, 1, 3, 4)       # K, r', s', di, dj, c
         return full.reshape(K, R2, S2, 16).contiguous()
+    if spec.kind == "conv_kernel_s2d4":
+        return pack_s2d(t, 4, spec.packed_shape)
     if spec.kind == "dense_kernel":
         return t.t().contiguous()
     out = torch.zeros(spec.packed_shape, dtype=t.dtype)
     out[:t.numel()] = t
+    return out
+
+
+def pack_s2d(t: torch.Tensor, s: int, packed_shape) -> torch.Tensor:
+    """Stride-s filter [kh,kw,ci,co] as the stride-1 filter over the space-to-depth(s) input:
+    packed[co][R][S][(dy*s+dx)*ci + c] = t[s*R+dy][s*S+dx][c][co]; zero beyond kh, kw, co and in the channel padding."""
+    kh, kw, ci, co = t.shape
+    K, R2, S2, Cs = packed_shape
+    full = torch.zeros(s * R2, s * S2, ci, K, dtype=t.dtype)
+    full[:kh, :kw, :, :co] = t
+    full = full.view(R2, s, S2, s, ci, K).permute(5, 0, 2, 1, 3, 4).reshape(K, R2, S2, s * s * ci)
+    out = torch.zeros(packed_shape, dtype=t.dtype)
+    out[..., :s * s * ci] = full
+    return out
+
+
+def unpack_s2d(p: torch.Tensor, s: int, tf_shape) -> torch.Tensor:
+    kh, kw, ci, co = tf_shape
+    K, R2, S2, Cs = p.shape
+    full = p[..., :s * s * ci].reshape(K, R2, S2, s, s, ci).permute(1, 3, 2, 4, 5, 0).reshape(s * R2, s * S2, ci, K)
+    return full[:kh, :kw, :, :co].contiguous()
+
+
+def embed_pool4(t: torch.Tensor, conv_stride: int = 2, kc: int = 64) -> torch.Tensor:
+    """conv(stride) + 2x2/2 max-pool as one conv of stride 2*stride: the four conv outputs of a pool window share
+    the receptive field of size k + stride, so filter (a, b) of the window is the original filter shifted by
+    (a*stride, b*stride) inside it.  [kh,kw,ci,co] -> [kh+stride, kw+stride, ci, 4*kc], filter index (2a+b)*kc + c."""
+    kh, kw, ci, co = t.shape
+    big = torch.zeros(kh + conv_stride, kw + conv_stride, ci, 4 * kc, dtype=t.dtype)
+    for a in range(2):
+        for b in range(2):
+            g = 2 * a + b
+            big[a * conv_stride:a * conv_stride + kh, b * conv_stride:b * conv_stride + kw, :, g * kc:g * kc + co] = t
+    return big
+
+
+def embed_index_map(spec: "VarSpec", derive) -> torch.Tensor:
+    """int32 [G, spec.numel]: position of every canonical (packed) element of `spec` in each copy of the derived
+    tensor produced by `derive(tf_tensor) -> list of G flat tensors` (one per copy, zeros elsewhere); -1 = none."""
+    n_tf = 1
+    for d in spec.tf_shape:
+        n_tf *= d
+    ids = torch.arange(1, n_tf + 1, dtype=torch.float64).reshape(spec.tf_shape)
+    canon = pack(spec, ids).reshape(-1).long()
+    canon_pos = torch.full((n_tf + 1,), -1, dtype=torch.long)
+    nz = canon.nonzero().reshape(-1)
+    canon_pos[canon[nz]] = nz
+    copies = derive(ids)
+    out = torch.full((len(copies), canon.numel()), -1, dtype=torch.int32)
+    for g, big in enumerate(copies):
+        big = big.reshape(-1).long()
+        pos = big.nonzero().reshape(-1)
+        out[g, canon_pos[big[pos]]] = pos.to(torch.int32)
     return out
 
 
@@ -69,6 +124,8 @@ def unpack(spec: VarSpec, p: torch.Tensor) -> torch.Tensor:
         K, R2, S2, C16 = spec.packed_shape
         full = p.view(K, R2, S2, 2, 2, 4).permute(1, 3, 2, 4, 5, 0).reshape(2 * R2, 2 * S2, 4, K)
         return full[:kh, :kw, :ci, :co].contiguous()
+    if spec.kind == "conv_kernel_s2d4":
+        return unpack_s2d(p, 4, spec.tf_shape)
     if spec.kind == "dense_kernel":
         return p.t().contiguous()
     return p[:spec.tf_shape[0]].contiguous()
@@ -102,18 +159,48 @@ def msdn_specs():
     v += _conv("coarse/conv/conv2d_3", (3, 3, 384, 384), (384, 3, 3, 384), "CoarseConv")
     v += _conv("coarse/conv/conv2d_2", (3, 3, 256, 384), (384, 3, 3, 256), "CoarseConv")
     v += _conv("coarse/conv/conv2d_1", (5, 5, 96, 256), (256, 5, 5, 96), "CoarseConv")
-    # 11x11x3 stored as 11x12x4: four 4-channel pixels = one 32-byte group for the stride-4 layer
-    v += _conv("coarse/conv/conv2d_0", (11, 11, 3, 96), (96, 11, 12, 4), "CoarseConv")
+    # 11x11x3 stride 4 stored as the 3x3x64 stride-1 filter over the space-to-depth(4) image (4x4 pixel blocks ->
+    # 48 channels, padded to 64 = 128-byte pixels): 9 taps of 128 bytes instead of 33 of 32 bytes for TMA / UMMA
+    c0 = _conv("coarse/conv/conv2d_0", (11, 11, 3, 96), (96, 3, 3, 64), "CoarseConv")
+    c0[0].kind = "conv_kernel_s2d4"
+    v += c0
     # FineA (lr 1e-3, :334-336): fine/third, fine/first
     v += _conv("fine/third", (5, 5, 64, 1), (1, 5, 5, 64), "FineA")
-    # 9x9x3 -> 63, stride 2, stored as the equivalent 5x5x16 -> 64 stride-1 filter over the space-to-depth
-    # (2x2 pixel blocks -> 16 channels) image: 32-byte pixels feed the im2col TMA / UMMA K = 16 directly
+    # 9x9x3 -> 63, stride 2: the canonical (optimizer-visible) copy is the 5x5x16 -> 64 space-to-depth(2) packing;
+    # the kernels read the DERIVED pool-embedded filter [256][3][3][64] (fine_first_embedded below) instead
     f1 = _conv("fine/first/conv2d", (9, 9, 3, 63), (64, 5, 5, 16), "FineA")
     f1[0].kind = "conv_kernel_s2d"
     v += f1
     # FineB (lr 0.01, :337-338)
     v += _conv("fine/second/conv2d", (5, 5, 64, 64), (64, 5, 5, 64), "FineB")
     return v
+
+
+FINE_FIRST_EMBEDDED_SHAPE = (256, 3, 3, 64)
+
+
+def fine_first_embedded(t: torch.Tensor) -> torch.Tensor:
+    """fine/first (9x9x3 -> 63, stride 2) + max-pool 2x2 (src/models.py:241-243) as ONE stride-4 11x11 convolution
+    with 4 x 64 filters, packed for the space-to-depth(4) image: [9,9,3,63] -> [256][3][3][64]."""
+    return pack_s2d(embed_pool4(t, 2, 64), 4, FINE_FIRST_EMBEDDED_SHAPE)
+
+
+def fine_first_index_maps(kernel_spec: "VarSpec", bias_spec: "VarSpec"):
+    """(kernel map int32 [4, numel], bias map int32 [4, 64]) for a3d_gather_sum_f32 / a3d_scatter_cast_bf16."""
+    def derive(ids):
+        copies = []
+        for g in range(4):
+            big = embed_pool4(ids, 2, 64)
+            sel = torch.zeros_like(big)
+            sel[..., g * 64:(g + 1) * 64] = big[..., g * 64:(g + 1) * 64]
+            copies.append(pack_s2d(sel, 4, FINE_FIRST_EMBEDDED_SHAPE))
+        return copies
+    kmap = embed_index_map(kernel_spec, derive)
+    bmap = torch.full((4, bias_spec.numel), -1, dtype=torch.int32)
+    n_real = bias_spec.tf_shape[0]
+    for g in range(4):
+        bmap[g, :n_real] = torch.arange(n_real, dtype=torch.int32) + g * 64
+    return kmap, bmap
 
 
 def dcnf_specs():

@@ -50,6 +50,7 @@ extern "C" {
 /* epilogue flags */
 #define A3D_EPI_RELU     1u
 #define A3D_EPI_SIGMOID  2u
+#define A3D_EPI_POOL4    4u   /* a3d_conv2d_pool4_fwd only (set internally) */
 
 typedef struct a3d_ctx a3d_ctx;
 
@@ -68,6 +69,14 @@ uint64_t a3d_launch_count(a3d_ctx* ctx);
  * src f32 [B,H,W,C] -> dst [B,OH,OW,dstC] (channels >= C are written as zero), dst_dtype F32|BF16. */
 int a3d_resize_bilinear_tf1(a3d_ctx*, const float* src, int B, int H, int W, int C,
                             void* dst, int OH, int OW, int dstC, int dst_dtype, void* stream);
+
+/* Same resize, written directly in space-to-depth layout (bf16): an s x s block of resized pixels becomes one
+ * pixel of s*s*C channels, dst[b][Y][X][(dy*s+dx)*C + c] = resized[b][s*Y+dy][s*X+dx][c]; channels
+ * [s*s*C, dstC) are zero.  dst [B,OH/s,OW/s,dstC].  MSDN (src/models.py:282, then :211 and :241): the 228x304x3
+ * image becomes 57x76x64, on which the stride-4 11x11 coarse/conv2d_0 and the pool-fused stride-2 9x9
+ * fine/first are both 3x3 stride-1 convolutions with 128-byte pixels. */
+int a3d_resize_bilinear_tf1_s2d(a3d_ctx*, const float* src, int B, int H, int W, int C,
+                                uint16_t* dst, int OH, int OW, int s, int dstC, void* stream);
 
 /* ---- convolution --------------------------------------------------------------------------- */
 typedef struct a3d_conv_desc {
@@ -105,6 +114,26 @@ int a3d_conv2d_dgrad(a3d_ctx*, const a3d_conv_desc*, const uint16_t* dy, const u
  * Both are OVERWRITTEN (not accumulated). */
 int a3d_conv2d_wgrad(a3d_ctx*, const a3d_conv_desc*, const uint16_t* x, const uint16_t* dy,
                      float* dw, float* db, void* ws, size_t ws_bytes, void* stream);
+
+/* Replaces conv2d + ReLU + max_pooling2d(2, 2) as ONE GEMM (src/models.py:241-243, fine/first): the caller
+ * supplies the "pool-embedded" filter in which the four conv outputs of a pool window are four groups of 64
+ * filters (K = 256, filter g*64 + c, g = 2*a + b for window position (a, b)) over one common receptive field;
+ * the pool is then a max over four accumulator columns of a GEMM row.  y bf16 [N,P,Q,ldy] (64 channels) =
+ * act(max_g conv_g + bias[c]); idx u8 [N,P,Q,64] (nullable) = first arg-max g (the MaxPoolGrad routing).
+ * Requires C % 64 == 0.  ws: only the A3D_IMPL_SIMT cross-check needs scratch (N*P*Q*256*4 bytes). */
+int a3d_conv2d_pool4_fwd(a3d_ctx*, const a3d_conv_desc*, const uint16_t* x, const uint16_t* w,
+                         const float* bias, uint16_t* y, uint8_t* idx, unsigned flags,
+                         void* ws, size_t ws_bytes, void* stream);
+/* MaxPoolGrad + ReluGrad of the above on the GEMM columns:
+ * dybig[row][g*64 + c] = (idx[row][c] == g && y[row][c] > 0) ? dy[row][c] : 0   (bf16 [rows][256]);
+ * a3d_conv2d_wgrad with the K = 256 descriptor then yields the embedded filter's gradient. */
+int a3d_pool4_bwd(a3d_ctx*, const uint16_t* dy, int lddy, const uint16_t* y, int ldy, const uint8_t* idx,
+                  uint16_t* dybig, size_t rows, void* stream);
+/* Embedded-filter maps: idx int32 [G][n], idx[g][e] = position of canonical element e in copy g of a derived
+ * tensor (-1: none).  gather_sum: dst[e] = sum_g src[idx[g][e]] (fold a derived filter's gradient into the
+ * canonical variable);  scatter_cast: dst[idx[g][e]] = bf16(src[e]) (refresh the derived filter). */
+int a3d_gather_sum_f32(a3d_ctx*, const float* src, const int* idx, int G, size_t n, float* dst, void* stream);
+int a3d_scatter_cast_bf16(a3d_ctx*, const float* src, const int* idx, int G, size_t n, uint16_t* dst, void* stream);
 
 /* ---- dense (tf.layers.dense) --------------------------------------------------------------- */
 /* Replaces src/models.py:228-232 (MSDN dense_0/1), :80-82,93 (DCNF).

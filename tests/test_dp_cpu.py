@@ -101,8 +101,9 @@ def test_pack_unpack_roundtrip_and_masks():
         s = a.specs[name]
         t = torch.rand(s.tf_shape, generator=g)
         assert torch.equal(unpack(s, pack(s, t)), t)
-    m = a.masks["coarse/conv/conv2d_0/kernel"].view(96, 11, 12, 4)
-    assert int(m.sum()) == 96 * 11 * 11 * 3 and not bool(m[:, :, 11, :].any()) and not bool(m[..., 3].any())
+    m = a.masks["coarse/conv/conv2d_0/kernel"].view(96, 3, 3, 64)        # space-to-depth(4) packing of 11x11x3
+    assert int(m.sum()) == 96 * 11 * 11 * 3 and not bool(m[..., 48:].any())
+    assert not bool(m[:, 2, :, 36:48].any())                              # filter row 11 (= 4*2+3) does not exist
     m = a.masks["fine/first/conv2d/kernel"].view(64, 5, 5, 16)
     assert int(m.sum()) == 63 * 9 * 9 * 3 and not bool(m[63].any())
     assert "coarse/conv/conv2d_1/kernel" not in a.masks

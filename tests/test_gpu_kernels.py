@@ -101,6 +101,9 @@ LAYERS = [
     ("dcnf_conv2d_1", 45, 45, 64, 256, 5, 5, 1, "valid"),
     ("dcnf_conv2d_2", 20, 20, 256, 256, 3, 3, 1, "valid"),
     ("c16_k32", 17, 19, 16, 32, 3, 3, 1, "same"),
+    # the two first layers on the space-to-depth(4) image (params.py: conv_kernel_s2d4 / fine_first_embedded)
+    ("conv2d_0_s2d4", 57, 76, 64, 96, 3, 3, 1, "valid"),
+    ("fine_first_pool_gemm", 57, 76, 64, 256, 3, 3, 1, "valid"),
 ]
 # 3-channel first layers as the B200 path stores them: 4-channel pixels, filter width padded so that
 # groups of 16/C pixels can be read as one 16-channel pixel (conv.cu `virtualize`)
@@ -398,3 +401,65 @@ def test_maxpool_f32_routing(ctx, N, H, W, C):
     gx = gx.permute(0, 2, 3, 1) * (x > 0)
     dx = ctx.maxpool2x2_idx_bwd(idx, dy, (N, H, W, C))
     assert torch.equal(dx.float(), gx)
+
+
+# ----------------------------------------------------------------------------- pool-fused conv, s2d resize, index maps
+@pytest.mark.parametrize("impl", ["tc", "simt"])
+def test_conv_pool4_fwd_bwd(ctx, impl):
+    """conv + bias + ReLU + 2x2 max-pool as one GEMM (a3d_conv2d_pool4_fwd) and its MaxPoolGrad/ReluGrad."""
+    N, H, W, Cc = 2, 57, 76, 64
+    d = ops.conv_desc(N, H, W, Cc, 256, 3, 3, 1, "valid", ldy=64, impl=L.IMPL_SIMT if impl == "simt" else L.IMPL_AUTO)
+    x = bf16_rand(N, H, W, Cc, seed=40)
+    w = bf16_rand(256, 3, 3, Cc, seed=41, scale=1.0 / math.sqrt(9 * Cc))
+    bias = (torch.rand(64, generator=torch.Generator().manual_seed(42)) - 0.5).to(DEV) * 0.2
+    y = torch.full((N, d.P, d.Q, 64), 7.0, dtype=torch.bfloat16, device=DEV)
+    idx = torch.full((N, d.P, d.Q, 64), 9, dtype=torch.uint8, device=DEV)
+    ctx.conv2d_pool4_fwd(d, x, w, bias, relu=True, out=y, idx=idx)
+    acc = torch_conv_ref(x, w, None, 1, 0, 0, d.P, d.Q, False).view(N, d.P, d.Q, 4, 64)
+    m, gi = acc.max(3)
+    ref = torch.relu(m + bias)
+    assert rel_err(y, ref) < 1e-2
+    # routing: identical wherever the winner is clear (f32 accumulation order differs in the last bits)
+    top2 = acc.topk(2, dim=3).values
+    clear = (top2[..., 0] - top2[..., 1]) > 1e-3
+    assert bool((idx.long()[clear] == gi[clear]).all()) and int(idx.max()) <= 3
+    # backward: dy routed to the arg-max group where the pooled output is positive
+    dy = bf16_rand(N, d.P, d.Q, 64, seed=43)
+    big = ctx.pool4_bwd(dy.view(-1, 64), y.view(-1, 64), idx)
+    exp = torch.zeros(N * d.P * d.Q, 4, 64, device=DEV)
+    exp.scatter_(1, idx.view(-1, 1, 64).long(), (dy.float() * (y.float() > 0)).view(-1, 1, 64))
+    assert torch.equal(big.float().view(-1, 4, 64), exp)
+
+
+def test_resize_s2d_matches_resize_then_space_to_depth(ctx):
+    g = torch.Generator().manual_seed(44)
+    src = torch.rand(2, 480, 640, 3, generator=g).to(DEV)
+    flat = ctx.resize_bilinear_tf1(src, 228, 304, dstC=3, dtype=torch.bfloat16)
+    out = torch.full((2, 57, 76, 64), 5.0, dtype=torch.bfloat16, device=DEV)
+    ctx.resize_bilinear_tf1_s2d(src, 228, 304, 4, out=out)
+    exp = flat.view(2, 57, 4, 76, 4, 3).permute(0, 1, 3, 2, 4, 5).reshape(2, 57, 76, 48)
+    assert torch.equal(out[..., :48], exp)
+    assert float(out[..., 48:].abs().max()) == 0.0
+
+
+def test_gather_sum_and_scatter_cast(ctx):
+    g = torch.Generator().manual_seed(45)
+    n, G, big = 1000, 4, 5000
+    perm = torch.stack([torch.randperm(big, generator=g)[:n] for _ in range(G)]).to(torch.int32)
+    perm[1, ::7] = -1
+    src = torch.rand(big, generator=g).to(DEV)
+    idx = perm.to(DEV)
+    dst = torch.empty(n, device=DEV)
+    ctx.gather_sum_f32(src, idx, dst)
+    exp = torch.zeros(n, device=DEV)
+    for k in range(G):
+        ok = idx[k] >= 0
+        exp[ok] += src[idx[k][ok].long()]
+    assert torch.allclose(dst, exp, atol=1e-6)
+    w = torch.rand(n, generator=g).to(DEV)
+    out = torch.zeros(big, dtype=torch.bfloat16, device=DEV)
+    one = idx[:1].contiguous()                       # a single copy: no write conflicts
+    ctx.scatter_cast_bf16(w, one, out)
+    exp = torch.zeros(big, dtype=torch.bfloat16, device=DEV)
+    exp[one[0].long()] = w.bfloat16()
+    assert torch.equal(out, exp)

@@ -1,0 +1,79 @@
+"""CPU checks of the packed layouts the CUDA path computes on (ann3depth_b200/params.py): the
+space-to-depth(4) packing of coarse/conv2d_0 (src/models.py:211) and the pool-embedded form of
+fine/first + max-pool (src/models.py:241-243) must be the SAME function as the TF-layout convolution the
+oracle evaluates, and the index maps must fold / re-embed exactly."""
+import torch
+import torch.nn.functional as F
+
+from ann3depth_b200 import params as P
+
+
+def _s2d4(img):
+    B, H, W, C = img.shape
+    out = torch.zeros(B, H // 4, W // 4, 64, dtype=img.dtype)
+    out[..., :16 * C] = img.view(B, H // 4, 4, W // 4, 4, C).permute(0, 1, 3, 2, 4, 5).reshape(B, H // 4, W // 4, 16 * C)
+    return out
+
+
+def _specs():
+    return {s.name: s for s in P.msdn_specs()}
+
+
+def test_conv0_space_to_depth4_is_the_stride4_conv():
+    g = torch.Generator().manual_seed(0)
+    img = torch.rand(2, 228, 304, 3, generator=g, dtype=torch.float64)
+    w = torch.rand(11, 11, 3, 96, generator=g, dtype=torch.float64) - 0.5
+    ref = F.conv2d(img.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), stride=4)
+    s = _specs()["coarse/conv/conv2d_0/kernel"]
+    pk = P.pack(s, w)
+    assert pk.shape == (96, 3, 3, 64) and torch.equal(P.unpack(s, pk), w)
+    got = F.conv2d(_s2d4(img).permute(0, 3, 1, 2), pk.permute(0, 3, 1, 2))
+    assert got.shape == ref.shape == (2, 96, 55, 74)
+    assert float((got - ref).abs().max()) < 1e-12
+
+
+def test_fine_first_pool_embedding_is_conv_then_maxpool():
+    g = torch.Generator().manual_seed(1)
+    img = torch.rand(2, 228, 304, 3, generator=g, dtype=torch.float64)
+    w = torch.rand(9, 9, 3, 63, generator=g, dtype=torch.float64) - 0.5
+    y = F.conv2d(img.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), stride=2)
+    assert y.shape == (2, 63, 110, 148)
+    pooled, arg = F.max_pool2d(y, 2, 2, return_indices=True)
+    big = P.fine_first_embedded(w)
+    assert big.shape == P.FINE_FIRST_EMBEDDED_SHAPE
+    acc = F.conv2d(_s2d4(img).permute(0, 3, 1, 2), big.permute(0, 3, 1, 2)).view(2, 4, 64, 55, 74)
+    m, gi = acc.max(1)
+    assert float((m[:, :63] - pooled).abs().max()) < 1e-12
+    assert float(m[:, 63].abs().max()) == 0.0                         # padding filter
+    # group index g = 2a + b <-> window position (a, b) of the 2x2 pool
+    a, b = gi[:, :63] // 2, gi[:, :63] % 2
+    ii = torch.arange(55).view(1, 1, 55, 1)
+    jj = torch.arange(74).view(1, 1, 1, 74)
+    flat = (2 * ii + a) * 148 + (2 * jj + b)
+    assert torch.equal(flat, arg)
+
+
+def test_fine_first_index_maps_fold_and_embed():
+    sp = _specs()
+    ks, bs = sp["fine/first/conv2d/kernel"], sp["fine/first/conv2d/bias"]
+    kmap, bmap = P.fine_first_index_maps(ks, bs)
+    assert kmap.shape == (4, ks.numel) and bmap.shape == (4, 64)
+    assert [int(x) for x in (kmap >= 0).sum(1)] == [9 * 9 * 3 * 63] * 4
+    w = torch.rand(9, 9, 3, 63, dtype=torch.float64) - 0.5
+    canon = P.pack(ks, w).reshape(-1)
+    big = torch.zeros(256 * 3 * 3 * 64, dtype=torch.float64)
+    for g in range(4):
+        m = kmap[g] >= 0
+        big[kmap[g][m].long()] = canon[m]
+    assert torch.equal(big.view(P.FINE_FIRST_EMBEDDED_SHAPE), P.fine_first_embedded(w))
+    # gradient fold == autograd through the embedding
+    gb = torch.rand(big.numel(), dtype=torch.float64)
+    fold = torch.zeros_like(canon)
+    for g in range(4):
+        m = kmap[g] >= 0
+        fold[m] += gb[kmap[g][m].long()]
+    wr = w.clone().requires_grad_(True)
+    (P.fine_first_embedded(wr).reshape(-1) * gb).sum().backward()
+    assert float((P.unpack(ks, fold.view(ks.packed_shape)) - wr.grad).abs().max()) < 1e-12
+    assert torch.equal(bmap[:, 63], torch.full((4,), -1, dtype=torch.int32))
+    assert torch.equal(bmap[2, :63], torch.arange(63, dtype=torch.int32) + 128)

@@ -96,6 +96,22 @@ def main():
                 rec[k + "_tflops"] = flops / rec[k + "_us"] / 1e6
         rows.append(rec)
         print(json.dumps(rec), flush=True)
+    # pool-fused fine/first (conv + ReLU + 2x2 max-pool in one GEMM)
+    if not args.only or "pool4" in args.only:
+        d = ops.conv_desc(32, 57, 76, 64, 256, 3, 3, 1, "valid", ldy=64)
+        x = (torch.rand(32, 57, 76, 64, device=dev) - 0.5).bfloat16()
+        w = (torch.rand(256, 3, 3, 64, device=dev) - 0.5).bfloat16()
+        b = torch.zeros(64, device=dev)
+        y = torch.empty(32, 55, 74, 64, dtype=torch.bfloat16, device=dev)
+        idx = torch.empty(32, 55, 74, 64, dtype=torch.uint8, device=dev)
+        rec = {"name": "f1 pool4 fused 3x3x64 -> 4x64 (s2d4)"}
+        fn = lambda: ctx.conv2d_pool4_fwd(d, x, w, b, relu=True, out=y, idx=idx)
+        fn(); torch.cuda.synchronize()
+        rec["fwd_us"] = timed(fn, args.reps, buf)
+        fn = lambda: ctx.conv2d_pool4_fwd(d, x, w, b, relu=True, out=y, idx=None)
+        rec["fwd_noidx_us"] = timed(fn, args.reps, buf)
+        rows.append(rec)
+        print(json.dumps(rec), flush=True)
     # dense layers (batch 32)
     for (M, Nn, K) in ((32, 4096, 12288), (32, 4070, 4096)):
         if args.only and "dense" not in args.only:
