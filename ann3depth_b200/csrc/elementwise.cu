@@ -672,15 +672,66 @@ __global__ void resize_bilinear_tf1_s2d_kernel(const float* __restrict__ src, in
   }
 }
 
+// s = 4, C = 3 (the MSDN image): one thread = one row of a 4x4 block = 4 resized pixels x 3 channels = 24 contiguous
+// output bytes; neighbouring threads read neighbouring source strips.  The zero channels [48, dstC) are written by
+// the dy == 0 thread (40 bytes when dstC = 64).
+__global__ void resize_bilinear_tf1_s2d4c3_kernel(const float* __restrict__ src, int B, int H, int W,
+                                                  uint16_t* __restrict__ dst, int OH, int OWs, int dstC, float sy, float sx) {
+  const size_t total = (size_t)B * OH * OWs;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int X = (int)(i % OWs);
+    size_t t = i / OWs;
+    const int oy = (int)(t % OH);
+    const int b = (int)(t / OH);
+    const float fy = oy * sy;
+    const int y0 = (int)floorf(fy);
+    const int y1 = min(y0 + 1, H - 1);
+    const float ly = fy - y0;
+    const float* r0 = src + ((size_t)b * H + y0) * W * 3;
+    const float* r1 = src + ((size_t)b * H + y1) * W * 3;
+    float v[12];
+#pragma unroll
+    for (int dx = 0; dx < 4; ++dx) {
+      const float fx = (X * 4 + dx) * sx;
+      const int x0 = (int)floorf(fx);
+      const int x1 = min(x0 + 1, W - 1);
+      const float lx = fx - x0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float tl = __ldg(r0 + (size_t)x0 * 3 + c), tr = __ldg(r0 + (size_t)x1 * 3 + c);
+        const float bl = __ldg(r1 + (size_t)x0 * 3 + c), br = __ldg(r1 + (size_t)x1 * 3 + c);
+        const float top = tl + (tr - tl) * lx;
+        const float bot = bl + (br - bl) * lx;
+        v[dx * 3 + c] = top + (bot - top) * ly;
+      }
+    }
+    const int Y = oy >> 2, dy = oy & 3;
+    uint16_t* o = dst + (((size_t)b * (OH >> 2) + Y) * OWs + X) * dstC;
+    uint2* o8 = reinterpret_cast<uint2*>(o + dy * 12);
+    o8[0] = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+    o8[1] = make_uint2(pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    o8[2] = make_uint2(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]));
+    if (dy == 0)
+      for (int k = 48; k < dstC; k += 4) *reinterpret_cast<uint2*>(o + k) = make_uint2(0u, 0u);
+  }
+}
+
 extern "C" int a3d_resize_bilinear_tf1_s2d(a3d_ctx* ctx, const float* src, int B, int H, int W, int C, uint16_t* dst,
                                            int OH, int OW, int s, int dstC, void* stream) {
   A3D_REQUIRE(ctx && src && dst, "resize_s2d: null argument");
   A3D_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && s > 0 && OH % s == 0 && OW % s == 0 && dstC % 8 == 0 &&
                   dstC >= s * s * C && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
               "resize_s2d: bad shape (OH, OW multiples of s; dstC %% 8 == 0 and >= s*s*C)");
+  float sy = (float)H / (float)OH, sx = (float)W / (float)OW;
+  if (s == 4 && C == 3) {
+    const size_t rows = (size_t)B * OH * (OW / 4);
+    int block = 256, grid = grid_for(ctx, rows, block);
+    resize_bilinear_tf1_s2d4c3_kernel<<<grid, block, 0, as_stream(stream)>>>(src, B, H, W, dst, OH, OW / 4, dstC, sy, sx);
+    A3D_LAUNCH_OK(ctx);
+    return 0;
+  }
   const size_t total = (size_t)B * (OH / s) * (OW / s) * (dstC / 8);
   int block = 256, grid = grid_for(ctx, total, block);
-  float sy = (float)H / (float)OH, sx = (float)W / (float)OW;
   resize_bilinear_tf1_s2d_kernel<<<grid, block, 0, as_stream(stream)>>>(src, B, H, W, C, reinterpret_cast<uint4*>(dst),
                                                                       OH / s, OW / s, s, dstC / 8, sy, sx);
   A3D_LAUNCH_OK(ctx);

@@ -3,6 +3,7 @@
 #include "tc_gemm.cuh"
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -263,6 +264,76 @@ int finish(a3d_ctx* ctx, const float* acc, const float* bias, const uint8_t* mas
 
 }  // namespace
 
+// ---- first-use autotuning -------------------------------------------------------------------------
+// The best tile width / split-K factor of the small MSDN layers depends on how many CTAs end up co-resident
+// and on wave quantisation in ways the closed-form heuristics above miss by up to 1.8x (profiles/sweep_r01_*).
+// The first launch of a shape (outside stream capture) therefore times every candidate configuration with CUDA
+// events on the launching stream and caches the winner; later launches -- including the captured ones of the
+// CUDA graph -- reuse it.  Candidate runs overwrite the same output, so tuning has no side effects.
+// A3D_AUTOTUNE=0 keeps the heuristic choice (candidate 0).
+namespace {
+struct TuneKey { int v[16]; };
+struct TuneEntry { TuneKey key; int choice; };
+TuneEntry g_tune[256];
+int g_tune_n = 0;
+
+bool autotune_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("A3D_AUTOTUNE"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
+
+// run(c) launches candidate c on `st`; returns the index of the fastest candidate (0 when tuning is unavailable)
+template <class F>
+int autotune(const TuneKey& key, int ncand, F run, cudaStream_t st) {
+  for (int i = 0; i < g_tune_n; ++i)
+    if (memcmp(&g_tune[i].key, &key, sizeof(TuneKey)) == 0) return g_tune[i].choice;
+  if (!autotune_enabled() || ncand <= 1) return 0;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return 0;
+  cudaEvent_t e0, e1;
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return 0;
+  int best = 0;
+  float best_ms = 1e30f;
+  for (int c = 0; c < ncand; ++c) {
+    if (run(c) != 0) continue;                     // warm-up (function attributes, L2)
+    cudaEventRecord(e0, st);
+    bool ok = true;
+    for (int r = 0; r < 3 && ok; ++r) ok = run(c) == 0;
+    cudaEventRecord(e1, st);
+    if (cudaEventSynchronize(e1) != cudaSuccess || !ok) continue;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best_ms) { best_ms = ms; best = c; }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (g_tune_n < 256) { g_tune[g_tune_n].key = key; g_tune[g_tune_n].choice = best; ++g_tune_n; }
+  if (getenv("A3D_AUTOTUNE_VERBOSE"))
+    fprintf(stderr, "a3d autotune: kind %d [%d %d %d %d %d %d %d %d %d] -> candidate %d of %d (%.1f us)\n", key.v[0],
+            key.v[1], key.v[2], key.v[3], key.v[4], key.v[5], key.v[6], key.v[7], key.v[8], key.v[9], best, ncand,
+            best_ms * 1e3f / 3);
+  return best;
+}
+// split-K candidates for the weight-streaming dense kernels: the heuristic first, then CTA counts of
+// 1, 1.5 and 2 x SM count (two CTAs are co-resident per SM; a partial extra wave doubles the time)
+int split_candidates(a3d_ctx* ctx, int tiles, int num_kb, int heuristic, int* out) {
+  int n = 0;
+  out[n++] = heuristic;
+  const int targets[4] = {ctx->sm_count, ctx->sm_count * 3 / 2, ctx->sm_count * 2, ctx->sm_count * 5 / 2};
+  for (int t = 0; t < 4; ++t) {
+    int s = targets[t] / tiles;
+    const int max_s = num_kb / 4 > 0 ? num_kb / 4 : 1;
+    if (s > max_s) s = max_s;
+    if (s < 1) s = 1;
+    bool dup = false;
+    for (int k = 0; k < n; ++k) dup |= out[k] == s;
+    if (!dup) out[n++] = s;
+  }
+  return n;
+}
+}  // namespace
+
 // ------------------------------------------------------------------------------------------------
 // convolution forward as an implicit GEMM: M = N*P*Q output pixels, N = K filters, K = R*S*C
 int a3d_tc_conv_fwd_supported(const a3d_conv_desc* d) {
@@ -314,36 +385,73 @@ int a3d_tc_conv_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, con
   const int cblocks = d->C / kc;
   const int num_kb = kc == 8 ? ceil_div(d->R * d->S * cblocks, 8) : d->R * d->S * cblocks;
   const long long M = (long long)d->N * d->P * d->Q;
-  int bn = pick_bn(d->K);
-  if (kc == 8 && bn < 32) bn = 32;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA;
   int rc = make_tmap_im2col(ctx, &tmA, x, d->N, d->H, d->W, d->C, -d->pad_t, -d->pad_l, d->P, d->Q, d->stride_h,
                             d->stride_w, kc, 128);
-  if (rc) return rc;
-  if (kc == 8) rc = make_tmap_chunked(ctx, &tmB, w, d->K, (uint64_t)d->R * d->S * d->C, bn);
-  else rc = make_tmap_2d(ctx, &tmB, w, d->K, (uint64_t)d->R * d->S * d->C, (uint64_t)d->R * d->S * d->C, kc, bn);
   if (rc) return rc;
   tc::Params p{};
   p.M = (int)M; p.N = d->K; p.num_kb = num_kb;
   p.a_mode = tc::A_IM2COL; p.a_k0 = 0;
   p.PQ = d->P * d->Q; p.Q = d->Q; p.sh = d->stride_h; p.sw = d->stride_w; p.lower_h = -d->pad_t; p.lower_w = -d->pad_l;
   p.S = d->S; p.cblocks = cblocks;
-  const int tiles = ceil_div(M, 128) * ceil_div(d->K, bn);
-  int splits = pick_splits(ctx, tiles, num_kb, 8);
-  if (splits > 1 && (!ws || ws_bytes < (size_t)M * d->K * sizeof(float))) splits = 1;
-  p.kb_per_split = ceil_div(num_kb, splits);
-  splits = ceil_div(num_kb, p.kb_per_split);
-  if (splits == 1) {
-    p.epi = y_dtype == A3D_F32 ? tc::EPI_ROW_F32 : tc::EPI_ROW_BF16;
-    p.out = y; p.ldo = d->ldy; p.bias = bias; p.flags = flags; p.atomic = 0;
-    return launch_kk(ctx, bn, kcb, tmA, tmB, p, 1, st);
+  const bool can_split = ws && ws_bytes >= (size_t)M * d->K * sizeof(float);
+
+  auto launch = [&](int bn, int splits) -> int {
+    CUtensorMap tmB;
+    int r = kc == 8 ? make_tmap_chunked(ctx, &tmB, w, d->K, (uint64_t)d->R * d->S * d->C, bn)
+                    : make_tmap_2d(ctx, &tmB, w, d->K, (uint64_t)d->R * d->S * d->C, (uint64_t)d->R * d->S * d->C, kc, bn);
+    if (r) return r;
+    tc::Params q = p;
+    if (!can_split) splits = 1;
+    q.kb_per_split = ceil_div(num_kb, splits);
+    splits = ceil_div(num_kb, q.kb_per_split);
+    if (splits == 1) {
+      q.epi = y_dtype == A3D_F32 ? tc::EPI_ROW_F32 : tc::EPI_ROW_BF16;
+      q.out = y; q.ldo = d->ldy; q.bias = bias; q.flags = flags; q.atomic = 0;
+      return launch_kk(ctx, bn, kcb, tmA, tmB, q, 1, st);
+    }
+    A3D_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)M * d->K * sizeof(float), st));
+    q.epi = tc::EPI_ROW_F32; q.out = ws; q.ldo = d->K; q.bias = nullptr; q.flags = 0; q.atomic = 1;
+    r = launch_kk(ctx, bn, kcb, tmA, tmB, q, splits, st);
+    if (r) return r;
+    return finish(ctx, reinterpret_cast<const float*>(ws), bias, nullptr, 0.f, y, y_dtype == A3D_F32, (size_t)M, d->K,
+                  d->ldy, flags, st);
+  };
+  auto tiles_of = [&](int bn) { return ceil_div(M, 128) * ceil_div(d->K, bn); };
+  // candidate 0 = heuristic; then the tile widths that cover K with little padding, each with 1 and ~1-2 waves of split-K
+  struct Cand { int bn, splits; };
+  Cand cand[24];
+  int nc = 0;
+  {
+    int bn0 = pick_bn(d->K);
+    if (kc == 8 && bn0 < 32) bn0 = 32;
+    cand[nc++] = {bn0, pick_splits(ctx, tiles_of(bn0), num_kb, 8)};
   }
-  A3D_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)M * d->K * sizeof(float), st));
-  p.epi = tc::EPI_ROW_F32; p.out = ws; p.ldo = d->K; p.bias = nullptr; p.flags = 0; p.atomic = 1;
-  rc = launch_kk(ctx, bn, kcb, tmA, tmB, p, splits, st);
-  if (rc) return rc;
-  return finish(ctx, reinterpret_cast<const float*>(ws), bias, nullptr, 0.f, y, y_dtype == A3D_F32, (size_t)M, d->K,
-                d->ldy, flags, st);
+  static const int widths[] = {64, 96, 128, 192, 256};
+  for (int i = 0; i < 5; ++i) {
+    const int bn = widths[i];
+    if (kc == 8 && bn > 128) continue;                        // chunked kernels exist up to BN = 128
+    if (kc == 16 && bn == 192) continue;                      // (no <192, 32> instantiation)
+    const int padded = ceil_div(d->K, bn) * bn;
+    if (padded > d->K + d->K / 3 + 15) continue;              // more than a third of the columns would be padding
+    const int tiles = tiles_of(bn);
+    const int sopts[3] = {1, ctx->sm_count / tiles, 2 * ctx->sm_count / tiles};
+    for (int t = 0; t < 3; ++t) {
+      int sp = sopts[t];
+      const int max_s = num_kb / 8 > 0 ? num_kb / 8 : 1;
+      if (sp > max_s) sp = max_s;
+      if (sp < 1 || !can_split) sp = 1;
+      bool dup = false;
+      for (int k = 0; k < nc; ++k) dup |= (cand[k].bn == bn && cand[k].splits == sp);
+      if (!dup && nc < 24) cand[nc++] = {bn, sp};
+    }
+  }
+  TuneKey key{};
+  const int kv[16] = {2, d->N, d->H, d->W, d->C, d->K, d->R, d->S, d->stride_h, d->stride_w, d->pad_t, d->pad_l,
+                      d->P, d->Q, d->ldy, y_dtype * 2 + (can_split ? 1 : 0)};
+  memcpy(key.v, kv, sizeof(kv));
+  const int best = autotune(key, nc, [&](int c) { return launch(cand[c].bn, cand[c].splits); }, st);
+  return launch(cand[best].bn, cand[best].splits);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -366,16 +474,25 @@ int a3d_tc_dense_fwd(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t* w
   tc::Params p{};
   p.M = N; p.N = M; p.num_kb = K / 64; p.a_mode = tc::A_TILED; p.a_k0 = 0;
   const int tiles = ceil_div(N, 128);
-  int splits = pick_splits(ctx, tiles, p.num_kb, 4);
+  int splits0 = pick_splits(ctx, tiles, p.num_kb, 4);
   // weight streaming is HBM-bound: two CTAs' worth of loads in flight per SM helps, so oversubscribe
-  if (splits * tiles < 2 * ctx->sm_count && p.num_kb / (splits * 2) >= 4) splits *= 2;
-  p.kb_per_split = ceil_div(p.num_kb, splits);
-  splits = ceil_div(p.num_kb, p.kb_per_split);
-  A3D_CHECK_CUDA(cudaMemsetAsync(acc_ws, 0, (size_t)M * N * sizeof(float), st));
+  if (splits0 * tiles < 2 * ctx->sm_count && p.num_kb / (splits0 * 2) >= 4) splits0 *= 2;
   p.epi = tc::EPI_COL_F32; p.out = acc_ws; p.ldo = N; p.bias = nullptr; p.flags = 0; p.atomic = 1;
-  rc = launch_kk(ctx, bn, 128, tmA, tmB, p, splits, st);
-  if (rc) return rc;
-  return finish(ctx, acc_ws, bias, mask, drop_rate, y, y_dtype == A3D_F32, (size_t)M, N, N, flags, st);
+  auto launch = [&](int splits) -> int {
+    tc::Params q = p;
+    q.kb_per_split = ceil_div(q.num_kb, splits);
+    splits = ceil_div(q.num_kb, q.kb_per_split);
+    A3D_CHECK_CUDA(cudaMemsetAsync(acc_ws, 0, (size_t)M * N * sizeof(float), st));
+    int r = launch_kk(ctx, bn, 128, tmA, tmB, q, splits, st);
+    if (r) return r;
+    return finish(ctx, acc_ws, bias, mask, drop_rate, y, y_dtype == A3D_F32, (size_t)M, N, N, flags, st);
+  };
+  int cand[8];
+  const int nc = split_candidates(ctx, tiles, p.num_kb, splits0, cand);
+  TuneKey key{};
+  const int kv[16] = {3, M, N, K, ldx, y_dtype, (int)flags, mask != nullptr};
+  memcpy(key.v, kv, sizeof(kv));
+  return launch(cand[autotune(key, nc, [&](int c) { return launch(cand[c]); }, st)]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -417,11 +534,9 @@ int a3d_tc_conv_wgrad(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, c
   const int cblocks = d->C / bw;
   const int RS = d->R * d->S;
   const int total_blocks = RS * cblocks;
-  int nblk = pick_nblk(bw, total_blocks);
-  static int nblk_env = -1, splits_env = -1;       // experiment knobs
+  static int nblk_env = -1, splits_env = -1;       // experiment knobs: force one configuration
   if (nblk_env < 0) { const char* e = getenv("A3D_WGRAD_NBLK"); nblk_env = e ? atoi(e) : 0; }
   if (splits_env < 0) { const char* e = getenv("A3D_WGRAD_SPLITS"); splits_env = e ? atoi(e) : 0; }
-  if (nblk_env > 0) nblk = nblk_env;
   const long long Mpix = (long long)d->N * d->P * d->Q;
   CUtensorMap tmA, tmB;
   int rc = make_tmap_2d(ctx, &tmA, dy, Mpix, d->K, d->ldy, 64, 64);
@@ -434,20 +549,56 @@ int a3d_tc_conv_wgrad(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, c
   p.a_mode = tc::A_TILED; p.b_im2col = 1; p.RS = RS;
   p.PQ = d->P * d->Q; p.Q = d->Q; p.sh = d->stride_h; p.sw = d->stride_w; p.lower_h = -d->pad_t; p.lower_w = -d->pad_l;
   p.S = d->S; p.cblocks = cblocks;
-  const int tiles = ceil_div(d->K, 128) * ceil_div(total_blocks, nblk);
-  int splits = pick_splits(ctx, tiles, p.num_kb, 4);
-  if (splits_env > 0) splits = splits_env;
-  p.kb_per_split = ceil_div(p.num_kb, splits);
-  splits = ceil_div(p.num_kb, p.kb_per_split);
-  p.epi = tc::EPI_ROW_F32; p.out = dw; p.ldo = (long long)RS * d->C; p.atomic = splits > 1;
-  if (splits > 1) A3D_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)d->K * RS * d->C * sizeof(float), st));
-#define A3D_WG(BW, NB) if (bw == BW && nblk == NB) return launch_wgrad<BW, NB>(ctx, tmA, tmB, p, splits, st);
-  A3D_WG(64, 4) A3D_WG(64, 3) A3D_WG(64, 2) A3D_WG(64, 1)
-  A3D_WG(32, 6) A3D_WG(32, 5) A3D_WG(32, 4) A3D_WG(32, 3)
-  A3D_WG(16, 16) A3D_WG(16, 11) A3D_WG(16, 8)
+  p.epi = tc::EPI_ROW_F32; p.out = dw; p.ldo = (long long)RS * d->C;
+
+  auto launch = [&](int nblk, int splits) -> int {
+    tc::Params q = p;
+    q.kb_per_split = ceil_div(q.num_kb, splits);
+    splits = ceil_div(q.num_kb, q.kb_per_split);
+    q.atomic = splits > 1;
+    if (splits > 1) A3D_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)d->K * RS * d->C * sizeof(float), st));
+#define A3D_WG(BW, NB) if (bw == BW && nblk == NB) return launch_wgrad<BW, NB>(ctx, tmA, tmB, q, splits, st);
+    A3D_WG(64, 4) A3D_WG(64, 3) A3D_WG(64, 2) A3D_WG(64, 1)
+    A3D_WG(32, 6) A3D_WG(32, 5) A3D_WG(32, 4) A3D_WG(32, 3)
+    A3D_WG(16, 16) A3D_WG(16, 11) A3D_WG(16, 8)
 #undef A3D_WG
-  a3d_set_error("tc conv wgrad: no kernel for BW=%d NBLK=%d", bw, nblk);
-  return A3D_ENOTSUP;
+    a3d_set_error("tc conv wgrad: no kernel for BW=%d NBLK=%d", bw, nblk);
+    return A3D_ENOTSUP;
+  };
+  auto tiles_of = [&](int nblk) { return ceil_div(d->K, 128) * ceil_div(total_blocks, nblk); };
+  if (nblk_env > 0 || splits_env > 0) {
+    const int nblk = nblk_env > 0 ? nblk_env : pick_nblk(bw, total_blocks);
+    return launch(nblk, splits_env > 0 ? splits_env : pick_splits(ctx, tiles_of(nblk), p.num_kb, 4));
+  }
+  // candidates: candidate 0 is the heuristic; then every tile width x {1, 1.5, 2, 3} waves' worth of CTAs
+  struct Cand { int nblk, splits; };
+  Cand cand[40];
+  int nc = 0;
+  {
+    const int nb0 = pick_nblk(bw, total_blocks);
+    cand[nc++] = {nb0, pick_splits(ctx, tiles_of(nb0), p.num_kb, 4)};
+  }
+  static const int w64[] = {1, 2, 3, 4, 0}, w32[] = {3, 4, 5, 6, 0}, w16[] = {8, 11, 16, 0};
+  const int* widths = bw == 64 ? w64 : bw == 32 ? w32 : w16;
+  for (int i = 0; widths[i]; ++i) {
+    const int tiles = tiles_of(widths[i]);
+    static const int target_x2[] = {2, 3, 4, 6};      // CTAs ~ target/2 x SM count
+    for (int t = 0; t < 4; ++t) {
+      int s = (ctx->sm_count * target_x2[t] / 2) / tiles;
+      const int max_s = p.num_kb / 4 > 0 ? p.num_kb / 4 : 1;
+      if (s > max_s) s = max_s;
+      if (s < 1) s = 1;
+      bool dup = false;
+      for (int k = 0; k < nc; ++k) dup |= (cand[k].nblk == widths[i] && cand[k].splits == s);
+      if (!dup && nc < 40) cand[nc++] = {widths[i], s};
+    }
+  }
+  TuneKey key{};
+  const int kv[16] = {1, d->N, d->H, d->W, d->C, d->K, d->R, d->S, d->stride_h, d->stride_w, d->pad_t, d->pad_l,
+                      d->P, d->Q, d->ldy, 0};
+  memcpy(key.v, kv, sizeof(kv));
+  const int best = autotune(key, nc, [&](int c) { return launch(cand[c].nblk, cand[c].splits); }, st);
+  return launch(cand[best].nblk, cand[best].splits);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -492,17 +643,27 @@ int a3d_tc_dense_dgrad(a3d_ctx* ctx, const uint16_t* dy, int lddy, const uint16_
   tc::Params p{};
   p.M = K; p.N = M; p.num_kb = ceil_div(N, 64); p.a_mode = tc::A_TILED;
   const int tiles = ceil_div(K, 128);
-  int splits = pick_splits(ctx, tiles, p.num_kb, 4);
-  if (splits * tiles < 2 * ctx->sm_count && p.num_kb / (splits * 2) >= 4) splits *= 2;
-  p.kb_per_split = ceil_div(p.num_kb, splits);
-  splits = ceil_div(p.num_kb, p.kb_per_split);
-  A3D_CHECK_CUDA(cudaMemsetAsync(acc_ws, 0, (size_t)M * K * sizeof(float), st));
+  int splits0 = pick_splits(ctx, tiles, p.num_kb, 4);
+  if (splits0 * tiles < 2 * ctx->sm_count && p.num_kb / (splits0 * 2) >= 4) splits0 *= 2;
   p.epi = tc::EPI_COL_F32; p.out = acc_ws; p.ldo = K; p.atomic = 1;
-  if (bn == 32) rc = launch_cfg<tc::Cfg<32, 128, true, false>>(ctx, tmA, tmB, p, splits, st);
-  else if (bn == 64) rc = launch_cfg<tc::Cfg<64, 128, true, false>>(ctx, tmA, tmB, p, splits, st);
-  else rc = launch_cfg<tc::Cfg<128, 128, true, false>>(ctx, tmA, tmB, p, splits, st);
-  if (rc) return rc;
-  return finish(ctx, acc_ws, nullptr, nullptr, 0.f, dx, 0, (size_t)M, K, K, 0, st);
+  auto launch = [&](int splits) -> int {
+    tc::Params q = p;
+    q.kb_per_split = ceil_div(q.num_kb, splits);
+    splits = ceil_div(q.num_kb, q.kb_per_split);
+    A3D_CHECK_CUDA(cudaMemsetAsync(acc_ws, 0, (size_t)M * K * sizeof(float), st));
+    int r;
+    if (bn == 32) r = launch_cfg<tc::Cfg<32, 128, true, false>>(ctx, tmA, tmB, q, splits, st);
+    else if (bn == 64) r = launch_cfg<tc::Cfg<64, 128, true, false>>(ctx, tmA, tmB, q, splits, st);
+    else r = launch_cfg<tc::Cfg<128, 128, true, false>>(ctx, tmA, tmB, q, splits, st);
+    if (r) return r;
+    return finish(ctx, acc_ws, nullptr, nullptr, 0.f, dx, 0, (size_t)M, K, K, 0, st);
+  };
+  int cand[8];
+  const int nc = split_candidates(ctx, tiles, p.num_kb, splits0, cand);
+  TuneKey key{};
+  const int kv[16] = {4, M, N, K, lddy};
+  memcpy(key.v, kv, sizeof(kv));
+  return launch(cand[autotune(key, nc, [&](int c) { return launch(cand[c]); }, st)]);
 }
 
 // wgrad: dw[n][k] = sum_b dy[b][n] x[b][k]; both operands MN-major with the batch as the reduction index.

@@ -71,7 +71,7 @@ class MSDNNet:
         self.tar = z(B, OUT_H, OUT_W, 1, **f32)         # resized target
         # conv outputs that feed a max-pool stay f32 and the pool records its routing (see a3d.h)
         self.c0 = z(B, 55, 74, 96, **f32)
-        self.p0 = z(B, 27, 37, 96, **bf)
+        self.p0 = z(B, 27, 37, 128, **bf)               # 96 channels + 32 zero: 128-byte pixels for conv2d_1
         self.i0 = torch.zeros(B, 27, 37, 96, dtype=torch.uint8, device=self.dev)
         self.c1 = z(B, 27, 37, 256, **f32)
         self.p1 = z(B, 13, 18, 256, **bf)
@@ -97,7 +97,7 @@ class MSDNNet:
         # ---- conv descriptors (src/models.py:211-223, 241-251)
         cd = ops.conv_desc
         self.d_c0 = cd(B, IN_H // 4, IN_W // 4, 64, 96, 3, 3, 1, "valid", impl=impl)   # 11x11x3 s4 as 3x3x64 s1
-        self.d_c1 = cd(B, 27, 37, 96, 256, 5, 5, 1, "same", impl=impl)
+        self.d_c1 = cd(B, 27, 37, 128, 256, 5, 5, 1, "same", impl=impl)
         self.d_c2 = cd(B, 13, 18, 256, 384, 3, 3, 1, "same", impl=impl)
         self.d_c3 = cd(B, 13, 18, 384, 384, 3, 3, 1, "same", impl=impl)
         self.d_c4 = cd(B, 13, 18, 384, 256, 3, 3, 2, "valid", impl=impl)
@@ -117,7 +117,7 @@ class MSDNNet:
             self.g_c2a, self.g_c2 = z(B, 13, 18, 384, **bf), z(B, 13, 18, 384, **bf)
             self.g_p1 = z(B, 13, 18, 256, **bf)
             self.g_c1 = z(B, 27, 37, 256, **bf)
-            self.g_p0 = z(B, 27, 37, 96, **bf)
+            self.g_p0 = z(B, 27, 37, 128, **bf)
             self.g_c0 = z(B, 55, 74, 96, **bf)
             self.g_f2a, self.g_f2 = z(B, 55, 74, 64, **bf), z(B, 55, 74, 64, **bf)
             self.g_cat = z(B, 55, 74, 64, **bf)

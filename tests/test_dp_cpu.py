@@ -106,7 +106,9 @@ def test_pack_unpack_roundtrip_and_masks():
     assert not bool(m[:, 2, :, 36:48].any())                              # filter row 11 (= 4*2+3) does not exist
     m = a.masks["fine/first/conv2d/kernel"].view(64, 5, 5, 16)
     assert int(m.sum()) == 63 * 9 * 9 * 3 and not bool(m[63].any())
-    assert "coarse/conv/conv2d_1/kernel" not in a.masks
+    assert "coarse/conv/conv2d_2/kernel" not in a.masks
+    m = a.masks["coarse/conv/conv2d_1/kernel"].view(256, 5, 5, 128)      # input channels stored 96 -> 128
+    assert int(m.sum()) == 256 * 5 * 5 * 96 and not bool(m[..., 96:].any())
 
 
 def test_bench_reference_arm_other_ranks_are_silent():

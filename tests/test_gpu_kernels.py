@@ -420,8 +420,8 @@ def test_conv_pool4_fwd_bwd(ctx, impl):
     ref = torch.relu(m + bias)
     assert rel_err(y, ref) < 1e-2
     # routing: identical wherever the winner is clear (f32 accumulation order differs in the last bits)
-    top2 = acc.topk(2, dim=3).values
-    clear = (top2[..., 0] - top2[..., 1]) > 1e-3
+    top2 = acc.topk(2, dim=3).values                # [N,P,Q,2,64]
+    clear = (top2[:, :, :, 0] - top2[:, :, :, 1]) > 1e-3
     assert bool((idx.long()[clear] == gi[clear]).all()) and int(idx.max()) <= 3
     # backward: dy routed to the arg-max group where the pooled output is positive
     dy = bf16_rand(N, d.P, d.Q, 64, seed=43)
