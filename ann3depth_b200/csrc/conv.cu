@@ -18,6 +18,14 @@ struct a3d_adam_args { float* w; float* m; float* v; uint16_t* wb; float lr_t, b
 int a3d_tc_dense_wgrad(a3d_ctx*, const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, int M, int N, int K,
                        cudaStream_t st, const a3d_adam_args* adam = nullptr);
 
+int a3d_simt_dense_wgrad_adam(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* w, float* m,
+                              float* v, uint16_t* wb, int M, int N, int K, float lr_t, float beta1, float beta2, float eps,
+                              float grad_scale, const float* lr_t_dev, cudaStream_t st);
+
+int a3d_mma_dense_wgrad_adam(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* w, float* m,
+                             float* v, uint16_t* wb, int M, int N, int K, float lr_t, float beta1, float beta2, float eps,
+                             float grad_scale, const float* lr_t_dev, cudaStream_t st);
+
 // tc_halo.cu
 struct HaloGeom { int Hp, Wp, Cp, need_copy; };
 size_t a3d_halo_ws_bytes(int N, int H, int W, int C, int ld, int K, int R, int S, int pt, int pl, int P, int Q, int flip);
@@ -441,6 +449,24 @@ extern "C" int a3d_dense_wgrad_adam(a3d_ctx* ctx, const uint16_t* x, int ldx, co
     int rc = a3d_colsum_bf16(ctx, dy, (size_t)M, N, lddy, db, st);
     if (rc) return rc;
   }
+  // Three implementations (A3D_FUSED_ADAM = mma | simt | tc): the optimizer-shaped streaming kernel that forms the
+  // gradient with warp-level mma.sync (default, batch <= 32), the same with the 32 FMAs per parameter on the CUDA
+  // cores, or the tcgen05 GEMM whose epilogue streams w/m/v through shared-memory-transposed coalesced accesses.
+  static int variant = -1;                   // 0 mma.sync (default), 1 CUDA cores, 2 tcgen05 epilogue
+  if (variant < 0) { const char* e = getenv("A3D_FUSED_ADAM"); variant = !e ? 0 : e[0] == 's' ? 1 : e[0] == 't' ? 2 : 0; }
+  if (variant == 0) {
+    int rc = a3d_mma_dense_wgrad_adam(ctx, x, ldx, dy, lddy, w, m, v, w_bf16, M, N, K, lr_t, beta1, beta2, eps,
+                                      grad_scale, lr_t_dev, st);
+    if (rc != A3D_ENOTSUP) return rc;
+  }
+  if (variant == 1) {
+    int rc = a3d_simt_dense_wgrad_adam(ctx, x, ldx, dy, lddy, w, m, v, w_bf16, M, N, K, lr_t, beta1, beta2, eps,
+                                       grad_scale, lr_t_dev, st);
+    if (rc != A3D_ENOTSUP) return rc;
+  }
+  A3D_REQUIRE(((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0 &&
+                  (!w_bf16 || (reinterpret_cast<uintptr_t>(w_bf16) & 7) == 0),
+              "dense wgrad+adam: w/m/v must be 16-byte aligned");
   a3d_adam_args a{w, m, v, w_bf16, lr_t, beta1, beta2, eps, grad_scale, lr_t_dev};
   return a3d_tc_dense_wgrad(ctx, x, ldx, dy, lddy, nullptr, M, N, K, st, &a);
 }

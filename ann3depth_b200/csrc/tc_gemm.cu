@@ -692,6 +692,10 @@ int a3d_tc_dense_wgrad(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t*
   // 104 KB so that two CTAs share an SM and one's epilogue hides the other's prologue (A3D_DWGRAD_BN overrides).
   static int bn_pref = -1;
   if (bn_pref < 0) { const char* e = getenv("A3D_DWGRAD_BN"); bn_pref = e ? atoi(e) : 128; }
+  if (adam) {
+    if (bn_pref >= 128 && K % 128 == 0) return launch_cfg<tc::Cfg<128, 128, true, true, 64, 3, true>>(ctx, tmA, tmB, p, 1, st);
+    return launch_cfg<tc::Cfg<64, 128, true, true, 64, 3, true>>(ctx, tmA, tmB, p, 1, st);
+  }
   if (bn_pref == 256 && K % 256 == 0) return launch_cfg<tc::Cfg<256, 128, true, true, 64>>(ctx, tmA, tmB, p, 1, st);
   if (bn_pref >= 128 && K % 128 == 0) return launch_cfg<tc::Cfg<128, 128, true, true, 64>>(ctx, tmA, tmB, p, 1, st);
   return launch_cfg<tc::Cfg<64, 128, true, true, 64>>(ctx, tmA, tmB, p, 1, st);

@@ -65,8 +65,10 @@ struct Params {
   const float* lr_t_dev;
 };
 
-template <int BN_, int KCB_, bool A_MN_, bool B_MN_, int B_BW_ = 64, int MIN_STAGES_ = 3>
+template <int BN_, int KCB_, bool A_MN_, bool B_MN_, int B_BW_ = 64, int MIN_STAGES_ = 3, bool ADAM_ = false>
 struct Cfg {
+  static constexpr bool ADAM = ADAM_;                     // compile the EPI_ADAM epilogue (24 float4 loads in flight:
+                                                          // 168 registers) only into the kernels that use it
   static constexpr int B_BW = B_BW_;                     // MN-major B: elements per block (64/32/16)
   static constexpr int B_BLK_BYTES = 64 * B_BW_ * 2;     // 64 K-rows x BW elements
   static constexpr int B_NBLK = BN_ / B_BW_;
@@ -300,6 +302,79 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       c_begin = NCH * 32;
     }
+    if constexpr (C::ADAM) {
+     if (p.epi == EPI_ADAM) {
+      // The accumulator is a weight-gradient tile.  Row-per-thread (the TMEM layout) is the wrong shape for streaming
+      // w/m/v, so each 32 x 32 chunk goes through this warp's swizzled shared-memory slab and is re-read with 8 lanes
+      // per row: every global access of the warp is four full 128-byte lines, and the 24 float4 loads of a chunk are
+      // all in flight before the first one is consumed.  The gradient itself never reaches HBM.
+      uint8_t* slab = smem + quarter * 8192;
+      const int row0 = m0 + quarter * 32;
+      const float lr_t = p.lr_t_dev ? __ldg(p.lr_t_dev) : p.lr_t;
+      const int rsub = lane >> 3, cq = lane & 7;
+      if (row0 < p.M) {
+#pragma unroll 1
+        for (int ch = 0; ch < C::BN / 32; ++ch) {
+          const int col0 = n0 + ch * 32;
+          if (col0 >= p.N) break;
+          {
+            uint32_t ra[16], rb[16];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ch * 32);
+            __syncwarp();                          // previous chunk's readers of the slab are done
+            ptx::tmem_ld_x16(taddr, ra);
+            ptx::tmem_ld_x16(taddr + 16, rb);
+            ptx::tmem_ld_wait();
+            const uint32_t srow = ptx::smem_u32(slab) + (uint32_t)lane * 128u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              ptx::st_shared_v4_b32(srow + (uint32_t)((j ^ (lane & 7)) << 4), ra[4 * j], ra[4 * j + 1], ra[4 * j + 2], ra[4 * j + 3]);
+              ptx::st_shared_v4_b32(srow + (uint32_t)(((j + 4) ^ (lane & 7)) << 4), rb[4 * j], rb[4 * j + 1], rb[4 * j + 2],
+                                    rb[4 * j + 3]);
+            }
+          }
+          __syncwarp();
+          const int col = col0 + cq * 4;
+          const bool col_ok = col + 4 <= p.N;
+          float4 W[8], Mo[8], V[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int row = row0 + it * 4 + rsub;
+            if (row < p.M && col_ok) {
+              const long long off = (long long)row * p.ldo + col;
+              W[it] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.out) + off);
+              Mo[it] = *reinterpret_cast<const float4*>(p.adam_m + off);
+              V[it] = *reinterpret_cast<const float4*>(p.adam_v + off);
+            }
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rsub;
+            const int row = row0 + rr;
+            if (row < p.M && col_ok) {
+              const float4 G = ptx::ld_shared_v4(ptx::smem_u32(slab) + (uint32_t)rr * 128u + (uint32_t)((cq ^ (rr & 7)) << 4));
+              const float g[4] = {G.x, G.y, G.z, G.w};
+              float* pw = &W[it].x; float* pm = &Mo[it].x; float* pv = &V[it].x;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float gk = g[j] * p.grad_scale;
+                pm[j] = p.beta1 * pm[j] + (1.f - p.beta1) * gk;
+                pv[j] = p.beta2 * pv[j] + (1.f - p.beta2) * gk * gk;
+                pw[j] = pw[j] - lr_t * pm[j] / (sqrtf(pv[j]) + p.eps);
+              }
+              const long long off = (long long)row * p.ldo + col;
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = W[it];
+              *reinterpret_cast<float4*>(p.adam_m + off) = Mo[it];
+              *reinterpret_cast<float4*>(p.adam_v + off) = V[it];
+              if (p.adam_wb)
+                *reinterpret_cast<uint2*>(p.adam_wb + off) =
+                    make_uint2(pack_bf16x2(W[it].x, W[it].y), pack_bf16x2(W[it].z, W[it].w));
+            }
+          }
+        }
+      }
+      c_begin = C::BN;
+     }
+    }
     if (p.epi == EPI_TMA_BF16) {
       // as above with 64 bf16 columns (= 128 bytes) per slab row; a tail of BN % 64 columns takes the register path
       uint8_t* slab0 = smem + quarter * 8192;
@@ -421,58 +496,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
       if (p.epi == EPI_ADAM) {
-        if (row_ok) {
-          const float lr_t = p.lr_t_dev ? __ldg(p.lr_t_dev) : p.lr_t;
-          const long long off = (long long)row * p.ldo + col0;
-          float* pw = reinterpret_cast<float*>(p.out) + off;
-          float* pm = p.adam_m + off;
-          float* pv = p.adam_v + off;
-          uint16_t* pb = p.adam_wb ? p.adam_wb + off : nullptr;
-          const bool vec = (col0 + 16 <= p.N) && ((reinterpret_cast<uintptr_t>(pw) & 15) == 0);
-          float w[16], m[16], vv[16];
-          if (vec) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float4 a = reinterpret_cast<const float4*>(pw)[j], b = reinterpret_cast<const float4*>(pm)[j],
-                     c = reinterpret_cast<const float4*>(pv)[j];
-              w[4 * j] = a.x; w[4 * j + 1] = a.y; w[4 * j + 2] = a.z; w[4 * j + 3] = a.w;
-              m[4 * j] = b.x; m[4 * j + 1] = b.y; m[4 * j + 2] = b.z; m[4 * j + 3] = b.w;
-              vv[4 * j] = c.x; vv[4 * j + 1] = c.y; vv[4 * j + 2] = c.z; vv[4 * j + 3] = c.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (col0 + j < p.N) { w[j] = pw[j]; m[j] = pm[j]; vv[j] = pv[j]; }
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float g = v[j] * p.grad_scale;
-            m[j] = p.beta1 * m[j] + (1.f - p.beta1) * g;
-            vv[j] = p.beta2 * vv[j] + (1.f - p.beta2) * g * g;
-            w[j] = w[j] - lr_t * m[j] / (sqrtf(vv[j]) + p.eps);
-          }
-          if (vec) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              reinterpret_cast<float4*>(pw)[j] = make_float4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-              reinterpret_cast<float4*>(pm)[j] = make_float4(m[4 * j], m[4 * j + 1], m[4 * j + 2], m[4 * j + 3]);
-              reinterpret_cast<float4*>(pv)[j] = make_float4(vv[4 * j], vv[4 * j + 1], vv[4 * j + 2], vv[4 * j + 3]);
-            }
-            if (pb) {
-              reinterpret_cast<uint4*>(pb)[0] = make_uint4(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]),
-                                                           pack_bf16x2(w[4], w[5]), pack_bf16x2(w[6], w[7]));
-              reinterpret_cast<uint4*>(pb)[1] = make_uint4(pack_bf16x2(w[8], w[9]), pack_bf16x2(w[10], w[11]),
-                                                           pack_bf16x2(w[12], w[13]), pack_bf16x2(w[14], w[15]));
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (col0 + j < p.N) {
-                pw[j] = w[j]; pm[j] = m[j]; pv[j] = vv[j];
-                if (pb) pb[j] = f32_to_bf16_bits(w[j]);
-              }
-          }
-        }
+        // handled above (coalesced pass through shared memory)
       } else if (p.epi == EPI_COL_F32) {
         float* o = reinterpret_cast<float*>(p.out);
         if (row_ok) {

@@ -7,6 +7,8 @@ stream; PyTorch only owns the buffers.  The whole step is captured in a CUDA gra
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib as L
@@ -41,12 +43,15 @@ class MSDNNet:
 
     def __init__(self, ctx: ops.Context, batch: int, in_hw=(480, 640), depth_hw=(55, 73), train=True,
                  beta2=ADAM_BETA2_REFERENCE, impl=L.IMPL_AUTO, dropout_seed=2, comm=None, grad_dtype=torch.float32,
-                 overlap=True, fuse_dense_adam=False):
+                 overlap=True, fuse_dense_adam=True):
         self.ctx, self.B, self.train, self.beta2, self.impl = ctx, batch, train, beta2, impl
         self.overlap = overlap                # phase-1 step on several streams (see _enqueue_phase1_overlapped)
-        # single GPU option: TF-Adam inside the dense wgrad epilogue (a3d_dense_wgrad_adam).  Correct, and it saves
-        # 8 B/param of HBM traffic, but measured SLOWER (2.67 vs 1.89 ms/step): four epilogue warps per CTA do not
-        # keep enough loads in flight to stream w/m/v at HBM rate.  Off by default until the epilogue is widened.
+        # single GPU: the dense weight gradients (32 FMAs per parameter at batch 32) are recomputed on the CUDA cores
+        # inside the HBM-bound TF-Adam pass (a3d_dense_wgrad_adam), so the 67 M-element f32 gradient is never written
+        # or re-read: 26 instead of 38 bytes per dense parameter and step.  Data parallel runs need the gradient in
+        # memory for the reduce-scatter and keep the separate kernels (dp.py shards the optimizer instead).
+        if os.environ.get("A3D_FUSE_DENSE_ADAM"):          # A/B measurements
+            fuse_dense_adam = os.environ["A3D_FUSE_DENSE_ADAM"] != "0"
         self.fuse_dense_adam = fuse_dense_adam
         self._s_fine = self._s_wgrad = self._s_cwgrad = None
         self.dev = torch.device(f"cuda:{ctx.device}")
@@ -197,21 +202,43 @@ class MSDNNet:
                      dout_bf16=self.g_fine if self.train else None)
 
     # ------------------------------------------------------------------ backward
-    def backward_coarse(self):
-        """d loss_coarse / d coarse variables (compute_gradients of src/models.py:319-324)."""
+    def _dense_wgrad_adam(self, layer, x, dy):
+        """Weight gradient + TF-Adam of one dense kernel in a single pass (the gradient never reaches HBM); the bias
+        gradient is produced as usual and gets its own (tiny) Adam launch.  Must run AFTER the layer's dgrad, the
+        last reader of the weights it overwrites."""
+        c, a, g = self.ctx, self.arena, "CoarseDense"
+        kn, bn_ = "coarse/dense/dense_" + layer + "/kernel", "coarse/dense/dense_" + layer + "/bias"
+        c.dense_wgrad_adam(x, dy, self.gw(bn_), a.view(a.w, kn), a.view(a.m, kn), a.view(a.v, kn), a.view(a.wb, kn),
+                           ADAM_LR[g], ADAM_BETA1, self.beta2, ADAM_EPS, max(self.adam_t[g], 1), 1.0,
+                           lr_t_dev=self.lr_dev[g])
+        s = a.specs[bn_]
+        sl = slice(s.offset, s.offset + s.size)
+        c.adam_tf(a.w[sl], a.g[sl], a.m[sl], a.v[sl], a.wb[sl], ADAM_LR[g], ADAM_BETA1, self.beta2, ADAM_EPS,
+                  max(self.adam_t[g], 1), 1.0, lr_t_dev=self.lr_dev[g])
+
+    def backward_coarse(self, fused_dense_adam=False):
+        """d loss_coarse / d coarse variables (compute_gradients of src/models.py:319-324).  With
+        `fused_dense_adam` the two dense kernels are updated on the spot (see _dense_wgrad_adam) and the caller
+        applies Adam to the CoarseConv group only."""
         c, B, K = self.ctx, self.B, "/kernel"
         hook = self.comm.bucket_ready if self.comm else (lambda *_: None)
         n = "coarse/dense/dense_"
-        c.dense_wgrad(self.d0, self.g_coarse, dw=self.gw(n + "1" + K), db=self.gw(n + "1/bias"), impl=self.impl)
-        hook(self, "dense_1")
+        if not fused_dense_adam:
+            c.dense_wgrad(self.d0, self.g_coarse, dw=self.gw(n + "1" + K), db=self.gw(n + "1/bias"), impl=self.impl)
+            hook(self, "dense_1")
         c.dense_dgrad(self.g_coarse, self.w(n + "1" + K), out=self.g_d0a, impl=self.impl)
         # dropout grad (mask * 1/(1-rate)) and relu grad (d0 > 0) in one pass
         c.dense_epilogue_bwd(self.g_d0a, self.d0, self.keep_mask, 0.5, L.EPI_RELU, out=self.g_d0)
-        c.dense_wgrad(self.c4.view(B, 12288), self.g_d0, dw=self.gw(n + "0" + K), db=self.gw(n + "0/bias"),
-                      impl=self.impl)
-        hook(self, "dense_0")
+        if fused_dense_adam:
+            self._dense_wgrad_adam("1", self.d0, self.g_coarse)
+        else:
+            c.dense_wgrad(self.c4.view(B, 12288), self.g_d0, dw=self.gw(n + "0" + K), db=self.gw(n + "0/bias"),
+                          impl=self.impl)
+            hook(self, "dense_0")
         c.dense_dgrad(self.g_d0, self.w(n + "0" + K), out=self.g_c4a.view(B, 12288), impl=self.impl)
         c.relu_bwd(self.c4, self.g_c4a, out=self.g_c4)
+        if fused_dense_adam:
+            self._dense_wgrad_adam("0", self.c4.view(B, 12288), self.g_d0)
         n = "coarse/conv/conv2d_"
         c.conv2d_wgrad(self.d_c4, self.c3, self.g_c4, dw=self.gw(n + "4" + K), db=self.gw(n + "4/bias"))
         c.conv2d_dgrad(self.d_c4, self.g_c4, self.w(n + "4" + K), out=self.g_c3, relu_src=self.c3)
@@ -358,17 +385,8 @@ class MSDNNet:
         fused = self.fuse_dense_adam and not self.comm
         a = self.arena
 
-        def dense_wgrad_adam(layer, x, dy):
-            # TF-Adam applied by the wgrad epilogue (the gradient never reaches HBM); the bias keeps the plain path
-            g = "CoarseDense"
-            kn, bn_ = nd + layer + K, nd + layer + "/bias"
-            c.dense_wgrad_adam(x, dy, self.gw(bn_), a.view(a.w, kn), a.view(a.m, kn), a.view(a.v, kn), a.view(a.wb, kn),
-                               ADAM_LR[g], ADAM_BETA1, self.beta2, ADAM_EPS, max(self.adam_t[g], 1), 1.0,
-                               lr_t_dev=self.lr_dev[g])
-            s = a.specs[bn_]
-            sl = slice(s.offset, s.offset + s.size)
-            c.adam_tf(a.w[sl], a.g[sl], a.m[sl], a.v[sl], a.wb[sl], ADAM_LR[g], ADAM_BETA1, self.beta2, ADAM_EPS,
-                      max(self.adam_t[g], 1), 1.0, lr_t_dev=self.lr_dev[g])
+        dense_wgrad_adam = self._dense_wgrad_adam
+        nd = "coarse/dense/dense_"
 
         e_loss = e_g
         c.dense_dgrad(self.g_coarse, self.w(nd + "1" + K), out=self.g_d0a, impl=self.impl)
@@ -432,8 +450,9 @@ class MSDNNet:
             return self._enqueue_phase1_overlapped()
         self.forward()
         if phase == 1:
-            self.backward_coarse()
-            groups = ("CoarseDense", "CoarseConv")
+            fused = self.fuse_dense_adam and not self.comm
+            self.backward_coarse(fused_dense_adam=fused)
+            groups = ("CoarseConv",) if fused else ("CoarseDense", "CoarseConv")
         elif phase == 2:
             self.backward_fine()
             groups = ("FineA", "FineB")

@@ -163,8 +163,8 @@ def per_op_profile(op, torch, reps=3):
                     detail = f"N{d.N} {d.H}x{d.W}x{d.C}->{d.P}x{d.Q}x{d.K} k{d.R}x{d.S} s{d.stride_h}"
                 elif name == "a3d_adam_tf":
                     detail = f"n={int(a[6])}"
-                elif name in ("a3d_dense_fwd", "a3d_dense_dgrad", "a3d_dense_wgrad"):
-                    i0 = {"a3d_dense_fwd": 10, "a3d_dense_dgrad": 6, "a3d_dense_wgrad": 7}[name]
+                elif name in ("a3d_dense_fwd", "a3d_dense_dgrad", "a3d_dense_wgrad", "a3d_dense_wgrad_adam"):
+                    i0 = {"a3d_dense_fwd": 10, "a3d_dense_dgrad": 6, "a3d_dense_wgrad": 7, "a3d_dense_wgrad_adam": 10}[name]
                     detail = "MNK=" + "x".join(str(int(x)) for x in a[i0:i0 + 3])
                 records.append((name, detail, e0, e1))
                 return rc
@@ -341,10 +341,14 @@ def gpu_arm(args, rank, world, local_rank):
                     "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": None,
                     "peak_kind": pk_kind + " burst", "share_of_step": top["ms"] / sum(r["ms"] for r in rows)}
         else:
-            # algorithmic bytes of the HBM-bound kernels: TF-Adam = 30 B/param
+            # algorithmic bytes of the HBM-bound kernels: TF-Adam = 30 B/param (read w,g,m,v;
+            # write w,m,v + bf16 mirror); fused dense wgrad + TF-Adam = 26 B/param (no gradient in memory)
             ach = None
             if top["op"] == "a3d_adam_tf" and top["detail"].startswith("n="):
                 ach = 30.0 * int(top["detail"][2:]) / (top["ms"] * 1e-3) / 1e9
+            elif top["op"] == "a3d_dense_wgrad_adam" and top["detail"].startswith("MNK="):
+                mm, nn, kk = (int(x) for x in top["detail"][4:].split("x"))
+                ach = (26.0 * nn * kk + 2.0 * mm * (nn + kk)) / (top["ms"] * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": f'{top["op"]} {top["detail"]}', "achieved": ach, "peak": pk["hbm_gbs"],
                     "unit": "GB/s", "frac": ach / pk["hbm_gbs"] if ach else None, "traffic": None, "peak_kind": pk_kind,
                     "share_of_step": top["ms"] / sum(r["ms"] for r in rows)}
@@ -358,6 +362,7 @@ def gpu_arm(args, rank, world, local_rank):
         roof["conv_tensor_frac_of_burst"] = roof["conv_tensor_tflops"] / pk["bf16_tflops"] if tms else None
         # conv + FC aggregate (the dense layers at batch 32 are weight-streaming, i.e. HBM-bound, kernels)
         dense_ops = [r for r in rows if r["op"] in ("a3d_dense_fwd", "a3d_dense_dgrad", "a3d_dense_wgrad")]
+        # (the fused wgrad + Adam pass runs its 32 FMAs per parameter on the CUDA cores: optimizer, not tensor, time)
         dfl = 0.0
         for r in dense_ops:
             try:
