@@ -1067,3 +1067,115 @@ int a3d_mma_dense_wgrad_adam(a3d_ctx* ctx, const uint16_t* x, int ldx, const uin
   A3D_LAUNCH_OK(ctx);
   return 0;
 }
+
+// ------------------------------------------------------------------------------------ data-parallel dense update
+// Data parallelism for the dense layers WITHOUT a gradient all-reduce: the weight gradient of a dense layer is the
+// rank-B outer product dy^T x, so instead of reducing N*K gradients (134 MB in bf16 for MSDN) the ranks all-gather
+// the two small activation matrices (x_all [n*B, K], dy_all [n*B, N]: ~1 MB per rank) and every rank updates ITS OWN
+// rows [row_lo, row_hi) of the weight matrix from the gathered batch, gradient formed by mma.sync and consumed by
+// TF-Adam in the same pass (grad_scale = 1/n).  The updated bf16 rows are then all-gathered (dp.py).
+// Same warp tiling as dense_wgrad_adam_mma_kernel<2,...>; the batch loop runs over M/16 MMA k-steps and reloads the
+// B fragments from L1/L2 (x_all is small and shared by every warp of the column strip).
+__global__ void __launch_bounds__(256, 3)
+dense_wgrad_adam_mma_rows_kernel(const uint16_t* __restrict__ x, int ldx, const uint16_t* __restrict__ dy, int lddy,
+                                 float* __restrict__ w, float* __restrict__ m, float* __restrict__ v,
+                                 uint16_t* __restrict__ wb, int M, int K, int row_lo, int row_hi, float lr_t, float b1,
+                                 float b2, float eps, float gs, const float* __restrict__ lr_dev) {
+  if (lr_dev) lr_t = __ldg(lr_dev);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int kc0 = blockIdx.x * 256 + warp * 32;
+  int colj[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) colj[j] = kc0 + 16 * (j >> 1) + 4 * (g >> 1) + 2 * (j & 1) + (g & 1);
+  const int ksteps = (M + 15) >> 4;
+  for (int n0 = row_lo + blockIdx.y * 16; n0 < row_hi; n0 += gridDim.y * 16) {
+    const int r0 = n0 + g, r1 = n0 + g + 8;
+    float acc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll 2
+    for (int kb = 0; kb < ksteps; ++kb) {
+      uint32_t afrag[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = (i & 1) ? r1 : r0;
+        const int b0 = kb * 16 + (i >> 1) * 8 + 2 * t;
+        const uint32_t lo = (row < row_hi && b0 < M) ? __ldg(dy + (size_t)b0 * lddy + row) : 0u;
+        const uint32_t hi = (row < row_hi && b0 + 1 < M) ? __ldg(dy + (size_t)(b0 + 1) * lddy + row) : 0u;
+        afrag[i] = lo | (hi << 16);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t bfrag[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int b0 = kb * 16 + h * 8 + 2 * t;
+          const uint32_t lo = b0 < M ? __ldg(x + (size_t)b0 * ldx + colj[j]) : 0u;
+          const uint32_t hi = b0 + 1 < M ? __ldg(x + (size_t)(b0 + 1) * ldx + colj[j]) : 0u;
+          bfrag[h] = lo | (hi << 16);
+        }
+        mma_bf16_16816(acc[j], afrag, bfrag);
+      }
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int row = half ? r1 : r0;
+      if (row < row_hi) {
+        float4 W[2], Mo[2], V[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const size_t off = (size_t)row * K + kc0 + 16 * q + 4 * t;
+          W[q] = *reinterpret_cast<const float4*>(w + off);
+          Mo[q] = *reinterpret_cast<const float4*>(m + off);
+          V[q] = *reinterpret_cast<const float4*>(v + off);
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const float gr[4] = {acc[2 * q][half * 2], acc[2 * q][half * 2 + 1], acc[2 * q + 1][half * 2],
+                               acc[2 * q + 1][half * 2 + 1]};
+          float* pw = &W[q].x; float* pm = &Mo[q].x; float* pv = &V[q].x;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float gk = gr[j] * gs;
+            pm[j] = b1 * pm[j] + (1.f - b1) * gk;
+            pv[j] = b2 * pv[j] + (1.f - b2) * gk * gk;
+            pw[j] = pw[j] - lr_t * pm[j] / (sqrtf(pv[j]) + eps);
+          }
+          const size_t off = (size_t)row * K + kc0 + 16 * q + 4 * t;
+          *reinterpret_cast<float4*>(w + off) = W[q];
+          *reinterpret_cast<float4*>(m + off) = Mo[q];
+          *reinterpret_cast<float4*>(v + off) = V[q];
+          if (wb) *reinterpret_cast<uint2*>(wb + off) = make_uint2(pack_bf16x2(W[q].x, W[q].y), pack_bf16x2(W[q].z, W[q].w));
+        }
+      }
+    }
+  }
+}
+
+extern "C" int a3d_dense_wgrad_adam_rows(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* w,
+                                         float* m, float* v, uint16_t* w_bf16, int M, int N, int K, int row_lo, int row_hi,
+                                         float lr_t, float beta1, float beta2, float eps, float grad_scale,
+                                         const float* lr_t_dev, void* stream) {
+  A3D_REQUIRE(ctx && x && dy && w && m && v && M > 0 && N > 0 && K > 0 && lddy >= N && ldx >= K,
+              "dense wgrad+adam rows: bad argument");
+  A3D_REQUIRE(K % 256 == 0 && aligned16(w) && aligned16(m) && aligned16(v) &&
+                  (!w_bf16 || (reinterpret_cast<uintptr_t>(w_bf16) & 7) == 0),
+              "dense wgrad+adam rows: needs K %% 256 == 0 and 16-byte aligned w/m/v");
+  if (row_hi > N) row_hi = N;
+  if (row_lo >= row_hi) return 0;
+  const int kblocks = K / 256;
+  int gy = 3 * ctx->sm_count / kblocks;
+  if (gy < 1) gy = 1;
+  if (gy > ceil_div(row_hi - row_lo, 16)) gy = ceil_div(row_hi - row_lo, 16);
+  dense_wgrad_adam_mma_rows_kernel<<<dim3(kblocks, gy), 256, 0, as_stream(stream)>>>(
+      x, ldx, dy, lddy, w, m, v, w_bf16, M, K, row_lo, row_hi, lr_t, beta1, beta2, eps, grad_scale, lr_t_dev);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
+// BiasAddGrad alone: db[c] = sum_rows dy[row][c]  (dy bf16 [rows][ld])
+extern "C" int a3d_bias_grad_bf16(a3d_ctx* ctx, const uint16_t* dy, size_t rows, int C, int ld, float* db, void* stream) {
+  A3D_REQUIRE(ctx && dy && db && rows > 0 && C > 0 && ld >= C, "bias grad: bad argument");
+  return a3d_colsum_bf16(ctx, dy, rows, C, ld, db, as_stream(stream));
+}

@@ -29,6 +29,12 @@ class DataParallel:
             return a.group_range(name)
         if name == "coarse_conv":
             return a.group_range("CoarseConv")
+        if name in ("coarse_conv_early", "coarse_conv_late"):
+            # the conv stack in two buckets (arena order = backward order conv2d_4 .. conv2d_0): the early one is
+            # exchanged under the remaining backward pass, only conv2d_1/conv2d_0 are left for the end of the step
+            lo, hi = a.group_range("CoarseConv")
+            cut = a.specs["coarse/conv/conv2d_1/kernel"].offset
+            return (lo, cut) if name == "coarse_conv_early" else (cut, hi)
         if name == "fine":
             lo_a, hi_a = a.group_range("FineA")
             lo_b, hi_b = a.group_range("FineB")
@@ -94,6 +100,59 @@ class DataParallel:
         self.bytes_per_step += n * 2 * 2
         self._sharded = getattr(self, "_sharded", set()) | {name}
 
+    def can_gather_dense(self, net, kernel_name, batch):
+        """The activation-gather update needs equal 16-row-aligned row slices and a gathered batch <= 256."""
+        s = net.arena.specs[kernel_name]
+        rows = s.packed_shape[0]
+        return rows % (self.world * 16) == 0 and batch * self.world <= 256 and s.packed_shape[1] % 256 == 0
+
+    def dense_gather_adam(self, net, kernel_name, bias_name, x, dy, group, lr, beta1, eps, after=None):
+        """Data-parallel step of ONE dense layer without a gradient all-reduce (a3d_dense_wgrad_adam_rows):
+             all-gather x [B,K] and dy [B,N] (MBs)  |  this rank updates its row slice of the kernel from the gathered
+             batch, gradient and TF-Adam in one pass (grad_scale 1/n)  |  every rank updates the (replicated) bias
+             from the gathered dy  |  all-gather of the updated bf16 kernel rows.
+        NVLink traffic per rank: the bf16 weights once (no reduce-scatter of gradients); HBM traffic: 26 B/param on
+        1/n of the kernel.  `after`: event of the last reader of the weights (the layer's dgrad)."""
+        a, c, n = net.arena, self.ctx, self.world
+        ks, bs = a.specs[kernel_name], a.specs[bias_name]
+        rows, K = ks.packed_shape
+        N = ks.tf_shape[1]
+        B = x.shape[0]
+        key = ("gather", kernel_name)
+        bufs = getattr(self, "_gbufs", None)
+        if bufs is None:
+            bufs = self._gbufs = {}
+        if key not in bufs:
+            bufs[key] = (torch.zeros(n * B, K, dtype=torch.bfloat16, device=x.device),
+                         torch.zeros(n * B, dy.shape[1], dtype=torch.bfloat16, device=x.device))
+        xg, dyg = bufs[key]
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            xg[self.rank * B:(self.rank + 1) * B].copy_(x)
+            dyg[self.rank * B:(self.rank + 1) * B].copy_(dy)
+            ops.allgather(c, xg.view(-1), B * K)
+            ops.allgather(c, dyg.view(-1), B * dy.shape[1])
+            if after is not None:
+                self.stream.wait_event(after)
+            t = max(net.adam_t[group], 1)
+            r = rows // n
+            c.dense_wgrad_adam_rows(xg, dyg, a.view(a.w, kernel_name), a.view(a.m, kernel_name), a.view(a.v, kernel_name),
+                                    a.view(a.wb, kernel_name), self.rank * r, (self.rank + 1) * r, lr, beta1, net.beta2,
+                                    eps, t, 1.0 / n, lr_t_dev=net.lr_dev[group], N=N)
+            # bias: replicated update from the gathered dy
+            sl = slice(bs.offset, bs.offset + bs.size)
+            c.bias_grad_bf16(dyg, N, a.g[bs.offset:bs.offset + N])
+            c.adam_tf(a.w[sl], a.g[sl], a.m[sl], a.v[sl], a.wb[sl], lr, beta1, net.beta2, eps, t, 1.0 / n,
+                      lr_t_dev=net.lr_dev[group])
+            ops.allgather(c, a.view(a.wb, kernel_name).view(-1), r * K)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        self._done.append(done)
+        self.bytes_per_step += (n * B * (K + dy.shape[1]) + rows * K) * 2
+        self._row_sharded = getattr(self, "_row_sharded", set()) | {kernel_name}
+
     def gather_master(self, net):
         """All-gather the f32 master weights and Adam slots of every sharded bucket (checkpoint / export)."""
         a = net.arena
@@ -102,6 +161,10 @@ class DataParallel:
             chunk = (hi - lo) // self.world
             for buf in (a.w, a.m, a.v):
                 ops.allgather(self.ctx, buf[lo:hi], chunk)
+        for name in sorted(getattr(self, "_row_sharded", ())):
+            rows, K = a.specs[name].packed_shape
+            for buf in (a.w, a.m, a.v):
+                ops.allgather(self.ctx, a.view(buf, name).view(-1), rows // self.world * K)
 
     def wait_all(self, net):
         cur = torch.cuda.current_stream()

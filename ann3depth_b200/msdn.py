@@ -131,14 +131,21 @@ class MSDNNet:
         self._graphs = {}
 
     # ------------------------------------------------------------------ parameters
+    def _real_rows(self, buf, name):
+        """Arena view of a variable; dense kernels whose output rows are padded (dense_1: 4070 -> 4096) are cut to
+        their real rows (a contiguous prefix), which is what the GEMM entry points take as N."""
+        s = self.arena.specs[name]
+        t = self.arena.view(buf, name)
+        return t[:s.tf_shape[1]] if s.kind == "dense_kernel" else t
+
     def w(self, name):
-        return self.arena.view(self.arena.wb, name)
+        return self._real_rows(self.arena.wb, name)
 
     def bias(self, name):
         return self.arena.view(self.arena.w, name + "/bias")
 
     def gw(self, name):
-        return self.arena.view(self.arena.g, name)
+        return self._real_rows(self.arena.g, name)
 
     def load_params(self, tf_params):
         self.arena.load_tf(tf_params)
@@ -208,7 +215,8 @@ class MSDNNet:
         last reader of the weights it overwrites."""
         c, a, g = self.ctx, self.arena, "CoarseDense"
         kn, bn_ = "coarse/dense/dense_" + layer + "/kernel", "coarse/dense/dense_" + layer + "/bias"
-        c.dense_wgrad_adam(x, dy, self.gw(bn_), a.view(a.w, kn), a.view(a.m, kn), a.view(a.v, kn), a.view(a.wb, kn),
+        rr = self._real_rows
+        c.dense_wgrad_adam(x, dy, self.gw(bn_), rr(a.w, kn), rr(a.m, kn), rr(a.v, kn), rr(a.wb, kn),
                            ADAM_LR[g], ADAM_BETA1, self.beta2, ADAM_EPS, max(self.adam_t[g], 1), 1.0,
                            lr_t_dev=self.lr_dev[g])
         s = a.specs[bn_]
@@ -392,7 +400,17 @@ class MSDNNet:
         c.dense_dgrad(self.g_coarse, self.w(nd + "1" + K), out=self.g_d0a, impl=self.impl)
         c.dense_epilogue_bwd(self.g_d0a, self.d0, self.keep_mask, 0.5, L.EPI_RELU, out=self.g_d0)
         e_g = mark(s0)
-        if not fused:
+        # data parallel, dense layers: exchange activations instead of gradients (dp.dense_gather_adam)
+        gather = bool(self.comm) and all(self.comm.can_gather_dense(self, nd + l + K, B) for l in "01") and \
+            os.environ.get("A3D_DP_GATHER", "1") != "0"
+
+        def dp_dense(layer, x, dy, after):
+            g = "CoarseDense"
+            self.comm.dense_gather_adam(self, nd + layer + K, nd + layer + "/bias", x, dy, g, ADAM_LR[g], ADAM_BETA1,
+                                        ADAM_EPS, after)
+        if gather:
+            on_wgrad(e_loss, lambda: dp_dense("1", self.d0, self.g_coarse, e_g))
+        elif not fused:
             # the bucket's Adam overwrites dense_1's weights: it waits for e_g (dense_1's dgrad has read them)
             on_wgrad(e_loss, lambda: (c.dense_wgrad(self.d0, self.g_coarse, dw=self.gw(nd + "1" + K),
                                                     db=self.gw(nd + "1/bias"), impl=self.impl),
@@ -403,7 +421,9 @@ class MSDNNet:
         c.dense_dgrad(self.g_d0, self.w(nd + "0" + K), out=self.g_c4a.view(B, 12288), impl=self.impl)
         c.relu_bwd(self.c4, self.g_c4a, out=self.g_c4)
         e_g = mark(s0)
-        if not fused:
+        if gather:
+            on_wgrad(e_d0, lambda: dp_dense("0", self.c4.view(B, 12288), self.g_d0, e_g))
+        elif not fused:
             on_wgrad(e_d0, lambda: (c.dense_wgrad(self.c4.view(B, 12288), self.g_d0, dw=self.gw(nd + "0" + K),
                                                   db=self.gw(nd + "0/bias"), impl=self.impl),
                                     self.comm and dp_update("dense_0", "CoarseDense", e_g)))
@@ -423,7 +443,10 @@ class MSDNNet:
         c.conv2d_dgrad(self.d_c2, self.g_c2, self.w(n + "2" + K), out=self.g_p1)
         c.maxpool2x2_idx_bwd(self.i1, self.g_p1, (B, 27, 37, 256), out=self.g_c1)
         e_g = mark(s0)
-        on_wgrad(e_g, lambda: c.conv2d_wgrad(self.d_c1, self.p0, self.g_c1, dw=self.gw(n + "1" + K), db=self.gw(n + "1/bias")), s3)
+        # DP: conv2d_4..2 are complete (their wgrads precede on s3, their dgrads -- the last readers of the weights the
+        # update overwrites -- precede e_g): exchange them now, under the rest of the backward pass
+        on_wgrad(e_g, lambda: (self.comm and dp_update("coarse_conv_early", "CoarseConv"),
+                               c.conv2d_wgrad(self.d_c1, self.p0, self.g_c1, dw=self.gw(n + "1" + K), db=self.gw(n + "1/bias"))), s3)
         c.conv2d_dgrad(self.d_c1, self.g_c1, self.w(n + "1" + K), out=self.g_p0)
         c.maxpool2x2_idx_bwd(self.i0, self.g_p0, (B, 55, 74, 96), out=self.g_c0)
         e_g = mark(s0)
@@ -432,7 +455,7 @@ class MSDNNet:
             c.conv2d_wgrad(self.d_c0, self.img4, self.g_c0, dw=self.gw(n + "0" + K), db=self.gw(n + "0/bias"))
             self._mask_padding("coarse/conv/conv2d_0/kernel")
             if self.comm:
-                dp_update("coarse_conv", "CoarseConv")
+                dp_update("coarse_conv_late", "CoarseConv")
                 self.comm.wait_all(self)
             else:
                 self.apply_adam(("CoarseConv",))

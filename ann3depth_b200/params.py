@@ -54,7 +54,12 @@ def pack(spec: VarSpec, t: torch.Tensor) -> torch.Tensor:
     if spec.kind == "conv_kernel_s2d4":
         return pack_s2d(t, 4, spec.packed_shape)
     if spec.kind == "dense_kernel":
-        return t.t().contiguous()
+        n_in, n_out = spec.tf_shape
+        if tuple(spec.packed_shape) == (n_out, n_in):
+            return t.t().contiguous()
+        out = torch.zeros(spec.packed_shape, dtype=t.dtype)           # output rows padded (dense_1: 4070 -> 4096)
+        out[:n_out, :n_in] = t.t()
+        return out
     out = torch.zeros(spec.packed_shape, dtype=t.dtype)
     out[:t.numel()] = t
     return out
@@ -127,7 +132,8 @@ def unpack(spec: VarSpec, p: torch.Tensor) -> torch.Tensor:
     if spec.kind == "conv_kernel_s2d4":
         return unpack_s2d(p, 4, spec.tf_shape)
     if spec.kind == "dense_kernel":
-        return p.t().contiguous()
+        n_in, n_out = spec.tf_shape
+        return p[:n_out, :n_in].t().contiguous()
     return p[:spec.tf_shape[0]].contiguous()
 
 
@@ -143,8 +149,8 @@ def _conv(name, tf_shape, packed, group):
             VarSpec(name + "/bias", (tf_shape[-1],), (packed[0],), "bias", group)]
 
 
-def _dense(name, n_in, n_out, group):
-    return [VarSpec(name + "/kernel", (n_in, n_out), (n_out, n_in), "dense_kernel", group),
+def _dense(name, n_in, n_out, group, rows=None):
+    return [VarSpec(name + "/kernel", (n_in, n_out), (rows or n_out, n_in), "dense_kernel", group),
             VarSpec(name + "/bias", (n_out,), (n_out,), "bias", group)]
 
 
@@ -152,7 +158,8 @@ def msdn_specs():
     """MSDN variables (src/models.py:208-251) in arena order."""
     v = []
     # CoarseDense (lr 0.1, src/models.py:322-324), backward order
-    v += _dense("coarse/dense/dense_1", 4096, 4070, "CoarseDense")
+    # output rows stored 4070 -> 4096 (zero rows): the kernel splits into equal row slices for 2/4/8 ranks (dp.py)
+    v += _dense("coarse/dense/dense_1", 4096, 4070, "CoarseDense", rows=4096)
     v += _dense("coarse/dense/dense_0", 12288, 4096, "CoarseDense")
     # CoarseConv (lr 1e-3, :319-321)
     v += _conv("coarse/conv/conv2d_4", (3, 3, 384, 256), (256, 3, 3, 384), "CoarseConv")

@@ -111,6 +111,56 @@ def test_pack_unpack_roundtrip_and_masks():
     assert int(m.sum()) == 256 * 5 * 5 * 96 and not bool(m[..., 96:].any())
 
 
+def _gather_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    B, K, N = 4, 64, 48
+    g = torch.Generator().manual_seed(10 + rank)
+    x, dy = torch.randn(B, K, generator=g), torch.randn(B, N, generator=g)
+    # activation-gather protocol of dp.dense_gather_adam: gather the small matrices, update own rows only
+    xs, dys = [torch.empty_like(x) for _ in range(world)], [torch.empty_like(dy) for _ in range(world)]
+    dist.all_gather(xs, x)
+    dist.all_gather(dys, dy)
+    x_all, dy_all = torch.cat(xs), torch.cat(dys)
+    r = N // world
+    mine = (dy_all.t() @ x_all)[rank * r:(rank + 1) * r] / world
+    # reference protocol: per-rank gradient, sum-allreduce, 1/n
+    full = dy.t() @ x
+    dist.all_reduce(full, op=dist.ReduceOp.SUM)
+    full /= world
+    rows = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(rows, mine)                                   # = the all-gather of the updated weight rows
+    if rank == 0:
+        torch.save({"gathered": torch.cat(rows), "allreduced": full}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dense_activation_gather_equals_gradient_allreduce(tmp_path):
+    """dW = dy^T x has rank B: all-gathering x and dy and updating one's own rows is the same update as the
+    gradient sum-allreduce it replaces (dp.dense_gather_adam, a3d_dense_wgrad_adam_rows)."""
+    world, port = 2, 29532
+    out = str(tmp_path / "gather.pt")
+    mp.spawn(_gather_worker, args=(world, port, out), nprocs=world, join=True)
+    got = torch.load(out)
+    assert torch.allclose(got["gathered"], got["allreduced"], atol=1e-5)
+
+
+def test_dense_gather_eligibility():
+    net = _Net()
+    dp = DataParallel.__new__(DataParallel)
+    for world, ok in ((2, True), (4, True), (8, True), (3, False)):
+        dp.world = world
+        for k in ("coarse/dense/dense_1/kernel", "coarse/dense/dense_0/kernel"):
+            assert dp.can_gather_dense(net, k, 32) is ok, (world, k)
+    dp.world = 8
+    assert not dp.can_gather_dense(net, "coarse/dense/dense_0/kernel", 64)       # gathered batch 512 > 256
+    s = net.arena.specs["coarse/dense/dense_1/kernel"]
+    assert s.packed_shape == (4096, 4096) and s.tf_shape == (4096, 4070)          # rows padded for equal slices
+    t = torch.rand(4096, 4070)
+    assert torch.equal(unpack(s, pack(s, t)), t) and float(pack(s, t)[4070:].abs().max()) == 0.0
+
+
 def test_bench_reference_arm_other_ranks_are_silent():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",

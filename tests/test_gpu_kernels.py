@@ -463,3 +463,38 @@ def test_gather_sum_and_scatter_cast(ctx):
     exp = torch.zeros(big, dtype=torch.bfloat16, device=DEV)
     exp[one[0].long()] = w.bfloat16()
     assert torch.equal(out, exp)
+
+
+@pytest.mark.parametrize("M,N,K,rows", [(32, 100, 512, (0, 100)), (64, 200, 512, (32, 160)), (256, 96, 256, (48, 96))])
+def test_dense_wgrad_adam_fused_and_rows(ctx, M, N, K, rows):
+    """Fused dense wgrad + TF-Adam (mma.sync gradient inside the optimizer pass): whole matrix (M <= 32) and the
+    data-parallel row-slice form with a gathered batch, against f32 torch math on the same bf16 operands."""
+    g = torch.Generator().manual_seed(50)
+    x = bf16_rand(M, K, seed=51)
+    lddy = (N + 7) // 8 * 8
+    dy = bf16_rand(M, lddy, seed=52)
+    w0 = torch.rand(N, K, generator=g).to(DEV)
+    m0 = (torch.rand(N, K, generator=g) * 0.1).to(DEV)
+    v0 = (torch.rand(N, K, generator=g) * 0.01).to(DEV)
+    lr, b1, b2, eps, t, gs = 0.1, 0.9, 0.999, 1e-8, 3, 0.5
+    grad = dy[:, :N].float().t() @ x.float() * gs
+    m1 = b1 * m0 + (1 - b1) * grad
+    v1 = b2 * v0 + (1 - b2) * grad * grad
+    w1 = w0 - ops.adam_lr_t(lr, b1, b2, t) * m1 / (v1.sqrt() + eps)
+    lo, hi = rows
+    w, m, v = w0.clone(), m0.clone(), v0.clone()
+    wb = torch.zeros(N, K, dtype=torch.bfloat16, device=DEV)
+    ctx.dense_wgrad_adam_rows(x, dy, w, m, v, wb, lo, hi, lr, b1, b2, eps, t, gs, N=N)
+    assert torch.allclose(m[lo:hi], m1[lo:hi], rtol=1e-4, atol=1e-6)
+    assert torch.allclose(v[lo:hi], v1[lo:hi], rtol=1e-4, atol=1e-7)
+    assert torch.allclose(w[lo:hi], w1[lo:hi], rtol=1e-4, atol=1e-5)
+    assert torch.equal(wb[lo:hi], w[lo:hi].bfloat16())
+    keep = torch.ones(N, dtype=torch.bool, device=DEV)
+    keep[lo:hi] = False
+    assert torch.equal(w[keep], w0[keep]) and torch.equal(m[keep], m0[keep]) and float(wb[keep].abs().max() if keep.any() else 0) == 0
+    if M <= 32 and K % 256 == 0:
+        w, m, v = w0.clone(), m0.clone(), v0.clone()
+        db = torch.zeros(N, device=DEV)
+        ctx.dense_wgrad_adam(x, dy, db, w, m, v, wb, lr, b1, b2, eps, t, gs)
+        assert torch.allclose(w, w1, rtol=1e-4, atol=1e-5) and torch.allclose(m, m1, rtol=1e-4, atol=1e-6)
+        assert torch.allclose(db, dy[:, :N].float().sum(0), rtol=1e-3, atol=1e-3)
