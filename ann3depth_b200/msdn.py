@@ -443,10 +443,9 @@ class MSDNNet:
         c.conv2d_dgrad(self.d_c2, self.g_c2, self.w(n + "2" + K), out=self.g_p1)
         c.maxpool2x2_idx_bwd(self.i1, self.g_p1, (B, 27, 37, 256), out=self.g_c1)
         e_g = mark(s0)
-        # DP: conv2d_4..2 are complete (their wgrads precede on s3, their dgrads -- the last readers of the weights the
-        # update overwrites -- precede e_g): exchange them now, under the rest of the backward pass
-        on_wgrad(e_g, lambda: (self.comm and dp_update("coarse_conv_early", "CoarseConv"),
-                               c.conv2d_wgrad(self.d_c1, self.p0, self.g_c1, dw=self.gw(n + "1" + K), db=self.gw(n + "1/bias"))), s3)
+        # (DP: exchanging conv2d_4..2 here as an early bucket was measured SLOWER at 2 GPUs, 1.30 vs 1.26 ms: three more
+        # NCCL launches cost more than the shorter tail saves; dp.bucket_range keeps the early/late split available)
+        on_wgrad(e_g, lambda: c.conv2d_wgrad(self.d_c1, self.p0, self.g_c1, dw=self.gw(n + "1" + K), db=self.gw(n + "1/bias")), s3)
         c.conv2d_dgrad(self.d_c1, self.g_c1, self.w(n + "1" + K), out=self.g_p0)
         c.maxpool2x2_idx_bwd(self.i0, self.g_p0, (B, 55, 74, 96), out=self.g_c0)
         e_g = mark(s0)
@@ -455,7 +454,7 @@ class MSDNNet:
             c.conv2d_wgrad(self.d_c0, self.img4, self.g_c0, dw=self.gw(n + "0" + K), db=self.gw(n + "0/bias"))
             self._mask_padding("coarse/conv/conv2d_0/kernel")
             if self.comm:
-                dp_update("coarse_conv_late", "CoarseConv")
+                dp_update("coarse_conv", "CoarseConv")
                 self.comm.wait_all(self)
             else:
                 self.apply_adam(("CoarseConv",))
