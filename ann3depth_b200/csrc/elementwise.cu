@@ -716,6 +716,58 @@ __global__ void resize_bilinear_tf1_s2d4c3_kernel(const float* __restrict__ src,
   }
 }
 
+// Row-staged variant (default when two source rows fit in shared memory): one block per resized output row.  The two
+// source rows the row interpolates between are loaded ONCE with coalesced float4 loads (every source byte crosses
+// HBM -> SM a single time: 118 MB for the MSDN batch), then 228 threads each produce one 8-byte piece (4 bf16) of
+// the space-to-depth output.
+__global__ void __launch_bounds__(256)
+resize_bilinear_tf1_s2d4c3_rows_kernel(const float* __restrict__ src, int H, int W, uint16_t* __restrict__ dst, int OH,
+                                       int OWs, int dstC, float sy, float sx) {
+  extern __shared__ float rows_sm[];                    // [2][W*3]
+  const int oy = blockIdx.x % OH, b = blockIdx.x / OH;
+  const float fy = oy * sy;
+  const int y0 = (int)floorf(fy);
+  const int y1 = min(y0 + 1, H - 1);
+  const float ly = fy - y0;
+  const int row_f4 = W * 3 / 4;
+  const float4* r0 = reinterpret_cast<const float4*>(src + ((size_t)b * H + y0) * W * 3);
+  const float4* r1 = reinterpret_cast<const float4*>(src + ((size_t)b * H + y1) * W * 3);
+  float4* s0 = reinterpret_cast<float4*>(rows_sm);
+  float4* s1 = s0 + row_f4;
+  for (int i = threadIdx.x; i < row_f4; i += blockDim.x) { s0[i] = __ldg(r0 + i); s1[i] = __ldg(r1 + i); }
+  __syncthreads();
+  const float* a0 = rows_sm;
+  const float* a1 = rows_sm + W * 3;
+  const int Y = oy >> 2, dy = oy & 3;
+  uint16_t* orow = dst + ((size_t)b * (OH >> 2) + Y) * OWs * dstC;
+  for (int t = threadIdx.x; t < OWs * 3; t += blockDim.x) {
+    const int X = t / 3, p = t - X * 3;               // piece p = values 4p .. 4p+3 of the 12 (dx, c) values
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = p * 4 + j;
+      const int dx = k / 3, c = k - dx * 3;
+      const float fx = (X * 4 + dx) * sx;
+      const int x0 = (int)floorf(fx);
+      const int x1 = min(x0 + 1, W - 1);
+      const float lx = fx - x0;
+      const float tl = a0[x0 * 3 + c], tr = a0[x1 * 3 + c], bl = a1[x0 * 3 + c], br = a1[x1 * 3 + c];
+      const float top = tl + (tr - tl) * lx;
+      const float bot = bl + (br - bl) * lx;
+      v[j] = top + (bot - top) * ly;
+    }
+    *reinterpret_cast<uint2*>(orow + (size_t)X * dstC + dy * 12 + p * 4) =
+        make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+  }
+  if (dy == 0) {
+    const int padq = (dstC - 48) / 4;                  // uint2 pieces of zero padding per pixel
+    for (int t = threadIdx.x; t < OWs * padq; t += blockDim.x) {
+      const int X = t / padq, q = t - X * padq;
+      *reinterpret_cast<uint2*>(orow + (size_t)X * dstC + 48 + q * 4) = make_uint2(0u, 0u);
+    }
+  }
+}
+
 extern "C" int a3d_resize_bilinear_tf1_s2d(a3d_ctx* ctx, const float* src, int B, int H, int W, int C, uint16_t* dst,
                                            int OH, int OW, int s, int dstC, void* stream) {
   A3D_REQUIRE(ctx && src && dst, "resize_s2d: null argument");
@@ -723,6 +775,13 @@ extern "C" int a3d_resize_bilinear_tf1_s2d(a3d_ctx* ctx, const float* src, int B
                   dstC >= s * s * C && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
               "resize_s2d: bad shape (OH, OW multiples of s; dstC %% 8 == 0 and >= s*s*C)");
   float sy = (float)H / (float)OH, sx = (float)W / (float)OW;
+  if (s == 4 && C == 3 && (W * 3) % 4 == 0 && (size_t)W * 3 * 2 * sizeof(float) <= 48 * 1024 && dstC % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    resize_bilinear_tf1_s2d4c3_rows_kernel<<<B * OH, 256, (size_t)W * 3 * 2 * sizeof(float), as_stream(stream)>>>(
+        src, H, W, dst, OH, OW / 4, dstC, sy, sx);
+    A3D_LAUNCH_OK(ctx);
+    return 0;
+  }
   if (s == 4 && C == 3) {
     const size_t rows = (size_t)B * OH * (OW / 4);
     int block = 256, grid = grid_for(ctx, rows, block);

@@ -308,6 +308,25 @@ class MSDNNet:
 
     # ------------------------------------------------------------------ phase-1 step on three streams
     def _enqueue_phase1_overlapped(self):
+        """The multi-stream phase-1 step with its critical path (resize, coarse forward, loss, dgrad chain) on a
+        HIGH-PRIORITY stream: whenever an SM slot frees up, pending CTAs of the chain are placed before those of the
+        fine / wgrad / optimizer streams, which fill the remaining slots.  (CUDA graph capture keeps the priority as
+        a kernel-node attribute.)  A3D_MAIN_PRIORITY=0 disables."""
+        if os.environ.get("A3D_MAIN_PRIORITY", "-1") == "0":
+            return self._enqueue_phase1_streams()
+        if getattr(self, "_s_main", None) is None:
+            self._s_main = torch.cuda.Stream(device=self.dev, priority=-1)
+        cur = torch.cuda.current_stream()
+        e_in = torch.cuda.Event()
+        e_in.record(cur)
+        with torch.cuda.stream(self._s_main):
+            self._s_main.wait_event(e_in)
+            self._enqueue_phase1_streams()
+            e_out = torch.cuda.Event()
+            e_out.record(self._s_main)
+        cur.wait_event(e_out)
+
+    def _enqueue_phase1_streams(self):
         """Same launches as forward() + backward_coarse() + apply_adam(), arranged by data dependence:
              main stream : resize, coarse forward, coarse loss, the dgrad chain (the critical path)
              fine stream : fine forward + fine loss (needs only the image and the coarse map)

@@ -74,7 +74,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.005)
 
     def summary(self):
         s = sorted(self.samples)
@@ -254,6 +254,23 @@ def gpu_arm(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.ncu:
+        # profiling hook (never a bench value): warm up (autotuning, graph capture), then expose exactly one
+        # un-graphed sequential step and one graph replay to `ncu --profile-from-start off`
+        for _ in range(3):
+            op.run()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        saved_overlap, op.net.overlap = op.net.overlap, False
+        op.run(use_graph=False)
+        op.net.overlap = saved_overlap
+        torch.cuda.synchronize()
+        op.run()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"ncu": "one sequential step + one graph replay profiled"}), flush=True)
+        return
+
     # ---- device-resident inputs: value
     launches0 = ctx.launches
     op.run(use_graph=False)
@@ -406,10 +423,11 @@ def gpu_arm(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="a3d", choices=["a3d", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu", action="store_true", help="profiling hook: cudaProfilerStart/Stop around two steps")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
