@@ -52,8 +52,8 @@ SIGNATURES = {
     "a3d_dense_wgrad": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
     "a3d_dense_wgrad_adam": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _f, _f, _vp, _vp]),
     "a3d_dense_wgrad_adam_rows": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _f, _f, _f,
-                                       _vp, _vp]),
-    "a3d_bias_grad_bf16": (_i, [_vp, _vp, _sz, _i, _i, _vp, _vp]),
+                                       _vp, _i, _sz, _sz, _vp]),
+    "a3d_bias_grad_bf16": (_i, [_vp, _vp, _sz, _i, _i, _vp, _i, _sz, _vp]),
     "a3d_dense_epilogue_bwd": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _sz, _u, _vp]),
     "a3d_maxpool2x2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "a3d_maxpool2x2_relu_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),

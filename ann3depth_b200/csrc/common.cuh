@@ -80,6 +80,8 @@ int a3d_simt_conv_dgrad(a3d_ctx*, const a3d_conv_desc*, const uint16_t* dy, cons
 int a3d_simt_conv_wgrad(a3d_ctx*, const a3d_conv_desc*, const uint16_t* x, const uint16_t* dy, float* dw,
                         cudaStream_t st);
 int a3d_colsum_bf16(a3d_ctx*, const uint16_t* a, size_t rows, int C, int ld, float* out, cudaStream_t st);
+int a3d_colsum_bf16_grouped(a3d_ctx*, const uint16_t* a, int rows, int C, int ld, int gb, size_t gs, float* out,
+                            cudaStream_t st);
 int a3d_simt_dense_fwd(a3d_ctx*, const uint16_t* x, int ldx, const uint16_t* w, const float* bias, const uint8_t* mask,
                        float drop_rate, void* y, int y_dtype, int M, int N, int K, unsigned flags, cudaStream_t st);
 int a3d_simt_dense_dgrad(a3d_ctx*, const uint16_t* dy, int lddy, const uint16_t* w, uint16_t* dx, int M, int N, int K,

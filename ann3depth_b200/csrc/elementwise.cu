@@ -1139,7 +1139,8 @@ __global__ void __launch_bounds__(256, 3)
 dense_wgrad_adam_mma_rows_kernel(const uint16_t* __restrict__ x, int ldx, const uint16_t* __restrict__ dy, int lddy,
                                  float* __restrict__ w, float* __restrict__ m, float* __restrict__ v,
                                  uint16_t* __restrict__ wb, int M, int K, int row_lo, int row_hi, float lr_t, float b1,
-                                 float b2, float eps, float gs, const float* __restrict__ lr_dev) {
+                                 float b2, float eps, float gs, const float* __restrict__ lr_dev, int gb, size_t xgs,
+                                 size_t dygs) {
   if (lr_dev) lr_t = __ldg(lr_dev);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -1155,13 +1156,17 @@ dense_wgrad_adam_mma_rows_kernel(const uint16_t* __restrict__ x, int ldx, const 
     for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
 #pragma unroll 2
     for (int kb = 0; kb < ksteps; ++kb) {
+      // gb is a multiple of 16: the 16 batch rows of an MMA k-step lie in ONE rank block (one division per k-step)
+      const int grp = (kb * 16) / gb, rin = kb * 16 - grp * gb;
+      const uint16_t* xk = x + (size_t)grp * xgs + (size_t)rin * ldx;
+      const uint16_t* dyk = dy + (size_t)grp * dygs + (size_t)rin * lddy;
       uint32_t afrag[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int row = (i & 1) ? r1 : r0;
-        const int b0 = kb * 16 + (i >> 1) * 8 + 2 * t;
-        const uint32_t lo = (row < row_hi && b0 < M) ? __ldg(dy + (size_t)b0 * lddy + row) : 0u;
-        const uint32_t hi = (row < row_hi && b0 + 1 < M) ? __ldg(dy + (size_t)(b0 + 1) * lddy + row) : 0u;
+        const int bl = (i >> 1) * 8 + 2 * t, b0 = kb * 16 + bl;
+        const uint32_t lo = (row < row_hi && b0 < M) ? __ldg(dyk + (size_t)bl * lddy + row) : 0u;
+        const uint32_t hi = (row < row_hi && b0 + 1 < M) ? __ldg(dyk + (size_t)(bl + 1) * lddy + row) : 0u;
         afrag[i] = lo | (hi << 16);
       }
 #pragma unroll
@@ -1169,9 +1174,9 @@ dense_wgrad_adam_mma_rows_kernel(const uint16_t* __restrict__ x, int ldx, const 
         uint32_t bfrag[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int b0 = kb * 16 + h * 8 + 2 * t;
-          const uint32_t lo = b0 < M ? __ldg(x + (size_t)b0 * ldx + colj[j]) : 0u;
-          const uint32_t hi = b0 + 1 < M ? __ldg(x + (size_t)(b0 + 1) * ldx + colj[j]) : 0u;
+          const int bl = h * 8 + 2 * t, b0 = kb * 16 + bl;
+          const uint32_t lo = b0 < M ? __ldg(xk + (size_t)bl * ldx + colj[j]) : 0u;
+          const uint32_t hi = b0 + 1 < M ? __ldg(xk + (size_t)(bl + 1) * ldx + colj[j]) : 0u;
           bfrag[h] = lo | (hi << 16);
         }
         mma_bf16_16816(acc[j], afrag, bfrag);
@@ -1215,7 +1220,8 @@ dense_wgrad_adam_mma_rows_kernel(const uint16_t* __restrict__ x, int ldx, const 
 extern "C" int a3d_dense_wgrad_adam_rows(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* w,
                                          float* m, float* v, uint16_t* w_bf16, int M, int N, int K, int row_lo, int row_hi,
                                          float lr_t, float beta1, float beta2, float eps, float grad_scale,
-                                         const float* lr_t_dev, void* stream) {
+                                         const float* lr_t_dev, int group_rows, size_t x_group_stride,
+                                         size_t dy_group_stride, void* stream) {
   A3D_REQUIRE(ctx && x && dy && w && m && v && M > 0 && N > 0 && K > 0 && lddy >= N && ldx >= K,
               "dense wgrad+adam rows: bad argument");
   A3D_REQUIRE(K % 256 == 0 && aligned16(w) && aligned16(m) && aligned16(v) &&
@@ -1223,18 +1229,26 @@ extern "C" int a3d_dense_wgrad_adam_rows(a3d_ctx* ctx, const uint16_t* x, int ld
               "dense wgrad+adam rows: needs K %% 256 == 0 and 16-byte aligned w/m/v");
   if (row_hi > N) row_hi = N;
   if (row_lo >= row_hi) return 0;
+  if (group_rows <= 0) {                       // plain [M, ld] matrices = one block of (M rounded up to 16) rows
+    group_rows = (M + 15) / 16 * 16;
+    x_group_stride = dy_group_stride = 0;
+  }
+  A3D_REQUIRE(group_rows % 16 == 0, "dense wgrad+adam rows: group_rows must be a multiple of 16");
   const int kblocks = K / 256;
   int gy = 3 * ctx->sm_count / kblocks;
   if (gy < 1) gy = 1;
   if (gy > ceil_div(row_hi - row_lo, 16)) gy = ceil_div(row_hi - row_lo, 16);
   dense_wgrad_adam_mma_rows_kernel<<<dim3(kblocks, gy), 256, 0, as_stream(stream)>>>(
-      x, ldx, dy, lddy, w, m, v, w_bf16, M, K, row_lo, row_hi, lr_t, beta1, beta2, eps, grad_scale, lr_t_dev);
+      x, ldx, dy, lddy, w, m, v, w_bf16, M, K, row_lo, row_hi, lr_t, beta1, beta2, eps, grad_scale, lr_t_dev, group_rows,
+      x_group_stride, dy_group_stride);
   A3D_LAUNCH_OK(ctx);
   return 0;
 }
 
-// BiasAddGrad alone: db[c] = sum_rows dy[row][c]  (dy bf16 [rows][ld])
-extern "C" int a3d_bias_grad_bf16(a3d_ctx* ctx, const uint16_t* dy, size_t rows, int C, int ld, float* db, void* stream) {
+// BiasAddGrad alone: db[c] = sum_rows dy[row][c]  (dy bf16 [rows][ld]; group_rows > 0: rank blocks as above)
+extern "C" int a3d_bias_grad_bf16(a3d_ctx* ctx, const uint16_t* dy, size_t rows, int C, int ld, float* db, int group_rows,
+                                  size_t group_stride, void* stream) {
   A3D_REQUIRE(ctx && dy && db && rows > 0 && C > 0 && ld >= C, "bias grad: bad argument");
+  if (group_rows > 0) return a3d_colsum_bf16_grouped(ctx, dy, (int)rows, C, ld, group_rows, group_stride, db, as_stream(stream));
   return a3d_colsum_bf16(ctx, dy, rows, C, ld, db, as_stream(stream));
 }

@@ -202,6 +202,15 @@ __global__ void colsum_bf16_cols_kernel(const uint16_t* __restrict__ a, int rows
   out[c] = s;
 }
 
+// the same over a batch stored in rank blocks (dp.dense_gather_adam): row r = row r % gb of block r / gb
+__global__ void colsum_bf16_cols_grouped_kernel(const uint16_t* __restrict__ a, int rows, int C, int ld, int gb, size_t gs,
+                                                float* __restrict__ out) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int r = 0; r < rows; ++r) s += bf16_bits_to_f32(a[(size_t)(r / gb) * gs + (size_t)(r % gb) * ld + c]);
+  out[c] = s;
+}
 // generic fallback (any C, any ld)
 __global__ void colsum_bf16_scalar_kernel(const uint16_t* __restrict__ a, size_t rows, int C, int ld,
                                           float* __restrict__ out, int rows_per_block) {
@@ -235,6 +244,13 @@ int a3d_simt_conv_wgrad(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x,
   ConvWgradProb p{x, dy, dw, d->N, d->H, d->W, d->C, d->K, d->R, d->S, d->stride_h, d->stride_w, d->pad_t, d->pad_l,
                   d->P, d->Q, d->ldy};
   return launch(ctx, p, d->K, (long long)d->R * d->S * d->C, st);
+}
+
+int a3d_colsum_bf16_grouped(a3d_ctx* ctx, const uint16_t* a, int rows, int C, int ld, int gb, size_t gs, float* out,
+                            cudaStream_t st) {
+  colsum_bf16_cols_grouped_kernel<<<ceil_div(C, 128), 128, 0, st>>>(a, rows, C, ld, gb, gs, out);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
 }
 
 int a3d_colsum_bf16(a3d_ctx* ctx, const uint16_t* a, size_t rows, int C, int ld, float* out, cudaStream_t st) {

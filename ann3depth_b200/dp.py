@@ -118,39 +118,41 @@ class DataParallel:
         rows, K = ks.packed_shape
         N = ks.tf_shape[1]
         B = x.shape[0]
+        lddy = dy.shape[1]
+        blk = B * (K + lddy)                  # one rank block: x [B,K] followed by dy [B,lddy] -> ONE all-gather
         key = ("gather", kernel_name)
         bufs = getattr(self, "_gbufs", None)
         if bufs is None:
             bufs = self._gbufs = {}
         if key not in bufs:
-            bufs[key] = (torch.zeros(n * B, K, dtype=torch.bfloat16, device=x.device),
-                         torch.zeros(n * B, dy.shape[1], dtype=torch.bfloat16, device=x.device))
-        xg, dyg = bufs[key]
+            bufs[key] = torch.zeros(n, blk, dtype=torch.bfloat16, device=x.device)
+        gbuf = bufs[key]
+        xg, dyg = gbuf.view(-1), gbuf.view(-1)[B * K:]
         ready = torch.cuda.Event()
         ready.record(torch.cuda.current_stream())
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ready)
-            xg[self.rank * B:(self.rank + 1) * B].copy_(x)
-            dyg[self.rank * B:(self.rank + 1) * B].copy_(dy)
-            ops.allgather(c, xg.view(-1), B * K)
-            ops.allgather(c, dyg.view(-1), B * dy.shape[1])
+            gbuf[self.rank, :B * K].view(B, K).copy_(x)
+            gbuf[self.rank, B * K:].view(B, lddy).copy_(dy)
+            ops.allgather(c, gbuf.view(-1), blk)
             if after is not None:
                 self.stream.wait_event(after)
             t = max(net.adam_t[group], 1)
             r = rows // n
             c.dense_wgrad_adam_rows(xg, dyg, a.view(a.w, kernel_name), a.view(a.m, kernel_name), a.view(a.v, kernel_name),
                                     a.view(a.wb, kernel_name), self.rank * r, (self.rank + 1) * r, lr, beta1, net.beta2,
-                                    eps, t, 1.0 / n, lr_t_dev=net.lr_dev[group], N=N)
+                                    eps, t, 1.0 / n, lr_t_dev=net.lr_dev[group], N=N, M=n * B, ldx=K, lddy=lddy,
+                                    group_rows=B, x_group_stride=blk, dy_group_stride=blk)
             # bias: replicated update from the gathered dy
             sl = slice(bs.offset, bs.offset + bs.size)
-            c.bias_grad_bf16(dyg, N, a.g[bs.offset:bs.offset + N])
+            c.bias_grad_bf16(dyg, N, a.g[bs.offset:bs.offset + N], rows=n * B, ld=lddy, group_rows=B, group_stride=blk)
             c.adam_tf(a.w[sl], a.g[sl], a.m[sl], a.v[sl], a.wb[sl], lr, beta1, net.beta2, eps, t, 1.0 / n,
                       lr_t_dev=net.lr_dev[group])
             ops.allgather(c, a.view(a.wb, kernel_name).view(-1), r * K)
             done = torch.cuda.Event()
             done.record(self.stream)
         self._done.append(done)
-        self.bytes_per_step += (n * B * (K + dy.shape[1]) + rows * K) * 2
+        self.bytes_per_step += (n * blk + rows * K) * 2
         self._row_sharded = getattr(self, "_row_sharded", set()) | {kernel_name}
 
     def gather_master(self, net):

@@ -473,7 +473,11 @@ class MSDNNet:
             c.conv2d_wgrad(self.d_c0, self.img4, self.g_c0, dw=self.gw(n + "0" + K), db=self.gw(n + "0/bias"))
             self._mask_padding("coarse/conv/conv2d_0/kernel")
             if self.comm:
-                dp_update("coarse_conv", "CoarseConv")
+                if os.environ.get("A3D_DP_CONV_ALLREDUCE", "0") == "1":      # f32 allreduce + replicated Adam (1 NCCL op)
+                    self.comm.bucket_ready(self, "coarse_conv",
+                                           then=lambda lo, hi: self.adam_range("CoarseConv", lo, hi, inv_world))
+                else:
+                    dp_update("coarse_conv", "CoarseConv")
                 self.comm.wait_all(self)
             else:
                 self.apply_adam(("CoarseConv",))

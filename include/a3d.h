@@ -163,13 +163,18 @@ int a3d_dense_wgrad_adam(a3d_ctx*, const uint16_t* x, int ldx, const uint16_t* d
  * grad_scale = 1/n this is the sharded optimizer step of n ranks x batch B without any gradient all-reduce: a dense
  * layer's gradient is the rank-M product dy_all^T x_all, so the ranks exchange activations (MBs) instead of
  * gradients (100s of MBs) -- replaces the parameter-server gradient push of src/ann3depth.py:78-92 for the dense
- * variables.  Requires K % 256 == 0. */
+ * variables.  Requires K % 256 == 0.
+ * group_rows > 0: the gathered batch is stored in rank blocks -- batch row b is row b % group_rows of block
+ * b / group_rows, blocks x_group_stride / dy_group_stride elements apart (x and dy of a rank travel in ONE
+ * all-gather); group_rows = 0: plain [M, ld] matrices. */
 int a3d_dense_wgrad_adam_rows(a3d_ctx*, const uint16_t* x, int ldx, const uint16_t* dy, int lddy,
                               float* w, float* m, float* v, uint16_t* w_bf16, int M, int N, int K,
                               int row_lo, int row_hi, float lr_t, float beta1, float beta2, float eps,
-                              float grad_scale, const float* lr_t_dev, void* stream);
-/* BiasAddGrad alone: db[c] = sum over rows of dy[row][c] (dy bf16 [rows][ld]). */
-int a3d_bias_grad_bf16(a3d_ctx*, const uint16_t* dy, size_t rows, int C, int ld, float* db, void* stream);
+                              float grad_scale, const float* lr_t_dev, int group_rows,
+                              size_t x_group_stride, size_t dy_group_stride, void* stream);
+/* BiasAddGrad alone: db[c] = sum over rows of dy[row][c] (dy bf16 [rows][ld]; group_rows / group_stride as above). */
+int a3d_bias_grad_bf16(a3d_ctx*, const uint16_t* dy, size_t rows, int C, int ld, float* db, int group_rows,
+                       size_t group_stride, void* stream);
 /* Elementwise backward of the dense epilogue: g_pre = g_post * mask/(1-rate) * act'(y).
  * y is the stored post-activation (pre-dropout) output; used between dense_1 dgrad and dense_0. */
 int a3d_dense_epilogue_bwd(a3d_ctx*, const uint16_t* g_post, const uint16_t* y, const uint8_t* keep_mask,

@@ -498,3 +498,35 @@ def test_dense_wgrad_adam_fused_and_rows(ctx, M, N, K, rows):
         ctx.dense_wgrad_adam(x, dy, db, w, m, v, wb, lr, b1, b2, eps, t, gs)
         assert torch.allclose(w, w1, rtol=1e-4, atol=1e-5) and torch.allclose(m, m1, rtol=1e-4, atol=1e-6)
         assert torch.allclose(db, dy[:, :N].float().sum(0), rtol=1e-3, atol=1e-3)
+
+
+def test_dense_rows_update_with_rank_blocks(ctx):
+    """The gathered batch stored as rank blocks [x_r | dy_r] (one all-gather per layer, dp.dense_gather_adam) must
+    give the same update and bias gradient as the plain [M, ld] matrices."""
+    n, B, N, K = 4, 16, 96, 256
+    lddy = 96
+    x = bf16_rand(n * B, K, seed=60)
+    dy = bf16_rand(n * B, lddy, seed=61)
+    g = torch.Generator().manual_seed(62)
+    w0 = torch.rand(N, K, generator=g).to(DEV)
+    m0 = (torch.rand(N, K, generator=g) * 0.1).to(DEV)
+    v0 = (torch.rand(N, K, generator=g) * 0.01).to(DEV)
+    args = (0.01, 0.9, 0.999, 1e-8, 2, 1.0 / n)
+    ref = [t.clone() for t in (w0, m0, v0)]
+    wb_ref = torch.zeros(N, K, dtype=torch.bfloat16, device=DEV)
+    ctx.dense_wgrad_adam_rows(x, dy, *ref, wb_ref, 16, 80, *args, N=N)
+    blk = B * (K + lddy)
+    gbuf = torch.zeros(n, blk, dtype=torch.bfloat16, device=DEV)
+    for r in range(n):
+        gbuf[r, :B * K] = x[r * B:(r + 1) * B].reshape(-1)
+        gbuf[r, B * K:] = dy[r * B:(r + 1) * B].reshape(-1)
+    got = [t.clone() for t in (w0, m0, v0)]
+    wb = torch.zeros(N, K, dtype=torch.bfloat16, device=DEV)
+    ctx.dense_wgrad_adam_rows(gbuf.view(-1), gbuf.view(-1)[B * K:], *got, wb, 16, 80, *args, N=N, M=n * B, ldx=K, lddy=lddy,
+                              group_rows=B, x_group_stride=blk, dy_group_stride=blk)
+    for a, b in zip(got, ref):
+        assert torch.equal(a, b)
+    assert torch.equal(wb, wb_ref)
+    db = torch.zeros(N, device=DEV)
+    ctx.bias_grad_bf16(gbuf.view(-1)[B * K:], N, db, rows=n * B, ld=lddy, group_rows=B, group_stride=blk)
+    assert torch.allclose(db, dy[:, :N].float().sum(0), rtol=1e-5, atol=1e-4)
