@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liba3d.so")
+LIB_PATH = os.environ.get("A3D_LIB") or os.path.join(_HERE, "liba3d.so")     # A3D_LIB: alternate build (experiments)
 
 A3D_F32, A3D_BF16 = 0, 1
 IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2

@@ -20,6 +20,18 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+// Stage-ring budget per CTA and the minimum pipeline depth.  Measured on the MSDN step (tools/gpu/run_r.sh):
+// 104 KB / >= 3 stages (two CTAs per SM) 1.128 ms; 72 KB / >= 2 stages (128x128 tiles: 64 KB, THREE CTAs per SM)
+// 1.072 ms; 64 KB / >= 2 stages 1.123 ms.  The MSDN tiles have 9..100 k-blocks, so a CTA's life is dominated by
+// its prologue (barrier init, TMEM alloc, first TMA round trip) and epilogue; a third resident CTA hides more of
+// that than a deeper ring does.
+#ifndef A3D_RING_KB
+#define A3D_RING_KB 72
+#endif
+#ifndef A3D_MIN_STAGES
+#define A3D_MIN_STAGES 2
+#endif
+
 namespace tc {
 
 enum AMode : int { A_TILED = 0, A_IM2COL = 1 };
@@ -65,7 +77,7 @@ struct Params {
   const float* lr_t_dev;
 };
 
-template <int BN_, int KCB_, bool A_MN_, bool B_MN_, int B_BW_ = 64, int MIN_STAGES_ = 3, bool ADAM_ = false>
+template <int BN_, int KCB_, bool A_MN_, bool B_MN_, int B_BW_ = 64, int MIN_STAGES_ = A3D_MIN_STAGES, bool ADAM_ = false>
 struct Cfg {
   static constexpr bool ADAM = ADAM_;                     // compile the EPI_ADAM epilogue (24 float4 loads in flight:
                                                           // 168 registers) only into the kernels that use it
@@ -82,9 +94,9 @@ struct Cfg {
   static constexpr int B_BYTES = B_MN_ ? B_NBLK * B_BLK_BYTES : CHUNKED ? 8 * BN_ * 16 : BN_ * KCB_;
   static_assert(!CHUNKED || (!A_MN_ && !B_MN_), "chunked mode is K-major only");
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  // ~104 KB of stages per CTA: two CTAs (of this or of a concurrently running kernel on another stream)
-  // fit on one SM, so one CTA's epilogue / prologue hides under the other's main loop.  At least 3 stages.
-  static constexpr int STAGES_RAW = (104 * 1024) / STAGE_BYTES;
+  // A3D_RING_KB of stages per CTA: two or three CTAs (of this or of a concurrently running kernel on another
+  // stream) fit on one SM, so one CTA's epilogue / prologue hides under the others' main loops.
+  static constexpr int STAGES_RAW = (A3D_RING_KB * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < MIN_STAGES_ ? MIN_STAGES_ : STAGES_RAW);
   static constexpr int TMEM_COLS = BN_ <= 32 ? 32 : BN_ <= 64 ? 64 : BN_ <= 128 ? 128 : 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
