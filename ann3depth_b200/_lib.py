@@ -87,6 +87,7 @@ SIGNATURES = {
     "a3d_allgather": (_i, [_vp, _vp, _sz, _i, _vp]),
     # engine unit-test hook (not part of the drop-in surface)
     "a3d_debug_tc_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "a3d_debug_tc_gemm_v": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "a3d_debug_tc_shift": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
 }
 

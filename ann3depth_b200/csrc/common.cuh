@@ -88,3 +88,15 @@ int a3d_simt_dense_dgrad(a3d_ctx*, const uint16_t* dy, int lddy, const uint16_t*
                          cudaStream_t st);
 int a3d_simt_dense_wgrad(a3d_ctx*, const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, int M, int N,
                          int K, cudaStream_t st);
+
+// dense_stream.cu: weight-streaming mma.sync kernels (batch <= 32 dense layers, single-filter convolution)
+int a3d_stream_mode();
+bool a3d_stream_dense_fwd_ok(int M, int N, int K, int ldx);
+bool a3d_stream_dense_dgrad_ok(int M, int N, int K, int lddy);
+int a3d_stream_dense_fwd(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t* w, float* acc, int M, int N, int K,
+                         int ctas, cudaStream_t st);
+int a3d_stream_dense_dgrad(a3d_ctx* ctx, const uint16_t* dy, int lddy, const uint16_t* w, float* acc, int M, int N, int K,
+                           int ctas, cudaStream_t st);
+bool a3d_conv_k1_tiled_ok(const a3d_conv_desc* d);
+int a3d_conv_k1_tiled(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, const uint16_t* w, const float* bias,
+                      void* y, int y_dtype, unsigned flags, cudaStream_t st);

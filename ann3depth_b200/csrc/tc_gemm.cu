@@ -198,19 +198,43 @@ int launch_cfg(a3d_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, con
   return 0;
 }
 
-// K-major x K-major dispatch over (BN, KCB)
+// K-major x K-major dispatch over (BN, KCB) and the tile variant:
+//   0  128-row tile, default ring (tc_gemm.cuh A3D_RING_KB / A3D_MIN_STAGES: most CTAs per SM)
+//   1  128-row tile, one stage more (long main loops -- conv2d_1 dgrad has 100 k-blocks -- want the deeper pipeline)
+//   2  256-row tile (two accumulators sharing every B stage: less L2->SM operand traffic), default ring
+//   3  256-row tile, three stages
+enum { V_BASE = 0, V_DEEP = 1, V_BM256 = 2, V_BM256_DEEP = 3, V_COUNT = 4 };
 int launch_kk(a3d_ctx* ctx, int bn, int kcb, const CUtensorMap& tmA, const CUtensorMap& tmB, const tc::Params& p,
-              int splits, cudaStream_t st) {
+              int splits, cudaStream_t st, int variant = V_BASE) {
+  if (variant == V_BASE) {
 #define A3D_CASE(BN, KCB) \
   if (bn == BN && kcb == KCB) return launch_cfg<tc::Cfg<BN, KCB, false, false>>(ctx, tmA, tmB, p, splits, st);
-  A3D_CASE(32, 128) A3D_CASE(64, 128) A3D_CASE(96, 128) A3D_CASE(128, 128) A3D_CASE(192, 128) A3D_CASE(256, 128)
-  A3D_CASE(32, 64) A3D_CASE(64, 64) A3D_CASE(96, 64) A3D_CASE(128, 64) A3D_CASE(192, 64) A3D_CASE(256, 64)
-  A3D_CASE(32, 32) A3D_CASE(64, 32) A3D_CASE(96, 32) A3D_CASE(128, 32) A3D_CASE(256, 32)
-  A3D_CASE(16, 128) A3D_CASE(16, 64) A3D_CASE(16, 32)
-  A3D_CASE(32, 16) A3D_CASE(64, 16) A3D_CASE(96, 16) A3D_CASE(128, 16)
+    A3D_CASE(32, 128) A3D_CASE(64, 128) A3D_CASE(96, 128) A3D_CASE(128, 128) A3D_CASE(192, 128) A3D_CASE(256, 128)
+    A3D_CASE(32, 64) A3D_CASE(64, 64) A3D_CASE(96, 64) A3D_CASE(128, 64) A3D_CASE(192, 64) A3D_CASE(256, 64)
+    A3D_CASE(32, 32) A3D_CASE(64, 32) A3D_CASE(96, 32) A3D_CASE(128, 32) A3D_CASE(256, 32)
+    A3D_CASE(16, 128) A3D_CASE(16, 64) A3D_CASE(16, 32)
+    A3D_CASE(32, 16) A3D_CASE(64, 16) A3D_CASE(96, 16) A3D_CASE(128, 16)
 #undef A3D_CASE
-  a3d_set_error("tc gemm: no kernel for BN=%d KCB=%d", bn, kcb);
+  } else if (kcb == 128) {
+#define A3D_CASEV(V, BN, MS, BM) \
+  if (variant == V && bn == BN) \
+    return launch_cfg<tc::Cfg<BN, 128, false, false, 64, MS, false, BM>>(ctx, tmA, tmB, p, splits, st);
+    A3D_CASEV(V_DEEP, 64, 4, 128) A3D_CASEV(V_DEEP, 96, 3, 128) A3D_CASEV(V_DEEP, 128, 3, 128)
+    A3D_CASEV(V_DEEP, 192, 3, 128) A3D_CASEV(V_DEEP, 256, 3, 128)
+    A3D_CASEV(V_BM256, 64, 2, 256) A3D_CASEV(V_BM256, 96, 2, 256) A3D_CASEV(V_BM256, 128, 2, 256)
+    A3D_CASEV(V_BM256, 256, 2, 256)
+    A3D_CASEV(V_BM256_DEEP, 64, 3, 256) A3D_CASEV(V_BM256_DEEP, 96, 3, 256) A3D_CASEV(V_BM256_DEEP, 128, 3, 256)
+    A3D_CASEV(V_BM256_DEEP, 256, 3, 256)
+#undef A3D_CASEV
+  }
+  a3d_set_error("tc gemm: no kernel for BN=%d KCB=%d variant=%d", bn, kcb, variant);
   return A3D_ENOTSUP;
+}
+bool variant_exists(int bn, int kcb, int variant) {
+  if (variant == V_BASE) return true;
+  if (kcb != 128) return false;
+  if (variant == V_DEEP) return bn == 64 || bn == 96 || bn == 128 || bn == 192 || bn == 256;
+  return bn == 64 || bn == 96 || bn == 128 || bn == 256;
 }
 
 int pick_bn(int n) {
@@ -295,15 +319,18 @@ int autotune(const TuneKey& key, int ncand, F run, cudaStream_t st) {
   if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return 0;
   int best = 0;
   float best_ms = 1e30f;
+  constexpr int kReps = 10;                        // 3 repetitions left the choice between near-ties to timer noise
+  const bool verbose = getenv("A3D_AUTOTUNE_VERBOSE") && atoi(getenv("A3D_AUTOTUNE_VERBOSE")) >= 2;
   for (int c = 0; c < ncand; ++c) {
     if (run(c) != 0) continue;                     // warm-up (function attributes, L2)
     cudaEventRecord(e0, st);
     bool ok = true;
-    for (int r = 0; r < 3 && ok; ++r) ok = run(c) == 0;
+    for (int r = 0; r < kReps && ok; ++r) ok = run(c) == 0;
     cudaEventRecord(e1, st);
     if (cudaEventSynchronize(e1) != cudaSuccess || !ok) continue;
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
+    if (verbose) fprintf(stderr, "a3d autotune:   kind %d candidate %d: %.1f us\n", key.v[0], c, ms * 1e3f / kReps);
     if (ms < best_ms) { best_ms = ms; best = c; }
   }
   cudaEventDestroy(e0);
@@ -312,7 +339,7 @@ int autotune(const TuneKey& key, int ncand, F run, cudaStream_t st) {
   if (getenv("A3D_AUTOTUNE_VERBOSE"))
     fprintf(stderr, "a3d autotune: kind %d [%d %d %d %d %d %d %d %d %d] -> candidate %d of %d (%.1f us)\n", key.v[0],
             key.v[1], key.v[2], key.v[3], key.v[4], key.v[5], key.v[6], key.v[7], key.v[8], key.v[9], best, ncand,
-            best_ms * 1e3f / 3);
+            best_ms * 1e3f / kReps);
   return best;
 }
 // split-K candidates for the weight-streaming dense kernels: the heuristic first, then CTA counts of
@@ -372,8 +399,20 @@ int a3d_tc_conv_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, con
     p.PQ = d->P * d->Q; p.Q = d->Q; p.sh = d->stride_h; p.sw = d->stride_w; p.lower_h = -d->pad_t; p.lower_w = -d->pad_l;
     p.S = d->S; p.cblocks = cblocks;
     p.epi = tc::EPI_POOL4_BF16; p.out = y; p.ldo = d->ldy; p.bias = bias; p.flags = flags; p.pool_idx = pool_idx;
-    // two stages of 48 KB: two CTAs per SM, one CTA's epilogue runs under the other's main loop
-    return launch_cfg<tc::Cfg<256, 128, false, false, 64, 2>>(ctx, tmA, tmB, p, 1, st);
+    // 128-row tiles with two stages of 48 KB (two CTAs per SM, one CTA's epilogue under the other's main loop),
+    // the same with three stages, or 256-row tiles (both accumulators fill the 512 TMEM columns)
+    auto run = [&](int c) -> int {
+      if (c == 1) return launch_cfg<tc::Cfg<256, 128, false, false, 64, 3>>(ctx, tmA, tmB, p, 1, st);
+      if (c == 2) return launch_cfg<tc::Cfg<256, 128, false, false, 64, 2, false, 256>>(ctx, tmA, tmB, p, 1, st);
+      if (c == 3) return launch_cfg<tc::Cfg<256, 128, false, false, 64, 3, false, 256>>(ctx, tmA, tmB, p, 1, st);
+      return launch_cfg<tc::Cfg<256, 128, false, false, 64, 2>>(ctx, tmA, tmB, p, 1, st);
+    };
+    if (const char* force = getenv("A3D_POOL4_FORCE")) return run(atoi(force));
+    TuneKey key{};
+    const int kv[16] = {5, d->N, d->H, d->W, d->C, d->K, d->R, d->S, d->stride_h, d->stride_w, d->pad_t, d->pad_l,
+                        d->P, d->Q, d->ldy, pool_idx != nullptr};
+    memcpy(key.v, kv, sizeof(kv));
+    return run(autotune(key, 4, run, st));
   }
   if (!a3d_tc_conv_fwd_supported(d)) {
     a3d_set_error("tc conv fwd: unsupported shape (C=%d must be a multiple of 16)", d->C);
@@ -396,7 +435,7 @@ int a3d_tc_conv_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, con
   p.S = d->S; p.cblocks = cblocks;
   const bool can_split = ws && ws_bytes >= (size_t)M * d->K * sizeof(float);
 
-  auto launch = [&](int bn, int splits) -> int {
+  auto launch = [&](int bn, int splits, int variant) -> int {
     CUtensorMap tmB;
     int r = kc == 8 ? make_tmap_chunked(ctx, &tmB, w, d->K, (uint64_t)d->R * d->S * d->C, bn)
                     : make_tmap_2d(ctx, &tmB, w, d->K, (uint64_t)d->R * d->S * d->C, (uint64_t)d->R * d->S * d->C, kc, bn);
@@ -408,24 +447,24 @@ int a3d_tc_conv_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, con
     if (splits == 1) {
       q.epi = y_dtype == A3D_F32 ? tc::EPI_ROW_F32 : tc::EPI_ROW_BF16;
       q.out = y; q.ldo = d->ldy; q.bias = bias; q.flags = flags; q.atomic = 0;
-      return launch_kk(ctx, bn, kcb, tmA, tmB, q, 1, st);
+      return launch_kk(ctx, bn, kcb, tmA, tmB, q, 1, st, variant);
     }
     A3D_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)M * d->K * sizeof(float), st));
     q.epi = tc::EPI_ROW_F32; q.out = ws; q.ldo = d->K; q.bias = nullptr; q.flags = 0; q.atomic = 1;
-    r = launch_kk(ctx, bn, kcb, tmA, tmB, q, splits, st);
+    r = launch_kk(ctx, bn, kcb, tmA, tmB, q, splits, st, variant);
     if (r) return r;
     return finish(ctx, reinterpret_cast<const float*>(ws), bias, nullptr, 0.f, y, y_dtype == A3D_F32, (size_t)M, d->K,
                   d->ldy, flags, st);
   };
   auto tiles_of = [&](int bn) { return ceil_div(M, 128) * ceil_div(d->K, bn); };
   // candidate 0 = heuristic; then the tile widths that cover K with little padding, each with 1 and ~1-2 waves of split-K
-  struct Cand { int bn, splits; };
-  Cand cand[24];
+  struct Cand { int bn, splits, variant; };
+  Cand cand[64];
   int nc = 0;
   {
     int bn0 = pick_bn(d->K);
     if (kc == 8 && bn0 < 32) bn0 = 32;
-    cand[nc++] = {bn0, pick_splits(ctx, tiles_of(bn0), num_kb, 8)};
+    cand[nc++] = {bn0, pick_splits(ctx, tiles_of(bn0), num_kb, 8), V_BASE};
   }
   static const int widths[] = {64, 96, 128, 192, 256};
   for (int i = 0; i < 5; ++i) {
@@ -441,17 +480,26 @@ int a3d_tc_conv_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, con
       const int max_s = num_kb / 8 > 0 ? num_kb / 8 : 1;
       if (sp > max_s) sp = max_s;
       if (sp < 1 || !can_split) sp = 1;
-      bool dup = false;
-      for (int k = 0; k < nc; ++k) dup |= (cand[k].bn == bn && cand[k].splits == sp);
-      if (!dup && nc < 24) cand[nc++] = {bn, sp};
+      for (int variant = 0; variant < V_COUNT; ++variant) {
+        if (!variant_exists(bn, kcb, variant)) continue;
+        // 256-row tiles only unsplit and when they still give every SM about one CTA
+        if (variant >= V_BM256 && (sp != 1 || tiles / 2 < ctx->sm_count * 3 / 4)) continue;
+        bool dup = false;
+        for (int k = 0; k < nc; ++k) dup |= (cand[k].bn == bn && cand[k].splits == sp && cand[k].variant == variant);
+        if (!dup && nc < 64) cand[nc++] = {bn, sp, variant};
+      }
     }
+  }
+  if (const char* force = getenv("A3D_CONV_FORCE")) {            // "bn,splits,variant": tests and A/B runs
+    int fbn = 0, fsp = 1, fv = 0;
+    if (sscanf(force, "%d,%d,%d", &fbn, &fsp, &fv) >= 1 && fbn > 0) return launch(fbn, fsp, fv);
   }
   TuneKey key{};
   const int kv[16] = {2, d->N, d->H, d->W, d->C, d->K, d->R, d->S, d->stride_h, d->stride_w, d->pad_t, d->pad_l,
                       d->P, d->Q, d->ldy, y_dtype * 2 + (can_split ? 1 : 0)};
   memcpy(key.v, kv, sizeof(kv));
-  const int best = autotune(key, nc, [&](int c) { return launch(cand[c].bn, cand[c].splits); }, st);
-  return launch(cand[best].bn, cand[best].splits);
+  const int best = autotune(key, nc, [&](int c) { return launch(cand[c].bn, cand[c].splits, cand[c].variant); }, st);
+  return launch(cand[best].bn, cand[best].splits, cand[best].variant);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -478,8 +526,10 @@ int a3d_tc_dense_fwd(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t* w
   // weight streaming is HBM-bound: two CTAs' worth of loads in flight per SM helps, so oversubscribe
   if (splits0 * tiles < 2 * ctx->sm_count && p.num_kb / (splits0 * 2) >= 4) splits0 *= 2;
   p.epi = tc::EPI_COL_F32; p.out = acc_ws; p.ldo = N; p.bias = nullptr; p.flags = 0; p.atomic = 1;
-  auto launch = [&](int splits) -> int {
+  auto launch = [&](int splits) -> int {          // splits >= 1000: interleaved k-blocks (Params::kb_interleave)
     tc::Params q = p;
+    q.kb_interleave = splits >= 1000;
+    splits %= 1000;
     q.kb_per_split = ceil_div(q.num_kb, splits);
     splits = ceil_div(q.num_kb, q.kb_per_split);
     A3D_CHECK_CUDA(cudaMemsetAsync(acc_ws, 0, (size_t)M * N * sizeof(float), st));
@@ -487,12 +537,30 @@ int a3d_tc_dense_fwd(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t* w
     if (r) return r;
     return finish(ctx, acc_ws, bias, mask, drop_rate, y, y_dtype == A3D_F32, (size_t)M, N, N, flags, st);
   };
-  int cand[8];
-  const int nc = split_candidates(ctx, tiles, p.num_kb, splits0, cand);
+  // batch <= 32: the weight-streaming mma.sync kernel (dense_stream.cu) competes with the tcgen05 tiles;
+  // candidates >= 100 are stream launches with 1x / 2x / 3x the resident CTA slots
+  const int smode = a3d_stream_mode();
+  const bool s_ok = smode != 0 && a3d_stream_dense_fwd_ok(M, N, K, ldx);
+  auto launch_stream = [&](int ctas) -> int {
+    int r = a3d_stream_dense_fwd(ctx, x, ldx, w, acc_ws, M, N, K, ctas, st);
+    if (r) return r;
+    return finish(ctx, acc_ws, bias, mask, drop_rate, y, y_dtype == A3D_F32, (size_t)M, N, N, flags, st);
+  };
+  if (s_ok && smode == 2) return launch_stream(2 * ctx->sm_count);
+  int cand[24];
+  int nc = split_candidates(ctx, tiles, p.num_kb, splits0, cand);
+  for (int i = 0, n0 = nc; i < n0; ++i)
+    if (cand[i] > 1) cand[nc++] = 1000 + cand[i];
+  if (s_ok)
+    for (int m = 1; m <= 3; ++m) cand[nc++] = 100 + m;
+  auto run = [&](int c) -> int {
+    return c >= 100 && c < 1000 ? launch_stream((c - 100) * 2 * ctx->sm_count) : launch(c);
+  };
+  if (const char* force = getenv("A3D_DENSE_FORCE")) return run(atoi(force));   // tests: e.g. 1006 = 6 interleaved splits
   TuneKey key{};
-  const int kv[16] = {3, M, N, K, ldx, y_dtype, (int)flags, mask != nullptr};
+  const int kv[16] = {3, M, N, K, ldx, y_dtype, (int)flags, mask != nullptr, s_ok};
   memcpy(key.v, kv, sizeof(kv));
-  return launch(cand[autotune(key, nc, [&](int c) { return launch(cand[c]); }, st)]);
+  return run(cand[autotune(key, nc, [&](int c) { return run(cand[c]); }, st)]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -646,8 +714,10 @@ int a3d_tc_dense_dgrad(a3d_ctx* ctx, const uint16_t* dy, int lddy, const uint16_
   int splits0 = pick_splits(ctx, tiles, p.num_kb, 4);
   if (splits0 * tiles < 2 * ctx->sm_count && p.num_kb / (splits0 * 2) >= 4) splits0 *= 2;
   p.epi = tc::EPI_COL_F32; p.out = acc_ws; p.ldo = K; p.atomic = 1;
-  auto launch = [&](int splits) -> int {
+  auto launch = [&](int splits) -> int {          // splits >= 1000: interleaved k-blocks
     tc::Params q = p;
+    q.kb_interleave = splits >= 1000;
+    splits %= 1000;
     q.kb_per_split = ceil_div(q.num_kb, splits);
     splits = ceil_div(q.num_kb, q.kb_per_split);
     A3D_CHECK_CUDA(cudaMemsetAsync(acc_ws, 0, (size_t)M * K * sizeof(float), st));
@@ -658,12 +728,28 @@ int a3d_tc_dense_dgrad(a3d_ctx* ctx, const uint16_t* dy, int lddy, const uint16_
     if (r) return r;
     return finish(ctx, acc_ws, nullptr, nullptr, 0.f, dx, 0, (size_t)M, K, K, 0, st);
   };
-  int cand[8];
-  const int nc = split_candidates(ctx, tiles, p.num_kb, splits0, cand);
+  const int smode = a3d_stream_mode();
+  const bool s_ok = smode != 0 && a3d_stream_dense_dgrad_ok(M, N, K, lddy);
+  auto launch_stream = [&](int ctas) -> int {
+    int r = a3d_stream_dense_dgrad(ctx, dy, lddy, w, acc_ws, M, N, K, ctas, st);
+    if (r) return r;
+    return finish(ctx, acc_ws, nullptr, nullptr, 0.f, dx, 0, (size_t)M, K, K, 0, st);
+  };
+  if (s_ok && smode == 2) return launch_stream(2 * ctx->sm_count);
+  int cand[24];
+  int nc = split_candidates(ctx, tiles, p.num_kb, splits0, cand);
+  for (int i = 0, n0 = nc; i < n0; ++i)
+    if (cand[i] > 1) cand[nc++] = 1000 + cand[i];
+  if (s_ok)
+    for (int m = 1; m <= 3; ++m) cand[nc++] = 100 + m;
+  auto run = [&](int c) -> int {
+    return c >= 100 && c < 1000 ? launch_stream((c - 100) * 2 * ctx->sm_count) : launch(c);
+  };
+  if (const char* force = getenv("A3D_DENSE_FORCE")) return run(atoi(force));
   TuneKey key{};
-  const int kv[16] = {4, M, N, K, lddy};
+  const int kv[16] = {4, M, N, K, lddy, s_ok};
   memcpy(key.v, kv, sizeof(kv));
-  return launch(cand[autotune(key, nc, [&](int c) { return launch(cand[c]); }, st)]);
+  return run(cand[autotune(key, nc, [&](int c) { return run(cand[c]); }, st)]);
 }
 
 // wgrad: dw[n][k] = sum_b dy[b][n] x[b][k]; both operands MN-major with the batch as the reduction index.
@@ -703,8 +789,15 @@ int a3d_tc_dense_wgrad(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t*
 
 // Raw GEMM for unit tests of the engine: D[M][N] (f32, row-major) = A * B^T with every combination
 // of operand majors.  K-major operand: [rows][K]; MN-major operand: [K][rows].
+extern "C" int a3d_debug_tc_gemm_v(a3d_ctx* ctx, const uint16_t* A, const uint16_t* B, float* D, int M, int N, int K,
+                                   int bn, int kcb, int a_mn, int b_mn, int splits, int variant, void* stream);
 extern "C" int a3d_debug_tc_gemm(a3d_ctx* ctx, const uint16_t* A, const uint16_t* B, float* D, int M, int N, int K,
                                  int bn, int kcb, int a_mn, int b_mn, int splits, void* stream) {
+  return a3d_debug_tc_gemm_v(ctx, A, B, D, M, N, K, bn, kcb, a_mn, b_mn, splits, 0, stream);
+}
+// variant: tile variant of launch_kk (K-major x K-major only): 1 deeper ring, 2 256-row tile, 3 both
+extern "C" int a3d_debug_tc_gemm_v(a3d_ctx* ctx, const uint16_t* A, const uint16_t* B, float* D, int M, int N, int K,
+                                   int bn, int kcb, int a_mn, int b_mn, int splits, int variant, void* stream) {
   A3D_REQUIRE(ctx && A && B && D, "debug gemm: null argument");
   cudaStream_t st = as_stream(stream);
   CUtensorMap tmA, tmB;
@@ -724,7 +817,7 @@ extern "C" int a3d_debug_tc_gemm(a3d_ctx* ctx, const uint16_t* A, const uint16_t
   splits = ceil_div(p.num_kb, p.kb_per_split);
   p.epi = tc::EPI_ROW_F32; p.out = D; p.ldo = N; p.atomic = splits > 1;
   if (splits > 1) A3D_CHECK_CUDA(cudaMemsetAsync(D, 0, (size_t)M * N * sizeof(float), st));
-  if (!a_mn && !b_mn) return launch_kk(ctx, bn, kcb, tmA, tmB, p, splits, st);
+  if (!a_mn && !b_mn) return launch_kk(ctx, bn, kcb, tmA, tmB, p, splits, st, variant);
 #define A3D_MN_CASE(BN, AM, BM_) \
   if (bn == BN && (bool)a_mn == AM && (bool)b_mn == BM_) \
     return launch_cfg<tc::Cfg<BN, 128, AM, BM_>>(ctx, tmA, tmB, p, splits, st);

@@ -54,6 +54,9 @@ struct Params {
   int M, N;                 // valid rows of A / rows of B (GEMM M, N)
   int num_kb;               // k-blocks in total
   int kb_per_split;         // k-blocks handled by one blockIdx.z
+  int kb_interleave;        // split z takes k-blocks z, z + gridDim.z, ... instead of a contiguous range: the CTAs of
+                            // one row tile then read ADJACENT 128-byte pieces of the same rows at the same time
+                            // (DRAM page locality when a weight matrix is streamed once: dense fwd / dgrad)
   // A operand addressing
   int a_mode;
   int a_k0;                 // tiled: first K coordinate
@@ -77,19 +80,26 @@ struct Params {
   const float* lr_t_dev;
 };
 
-template <int BN_, int KCB_, bool A_MN_, bool B_MN_, int B_BW_ = 64, int MIN_STAGES_ = A3D_MIN_STAGES, bool ADAM_ = false>
+template <int BN_, int KCB_, bool A_MN_, bool B_MN_, int B_BW_ = 64, int MIN_STAGES_ = A3D_MIN_STAGES, bool ADAM_ = false,
+          int BM_ = 128>
 struct Cfg {
+  // BM = 256: the CTA owns TWO 128-row accumulators (TMEM columns [0,BN) and [BN,2BN)) that share every B stage:
+  // operand traffic per FLOP drops from (128+BN) to (256+BN)/2 rows per k-block -- the 5x5 layers are bound by
+  // L2->SM operand bandwidth (conv2d_1: 819 MB per launch at ~13 TB/s), not by the tensor pipe.  K-major A only.
+  static constexpr int MT = BM_ / 128;
+  static_assert(BM_ == 128 || (BM_ == 256 && !A_MN_ && KCB_ != 16 && !ADAM_), "BM = 256: K-major swizzled A only");
   static constexpr bool ADAM = ADAM_;                     // compile the EPI_ADAM epilogue (24 float4 loads in flight:
                                                           // 168 registers) only into the kernels that use it
   static constexpr int B_BW = B_BW_;                     // MN-major B: elements per block (64/32/16)
   static constexpr int B_BLK_BYTES = 64 * B_BW_ * 2;     // 64 K-rows x BW elements
   static constexpr int B_NBLK = BN_ / B_BW_;
-  static constexpr int BM = 128;
+  static constexpr int BM = BM_;
   static constexpr int BN = BN_;
   static constexpr int KCB = KCB_;                       // K-major: bytes of K per row per stage
   static constexpr bool A_MN = A_MN_, B_MN = B_MN_;
   static constexpr bool CHUNKED = (KCB_ == 16);           // 8 chunks of 16 B per stage, no swizzle
   static constexpr int KELEMS = (A_MN_ || B_MN_ || CHUNKED) ? 64 : KCB_ / 2;   // K elements per stage
+  static constexpr int A_SUB_BYTES = 128 * KCB_;            // one 128-row K-major sub-tile
   static constexpr int A_BYTES = A_MN_ ? 2 * 8192 : CHUNKED ? 8 * BM * 16 : BM * KCB_;
   static constexpr int B_BYTES = B_MN_ ? B_NBLK * B_BLK_BYTES : CHUNKED ? 8 * BN_ * 16 : BN_ * KCB_;
   static_assert(!CHUNKED || (!A_MN_ && !B_MN_), "chunked mode is K-major only");
@@ -98,7 +108,8 @@ struct Cfg {
   // stream) fit on one SM, so one CTA's epilogue / prologue hides under the others' main loops.
   static constexpr int STAGES_RAW = (A3D_RING_KB * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < MIN_STAGES_ ? MIN_STAGES_ : STAGES_RAW);
-  static constexpr int TMEM_COLS = BN_ <= 32 ? 32 : BN_ <= 64 ? 64 : BN_ <= 128 ? 128 : 256;
+  static constexpr int ACC_COLS = MT * BN_;
+  static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(!(A_MN_ || B_MN_) || KCB_ == 128, "MN-major operands use 128-byte rows");
   static_assert(!B_MN_ || BN_ % B_BW_ == 0, "MN-major B needs BN % BW == 0");
@@ -122,10 +133,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * C::BM;
   const int n0 = blockIdx.y * C::BN;
-  const int kb_begin = blockIdx.z * p.kb_per_split;
+  int kb_begin = blockIdx.z * p.kb_per_split, kb_step = 1;
   int kb_end = kb_begin + p.kb_per_split;
   if (kb_end > p.num_kb) kb_end = p.num_kb;
-  const int nkb = kb_end - kb_begin;      // host guarantees nkb >= 1
+  int nkb = kb_end - kb_begin;            // host guarantees nkb >= 1
+  if (p.kb_interleave) {
+    kb_begin = blockIdx.z;
+    kb_step = gridDim.z;
+    nkb = (p.num_kb - kb_begin + kb_step - 1) / kb_step;
+  }
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -147,6 +163,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int n_img = 0, h0 = 0, w0 = 0;
+      int n_img1 = 0, h01 = 0, w01 = 0;          // second 128-row sub-tile (BM = 256)
+      // a second sub-tile that starts beyond M is not loaded at all (its accumulator rows are never stored)
+      const bool sub1 = C::MT == 2 && m0 + 128 < p.M;
+      const uint32_t stage_tx = C::STAGE_BYTES - ((C::MT == 2 && !sub1) ? C::A_SUB_BYTES : 0);
       if (p.a_mode == A_IM2COL) {
         // first output pixel of this tile -> base coordinates in input space
         n_img = m0 / p.PQ;
@@ -154,15 +174,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         int p0 = rem / p.Q, q0 = rem - p0 * p.Q;
         h0 = p.lower_h + p0 * p.sh;
         w0 = p.lower_w + q0 * p.sw;
+        if (sub1) {
+          n_img1 = (m0 + 128) / p.PQ;
+          rem = m0 + 128 - n_img1 * p.PQ;
+          p0 = rem / p.Q; q0 = rem - p0 * p.Q;
+          h01 = p.lower_h + p0 * p.sh;
+          w01 = p.lower_w + q0 * p.sw;
+        }
       }
       for (int i = 0; i < nkb; ++i) {
-        const int kb = kb_begin + i;
+        const int kb = kb_begin + i * kb_step;
         const int stage = i % C::STAGES;
         const uint32_t phase = (i / C::STAGES) & 1;
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sA = smem + stage * C::STAGE_BYTES;
         uint8_t* sB = sA + C::A_BYTES;
-        ptx::mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+        ptx::mbar_expect_tx(&full_bar[stage], stage_tx);
         // ---- A
         if constexpr (C::CHUNKED) {
           // 8 im2col loads of 128 pixels x 8 channels (one per tap / channel-chunk), one 3-D load of B
@@ -178,11 +205,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         } else if constexpr (!C::A_MN) {
           if (p.a_mode == A_TILED) {
             ptx::tma_load_2d(sA, &tmA, &full_bar[stage], p.a_k0 + kb * C::KELEMS, m0);
+            if (sub1) ptx::tma_load_2d(sA + C::A_SUB_BYTES, &tmA, &full_bar[stage], p.a_k0 + kb * C::KELEMS, m0 + 128);
           } else {
             int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
             int r = tap / p.S, s = tap - r * p.S;
             ptx::tma_load_im2col_4d(sA, &tmA, &full_bar[stage], cb * C::KELEMS, w0, h0, n_img, (uint16_t)s,
                                     (uint16_t)r);
+            if (sub1)
+              ptx::tma_load_im2col_4d(sA + C::A_SUB_BYTES, &tmA, &full_bar[stage], cb * C::KELEMS, w01, h01, n_img1,
+                                      (uint16_t)s, (uint16_t)r);
           }
         } else {
           // MN-major A: global [K rows][M cols]; two 64-column boxes of 64 K-rows
@@ -220,7 +251,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(C::BM, C::BN, C::A_MN ? 1 : 0, C::B_MN ? 1 : 0);
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, C::BN, C::A_MN ? 1 : 0, C::B_MN ? 1 : 0);
       constexpr uint32_t k_layout =
           C::KCB == 128 ? ptx::LAYOUT_SW128 : C::KCB == 64 ? ptx::LAYOUT_SW64 : ptx::LAYOUT_SW32;
       for (int i = 0; i < nkb; ++i) {
@@ -246,9 +277,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         constexpr uint32_t b_step =
             C::B_MN ? ((16 * C::B_BW * 2) >> 4) : C::CHUNKED ? ((2 * C::BN * 16) >> 4) : (32 >> 4);
 #pragma unroll
-        for (int k = 0; k < C::KELEMS / 16; ++k)
+        for (int k = 0; k < C::KELEMS / 16; ++k) {
           ptx::umma_bf16(tmem_base, a_desc + (uint64_t)(k * a_step), b_desc + (uint64_t)(k * b_step), idesc,
                          (uint32_t)((i | k) != 0));
+          if constexpr (C::MT == 2)              // second accumulator: next 128 rows of A, same B stage
+            ptx::umma_bf16(tmem_base + (uint32_t)C::BN, a_desc + (uint64_t)((C::A_SUB_BYTES >> 4) + k * a_step),
+                           b_desc + (uint64_t)(k * b_step), idesc, (uint32_t)((i | k) != 0));
+        }
         ptx::umma_commit(&empty_bar[stage]);       // frees the smem stage when these MMAs retire
       }
       ptx::umma_commit(tmem_full_bar);             // accumulator complete
@@ -258,6 +293,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
     ptx::mbar_wait(tmem_full_bar, 0);
     ptx::tc_fence_after_sync();
+    const int m0_cta = m0;
+    const uint32_t tmem_cta = tmem_base;
+#pragma unroll 1
+    for (int mt = 0; mt < C::MT; ++mt) {           // one pass per 128-row accumulator
+    const int m0 = m0_cta + mt * 128;
+    if (m0 >= p.M) break;                          // warp-uniform
+    const uint32_t tmem_base = tmem_cta + (uint32_t)(mt * C::BN);
     const int row = m0 + quarter * 32 + lane;
     const bool row_ok = row < p.M;
     int c_begin = 0;
@@ -566,6 +608,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     }
+    }  // mt
   }
 
   ptx::tc_fence_before_sync();

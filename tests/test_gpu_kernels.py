@@ -62,6 +62,22 @@ def test_tc_gemm_kmajor_splitk_long(ctx):
     assert rel_err(ctx.debug_tc_gemm(A, B, M, N, K, 128, 128, splits=5), ref) < 2e-3
 
 
+@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("bn", [64, 96, 128, 256])
+@pytest.mark.parametrize("M", [300, 512, 129, 1000])
+def test_tc_gemm_tile_variants(ctx, variant, bn, M):
+    """deeper stage rings and 256-row (two-accumulator) tiles; M values leave the second sub-tile empty (129 -> one
+    row), partial (300) or absent for the last CTA (1000 = 3 x 256 + 232)"""
+    N, K = bn - 8, 64 * 7
+    A = bf16_rand(M, K, seed=7)
+    B = bf16_rand(N, K, seed=8)
+    D = ctx.debug_tc_gemm(A, B, M, N, K, bn, 128, variant=variant)
+    assert rel_err(D, A.float() @ B.float().t()) < 2e-3
+    if variant >= 2:
+        D = ctx.debug_tc_gemm(A, B, M, N, K, bn, 128, splits=3, variant=variant)
+        assert rel_err(D, A.float() @ B.float().t()) < 2e-3
+
+
 @pytest.mark.parametrize("a_mn,b_mn,bn", [(True, True, 128), (True, True, 64), (True, True, 256),
                                           (True, False, 32), (True, False, 128), (False, True, 128)])
 def test_tc_gemm_mn_major(ctx, a_mn, b_mn, bn):
@@ -134,6 +150,32 @@ def test_conv_fwd(ctx, layer, impl):
     yf = ctx.conv2d_fwd(d, x, w, bias, relu=False, out_dtype=torch.float32)
     ref = torch_conv_ref(x, w, bias, stride, d.pad_t, d.pad_l, d.P, d.Q, False)
     assert rel_err(yf, ref) < 2e-3
+
+
+LAYERS_BY_NAME = {l[0]: l for l in LAYERS}
+
+
+@pytest.mark.parametrize("force", ["128,1,1", "128,1,2", "256,1,2", "256,1,3", "64,1,2", "96,1,3"])
+@pytest.mark.parametrize("layer", [LAYERS_BY_NAME[n] for n in ("conv2d_1", "fine_second", "conv2d_0_s2d4", "dcnf_conv2d_1")],
+                         ids=["conv2d_1", "fine_second", "conv2d_0_s2d4", "dcnf_conv2d_1"])
+def test_conv_fwd_tile_variants(ctx, monkeypatch, layer, force):
+    """im2col-mode A operand with 256-row tiles: the second sub-tile has its own (image, row, column) origin"""
+    name, H, W, Cc, K, R, S, stride, padding = layer
+    if int(force.split(",")[0]) > K + K // 3 + 15 and K > 64:
+        pytest.skip("tile wider than the layer")
+    Cc = (Cc + 63) // 64 * 64              # the tile variants exist for 128-byte channel blocks (conv2d_1 is stored with 128)
+    N = 3
+    d = ops.conv_desc(N, H, W, Cc, K, R, S, stride, padding, impl=L.IMPL_TC)
+    x = bf16_rand(N, H, W, Cc, seed=10)
+    w = bf16_rand(K, R, S, Cc, seed=11, scale=1.0 / math.sqrt(R * S * Cc))
+    bias = (torch.rand(K, generator=torch.Generator().manual_seed(12)) - 0.5).to(DEV)
+    monkeypatch.setenv("A3D_CONV_FORCE", force)
+    yf = ctx.conv2d_fwd(d, x, w, bias, relu=False, out_dtype=torch.float32)
+    yb = ctx.conv2d_fwd(d, x, w, bias, relu=True)
+    monkeypatch.delenv("A3D_CONV_FORCE")
+    ref = torch_conv_ref(x, w, bias, stride, d.pad_t, d.pad_l, d.P, d.Q, False)
+    assert rel_err(yf, ref) < 2e-3
+    assert rel_err(yb, torch.relu(ref)) < 1e-2
 
 
 @pytest.mark.parametrize("layer", SMALL_C_LAYERS, ids=[l[0] for l in SMALL_C_LAYERS])
@@ -237,6 +279,67 @@ def test_dense_bwd(ctx, M, N, K, ld, impl):
     dw, _ = ctx.dense_wgrad(x, dyp, db=db, N=N, impl=code)
     assert rel_err(dw, dy.float().t() @ x.float()) < 2e-3
     assert rel_err(db, dy.float().sum(0)) < 2e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(32, 4096, 12288), (32, 4070, 4096), (7, 300, 192), (32, 256, 64), (1, 4070, 4096)])
+def test_dense_stream_kernels(ctx, monkeypatch, M, N, K):
+    """csrc/dense_stream.cu (weight-streaming mma.sync path for batch <= 32), forced with A3D_DENSE_STREAM=2,
+    against fp32 evaluation of the same bf16 operands and against the tcgen05 path (A3D_DENSE_STREAM=0)."""
+    x = bf16_rand(M, K, seed=40)
+    w = bf16_rand(N, K, seed=41, scale=1.0 / math.sqrt(K))
+    bias = (torch.rand(N, generator=torch.Generator().manual_seed(42)) - 0.5).to(DEV)
+    mask = (torch.rand(M, N, generator=torch.Generator().manual_seed(43)) < 0.5).to(torch.uint8).to(DEV)
+    ld = (N + 7) // 8 * 8 + 8
+    dyp = torch.full((M, ld), float("nan"), dtype=torch.bfloat16, device=DEV)     # padding must never be read as data
+    dyp[:, :N] = bf16_rand(M, N, seed=44)
+    dy = dyp[:, :N]
+    out = {}
+    for mode in ("2", "0"):
+        monkeypatch.setenv("A3D_DENSE_STREAM", mode)
+        n0 = ctx.launches
+        y = ctx.dense_fwd(x, w, bias, flags=L.EPI_RELU, keep_mask=mask, drop_rate=0.5, out_dtype=torch.float32, impl=L.IMPL_TC)
+        dx = ctx.dense_dgrad(dyp, w, impl=L.IMPL_TC)
+        torch.cuda.synchronize()
+        assert ctx.launches > n0
+        out[mode] = (y, dx)
+    ref_y = torch.relu(x.float() @ w.float().t() + bias) * mask.float() * 2.0
+    ref_dx = dy.float() @ w.float()
+    for mode in ("2", "0"):
+        assert rel_err(out[mode][0], ref_y) < 2e-3, mode
+        assert rel_err(out[mode][1], ref_dx) < 1e-2, mode
+    assert rel_err(out["2"][0], out["0"][0]) < 1e-3
+
+
+@pytest.mark.parametrize("H,W,R,pad", [(55, 74, 5, "same"), (9, 13, 3, "same"), (12, 20, 5, "valid"), (3, 150, 5, "same")])
+def test_conv_k1_tiled(ctx, monkeypatch, H, W, R, pad):
+    """single-filter 64-channel convolution (MSDN fine/third): tiled mma.sync kernel vs torch and vs the GEMM path"""
+    N, Cc = 3, 64
+    d = ops.conv_desc(N, H, W, Cc, 1, R, R, 1, pad)
+    x = bf16_rand(N, H, W, Cc, seed=50)
+    w = bf16_rand(1, R, R, Cc, seed=51, scale=1.0 / math.sqrt(R * R * Cc))
+    bias = torch.tensor([0.37], device=DEV)
+    ref = torch_conv_ref(x, w, bias, 1, d.pad_t, d.pad_l, d.P, d.Q, False)
+    y = ctx.conv2d_fwd(d, x, w, bias, relu=False, out_dtype=torch.float32)
+    assert y.shape == ref.shape
+    assert rel_err(y, ref) < 2e-3
+    yr = ctx.conv2d_fwd(d, x, w, bias, relu=True)
+    assert rel_err(yr, torch.relu(ref)) < 1e-2
+
+
+@pytest.mark.parametrize("force", ["6", "1006", "1011", "1001"])
+def test_dense_interleaved_splits(ctx, monkeypatch, force):
+    """split-K with interleaved k-blocks (Params::kb_interleave) against contiguous ranges and fp32"""
+    M, N, K = 32, 4070, 4096
+    x = bf16_rand(M, K, seed=45)
+    w = bf16_rand(N, K, seed=46, scale=1.0 / math.sqrt(K))
+    dyp = torch.zeros(M, 4096, dtype=torch.bfloat16, device=DEV)
+    dyp[:, :N] = bf16_rand(M, N, seed=47)
+    monkeypatch.setenv("A3D_DENSE_FORCE", force)
+    y = ctx.dense_fwd(x, w, None, flags=0, out_dtype=torch.float32, impl=L.IMPL_TC)
+    dx = ctx.dense_dgrad(dyp, w, impl=L.IMPL_TC)
+    monkeypatch.delenv("A3D_DENSE_FORCE")
+    assert rel_err(y, x.float() @ w.float().t()) < 2e-3
+    assert rel_err(dx, dyp[:, :N].float() @ w.float()) < 1e-2
 
 
 def test_dense_bwd_unaligned_falls_back(ctx):
