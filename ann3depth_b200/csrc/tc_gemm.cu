@@ -571,10 +571,10 @@ int a3d_tc_dense_fwd(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t* w
 //   B = X in im2col mode, 64 pixels x BW channels per (tap, channel-block)
 // split-K over the pixel range with fp32 atomics into the (zeroed) dW.
 namespace {
-template <int BW, int NBLK>
+template <int BW, int NBLK, int BM = 128>
 int launch_wgrad(a3d_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const tc::Params& p, int splits,
                  cudaStream_t st) {
-  return launch_cfg<tc::Cfg<BW * NBLK, 128, true, true, BW>>(ctx, tmA, tmB, p, splits, st);
+  return launch_cfg<tc::Cfg<BW * NBLK, 128, true, true, BW, A3D_MIN_STAGES, false, BM>>(ctx, tmA, tmB, p, splits, st);
 }
 int pick_nblk(int bw, int total_blocks) {
   static const int c64[] = {4, 3, 2, 1, 0}, c32[] = {6, 5, 4, 3, 0}, c16[] = {16, 11, 8, 0};
@@ -619,12 +619,21 @@ int a3d_tc_conv_wgrad(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, c
   p.S = d->S; p.cblocks = cblocks;
   p.epi = tc::EPI_ROW_F32; p.out = dw; p.ldo = (long long)RS * d->C;
 
-  auto launch = [&](int nblk, int splits) -> int {
+  // bm = 256: 256 filters per CTA, i.e. two accumulators share every im2col stage of X (the expensive operand)
+  auto launch = [&](int nblk, int splits, int bm = 128) -> int {
     tc::Params q = p;
     q.kb_per_split = ceil_div(q.num_kb, splits);
     splits = ceil_div(q.num_kb, q.kb_per_split);
     q.atomic = splits > 1;
     if (splits > 1) A3D_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)d->K * RS * d->C * sizeof(float), st));
+    if (bm == 256) {
+      if (bw == 64 && nblk == 4) return launch_wgrad<64, 4, 256>(ctx, tmA, tmB, q, splits, st);
+      if (bw == 64 && nblk == 3) return launch_wgrad<64, 3, 256>(ctx, tmA, tmB, q, splits, st);
+      if (bw == 64 && nblk == 2) return launch_wgrad<64, 2, 256>(ctx, tmA, tmB, q, splits, st);
+      if (bw == 64 && nblk == 1) return launch_wgrad<64, 1, 256>(ctx, tmA, tmB, q, splits, st);
+      a3d_set_error("tc conv wgrad: no 256-row kernel for BW=%d NBLK=%d", bw, nblk);
+      return A3D_ENOTSUP;
+    }
 #define A3D_WG(BW, NB) if (bw == BW && nblk == NB) return launch_wgrad<BW, NB>(ctx, tmA, tmB, q, splits, st);
     A3D_WG(64, 4) A3D_WG(64, 3) A3D_WG(64, 2) A3D_WG(64, 1)
     A3D_WG(32, 6) A3D_WG(32, 5) A3D_WG(32, 4) A3D_WG(32, 3)
@@ -633,40 +642,51 @@ int a3d_tc_conv_wgrad(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, c
     a3d_set_error("tc conv wgrad: no kernel for BW=%d NBLK=%d", bw, nblk);
     return A3D_ENOTSUP;
   };
-  auto tiles_of = [&](int nblk) { return ceil_div(d->K, 128) * ceil_div(total_blocks, nblk); };
+  auto tiles_of = [&](int nblk, int bm = 128) { return ceil_div(d->K, bm) * ceil_div(total_blocks, nblk); };
+  static int bm_env = -1;
+  if (bm_env < 0) { const char* e = getenv("A3D_WGRAD_BM"); bm_env = e ? atoi(e) : 0; }
+  if (const char* force = getenv("A3D_WGRAD_FORCE")) {           // "nblk,splits,bm": tests and A/B runs
+    int fn = 0, fs = 1, fb = 128;
+    if (sscanf(force, "%d,%d,%d", &fn, &fs, &fb) >= 1 && fn > 0) return launch(fn, fs, fb);
+  }
   if (nblk_env > 0 || splits_env > 0) {
     const int nblk = nblk_env > 0 ? nblk_env : pick_nblk(bw, total_blocks);
-    return launch(nblk, splits_env > 0 ? splits_env : pick_splits(ctx, tiles_of(nblk), p.num_kb, 4));
+    const int bm = bm_env == 256 && bw == 64 && nblk <= 4 ? 256 : 128;
+    return launch(nblk, splits_env > 0 ? splits_env : pick_splits(ctx, tiles_of(nblk, bm), p.num_kb, 4), bm);
   }
-  // candidates: candidate 0 is the heuristic; then every tile width x {1, 1.5, 2, 3} waves' worth of CTAs
-  struct Cand { int nblk, splits; };
-  Cand cand[40];
+  // candidates: candidate 0 is the heuristic; then every tile width x {1, 1.5, 2, 3} waves' worth of CTAs,
+  // with 128 and (layers with > 128 filters, 64-channel blocks) 256 filters per CTA
+  struct Cand { int nblk, splits, bm; };
+  Cand cand[80];
   int nc = 0;
   {
     const int nb0 = pick_nblk(bw, total_blocks);
-    cand[nc++] = {nb0, pick_splits(ctx, tiles_of(nb0), p.num_kb, 4)};
+    cand[nc++] = {nb0, pick_splits(ctx, tiles_of(nb0), p.num_kb, 4), 128};
   }
   static const int w64[] = {1, 2, 3, 4, 0}, w32[] = {3, 4, 5, 6, 0}, w16[] = {8, 11, 16, 0};
   const int* widths = bw == 64 ? w64 : bw == 32 ? w32 : w16;
-  for (int i = 0; widths[i]; ++i) {
-    const int tiles = tiles_of(widths[i]);
-    static const int target_x2[] = {2, 3, 4, 6};      // CTAs ~ target/2 x SM count
-    for (int t = 0; t < 4; ++t) {
-      int s = (ctx->sm_count * target_x2[t] / 2) / tiles;
-      const int max_s = p.num_kb / 4 > 0 ? p.num_kb / 4 : 1;
-      if (s > max_s) s = max_s;
-      if (s < 1) s = 1;
-      bool dup = false;
-      for (int k = 0; k < nc; ++k) dup |= (cand[k].nblk == widths[i] && cand[k].splits == s);
-      if (!dup && nc < 40) cand[nc++] = {widths[i], s};
+  for (int bm = 128; bm <= 256; bm += 128) {
+    if (bm == 256 && (bw != 64 || d->K <= 128)) continue;
+    for (int i = 0; widths[i]; ++i) {
+      const int tiles = tiles_of(widths[i], bm);
+      static const int target_x2[] = {2, 3, 4, 6};      // CTAs ~ target/2 x SM count
+      for (int t = 0; t < 4; ++t) {
+        int s = (ctx->sm_count * target_x2[t] / 2) / tiles;
+        const int max_s = p.num_kb / 4 > 0 ? p.num_kb / 4 : 1;
+        if (s > max_s) s = max_s;
+        if (s < 1) s = 1;
+        bool dup = false;
+        for (int k = 0; k < nc; ++k) dup |= (cand[k].nblk == widths[i] && cand[k].splits == s && cand[k].bm == bm);
+        if (!dup && nc < 80) cand[nc++] = {widths[i], s, bm};
+      }
     }
   }
   TuneKey key{};
   const int kv[16] = {1, d->N, d->H, d->W, d->C, d->K, d->R, d->S, d->stride_h, d->stride_w, d->pad_t, d->pad_l,
                       d->P, d->Q, d->ldy, 0};
   memcpy(key.v, kv, sizeof(kv));
-  const int best = autotune(key, nc, [&](int c) { return launch(cand[c].nblk, cand[c].splits); }, st);
-  return launch(cand[best].nblk, cand[best].splits);
+  const int best = autotune(key, nc, [&](int c) { return launch(cand[c].nblk, cand[c].splits, cand[c].bm); }, st);
+  return launch(cand[best].nblk, cand[best].splits, cand[best].bm);
 }
 
 // ------------------------------------------------------------------------------------------------

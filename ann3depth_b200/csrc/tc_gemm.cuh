@@ -87,7 +87,7 @@ struct Cfg {
   // operand traffic per FLOP drops from (128+BN) to (256+BN)/2 rows per k-block -- the 5x5 layers are bound by
   // L2->SM operand bandwidth (conv2d_1: 819 MB per launch at ~13 TB/s), not by the tensor pipe.  K-major A only.
   static constexpr int MT = BM_ / 128;
-  static_assert(BM_ == 128 || (BM_ == 256 && !A_MN_ && KCB_ != 16 && !ADAM_), "BM = 256: K-major swizzled A only");
+  static_assert(BM_ == 128 || (BM_ == 256 && KCB_ != 16 && !ADAM_), "BM = 256: swizzled A, no Adam epilogue");
   static constexpr bool ADAM = ADAM_;                     // compile the EPI_ADAM epilogue (24 float4 loads in flight:
                                                           // 168 registers) only into the kernels that use it
   static constexpr int B_BW = B_BW_;                     // MN-major B: elements per block (64/32/16)
@@ -99,8 +99,8 @@ struct Cfg {
   static constexpr bool A_MN = A_MN_, B_MN = B_MN_;
   static constexpr bool CHUNKED = (KCB_ == 16);           // 8 chunks of 16 B per stage, no swizzle
   static constexpr int KELEMS = (A_MN_ || B_MN_ || CHUNKED) ? 64 : KCB_ / 2;   // K elements per stage
-  static constexpr int A_SUB_BYTES = 128 * KCB_;            // one 128-row K-major sub-tile
-  static constexpr int A_BYTES = A_MN_ ? 2 * 8192 : CHUNKED ? 8 * BM * 16 : BM * KCB_;
+  static constexpr int A_SUB_BYTES = A_MN_ ? 2 * 8192 : 128 * KCB_;      // one 128-row sub-tile
+  static constexpr int A_BYTES = A_MN_ ? MT * 2 * 8192 : CHUNKED ? 8 * BM * 16 : BM * KCB_;
   static constexpr int B_BYTES = B_MN_ ? B_NBLK * B_BLK_BYTES : CHUNKED ? 8 * BN_ * 16 : BN_ * KCB_;
   static_assert(!CHUNKED || (!A_MN_ && !B_MN_), "chunked mode is K-major only");
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -219,6 +219,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           // MN-major A: global [K rows][M cols]; two 64-column boxes of 64 K-rows
           ptx::tma_load_2d(sA, &tmA, &full_bar[stage], m0, kb * 64);
           ptx::tma_load_2d(sA + 8192, &tmA, &full_bar[stage], m0 + 64, kb * 64);
+          if (sub1) {
+            ptx::tma_load_2d(sA + 16384, &tmA, &full_bar[stage], m0 + 128, kb * 64);
+            ptx::tma_load_2d(sA + 24576, &tmA, &full_bar[stage], m0 + 192, kb * 64);
+          }
         }
         // ---- B
         if constexpr (C::CHUNKED) {

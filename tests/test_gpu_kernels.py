@@ -248,6 +248,32 @@ def test_conv_dgrad_wgrad(ctx, layer, impl):
     assert rel_err(db, dy.float().sum((0, 1, 2))) < 2e-3
 
 
+@pytest.mark.parametrize("force", ["4,1,256", "2,5,256", "3,2,256", "1,3,256"])
+@pytest.mark.parametrize("layer", [("k256", 27, 37, 128, 256, 5, 5, 1, "same"), ("k384", 13, 18, 256, 384, 3, 3, 1, "same"),
+                                   ("k256_s2", 13, 18, 384, 256, 3, 3, 2, "valid")], ids=["k256", "k384", "k256_s2"])
+def test_conv_wgrad_256_filter_tiles(ctx, monkeypatch, layer, force):
+    """weight gradient with two 128-filter accumulators per CTA sharing the im2col stages of X (MN-major A, BM = 256);
+    384 filters = one full and one half tile"""
+    name, H, W, Cc, K, R, S, stride, padding = layer
+    N = 3
+    d = ops.conv_desc(N, H, W, Cc, K, R, S, stride, padding, impl=L.IMPL_TC)
+    x = bf16_rand(N, H, W, Cc, seed=20)
+    dy = bf16_rand(N, d.P, d.Q, K, seed=21)
+    monkeypatch.setenv("A3D_WGRAD_FORCE", force)
+    dw, _ = ctx.conv2d_wgrad(d, x, dy)
+    monkeypatch.setenv("A3D_WGRAD_FORCE", force.replace(",256", ",128"))
+    dw_ref, _ = ctx.conv2d_wgrad(d, x, dy)
+    monkeypatch.delenv("A3D_WGRAD_FORCE")
+    wr = torch.zeros(K, R, S, Cc, device=DEV).requires_grad_(True)
+    pb = max((d.P - 1) * stride + R - H - d.pad_t, 0)
+    pr = max((d.Q - 1) * stride + S - W - d.pad_l, 0)
+    yr = F.conv2d(F.pad(x.float().permute(0, 3, 1, 2), (d.pad_l, pr, d.pad_t, pb)), wr.permute(0, 3, 1, 2), None,
+                  stride=stride)[:, :, :d.P, :d.Q]
+    (gw,) = torch.autograd.grad(yr, (wr,), dy.float().permute(0, 3, 1, 2))
+    assert rel_err(dw, gw) < 2e-3
+    assert rel_err(dw, dw_ref) < 1e-3
+
+
 # ----------------------------------------------------------------------------- dense
 @pytest.mark.parametrize("impl", ["simt", "tc"])
 @pytest.mark.parametrize("M,N,K", [(32, 4096, 12288), (32, 4070, 4096), (8, 128, 12544), (5, 200, 256)])
