@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("A3D_LIB") or os.path.join(_HERE, "liba3d.so")     # A3D_LIB: alternate build (experiments)
 
 A3D_F32, A3D_BF16 = 0, 1
+A3D_ENOTSUP = -5
 IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
 EPI_RELU, EPI_SIGMOID = 1, 2
 OP_FWD, OP_DGRAD, OP_WGRAD = 0, 1, 2
@@ -46,6 +47,8 @@ SIGNATURES = {
     "a3d_conv2d_ws_bytes": (_sz, [_vp, C.POINTER(ConvDesc), _i]),
     "a3d_conv2d_fwd": (_i, [_vp, C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _i, _u, _vp, _sz, _vp]),
     "a3d_conv2d_dgrad": (_i, [_vp, C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "a3d_conv2d_dgrad_prepare": (_i, [_vp, C.POINTER(ConvDesc), _vp, _vp, _vp]),
+    "a3d_conv2d_dgrad_prepared": (_i, [_vp, C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "a3d_conv2d_wgrad": (_i, [_vp, C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "a3d_dense_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _i, _vp, _i, _i, _i, _u, _i, _vp]),
     "a3d_dense_dgrad": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

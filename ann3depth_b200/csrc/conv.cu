@@ -304,7 +304,51 @@ extern "C" int a3d_conv2d_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16
 }
 
 static int dgrad_impl(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* dy, const uint16_t* w, uint16_t* dx,
-                      const uint16_t* relu_src, bool* relu_done, void* ws, size_t ws_bytes, cudaStream_t st);
+                      const uint16_t* relu_src, bool* relu_done, void* ws, size_t ws_bytes, cudaStream_t st,
+                      const uint16_t* wflip = nullptr);
+
+static int launch_flip(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* w, uint16_t* wd, cudaStream_t st) {
+  size_t total = (size_t)d->K * d->R * d->S * d->C;
+  int grid = (int)((total + 255) / 256);
+  if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+  flip_filter_kernel<<<grid, 256, 0, st>>>(w, wd, d->K, d->R * d->S, d->C);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
+// The dgrad of a stride-1 convolution runs as a forward convolution of dY with the spatially flipped,
+// channel-transposed filter.  The flip depends only on the weights, so a training loop can take it off the
+// backward critical path: prepare it (on any stream) once the weights of the step are final, then call
+// a3d_conv2d_dgrad_prepared.  Returns A3D_ENOTSUP when this shape's dgrad does not use a flipped filter.
+extern "C" int a3d_conv2d_dgrad_prepare(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* w, uint16_t* wflip,
+                                        void* stream) {
+  A3D_REQUIRE(ctx && w && wflip, "conv dgrad prepare: null argument");
+  int rc = check_desc(d);
+  if (rc) return rc;
+  if (d->impl == A3D_IMPL_SIMT || !dgrad_as_fwd_ok(d)) {
+    a3d_set_error("conv dgrad prepare: this shape's dgrad does not use a flipped filter");
+    return A3D_ENOTSUP;
+  }
+  return launch_flip(ctx, d, w, wflip, as_stream(stream));
+}
+
+extern "C" int a3d_conv2d_dgrad_prepared(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* dy, const uint16_t* wflip,
+                                         uint16_t* dx, const uint16_t* relu_src, void* ws, size_t ws_bytes,
+                                         void* stream) {
+  A3D_REQUIRE(ctx && dy && wflip && dx, "conv dgrad (prepared): null argument");
+  int rc = check_desc(d);
+  if (rc) return rc;
+  A3D_REQUIRE(d->impl != A3D_IMPL_SIMT && dgrad_as_fwd_ok(d), "conv dgrad (prepared): shape has no flipped-filter dgrad");
+  cudaStream_t st = as_stream(stream);
+  bool relu_done = false;
+  rc = dgrad_impl(ctx, d, dy, nullptr, dx, relu_src, &relu_done, ws, ws_bytes, st, wflip);
+  if (rc) return rc;
+  if (relu_src && !relu_done) {
+    A3D_REQUIRE(d->C % 8 == 0, "conv dgrad: fused ReluGrad needs C %% 8 == 0");
+    return a3d_relu_bwd(ctx, relu_src, dx, d->C, dx, (size_t)d->N * d->H * d->W, d->C, st);     // in place
+  }
+  return 0;
+}
 
 extern "C" int a3d_conv2d_dgrad(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* dy, const uint16_t* w,
                                 uint16_t* dx, const uint16_t* relu_src, void* ws, size_t ws_bytes, void* stream) {
@@ -323,9 +367,18 @@ extern "C" int a3d_conv2d_dgrad(a3d_ctx* ctx, const a3d_conv_desc* d, const uint
 }
 
 static int dgrad_impl(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* dy, const uint16_t* w, uint16_t* dx,
-                      const uint16_t* relu_src, bool* relu_done, void* ws, size_t ws_bytes, cudaStream_t st) {
+                      const uint16_t* relu_src, bool* relu_done, void* ws, size_t ws_bytes, cudaStream_t st,
+                      const uint16_t* wflip) {
   int rc = 0;
   const size_t filt = filt_bytes(d);
+  if (wflip) {                                   // filter already flipped by a3d_conv2d_dgrad_prepare
+    a3d_conv_desc e = *d;
+    e.H = d->P; e.W = d->Q; e.C = d->K;          // "input" is dy
+    e.K = d->C; e.P = d->H; e.Q = d->W; e.ldy = d->C;
+    e.pad_t = d->R - 1 - d->pad_t; e.pad_l = d->S - 1 - d->pad_l;
+    e.stride_h = e.stride_w = 1;
+    return a3d_tc_conv_fwd(ctx, &e, dy, wflip, nullptr, dx, A3D_BF16, 0, ws, ws_bytes, st);
+  }
   if (d->impl != A3D_IMPL_SIMT && dgrad_as_fwd_ok(d)) {
     const int pt2 = d->R - 1 - d->pad_t, pl2 = d->S - 1 - d->pad_l;
     int Wp = d->W + d->S - 1; if (Wp < d->Q + pl2) Wp = d->Q + pl2;
@@ -339,11 +392,8 @@ static int dgrad_impl(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* dy, 
   }
   if (d->impl != A3D_IMPL_SIMT && dgrad_as_fwd_ok(d) && ws && ws_bytes >= filt) {
     uint16_t* wd = reinterpret_cast<uint16_t*>(ws);
-    size_t total = (size_t)d->K * d->R * d->S * d->C;
-    int grid = (int)((total + 255) / 256);
-    if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
-    flip_filter_kernel<<<grid, 256, 0, st>>>(w, wd, d->K, d->R * d->S, d->C);
-    A3D_LAUNCH_OK(ctx);
+    rc = launch_flip(ctx, d, w, wd, st);
+    if (rc) return rc;
     a3d_conv_desc e = *d;
     e.H = d->P; e.W = d->Q; e.C = d->K;          // "input" is dy
     e.K = d->C; e.P = d->H; e.Q = d->W; e.ldy = d->C;

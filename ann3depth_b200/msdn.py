@@ -54,6 +54,7 @@ class MSDNNet:
             fuse_dense_adam = os.environ["A3D_FUSE_DENSE_ADAM"] != "0"
         self.fuse_dense_adam = fuse_dense_adam
         self._s_fine = self._s_wgrad = self._s_cwgrad = None
+        self._wflip = None            # flipped filters of the stride-1 dgrads (refreshed at the start of every step)
         self.dev = torch.device(f"cuda:{ctx.device}")
         self.in_hw, self.depth_hw = in_hw, depth_hw
         self.comm = comm                      # data-parallel hook (ann3depth_b200.dp.DataParallel) or None
@@ -357,6 +358,8 @@ class MSDNNet:
             return e
 
         # ---- fine stream, part 0: what the critical path needs only later (depth target, dropout mask)
+        n0 = "coarse/conv/conv2d_"
+        prep = os.environ.get("A3D_DGRAD_PREPARE", "1") != "0"
         e_start = mark(s0)
         with torch.cuda.stream(s1):
             s1.wait_event(e_start)
@@ -364,6 +367,16 @@ class MSDNNet:
             if not self.external_mask:
                 c.bernoulli_mask(self.keep_mask, 0.5, self.dropout_seed, self.step_dev)
             e_aux = mark(s1)
+            # flipped filters of the stride-1 dgrads (weights are final since the previous step's Adam): three small
+            # transposes that used to sit inside the dgrad chain
+            if self._wflip is None:
+                self._wflip = {}
+                for i, dsc in (("3", self.d_c3), ("2", self.d_c2), ("1", self.d_c1)):
+                    self._wflip[i] = c.conv2d_dgrad_prepare(dsc, self.w(n0 + i + K)) if prep else None
+            for i, dsc in (("3", self.d_c3), ("2", self.d_c2), ("1", self.d_c1)):
+                if self._wflip[i] is not None:
+                    c.conv2d_dgrad_prepare(dsc, self.w(n0 + i + K), out=self._wflip[i])
+            e_flip = mark(s1)
         # ---- main: preprocessing
         c.resize_bilinear_tf1_s2d(self.images, IN_H, IN_W, 4, out=self.img4)
         e_img = mark(s0)
@@ -417,6 +430,18 @@ class MSDNNet:
 
         fused = self.fuse_dense_adam and not self.comm
         a = self.arena
+        # Single GPU: the bias gradients (latency-bound column sums of dY, 7-10 us each) leave the conv-wgrad stream
+        # for the fine stream, whose forward work is long done by then: they run next to the wgrad GEMMs, not before them.
+        side_bias = (not self.comm) and s1 is not s0 and os.environ.get("A3D_SIDE_BIAS", "1") != "0"
+
+        def conv_wgrad(desc, x, dy, name, event):
+            if side_bias:
+                with torch.cuda.stream(s1):
+                    s1.wait_event(event)
+                    c.bias_grad_bf16(dy.view(-1, dy.shape[-1]), dy.shape[-1], self.gw(name + "/bias"))
+                on_wgrad(event, lambda: c.conv2d_wgrad(desc, x, dy, dw=self.gw(name + K), db=None), s3)
+            else:
+                on_wgrad(event, lambda: c.conv2d_wgrad(desc, x, dy, dw=self.gw(name + K), db=self.gw(name + "/bias")), s3)
 
         dense_wgrad_adam = self._dense_wgrad_adam
         nd = "coarse/dense/dense_"
@@ -458,21 +483,22 @@ class MSDNNet:
             # single GPU: the dense group's Adam runs under the conv backward.  It overwrites the dense weight
             # mirror, so it waits for e_g: both dense dgrads (the last readers of those weights) are done.
             on_wgrad(e_g, lambda: self.apply_adam(("CoarseDense",)))
-        on_wgrad(e_g, lambda: c.conv2d_wgrad(self.d_c4, self.c3, self.g_c4, dw=self.gw(n + "4" + K), db=self.gw(n + "4/bias")), s3)
+        conv_wgrad(self.d_c4, self.c3, self.g_c4, n + "4", e_g)
         c.conv2d_dgrad(self.d_c4, self.g_c4, self.w(n + "4" + K), out=self.g_c3, relu_src=self.c3)
         e_g = mark(s0)
-        on_wgrad(e_g, lambda: c.conv2d_wgrad(self.d_c3, self.c2, self.g_c3, dw=self.gw(n + "3" + K), db=self.gw(n + "3/bias")), s3)
-        c.conv2d_dgrad(self.d_c3, self.g_c3, self.w(n + "3" + K), out=self.g_c2, relu_src=self.c2)
+        conv_wgrad(self.d_c3, self.c2, self.g_c3, n + "3", e_g)
+        s0.wait_event(e_flip)
+        c.conv2d_dgrad(self.d_c3, self.g_c3, self.w(n + "3" + K), out=self.g_c2, relu_src=self.c2, wflip=self._wflip["3"])
         e_g = mark(s0)
-        on_wgrad(e_g, lambda: c.conv2d_wgrad(self.d_c2, self.p1, self.g_c2, dw=self.gw(n + "2" + K), db=self.gw(n + "2/bias")), s3)
-        c.conv2d_dgrad(self.d_c2, self.g_c2, self.w(n + "2" + K), out=self.g_p1)
+        conv_wgrad(self.d_c2, self.p1, self.g_c2, n + "2", e_g)
+        c.conv2d_dgrad(self.d_c2, self.g_c2, self.w(n + "2" + K), out=self.g_p1, wflip=self._wflip["2"])
         c.maxpool2x2_idx_bwd(self.i1, self.g_p1, (B, 27, 37, 256), out=self.g_c1)
         e_g = mark(s0)
         # (DP: exchanging conv2d_4..2 here as an early bucket was measured SLOWER at 2 GPUs, 1.30 vs 1.26 ms: three more
         # NCCL launches cost more than the shorter tail saves; dp.bucket_range keeps the early/late split available)
-        on_wgrad(e_g, lambda: c.conv2d_wgrad(self.d_c1, self.p0, self.g_c1, dw=self.gw(n + "1" + K), db=self.gw(n + "1/bias")), s3)
+        conv_wgrad(self.d_c1, self.p0, self.g_c1, n + "1", e_g)
         e_w1 = mark(s3)                                # gradients of conv2d_4 .. conv2d_1 are complete
-        c.conv2d_dgrad(self.d_c1, self.g_c1, self.w(n + "1" + K), out=self.g_p0)
+        c.conv2d_dgrad(self.d_c1, self.g_c1, self.w(n + "1" + K), out=self.g_p0, wflip=self._wflip["1"])
         c.maxpool2x2_idx_bwd(self.i0, self.g_p0, (B, 55, 74, 96), out=self.g_c0)
         e_g = mark(s0)
         # Single GPU: TF-Adam of conv2d_4 .. conv2d_1 (99 % of the group) runs on the idle fine stream next to
@@ -489,8 +515,17 @@ class MSDNNet:
                 self.adam_range("CoarseConv", lo_cc, split_cc)
                 e_fine = mark(s1)
 
+        e_b0 = None
+        if side_bias:
+            with torch.cuda.stream(s1):
+                s1.wait_event(e_g)
+                c.bias_grad_bf16(self.g_c0.view(-1, 96), 96, self.gw(n + "0/bias"))
+                e_b0 = mark(s1)
+
         def conv0_and_adam():
-            c.conv2d_wgrad(self.d_c0, self.img4, self.g_c0, dw=self.gw(n + "0" + K), db=self.gw(n + "0/bias"))
+            c.conv2d_wgrad(self.d_c0, self.img4, self.g_c0, dw=self.gw(n + "0" + K), db=None if side_bias else self.gw(n + "0/bias"))
+            if e_b0 is not None:
+                s3.wait_event(e_b0)
             self._mask_padding("coarse/conv/conv2d_0/kernel")
             if self.comm:
                 if os.environ.get("A3D_DP_CONV_ALLREDUCE", "0") == "1":      # f32 allreduce + replicated Adam (1 NCCL op)

@@ -270,11 +270,26 @@ class Context:
                                         L.EPI_RELU if relu else 0, _ptr(ws), ws.numel(), _stream()), "conv2d_fwd")
         return out
 
-    def conv2d_dgrad(self, d, dy, w, out=None, relu_src=None):
-        """relu_src: post-ReLU activation that was the layer's input -> fused ReluGrad of the producer."""
+    def conv2d_dgrad_prepare(self, d, w, out=None):
+        """Flipped, channel-transposed filter for conv2d_dgrad(wflip=...); None when the shape's dgrad does not use one."""
+        if out is None:
+            out = torch.empty(d.C, d.R, d.S, d.K, dtype=torch.bfloat16, device=w.device)
+        rc = self.lib.a3d_conv2d_dgrad_prepare(self.h, C.byref(d), _ptr(w), _ptr(out), _stream())
+        if rc == L.A3D_ENOTSUP:
+            return None
+        L.check(rc, "conv2d_dgrad_prepare")
+        return out
+
+    def conv2d_dgrad(self, d, dy, w, out=None, relu_src=None, wflip=None):
+        """relu_src: post-ReLU activation that was the layer's input -> fused ReluGrad of the producer.
+        wflip: filter prepared by conv2d_dgrad_prepare (w is then unused)."""
         if out is None:
             out = torch.empty(d.N, d.H, d.W, d.C, dtype=torch.bfloat16, device=dy.device)
         ws, nb = self.conv_ws(d, L.OP_DGRAD)
+        if wflip is not None:
+            L.check(self.lib.a3d_conv2d_dgrad_prepared(self.h, C.byref(d), _ptr(dy), _ptr(wflip), _ptr(out), _ptr(relu_src),
+                                                       _ptr(ws), ws.numel(), _stream()), "conv2d_dgrad_prepared")
+            return out
         L.check(self.lib.a3d_conv2d_dgrad(self.h, C.byref(d), _ptr(dy), _ptr(w), _ptr(out), _ptr(relu_src), _ptr(ws),
                                           ws.numel(), _stream()), "conv2d_dgrad")
         return out

@@ -110,6 +110,13 @@ int a3d_conv2d_fwd(a3d_ctx*, const a3d_conv_desc*, const uint16_t* x, const uint
  * the ReluGrad of the producing layer is fused: dx = relu_src > 0 ? dx : 0. */
 int a3d_conv2d_dgrad(a3d_ctx*, const a3d_conv_desc*, const uint16_t* dy, const uint16_t* w,
                      uint16_t* dx, const uint16_t* relu_src, void* ws, size_t ws_bytes, void* stream);
+/* Same op with the weight-only part hoisted out of the backward chain.  The dgrad of a stride-1 convolution is a
+ * forward convolution of dy with the spatially flipped, channel-transposed filter; `prepare` writes that filter
+ * (K*R*S*C bf16, caller-owned) from w on any stream once the step's weights are final, `prepared` consumes it.
+ * prepare returns A3D_ENOTSUP for shapes whose dgrad does not use a flipped filter (strided convolutions). */
+int a3d_conv2d_dgrad_prepare(a3d_ctx*, const a3d_conv_desc*, const uint16_t* w, uint16_t* wflip, void* stream);
+int a3d_conv2d_dgrad_prepared(a3d_ctx*, const a3d_conv_desc*, const uint16_t* dy, const uint16_t* wflip,
+                              uint16_t* dx, const uint16_t* relu_src, void* ws, size_t ws_bytes, void* stream);
 /* Replaces Conv2DBackpropFilter + BiasAddGrad.  dw f32 OHWI, db f32 [K] (nullable).
  * Both are OVERWRITTEN (not accumulated). */
 int a3d_conv2d_wgrad(a3d_ctx*, const a3d_conv_desc*, const uint16_t* x, const uint16_t* dy,

@@ -248,6 +248,26 @@ def test_conv_dgrad_wgrad(ctx, layer, impl):
     assert rel_err(db, dy.float().sum((0, 1, 2))) < 2e-3
 
 
+def test_conv_dgrad_prepared_filter(ctx):
+    """a3d_conv2d_dgrad_prepare + a3d_conv2d_dgrad_prepared == a3d_conv2d_dgrad """
+    for name in ("conv2d_1", "conv2d_2", "conv2d_3"):
+        _, H, W, Cc, K, R, S, stride, padding = LAYERS_BY_NAME[name]
+        Cc = (Cc + 63) // 64 * 64
+        d = ops.conv_desc(2, H, W, Cc, K, R, S, stride, padding, impl=L.IMPL_AUTO)
+        w = bf16_rand(K, R, S, Cc, seed=21, scale=1.0 / math.sqrt(R * S * Cc))
+        dy = bf16_rand(2, d.P, d.Q, K, seed=22)
+        src = torch.relu(bf16_rand(2, H, W, Cc, seed=23))
+        wf = ctx.conv2d_dgrad_prepare(d, w)
+        assert wf is not None
+        a = ctx.conv2d_dgrad(d, dy, w, relu_src=src)
+        b = ctx.conv2d_dgrad(d, dy, None, relu_src=src, wflip=wf)
+        assert torch.equal(wf, w.permute(3, 1, 2, 0).flip(1, 2).contiguous())
+        assert rel_err(a, b) < 5e-3        # the two calls may be tuned to different tiles / split-K orders
+    _, H, W, Cc, K, R, S, stride, padding = LAYERS_BY_NAME["conv2d_4"]      # strided: no flipped filter
+    d = ops.conv_desc(2, H, W, Cc, K, R, S, stride, padding, impl=L.IMPL_AUTO)
+    assert ctx.conv2d_dgrad_prepare(d, bf16_rand(K, R, S, Cc, seed=21)) is None
+
+
 @pytest.mark.parametrize("force", ["4,1,256", "2,5,256", "3,2,256", "1,3,256"])
 @pytest.mark.parametrize("layer", [("k256", 27, 37, 128, 256, 5, 5, 1, "same"), ("k384", 13, 18, 256, 384, 3, 3, 1, "same"),
                                    ("k256_s2", 13, 18, 384, 256, 3, 3, 2, "valid")], ids=["k256", "k384", "k256_s2"])
