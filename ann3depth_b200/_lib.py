@@ -40,6 +40,7 @@ SIGNATURES = {
     "a3d_launch_count": (C.c_uint64, [_vp]),
     "a3d_resize_bilinear_tf1": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp]),
     "a3d_resize_bilinear_tf1_s2d": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp]),
+    "a3d_resize_bilinear_tf1_s2d_u8": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp]),
     "a3d_conv2d_pool4_fwd": (_i, [_vp, C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _u, _vp, _sz, _vp]),
     "a3d_pool4_bwd": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     "a3d_gather_sum_f32": (_i, [_vp, _vp, _vp, _i, _sz, _vp, _vp]),

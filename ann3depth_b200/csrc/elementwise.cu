@@ -768,6 +768,117 @@ resize_bilinear_tf1_s2d4c3_rows_kernel(const float* __restrict__ src, int H, int
   }
 }
 
+// Pipelined variant of the row-staged kernel: persistent blocks, each walks over output rows and copies the two
+// source rows of its NEXT output row into the other half of shared memory (cp.async, 16 bytes per thread and
+// instruction) while it interpolates the current one, so every resident block always has loads in flight
+// (the one-shot kernel above spends half of each block's life in its compute/store phase: 2.9 TB/s).
+// T = float (the reference's tensor contract, src/data.py:82-86) or uint8_t (8-bit wire format: value / 255,
+// i.e. the pixels before tools/data_tf_converter.py:36-37 turned them into floats; `scale` = 1/255).
+template <typename T>
+__global__ void __launch_bounds__(256)
+resize_s2d4c3_rows_pipelined_kernel(const T* __restrict__ src, int H, int W, uint16_t* __restrict__ dst, int OH, int OWs,
+                                    int dstC, float sy, float sx, int total_rows, float scale) {
+  extern __shared__ __align__(16) uint8_t rp_sm[];      // [2 buffers][2 rows][W*3*sizeof(T)]
+  const int row_bytes = W * 3 * (int)sizeof(T);
+  const int row_ch = row_bytes / 16;                    // 16-byte chunks per source row
+  const uint32_t sm_base = static_cast<uint32_t>(__cvta_generic_to_shared(rp_sm));
+  auto issue = [&](int r, int buf) {
+    const int oy = r % OH, b = r / OH;
+    const int y0 = (int)floorf(oy * sy);
+    const int y1 = min(y0 + 1, H - 1);
+    const uint8_t* r0 = reinterpret_cast<const uint8_t*>(src + ((size_t)b * H + y0) * W * 3);
+    const uint8_t* r1 = reinterpret_cast<const uint8_t*>(src + ((size_t)b * H + y1) * W * 3);
+    const uint32_t d0 = sm_base + (uint32_t)(buf * 2 * row_bytes);
+    for (int i = threadIdx.x; i < 2 * row_ch; i += blockDim.x) {
+      const int which = i >= row_ch;
+      const int j = i - which * row_ch;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + (uint32_t)(which * row_bytes + j * 16)),
+                   "l"((which ? r1 : r0) + (size_t)j * 16)
+                   : "memory");
+    }
+  };
+  int r = blockIdx.x, buf = 0;
+  if (r < total_rows) issue(r, 0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (; r < total_rows; r += gridDim.x) {
+    const int nxt = r + gridDim.x;
+    if (nxt < total_rows) issue(nxt, buf ^ 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");       // the rows of r have landed (this thread's copies)
+    __syncthreads();                                           // ... and everybody else's
+    const T* a0 = reinterpret_cast<const T*>(rp_sm + (size_t)buf * 2 * row_bytes);
+    const T* a1 = reinterpret_cast<const T*>(rp_sm + (size_t)buf * 2 * row_bytes + row_bytes);
+    const int oy = r % OH, b = r / OH;
+    const float fy = oy * sy;
+    const float ly = fy - floorf(fy);
+    const int Y = oy >> 2, dy = oy & 3;
+    uint16_t* orow = dst + ((size_t)b * (OH >> 2) + Y) * OWs * dstC;
+    for (int t = threadIdx.x; t < OWs * 3; t += blockDim.x) {
+      const int X = t / 3, p = t - X * 3;               // piece p = values 4p .. 4p+3 of the 12 (dx, c) values
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = p * 4 + j;
+        const int dx = k / 3, c = k - dx * 3;
+        const float fx = (X * 4 + dx) * sx;
+        const int x0 = (int)floorf(fx);
+        const int x1 = min(x0 + 1, W - 1);
+        const float lx = fx - x0;
+        const float tl = (float)a0[x0 * 3 + c], tr = (float)a0[x1 * 3 + c], bl = (float)a1[x0 * 3 + c],
+                    br = (float)a1[x1 * 3 + c];
+        const float top = tl + (tr - tl) * lx;
+        const float bot = bl + (br - bl) * lx;
+        v[j] = (top + (bot - top) * ly) * scale;
+      }
+      *reinterpret_cast<uint2*>(orow + (size_t)X * dstC + dy * 12 + p * 4) =
+          make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+    }
+    if (dy == 0) {
+      const int padq = (dstC - 48) / 4;                  // uint2 pieces of zero padding per pixel
+      for (int t = threadIdx.x; t < OWs * padq; t += blockDim.x) {
+        const int X = t / padq, q = t - X * padq;
+        *reinterpret_cast<uint2*>(orow + (size_t)X * dstC + 48 + q * 4) = make_uint2(0u, 0u);
+      }
+    }
+    __syncthreads();                                           // buffer `buf` is refilled in the next iteration
+    buf ^= 1;
+  }
+}
+
+template <typename T>
+static int launch_resize_pipelined(a3d_ctx* ctx, const T* src, int B, int H, int W, uint16_t* dst, int OH, int OW,
+                                   int dstC, float scale, cudaStream_t st) {
+  const size_t smem = (size_t)W * 3 * sizeof(T) * 4;
+  static int blocks_per_sm = 0;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    A3D_CHECK_CUDA(cudaFuncSetAttribute(resize_s2d4c3_rows_pipelined_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+    A3D_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, resize_s2d4c3_rows_pipelined_kernel<T>,
+                                                                 256, smem));
+    smem_set = smem;
+  }
+  const int total = B * OH;
+  int grid = ctx->sm_count * (blocks_per_sm > 0 ? blocks_per_sm : 1);
+  if (grid > total) grid = total;
+  resize_s2d4c3_rows_pipelined_kernel<T><<<grid, 256, smem, st>>>(src, H, W, dst, OH, OW / 4, dstC, (float)H / (float)OH,
+                                                                 (float)W / (float)OW, total, scale);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
+// 8-bit images: dst = space-to-depth(4) of resize(src / 255).  Same kernel as the float path, a quarter of the
+// bytes over PCIe and HBM.
+extern "C" int a3d_resize_bilinear_tf1_s2d_u8(a3d_ctx* ctx, const uint8_t* src, int B, int H, int W, int C, uint16_t* dst,
+                                              int OH, int OW, int s, int dstC, void* stream) {
+  A3D_REQUIRE(ctx && src && dst, "resize_s2d_u8: null argument");
+  A3D_REQUIRE(B > 0 && H > 0 && W > 0 && C == 3 && s == 4 && OH % 4 == 0 && OW % 4 == 0 && dstC % 8 == 0 && dstC >= 48 &&
+                  (reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (W * 3) % 16 == 0 &&
+                  (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (size_t)W * 3 * 4 <= 200 * 1024,
+              "resize_s2d_u8: needs C == 3, s == 4, 16-byte aligned source rows (W*3 %% 16 == 0)");
+  return launch_resize_pipelined<uint8_t>(ctx, src, B, H, W, dst, OH, OW, dstC, 1.f / 255.f, as_stream(stream));
+}
+
 extern "C" int a3d_resize_bilinear_tf1_s2d(a3d_ctx* ctx, const float* src, int B, int H, int W, int C, uint16_t* dst,
                                            int OH, int OW, int s, int dstC, void* stream) {
   A3D_REQUIRE(ctx && src && dst, "resize_s2d: null argument");
@@ -775,6 +886,11 @@ extern "C" int a3d_resize_bilinear_tf1_s2d(a3d_ctx* ctx, const float* src, int B
                   dstC >= s * s * C && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
               "resize_s2d: bad shape (OH, OW multiples of s; dstC %% 8 == 0 and >= s*s*C)");
   float sy = (float)H / (float)OH, sx = (float)W / (float)OW;
+  static int pipelined = -1;                       // A3D_RESIZE_PIPELINED=0: the one-shot row-staged kernel
+  if (pipelined < 0) { const char* e = getenv("A3D_RESIZE_PIPELINED"); pipelined = e ? atoi(e) : 1; }
+  if (pipelined && s == 4 && C == 3 && (W * 3) % 4 == 0 && (size_t)W * 3 * 4 * sizeof(float) <= 100 * 1024 &&
+      dstC % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0)
+    return launch_resize_pipelined<float>(ctx, src, B, H, W, dst, OH, OW, dstC, 1.f, as_stream(stream));
   if (s == 4 && C == 3 && (W * 3) % 4 == 0 && (size_t)W * 3 * 2 * sizeof(float) <= 48 * 1024 && dstC % 4 == 0 &&
       (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
     resize_bilinear_tf1_s2d4c3_rows_kernel<<<B * OH, 256, (size_t)W * 3 * 2 * sizeof(float), as_stream(stream)>>>(

@@ -25,9 +25,10 @@ def get_context(device=None) -> ops.Context:
     return _contexts[device]
 
 
-def _check_inputs(images, depths):
+def _check_inputs(images, depths, allow_u8=False):
     for t, ch, nm in ((images, 3, "images"), (depths, 1, "depths")):
-        if not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float32 and t.dim() == 4 and t.shape[-1] == ch
+        ok_dtype = t.dtype == torch.float32 or (allow_u8 and nm == "images" and t.dtype == torch.uint8)
+        if not (torch.is_tensor(t) and t.is_cuda and ok_dtype and t.dim() == 4 and t.shape[-1] == ch
                 and t.is_contiguous()):
             raise ValueError(f"{nm} must be a contiguous float32 CUDA tensor [B,H,W,{ch}] (NHWC)")
     if images.shape[0] != depths.shape[0]:
@@ -63,7 +64,10 @@ class _MultiScaleDeepNetwork:
     """Eigen et al. (2014) multi-scale deep network; mirrors src/models.py:203-367."""
 
     def __call__(self, images, depths, train=True, **net_kwargs):
-        _check_inputs(images, depths)
+        # beyond the reference contract: uint8 images (pixel values 0..255, read as pixel / 255) are accepted too --
+        # the reference's own pixels are k/255 (tools/data_tf_converter.py:36-37), so this is the same data at a
+        # quarter of the host->device bytes
+        _check_inputs(images, depths, allow_u8=True)
         ctx = get_context(images.device.index)
         net = MSDNNet(ctx, images.shape[0], tuple(images.shape[1:3]), tuple(depths.shape[1:3]), train=train,
                       **net_kwargs)

@@ -110,6 +110,10 @@ class Context:
     def resize_bilinear_tf1_s2d(self, src, OH, OW, s, out):
         """Resize + space-to-depth(s): out bf16 [B, OH/s, OW/s, dstC >= s*s*C]."""
         B, H, W, Cc = src.shape
+        if src.dtype == torch.uint8:               # 8-bit wire format: pixel / 255 folded into the kernel
+            L.check(self.lib.a3d_resize_bilinear_tf1_s2d_u8(self.h, _ptr(src), B, H, W, Cc, _ptr(out), OH, OW, s,
+                                                            out.shape[-1], _stream()), "resize_s2d_u8")
+            return out
         L.check(self.lib.a3d_resize_bilinear_tf1_s2d(self.h, _ptr(src), B, H, W, Cc, _ptr(out), OH, OW, s,
                                                      out.shape[-1], _stream()), "resize_s2d")
         return out

@@ -247,7 +247,8 @@ def gpu_arm(args, rank, world, local_rank):
     images_h, depths_h = images_h.pin_memory(), depths_h.pin_memory()
     images, depths = images_h.to(dev), depths_h.to(dev)
     op = models.msdn(images, depths, train=True, comm=comm)
-    op.net.load_params(glorot_params(seed=1))
+    params_cpu = glorot_params(seed=1)
+    op.net.load_params(params_cpu)
 
     def barrier():
         if world > 1:
@@ -297,46 +298,66 @@ def gpu_arm(args, rank, world, local_rank):
 
     # ---- end to end: pinned host batch -> H2D (prefetched on a copy stream) -> step -> loss D2H
     copy_stream = torch.cuda.Stream(device=dev)
-    stage = [(torch.empty_like(images), torch.empty_like(depths)) for _ in range(2)]
-    loss_h = torch.empty(2, dtype=torch.float32).pin_memory()
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    freed = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def prefetch(i):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(freed[i % 2])
-            stage[i % 2][0].copy_(images_h, non_blocking=True)
-            stage[i % 2][1].copy_(depths_h, non_blocking=True)
-            ready[i % 2].record(copy_stream)
+    def measure_e2e(op_, images_dev, images_host):
+        stage = [(torch.empty_like(images_dev), torch.empty_like(depths)) for _ in range(2)]
+        loss_h = torch.empty(2, dtype=torch.float32).pin_memory()
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        freed = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def e2e_loop(n):
-        cur = torch.cuda.current_stream()
-        for f in freed:
-            f.record(cur)
-        prefetch(0)
-        for i in range(n):
-            if i + 1 < n:
-                prefetch(i + 1)
-            cur.wait_event(ready[i % 2])
-            images.copy_(stage[i % 2][0], non_blocking=True)
-            depths.copy_(stage[i % 2][1], non_blocking=True)
-            freed[i % 2].record(cur)
-            op.run()
-            loss_h[0:1].copy_(op.losses["loss/coarse_loss"], non_blocking=True)
-            loss_h[1:2].copy_(op.losses["loss/fine_loss"], non_blocking=True)
-            cur.synchronize()                       # the driver reads the loss every step
-        return float(loss_h[0])
+        def prefetch(i):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[i % 2])
+                stage[i % 2][0].copy_(images_host, non_blocking=True)
+                stage[i % 2][1].copy_(depths_h, non_blocking=True)
+                ready[i % 2].record(copy_stream)
 
-    e2e_loop(3)
-    barrier()
-    t0 = time.perf_counter()
-    last_loss = e2e_loop(args.steps)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s])
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = BATCH * world * args.steps / float(t)
+        def e2e_loop(n):
+            cur = torch.cuda.current_stream()
+            for f in freed:
+                f.record(cur)
+            prefetch(0)
+            for i in range(n):
+                if i + 1 < n:
+                    prefetch(i + 1)
+                cur.wait_event(ready[i % 2])
+                images_dev.copy_(stage[i % 2][0], non_blocking=True)
+                depths.copy_(stage[i % 2][1], non_blocking=True)
+                freed[i % 2].record(cur)
+                op_.run()
+                loss_h[0:1].copy_(op_.losses["loss/coarse_loss"], non_blocking=True)
+                loss_h[1:2].copy_(op_.losses["loss/fine_loss"], non_blocking=True)
+                cur.synchronize()                       # the driver reads the loss every step
+            return float(loss_h[0])
+
+        e2e_loop(3)
+        barrier()
+        t0 = time.perf_counter()
+        last = e2e_loop(args.steps)
+        barrier()
+        tt = torch.tensor([time.perf_counter() - t0])
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return BATCH * world * args.steps / float(tt), last
+
+    # headline e2e: the reference's tensor contract (float32 images, src/data.py:82-86)
+    e2e_value, last_loss = measure_e2e(op, images, images_h)
+    # secondary: the same pixels as uint8 (0..255, read as pixel / 255 by the resize kernel) -- a quarter of the
+    # PCIe bytes.  Single GPU only (a second net: its own arena, graph and inputs).
+    e2e_u8 = None
+    if world == 1 and os.environ.get("A3D_BENCH_U8", "1") != "0":
+        images8_h = (images_h * 255.0).round().clamp_(0, 255).to(torch.uint8).pin_memory()
+        images8 = images8_h.to(dev)
+        op8 = models.msdn(images8, depths, train=True)
+        op8.net.load_params(params_cpu)
+        for _ in range(3):
+            op8.run()
+        torch.cuda.synchronize()
+        v8, loss8 = measure_e2e(op8, images8, images8_h)
+        e2e_u8 = {"value": v8, "unit": "images/s", "h2d_bytes_per_step": BATCH * (480 * 640 * 3 + 55 * 73 * 4),
+                  "d2h_bytes_per_step": D2H_BYTES, "last_loss": loss8,
+                  "note": "uint8 images (pixel/255 in the resize kernel); beyond the reference's float32 contract"}
+        del op8
 
     if rank == 0:
         pk, pk_kind = peaks()
@@ -411,6 +432,7 @@ def gpu_arm(args, rank, world, local_rank):
                                   "conv: reduce-scatter(bf16) -> sharded Adam -> all-gather(bf16 weights)") if world > 1 else None},
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": H2D_BYTES,
                         "d2h_bytes_per_step": D2H_BYTES, "last_loss": last_loss},
+                "e2e_u8": e2e_u8,
                 "gpu_launches": launches_per_step * args.steps,
                 "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)

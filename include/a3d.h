@@ -77,6 +77,11 @@ int a3d_resize_bilinear_tf1(a3d_ctx*, const float* src, int B, int H, int W, int
  * fine/first are both 3x3 stride-1 convolutions with 128-byte pixels. */
 int a3d_resize_bilinear_tf1_s2d(a3d_ctx*, const float* src, int B, int H, int W, int C,
                                 uint16_t* dst, int OH, int OW, int s, int dstC, void* stream);
+/* Same with 8-bit pixels (the images before tools/data_tf_converter.py:36-37 turned them into floats):
+ * dst = space-to-depth(resize(src / 255)).  C == 3, s == 4, W*3 a multiple of 16.  A quarter of the bytes over
+ * PCIe and HBM; beyond the reference's float32 tensor contract (src/data.py:82-86), offered next to it. */
+int a3d_resize_bilinear_tf1_s2d_u8(a3d_ctx*, const uint8_t* src, int B, int H, int W, int C,
+                                uint16_t* dst, int OH, int OW, int s, int dstC, void* stream);
 
 /* ---- convolution --------------------------------------------------------------------------- */
 typedef struct a3d_conv_desc {

@@ -591,6 +591,25 @@ def test_resize_s2d_matches_resize_then_space_to_depth(ctx):
     assert float(out[..., 48:].abs().max()) == 0.0
 
 
+def test_resize_s2d_uint8_and_pipelined(ctx, monkeypatch):
+    """uint8 images (pixel / 255) through the pipelined resize kernel == float path on the same pixels; batch > grid
+    so that persistent blocks walk over several rows; ragged width (W*3 % 16 == 0 only)"""
+    g = torch.Generator().manual_seed(46)
+    for B, H, W in ((5, 480, 640), (1, 50, 64)):
+        OH, OW = (228, 304) if H == 480 else (24, 28)
+        u8 = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8).to(DEV)
+        f32 = u8.float() / 255.0
+        ref = torch.full((B, OH // 4, OW // 4, 64), 5.0, dtype=torch.bfloat16, device=DEV)
+        ctx.resize_bilinear_tf1_s2d(f32, OH, OW, 4, out=ref)
+        out = torch.full_like(ref, 7.0)
+        ctx.resize_bilinear_tf1_s2d(u8, OH, OW, 4, out=out)
+        assert float((out.float() - ref.float()).abs().max()) <= 2.0 ** -8      # one bf16 ulp at 1.0 (rounding order)
+        assert float(out[..., 48:].abs().max()) == 0.0
+        flat = ctx.resize_bilinear_tf1(f32, OH, OW, dstC=3, dtype=torch.bfloat16)
+        exp = flat.view(B, OH // 4, 4, OW // 4, 4, 3).permute(0, 1, 3, 2, 4, 5).reshape(B, OH // 4, OW // 4, 48)
+        assert torch.equal(ref[..., :48], exp)
+
+
 def test_gather_sum_and_scatter_cast(ctx):
     g = torch.Generator().manual_seed(45)
     n, G, big = 1000, 4, 5000
