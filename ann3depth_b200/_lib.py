@@ -98,6 +98,10 @@ SIGNATURES = {
 _lib = None
 
 
+def signature_names():
+    return list(SIGNATURES)
+
+
 def load():
     """dlopen liba3d.so and bind every declared symbol.  Raises A3DError if it is missing."""
     global _lib

@@ -22,6 +22,7 @@ import time
 import torch
 
 from . import data, models
+from .summary import EventWriter, SummaryHook, TraceHook
 from .init import glorot_params
 
 logger = logging.getLogger("ann3depth")
@@ -37,20 +38,6 @@ class StopAtSignalHook:
 
     def _handler(self, signum, frame):
         self.signal_received = signum
-
-
-class TraceHook:
-    """src/tfhelper.py:192-249: trace the first step after a (re)start and every N-th step.  Here a
-    trace is the per-kernel CUDA-event timeline of one un-graphed step, written as JSON."""
-
-    def __init__(self, ckptdir, every_step=5000):
-        self.ckptdir, self.every, self._trace = ckptdir, every_step, True
-
-    def wants_trace(self):
-        return self._trace
-
-    def after_run(self, global_step):
-        self._trace = not ((global_step + 1) % self.every)
 
 
 def save_checkpoint(op, ckptdir):
@@ -128,7 +115,11 @@ def main(argv=None):
         logger.info(f"Restored checkpoint at global step {op.global_step}.")
 
     stop_hook = StopAtSignalHook()
-    trace_hook = TraceHook(ckptdir, 5000)
+    # chief-only observability, as in the reference (src/ann3depth.py:98-111): loss summaries every --sumfreq
+    # steps and a per-kernel trace of the first step after a (re)start and of every 5000th step, both in ckptdir
+    writer = EventWriter(ckptdir) if chief else None
+    summary_hook = SummaryHook(ckptdir, args.sumfreq, writer) if chief else None
+    trace_hook = TraceHook(ckptdir, 5000, writer) if chief else None
     if args.timeout:
         logger.info(f"Starting alarm: {args.timeout} s timeout.")
         signal.alarm(args.timeout)
@@ -138,8 +129,12 @@ def main(argv=None):
     last_log_step = op.global_step
     while op.global_step < args.steps and not stop_hook.signal_received:       # StopAtStepHook(last_step)
         inp.next_batch()
-        op.run(use_graph=not trace_hook.wants_trace())
-        trace_hook.after_run(op.global_step - 1)
+        if trace_hook is not None:
+            trace_hook.run(op)
+        else:
+            op.run()
+        if summary_hook is not None:
+            summary_hook.after_run(op, args.batchsize * world)
         if op.global_step % args.sumfreq == 0:
             torch.cuda.synchronize()
             now = time.time()
@@ -155,6 +150,7 @@ def main(argv=None):
     torch.cuda.synchronize()
     if chief:
         save_checkpoint(op, ckptdir)
+        writer.close()
     logger.info("Session stopped.")
     return stop_hook.signal_received
 

@@ -250,3 +250,47 @@ def test_phase_schedule_and_inference():
     p64 = {k: v.double() for k, v in p.items()}
     ref = OM.forward(p64, images.double(), depths.double(), None, False)
     assert rel(out.cpu(), ref["fine"]) < 1e-2
+
+
+def test_uint8_images_match_float_images():
+    """models.msdn accepts uint8 images (pixel / 255 inside the resize kernel): same step as the float tensor"""
+    B = 2
+    images, depths, mask = make_inputs(B)
+    u8 = (images * 255).round().clamp(0, 255).to(torch.uint8)
+    p = conditioned_params()
+    opf = build(B, p, mask, u8.float() / 255.0, depths)
+    op8 = build(B, p, mask, u8, depths)
+    opf.run(use_graph=False)
+    op8.run(use_graph=False)
+    torch.cuda.synchronize()
+    assert rel(op8.net.fine, opf.net.fine) < 1e-2 and rel(op8.net.coarse, opf.net.coarse) < 1e-2
+    assert abs(float(op8.net.loss_coarse) - float(opf.net.loss_coarse)) <= 1e-2 * abs(float(opf.net.loss_coarse))
+
+
+def test_trace_and_summary_hooks_on_a_real_op(tmp_path):
+    """TraceHook writes a Chrome trace with one slice per liba3d call of the traced (un-graphed) step; SummaryHook
+    writes the two losses (GraphKeys.LOSSES) as TensorBoard scalars (src/tfhelper.py:137-157,192-249)."""
+    import json
+    from ann3depth_b200 import summary as S
+    B = 2
+    images, depths, mask = make_inputs(B)
+    op = build(B, conditioned_params(), mask, images, depths)
+    writer = S.EventWriter(str(tmp_path))
+    trace, summ = S.TraceHook(str(tmp_path), every_step=3, writer=writer), S.SummaryHook(str(tmp_path), 2, writer)
+    lib_fn = op.net.ctx.lib.a3d_conv2d_fwd
+    for _ in range(4):
+        trace.run(op)
+        summ.after_run(op, B)
+    writer.close()
+    assert op.net.ctx.lib.a3d_conv2d_fwd is lib_fn                      # the wrappers are gone after the trace
+    assert op.global_step == 4
+    tl = json.load(open(tmp_path / "timeline-0.json"))
+    slices = [e for e in tl["traceEvents"] if e.get("ph") == "X"]
+    names = {e["name"] for e in slices}
+    assert len(slices) > 30 and {"a3d_conv2d_fwd", "a3d_silog_loss", "a3d_dense_wgrad_adam"} <= names
+    assert all(e["dur"] >= 0 and e["ts"] >= 0 for e in slices)
+    assert len({e["tid"] for e in slices}) >= 3                         # main, fine and wgrad streams
+    assert (tmp_path / "timeline-3.json").exists() and not (tmp_path / "timeline-1.json").exists()
+    loader = pytest.importorskip("tensorboard.backend.event_processing.event_file_loader")
+    tags = [(e.step, v.tag) for e in loader.EventFileLoader(writer.path).Load() for v in e.summary.value]
+    assert (2, "loss/coarse_loss") in tags and (4, "loss/fine_loss") in tags and (1, "trace/liba3d_calls") in tags
