@@ -35,6 +35,12 @@ class DataParallel:
             lo, hi = a.group_range("CoarseConv")
             cut = a.specs["coarse/conv/conv2d_1/kernel"].offset
             return (lo, cut) if name == "coarse_conv_early" else (cut, hi)
+        if name in ("coarse_conv_main", "coarse_conv_0"):
+            # conv2d_4 .. conv2d_1 (99 % of the group; exchanged under the rest of the backward pass) | conv2d_0
+            # (55 k parameters: the only exchange left in the step's tail)
+            lo, hi = a.group_range("CoarseConv")
+            cut = a.specs["coarse/conv/conv2d_0/kernel"].offset
+            return (lo, cut) if name == "coarse_conv_main" else (cut, hi)
         if name == "fine":
             lo_a, hi_a = a.group_range("FineA")
             lo_b, hi_b = a.group_range("FineB")

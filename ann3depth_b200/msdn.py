@@ -430,15 +430,20 @@ class MSDNNet:
 
         fused = self.fuse_dense_adam and not self.comm
         a = self.arena
-        # Single GPU: the bias gradients (latency-bound column sums of dY, 7-10 us each) leave the conv-wgrad stream
+        # The bias gradients (latency-bound column sums of dY, 7-10 us each) leave the conv-wgrad stream
         # for the fine stream, whose forward work is long done by then: they run next to the wgrad GEMMs, not before them.
-        side_bias = (not self.comm) and s1 is not s0 and os.environ.get("A3D_SIDE_BIAS", "1") != "0"
+        # (Data parallel: measured slower at 2 GPUs, 1.184 vs 1.144 ms -- the comm stream's NCCL kernels already fill
+        # those gaps -- so there A3D_SIDE_BIAS must be set to 2 to enable it.)
+        sb_env = os.environ.get("A3D_SIDE_BIAS", "1")
+        side_bias = s1 is not s0 and (sb_env == "2" or (sb_env != "0" and not self.comm))
+        e_bias = {}
 
         def conv_wgrad(desc, x, dy, name, event):
             if side_bias:
                 with torch.cuda.stream(s1):
                     s1.wait_event(event)
                     c.bias_grad_bf16(dy.view(-1, dy.shape[-1]), dy.shape[-1], self.gw(name + "/bias"))
+                    e_bias[name] = mark(s1)
                 on_wgrad(event, lambda: c.conv2d_wgrad(desc, x, dy, dw=self.gw(name + K), db=None), s3)
             else:
                 on_wgrad(event, lambda: c.conv2d_wgrad(desc, x, dy, dw=self.gw(name + K), db=self.gw(name + "/bias")), s3)
@@ -507,6 +512,18 @@ class MSDNNet:
         lo_cc, hi_cc = a.group_range("CoarseConv")
         split_cc = a.specs["coarse/conv/conv2d_0/kernel"].offset
         split_ok = (not self.comm) and lo_cc < split_cc < hi_cc and a.specs["coarse/conv/conv2d_0/bias"].offset > split_cc
+        # Data parallel, optional (A3D_DP_CONV_SPLIT=1): the same cut for the exchange.  conv2d_4 .. conv2d_1 go through
+        # reduce-scatter -> sharded Adam -> all-gather right behind conv2d_1's weight gradient, under conv2d_1's dgrad and
+        # conv2d_0's wgrad; the tail keeps ONE small f32 allreduce (conv2d_0) + its replicated Adam instead of three
+        # collectives.  Measured at 2 GPUs: 1.20 ms against 1.18 ms unsplit -- the extra NCCL kernels take SM slots from
+        # the GEMMs they overlap with -- so it is off by default.
+        dp_split = bool(self.comm) and lo_cc < split_cc < hi_cc and (split_cc - lo_cc) % (self.comm.world * 8) == 0 and \
+            os.environ.get("A3D_DP_CONV_SPLIT", "0") == "1" and os.environ.get("A3D_DP_CONV_ALLREDUCE", "0") != "1"
+        if dp_split:
+            with torch.cuda.stream(s3):
+                if side_bias:
+                    s3.wait_event(e_bias[n + "1"])         # s1 is in order: the biases of conv2d_4 .. conv2d_1 are done
+                dp_update("coarse_conv_main", "CoarseConv", e_g)
         if split_ok:
             with torch.cuda.stream(s1):
                 s1.wait_event(e_fine)
@@ -527,7 +544,11 @@ class MSDNNet:
             if e_b0 is not None:
                 s3.wait_event(e_b0)
             self._mask_padding("coarse/conv/conv2d_0/kernel")
-            if self.comm:
+            if self.comm and dp_split:
+                self.comm.bucket_ready(self, "coarse_conv_0",
+                                       then=lambda lo, hi: self.adam_range("CoarseConv", lo, hi, inv_world))
+                self.comm.wait_all(self)
+            elif self.comm:
                 if os.environ.get("A3D_DP_CONV_ALLREDUCE", "0") == "1":      # f32 allreduce + replicated Adam (1 NCCL op)
                     self.comm.bucket_ready(self, "coarse_conv",
                                            then=lambda lo, hi: self.adam_range("CoarseConv", lo, hi, inv_world))
