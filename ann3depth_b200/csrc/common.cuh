@@ -65,6 +65,30 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return (uint32_t)f32_to_bf16_bits(lo) | ((uint32_t)f32_to_bf16_bits(hi) << 16);
 }
 
+// Flat index -> (n, h, w, c) of an [N][H][W][C] grid.  64-bit div/mod costs ~100 instructions each and made the
+// pool / col2im kernels index-math-bound (pool backward: 21 us for 33 MB); every MSDN tensor has < 2^32 elements,
+// so the 32-bit path is the one taken.
+__device__ __forceinline__ void split_nhwc(size_t i, int H, int W, int C, int& n, int& h, int& w, int& c) {
+  if (i <= 0xffffffffull) {
+    uint32_t u = (uint32_t)i;
+    uint32_t q = u / (uint32_t)C; c = (int)(u - q * (uint32_t)C); u = q;
+    q = u / (uint32_t)W; w = (int)(u - q * (uint32_t)W); u = q;
+    q = u / (uint32_t)H; h = (int)(u - q * (uint32_t)H); n = (int)q;
+  } else {
+    c = (int)(i % C); size_t t = i / C;
+    w = (int)(t % W); t /= W;
+    h = (int)(t % H); n = (int)(t / H);
+  }
+}
+__device__ __forceinline__ void split_rc(size_t i, int C, size_t& r, int& c) {
+  if (i <= 0xffffffffull) {
+    uint32_t u = (uint32_t)i, q = u / (uint32_t)C;
+    r = q; c = (int)(u - q * (uint32_t)C);
+  } else {
+    r = i / C; c = (int)(i - r * C);
+  }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

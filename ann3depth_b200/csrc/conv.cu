@@ -151,12 +151,8 @@ __global__ void col2im_kernel(const float* __restrict__ col, uint16_t* __restric
   const size_t J = (size_t)R * S * C;
   size_t total = (size_t)N * H * W * C8;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int c8 = (int)(i % C8);
-    size_t t = i / C8;
-    int iw = (int)(t % W);
-    t /= W;
-    int ih = (int)(t % H);
-    int n = (int)(t / H);
+    int n, ih, iw, c8;
+    split_nhwc(i, H, W, C8, n, ih, iw, c8);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int r = 0; r < R; ++r) {
       int ph = ih + pt - r;

@@ -79,12 +79,8 @@ __global__ void maxpool2x2_fwd_kernel(const uint4* __restrict__ x, int N, int H,
   int OH = H / 2, OW = W / 2;
   size_t total = (size_t)N * OH * OW * C8;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % C8);
-    size_t t = i / C8;
-    int ow = (int)(t % OW);
-    t /= OW;
-    int oh = (int)(t % OH);
-    int n = (int)(t / OH);
+    int n, oh, ow, c;
+    split_nhwc(i, OH, OW, C8, n, oh, ow, c);
     const uint4* p = x + (((size_t)n * H + 2 * oh) * W + 2 * ow) * C8 + c;
     uint4 a = __ldg(p), b = __ldg(p + C8), d = __ldg(p + (size_t)W * C8), e = __ldg(p + (size_t)W * C8 + C8);
     y[(((size_t)n * OH + oh) * OW + ow) * ldy8 + c] = max_bf16x8(max_bf16x8(a, b), max_bf16x8(d, e));
@@ -111,12 +107,8 @@ __global__ void maxpool2x2_relu_bwd_kernel(const uint4* __restrict__ x, const ui
   int GH = (H + 1) / 2, GW = (W + 1) / 2;   // windows incl. the partial ones on the odd edge
   size_t total = (size_t)N * GH * GW * C8;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % C8);
-    size_t t = i / C8;
-    int gw = (int)(t % GW);
-    t /= GW;
-    int gh = (int)(t % GH);
-    int n = (int)(t / GH);
+    int n, gh, gw, c;
+    split_nhwc(i, GH, GW, C8, n, gh, gw, c);
     int h0 = 2 * gh, w0 = 2 * gw;
     bool covered = (gh < OH) && (gw < OW);
     size_t base = (((size_t)n * H + h0) * W + w0) * C8 + c;
@@ -173,8 +165,8 @@ __global__ void relu_bwd_kernel(const uint4* __restrict__ y, const uint4* __rest
                                 size_t rows, int C8) {
   size_t total = rows * C8;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    size_t r = i / C8;
-    int c = (int)(i % C8);
+    size_t r; int c;
+    split_rc(i, C8, r, c);
     uint4 yv = __ldg(y + i), g = __ldg(dy + r * lddy8 + c), o;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -472,12 +464,8 @@ __global__ void maxpool2x2_fwd_f32_kernel(const float4* __restrict__ x, int N, i
   int OH = H / 2, OW = W / 2;
   size_t total = (size_t)N * OH * OW * C4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % C4);
-    size_t t = i / C4;
-    int ow = (int)(t % OW);
-    t /= OW;
-    int oh = (int)(t % OH);
-    int n = (int)(t / OH);
+    int n, oh, ow, c;
+    split_nhwc(i, OH, OW, C4, n, oh, ow, c);
     const float4* p = x + (((size_t)n * H + 2 * oh) * W + 2 * ow) * C4 + c;
     float4 v[4] = {__ldg(p), __ldg(p + C4), __ldg(p + (size_t)W * C4), __ldg(p + (size_t)W * C4 + C4)};
     float m[4];
@@ -520,12 +508,8 @@ __global__ void maxpool2x2_idx_bwd_kernel(const uint32_t* __restrict__ idx, cons
   int GH = (H + 1) / 2, GW = (W + 1) / 2;
   size_t total = (size_t)N * GH * GW * C4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % C4);
-    size_t t = i / C4;
-    int gw = (int)(t % GW);
-    t /= GW;
-    int gh = (int)(t % GH);
-    int n = (int)(t / GH);
+    int n, gh, gw, c;
+    split_nhwc(i, GH, GW, C4, n, gh, gw, c);
     int h0 = 2 * gh, w0 = 2 * gw;
     bool covered = (gh < OH) && (gw < OW);
     size_t base = (((size_t)n * H + h0) * W + w0) * C4 + c;
@@ -606,12 +590,8 @@ __global__ void space_to_depth2_kernel(const uint2* __restrict__ src, int N, int
   size_t total = (size_t)N * H * W * C4;
   const int H2 = H / 2, W2 = W / 2;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % C4);
-    size_t t = i / C4;
-    int w = (int)(t % W);
-    t /= W;
-    int h = (int)(t % H);
-    int n = (int)(t / H);
+    int n, h, w, c;
+    split_nhwc(i, H, W, C4, n, h, w, c);
     size_t o = ((((size_t)n * H2 + h / 2) * W2 + w / 2) * 4 + (h & 1) * 2 + (w & 1)) * C4 + c;
     dst[o] = __ldg(src + i);
   }

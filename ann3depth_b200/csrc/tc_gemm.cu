@@ -262,8 +262,8 @@ __global__ void bias_act_cast_kernel(const float* __restrict__ acc, const float*
                                      size_t rows, int n, long long ldy, unsigned flags) {
   size_t total = rows * n;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    size_t r = i / n;
-    int c = (int)(i - r * n);
+    size_t r; int c;
+    split_rc(i, n, r, c);
     float v = acc[i];
     if (bias) v += bias[c];
     if (flags & A3D_EPI_RELU) v = fmaxf(v, 0.f);
