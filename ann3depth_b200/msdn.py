@@ -509,6 +509,10 @@ class MSDNNet:
         # Single GPU: TF-Adam of conv2d_4 .. conv2d_1 (99 % of the group) runs on the idle fine stream next to
         # conv2d_0's weight gradient; only conv2d_0's 55 k parameters are updated in the step's tail.  The group is
         # one contiguous arena range in backward order, so this is the same update as two launches.
+        # DP exchange of the conv stack (4 M parameters, at the very end of the step): from 4 ranks on ONE f32 allreduce
+        # + replicated Adam beats cast + reduce-scatter + sharded Adam + all-gather (4 GPUs: 1.160 vs 1.185 ms; the
+        # collectives are latency-bound at 8-16 MB); at 2 ranks the sharded form was the faster one.
+        conv_allreduce = os.environ.get("A3D_DP_CONV_ALLREDUCE", "1" if (self.comm and self.comm.world >= 4) else "0") == "1"
         lo_cc, hi_cc = a.group_range("CoarseConv")
         split_cc = a.specs["coarse/conv/conv2d_0/kernel"].offset
         split_ok = (not self.comm) and lo_cc < split_cc < hi_cc and a.specs["coarse/conv/conv2d_0/bias"].offset > split_cc
@@ -518,7 +522,7 @@ class MSDNNet:
         # collectives.  Measured at 2 GPUs: 1.20 ms against 1.18 ms unsplit -- the extra NCCL kernels take SM slots from
         # the GEMMs they overlap with -- so it is off by default.
         dp_split = bool(self.comm) and lo_cc < split_cc < hi_cc and (split_cc - lo_cc) % (self.comm.world * 8) == 0 and \
-            os.environ.get("A3D_DP_CONV_SPLIT", "0") == "1" and os.environ.get("A3D_DP_CONV_ALLREDUCE", "0") != "1"
+            os.environ.get("A3D_DP_CONV_SPLIT", "0") == "1" and not conv_allreduce
         if dp_split:
             with torch.cuda.stream(s3):
                 if side_bias:
@@ -549,7 +553,7 @@ class MSDNNet:
                                        then=lambda lo, hi: self.adam_range("CoarseConv", lo, hi, inv_world))
                 self.comm.wait_all(self)
             elif self.comm:
-                if os.environ.get("A3D_DP_CONV_ALLREDUCE", "0") == "1":      # f32 allreduce + replicated Adam (1 NCCL op)
+                if conv_allreduce:                                          # f32 allreduce + replicated Adam (1 NCCL op)
                     self.comm.bucket_ready(self, "coarse_conv",
                                            then=lambda lo, hi: self.adam_range("CoarseConv", lo, hi, inv_world))
                 else:

@@ -1,11 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
 N=${1:-8}
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29534 tools/dp_parity.py 2>&1 | grep -v "^\*\|OMP\|NCCL version\|^$" | tail -5 | cut -c1-300
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 30 --warmup 5 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "rc=$?"
-tail -3 gpurun_out/bench_n$N.err | grep -v "^\*\|OMP\|NCCL version" | cut -c1-300
-python - <<P
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 60 --warmup 5 2>gpurun_out/bench_n${N}.err > gpurun_out/bench_n${N}.json
+python -c "
 import json
-l=json.loads(open('gpurun_out/bench_n$N.json').read().strip().splitlines()[-1])
-print(l['n_gpus'], round(l['ms_per_step'],4), round(l['value']), round(l['e2e']['value']))
-P
+l = json.loads(open('gpurun_out/bench_n${N}.json').read().strip().splitlines()[-1])
+print('n=$N', round(l['ms_per_step'], 4), round(l['value']), 'e2e', round(l['e2e']['value']))
+"
