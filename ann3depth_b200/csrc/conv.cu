@@ -448,9 +448,19 @@ extern "C" int a3d_dense_fwd(a3d_ctx* ctx, const uint16_t* x, int ldx, const uin
                              int N, int K, unsigned flags, int impl, void* stream) {
   A3D_REQUIRE(ctx && x && w && y && M > 0 && N > 0 && K > 0 && ldx >= K, "dense fwd: bad argument");
   cudaStream_t st = as_stream(stream);
-  bool tc_ok = (K % 64 == 0) && (ldx % 8 == 0) && M <= 256 && acc_ws;
-  if (impl != A3D_IMPL_SIMT && tc_ok)
-    return a3d_tc_dense_fwd(ctx, x, ldx, w, bias, keep_mask, drop_rate, y, y_dtype, acc_ws, M, N, K, flags, st);
+  bool tc_ok = (K % 64 == 0) && (ldx % 8 == 0) && acc_ws;
+  if (impl != A3D_IMPL_SIMT && tc_ok) {
+    // the batch is the UMMA N dimension (<= 256): larger batches (inference sweep, bs 512) go in chunks of 256 rows
+    const size_t ysz = y_dtype == A3D_F32 ? 4 : 2;
+    for (int m0 = 0; m0 < M; m0 += 256) {
+      const int mc = M - m0 < 256 ? M - m0 : 256;
+      int rc = a3d_tc_dense_fwd(ctx, x + (size_t)m0 * ldx, ldx, w, bias, keep_mask ? keep_mask + (size_t)m0 * N : nullptr,
+                                drop_rate, reinterpret_cast<uint8_t*>(y) + (size_t)m0 * N * ysz, y_dtype,
+                                acc_ws + (size_t)m0 * N, mc, N, K, flags, st);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   if (impl == A3D_IMPL_TC) {
     a3d_set_error("dense fwd: shape not supported by the tcgen05 path (M=%d N=%d K=%d)", M, N, K);
     return A3D_ENOTSUP;

@@ -296,7 +296,8 @@ def test_conv_wgrad_256_filter_tiles(ctx, monkeypatch, layer, force):
 
 # ----------------------------------------------------------------------------- dense
 @pytest.mark.parametrize("impl", ["simt", "tc"])
-@pytest.mark.parametrize("M,N,K", [(32, 4096, 12288), (32, 4070, 4096), (8, 128, 12544), (5, 200, 256)])
+@pytest.mark.parametrize("M,N,K", [(32, 4096, 12288), (32, 4070, 4096), (8, 128, 12544), (5, 200, 256), (300, 136, 256),
+                                   (512, 264, 128)])
 def test_dense_fwd(ctx, impl, M, N, K):
     x = bf16_rand(M, K, seed=30)
     w = bf16_rand(N, K, seed=31, scale=1.0 / math.sqrt(K))

@@ -11,7 +11,8 @@ from ann3depth_b200.init import glorot_params
 FWD_FLOP = 4.110e9
 rows = []
 p = glorot_params(1)
-for bs in (1, 2, 4, 8, 16, 32, 64, 128, 256, 512):
+BATCHES = tuple(int(b) for b in os.environ.get("A3D_SWEEP_BATCHES", "1,2,4,8,16,32,64,128,256,512").split(","))
+for bs in BATCHES:
     g = torch.Generator().manual_seed(bs)
     images = torch.rand(bs, 480, 640, 3, generator=g).cuda()
     depths = torch.zeros(bs, 55, 73, 1).cuda()
