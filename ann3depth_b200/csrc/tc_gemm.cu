@@ -1,6 +1,7 @@
 // tc_gemm.cu -- host side of the tcgen05 GEMM engine: tensor-map construction, tile/split selection
 // and the launchers used by the convolution / dense entry points.
 #include "tc_gemm.cuh"
+#include "tc_persist.cuh"
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -203,7 +204,44 @@ int launch_cfg(a3d_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, con
 //   1  128-row tile, one stage more (long main loops -- conv2d_1 dgrad has 100 k-blocks -- want the deeper pipeline)
 //   2  256-row tile (two accumulators sharing every B stage: less L2->SM operand traffic), default ring
 //   3  256-row tile, three stages
-enum { V_BASE = 0, V_DEEP = 1, V_BM256 = 2, V_BM256_DEEP = 3, V_COUNT = 4 };
+//   4..6  EXPERIMENTAL persistent kernel (tc_persist.cuh) with 2 / 3 / 4 stages; candidates only with A3D_PERSIST=1
+enum { V_BASE = 0, V_DEEP = 1, V_BM256 = 2, V_BM256_DEEP = 3, V_PERSIST2 = 4, V_PERSIST3 = 5, V_PERSIST4 = 6, V_COUNT = 7 };
+bool persist_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("A3D_PERSIST"); v = e ? atoi(e) : 0; }
+  return v != 0;
+}
+
+template <class C, int NSTAGE>
+int launch_persist(a3d_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const tc::Params& p_in, cudaStream_t st) {
+  using P = tc::PersistCfg<C, NSTAGE>;
+  static_assert(P::SMEM_BYTES <= 227 * 1024, "persistent kernel: stage ring + staging exceed shared memory");
+  static int ctas_per_sm = -1;
+  if (ctas_per_sm < 0) {
+    A3D_CHECK_CUDA(cudaFuncSetAttribute(tc::gemm_persist_kernel<C, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        P::SMEM_BYTES));
+    int occ = 0;
+    A3D_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc::gemm_persist_kernel<C, NSTAGE>, 192, P::SMEM_BYTES));
+    const int by_tmem = 512 / P::TMEM_COLS;        // a CTA keeps its TMEM columns for its whole life
+    ctas_per_sm = occ < by_tmem ? occ : by_tmem;
+  }
+  if (ctas_per_sm < 1) { a3d_set_error("persistent gemm: kernel does not fit an SM"); return A3D_ENOTSUP; }
+  tc::Params p = p_in;
+  if (p.atomic || p.kb_per_split < p.num_kb) { a3d_set_error("persistent gemm: no split-K"); return A3D_ENOTSUP; }
+  CUtensorMap tmC;
+  bool use_c = false;
+  int rc = maybe_tma_out(ctx, p, &tmC, &use_c);
+  if (rc) return rc;
+  const bool ok = use_c && ((p.epi == tc::EPI_TMA_F32 && C::BN % 32 == 0) || (p.epi == tc::EPI_TMA_BF16 && C::BN % 64 == 0));
+  if (!ok) { a3d_set_error("persistent gemm: needs a TMA-store epilogue (f32: BN %% 32, bf16: BN %% 64)"); return A3D_ENOTSUP; }
+  const int tiles_m = ceil_div(p.M, 128), tiles_n = ceil_div(p.N, C::BN);
+  int grid = ctx->sm_count * ctas_per_sm;
+  if (grid > tiles_m * tiles_n) grid = tiles_m * tiles_n;
+  tc::gemm_persist_kernel<C, NSTAGE><<<grid, 192, P::SMEM_BYTES, st>>>(tmA, tmB, tmC, p, tiles_m, tiles_n);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
 int launch_kk(a3d_ctx* ctx, int bn, int kcb, const CUtensorMap& tmA, const CUtensorMap& tmB, const tc::Params& p,
               int splits, cudaStream_t st, int variant = V_BASE) {
   if (variant == V_BASE) {
@@ -226,6 +264,15 @@ int launch_kk(a3d_ctx* ctx, int bn, int kcb, const CUtensorMap& tmA, const CUten
     A3D_CASEV(V_BM256_DEEP, 64, 3, 256) A3D_CASEV(V_BM256_DEEP, 96, 3, 256) A3D_CASEV(V_BM256_DEEP, 128, 3, 256)
     A3D_CASEV(V_BM256_DEEP, 256, 3, 256)
 #undef A3D_CASEV
+#define A3D_CASEP(BN) \
+  if (bn == BN) { \
+    using C_ = tc::Cfg<BN, 128, false, false>; \
+    if (variant == V_PERSIST2) return launch_persist<C_, 2>(ctx, tmA, tmB, p, st); \
+    if (variant == V_PERSIST3) return launch_persist<C_, 3>(ctx, tmA, tmB, p, st); \
+    if (variant == V_PERSIST4) return launch_persist<C_, 4>(ctx, tmA, tmB, p, st); \
+  }
+    if (variant >= V_PERSIST2 && splits == 1) { A3D_CASEP(64) A3D_CASEP(96) A3D_CASEP(128) A3D_CASEP(192) A3D_CASEP(256) }
+#undef A3D_CASEP
   }
   a3d_set_error("tc gemm: no kernel for BN=%d KCB=%d variant=%d", bn, kcb, variant);
   return A3D_ENOTSUP;
@@ -234,6 +281,7 @@ bool variant_exists(int bn, int kcb, int variant) {
   if (variant == V_BASE) return true;
   if (kcb != 128) return false;
   if (variant == V_DEEP) return bn == 64 || bn == 96 || bn == 128 || bn == 192 || bn == 256;
+  if (variant >= V_PERSIST2) return persist_enabled() && (bn == 64 || bn == 96 || bn == 128 || bn == 192 || bn == 256);
   return bn == 64 || bn == 96 || bn == 128 || bn == 256;
 }
 
@@ -518,7 +566,9 @@ int a3d_tc_conv_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, con
       for (int variant = 0; variant < V_COUNT; ++variant) {
         if (!variant_exists(bn, kcb, variant)) continue;
         // 256-row tiles only unsplit and when they still give every SM about one CTA
-        if (variant >= V_BM256 && (sp != 1 || tiles / 2 < ctx->sm_count * 3 / 4)) continue;
+        if ((variant == V_BM256 || variant == V_BM256_DEEP) && (sp != 1 || tiles / 2 < ctx->sm_count * 3 / 4)) continue;
+        // persistent kernel: unsplit, and only where a CTA gets more than one tile
+        if (variant >= V_PERSIST2 && (sp != 1 || tiles <= ctx->sm_count)) continue;
         bool dup = false;
         for (int k = 0; k < nc; ++k) dup |= (cand[k].bn == bn && cand[k].splits == sp && cand[k].variant == variant);
         if (!dup && nc < 64) cand[nc++] = {bn, sp, variant};

@@ -155,6 +155,21 @@ def test_conv_fwd(ctx, layer, impl):
 LAYERS_BY_NAME = {l[0]: l for l in LAYERS}
 
 
+@pytest.mark.skipif(__import__("os").environ.get("A3D_TEST_PERSIST") != "1",
+                    reason="experimental persistent GEMM kernel (tc_persist.cuh): set A3D_TEST_PERSIST=1 A3D_PERSIST=1")
+@pytest.mark.parametrize("variant", [4, 5, 6])
+@pytest.mark.parametrize("bn", [64, 96, 128, 192, 256])
+@pytest.mark.parametrize("M", [300, 128 * 160 + 5, 128 * 700])
+def test_tc_gemm_persistent(ctx, variant, bn, M):
+    """persistent tile loop with double-buffered TMEM accumulators: 3 tiles (fewer than CTAs), 161 x n tiles (about one
+    per CTA) and 700 x n tiles (several per CTA: buffer reuse, stage-counter wrap-around across tiles)"""
+    N, K = 2 * bn - 8, 64 * 5
+    A = bf16_rand(M, K, seed=7)
+    B = bf16_rand(N, K, seed=8)
+    D = ctx.debug_tc_gemm(A, B, M, N, K, bn, 128, variant=variant)
+    assert rel_err(D, A.float() @ B.float().t()) < 2e-3
+
+
 @pytest.mark.parametrize("force", ["128,1,1", "128,1,2", "256,1,2", "256,1,3", "64,1,2", "96,1,3"])
 @pytest.mark.parametrize("layer", [LAYERS_BY_NAME[n] for n in ("conv2d_1", "fine_second", "conv2d_0_s2d4", "dcnf_conv2d_1")],
                          ids=["conv2d_1", "fine_second", "conv2d_0_s2d4", "dcnf_conv2d_1"])
