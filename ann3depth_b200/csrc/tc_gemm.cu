@@ -2,6 +2,7 @@
 // and the launchers used by the convolution / dense entry points.
 #include "tc_gemm.cuh"
 #include "tc_persist.cuh"
+#include "tc_mcast.cuh"
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -205,11 +206,50 @@ int launch_cfg(a3d_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, con
 //   2  256-row tile (two accumulators sharing every B stage: less L2->SM operand traffic), default ring
 //   3  256-row tile, three stages
 //   4..6  EXPERIMENTAL persistent kernel (tc_persist.cuh) with 2 / 3 / 4 stages; candidates only with A3D_PERSIST=1
-enum { V_BASE = 0, V_DEEP = 1, V_BM256 = 2, V_BM256_DEEP = 3, V_PERSIST2 = 4, V_PERSIST3 = 5, V_PERSIST4 = 6, V_COUNT = 7 };
+//   7..10 EXPERIMENTAL cluster kernel (tc_mcast.cuh): weight tile multicast to 2 / 4 CTAs, default ring / one stage
+//         more; candidates only with A3D_MCAST=1.  NOTE: tmB must then have a box of BN / CL rows (mcast_cl()).
+enum { V_BASE = 0, V_DEEP = 1, V_BM256 = 2, V_BM256_DEEP = 3, V_PERSIST2 = 4, V_PERSIST3 = 5, V_PERSIST4 = 6,
+       V_MC2 = 7, V_MC2_DEEP = 8, V_MC4 = 9, V_MC4_DEEP = 10, V_COUNT = 11 };
+int mcast_cl(int variant) { return variant == V_MC2 || variant == V_MC2_DEEP ? 2 : variant == V_MC4 || variant == V_MC4_DEEP ? 4 : 1; }
+bool mcast_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("A3D_MCAST"); v = e ? atoi(e) : 0; }
+  return v != 0;
+}
 bool persist_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("A3D_PERSIST"); v = e ? atoi(e) : 0; }
   return v != 0;
+}
+
+template <class C, int CL>
+int launch_mcast(a3d_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB_slice, const tc::Params& p_in, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    A3D_CHECK_CUDA(cudaFuncSetAttribute(tc::gemm_mcast_kernel<C, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  tc::Params p = p_in;
+  if (p.atomic || p.kb_per_split < p.num_kb) { a3d_set_error("multicast gemm: no split-K"); return A3D_ENOTSUP; }
+  CUtensorMap tmC;
+  bool use_c = false;
+  int rc = maybe_tma_out(ctx, p, &tmC, &use_c);
+  if (rc) return rc;
+  const bool ok = use_c && ((p.epi == tc::EPI_TMA_F32 && C::BN % 32 == 0) || (p.epi == tc::EPI_TMA_BF16 && C::BN % 64 == 0));
+  if (!ok) { a3d_set_error("multicast gemm: needs a TMA-store epilogue (f32: BN %% 32, bf16: BN %% 64)"); return A3D_ENOTSUP; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ceil_div(ceil_div(p.M, 128), CL) * CL, ceil_div(p.N, C::BN), 1);
+  cfg.blockDim = dim3(192, 1, 1);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  A3D_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc::gemm_mcast_kernel<C, CL>, tmA, tmB_slice, tmC, p));
+  A3D_LAUNCH_OK(ctx);
+  return 0;
 }
 
 template <class C, int NSTAGE>
@@ -271,8 +311,19 @@ int launch_kk(a3d_ctx* ctx, int bn, int kcb, const CUtensorMap& tmA, const CUten
     if (variant == V_PERSIST3) return launch_persist<C_, 3>(ctx, tmA, tmB, p, st); \
     if (variant == V_PERSIST4) return launch_persist<C_, 4>(ctx, tmA, tmB, p, st); \
   }
-    if (variant >= V_PERSIST2 && splits == 1) { A3D_CASEP(64) A3D_CASEP(96) A3D_CASEP(128) A3D_CASEP(192) A3D_CASEP(256) }
+    if (variant >= V_PERSIST2 && variant <= V_PERSIST4 && splits == 1) {
+      A3D_CASEP(64) A3D_CASEP(96) A3D_CASEP(128) A3D_CASEP(192) A3D_CASEP(256)
+    }
 #undef A3D_CASEP
+#define A3D_CASEM(BN) \
+  if (bn == BN) { \
+    if (variant == V_MC2) return launch_mcast<tc::Cfg<BN, 128, false, false>, 2>(ctx, tmA, tmB, p, st); \
+    if (variant == V_MC2_DEEP) return launch_mcast<tc::Cfg<BN, 128, false, false, 64, 3>, 2>(ctx, tmA, tmB, p, st); \
+    if (variant == V_MC4) return launch_mcast<tc::Cfg<BN, 128, false, false>, 4>(ctx, tmA, tmB, p, st); \
+    if (variant == V_MC4_DEEP) return launch_mcast<tc::Cfg<BN, 128, false, false, 64, 3>, 4>(ctx, tmA, tmB, p, st); \
+  }
+    if (variant >= V_MC2 && splits == 1) { A3D_CASEM(64) A3D_CASEM(128) A3D_CASEM(256) }
+#undef A3D_CASEM
   }
   a3d_set_error("tc gemm: no kernel for BN=%d KCB=%d variant=%d", bn, kcb, variant);
   return A3D_ENOTSUP;
@@ -281,6 +332,7 @@ bool variant_exists(int bn, int kcb, int variant) {
   if (variant == V_BASE) return true;
   if (kcb != 128) return false;
   if (variant == V_DEEP) return bn == 64 || bn == 96 || bn == 128 || bn == 192 || bn == 256;
+  if (variant >= V_MC2) return mcast_enabled() && (bn == 64 || bn == 128 || bn == 256);
   if (variant >= V_PERSIST2) return persist_enabled() && (bn == 64 || bn == 96 || bn == 128 || bn == 192 || bn == 256);
   return bn == 64 || bn == 96 || bn == 128 || bn == 256;
 }
@@ -520,8 +572,10 @@ int a3d_tc_conv_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, con
 
   auto launch = [&](int bn, int splits, int variant) -> int {
     CUtensorMap tmB;
+    const int box_rows = bn / mcast_cl(variant);              // cluster kernel: every CTA loads a slice of the weight tile
     int r = kc == 8 ? make_tmap_chunked(ctx, &tmB, w, d->K, (uint64_t)d->R * d->S * d->C, bn)
-                    : make_tmap_2d(ctx, &tmB, w, d->K, (uint64_t)d->R * d->S * d->C, (uint64_t)d->R * d->S * d->C, kc, bn);
+                    : make_tmap_2d(ctx, &tmB, w, d->K, (uint64_t)d->R * d->S * d->C, (uint64_t)d->R * d->S * d->C, kc,
+                                   box_rows);
     if (r) return r;
     tc::Params q = p;
     if (!can_split) splits = 1;
@@ -568,7 +622,9 @@ int a3d_tc_conv_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, con
         // 256-row tiles only unsplit and when they still give every SM about one CTA
         if ((variant == V_BM256 || variant == V_BM256_DEEP) && (sp != 1 || tiles / 2 < ctx->sm_count * 3 / 4)) continue;
         // persistent kernel: unsplit, and only where a CTA gets more than one tile
-        if (variant >= V_PERSIST2 && (sp != 1 || tiles <= ctx->sm_count)) continue;
+        if (variant >= V_PERSIST2 && variant <= V_PERSIST4 && (sp != 1 || tiles <= ctx->sm_count)) continue;
+        // cluster kernel: unsplit, enough M tiles that sharing the weight tile matters
+        if (variant >= V_MC2 && (sp != 1 || ceil_div(M, 128) < 8)) continue;
         bool dup = false;
         for (int k = 0; k < nc; ++k) dup |= (cand[k].bn == bn && cand[k].splits == sp && cand[k].variant == variant);
         if (!dup && nc < 64) cand[nc++] = {bn, sp, variant};
@@ -913,7 +969,7 @@ extern "C" int a3d_debug_tc_gemm_v(a3d_ctx* ctx, const uint16_t* A, const uint16
   else rc = make_tmap_2d(ctx, &tmA, A, M, K, K, kelems, 128);
   if (rc) return rc;
   if (b_mn) rc = make_tmap_2d(ctx, &tmB, B, K, N, N, 64, 64);
-  else rc = make_tmap_2d(ctx, &tmB, B, N, K, K, kelems, bn);
+  else rc = make_tmap_2d(ctx, &tmB, B, N, K, K, kelems, bn / mcast_cl(variant));
   if (rc) return rc;
   tc::Params p{};
   p.M = M; p.N = N; p.num_kb = K / kelems; p.a_mode = tc::A_TILED;

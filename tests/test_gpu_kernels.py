@@ -170,6 +170,21 @@ def test_tc_gemm_persistent(ctx, variant, bn, M):
     assert rel_err(D, A.float() @ B.float().t()) < 2e-3
 
 
+@pytest.mark.skipif(__import__("os").environ.get("A3D_TEST_MCAST") != "1",
+                    reason="experimental cluster/multicast GEMM kernel (tc_mcast.cuh): set A3D_TEST_MCAST=1 A3D_MCAST=1")
+@pytest.mark.parametrize("variant", [7, 8, 9, 10])
+@pytest.mark.parametrize("bn", [64, 128, 256])
+@pytest.mark.parametrize("M", [100, 128 * 5 + 7, 128 * 301])
+def test_tc_gemm_multicast(ctx, variant, bn, M):
+    """weight tile multicast across a cluster of 2 / 4 CTAs along M: fewer tiles than one cluster (padding CTAs), a ragged
+    last cluster (6 tiles), many clusters; K = 9 k-blocks > ring depth"""
+    N, K = 2 * bn - 8, 64 * 9
+    A = bf16_rand(M, K, seed=7)
+    B = bf16_rand(N, K, seed=8)
+    D = ctx.debug_tc_gemm(A, B, M, N, K, bn, 128, variant=variant)
+    assert rel_err(D, A.float() @ B.float().t()) < 2e-3
+
+
 @pytest.mark.parametrize("force", ["128,1,1", "128,1,2", "256,1,2", "256,1,3", "64,1,2", "96,1,3"])
 @pytest.mark.parametrize("layer", [LAYERS_BY_NAME[n] for n in ("conv2d_1", "fine_second", "conv2d_0_s2d4", "dcnf_conv2d_1")],
                          ids=["conv2d_1", "fine_second", "conv2d_0_s2d4", "dcnf_conv2d_1"])

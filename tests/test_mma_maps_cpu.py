@@ -31,3 +31,5 @@ def test_persistent_kernel_barrier_protocol():
     for nstage in (2, 3, 4):
         for tiles, nkb in ((1, 1), (2, 9), (5, 3), (8, 2)):
             P.simulate(nstage, tiles, nkb, seed=nstage * 31 + tiles)
+    for cl, nstage, nkb in ((2, 2, 9), (4, 2, 5), (4, 3, 50), (2, 3, 1)):
+        P.simulate_mcast(cl, nstage, nkb, seed=cl * 7 + nkb)

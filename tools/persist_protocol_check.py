@@ -95,6 +95,86 @@ def simulate(nstage, tiles, nkb, seed):
     assert sorted(log["epi"]) == sorted((w, j) for w in range(4) for j in range(tiles))
 
 
+class TxBar:
+    """full barrier of the multicast kernel: one arrival (expect_tx by the local producer) + (1 + CL) transfers; the
+    transfers of peers may land before the local expect_tx (the pending arrival keeps the phase open)."""
+    def __init__(self, units):
+        self.units, self.arrived, self.tx, self.phase = units, 0, 0, 0
+
+    def _maybe_flip(self):
+        if self.arrived == 1 and self.tx == self.units:
+            self.phase ^= 1
+            self.arrived, self.tx = 0, 0
+
+    def expect(self):
+        assert self.arrived == 0
+        self.arrived = 1
+        self._maybe_flip()
+
+    def complete(self):
+        self.tx += 1
+        assert self.tx <= self.units, "more transfers than one phase expects: a slice overtook a whole round"
+        self._maybe_flip()
+
+    def passed(self, parity):
+        return self.phase != parity
+
+
+def simulate_mcast(cl, nstage, nkb, seed):
+    """csrc/tc_mcast.cuh: CL CTAs, each a producer and an MMA issuer; empty[s] of every CTA counts CL arrivals (every
+    issuer's commit is multicast), full[s] = own A box + CL weight slices.  Checks: no deadlock, a stage is never
+    written (by anybody's slice or the local A box) while the local MMAs of the previous round still read it."""
+    rng = random.Random(seed)
+    full = [[TxBar(1 + cl) for _ in range(nstage)] for _ in range(cl)]
+    empty = [[MBar(cl) for _ in range(nstage)] for _ in range(cl)]
+    reading = [[None] * nstage for _ in range(cl)]     # round whose data the stage holds / is being filled with
+    consumed = [[-1] * nstage for _ in range(cl)]      # last round the local MMAs have retired from the stage
+    mma_log = [[] for _ in range(cl)]
+
+    def write_check(c, s, rnd):
+        assert consumed[c][s] == rnd - nstage or rnd < nstage, \
+            f"CTA {c} stage {s}: data of round {rnd} written before round {rnd - nstage} was consumed"
+
+    def producer(c):
+        for i in range(nkb):
+            s, ph = i % nstage, (i // nstage) & 1
+            while not empty[c][s].passed(ph ^ 1):
+                yield
+            full[c][s].expect()
+            write_check(c, s, i)
+            full[c][s].complete()                      # own A box
+            yield
+            for d in range(cl):                        # this CTA's slice, multicast to every CTA
+                write_check(d, s, i)
+                full[d][s].complete()
+            yield
+
+    def issuer(c):
+        for i in range(nkb):
+            s, ph = i % nstage, (i // nstage) & 1
+            while not full[c][s].passed(ph):
+                yield
+            mma_log[c].append(i)
+            consumed[c][s] = i
+            for d in range(cl):                        # multicast commit
+                empty[d][s].arrive()
+            yield
+
+    roles = [producer(c) for c in range(cl)] + [issuer(c) for c in range(cl)]
+    alive = list(range(len(roles)))
+    idle = 0
+    while alive:
+        i = rng.choice(alive)
+        before = sum(len(m) for m in mma_log)
+        try:
+            next(roles[i])
+        except StopIteration:
+            alive.remove(i)
+        idle = 0 if sum(len(m) for m in mma_log) != before else idle + 1
+        assert idle < 20000, "deadlock"
+    assert all(m == list(range(nkb)) for m in mma_log)
+
+
 def main():
     n = 0
     for nstage in (2, 3, 4):
@@ -104,6 +184,14 @@ def main():
                     simulate(nstage, tiles, nkb, seed)
                     n += 1
     print(f"persistent-kernel barrier protocol OK ({n} schedules)")
+    n = 0
+    for cl in (2, 4):
+        for nstage in (2, 3):
+            for nkb in (1, 2, 5, 9, 50):
+                for seed in range(5):
+                    simulate_mcast(cl, nstage, nkb, seed)
+                    n += 1
+    print(f"multicast-kernel barrier protocol OK ({n} schedules)")
 
 
 if __name__ == "__main__":
