@@ -235,7 +235,8 @@ int launch_mcast(a3d_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB_sl
   bool use_c = false;
   int rc = maybe_tma_out(ctx, p, &tmC, &use_c);
   if (rc) return rc;
-  const bool ok = use_c && ((p.epi == tc::EPI_TMA_F32 && C::BN % 32 == 0) || (p.epi == tc::EPI_TMA_BF16 && C::BN % 64 == 0));
+  const bool ok = use_c && ((p.epi == tc::EPI_TMA_F32 && C::BN % 32 == 0) || (p.epi == tc::EPI_TMA_BF16 && C::BN % 64 == 0) ||
+                           (p.epi == tc::EPI_POOL4_BF16 && C::BN == 256));
   if (!ok) { a3d_set_error("multicast gemm: needs a TMA-store epilogue (f32: BN %% 32, bf16: BN %% 64)"); return A3D_ENOTSUP; }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(ceil_div(ceil_div(p.M, 128), CL) * CL, ceil_div(p.N, C::BN), 1);
@@ -537,6 +538,14 @@ int a3d_tc_conv_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, con
     // 128-row tiles with two stages of 48 KB (two CTAs per SM, one CTA's epilogue under the other's main loop),
     // the same with three stages, or 256-row tiles (both accumulators fill the 512 TMEM columns)
     auto run = [&](int c) -> int {
+      if (c >= 4) {                                // EXPERIMENTAL (A3D_MCAST=1): weight tile multicast to 2 / 4 CTAs
+        const int cl = c == 4 ? 2 : 4;
+        CUtensorMap tmBs;
+        int r = make_tmap_2d(ctx, &tmBs, w, 256, (uint64_t)d->R * d->S * d->C, (uint64_t)d->R * d->S * d->C, 64, 256 / cl);
+        if (r) return r;
+        if (cl == 2) return launch_mcast<tc::Cfg<256, 128, false, false>, 2>(ctx, tmA, tmBs, p, st);
+        return launch_mcast<tc::Cfg<256, 128, false, false>, 4>(ctx, tmA, tmBs, p, st);
+      }
       if (c == 1) return launch_cfg<tc::Cfg<256, 128, false, false, 64, 3>>(ctx, tmA, tmB, p, 1, st);
       if (c == 2) return launch_cfg<tc::Cfg<256, 128, false, false, 64, 2, false, 256>>(ctx, tmA, tmB, p, 1, st);
       if (c == 3) return launch_cfg<tc::Cfg<256, 128, false, false, 64, 3, false, 256>>(ctx, tmA, tmB, p, 1, st);
@@ -547,7 +556,7 @@ int a3d_tc_conv_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, con
     const int kv[16] = {5, d->N, d->H, d->W, d->C, d->K, d->R, d->S, d->stride_h, d->stride_w, d->pad_t, d->pad_l,
                         d->P, d->Q, d->ldy, pool_idx != nullptr};
     memcpy(key.v, kv, sizeof(kv));
-    return run(autotune(key, 4, run, st));
+    return run(autotune(key, mcast_enabled() ? 6 : 4, run, st));
   }
   if (!a3d_tc_conv_fwd_supported(d)) {
     a3d_set_error("tc conv fwd: unsupported shape (C=%d must be a multiple of 16)", d->C);

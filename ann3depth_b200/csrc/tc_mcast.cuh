@@ -18,7 +18,8 @@
 //     before exit (no CTA leaves while peers can still signal its barriers);
 //   * grid.x is padded to a multiple of CL; a padding CTA (m0 >= M) runs the whole protocol on tile 0's A operand and
 //     stores nothing.
-// Epilogues: tc::EPI_TMA_F32 / tc::EPI_TMA_BF16 without split-K, as in tc_persist.cuh.
+// Epilogues: tc::EPI_TMA_F32 / tc::EPI_TMA_BF16 without split-K, as in tc_persist.cuh, and (BN = 256) the pool-fused
+// tc::EPI_POOL4_BF16 of fine/first.
 #pragma once
 #include "tc_gemm.cuh"
 
@@ -197,6 +198,53 @@ gemm_mcast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             ptx::tma_store_2d(&tmC, slab, col0, row0);
             ptx::bulk_commit();
           }
+        }
+      } else if (C::BN == 256 && p.epi == EPI_POOL4_BF16) {
+        // fused 2x2 max-pool over the four 64-column groups (same epilogue as tc_gemm.cuh EPI_POOL4_BF16)
+        uint8_t* slab = slab0;
+        const int row = row0 + lane;
+        const bool row_ok = row < p.M;
+        const uint32_t srow = ptx::smem_u32(slab) + (uint32_t)lane * 128u;
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t r0[16], r1[16], r2[16], r3[16];
+          const uint32_t taddr = tmem_acc + (uint32_t)(cc * 16);
+          __syncwarp();
+          ptx::tmem_ld_x16(taddr, r0);
+          ptx::tmem_ld_x16(taddr + 64, r1);
+          ptx::tmem_ld_x16(taddr + 128, r2);
+          ptx::tmem_ld_x16(taddr + 192, r3);
+          ptx::tmem_ld_wait();
+          float v[16];
+          uint32_t gi[4] = {0, 0, 0, 0};
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            float m = __uint_as_float(r0[q]);
+            uint32_t g = 0;
+            const float a1 = __uint_as_float(r1[q]), a2 = __uint_as_float(r2[q]), a3 = __uint_as_float(r3[q]);
+            if (a1 > m) { m = a1; g = 1; }                    // strict '>' keeps the FIRST arg-max (TF MaxPoolGrad)
+            if (a2 > m) { m = a2; g = 2; }
+            if (a3 > m) { m = a3; g = 3; }
+            if (p.bias) m += __ldg(p.bias + cc * 16 + q);
+            if (p.flags & A3D_EPI_RELU) m = fmaxf(m, 0.f);
+            v[q] = m;
+            gi[q >> 2] |= g << ((q & 3) * 8);
+          }
+#pragma unroll
+          for (int qq = 0; qq < 2; ++qq) {
+            const int q = cc * 2 + qq;
+            ptx::st_shared_v4_b32(srow + (uint32_t)((q ^ (lane & 7)) << 4), pack_bf16x2(v[8 * qq], v[8 * qq + 1]),
+                                  pack_bf16x2(v[8 * qq + 2], v[8 * qq + 3]), pack_bf16x2(v[8 * qq + 4], v[8 * qq + 5]),
+                                  pack_bf16x2(v[8 * qq + 6], v[8 * qq + 7]));
+          }
+          if (p.pool_idx && row_ok)
+            *reinterpret_cast<uint4*>(p.pool_idx + (size_t)row * 64 + cc * 16) = make_uint4(gi[0], gi[1], gi[2], gi[3]);
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::tma_store_2d(&tmC, slab, 0, row0);
+          ptx::bulk_commit();
         }
       } else {                                                // EPI_TMA_BF16
         constexpr int NCH = C::BN / 64;

@@ -611,6 +611,27 @@ def test_conv_pool4_fwd_bwd(ctx, impl):
     assert torch.equal(big.float().view(-1, 4, 64), exp)
 
 
+@pytest.mark.skipif(__import__("os").environ.get("A3D_TEST_MCAST") != "1",
+                    reason="experimental cluster/multicast GEMM kernel (tc_mcast.cuh): set A3D_TEST_MCAST=1 A3D_MCAST=1")
+@pytest.mark.parametrize("force", ["4", "5"])
+def test_conv_pool4_fwd_multicast(ctx, monkeypatch, force):
+    """pool-fused fine/first GEMM through the cluster kernel (weight tile multicast to 2 / 4 CTAs) == one-CTA kernel"""
+    N, H, W, Cc = 3, 57, 76, 64
+    d = ops.conv_desc(N, H, W, Cc, 256, 3, 3, 1, "valid", ldy=64, impl=L.IMPL_AUTO)
+    x = bf16_rand(N, H, W, Cc, seed=40)
+    w = bf16_rand(256, 3, 3, Cc, seed=41, scale=1.0 / math.sqrt(9 * Cc))
+    bias = (torch.rand(64, generator=torch.Generator().manual_seed(42)) - 0.5).to(DEV) * 0.2
+    res = []
+    for f in ("0", force):
+        monkeypatch.setenv("A3D_POOL4_FORCE", f)
+        y = torch.full((N, d.P, d.Q, 64), 7.0, dtype=torch.bfloat16, device=DEV)
+        idx = torch.full((N, d.P, d.Q, 64), 9, dtype=torch.uint8, device=DEV)
+        ctx.conv2d_pool4_fwd(d, x, w, bias, relu=True, out=y, idx=idx)
+        res.append((y, idx))
+    monkeypatch.delenv("A3D_POOL4_FORCE")
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])     # same MMA order: bit-exact
+
+
 def test_resize_s2d_matches_resize_then_space_to_depth(ctx):
     g = torch.Generator().manual_seed(44)
     src = torch.rand(2, 480, 640, 3, generator=g).to(DEV)
