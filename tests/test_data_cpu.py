@@ -42,9 +42,13 @@ def _example(features, packed):
 
 
 def _write(path, records):
+    # masked CRC-32C framing as TFRecordWriter writes it (the CRC itself is pinned to the RFC 3720 vectors in
+    # tests/test_summary_cpu.py); the reader verifies it
+    from ann3depth_b200.summary import masked_crc32c
     with open(path, "wb") as f:
         for r in records:
-            f.write(struct.pack("<Q", len(r)) + b"\0\0\0\0" + r + b"\0\0\0\0")
+            head = struct.pack("<Q", len(r))
+            f.write(head + struct.pack("<I", masked_crc32c(head)) + r + struct.pack("<I", masked_crc32c(r)))
 
 
 def test_tfrecord_roundtrip(tmp_path):

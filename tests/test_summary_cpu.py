@@ -33,6 +33,22 @@ def test_tfrecord_frames_are_read_by_the_package_reader(tmp_path):
     assert list(data.tfrecord_iterator(str(p))) == [b"first", b"", bytes(range(200))]
 
 
+def test_tfrecord_reader_rejects_corruption(tmp_path):
+    from ann3depth_b200 import data
+    good = S.tfrecord_frame(b"first") + S.tfrecord_frame(bytes(range(100)))
+    cases = {"flipped length bit": bytearray(good), "flipped data bit": bytearray(good), "truncated": bytearray(good[:-3]),
+             "half a header": bytearray(good + b"\x01\x02\x03")}
+    cases["flipped length bit"][0] ^= 0x10
+    cases["flipped data bit"][12 + 2] ^= 0x01
+    for name, blob in cases.items():
+        p = tmp_path / "bad.tfrecords"
+        p.write_bytes(bytes(blob))
+        with pytest.raises(IOError):
+            list(data.tfrecord_iterator(str(p)))
+    p.write_bytes(bytes(cases["flipped data bit"]))
+    assert len(list(data.tfrecord_iterator(str(p), verify=None))) == 2        # framing intact, payload unchecked
+
+
 def test_event_file_is_valid_for_tensorboard(tmp_path):
     loader_mod = pytest.importorskip("tensorboard.backend.event_processing.event_file_loader")
     w = S.EventWriter(str(tmp_path))
