@@ -249,17 +249,23 @@ class MSDNNet:
         if fused_dense_adam:
             self._dense_wgrad_adam("0", self.c4.view(B, 12288), self.g_d0)
         n = "coarse/conv/conv2d_"
-        c.conv2d_wgrad(self.d_c4, self.c3, self.g_c4, dw=self.gw(n + "4" + K), db=self.gw(n + "4/bias"))
+
+        def wgrad(desc, x, dy, name):
+            # bias gradient (a column sum of dY, not a tensor-core op) as its own call, like the multi-stream schedule
+            # does: bench.py's per-kernel table then times the wgrad GEMM alone
+            c.bias_grad_bf16(dy.view(-1, dy.shape[-1]), dy.shape[-1], self.gw(name + "/bias"))
+            c.conv2d_wgrad(desc, x, dy, dw=self.gw(name + K), db=None)
+        wgrad(self.d_c4, self.c3, self.g_c4, n + "4")
         c.conv2d_dgrad(self.d_c4, self.g_c4, self.w(n + "4" + K), out=self.g_c3, relu_src=self.c3)
-        c.conv2d_wgrad(self.d_c3, self.c2, self.g_c3, dw=self.gw(n + "3" + K), db=self.gw(n + "3/bias"))
+        wgrad(self.d_c3, self.c2, self.g_c3, n + "3")
         c.conv2d_dgrad(self.d_c3, self.g_c3, self.w(n + "3" + K), out=self.g_c2, relu_src=self.c2)
-        c.conv2d_wgrad(self.d_c2, self.p1, self.g_c2, dw=self.gw(n + "2" + K), db=self.gw(n + "2/bias"))
+        wgrad(self.d_c2, self.p1, self.g_c2, n + "2")
         c.conv2d_dgrad(self.d_c2, self.g_c2, self.w(n + "2" + K), out=self.g_p1)
         c.maxpool2x2_idx_bwd(self.i1, self.g_p1, (self.B, 27, 37, 256), out=self.g_c1)
-        c.conv2d_wgrad(self.d_c1, self.p0, self.g_c1, dw=self.gw(n + "1" + K), db=self.gw(n + "1/bias"))
+        wgrad(self.d_c1, self.p0, self.g_c1, n + "1")
         c.conv2d_dgrad(self.d_c1, self.g_c1, self.w(n + "1" + K), out=self.g_p0)
         c.maxpool2x2_idx_bwd(self.i0, self.g_p0, (self.B, 55, 74, 96), out=self.g_c0)
-        c.conv2d_wgrad(self.d_c0, self.img4, self.g_c0, dw=self.gw(n + "0" + K), db=self.gw(n + "0/bias"))
+        wgrad(self.d_c0, self.img4, self.g_c0, n + "0")
         self._mask_padding("coarse/conv/conv2d_0/kernel")
         hook(self, "coarse_conv")
 
