@@ -292,7 +292,7 @@ def test_conv_dgrad_prepared_filter(ctx):
         a = ctx.conv2d_dgrad(d, dy, w, relu_src=src)
         b = ctx.conv2d_dgrad(d, dy, None, relu_src=src, wflip=wf)
         assert torch.equal(wf, w.permute(3, 1, 2, 0).flip(1, 2).contiguous())
-        assert rel_err(a, b) < 5e-3        # the two calls may be tuned to different tiles / split-K orders
+        assert rel_err(a, b) < 1e-2        # two tunings / split-K orders: at most one bf16 ulp (2^-7 relative) apart
     _, H, W, Cc, K, R, S, stride, padding = LAYERS_BY_NAME["conv2d_4"]      # strided: no flipped filter
     d = ops.conv_desc(2, H, W, Cc, K, R, S, stride, padding, impl=L.IMPL_AUTO)
     assert ctx.conv2d_dgrad_prepare(d, bf16_rand(K, R, S, Cc, seed=21)) is None
