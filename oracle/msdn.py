@@ -180,12 +180,13 @@ def group_of(name: str) -> str:
     raise KeyError(name)
 
 
-def grads(p, images, depths, dropout_mask, which="coarse", q=_ident):
+def grads(p, images, depths, dropout_mask, which="coarse", q=_ident, copy=True):
     """Gradients as ``optimizer.compute_gradients(loss, var_list)`` would return them
     (src/models.py:314): 'coarse' -> d loss_coarse / d coarse vars; 'fine' -> d loss_fine /
     d fine vars (coarse map treated as a constant input, since only fine variables are in
     var_list); 'all' -> both, for the all-parameter gradient-parity configuration."""
-    leaves = OrderedDict((n, v.detach().clone().requires_grad_(True)) for n, v in p.items())
+    # copy=False: the leaves alias the caller's tensors (no 283 MB clone per step; the timed CPU arm of bench.py)
+    leaves = OrderedDict((n, (v.detach().clone() if copy else v.detach()).requires_grad_(True)) for n, v in p.items())
     out = forward(leaves, images, depths, dropout_mask, True, q)
     res = OrderedDict()
     if which in ("coarse", "all"):
@@ -213,9 +214,10 @@ class TrainState:
         self.beta2 = beta2
 
 
-def train_step(state: TrainState, images, depths, dropout_mask, q=_ident):
+def train_step(state: TrainState, images, depths, dropout_mask, q=_ident, inplace=False):
     """One ``session.run(model_op)`` (src/ann3depth.py:126-127): forward of both stacks, then
-    only the taken tf.case branch's gradient/apply ops (src/models.py:353-359)."""
+    only the taken tf.case branch's gradient/apply ops (src/models.py:353-359).
+    inplace=True updates variables and Adam slots in place, as TF does (no per-step copies of the 283 MB state)."""
     B = images.shape[0]
     ph = phase_of(state.global_step, B)
     if ph == 3:
@@ -223,13 +225,14 @@ def train_step(state: TrainState, images, depths, dropout_mask, q=_ident):
         state.global_step += 1
         return out, ph
     which = "coarse" if ph == 1 else "fine"
-    g, out = grads(state.p, images, depths, dropout_mask, which, q)
+    g, out = grads(state.p, images, depths, dropout_mask, which, q, copy=not inplace)
     for gname in (("CoarseConv", "CoarseDense") if ph == 1 else ("FineA", "FineB")):
         state.t[gname] += 1
     for n, gr in g.items():
         gname = group_of(n)
         lr = ADAM_GROUPS[gname][0]
-        state.p[n], state.m[n], state.v[n] = T.tf_adam_update(
+        upd = T.tf_adam_update_ if inplace else T.tf_adam_update
+        state.p[n], state.m[n], state.v[n] = upd(
             state.p[n], gr, state.m[n], state.v[n], state.t[gname], lr,
             ADAM_BETA1, state.beta2, ADAM_EPS)
     state.global_step += 1

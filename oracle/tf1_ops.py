@@ -164,6 +164,17 @@ def tf_adam_update(w, g, m, v, t, lr, beta1=0.9, beta2=0.999, eps=1e-8):
     return w, m, v
 
 
+def tf_adam_update_(w, g, m, v, t, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+    """In-place form of ``tf_adam_update`` (TF updates its variables and slots in place: ApplyAdam writes
+    var/m/v, no copies).  Same arithmetic, same order of operations; one temporary the size of the variable."""
+    lr_t = lr * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
+    with torch.no_grad():
+        m.mul_(beta1).add_(g, alpha=1.0 - beta1)
+        v.mul_(beta2).addcmul_(g, g, value=1.0 - beta2)
+        w.addcdiv_(m, torch.sqrt(v).add_(eps), value=-lr_t)
+    return w, m, v
+
+
 def sgd_update(w, g, lr):
     """``tf.train.GradientDescentOptimizer(lr)`` apply (src/models.py:198-200)."""
     return w - lr * g
