@@ -40,12 +40,34 @@ class StopAtSignalHook:
         self.signal_received = signum
 
 
-def save_checkpoint(op, ckptdir):
-    os.makedirs(ckptdir, exist_ok=True)
+CKPT_FORMAT = 2
+
+
+def save_checkpoint(op, ckptdir, comm=None, write=True):
+    """Variables, optimizer slots and global_step, keyed by the reference's TF variable names in TF layouts (HWIO conv
+    kernels, [in, out] dense kernels): the file survives changes of the packed arena layout, like a TF Saver checkpoint
+    (MonitoredTrainingSession(checkpoint_dir=...), src/ann3depth.py:113-125).
+    Data parallel: EVERY rank must call this at the same step (`comm` set, `write` only on the chief) -- the sharded
+    optimizer keeps each rank's f32 master weights / Adam slots current only for the slice it owns, so they are
+    all-gathered first (dp.DataParallel.gather_master)."""
     net = op.net
-    state = {"w": net.arena.w.cpu(), "global_step": net.global_step}
+    if comm is not None:
+        if getattr(comm, "stream", None) is not None:
+            with torch.cuda.stream(comm.stream):
+                comm.stream.wait_stream(torch.cuda.current_stream())
+                comm.gather_master(net)
+            torch.cuda.current_stream().wait_stream(comm.stream)
+        else:
+            comm.gather_master(net)
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    if not write:
+        return
+    os.makedirs(ckptdir, exist_ok=True)
+    state = {"format": CKPT_FORMAT, "variables": net.arena.export_tf(), "global_step": net.global_step}
     if net.arena.m is not None:
-        state.update(m=net.arena.m.cpu(), v=net.arena.v.cpu())
+        state["adam_m"] = net.arena.export_tf(net.arena.m)
+        state["adam_v"] = net.arena.export_tf(net.arena.v)
     if hasattr(net, "adam_t"):
         state["adam_t"] = dict(net.adam_t)
     tmp = os.path.join(ckptdir, "model.ckpt.tmp")
@@ -58,20 +80,42 @@ def restore_checkpoint(op, ckptdir):
     if not os.path.exists(path):
         return False
     state = torch.load(path, map_location="cpu")
+    if state.get("format") != CKPT_FORMAT:
+        raise ValueError(f"{path}: unknown checkpoint format {state.get('format')!r} (expected {CKPT_FORMAT})")
     net = op.net
-    net.arena.w.copy_(state["w"])
-    net.arena.wb.copy_(net.arena.w)
+    net.arena.load_tf(state["variables"])          # also refreshes the bf16 mirror
     if hasattr(net, "refresh_derived"):
         net.refresh_derived()               # filters derived from the arena (MSDN pool-fused fine/first)
-    if "m" in state and net.arena.m is not None:
-        net.arena.m.copy_(state["m"])
-        net.arena.v.copy_(state["v"])
+    if "adam_m" in state and net.arena.m is not None:
+        net.arena.load_tf(state["adam_m"], net.arena.m)
+        net.arena.load_tf(state["adam_v"], net.arena.v)
     net.global_step = int(state["global_step"])
     if hasattr(net, "step_dev"):
         net.step_dev.fill_(net.global_step)
     if "adam_t" in state and hasattr(net, "adam_t"):
         net.adam_t.update(state["adam_t"])
     return True
+
+
+class StopConsensus:
+    """Data parallel: signals (SIGALRM / SIGTERM / SIGUSR1 ...) and the chief's checkpoint timer fire at different step
+    boundaries on different ranks, but leaving the loop or entering the checkpoint's all-gathers on one rank alone would
+    leave the others blocked in NCCL collectives forever.  Every `every` steps the ranks MAX-reduce (signal number,
+    checkpoint due) over the gloo control plane and all act on the reduced values at the same step."""
+
+    def __init__(self, world, every=8):
+        self.world, self.every = world, max(int(every), 1)
+
+    def decide(self, step, signal_received, ckpt_due):
+        """-> (signal number agreed to stop on, or 0; take a checkpoint now)"""
+        if self.world == 1:
+            return signal_received, ckpt_due
+        if step % self.every:
+            return 0, False
+        import torch.distributed as dist
+        t = torch.tensor([int(signal_received), int(bool(ckpt_due))], dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return int(t[0]), bool(t[1])
 
 
 def setup_model(args, comm=None):
@@ -120,14 +164,25 @@ def main(argv=None):
     writer = EventWriter(ckptdir) if chief else None
     summary_hook = SummaryHook(ckptdir, args.sumfreq, writer) if chief else None
     trace_hook = TraceHook(ckptdir, 5000, writer) if chief else None
-    if args.timeout:
+    # the reference arms the alarm only for cluster jobs (`if args.job_name != 'local'`, src/ann3depth.py:107-109):
+    # a plain single-process run is not stopped after --timeout seconds
+    if args.timeout and (world > 1 or args.job_name != "local"):
         logger.info(f"Starting alarm: {args.timeout} s timeout.")
         signal.alarm(args.timeout)
 
     logger.info("Starting session.")
+    consensus = StopConsensus(world)
     last_ckpt = last_log = time.time()
     last_log_step = op.global_step
-    while op.global_step < args.steps and not stop_hook.signal_received:       # StopAtStepHook(last_step)
+    stop_signal = 0
+    while op.global_step < args.steps:                                         # StopAtStepHook(last_step)
+        ckpt_due = chief and time.time() - last_ckpt > args.ckptfreq
+        stop_signal, take_ckpt = consensus.decide(op.global_step, stop_hook.signal_received, ckpt_due)
+        if take_ckpt:
+            save_checkpoint(op, ckptdir, comm, write=chief)
+            last_ckpt = time.time()
+        if stop_signal:                                                        # StopAtSignalHook.after_run
+            break
         inp.next_batch()
         if trace_hook is not None:
             trace_hook.run(op)
@@ -143,16 +198,23 @@ def main(argv=None):
             logger.info(f"step {op.global_step} losses {losses} global_step/sec {rate:.2f} "
                         f"images/sec {rate * args.batchsize * world:.1f}")
             last_log, last_log_step = now, op.global_step
-        if chief and time.time() - last_ckpt > args.ckptfreq:
-            torch.cuda.synchronize()
-            save_checkpoint(op, ckptdir)
-            last_ckpt = time.time()
+    if world > 1 and not stop_signal:
+        # the step limit is reached by all ranks together; a signal that arrived since the last consensus point still
+        # decides the exit code (and every rank takes part in the final checkpoint either way)
+        import torch.distributed as dist
+        t = torch.tensor([int(stop_hook.signal_received)], dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        stop_signal = int(t[0])
+    elif not stop_signal:
+        stop_signal = stop_hook.signal_received
     torch.cuda.synchronize()
+    save_checkpoint(op, ckptdir, comm, write=chief)
     if chief:
-        save_checkpoint(op, ckptdir)
         writer.close()
+    if hasattr(inp, "close"):
+        inp.close()
     logger.info("Session stopped.")
-    return stop_hook.signal_received
+    return stop_signal
 
 
 def parse_args(argv=None):

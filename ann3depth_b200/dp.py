@@ -100,11 +100,44 @@ class DataParallel:
                                    a.wb[s:s + chunk], lr, beta1, net.beta2, eps, max(net.adam_t[group], 1),
                                    1.0 / self.world, lr_t_dev=net.lr_dev[group])
             ops.allgather(self.ctx, a.wb[lo:hi], chunk)
+            self._sync_sharded_biases(net, lo, hi, chunk)
             done = torch.cuda.Event()
             done.record(self.stream)
         self._done.append(done)
         self.bytes_per_step += n * 2 * 2
         self._sharded = getattr(self, "_sharded", set()) | {name}
+
+    def _sync_sharded_biases(self, net, lo, hi, chunk):
+        """The kernels read biases as f32 from the MASTER buffer (msdn.MSDNNet.bias), which a sharded Adam updates only
+        on the rank that owns the slice: publish the owners' values of every bias segment in [lo, hi) to all ranks.
+        A few KB: each rank contributes its owned elements (zeros elsewhere) to one small f32 sum-allreduce."""
+        a = net.arena
+        key = ("bias_sync", lo, hi)
+        plan = getattr(self, "_bias_plans", None)
+        if plan is None:
+            plan = self._bias_plans = {}
+        if key not in plan:
+            segs, pos = [], 0
+            for s in a.specs.values():
+                if s.kind == "bias" and lo <= s.offset and s.offset + s.numel <= hi:
+                    segs.append((s.offset, s.numel, pos))
+                    pos += (s.numel + 3) // 4 * 4
+            own_lo, own_hi = lo + self.rank * chunk, lo + (self.rank + 1) * chunk
+            mine = []
+            for off, n, pos_ in segs:
+                b, e = max(off, own_lo), min(off + n, own_hi)
+                if b < e:
+                    mine.append((b, e, pos_ + b - off))
+            plan[key] = (segs, mine, torch.zeros(max(pos, 4), dtype=torch.float32, device=a.w.device))
+        segs, mine, stage = plan[key]
+        if not segs:
+            return
+        stage.zero_()
+        for b, e, p0 in mine:
+            stage[p0:p0 + e - b].copy_(a.w[b:e])
+        self.ctx.allreduce_sum(stage)
+        for off, n, p0 in segs:
+            a.w[off:off + n].copy_(stage[p0:p0 + n])
 
     def can_gather_dense(self, net, kernel_name, batch):
         """The activation-gather update needs equal 16-row-aligned row slices and a gathered batch <= 256."""

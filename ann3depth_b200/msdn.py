@@ -601,6 +601,24 @@ class MSDNNet:
                 self.refresh_derived()                   # fine/first moved: re-embed it into the pool-fused filter
         self.ctx.increment_i64(self.step_dev)            # global_step += 1 (src/models.py:329,343,356)
 
+    def _ensure_graph(self, phase):
+        """Warm-up launch outside capture (sets function attributes, allocates workspaces, autotunes first-use shapes;
+        its side effects on the variables are rolled back), then capture of the phase's step in a CUDA graph."""
+        gr = self._graphs.get(phase)
+        if gr is None:
+            saved = (self.arena.w.clone(), self.arena.m.clone(), self.arena.v.clone(), self.arena.wb.clone(),
+                     self.step_dev.clone())
+            self._enqueue_step(phase)
+            torch.cuda.synchronize()
+            self.arena.w.copy_(saved[0]); self.arena.m.copy_(saved[1]); self.arena.v.copy_(saved[2])
+            self.arena.wb.copy_(saved[3]); self.step_dev.copy_(saved[4])
+            self.refresh_derived()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                self._enqueue_step(phase)
+            self._graphs[phase] = gr        # the capture itself does not execute
+        return gr
+
     def train_step(self, use_graph=True):
         """One `session.run(model_op)` of the reference loop (src/ann3depth.py:126-127)."""
         assert self.train
@@ -609,22 +627,13 @@ class MSDNNet:
         for g in groups:                                   # each Adam instance owns its beta-power state
             self.adam_t[g] += 1
             self.lr_dev[g].fill_(ops.adam_lr_t(ADAM_LR[g], ADAM_BETA1, self.beta2, self.adam_t[g]))
+        # Data parallel: the warm-up launch in front of a capture executes one extra set of collectives.  EVERY rank
+        # therefore captures on its first step of a phase, also a rank whose step is about to run un-graphed (the chief's
+        # traced first step, summary.TraceHook): otherwise its peers' warm-up collectives would pair with its real ones
+        # and every later collective would be off by one step.
+        if use_graph or self.comm is not None:
+            gr = self._ensure_graph(phase)
         if use_graph:
-            gr = self._graphs.get(phase)
-            if gr is None:
-                # warm-up launch outside capture (sets func attributes, allocates workspaces), then capture
-                saved = (self.arena.w.clone(), self.arena.m.clone(), self.arena.v.clone(), self.arena.wb.clone(),
-                         self.step_dev.clone())
-                self._enqueue_step(phase)
-                torch.cuda.synchronize()
-                self.arena.w.copy_(saved[0]); self.arena.m.copy_(saved[1]); self.arena.v.copy_(saved[2])
-                self.arena.wb.copy_(saved[3]); self.step_dev.copy_(saved[4])
-                self.refresh_derived()
-                gr = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gr):
-                    self._enqueue_step(phase)
-                self._graphs[phase] = gr
-                # the capture itself does not execute; fall through to the replay below
             gr.replay()
         else:
             self._enqueue_step(phase)

@@ -453,19 +453,25 @@ class Context:
         L.check(self.lib.a3d_allreduce_sum(self.h, _ptr(t), count if count is not None else t.numel(), code,
                                            _stream()), "allreduce")
 
+    def reduce_scatter_sum(self, t, chunk):
+        """In place on t (world*chunk elements): afterwards rank r holds the sum in t[r*chunk:(r+1)*chunk]."""
+        L.check(self.lib.a3d_reduce_scatter_sum(self.h, _ptr(t), chunk, _code(t), _stream()), "reduce_scatter")
+
+    def allgather(self, t, chunk):
+        """In place on t (world*chunk elements): publishes every rank's slice t[r*chunk:(r+1)*chunk]."""
+        L.check(self.lib.a3d_allgather(self.h, _ptr(t), chunk, _code(t), _stream()), "allgather")
+
 
 def _code(t):
     return L.A3D_BF16 if t.dtype == torch.bfloat16 else L.A3D_F32
 
 
 def reduce_scatter_sum(ctx, t, chunk):
-    """In place on t (world*chunk elements): afterwards rank r holds the sum in t[r*chunk:(r+1)*chunk]."""
-    L.check(ctx.lib.a3d_reduce_scatter_sum(ctx.h, _ptr(t), chunk, _code(t), _stream()), "reduce_scatter")
+    ctx.reduce_scatter_sum(t, chunk)
 
 
 def allgather(ctx, t, chunk):
-    """In place on t (world*chunk elements): publishes every rank's slice t[r*chunk:(r+1)*chunk]."""
-    L.check(ctx.lib.a3d_allgather(ctx.h, _ptr(t), chunk, _code(t), _stream()), "allgather")
+    ctx.allgather(t, chunk)
 
 
 def comm_unique_id(nccl_path: str | None = None) -> bytes:

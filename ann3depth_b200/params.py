@@ -275,13 +275,16 @@ class Arena:
             tot += n
         return tot
 
-    def load_tf(self, tf_params: dict):
-        """Copy TF-layout tensors (any float dtype, CPU or GPU) into the arena and refresh the mirror."""
+    def load_tf(self, tf_params: dict, buf=None):
+        """Copy TF-layout tensors (any float dtype, CPU or GPU) into the arena and refresh the mirror.
+        `buf`: another arena-shaped f32 buffer (the Adam slots m / v when a checkpoint is restored) instead of w."""
+        dst = self.w if buf is None else buf
         for name, s in self.specs.items():
             t = tf_params[name].detach().to("cpu", torch.float32)
             assert tuple(t.shape) == tuple(s.tf_shape), (name, t.shape, s.tf_shape)
-            self.view(self.w, name).copy_(pack(s, t))
-        self.wb.copy_(self.w)       # load-time only; the step itself refreshes the mirror in liba3d
+            self.view(dst, name).copy_(pack(s, t))
+        if buf is None:
+            self.wb.copy_(self.w)   # load-time only; the step itself refreshes the mirror in liba3d
 
     def export_tf(self, buf=None):
         buf = self.w if buf is None else buf

@@ -85,3 +85,56 @@ def test_varint_multibyte_lengths(tmp_path):
     (e,) = [data.parse_example(r) for r in data.tfrecord_iterator(str(path))]
     assert len(e["image"]) == 48 * 64 * 3 * 4
     assert np.array_equal(np.frombuffer(e["image"], dtype=np.float32), img)
+
+
+def _dataset(tmp_path, n, hw=(4, 6), dhw=(2, 3)):
+    """n records whose image is the constant (i+1)/255 and whose depth is (i+1)/510: a sample identifies its record."""
+    import os
+    recs = []
+    for i in range(n):
+        img = np.full((*hw, 3), (i + 1) / 255. - .5, dtype=np.float32)
+        dep = np.full((*dhw, 1), (i + 1) / 510. - .5, dtype=np.float32)
+        recs.append(_example({"image_height": hw[0], "image_width": hw[1], "image_channels": 3, "depth_height": dhw[0],
+                              "depth_width": dhw[1], "depth_channels": 1, "image": img.tobytes(), "depth": dep.tobytes()},
+                             i % 2 == 0))
+    os.makedirs(tmp_path / "nyu", exist_ok=True)
+    _write(tmp_path / "nyu" / "train.tfrecords", recs)
+    return str(tmp_path)
+
+
+def test_threaded_loader_reads_shuffled_records(tmp_path):
+    """data.inputs (src/data.py:28-55): worker threads + shuffle pool; every sample is a record of the file (+0.5 applied,
+    shapes from the record header), image and depth of a sample belong together, and all records turn up."""
+    import torch
+    n, B = 7, 4
+    inp = data.inputs(_dataset(tmp_path, n), "nyu", B, device="cpu", seed=3, num_threads=2)
+    assert tuple(inp.images.shape) == (B, 4, 6, 3) and tuple(inp.depths.shape) == (B, 2, 3, 1)
+    assert [tuple(x) for x in data.tfrecord_index(inp.path)][0][0] == 12 and len(data.tfrecord_index(inp.path)) == n
+    seen = set()
+    for _ in range(12):
+        im, dp = inp.next_batch()
+        ids = torch.round(im[:, 0, 0, 0] * 255).long()
+        assert torch.allclose(im, (ids.float() / 255).view(B, 1, 1, 1).expand_as(im), atol=1e-6)
+        assert torch.allclose(dp, (ids.float() / 510).view(B, 1, 1, 1).expand_as(dp), atol=1e-6)
+        assert int(ids.min()) >= 1 and int(ids.max()) <= n
+        seen.update(ids.tolist())
+    inp.close()
+    assert seen == set(range(1, n + 1))
+
+
+def test_threaded_loader_synthetic_host_and_errors(tmp_path):
+    import pytest
+    inp = data.inputs(str(tmp_path), "none", 2, device="cpu", synthetic="host", image_hw=(8, 8), depth_hw=(5, 7))
+    a = inp.images.clone()
+    inp.next_batch()
+    assert not (a == inp.images).all()
+    assert 0.0 <= float(inp.images.min()) and float(inp.images.max()) < 1.0
+    assert 0.05 <= float(inp.depths.min()) and float(inp.depths.max()) < 1.0
+    inp.close()
+    root = _dataset(tmp_path, 3)
+    path = tmp_path / "nyu" / "train.tfrecords"
+    raw = bytearray(path.read_bytes())
+    raw[3] ^= 0x40                                   # corrupt the first length field
+    path.write_bytes(bytes(raw))
+    with pytest.raises(IOError):
+        data.inputs(root, "nyu", 2, device="cpu")

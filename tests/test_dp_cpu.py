@@ -166,3 +166,112 @@ def test_bench_reference_arm_other_ranks_are_silent():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
                         "--steps", "1", "--warmup", "0"], env=env, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+# ----------------------------------------------------------------------------- sharded optimizer state (gloo, world 2)
+class _GlooCtx:
+    """liba3d's in-place collectives (ops.Context.allreduce_sum / allgather / reduce_scatter_sum) over gloo."""
+
+    def allreduce_sum(self, t, count=None):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    def allgather(self, t, chunk):
+        r = dist.get_rank()
+        parts = [torch.empty(chunk, dtype=t.dtype) for _ in range(dist.get_world_size())]
+        dist.all_gather(parts, t[r * chunk:(r + 1) * chunk].clone())
+        t.copy_(torch.cat(parts))
+
+
+def _fake_dp(rank, world):
+    dp = DataParallel.__new__(DataParallel)
+    dp.ctx, dp.rank, dp.world, dp.stream, dp._done, dp.bytes_per_step = _GlooCtx(), rank, world, None, [], 0
+    return dp
+
+
+def _shard_worker(rank, world, port, outdir):
+    from ann3depth_b200 import ann3depth as drv
+    from ann3depth_b200.params import dcnf_specs
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class Net:
+        pass
+    net = Net()
+    net.arena = a = Arena(dcnf_specs(), "cpu", with_adam=True)
+    net.global_step, net.adam_t = 17, {"SGD": 17}
+    op = type("Op", (), {"net": net})()
+    dp = _fake_dp(rank, world)
+    lo, hi = a.group_range("SGD")
+    chunk = (hi - lo) // world
+    truth = {k: torch.arange(a.total, dtype=torch.float32) * s for k, s in (("w", 1e-3), ("m", 2e-3), ("v", 3e-3))}
+    own = slice(lo + rank * chunk, lo + (rank + 1) * chunk)
+    for k in ("w", "m", "v"):                       # a sharded optimizer: only this rank's slice is current
+        buf = getattr(a, k)
+        buf.fill_(-1.0)
+        buf[own] = truth[k][own]
+        buf[:lo], buf[hi:] = truth[k][:lo], truth[k][hi:]     # outside the sharded bucket everything is replicated
+    # 1. the f32 biases the kernels read become current on every rank (ADVICE r1: stale biases outside the own slice)
+    dp._sync_sharded_biases(net, lo, hi, chunk)
+    for s in a.specs.values():
+        if s.kind == "bias" and lo <= s.offset < hi:
+            got, exp = a.w[s.offset:s.offset + s.numel], truth["w"][s.offset:s.offset + s.numel]
+            assert torch.equal(got, exp), (rank, s.name)
+    # 2. a checkpoint taken under DP holds the owners' values of EVERY slice (gather_master before the chief writes)
+    dp._sharded = {"SGD"}
+    drv.save_checkpoint(op, outdir, comm=dp, write=rank == 0)
+    dist.barrier()
+    net2 = Net()
+    net2.arena = Arena(dcnf_specs(), "cpu", with_adam=True)
+    net2.global_step, net2.adam_t = 0, {"SGD": 0}
+    assert drv.restore_checkpoint(type("Op", (), {"net": net2})(), outdir)
+    for k in ("w", "m", "v"):
+        # (padding entries of a packed segment are not variables and are not part of the checkpoint)
+        exp_full = truth[k]
+        got_tf = net2.arena.export_tf(getattr(net2.arena, k))
+        exp_tf = {n: unpack(sp, a.view(exp_full, n)) for n, sp in a.specs.items()}
+        for n in exp_tf:
+            assert torch.equal(got_tf[n], exp_tf[n]), (rank, k, n)
+    assert net2.global_step == 17 and net2.adam_t == {"SGD": 17}
+    assert torch.equal(net2.arena.wb, net2.arena.w.to(torch.bfloat16))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_bias_sync_and_dp_checkpoint(tmp_path):
+    world, port = 2, 29533
+    mp.spawn(_shard_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+
+
+def test_stop_consensus_single_process_passthrough():
+    from ann3depth_b200.ann3depth import StopConsensus
+    c = StopConsensus(1)
+    assert c.decide(3, 10, True) == (10, True) and c.decide(4, 0, False) == (0, False)
+
+
+def _stop_worker(rank, world, port, out):
+    from ann3depth_b200.ann3depth import StopConsensus
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    c = StopConsensus(world, every=4)
+    log = []
+    for step in range(12):
+        # rank 1 receives SIGUSR1 (10) "during" step 5; the chief's checkpoint timer fires at step 2
+        sig = 10 if (rank == 1 and step >= 5) else 0
+        due = rank == 0 and step >= 2
+        s, ck = c.decide(step, sig, due)
+        log.append((step, s, ck))
+        if s:
+            break
+    torch.save(log, out + f".{rank}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_stop_consensus_all_ranks_stop_at_the_same_step(tmp_path):
+    world, port = 2, 29534
+    out = str(tmp_path / "stop")
+    mp.spawn(_stop_worker, args=(world, port, out), nprocs=world, join=True)
+    a, b = torch.load(out + ".0"), torch.load(out + ".1")
+    assert a == b                                             # identical decisions on both ranks
+    assert a[-1] == (8, 10, True)                             # first consensus point after the signal: step 8
+    assert (4, 0, True) in a and (0, 0, False) in a           # the chief's checkpoint request reaches rank 1 too
