@@ -53,6 +53,9 @@ SIGNATURES = {
     "a3d_conv2d_wgrad": (_i, [_vp, C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "a3d_dense_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _i, _vp, _i, _i, _i, _u, _i, _vp]),
     "a3d_dense_dgrad": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "a3d_stamp": (_i, [_vp, _vp, _vp]),
+    "a3d_allgather_multi": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "a3d_dense_dgrad_act": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _f, _u, _vp]),
     "a3d_dense_wgrad": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
     "a3d_dense_wgrad_adam": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _f, _f, _vp, _vp]),
     "a3d_dense_wgrad_adam_rows": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _f, _f, _f,

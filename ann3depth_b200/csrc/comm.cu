@@ -110,3 +110,25 @@ extern "C" int a3d_allgather(a3d_ctx* ctx, void* buf, size_t chunk, int dtype, v
   if (r) { a3d_set_error("ncclAllGather -> %d", r); return A3D_ENCCL; }
   return 0;
 }
+
+// Several all-gathers as ONE NCCL group (one fused launch, one latency): bufs[i] holds nranks * chunks[i] elements and
+// is gathered in place like a3d_allgather.  Used for the activation matrices of all dense layers (dp.py).
+extern "C" int a3d_allgather_multi(a3d_ctx* ctx, void* const* bufs, const size_t* chunks, int n, int dtype, void* stream) {
+  A3D_REQUIRE(ctx && bufs && chunks && n > 0, "allgather_multi: bad argument");
+  if (!ctx->nccl_comm) { a3d_set_error("allgather_multi: communicator not initialised"); return A3D_ENCCL; }
+  typedef int (*fn_group)(void);
+  fn_allgather f = (fn_allgather)dlsym(ctx->nccl_lib, "ncclAllGather");
+  fn_group gs = (fn_group)dlsym(ctx->nccl_lib, "ncclGroupStart");
+  fn_group ge = (fn_group)dlsym(ctx->nccl_lib, "ncclGroupEnd");
+  if (!f || !gs || !ge) { a3d_set_error("ncclAllGather / ncclGroupStart / ncclGroupEnd not found"); return A3D_ENCCL; }
+  int rank = 0, rc = comm_rank(ctx, &rank);
+  if (rc) return rc;
+  const size_t es = dtype == A3D_BF16 ? 2 : 4;
+  int r = gs();
+  for (int i = 0; i < n && !r; ++i)
+    r = f(reinterpret_cast<char*>(bufs[i]) + (size_t)rank * chunks[i] * es, bufs[i], chunks[i], dtype == A3D_BF16 ? 9 : 7,
+          ctx->nccl_comm, as_stream(stream));
+  int r2 = ge();
+  if (r || r2) { a3d_set_error("grouped ncclAllGather -> %d / %d", r, r2); return A3D_ENCCL; }
+  return 0;
+}

@@ -12,8 +12,9 @@ int a3d_tc_dgrad_cols(a3d_ctx*, const a3d_conv_desc*, const uint16_t* dy, const 
 int a3d_tc_dense_fwd(a3d_ctx*, const uint16_t* x, int ldx, const uint16_t* w, const float* bias, const uint8_t* mask,
                      float drop_rate, void* y, int y_dtype, float* acc_ws, int M, int N, int K, unsigned flags,
                      cudaStream_t st);
+struct a3d_actbwd_args { const uint16_t* y; const uint8_t* keep_mask; float drop_rate; unsigned flags; };
 int a3d_tc_dense_dgrad(a3d_ctx*, const uint16_t* dy, int lddy, const uint16_t* w, uint16_t* dx, float* acc_ws, int M,
-                       int N, int K, cudaStream_t st);
+                       int N, int K, cudaStream_t st, const a3d_actbwd_args* ab = nullptr);
 struct a3d_adam_args { float* w; float* m; float* v; uint16_t* wb; float lr_t, beta1, beta2, eps, grad_scale; const float* lr_t_dev; };
 int a3d_tc_dense_wgrad(a3d_ctx*, const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, int M, int N, int K,
                        cudaStream_t st, const a3d_adam_args* adam = nullptr);
@@ -479,6 +480,27 @@ extern "C" int a3d_dense_dgrad(a3d_ctx* ctx, const uint16_t* dy, int lddy, const
     return A3D_ENOTSUP;
   }
   return a3d_simt_dense_dgrad(ctx, dy, lddy, w, dx, M, N, K, st);
+}
+
+// dgrad + the activation gradient of the layer that produced x (y_act = its stored post-activation / post-dropout
+// output [M,K]): dx = act'(y_act) * keep_mask/(1-rate) * (dy . w) in the dgrad's own finishing pass.
+extern "C" int a3d_dense_dgrad_act(a3d_ctx* ctx, const uint16_t* dy, int lddy, const uint16_t* w, uint16_t* dx,
+                                   float* acc_ws, int M, int N, int K, int impl, const uint16_t* y_act,
+                                   const uint8_t* keep_mask, float drop_rate, unsigned flags, void* stream) {
+  A3D_REQUIRE(ctx && dy && w && dx && y_act && M > 0 && N > 0 && K > 0 && lddy >= N, "dense dgrad+act: bad argument");
+  cudaStream_t st = as_stream(stream);
+  bool tc_ok = (K % 8 == 0) && (lddy % 8 == 0) && M <= 128 && acc_ws;
+  if (impl != A3D_IMPL_SIMT && tc_ok) {
+    a3d_actbwd_args ab{y_act, keep_mask, drop_rate, flags};
+    return a3d_tc_dense_dgrad(ctx, dy, lddy, w, dx, acc_ws, M, N, K, st, &ab);
+  }
+  if (impl == A3D_IMPL_TC) {
+    a3d_set_error("dense dgrad+act: shape not supported by the tcgen05 path (M=%d N=%d K=%d lddy=%d)", M, N, K, lddy);
+    return A3D_ENOTSUP;
+  }
+  int rc = a3d_simt_dense_dgrad(ctx, dy, lddy, w, dx, M, N, K, st);
+  if (rc) return rc;
+  return a3d_dense_epilogue_bwd(ctx, dx, y_act, keep_mask, drop_rate, dx, (size_t)M * K, flags, stream);     // in place
 }
 
 extern "C" int a3d_dense_wgrad(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw,

@@ -449,6 +449,18 @@ extern "C" int a3d_bernoulli_mask(a3d_ctx* ctx, uint8_t* keep, size_t n, float k
   A3D_LAUNCH_OK(ctx);
   return 0;
 }
+// ---- in-graph timeline: one thread writes the GPU's global nanosecond timer; captured in a CUDA graph like any kernel
+__global__ void stamp_kernel(unsigned long long* slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *slot = t;
+}
+extern "C" int a3d_stamp(a3d_ctx* ctx, uint64_t* slot, void* stream) {
+  A3D_REQUIRE(ctx && slot, "stamp: null argument");
+  stamp_kernel<<<1, 1, 0, as_stream(stream)>>>(reinterpret_cast<unsigned long long*>(slot));
+  A3D_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
 __global__ void increment_i64_kernel(int64_t* p) { *p += 1; }
 extern "C" int a3d_increment_i64(a3d_ctx* ctx, int64_t* p, void* stream) {
   A3D_REQUIRE(ctx && p, "increment: null argument");
@@ -1204,11 +1216,19 @@ int a3d_mma_dense_wgrad_adam(a3d_ctx* ctx, const uint16_t* x, int ldx, const uin
     return A3D_ENOTSUP;
   // A3D_FUSED_ADAM_CFG = <QN><BPS><PF> digits, e.g. "241" = 32-column warp tiles, 4 blocks/SM, prefetch
   static int cfg = -1;
-  if (cfg < 0) { const char* e = getenv("A3D_FUSED_ADAM_CFG"); cfg = e ? atoi(e) : 230; }
+  if (cfg < 0) { const char* e = getenv("A3D_FUSED_ADAM_CFG"); cfg = e ? atoi(e) : 231; }
   const int qn = cfg / 100, bps = (cfg / 10) % 10, pf = cfg % 10;
   const int kblocks = K / (128 * qn);
   int gy = bps * ctx->sm_count / kblocks;            // one resident wave
   if (gy < 1) gy = 1;
+  // A3D_FUSED_ADAM_TILES = t > 0: NON-persistent grid, every CTA updates t row tiles and retires.  A resident wave of
+  // this kernel holds ~61 k of the SM's 64 k registers for its whole life, so no tensor-core CTA of the concurrently
+  // running backward GEMMs can start next to it (measured with tools/ablate_step.py: the update costs 0.33 ms of the
+  // 0.99 ms step, almost its stand-alone duration).  Short-lived CTAs hand their SM back every few microseconds and the
+  // pending CTAs of the high-priority main stream take it first.
+  static int tiles_per_cta = -1;
+  if (tiles_per_cta < 0) { const char* e = getenv("A3D_FUSED_ADAM_TILES"); tiles_per_cta = e ? atoi(e) : 0; }
+  if (tiles_per_cta > 0) gy = ceil_div(ceil_div(N, 16), tiles_per_cta);
   if (gy > ceil_div(N, 16)) gy = ceil_div(N, 16);
   dim3 grid(kblocks, gy);
 #define A3D_MMA_ADAM(QN, BPS, PF)                                                                                     \
@@ -1218,6 +1238,7 @@ int a3d_mma_dense_wgrad_adam(a3d_ctx* ctx, const uint16_t* x, int ldx, const uin
   A3D_MMA_ADAM(2, 3, 0) A3D_MMA_ADAM(2, 3, 1) A3D_MMA_ADAM(2, 2, 0) A3D_MMA_ADAM(2, 2, 1)
   A3D_MMA_ADAM(1, 4, 0) A3D_MMA_ADAM(1, 4, 1) A3D_MMA_ADAM(1, 3, 0) A3D_MMA_ADAM(1, 3, 1)
   A3D_MMA_ADAM(1, 6, 0) A3D_MMA_ADAM(1, 6, 1)
+  A3D_MMA_ADAM(2, 1, 0) A3D_MMA_ADAM(2, 1, 1) A3D_MMA_ADAM(1, 2, 0) A3D_MMA_ADAM(1, 2, 1) A3D_MMA_ADAM(1, 1, 1)
 #undef A3D_MMA_ADAM
   A3D_LAUNCH_OK(ctx);
   return 0;

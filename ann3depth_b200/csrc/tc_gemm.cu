@@ -3,6 +3,7 @@
 #include "tc_gemm.cuh"
 #include "tc_persist.cuh"
 #include "tc_mcast.cuh"
+#include "tc_pair.cuh"
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -208,9 +209,20 @@ int launch_cfg(a3d_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, con
 //   4..6  EXPERIMENTAL persistent kernel (tc_persist.cuh) with 2 / 3 / 4 stages; candidates only with A3D_PERSIST=1
 //   7..10 EXPERIMENTAL cluster kernel (tc_mcast.cuh): weight tile multicast to 2 / 4 CTAs, default ring / one stage
 //         more; candidates only with A3D_MCAST=1.  NOTE: tmB must then have a box of BN / CL rows (mcast_cl()).
+//   11,12 CTA-pair kernel (tc_pair.cuh): tcgen05.mma.cta_group::2, 256 x BN tile per pair, each CTA holds half the
+//         weight tile; 11 = short ring (two CTAs per SM), 12 = deep ring (one CTA per SM).  tmB box = BN / 2 rows.
 enum { V_BASE = 0, V_DEEP = 1, V_BM256 = 2, V_BM256_DEEP = 3, V_PERSIST2 = 4, V_PERSIST3 = 5, V_PERSIST4 = 6,
-       V_MC2 = 7, V_MC2_DEEP = 8, V_MC4 = 9, V_MC4_DEEP = 10, V_COUNT = 11 };
-int mcast_cl(int variant) { return variant == V_MC2 || variant == V_MC2_DEEP ? 2 : variant == V_MC4 || variant == V_MC4_DEEP ? 4 : 1; }
+       V_MC2 = 7, V_MC2_DEEP = 8, V_MC4 = 9, V_MC4_DEEP = 10, V_PAIR = 11, V_PAIR_DEEP = 12, V_COUNT = 13 };
+int mcast_cl(int variant) {
+  return variant == V_MC2 || variant == V_MC2_DEEP || variant == V_PAIR || variant == V_PAIR_DEEP ? 2
+         : variant == V_MC4 || variant == V_MC4_DEEP ? 4 : 1;
+}
+// A3D_PAIR: 0 off, 1 deep ring only, 2 (default) both pair variants are tuner candidates
+int pair_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("A3D_PAIR"); v = e ? atoi(e) : 2; }
+  return v;
+}
 bool mcast_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("A3D_MCAST"); v = e ? atoi(e) : 0; }
@@ -249,6 +261,37 @@ int launch_mcast(a3d_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB_sl
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   A3D_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc::gemm_mcast_kernel<C, CL>, tmA, tmB_slice, tmC, p));
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
+template <class C>
+int launch_pair(a3d_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB_half, const tc::Params& p_in, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    A3D_CHECK_CUDA(cudaFuncSetAttribute(tc::gemm_pair_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  tc::Params p = p_in;
+  if (p.atomic || p.kb_per_split < p.num_kb) { a3d_set_error("pair gemm: no split-K"); return A3D_ENOTSUP; }
+  CUtensorMap tmC;
+  bool use_c = false;
+  int rc = maybe_tma_out(ctx, p, &tmC, &use_c);
+  if (rc) return rc;
+  const bool ok = use_c && ((p.epi == tc::EPI_TMA_F32 && C::BN % 32 == 0) || (p.epi == tc::EPI_TMA_BF16 && C::BN % 64 == 0) ||
+                           (p.epi == tc::EPI_POOL4_BF16 && C::BN == 256));
+  if (!ok) { a3d_set_error("pair gemm: needs a TMA-store epilogue (f32: BN %% 32, bf16: BN %% 64)"); return A3D_ENOTSUP; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ceil_div(ceil_div(p.M, 128), 2) * 2, ceil_div(p.N, C::BN), 1);
+  cfg.blockDim = dim3(192, 1, 1);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  A3D_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc::gemm_pair_kernel<C>, tmA, tmB_half, tmC, p));
   A3D_LAUNCH_OK(ctx);
   return 0;
 }
@@ -323,8 +366,17 @@ int launch_kk(a3d_ctx* ctx, int bn, int kcb, const CUtensorMap& tmA, const CUten
     if (variant == V_MC4) return launch_mcast<tc::Cfg<BN, 128, false, false>, 4>(ctx, tmA, tmB, p, st); \
     if (variant == V_MC4_DEEP) return launch_mcast<tc::Cfg<BN, 128, false, false, 64, 3>, 4>(ctx, tmA, tmB, p, st); \
   }
-    if (variant >= V_MC2 && splits == 1) { A3D_CASEM(64) A3D_CASEM(128) A3D_CASEM(256) }
+    if (variant >= V_MC2 && variant <= V_MC4_DEEP && splits == 1) { A3D_CASEM(64) A3D_CASEM(128) A3D_CASEM(256) }
 #undef A3D_CASEM
+#define A3D_CASE2(BN, NS, ND) \
+  if (bn == BN) { \
+    if (variant == V_PAIR) return launch_pair<tc::PairCfg<BN, 128, NS>>(ctx, tmA, tmB, p, st); \
+    return launch_pair<tc::PairCfg<BN, 128, ND>>(ctx, tmA, tmB, p, st); \
+  }
+    if ((variant == V_PAIR || variant == V_PAIR_DEEP) && splits == 1) {
+      A3D_CASE2(64, 4, 8) A3D_CASE2(96, 4, 8) A3D_CASE2(128, 4, 8) A3D_CASE2(192, 3, 7) A3D_CASE2(256, 3, 6)
+    }
+#undef A3D_CASE2
   }
   a3d_set_error("tc gemm: no kernel for BN=%d KCB=%d variant=%d", bn, kcb, variant);
   return A3D_ENOTSUP;
@@ -333,6 +385,8 @@ bool variant_exists(int bn, int kcb, int variant) {
   if (variant == V_BASE) return true;
   if (kcb != 128) return false;
   if (variant == V_DEEP) return bn == 64 || bn == 96 || bn == 128 || bn == 192 || bn == 256;
+  if (variant == V_PAIR) return pair_mode() >= 2 && (bn == 64 || bn == 96 || bn == 128 || bn == 192 || bn == 256);
+  if (variant == V_PAIR_DEEP) return pair_mode() >= 1 && (bn == 64 || bn == 96 || bn == 128 || bn == 192 || bn == 256);
   if (variant >= V_MC2) return mcast_enabled() && (bn == 64 || bn == 128 || bn == 256);
   if (variant >= V_PERSIST2) return persist_enabled() && (bn == 64 || bn == 96 || bn == 128 || bn == 192 || bn == 256);
   return bn == 64 || bn == 96 || bn == 128 || bn == 256;
@@ -372,6 +426,22 @@ __global__ void bias_act_cast_kernel(const float* __restrict__ acc, const float*
     if (mask) v = mask[i] ? v * drop_scale : 0.f;
     if (y_f32) reinterpret_cast<float*>(y)[r * ldy + c] = v;
     else reinterpret_cast<uint16_t*>(y)[r * ldy + c] = f32_to_bf16_bits(v);
+  }
+}
+
+// dense dgrad finish with the producer layer's activation gradient folded in (DropoutGrad, then ReluGrad / SigmoidGrad on
+// the stored post-activation value y): dx = bf16(act'(y) * mask/(1-rate) * acc).  Same arithmetic as the separate
+// dense_epilogue_bwd pass it replaces (x 1/(1-rate) = x2 is exact in bf16), one kernel and one bf16 round trip less.
+__global__ void act_bwd_cast_kernel(const float* __restrict__ acc, const uint16_t* __restrict__ y,
+                                    const uint8_t* __restrict__ mask, float scale, uint16_t* __restrict__ dx, size_t n,
+                                    unsigned flags) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float g = bf16_bits_to_f32(f32_to_bf16_bits(acc[i]));      // the separate pass saw the bf16-rounded dgrad
+    if (mask) g = mask[i] ? g * scale : 0.f;
+    const float yv = bf16_bits_to_f32(y[i]);
+    if (flags & A3D_EPI_RELU) g = yv > 0.f ? g : 0.f;
+    if (flags & A3D_EPI_SIGMOID) g = g * yv * (1.f - yv);
+    dx[i] = f32_to_bf16_bits(g);
   }
 }
 
@@ -538,6 +608,13 @@ int a3d_tc_conv_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, con
     // 128-row tiles with two stages of 48 KB (two CTAs per SM, one CTA's epilogue under the other's main loop),
     // the same with three stages, or 256-row tiles (both accumulators fill the 512 TMEM columns)
     auto run = [&](int c) -> int {
+      if (c == 6 || c == 7) {                      // CTA pair (tc_pair.cuh): each CTA holds 128 of the 256 filter rows
+        CUtensorMap tmBh;
+        int r = make_tmap_2d(ctx, &tmBh, w, 256, (uint64_t)d->R * d->S * d->C, (uint64_t)d->R * d->S * d->C, 64, 128);
+        if (r) return r;
+        if (c == 6) return launch_pair<tc::PairCfg<256, 128, 3>>(ctx, tmA, tmBh, p, st);
+        return launch_pair<tc::PairCfg<256, 128, 6>>(ctx, tmA, tmBh, p, st);
+      }
       if (c >= 4) {                                // EXPERIMENTAL (A3D_MCAST=1): weight tile multicast to 2 / 4 CTAs
         const int cl = c == 4 ? 2 : 4;
         CUtensorMap tmBs;
@@ -556,7 +633,13 @@ int a3d_tc_conv_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, con
     const int kv[16] = {5, d->N, d->H, d->W, d->C, d->K, d->R, d->S, d->stride_h, d->stride_w, d->pad_t, d->pad_l,
                         d->P, d->Q, d->ldy, pool_idx != nullptr};
     memcpy(key.v, kv, sizeof(kv));
-    return run(autotune(key, mcast_enabled() ? 6 : 4, run, st));
+    // candidates 0..3 one-CTA tiles, 4..5 multicast clusters (A3D_MCAST=1 only), 6..7 CTA pairs
+    int cands[8], nc = 0;
+    for (int c = 0; c < 4; ++c) cands[nc++] = c;
+    if (mcast_enabled()) { cands[nc++] = 4; cands[nc++] = 5; }
+    if (pair_mode() >= 2) cands[nc++] = 6;
+    if (pair_mode() >= 1) cands[nc++] = 7;
+    return run(cands[autotune(key, nc, [&](int i) { return run(cands[i]); }, st)]);
   }
   if (!a3d_tc_conv_fwd_supported(d)) {
     a3d_set_error("tc conv fwd: unsupported shape (C=%d must be a multiple of 16)", d->C);
@@ -634,6 +717,8 @@ int a3d_tc_conv_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, con
         if (variant >= V_PERSIST2 && variant <= V_PERSIST4 && (sp != 1 || tiles <= ctx->sm_count)) continue;
         // cluster kernel: unsplit, enough M tiles that sharing the weight tile matters
         if (variant >= V_MC2 && (sp != 1 || ceil_div(M, 128) < 8)) continue;
+        // pair kernel with an f32 output: 32-column slabs, any BN; with a bf16 output BN % 64 (checked at launch)
+        if ((variant == V_PAIR || variant == V_PAIR_DEEP) && y_dtype != A3D_F32 && bn % 64) continue;
         bool dup = false;
         for (int k = 0; k < nc; ++k) dup |= (cand[k].bn == bn && cand[k].splits == sp && cand[k].variant == variant);
         if (!dup && nc < 64) cand[nc++] = {bn, sp, variant};
@@ -866,13 +951,24 @@ int a3d_tc_dgrad_cols(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* dy, 
 
 // ------------------------------------------------------------------------------------------------
 // dense backward.  dgrad: dx[b][k] = sum_n dy[b][n] w[n][k]  -> D^T[k][b], A = w MN-major, B = dy K-major.
+struct a3d_actbwd_args { const uint16_t* y; const uint8_t* keep_mask; float drop_rate; unsigned flags; };
 int a3d_tc_dense_dgrad(a3d_ctx* ctx, const uint16_t* dy, int lddy, const uint16_t* w, uint16_t* dx, float* acc_ws,
-                       int M, int N, int K, cudaStream_t st) {
+                       int M, int N, int K, cudaStream_t st, const a3d_actbwd_args* ab = nullptr) {
   if (K % 8 || lddy % 8 || M > 128 || !acc_ws) {
     a3d_set_error("tc dense dgrad: needs K %% 8 == 0, lddy %% 8 == 0, batch <= 128, workspace");
     return A3D_ENOTSUP;
   }
   const int bn = M <= 32 ? 32 : M <= 64 ? 64 : 128;
+  auto finish_dx = [&]() -> int {
+    if (!ab) return finish(ctx, acc_ws, nullptr, nullptr, 0.f, dx, 0, (size_t)M, K, K, 0, st);
+    const size_t total = (size_t)M * K;
+    size_t blocks = (total + 255) / 256;
+    if (blocks > (size_t)ctx->sm_count * 16) blocks = (size_t)ctx->sm_count * 16;
+    act_bwd_cast_kernel<<<(int)blocks, 256, 0, st>>>(acc_ws, ab->y, ab->keep_mask, 1.f / (1.f - ab->drop_rate), dx, total,
+                                                    ab->flags);
+    A3D_LAUNCH_OK(ctx);
+    return 0;
+  };
   CUtensorMap tmA, tmB;
   int rc = make_tmap_2d(ctx, &tmA, w, N, K, K, 64, 64);
   if (rc) return rc;
@@ -896,14 +992,14 @@ int a3d_tc_dense_dgrad(a3d_ctx* ctx, const uint16_t* dy, int lddy, const uint16_
     else if (bn == 64) r = launch_cfg<tc::Cfg<64, 128, true, false>>(ctx, tmA, tmB, q, splits, st);
     else r = launch_cfg<tc::Cfg<128, 128, true, false>>(ctx, tmA, tmB, q, splits, st);
     if (r) return r;
-    return finish(ctx, acc_ws, nullptr, nullptr, 0.f, dx, 0, (size_t)M, K, K, 0, st);
+    return finish_dx();
   };
   const int smode = a3d_stream_mode();
   const bool s_ok = smode != 0 && a3d_stream_dense_dgrad_ok(M, N, K, lddy);
   auto launch_stream = [&](int ctas) -> int {
     int r = a3d_stream_dense_dgrad(ctx, dy, lddy, w, acc_ws, M, N, K, ctas, st);
     if (r) return r;
-    return finish(ctx, acc_ws, nullptr, nullptr, 0.f, dx, 0, (size_t)M, K, K, 0, st);
+    return finish_dx();
   };
   if (s_ok && smode == 2) return launch_stream(2 * ctx->sm_count);
   int cand[24];

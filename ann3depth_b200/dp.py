@@ -9,6 +9,8 @@ rank x batch n*B (gradients averaged: sum-allreduce, 1/n folded into the optimiz
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -18,7 +20,10 @@ class DataParallel:
     def __init__(self, ctx: ops.Context, rank: int, world: int, unique_id: bytes, nccl_path: str | None = None):
         self.ctx, self.rank, self.world = ctx, rank, world
         ctx.comm_init(unique_id, rank, world, nccl_path)
-        self.stream = torch.cuda.Stream(device=ctx.device)
+        # The communication stream outranks the compute streams: its kernels are few and short (NCCL CTAs, the row-sharded
+        # dense update) but sit on the step's critical chain; at normal priority the 13 / 35 us row updates of an 8-GPU
+        # step waited ~170 / 200 us for a free SM slot among the backward GEMMs' CTAs (profiles/step_timeline_r02_n8*).
+        self.stream = torch.cuda.Stream(device=ctx.device, priority=int(os.environ.get("A3D_DP_COMM_PRIORITY", "-3")))
         self._done = []
         self.bytes_per_step = 0
 
@@ -63,7 +68,9 @@ class DataParallel:
         ready.record(torch.cuda.current_stream())
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ready)
+            self.ctx.stamp(f"comm: allreduce {name} begin")
             self.ctx.allreduce_sum(net.arena.g[lo:hi])
+            self.ctx.stamp(f"comm: allreduce {name} end")
             if then is not None:
                 if after is not None:
                     self.stream.wait_event(after)
@@ -92,7 +99,9 @@ class DataParallel:
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ready)
             self.ctx.cast_f32_bf16(a.g[lo:hi], a.gb[lo:hi])
+            self.ctx.stamp(f"comm: reduce-scatter {name} begin")
             ops.reduce_scatter_sum(self.ctx, a.gb[lo:hi], chunk)
+            self.ctx.stamp(f"comm: reduce-scatter {name} end")
             if after is not None:
                 self.stream.wait_event(after)
             s = lo + self.rank * chunk
@@ -101,6 +110,7 @@ class DataParallel:
                                    1.0 / self.world, lr_t_dev=net.lr_dev[group])
             ops.allgather(self.ctx, a.wb[lo:hi], chunk)
             self._sync_sharded_biases(net, lo, hi, chunk)
+            self.ctx.stamp(f"comm: sharded adam + allgather {name} end")
             done = torch.cuda.Event()
             done.record(self.stream)
         self._done.append(done)
@@ -173,7 +183,9 @@ class DataParallel:
             self.stream.wait_event(ready)
             gbuf[self.rank, :B * K].view(B, K).copy_(x)
             gbuf[self.rank, B * K:].view(B, lddy).copy_(dy)
+            c.stamp(f"comm: allgather x,dy {kernel_name.split('/')[-2]} begin")
             ops.allgather(c, gbuf.view(-1), blk)
+            c.stamp(f"comm: allgather x,dy {kernel_name.split('/')[-2]} end")
             if after is not None:
                 self.stream.wait_event(after)
             t = max(net.adam_t[group], 1)
@@ -187,16 +199,175 @@ class DataParallel:
             c.bias_grad_bf16(dyg, N, a.g[bs.offset:bs.offset + N], rows=n * B, ld=lddy, group_rows=B, group_stride=blk)
             c.adam_tf(a.w[sl], a.g[sl], a.m[sl], a.v[sl], a.wb[sl], lr, beta1, net.beta2, eps, t, 1.0 / n,
                       lr_t_dev=net.lr_dev[group])
+            c.stamp(f"comm: rows update {kernel_name.split('/')[-2]} end")
             ops.allgather(c, a.view(a.wb, kernel_name).view(-1), r * K)
+            c.stamp(f"comm: allgather bf16 rows {kernel_name.split('/')[-2]} end")
             done = torch.cuda.Event()
             done.record(self.stream)
         self._done.append(done)
         self.bytes_per_step += (n * blk + rows * K) * 2
         self._row_sharded = getattr(self, "_row_sharded", set()) | {kernel_name}
 
+    def dense_gather_adam_merged(self, net, layers, group, lr, beta1, eps, ready):
+        """dense_gather_adam for SEVERAL dense layers with one activation all-gather and a DEFERRED weight publish:
+             ONE all-gather of every layer's x [B,K] and dy [B,N] (one latency-bound collective instead of one per layer)
+             |  per layer: this rank updates its row slice from the gathered batch (a3d_dense_wgrad_adam_rows) and the
+                replicated bias, behind that layer's `after` event (its dgrad: the last reader of the old weights).
+           The all-gather of the updated bf16 rows is NOT enqueued here: nobody reads those weights before the next step's
+           dense forward, so `publish_rows` runs at the START of the next step on the comm stream, under the next step's
+           resize + convolution forward (the 134 MB weight exchange was ~330 us of serial NCCL time at the end of the
+           8-GPU step; profiles/step_timeline_r02_n8_rank0.json).  `flush` publishes outside a step (checkpoint, export,
+           end of a timed loop).
+        layers: [(kernel_name, bias_name, x, dy, after_event)]; ready: event after which every x / dy is final."""
+        a, c, n = net.arena, self.ctx, self.world
+        publish_now = set(os.environ.get("A3D_DP_PUBLISH_NOW", "dense_1").split(","))
+        B = layers[0][2].shape[0]
+        # Gathered batch <= 64 rows: the mma.sync row kernel forms the gradient in registers and applies TF-Adam in the
+        # same pass (26 B/param).  Beyond that its per-row-tile reload of x outweighs the fusion (8 GPUs, batch 256: 0.22
+        # of the HBM roofline, 112 us for this rank's slice of dense_0), so the slice's gradient comes from the tcgen05
+        # GEMM (f32, L2-resident: 25 MB) followed by the streaming TF-Adam pass.
+        use_gemm = n * B > int(os.environ.get("A3D_DP_ROWS_MAX_BATCH", "64"))
+        bufs = getattr(self, "_gbufs", None)
+        if bufs is None:
+            bufs = self._gbufs = {}
+        t = max(net.adam_t[group], 1)
+
+        def finish_layer(kn, bn_, dy_all, N, lddy, rows, K, r, group_rows=0, group_stride=0):
+            bs = a.specs[bn_]
+            sl = slice(bs.offset, bs.offset + bs.size)
+            c.bias_grad_bf16(dy_all, N, a.g[bs.offset:bs.offset + N], rows=n * B, ld=lddy, group_rows=group_rows,
+                             group_stride=group_stride)
+            c.adam_tf(a.w[sl], a.g[sl], a.m[sl], a.v[sl], a.wb[sl], lr, beta1, net.beta2, eps, t, 1.0 / n,
+                      lr_t_dev=net.lr_dev[group])
+            c.stamp(f"comm: rows update {kn.split('/')[-2]} end")
+            self.bytes_per_step += rows * K * 2
+            self._row_sharded = getattr(self, "_row_sharded", set()) | {kn}
+            if kn.split("/")[-2] in publish_now:
+                # a layer updated early in the backward pass is published right away: the comm stream is idle until
+                # the conv gradients exist, and the next step's start then only carries the rest
+                ops.allgather(c, a.view(a.wb, kn).view(-1), r * K)
+                c.stamp(f"comm: publish bf16 rows {kn.split('/')[-2]} (in step) end")
+            else:
+                self._unpublished = getattr(self, "_unpublished", set()) | {kn}
+
+        self.rows_launches = getattr(self, "rows_launches", {})
+        if use_gemm:
+            key = ("gather_plain",) + tuple(l[0] for l in layers)
+            if key not in bufs:
+                bufs[key] = [(torch.zeros(n * B, x.shape[1], dtype=torch.bfloat16, device=x.device),
+                              torch.zeros(n * B, dy.shape[1], dtype=torch.bfloat16, device=x.device))
+                             for _, _, x, dy, _ in layers]
+            mats = bufs[key]
+            with torch.cuda.stream(self.stream):
+                self.stream.wait_event(ready)
+                for (kn, bn_, x, dy, after), (xg, dyg) in zip(layers, mats):
+                    xg[self.rank * B:(self.rank + 1) * B].copy_(x)
+                    dyg[self.rank * B:(self.rank + 1) * B].copy_(dy)
+                c.stamp("comm: allgather x,dy (all dense layers) begin")
+                c.allgather_multi([m_.view(-1) for pair in mats for m_ in pair])
+                c.stamp("comm: allgather x,dy (all dense layers) end")
+                for (kn, bn_, x, dy, after), (xg, dyg) in zip(layers, mats):
+                    ks = a.specs[kn]
+                    rows, K = ks.packed_shape
+                    N, lddy = ks.tf_shape[1], dy.shape[1]
+                    r = rows // n
+                    lo_r = self.rank * r
+                    s0_ = ks.offset + lo_r * K
+                    if after is not None:
+                        self.stream.wait_event(after)
+
+                    def rows_launch(kn=kn, xg=xg, dyg=dyg, lo_r=lo_r, r=r, K=K, s0_=s0_):
+                        c.dense_wgrad(xg, dyg[:, lo_r:lo_r + r], dw=a.view(a.g, kn)[lo_r:lo_r + r], db=None, N=r)
+                        sl = slice(s0_, s0_ + r * K)
+                        c.adam_tf(a.w[sl], a.g[sl], a.m[sl], a.v[sl], a.wb[sl], lr, beta1, net.beta2, eps, t, 1.0 / n,
+                                  lr_t_dev=net.lr_dev[group])
+                    rows_launch()
+                    self.rows_launches[kn] = (rows_launch, dict(M=n * B, rows=r, rows_all=rows, K=K, lddy=lddy,
+                                                                kernel="a3d_dense_wgrad (row slice, tcgen05) + a3d_adam_tf",
+                                                                bytes_per_param=34.0))
+                    finish_layer(kn, bn_, dyg, N, lddy, rows, K, r)
+                done = torch.cuda.Event()
+                done.record(self.stream)
+            self._done.append(done)
+            self.bytes_per_step += sum(m_.numel() for pair in mats for m_ in pair) * 2
+            return
+        offs, blk = [], 0
+        for kn, bn_, x, dy, after in layers:
+            K, lddy = x.shape[1], dy.shape[1]
+            offs.append((blk, blk + B * K))
+            blk += B * (K + lddy)
+        key = ("gather_merged",) + tuple(l[0] for l in layers)
+        if key not in bufs:
+            bufs[key] = torch.zeros(n, blk, dtype=torch.bfloat16, device=layers[0][2].device)
+        gbuf = bufs[key]
+        flat = gbuf.view(-1)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            for (kn, bn_, x, dy, after), (ox, ody) in zip(layers, offs):
+                K, lddy = x.shape[1], dy.shape[1]
+                gbuf[self.rank, ox:ox + B * K].view(B, K).copy_(x)
+                gbuf[self.rank, ody:ody + B * lddy].view(B, lddy).copy_(dy)
+            c.stamp("comm: allgather x,dy (all dense layers) begin")
+            ops.allgather(c, flat, blk)
+            c.stamp("comm: allgather x,dy (all dense layers) end")
+            for (kn, bn_, x, dy, after), (ox, ody) in zip(layers, offs):
+                ks = a.specs[kn]
+                rows, K = ks.packed_shape
+                N, lddy = ks.tf_shape[1], dy.shape[1]
+                r = rows // n
+                if after is not None:
+                    self.stream.wait_event(after)
+
+                def rows_launch(ox=ox, ody=ody, kn=kn, r=r, N=N, K=K, lddy=lddy):
+                    c.dense_wgrad_adam_rows(flat[ox:], flat[ody:], a.view(a.w, kn), a.view(a.m, kn), a.view(a.v, kn),
+                                            a.view(a.wb, kn), self.rank * r, (self.rank + 1) * r, lr, beta1, net.beta2, eps,
+                                            t, 1.0 / n, lr_t_dev=net.lr_dev[group], N=N, M=n * B, ldx=K, lddy=lddy,
+                                            group_rows=B, x_group_stride=blk, dy_group_stride=blk)
+                rows_launch()
+                # bench.py times exactly this launch for the data-parallel roofline line
+                self.rows_launches[kn] = (rows_launch, dict(M=n * B, rows=r, rows_all=rows, K=K, lddy=lddy,
+                                                            kernel="a3d_dense_wgrad_adam_rows", bytes_per_param=26.0))
+                finish_layer(kn, bn_, flat[ody:], N, lddy, rows, K, r, group_rows=B, group_stride=blk)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        self._done.append(done)
+        self.bytes_per_step += n * blk * 2
+
+    def publish_rows(self, net):
+        """All-gather of the bf16 rows updated by the previous step's dense_gather_adam_merged; enqueued on the comm stream
+        behind whatever the current stream has done so far.  Returns the event the first reader of the dense weights has
+        to wait for (None when nothing is pending)."""
+        pending = sorted(getattr(self, "_unpublished", ()))
+        if not pending:
+            return None
+        a, c = net.arena, self.ctx
+        start = torch.cuda.Event()
+        start.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(start)
+            c.stamp("comm: publish bf16 rows begin")
+            for kn in pending:
+                rows, K = a.specs[kn].packed_shape
+                ops.allgather(c, a.view(a.wb, kn).view(-1), rows // self.world * K)
+            c.stamp("comm: publish bf16 rows end")
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return ev
+
+    def flush(self, net):
+        """Publish pending weight rows NOW (outside a step): before anything reads the bf16 mirror of rows another rank
+        owns -- checkpoints, exports, parity checks, the end of a timed loop."""
+        ev = self.publish_rows(net)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+
     def gather_master(self, net):
         """All-gather the f32 master weights and Adam slots of every sharded bucket (checkpoint / export)."""
         a = net.arena
+        pending = sorted(getattr(self, "_unpublished", ()))
+        for kn in pending:                                   # runs on the caller's (comm) stream, like the rest below
+            rows, K = a.specs[kn].packed_shape
+            ops.allgather(self.ctx, a.view(a.wb, kn).view(-1), rows // self.world * K)
         for name in sorted(getattr(self, "_sharded", ())):
             lo, hi = self.bucket_range(net, name)
             chunk = (hi - lo) // self.world

@@ -130,6 +130,8 @@ class MSDNNet:
             self.g_f1big = None                          # [B*4070, 256] bf16, allocated on first use (phase 2 only)
             self.g_wbig = None
         self._graphs = {}
+        if os.environ.get("A3D_TIMELINE") == "1" and ctx.timeline is None:
+            ctx.timeline = ops.StepTimeline(self.dev)
 
     # ------------------------------------------------------------------ parameters
     def _real_rows(self, buf, name):
@@ -158,6 +160,12 @@ class MSDNNet:
         a = self.arena
         s = a.specs["fine/first/conv2d/kernel"]
         self.ctx.scatter_cast_bf16(a.w[s.offset:s.offset + s.numel], self.emb_k, self.wbig)
+
+    def flush(self):
+        """Data parallel: make the bf16 weight mirror current on this rank (rows other ranks updated in the last step are
+        otherwise fetched at the start of the next one).  Collective: every rank must call it."""
+        if self.comm:
+            self.comm.flush(self)
 
     def export_params(self):
         return self.arena.export_tf()
@@ -235,17 +243,17 @@ class MSDNNet:
         if not fused_dense_adam:
             c.dense_wgrad(self.d0, self.g_coarse, dw=self.gw(n + "1" + K), db=self.gw(n + "1/bias"), impl=self.impl)
             hook(self, "dense_1")
-        c.dense_dgrad(self.g_coarse, self.w(n + "1" + K), out=self.g_d0a, impl=self.impl)
-        # dropout grad (mask * 1/(1-rate)) and relu grad (d0 > 0) in one pass
-        c.dense_epilogue_bwd(self.g_d0a, self.d0, self.keep_mask, 0.5, L.EPI_RELU, out=self.g_d0)
+        # dropout grad (mask * 1/(1-rate)) and relu grad (d0 > 0) ride in the dgrad's finishing pass
+        c.dense_dgrad_act(self.g_coarse, self.w(n + "1" + K), self.d0, self.keep_mask, 0.5, L.EPI_RELU, out=self.g_d0,
+                          impl=self.impl)
         if fused_dense_adam:
             self._dense_wgrad_adam("1", self.d0, self.g_coarse)
         else:
             c.dense_wgrad(self.c4.view(B, 12288), self.g_d0, dw=self.gw(n + "0" + K), db=self.gw(n + "0/bias"),
                           impl=self.impl)
             hook(self, "dense_0")
-        c.dense_dgrad(self.g_d0, self.w(n + "0" + K), out=self.g_c4a.view(B, 12288), impl=self.impl)
-        c.relu_bwd(self.c4, self.g_c4a, out=self.g_c4)
+        c.dense_dgrad_act(self.g_d0, self.w(n + "0" + K), self.c4.view(B, 12288), None, 0.0, L.EPI_RELU,
+                          out=self.g_c4.view(B, 12288), impl=self.impl)
         if fused_dense_adam:
             self._dense_wgrad_adam("0", self.c4.view(B, 12288), self.g_d0)
         n = "coarse/conv/conv2d_"
@@ -353,6 +361,12 @@ class MSDNNet:
             s2 = s2 if "wgrad" in self.overlap else s0
             s3 = s3 if "wgrad" in self.overlap else s0
         inv_world = 1.0 / self.comm.world if self.comm else 1.0
+        if c.timeline is not None:
+            c.timeline.begin()
+        c.stamp("step begin")
+        # data parallel: the dense rows other ranks updated in the PREVIOUS step arrive now, under this step's resize and
+        # convolution forward (dp.dense_gather_adam_merged / publish_rows); the dense forward waits for them
+        e_pub = self.comm.publish_rows(self) if self.comm else None
 
         def dp_update(bucket, group, after=None):     # DP: reduce-scatter -> sharded TF-Adam -> all-gather (dp.py)
             self.comm.sharded_adam(self, bucket, group, ADAM_LR[group], ADAM_BETA1, ADAM_EPS, after)
@@ -367,6 +381,9 @@ class MSDNNet:
         n0 = "coarse/conv/conv2d_"
         prep = os.environ.get("A3D_DGRAD_PREPARE", "1") != "0"
         e_start = mark(s0)
+        for side in (s2, s3):                 # every side stream forks from the step's start (a stream that happens to
+            if side is not s0:                # get no work in some mode must still be part of the capture to be joined)
+                side.wait_event(e_start)
         with torch.cuda.stream(s1):
             s1.wait_event(e_start)
             c.resize_bilinear_tf1(self.depths, OUT_H, OUT_W, out=self.tar)
@@ -385,6 +402,7 @@ class MSDNNet:
             e_flip = mark(s1)
         # ---- main: preprocessing
         c.resize_bilinear_tf1_s2d(self.images, IN_H, IN_W, 4, out=self.img4)
+        c.stamp("resize done")
         e_img = mark(s0)
         # ---- fine stream, part 1: first conv + pool need only the image
         with torch.cuda.stream(s1):
@@ -392,6 +410,7 @@ class MSDNNet:
             s1.wait_event(e_img)
             c.conv2d_pool4_fwd(self.d_f1, self.img4, self.wbig, self.bias("fine/first/conv2d"), relu=True, out=self.cat,
                                idx=self.if1)
+            c.stamp("fine/first done")
             c.ws_tag = ""
         # ---- main: coarse forward
         n = "coarse/conv/conv2d_"
@@ -402,11 +421,15 @@ class MSDNNet:
         c.conv2d_fwd(self.d_c2, self.p1, self.w(n + "2" + K), self.bias(n + "2"), relu=True, out=self.c2)
         c.conv2d_fwd(self.d_c3, self.c2, self.w(n + "3" + K), self.bias(n + "3"), relu=True, out=self.c3)
         c.conv2d_fwd(self.d_c4, self.c3, self.w(n + "4" + K), self.bias(n + "4"), relu=True, out=self.c4)
+        c.stamp("coarse conv fwd done")
         s0.wait_event(e_aux)
+        if e_pub is not None:
+            s0.wait_event(e_pub)
         nd = "coarse/dense/dense_"
         c.dense_fwd(self.c4.view(B, 12288), self.w(nd + "0" + K), self.bias(nd + "0"), flags=L.EPI_RELU,
                     keep_mask=self.keep_mask, drop_rate=0.5, out=self.d0, impl=self.impl)
         c.dense_fwd(self.d0, self.w(nd + "1" + K), self.bias(nd + "1"), flags=0, out=self.coarse, impl=self.impl)
+        c.stamp("dense fwd done")
         e_coarse = mark(s0)
         # ---- fine stream, part 2
         with torch.cuda.stream(s1):
@@ -419,6 +442,7 @@ class MSDNNet:
                          out=self.fine.view(B, 55, 74, 1))
             c.silog_loss(self.fine, self.tar, LAMBDA_OVER_N, want_grad=False, loss_ps=self.lps_fine, loss=self.loss_fine,
                          dout_bf16=self.g_fine)
+            c.stamp("fine fwd + loss done")
             c.ws_tag = ""
             e_fine = mark(s1)
         # ---- main: coarse loss, then the dgrad chain; wgrad stream follows each dY
@@ -426,12 +450,16 @@ class MSDNNet:
                      loss=self.loss_coarse, dout_bf16=self.g_coarse, dout_ld=4096)
         e_g = mark(s0)
 
-        def on_wgrad(event, fn, stream=None):
+        def on_wgrad(event, fn, stream=None, label=None):
             stream = stream or s2
             with torch.cuda.stream(stream):
                 c.ws_tag = "wgrad" if stream is s2 else "cwgrad"
                 stream.wait_event(event)
+                if label:
+                    c.stamp(label + " begin")
                 fn()
+                if label:
+                    c.stamp(label + " end")
                 c.ws_tag = ""
 
         fused = self.fuse_dense_adam and not self.comm
@@ -458,8 +486,8 @@ class MSDNNet:
         nd = "coarse/dense/dense_"
 
         e_loss = e_g
-        c.dense_dgrad(self.g_coarse, self.w(nd + "1" + K), out=self.g_d0a, impl=self.impl)
-        c.dense_epilogue_bwd(self.g_d0a, self.d0, self.keep_mask, 0.5, L.EPI_RELU, out=self.g_d0)
+        c.dense_dgrad_act(self.g_coarse, self.w(nd + "1" + K), self.d0, self.keep_mask, 0.5, L.EPI_RELU, out=self.g_d0,
+                          impl=self.impl)
         e_g = mark(s0)
         # data parallel, dense layers: exchange activations instead of gradients (dp.dense_gather_adam)
         gather = bool(self.comm) and all(self.comm.can_gather_dense(self, nd + l + K, B) for l in "01") and \
@@ -469,33 +497,45 @@ class MSDNNet:
             g = "CoarseDense"
             self.comm.dense_gather_adam(self, nd + layer + K, nd + layer + "/bias", x, dy, g, ADAM_LR[g], ADAM_BETA1,
                                         ADAM_EPS, after)
-        if gather:
-            on_wgrad(e_loss, lambda: dp_dense("1", self.d0, self.g_coarse, e_g))
-        elif not fused:
+        merged = gather and os.environ.get("A3D_DP_MERGED", "1") != "0"
+        e_g1 = e_g
+        if gather and not merged:
+            on_wgrad(e_loss, lambda: dp_dense("1", self.d0, self.g_coarse, e_g), label="dp dense_1 enqueue")
+        elif not fused and not gather:
             # the bucket's Adam overwrites dense_1's weights: it waits for e_g (dense_1's dgrad has read them)
             on_wgrad(e_loss, lambda: (c.dense_wgrad(self.d0, self.g_coarse, dw=self.gw(nd + "1" + K),
                                                     db=self.gw(nd + "1/bias"), impl=self.impl),
                                       self.comm and dp_update("dense_1", "CoarseDense", e_g)))
         if fused:       # updates dense_1's weights: must follow dense_1's dgrad, their last reader
-            on_wgrad(e_g, lambda: dense_wgrad_adam("1", self.d0, self.g_coarse))
+            on_wgrad(e_g, lambda: dense_wgrad_adam("1", self.d0, self.g_coarse), label="dense_1 wgrad+adam")
         e_d0 = e_g
-        c.dense_dgrad(self.g_d0, self.w(nd + "0" + K), out=self.g_c4a.view(B, 12288), impl=self.impl)
-        c.relu_bwd(self.c4, self.g_c4a, out=self.g_c4)
+        c.dense_dgrad_act(self.g_d0, self.w(nd + "0" + K), self.c4.view(B, 12288), None, 0.0, L.EPI_RELU,
+                          out=self.g_c4.view(B, 12288), impl=self.impl)
         e_g = mark(s0)
-        if gather:
-            on_wgrad(e_d0, lambda: dp_dense("0", self.c4.view(B, 12288), self.g_d0, e_g))
+        if merged:
+            # one activation all-gather for both layers as soon as g_d0 exists (e_d0); each layer's row update waits for
+            # its own dgrad; the updated rows are published at the start of the next step
+            g_ = "CoarseDense"
+            self.comm.dense_gather_adam_merged(
+                self, [(nd + "1" + K, nd + "1/bias", self.d0, self.g_coarse, e_g1),
+                       (nd + "0" + K, nd + "0/bias", self.c4.view(B, 12288), self.g_d0, e_g)],
+                g_, ADAM_LR[g_], ADAM_BETA1, ADAM_EPS, ready=e_d0)
+        elif gather:
+            on_wgrad(e_d0, lambda: dp_dense("0", self.c4.view(B, 12288), self.g_d0, e_g), label="dp dense_0 enqueue")
         elif not fused:
             on_wgrad(e_d0, lambda: (c.dense_wgrad(self.c4.view(B, 12288), self.g_d0, dw=self.gw(nd + "0" + K),
                                                   db=self.gw(nd + "0/bias"), impl=self.impl),
                                     self.comm and dp_update("dense_0", "CoarseDense", e_g)))
+        c.stamp("dense dgrad done")
         if fused:
-            on_wgrad(e_g, lambda: dense_wgrad_adam("0", self.c4.view(B, 12288), self.g_d0))
+            on_wgrad(e_g, lambda: dense_wgrad_adam("0", self.c4.view(B, 12288), self.g_d0), label="dense_0 wgrad+adam")
         elif not self.comm:
             # single GPU: the dense group's Adam runs under the conv backward.  It overwrites the dense weight
             # mirror, so it waits for e_g: both dense dgrads (the last readers of those weights) are done.
             on_wgrad(e_g, lambda: self.apply_adam(("CoarseDense",)))
         conv_wgrad(self.d_c4, self.c3, self.g_c4, n + "4", e_g)
         c.conv2d_dgrad(self.d_c4, self.g_c4, self.w(n + "4" + K), out=self.g_c3, relu_src=self.c3)
+        c.stamp("dgrad conv2d_4 done")
         e_g = mark(s0)
         conv_wgrad(self.d_c3, self.c2, self.g_c3, n + "3", e_g)
         s0.wait_event(e_flip)
@@ -504,6 +544,7 @@ class MSDNNet:
         conv_wgrad(self.d_c2, self.p1, self.g_c2, n + "2", e_g)
         c.conv2d_dgrad(self.d_c2, self.g_c2, self.w(n + "2" + K), out=self.g_p1, wflip=self._wflip["2"])
         c.maxpool2x2_idx_bwd(self.i1, self.g_p1, (B, 27, 37, 256), out=self.g_c1)
+        c.stamp("dgrad conv2d_3,2 + pool bwd done")
         e_g = mark(s0)
         # (DP: exchanging conv2d_4..2 here as an early bucket was measured SLOWER at 2 GPUs, 1.30 vs 1.26 ms: three more
         # NCCL launches cost more than the shorter tail saves; dp.bucket_range keeps the early/late split available)
@@ -511,6 +552,7 @@ class MSDNNet:
         e_w1 = mark(s3)                                # gradients of conv2d_4 .. conv2d_1 are complete
         c.conv2d_dgrad(self.d_c1, self.g_c1, self.w(n + "1" + K), out=self.g_p0, wflip=self._wflip["1"])
         c.maxpool2x2_idx_bwd(self.i0, self.g_p0, (B, 55, 74, 96), out=self.g_c0)
+        c.stamp("dgrad conv2d_1 + pool bwd done")
         e_g = mark(s0)
         # Single GPU: TF-Adam of conv2d_4 .. conv2d_1 (99 % of the group) runs on the idle fine stream next to
         # conv2d_0's weight gradient; only conv2d_0's 55 k parameters are updated in the step's tail.  The group is
@@ -529,6 +571,18 @@ class MSDNNet:
         # the GEMMs they overlap with -- so it is off by default.
         dp_split = bool(self.comm) and lo_cc < split_cc < hi_cc and (split_cc - lo_cc) % (self.comm.world * 8) == 0 and \
             os.environ.get("A3D_DP_CONV_SPLIT", "0") == "1" and not conv_allreduce
+        # With the f32-allreduce exchange (4+ ranks) the same cut is ON by default: conv2d_4 .. conv2d_1 (99 % of the bucket)
+        # are all-reduced and updated behind conv2d_1's weight gradient, under conv2d_1's dgrad, the pool backward and
+        # conv2d_0's wgrad; the step's tail exchanges conv2d_0's 55 k parameters only.  (8 GPUs, profiles/
+        # step_timeline_r02_n8_rank0.json: the single 16 MB allreduce + Adam was ~150 us of exposed tail.)
+        dp_split_ar = bool(self.comm) and conv_allreduce and lo_cc < split_cc < hi_cc and \
+            os.environ.get("A3D_DP_CONV_SPLIT", "1") == "1"
+        if dp_split_ar:
+            with torch.cuda.stream(s3):
+                if side_bias:
+                    s3.wait_event(e_bias[n + "1"])
+                self.comm.bucket_ready(self, "coarse_conv_main", after=e_g,
+                                       then=lambda lo, hi: self.adam_range("CoarseConv", lo, hi, inv_world))
         if dp_split:
             with torch.cuda.stream(s3):
                 if side_bias:
@@ -554,7 +608,7 @@ class MSDNNet:
             if e_b0 is not None:
                 s3.wait_event(e_b0)
             self._mask_padding("coarse/conv/conv2d_0/kernel")
-            if self.comm and dp_split:
+            if self.comm and (dp_split or dp_split_ar):
                 self.comm.bucket_ready(self, "coarse_conv_0",
                                        then=lambda lo, hi: self.adam_range("CoarseConv", lo, hi, inv_world))
                 self.comm.wait_all(self)
@@ -569,18 +623,21 @@ class MSDNNet:
                 self.adam_range("CoarseConv", split_cc, hi_cc)
             else:
                 self.apply_adam(("CoarseConv",))
-        on_wgrad(e_g, conv0_and_adam, s3)
+        on_wgrad(e_g, conv0_and_adam, s3, label="conv2d_0 wgrad + conv exchange/adam")
         # ---- join
         s0.wait_event(e_fine)
         s0.wait_event(mark(s2))
         if s3 is not s2:
             s0.wait_event(mark(s3))
         c.increment_i64(self.step_dev)
+        c.stamp("step end")
 
     # ------------------------------------------------------------------ one session.run(model_op)
     def _enqueue_step(self, phase):
         if phase == 1 and self.overlap and self.train:
             return self._enqueue_phase1_overlapped()
+        if self.comm:
+            self.comm.flush(self)                       # rows updated by a previous (overlapped) step
         self.forward()
         if phase == 1:
             fused = self.fuse_dense_adam and not self.comm

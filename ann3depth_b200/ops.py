@@ -66,6 +66,7 @@ class Context:
         self.h = h
         self._ws = {}
         self.ws_tag = ""          # set per stream by multi-stream callers: concurrent launches must not share scratch
+        self.timeline = None      # StepTimeline when A3D_TIMELINE=1 (stamp() is a no-op otherwise)
 
     def close(self):
         if getattr(self, "h", None):
@@ -85,6 +86,11 @@ class Context:
     @property
     def launches(self):
         return int(self.lib.a3d_launch_count(self.h))
+
+    def stamp(self, label):
+        """In-graph timeline mark on the current stream (see StepTimeline); no-op unless a timeline is attached."""
+        if self.timeline is not None:
+            self.timeline.mark(self, label)
 
     def workspace(self, key, nbytes):
         """Persistent scratch buffers (allocated once, so steps stay CUDA-graph capturable)."""
@@ -330,14 +336,26 @@ class Context:
                                          _stream()), "dense_dgrad")
         return out
 
-    def dense_wgrad(self, x, dy, dw=None, db=None, impl=L.IMPL_AUTO, N=None):
-        """dw[N,K] = dy[:, :N]^T x ; dy row stride = dy.shape[1], x row stride = x.shape[1]."""
+    def dense_dgrad_act(self, dy, w, y_act, keep_mask=None, drop_rate=0.0, flags=L.EPI_RELU, out=None, impl=L.IMPL_AUTO):
+        """dense_dgrad + DropoutGrad + ReluGrad/SigmoidGrad of the producer layer in one finishing pass."""
         M, lddy = dy.shape
-        N = N if N is not None else (dw.shape[0] if dw is not None else lddy)
+        N, K = w.shape
+        if out is None:
+            out = torch.empty(M, K, dtype=torch.bfloat16, device=dy.device)
+        acc = self.workspace(("dense_dacc", M, K), M * K * 4)
+        L.check(self.lib.a3d_dense_dgrad_act(self.h, _ptr(dy), lddy, _ptr(w), _ptr(out), _ptr(acc), M, N, K, impl,
+                                             _ptr(y_act), _ptr(keep_mask), drop_rate, flags, _stream()), "dense_dgrad_act")
+        return out
+
+    def dense_wgrad(self, x, dy, dw=None, db=None, impl=L.IMPL_AUTO, N=None):
+        """dw[N,K] = dy[:, :N]^T x ; row strides are the tensors' own (dy may be a column slice of a wider matrix)."""
+        M = dy.shape[0]
+        lddy, ldx = dy.stride(0), x.stride(0)
+        N = N if N is not None else (dw.shape[0] if dw is not None else dy.shape[1])
         K = x.shape[1]
         if dw is None:
             dw = torch.empty(N, K, dtype=torch.float32, device=x.device)
-        L.check(self.lib.a3d_dense_wgrad(self.h, _ptr(x), K, _ptr(dy), lddy, _ptr(dw), _ptr(db), M, N, K, impl,
+        L.check(self.lib.a3d_dense_wgrad(self.h, _ptr(x), ldx, _ptr(dy), lddy, _ptr(dw), _ptr(db), M, N, K, impl,
                                          _stream()), "dense_wgrad")
         return dw, db
 
@@ -447,6 +465,7 @@ class Context:
         buf = C.create_string_buffer(id_bytes, 128)
         L.check(self.lib.a3d_comm_init(self.h, nccl_path.encode() if nccl_path else None, buf, rank, nranks),
                 "comm_init")
+        self._world = nranks
 
     def allreduce_sum(self, t, count=None):
         code = L.A3D_BF16 if t.dtype == torch.bfloat16 else L.A3D_F32
@@ -457,9 +476,45 @@ class Context:
         """In place on t (world*chunk elements): afterwards rank r holds the sum in t[r*chunk:(r+1)*chunk]."""
         L.check(self.lib.a3d_reduce_scatter_sum(self.h, _ptr(t), chunk, _code(t), _stream()), "reduce_scatter")
 
+    def allgather_multi(self, tensors):
+        """Grouped in-place all-gather of several equal-dtype tensors (each world * chunk elements): one NCCL launch."""
+        n = len(tensors)
+        ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in tensors])
+        chunks = (C.c_size_t * n)(*[t.numel() // self._world for t in tensors])
+        L.check(self.lib.a3d_allgather_multi(self.h, ptrs, chunks, n, _code(tensors[0]), _stream()), "allgather_multi")
+
     def allgather(self, t, chunk):
         """In place on t (world*chunk elements): publishes every rank's slice t[r*chunk:(r+1)*chunk]."""
         L.check(self.lib.a3d_allgather(self.h, _ptr(t), chunk, _code(t), _stream()), "allgather")
+
+
+class StepTimeline:
+    """Per-stream time marks INSIDE a captured step (the whole step is one CUDA graph, so it cannot be timed call by
+    call): `ctx.stamp(label)` enqueues a one-thread kernel that stores the GPU's global timer when its stream gets there.
+    Every enqueue of the step (warm-up, capture) re-registers the same labels in the same order; a graph replay then
+    refreshes the slots and `read()` returns [(label, stream id, microseconds since the first mark)]."""
+
+    def __init__(self, device, capacity=256):
+        self.slots = torch.zeros(capacity, dtype=torch.int64, device=device)
+        self.labels, self.n = [], 0
+
+    def begin(self):
+        self.n = 0
+
+    def mark(self, ctx, label):
+        st = torch.cuda.current_stream()
+        if self.n < len(self.labels):
+            self.labels[self.n] = (label, st.cuda_stream)
+        else:
+            self.labels.append((label, st.cuda_stream))
+        L.check(ctx.lib.a3d_stamp(ctx.h, C.c_void_p(self.slots[self.n:].data_ptr()), C.c_void_p(st.cuda_stream)), "stamp")
+        self.n += 1
+
+    def read(self):
+        torch.cuda.synchronize()
+        t = self.slots[:self.n].cpu().tolist()
+        t0 = min(t) if t else 0
+        return [(lab, st, (ti - t0) / 1e3) for (lab, st), ti in zip(self.labels[:self.n], t)]
 
 
 def _code(t):

@@ -291,6 +291,7 @@ def gpu_arm(args, rank, world, local_rank):
     e0.record()
     for _ in range(args.steps):
         op.run()
+    op.net.flush()          # DP: the last step's deferred weight-row exchange belongs to the timed region (no-op at N=1)
     e1.record()
     barrier()
     sampler.stop_flag = True
@@ -402,44 +403,27 @@ def gpu_arm(args, rank, world, local_rank):
             roof["traffic"] = traffic.get(roof["kernel"])
         except Exception:
             pass
-        if world > 1 and saved_comm is not None and getattr(saved_comm, "_gbufs", None):
+        if world > 1 and saved_comm is not None and getattr(saved_comm, "rows_launches", None):
             # Data parallel: the dominant kernel of the step is not the single-GPU fused update but its row-sharded
-            # form on the all-gathered batch (dp.dense_gather_adam -> a3d_dense_wgrad_adam_rows).  Time exactly that
-            # launch (rank 0, no collective inside) with CUDA events and report ITS roofline.
-            from ann3depth_b200.msdn import ADAM_LR, ADAM_BETA1, ADAM_EPS
-            net, a = op.net, op.net.arena
+            # form on the all-gathered batch (dp.dense_gather_adam_merged -> a3d_dense_wgrad_adam_rows).  Time exactly
+            # that launch (rank 0, no collective inside) with CUDA events and report ITS roofline.
             kn = "coarse/dense/dense_0/kernel"
-            gbuf = saved_comm._gbufs.get(("gather", kn))
-            if gbuf is not None:
-                rows_all, Kd = a.specs[kn].packed_shape
-                Nd = a.specs[kn].tf_shape[1]
-                r = rows_all // world
-                blk = gbuf.shape[1]
-                lddy = (blk - BATCH * Kd) // BATCH
-                xg, dyg = gbuf.view(-1), gbuf.view(-1)[BATCH * Kd:]
-
-                def rows_launch():
-                    ctx.dense_wgrad_adam_rows(xg, dyg, a.view(a.w, kn), a.view(a.m, kn), a.view(a.v, kn), a.view(a.wb, kn),
-                                              rank * r, (rank + 1) * r, ADAM_LR["CoarseDense"], ADAM_BETA1, net.beta2,
-                                              ADAM_EPS, max(net.adam_t["CoarseDense"], 1), 1.0 / world,
-                                              lr_t_dev=net.lr_dev["CoarseDense"], N=Nd, M=world * BATCH, ldx=Kd, lddy=lddy,
-                                              group_rows=BATCH, x_group_stride=blk, dy_group_stride=blk)
-                for _ in range(3):
-                    rows_launch()
-                ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-                ev[0].record()
-                for _ in range(10):
-                    rows_launch()
-                ev[1].record()
-                torch.cuda.synchronize()
-                ms = ev[0].elapsed_time(ev[1]) / 10
-                Mg = world * BATCH
-                ach = (26.0 * r * Kd + 2.0 * Mg * (Kd + lddy)) / (ms * 1e-3) / 1e9
-                roof = {"bound": "hbm", "kernel": f"a3d_dense_wgrad_adam_rows M={Mg} rows={r}/{rows_all} K={Kd}",
-                        "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                        "traffic": None, "peak_kind": pk_kind, "launch_ms": ms,
-                        "note": "timed alone on rank 0 (10 launches, CUDA events); L2-resident repeats are not possible: "
-                                "the row slice (26 B x %d params) exceeds L2" % (r * Kd)}
+            rows_launch, g = saved_comm.rows_launches[kn]
+            for _ in range(3):
+                rows_launch()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ev[0].record()
+            for _ in range(10):
+                rows_launch()
+            ev[1].record()
+            torch.cuda.synchronize()
+            ms = ev[0].elapsed_time(ev[1]) / 10
+            ach = (g["bytes_per_param"] * g["rows"] * g["K"] + 2.0 * g["M"] * (g["K"] + g["lddy"])) / (ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": f"{g['kernel']} M={g['M']} rows={g['rows']}/{g['rows_all']} K={g['K']}",
+                    "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                    "traffic": None, "peak_kind": pk_kind, "launch_ms": ms,
+                    "note": "timed alone on rank 0 (10 launches, CUDA events); this rank's row slice is %.0f B x %d params "
+                            "per launch" % (g["bytes_per_param"], g["rows"] * g["K"])}
         roof["conv_tensor_tflops"] = tflops / (tms * 1e-3) / 1e12 if tms else None
         roof["conv_tensor_frac_of_burst"] = roof["conv_tensor_tflops"] / pk["bf16_tflops"] if tms else None
         # conv + FC aggregate (the dense layers at batch 32 are weight-streaming, i.e. HBM-bound, kernels)

@@ -159,6 +159,13 @@ int a3d_dense_fwd(a3d_ctx*, const uint16_t* x, int ldx, const uint16_t* w, const
  * elements for the tensor-core path), dx bf16 [M,K], acc_ws f32 [M,K]. */
 int a3d_dense_dgrad(a3d_ctx*, const uint16_t* dy, int lddy, const uint16_t* w, uint16_t* dx, float* acc_ws,
                     int M, int N, int K, int impl, void* stream);
+/* a3d_dense_dgrad followed by the activation gradient of the layer that produced x, in the dgrad's own finishing pass
+ * (MatMul grad -> DropoutGrad -> ReluGrad / SigmoidGrad of src/models.py:228-232 backwards): y_act bf16 [M,K] is that
+ * layer's stored post-activation (and post-dropout) output, keep_mask u8 [M,K] nullable, flags A3D_EPI_RELU/SIGMOID.
+ * Equals a3d_dense_dgrad + a3d_dense_epilogue_bwd bit for bit. */
+int a3d_dense_dgrad_act(a3d_ctx*, const uint16_t* dy, int lddy, const uint16_t* w, uint16_t* dx, float* acc_ws,
+                        int M, int N, int K, int impl, const uint16_t* y_act, const uint8_t* keep_mask,
+                        float drop_rate, unsigned flags, void* stream);
 /* dw[N,K] = dy[M,N]^T . x[M,K] ; db[N] = sum_M dy.   dw/db f32, overwritten. */
 int a3d_dense_wgrad(a3d_ctx*, const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, float* db,
                     int M, int N, int K, int impl, void* stream);
@@ -248,6 +255,10 @@ int a3d_bernoulli_mask(a3d_ctx*, uint8_t* keep, size_t n, float keep_prob, uint6
                        const int64_t* counter_dev, void* stream);
 /* *p += 1 (device-resident global_step, src/models.py:279,329,343,356). */
 int a3d_increment_i64(a3d_ctx*, int64_t* p, void* stream);
+/* Timeline probe (src/tfhelper.py:192-249 TraceHook's role, for steps that run as ONE captured CUDA graph and therefore
+ * cannot be timed call by call): enqueues a one-thread kernel that stores %globaltimer (ns) in *slot when the stream
+ * reaches it.  Not counted as a launch (a3d_launch_count). */
+int a3d_stamp(a3d_ctx*, uint64_t* slot, void* stream);
 /* f32 -> bf16 cast of a flat segment (weight mirror refresh). */
 int a3d_cast_f32_bf16(a3d_ctx*, const float* src, uint16_t* dst, size_t n, void* stream);
 
@@ -316,6 +327,8 @@ int a3d_allreduce_sum(a3d_ctx*, void* buf, size_t count, int dtype, void* stream
  * rank r holds the sum in buf[r*chunk, (r+1)*chunk); the all-gather publishes every rank's slice. */
 int a3d_reduce_scatter_sum(a3d_ctx*, void* buf, size_t chunk, int dtype, void* stream);
 int a3d_allgather(a3d_ctx*, void* buf, size_t chunk, int dtype, void* stream);
+/* n all-gathers as one NCCL group (one launch): bufs[i] = nranks * chunks[i] elements, gathered in place. */
+int a3d_allgather_multi(a3d_ctx*, void* const* bufs, const size_t* chunks, int n, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

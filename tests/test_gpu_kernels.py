@@ -185,7 +185,22 @@ def test_tc_gemm_multicast(ctx, variant, bn, M):
     assert rel_err(D, A.float() @ B.float().t()) < 2e-3
 
 
-@pytest.mark.parametrize("force", ["128,1,1", "128,1,2", "256,1,2", "256,1,3", "64,1,2", "96,1,3"])
+@pytest.mark.parametrize("variant", [11, 12])
+@pytest.mark.parametrize("bn", [64, 96, 128, 192, 256])
+@pytest.mark.parametrize("M", [100, 128 * 5 + 7, 128 * 300 + 1])
+def test_tc_gemm_cta_pair(ctx, variant, bn, M):
+    """tcgen05.mma.cta_group::2 (tc_pair.cuh): 256 x BN tile per CTA pair, each CTA holds half of the B tile.  Fewer rows
+    than one CTA (the peer of the only pair is all padding), an odd tile count (ragged last pair), many pairs; two N
+    tiles with a clipped last one; K = 9 k-blocks > the short ring's depth."""
+    N, K = 2 * bn - 8, 64 * 9
+    A = bf16_rand(M, K, seed=7)
+    B = bf16_rand(N, K, seed=8)
+    D = ctx.debug_tc_gemm(A, B, M, N, K, bn, 128, variant=variant)
+    assert rel_err(D, A.float() @ B.float().t()) < 2e-3
+
+
+@pytest.mark.parametrize("force", ["128,1,1", "128,1,2", "256,1,2", "256,1,3", "64,1,2", "96,1,3", "256,1,11", "128,1,12",
+                                   "64,1,11", "192,1,12"])
 @pytest.mark.parametrize("layer", [LAYERS_BY_NAME[n] for n in ("conv2d_1", "fine_second", "conv2d_0_s2d4", "dcnf_conv2d_1")],
                          ids=["conv2d_1", "fine_second", "conv2d_0_s2d4", "dcnf_conv2d_1"])
 def test_conv_fwd_tile_variants(ctx, monkeypatch, layer, force):
@@ -470,6 +485,29 @@ def test_relu_bwd_and_dense_epilogue_bwd(ctx):
     assert torch.equal(g, ref)
 
 
+@pytest.mark.parametrize("M,N,K,drop", [(32, 4070, 4096, True), (32, 4096, 12288, False), (7, 128, 512, True)])
+def test_dense_dgrad_act_equals_two_passes(ctx, M, N, K, drop):
+    """a3d_dense_dgrad_act (dgrad + DropoutGrad + ReluGrad in the finishing pass) == a3d_dense_dgrad followed by
+    a3d_dense_epilogue_bwd, bit for bit (src/models.py:228-232 backwards)."""
+    ld = (N + 7) // 8 * 8
+    dy = bf16_rand(M, ld, seed=60)
+    w = bf16_rand(N, K, seed=61, scale=0.05)
+    y = torch.relu(bf16_rand(M, K, seed=62).float()).to(torch.bfloat16)
+    mask = (torch.rand(M, K, generator=torch.Generator().manual_seed(63)) < 0.5).to(torch.uint8).to(DEV) if drop else None
+    rate = 0.5 if drop else 0.0
+    a = ctx.dense_dgrad(dy, w)
+    a = ctx.dense_epilogue_bwd(a, y, mask, rate, L.EPI_RELU)
+    b = ctx.dense_dgrad_act(dy, w, y, mask, rate, L.EPI_RELU)
+    # the split-K partial sums are accumulated with f32 atomics: two runs of the SAME GEMM differ in the last bit now and
+    # then, so compare as the other dense tests do
+    assert rel_err(b, a.float()) < 2e-2
+    ref = (dy[:, :N].float() @ w.float()) * (y.float() > 0)
+    if drop:
+        ref = ref * mask.float() * 2.0
+    assert rel_err(b, ref) < 2e-2
+    assert bool(((b.float() == 0) | (y.float() > 0)).all())            # exact zeros wherever the unit was off
+
+
 @pytest.mark.parametrize("quantised", [False, True])
 def test_silog_loss_vs_oracle(ctx, quantised):
     g = torch.Generator().manual_seed(45)
@@ -609,6 +647,25 @@ def test_conv_pool4_fwd_bwd(ctx, impl):
     exp = torch.zeros(N * d.P * d.Q, 4, 64, device=DEV)
     exp.scatter_(1, idx.view(-1, 1, 64).long(), (dy.float() * (y.float() > 0)).view(-1, 1, 64))
     assert torch.equal(big.float().view(-1, 4, 64), exp)
+
+
+@pytest.mark.parametrize("force", ["6", "7"])
+def test_conv_pool4_fwd_cta_pair(ctx, monkeypatch, force):
+    """pool-fused fine/first GEMM through the CTA-pair kernel (short / deep ring) == one-CTA kernel, bit for bit"""
+    N, H, W, Cc = 3, 57, 76, 64
+    d = ops.conv_desc(N, H, W, Cc, 256, 3, 3, 1, "valid", ldy=64, impl=L.IMPL_AUTO)
+    x = bf16_rand(N, H, W, Cc, seed=40)
+    w = bf16_rand(256, 3, 3, Cc, seed=41, scale=1.0 / math.sqrt(9 * Cc))
+    bias = (torch.rand(64, generator=torch.Generator().manual_seed(42)) - 0.5).to(DEV) * 0.2
+    res = []
+    for f in ("0", force):
+        monkeypatch.setenv("A3D_POOL4_FORCE", f)
+        y = torch.full((N, d.P, d.Q, 64), 7.0, dtype=torch.bfloat16, device=DEV)
+        idx = torch.full((N, d.P, d.Q, 64), 9, dtype=torch.uint8, device=DEV)
+        ctx.conv2d_pool4_fwd(d, x, w, bias, relu=True, out=y, idx=idx)
+        res.append((y, idx))
+    monkeypatch.delenv("A3D_POOL4_FORCE")
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])     # same MMA order: bit-exact
 
 
 @pytest.mark.skipif(__import__("os").environ.get("A3D_TEST_MCAST") != "1",

@@ -38,6 +38,7 @@ def main():
     groups = {
         "none": {},
         "adam": {"adam_tf": noop},
+        "fused dense wgrad+adam (both layers)": {"dense_wgrad_adam": noop},
         "dense_wgrad": {"dense_wgrad": noop},
         "dense_fwd+dgrad": {"dense_fwd": noop, "dense_dgrad": noop},
         "conv_wgrad": {"conv2d_wgrad": noop},

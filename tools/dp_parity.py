@@ -30,6 +30,8 @@ from ann3depth_b200.dp import DataParallel  # noqa: E402
 def all_equal(t, world):
     """True when every rank holds the same tensor bits."""
     mine = t.detach().cpu().contiguous()
+    if mine.dtype in (torch.int16, torch.bfloat16):      # gloo has no 16-bit types
+        mine = mine.view(torch.int16).to(torch.int32)
     ref = mine.clone()
     dist.broadcast(ref, src=0)
     flags = [None] * world
@@ -62,6 +64,7 @@ def main():
     net.load_params(p)
     net.set_dropout_mask(mask.to(dev))
     op.run()                                             # graph path, as bench.py runs it
+    net.flush()                                          # rows updated by peers are otherwise fetched by the next step
     torch.cuda.synchronize()
     report = {"n_gpus": world, "batch_per_gpu": B}
     report["identical_bf16_weights_after_step_1"] = all_equal(net.arena.wb.view(torch.int16), world)
@@ -101,6 +104,7 @@ def main():
         report["loss_coarse_oracle_big_batch"] = loss_ref
     # a second step: replicas must stay in lock-step
     op.run()
+    net.flush()
     torch.cuda.synchronize()
     report["identical_bf16_weights_after_step_2"] = all_equal(net.arena.wb.view(torch.int16), world)
     bias_ok = True
