@@ -25,11 +25,22 @@ CUtensorMapSwizzle swizzle_for(int row_bytes) {
                            : CU_TENSOR_MAP_SWIZZLE_NONE;
 }
 
-// bf16 2-D tensor [rows][cols] (cols contiguous, row pitch ld elements); box = box_cols x box_rows.
+// Operand element type of a tensor map: 2 = bf16; 4 = f32 read as TFLOAT32 -- the TMA unit rounds the low 13 mantissa
+// bits away (round to nearest) on the way into shared memory, so kind::tf32 MMAs see properly rounded TF32 values
+// instead of truncated ones.  A3D_TF32_TMAP=0 selects plain FLOAT32 maps (the MMA then truncates).
+CUtensorMapDataType tmap_dtype(int elt) {
+  if (elt == 2) return CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("A3D_TF32_TMAP"); v = e ? atoi(e) : 1; }
+  return v ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+}
+
+// 2-D operand tensor [rows][cols] (cols contiguous, row pitch ld elements of `elt` bytes); box = box_cols x box_rows.
+// mn_major: the operand is consumed MN-major; for 4-byte elements that needs the 32-byte-atom variant of the 128-byte swizzle.
 int make_tmap_2d(a3d_ctx* ctx, CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
-                 uint32_t box_cols, uint32_t box_rows) {
+                 uint32_t box_cols, uint32_t box_rows, int elt = 2, bool mn_major = false) {
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 2};
+  cuuint64_t strides[1] = {ld * (uint64_t)elt};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides[0] & 15)) {
@@ -37,8 +48,9 @@ int make_tmap_2d(a3d_ctx* ctx, CUtensorMap* tm, const void* base, uint64_t rows,
     return A3D_EINVAL;
   }
   CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->fn_encode_tiled)(
-      tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(box_cols * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+      tm, tmap_dtype(elt), 2, const_cast<void*>(base), dims, strides, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, (elt == 4 && mn_major) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : swizzle_for(box_cols * elt),
+      CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     a3d_set_error("cuTensorMapEncodeTiled failed (%d): rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r,
@@ -71,11 +83,12 @@ int make_tmap_chunked(a3d_ctx* ctx, CUtensorMap* tm, const void* base, uint64_t 
   return 0;
 }
 
-// bf16 NHWC activation tensor in im2col mode.  Base pixels run over lower + {0..P-1} * stride per axis.
+// NHWC activation tensor (bf16, or f32 read as TF32) in im2col mode.  Base pixels run over lower + {0..P-1} * stride per axis.
 int make_tmap_im2col(a3d_ctx* ctx, CUtensorMap* tm, const void* base, int N, int H, int W, int C, int lower_h,
-                     int lower_w, int P, int Q, int sh, int sw, uint32_t chan_box, uint32_t pixels) {
+                     int lower_w, int P, int Q, int sh, int sw, uint32_t chan_box, uint32_t pixels, int elt = 2,
+                     bool mn_major = false) {
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint64_t strides[3] = {(cuuint64_t)C * elt, (cuuint64_t)W * C * elt, (cuuint64_t)H * W * C * elt};
   // tightest bounding box that still contains the last base pixel (see DESIGN.md "im2col corners")
   int upper_w = lower_w + (Q - 1) * sw + 1 - W;
   int upper_h = lower_h + (P - 1) * sh + 1 - H;
@@ -93,8 +106,9 @@ int make_tmap_im2col(a3d_ctx* ctx, CUtensorMap* tm, const void* base, int N, int
     return A3D_EINVAL;
   }
   CUresult r = reinterpret_cast<EncodeIm2colFn>(ctx->fn_encode_im2col)(
-      tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, lower, upper, chan_box, pixels,
-      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(chan_box * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+      tm, tmap_dtype(elt), 4, const_cast<void*>(base), dims, strides, lower, upper, chan_box, pixels,
+      estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+      (elt == 4 && mn_major) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : swizzle_for(chan_box * elt), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     a3d_set_error("cuTensorMapEncodeIm2col failed (%d): NHWC=%d,%d,%d,%d lower=%d,%d upper=%d,%d box=%u x %u", (int)r, N,
@@ -104,7 +118,7 @@ int make_tmap_im2col(a3d_ctx* ctx, CUtensorMap* tm, const void* base, int N, int
   // Driver quirk also worked around by CUTLASS (copy_traits_sm90_im2col.hpp): for tensors smaller
   // than 128 KiB, drivers <= 13.1 set a descriptor bit that makes im2col loads fault.
   if (ctx->driver_version <= 13010) {
-    size_t bytes = (size_t)N * H * W * C * 2;
+    size_t bytes = (size_t)N * H * W * C * elt;
     if (bytes < 131072) reinterpret_cast<uint64_t*>(tm)[1] &= ~(1ull << 21);
   }
   return 0;
@@ -1092,5 +1106,41 @@ extern "C" int a3d_debug_tc_gemm_v(a3d_ctx* ctx, const uint16_t* A, const uint16
   A3D_MN_CASE(64, false, true) A3D_MN_CASE(128, false, true) A3D_MN_CASE(256, false, true)
 #undef A3D_MN_CASE
   a3d_set_error("debug gemm: no kernel for BN=%d a_mn=%d b_mn=%d", bn, a_mn, b_mn);
+  return A3D_ENOTSUP;
+}
+
+// ---- TF32 (kind::tf32) engine test hook: D[M][N] (f32) = A * B^T with f32 operands read as TF32, every combination of
+// operand majors.  K-major operand: [rows][K]; MN-major operand: [K][rows].  kcb: bytes of K per row and stage (K-major).
+extern "C" int a3d_debug_tc_gemm_tf32(a3d_ctx* ctx, const float* A, const float* B, float* D, int M, int N, int K, int bn,
+                                      int kcb, int a_mn, int b_mn, int splits, void* stream) {
+  A3D_REQUIRE(ctx && A && B && D, "debug gemm tf32: null argument");
+  cudaStream_t st = as_stream(stream);
+  CUtensorMap tmA, tmB;
+  int rc;
+  const int kelems = (a_mn || b_mn) ? 32 : kcb / 4;
+  A3D_REQUIRE(K % kelems == 0, "debug gemm tf32: K must be a multiple of %d", kelems);
+  if (a_mn) rc = make_tmap_2d(ctx, &tmA, A, K, M, M, 32, 32, 4, true);
+  else rc = make_tmap_2d(ctx, &tmA, A, M, K, K, kelems, 128, 4);
+  if (rc) return rc;
+  if (b_mn) rc = make_tmap_2d(ctx, &tmB, B, K, N, N, 32, 32, 4, true);
+  else rc = make_tmap_2d(ctx, &tmB, B, N, K, K, kelems, bn, 4);
+  if (rc) return rc;
+  tc::Params p{};
+  p.M = M; p.N = N; p.num_kb = K / kelems; p.a_mode = tc::A_TILED;
+  if (splits < 1) splits = 1;
+  p.kb_per_split = ceil_div(p.num_kb, splits);
+  splits = ceil_div(p.num_kb, p.kb_per_split);
+  p.epi = tc::EPI_ROW_F32; p.out = D; p.ldo = N; p.atomic = splits > 1;
+  if (splits > 1) A3D_CHECK_CUDA(cudaMemsetAsync(D, 0, (size_t)M * N * sizeof(float), st));
+#define A3D_T32(BN, KCB, AM, BM_) \
+  if (bn == BN && kcb == KCB && (bool)a_mn == AM && (bool)b_mn == BM_) \
+    return launch_cfg<tc::Cfg<BN, KCB, AM, BM_, 32, A3D_MIN_STAGES, false, 128, 4>>(ctx, tmA, tmB, p, splits, st);
+  A3D_T32(32, 128, false, false) A3D_T32(64, 128, false, false) A3D_T32(128, 128, false, false) A3D_T32(256, 128, false, false)
+  A3D_T32(64, 64, false, false) A3D_T32(128, 64, false, false) A3D_T32(64, 32, false, false) A3D_T32(16, 128, false, false)
+  A3D_T32(64, 128, true, true) A3D_T32(128, 128, true, true) A3D_T32(256, 128, true, true)
+  A3D_T32(32, 128, true, false) A3D_T32(64, 128, true, false) A3D_T32(128, 128, true, false)
+  A3D_T32(64, 128, false, true) A3D_T32(128, 128, false, true) A3D_T32(256, 128, false, true)
+#undef A3D_T32
+  a3d_set_error("debug gemm tf32: no kernel for BN=%d KCB=%d a_mn=%d b_mn=%d", bn, kcb, a_mn, b_mn);
   return A3D_ENOTSUP;
 }

@@ -80,9 +80,19 @@ struct Params {
   const float* lr_t_dev;
 };
 
+// ELT_ = operand element size in bytes: 2 = bf16 (kind::f16), 4 = f32 consumed as TF32 (kind::tf32).  All shared-memory
+// geometry below is in BYTES, so the two differ only in elements per row: a UMMA K step is always 32 bytes (16 bf16 /
+// 8 tf32), an MN-major row always 128 bytes (64 bf16 / 32 tf32 elements), and an MN-major stage holds 128 / ELT K-rows.
 template <int BN_, int KCB_, bool A_MN_, bool B_MN_, int B_BW_ = 64, int MIN_STAGES_ = A3D_MIN_STAGES, bool ADAM_ = false,
-          int BM_ = 128>
+          int BM_ = 128, int ELT_ = 2>
 struct Cfg {
+  static constexpr int ELT = ELT_;
+  static constexpr int KROWS = 128 / ELT_;                // MN-major: K rows per stage (64 bf16, 32 tf32)
+  static constexpr int A_MN_BLOCKS = ELT_;                // MN-major A: 128-byte-wide blocks per 128 rows (2 / 4)
+  static constexpr int A_MN_BLK_BYTES = KROWS * 128;      // one block: KROWS rows x 128 bytes (8 KB / 4 KB)
+  static constexpr int A_MN_BLK_ELEMS = 128 / ELT_;       // M elements per block (64 / 32)
+  static_assert(ELT_ == 2 || (ELT_ == 4 && KCB_ != 16 && !ADAM_ && BM_ == 128), "tf32: swizzled operands, plain epilogues");
+  static_assert(ELT_ == 2 || !B_MN_ || B_BW_ == 32, "tf32 MN-major B: 128-byte rows only (32-byte-atom swizzle)");
   // BM = 256: the CTA owns TWO 128-row accumulators (TMEM columns [0,BN) and [BN,2BN)) that share every B stage:
   // operand traffic per FLOP drops from (128+BN) to (256+BN)/2 rows per k-block -- the 5x5 layers are bound by
   // L2->SM operand bandwidth (conv2d_1: 819 MB per launch at ~13 TB/s), not by the tensor pipe.  K-major A only.
@@ -90,17 +100,17 @@ struct Cfg {
   static_assert(BM_ == 128 || (BM_ == 256 && KCB_ != 16 && !ADAM_), "BM = 256: swizzled A, no Adam epilogue");
   static constexpr bool ADAM = ADAM_;                     // compile the EPI_ADAM epilogue (24 float4 loads in flight:
                                                           // 168 registers) only into the kernels that use it
-  static constexpr int B_BW = B_BW_;                     // MN-major B: elements per block (64/32/16)
-  static constexpr int B_BLK_BYTES = 64 * B_BW_ * 2;     // 64 K-rows x BW elements
+  static constexpr int B_BW = B_BW_;                     // MN-major B: elements per block (row = B_BW * ELT = 128/64/32 bytes)
+  static constexpr int B_BLK_BYTES = KROWS * B_BW_ * ELT_;   // KROWS K-rows x BW elements
   static constexpr int B_NBLK = BN_ / B_BW_;
   static constexpr int BM = BM_;
   static constexpr int BN = BN_;
   static constexpr int KCB = KCB_;                       // K-major: bytes of K per row per stage
   static constexpr bool A_MN = A_MN_, B_MN = B_MN_;
   static constexpr bool CHUNKED = (KCB_ == 16);           // 8 chunks of 16 B per stage, no swizzle
-  static constexpr int KELEMS = (A_MN_ || B_MN_ || CHUNKED) ? 64 : KCB_ / 2;   // K elements per stage
-  static constexpr int A_SUB_BYTES = A_MN_ ? 2 * 8192 : 128 * KCB_;      // one 128-row sub-tile
-  static constexpr int A_BYTES = A_MN_ ? MT * 2 * 8192 : CHUNKED ? 8 * BM * 16 : BM * KCB_;
+  static constexpr int KELEMS = (A_MN_ || B_MN_) ? KROWS : CHUNKED ? 64 : KCB_ / ELT_;   // K elements per stage
+  static constexpr int A_SUB_BYTES = A_MN_ ? A_MN_BLOCKS * A_MN_BLK_BYTES : 128 * KCB_;  // one 128-row sub-tile (16 KB)
+  static constexpr int A_BYTES = A_MN_ ? MT * A_SUB_BYTES : CHUNKED ? 8 * BM * 16 : BM * KCB_;
   static constexpr int B_BYTES = B_MN_ ? B_NBLK * B_BLK_BYTES : CHUNKED ? 8 * BN_ * 16 : BN_ * KCB_;
   static_assert(!CHUNKED || (!A_MN_ && !B_MN_), "chunked mode is K-major only");
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -113,7 +123,7 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(!(A_MN_ || B_MN_) || KCB_ == 128, "MN-major operands use 128-byte rows");
   static_assert(!B_MN_ || BN_ % B_BW_ == 0, "MN-major B needs BN % BW == 0");
-  static_assert(B_BW_ == 64 || B_BW_ == 32 || B_BW_ == 16, "MN-major block width");
+  static_assert(B_BW_ * ELT_ == 128 || B_BW_ * ELT_ == 64 || B_BW_ * ELT_ == 32, "MN-major block width: 128/64/32-byte rows");
   static_assert(BN_ % 16 == 0 && BN_ >= 16 && BN_ <= 256, "UMMA N");
 };
 
@@ -216,12 +226,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                       (uint16_t)s, (uint16_t)r);
           }
         } else {
-          // MN-major A: global [K rows][M cols]; two 64-column boxes of 64 K-rows
-          ptx::tma_load_2d(sA, &tmA, &full_bar[stage], m0, kb * 64);
-          ptx::tma_load_2d(sA + 8192, &tmA, &full_bar[stage], m0 + 64, kb * 64);
+          // MN-major A: global [K rows][M cols]; 128-byte-wide boxes of KROWS K-rows (2 per 128 rows for bf16, 4 for tf32)
+#pragma unroll
+          for (int b = 0; b < C::A_MN_BLOCKS; ++b)
+            ptx::tma_load_2d(sA + b * C::A_MN_BLK_BYTES, &tmA, &full_bar[stage], m0 + b * C::A_MN_BLK_ELEMS, kb * C::KROWS);
           if (sub1) {
-            ptx::tma_load_2d(sA + 16384, &tmA, &full_bar[stage], m0 + 128, kb * 64);
-            ptx::tma_load_2d(sA + 24576, &tmA, &full_bar[stage], m0 + 192, kb * 64);
+#pragma unroll
+            for (int b = 0; b < C::A_MN_BLOCKS; ++b)
+              ptx::tma_load_2d(sA + C::A_SUB_BYTES + b * C::A_MN_BLK_BYTES, &tmA, &full_bar[stage],
+                               m0 + 128 + b * C::A_MN_BLK_ELEMS, kb * C::KROWS);
           }
         }
         // ---- B
@@ -232,10 +245,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         } else if (!p.b_im2col) {
 #pragma unroll
           for (int j = 0; j < C::B_NBLK; ++j)
-            ptx::tma_load_2d(sB + j * C::B_BLK_BYTES, &tmB, &full_bar[stage], n0 + j * C::B_BW, kb * 64);
+            ptx::tma_load_2d(sB + j * C::B_BLK_BYTES, &tmB, &full_bar[stage], n0 + j * C::B_BW, kb * C::KROWS);
         } else {
-          // 64 consecutive output pixels starting at kb*64 -> base coordinates in input space
-          const int mk = kb * 64;
+          // KROWS consecutive output pixels starting at kb*KROWS -> base coordinates in input space
+          const int mk = kb * C::KROWS;
           const int ni = mk / p.PQ;
           const int rem = mk - ni * p.PQ;
           const int pp = rem / p.Q, qq = rem - pp * p.Q;
@@ -255,7 +268,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, C::BN, C::A_MN ? 1 : 0, C::B_MN ? 1 : 0);
+      constexpr uint32_t idesc = C::ELT == 4 ? ptx::make_idesc_tf32(128, C::BN, C::A_MN ? 1 : 0, C::B_MN ? 1 : 0)
+                                             : ptx::make_idesc_bf16(128, C::BN, C::A_MN ? 1 : 0, C::B_MN ? 1 : 0);
       constexpr uint32_t k_layout =
           C::KCB == 128 ? ptx::LAYOUT_SW128 : C::KCB == 64 ? ptx::LAYOUT_SW64 : ptx::LAYOUT_SW32;
       for (int i = 0; i < nkb; ++i) {
@@ -267,26 +281,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const uint32_t sB = sA + C::A_BYTES;
         // K-major : SBO = 8 rows * KCB bytes, LBO unused (1) ; K step = 32 B inside the swizzled row
         // MN-major: SBO = 1024 (next 8 K-rows), LBO = 8192 (next 64 MN elements) ; K step = 16 rows = 2048 B
-        const uint64_t a_desc = C::A_MN      ? ptx::make_smem_desc(sA, 8192, 1024, ptx::LAYOUT_SW128)
+        // MN-major tf32: the hardware transposes 32-byte units, so the canonical layout is the 128-byte swizzle with
+        // 32-byte atomicity (TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; descriptor layout 1): swizzle atoms of 4 K-rows
+        // (SBO = 512 bytes) instead of 8 (SBO = 1024)
+        constexpr uint32_t mn_layout = C::ELT == 4 ? ptx::LAYOUT_SW128_B32 : ptx::LAYOUT_SW128;
+        constexpr uint32_t mn_sbo = C::ELT == 4 ? 512 : 1024;
+        const uint64_t a_desc = C::A_MN      ? ptx::make_smem_desc(sA, C::A_MN_BLK_BYTES, mn_sbo, mn_layout)
                                 : C::CHUNKED ? ptx::make_smem_desc(sA, C::BM * 16, 128, ptx::LAYOUT_NONE)
                                              : ptx::make_smem_desc(sA, 16, 8 * C::KCB, k_layout);
         // MN-major B with block width BW: row pitch BW*2 bytes, 8-row atom = 16*BW bytes (SBO),
         // next block of BW columns at 64 rows * BW*2 bytes (LBO), swizzle = row pitch
-        constexpr uint32_t b_mn_layout =
-            C::B_BW == 64 ? ptx::LAYOUT_SW128 : C::B_BW == 32 ? ptx::LAYOUT_SW64 : ptx::LAYOUT_SW32;
-        const uint64_t b_desc = C::B_MN      ? ptx::make_smem_desc(sB, C::B_BLK_BYTES, 16 * C::B_BW, b_mn_layout)
+        constexpr uint32_t b_mn_layout = C::ELT == 4 ? ptx::LAYOUT_SW128_B32
+                                         : C::B_BW * C::ELT == 128 ? ptx::LAYOUT_SW128
+                                         : C::B_BW * C::ELT == 64 ? ptx::LAYOUT_SW64 : ptx::LAYOUT_SW32;
+        constexpr uint32_t b_mn_sbo = C::ELT == 4 ? 512 : 8 * C::B_BW * C::ELT;
+        const uint64_t b_desc = C::B_MN      ? ptx::make_smem_desc(sB, C::B_BLK_BYTES, b_mn_sbo, b_mn_layout)
                                 : C::CHUNKED ? ptx::make_smem_desc(sB, C::BN * 16, 128, ptx::LAYOUT_NONE)
                                              : ptx::make_smem_desc(sB, 16, 8 * C::KCB, k_layout);
-        constexpr uint32_t a_step = C::A_MN ? (2048 >> 4) : C::CHUNKED ? ((2 * C::BM * 16) >> 4) : (32 >> 4);
+        // one UMMA covers 32 bytes of K: 16 bf16 / 8 tf32 elements.  K-major: 32 bytes along the swizzled row;
+        // MN-major: 32 / ELT K-rows of 128 (A) or B_BW * ELT (B) bytes
+        constexpr int KSTEP = 32 / C::ELT;
+        constexpr uint32_t a_step = C::A_MN ? ((KSTEP * 128) >> 4) : C::CHUNKED ? ((2 * C::BM * 16) >> 4) : (32 >> 4);
         constexpr uint32_t b_step =
-            C::B_MN ? ((16 * C::B_BW * 2) >> 4) : C::CHUNKED ? ((2 * C::BN * 16) >> 4) : (32 >> 4);
+            C::B_MN ? ((KSTEP * C::B_BW * C::ELT) >> 4) : C::CHUNKED ? ((2 * C::BN * 16) >> 4) : (32 >> 4);
 #pragma unroll
-        for (int k = 0; k < C::KELEMS / 16; ++k) {
-          ptx::umma_bf16(tmem_base, a_desc + (uint64_t)(k * a_step), b_desc + (uint64_t)(k * b_step), idesc,
-                         (uint32_t)((i | k) != 0));
-          if constexpr (C::MT == 2)              // second accumulator: next 128 rows of A, same B stage
-            ptx::umma_bf16(tmem_base + (uint32_t)C::BN, a_desc + (uint64_t)((C::A_SUB_BYTES >> 4) + k * a_step),
-                           b_desc + (uint64_t)(k * b_step), idesc, (uint32_t)((i | k) != 0));
+        for (int k = 0; k < C::KELEMS / KSTEP; ++k) {
+          if constexpr (C::ELT == 4) {
+            ptx::umma_tf32(tmem_base, a_desc + (uint64_t)(k * a_step), b_desc + (uint64_t)(k * b_step), idesc,
+                           (uint32_t)((i | k) != 0));
+          } else {
+            ptx::umma_bf16(tmem_base, a_desc + (uint64_t)(k * a_step), b_desc + (uint64_t)(k * b_step), idesc,
+                           (uint32_t)((i | k) != 0));
+            if constexpr (C::MT == 2)            // second accumulator: next 128 rows of A, same B stage
+              ptx::umma_bf16(tmem_base + (uint32_t)C::BN, a_desc + (uint64_t)((C::A_SUB_BYTES >> 4) + k * a_step),
+                             b_desc + (uint64_t)(k * b_step), idesc, (uint32_t)((i | k) != 0));
+          }
         }
         ptx::umma_commit(&empty_bar[stage]);       // frees the smem stage when these MMAs retire
       }

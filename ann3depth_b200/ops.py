@@ -396,6 +396,13 @@ class Context:
                                              splits, variant, _stream()), "debug_tc_gemm")
         return D
 
+    def debug_tc_gemm_tf32(self, A, B, M, N, K, bn, kcb=128, a_mn=False, b_mn=False, splits=1):
+        """f32 operands consumed as TF32 (tcgen05.mma kind::tf32): D[M,N] = A . B^T"""
+        D = torch.empty(M, N, dtype=torch.float32, device=A.device)
+        L.check(self.lib.a3d_debug_tc_gemm_tf32(self.h, _ptr(A), _ptr(B), _ptr(D), M, N, K, bn, kcb, int(a_mn), int(b_mn),
+                                                splits, _stream()), "debug_tc_gemm_tf32")
+        return D
+
     # ------------------------------------------------------------------ DCNF
     def pairwise_dense(self, sims, w2, b1, out=None):
         n = sims.numel() // 2

@@ -108,6 +108,38 @@ def torch_conv_ref(x_nhwc, w_ohwi, bias, stride, pad_t, pad_l, P, Q, relu):
 
 # (name, H, W, C, K, R, S, stride, padding) -- the MSDN layers (src/models.py:211-251), channel
 # counts as stored by the B200 path, plus DCNF-style VALID layers (src/models.py:64-72)
+def tf32_round(t):
+    """round-to-nearest-even to 10 explicit mantissa bits (what a TFLOAT32 tensor map delivers to shared memory)"""
+    i = t.contiguous().view(torch.int32)
+    r = (i + 0x0FFF + ((i >> 13) & 1)) & ~0x1FFF
+    return r.view(torch.float32)
+
+
+@pytest.mark.parametrize("a_mn,b_mn,bn,kcb", [(False, False, 128, 128), (False, False, 64, 64), (False, False, 64, 32),
+                                               (False, False, 256, 128), (False, False, 16, 128),
+                                               (True, True, 128, 128), (True, True, 64, 128), (True, False, 32, 128),
+                                               (True, False, 128, 128), (False, True, 128, 128), (False, True, 256, 128)])
+@pytest.mark.parametrize("splits", [1, 3])
+def test_tc_gemm_tf32(ctx, a_mn, b_mn, bn, kcb, splits):
+    """tcgen05.mma kind::tf32 with f32 operands in shared memory, K-major and MN-major, against an f64 product of the
+    TF32-rounded operands (exact up to f32 accumulation order) and within 1e-3 of the unrounded f32 product."""
+    M, N, K = 128 * 3 + 40, 2 * bn - 8, 32 * 9
+    g = torch.Generator().manual_seed(5)
+    A = torch.randn(M, K, generator=g).to(DEV)
+    B = torch.randn(N, K, generator=g).to(DEV)
+    Ad = A.t().contiguous() if a_mn else A
+    Bd = B.t().contiguous() if b_mn else B
+    if a_mn and M % 4:                                   # MN-major row pitch must be 16-byte aligned
+        pytest.skip("unaligned")
+    D = ctx.debug_tc_gemm_tf32(Ad, Bd, M, N, K, bn, kcb, a_mn=a_mn, b_mn=b_mn, splits=splits)
+    ref_r = (tf32_round(A).double() @ tf32_round(B).double().t())
+    ref = A.double() @ B.double().t()
+    err_r = float((D.double() - ref_r).abs().max() / ref_r.abs().max())
+    err = float((D.double() - ref).abs().max() / ref.abs().max())
+    print("tf32 gemm: vs rounded operands", err_r, "vs exact", err)
+    assert err_r < 2e-6 and err < 2e-3
+
+
 LAYERS = [
     ("conv2d_1", 27, 37, 96, 256, 5, 5, 1, "same"),
     ("conv2d_2", 13, 18, 256, 384, 3, 3, 1, "same"),
