@@ -54,6 +54,25 @@ SIGNATURES = {
     "a3d_dense_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _i, _vp, _i, _i, _i, _u, _i, _vp]),
     "a3d_dense_dgrad": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "a3d_stamp": (_i, [_vp, _vp, _vp]),
+    "a3d_conv2d_ws_bytes_tf32": (_sz, [_vp, C.POINTER(ConvDesc), _i]),
+    "a3d_conv2d_fwd_tf32": (_i, [_vp, C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _u, _vp, _sz, _vp]),
+    "a3d_conv2d_dgrad_tf32": (_i, [_vp, C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "a3d_conv2d_wgrad_tf32": (_i, [_vp, C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp]),
+    "a3d_dense_fwd_tf32": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _vp, _i, _i, _i, _u, _vp]),
+    "a3d_dense_dgrad_tf32": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _f, _u, _vp]),
+    "a3d_dense_wgrad_tf32": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),
+    "a3d_resize_bilinear_tf1_s2d_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp]),
+    "a3d_maxpool2x2_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
+    "a3d_maxpool2x2_idx_bwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "a3d_act_bwd_f32": (_i, [_vp, _vp, _i, _vp, _vp, _f, _vp, _sz, _i, _u, _vp]),
+    "a3d_scatter_channel_f32": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp]),
+    "a3d_pool4_reduce_f32": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _sz, _u, _vp]),
+    "a3d_pool4_bwd_f32": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _sz, _vp]),
+    "a3d_bias_grad_f32": (_i, [_vp, _vp, _sz, _i, _i, _vp, _vp]),
+    "a3d_scatter_f32": (_i, [_vp, _vp, _vp, _i, _sz, _vp, _vp]),
+    "a3d_conv_k1_fwd_f32": (_i, [_vp, C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _u, _vp]),
+    "a3d_conv_k1_dgrad_f32": (_i, [_vp, C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp]),
+    "a3d_conv_k1_wgrad_f32": (_i, [_vp, C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp]),
     "a3d_allgather_multi": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "a3d_dense_dgrad_act": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _f, _u, _vp]),
     "a3d_dense_wgrad": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp]),

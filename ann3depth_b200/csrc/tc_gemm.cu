@@ -1109,6 +1109,213 @@ extern "C" int a3d_debug_tc_gemm_v(a3d_ctx* ctx, const uint16_t* A, const uint16
   return A3D_ENOTSUP;
 }
 
+// =====================================================================================================================
+// TF32 precision mode: the same implicit-GEMM formulations with float32 tensors in HBM / shared memory and
+// tcgen05.mma kind::tf32 (10-bit mantissa inputs, f32 accumulation) -- the reference's arithmetic is float32
+// (src/models.py:211-251); BASELINE.json's north star asks for 1e-4 agreement in this mode.  One tile configuration per
+// shape class and closed-form split-K (no autotuning: the mode is about precision; its step time is reported, not tuned).
+// =====================================================================================================================
+namespace {
+template <int BN, bool AM, bool BM_, int MS = A3D_MIN_STAGES>
+using CfgT = tc::Cfg<BN, 128, AM, BM_, 32, MS, false, 128, 4>;
+
+__global__ void act_bwd_cast_f32_kernel(const float* __restrict__ acc, const float* __restrict__ y,
+                                        const uint8_t* __restrict__ mask, float scale, float* __restrict__ dx, size_t n,
+                                        unsigned flags) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float g = acc[i];
+    if (mask) g = mask[i] ? g * scale : 0.f;
+    if (y) {
+      const float yv = y[i];
+      if (flags & A3D_EPI_RELU) g = yv > 0.f ? g : 0.f;
+      if (flags & A3D_EPI_SIGMOID) g = g * yv * (1.f - yv);
+    }
+    dx[i] = g;
+  }
+}
+}  // namespace
+
+int a3d_tc_conv_fwd_tf32(a3d_ctx* ctx, const a3d_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
+                         unsigned flags, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (d->C % 32 || d->stride_h > 8 || d->stride_w > 8 || d->R > 256 || d->S > 256) {
+    a3d_set_error("tf32 conv fwd: needs C %% 32 == 0 (C=%d)", d->C);
+    return A3D_ENOTSUP;
+  }
+  const int cblocks = d->C / 32;
+  const int num_kb = d->R * d->S * cblocks;
+  const long long M = (long long)d->N * d->P * d->Q;
+  const long long J = (long long)d->R * d->S * d->C;
+  const int bn = d->K <= 16 ? 16 : d->K <= 64 ? 64 : d->K <= 128 ? 128 : (d->K % 256 == 0 ? 256 : 128);
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_im2col(ctx, &tmA, x, d->N, d->H, d->W, d->C, -d->pad_t, -d->pad_l, d->P, d->Q, d->stride_h, d->stride_w,
+                            32, 128, 4);
+  if (rc) return rc;
+  rc = make_tmap_2d(ctx, &tmB, w, d->K, J, J, 32, bn, 4);
+  if (rc) return rc;
+  tc::Params p{};
+  p.M = (int)M; p.N = d->K; p.num_kb = num_kb; p.a_mode = tc::A_IM2COL;
+  p.PQ = d->P * d->Q; p.Q = d->Q; p.sh = d->stride_h; p.sw = d->stride_w; p.lower_h = -d->pad_t; p.lower_w = -d->pad_l;
+  p.S = d->S; p.cblocks = cblocks;
+  const bool can_split = ws && ws_bytes >= (size_t)M * d->K * sizeof(float);
+  int splits = can_split ? pick_splits(ctx, ceil_div(M, 128) * ceil_div(d->K, bn), num_kb, 8) : 1;
+  p.kb_per_split = ceil_div(num_kb, splits);
+  splits = ceil_div(num_kb, p.kb_per_split);
+  if (splits == 1) {
+    p.epi = tc::EPI_ROW_F32; p.out = y; p.ldo = d->ldy; p.bias = bias; p.flags = flags; p.atomic = 0;
+  } else {
+    A3D_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)M * d->K * sizeof(float), st));
+    p.epi = tc::EPI_ROW_F32; p.out = ws; p.ldo = d->K; p.bias = nullptr; p.flags = 0; p.atomic = 1;
+  }
+  rc = bn == 16 ? launch_cfg<CfgT<16, false, false>>(ctx, tmA, tmB, p, splits, st)
+       : bn == 64 ? launch_cfg<CfgT<64, false, false>>(ctx, tmA, tmB, p, splits, st)
+       : bn == 128 ? launch_cfg<CfgT<128, false, false>>(ctx, tmA, tmB, p, splits, st)
+                   : launch_cfg<CfgT<256, false, false>>(ctx, tmA, tmB, p, splits, st);
+  if (rc || splits == 1) return rc;
+  return finish(ctx, reinterpret_cast<const float*>(ws), bias, nullptr, 0.f, y, 1, (size_t)M, d->K, d->ldy, flags, st);
+}
+
+int a3d_tc_conv_wgrad_tf32(a3d_ctx* ctx, const a3d_conv_desc* d, const float* x, const float* dy, float* dw,
+                           cudaStream_t st) {
+  if (d->C % 32 || d->ldy % 4 || d->stride_h > 8 || d->stride_w > 8) {
+    a3d_set_error("tf32 conv wgrad: needs C %% 32 == 0 and a 16-byte aligned dY pitch (C=%d ldy=%d)", d->C, d->ldy);
+    return A3D_ENOTSUP;
+  }
+  const int cblocks = d->C / 32, RS = d->R * d->S, total_blocks = RS * cblocks;
+  const long long Mpix = (long long)d->N * d->P * d->Q;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d(ctx, &tmA, dy, Mpix, d->K, d->ldy, 32, 32, 4, true);
+  if (rc) return rc;
+  rc = make_tmap_im2col(ctx, &tmB, x, d->N, d->H, d->W, d->C, -d->pad_t, -d->pad_l, d->P, d->Q, d->stride_h, d->stride_w,
+                        32, 32, 4, true);
+  if (rc) return rc;
+  tc::Params p{};
+  p.M = d->K; p.N = RS * d->C; p.num_kb = ceil_div(Mpix, 32);
+  p.a_mode = tc::A_TILED; p.b_im2col = 1; p.RS = RS;
+  p.PQ = d->P * d->Q; p.Q = d->Q; p.sh = d->stride_h; p.sw = d->stride_w; p.lower_h = -d->pad_t; p.lower_w = -d->pad_l;
+  p.S = d->S; p.cblocks = cblocks;
+  p.epi = tc::EPI_ROW_F32; p.out = dw; p.ldo = (long long)RS * d->C;
+  int nblk = 8, best_pad = 1 << 30;
+  for (int nb = 8; nb >= 1; nb /= 2) {                      // widest tile with the least padding
+    const int padded = ceil_div(total_blocks, nb) * nb;
+    if (padded < best_pad) { best_pad = padded; nblk = nb; }
+  }
+  const int tiles = ceil_div(d->K, 128) * ceil_div(total_blocks, nblk);
+  int splits = pick_splits(ctx, tiles, p.num_kb, 8);
+  p.kb_per_split = ceil_div(p.num_kb, splits);
+  splits = ceil_div(p.num_kb, p.kb_per_split);
+  p.atomic = splits > 1;
+  if (splits > 1) A3D_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)d->K * RS * d->C * sizeof(float), st));
+  if (nblk == 8) return launch_cfg<CfgT<256, true, true>>(ctx, tmA, tmB, p, splits, st);
+  if (nblk == 4) return launch_cfg<CfgT<128, true, true>>(ctx, tmA, tmB, p, splits, st);
+  if (nblk == 2) return launch_cfg<CfgT<64, true, true>>(ctx, tmA, tmB, p, splits, st);
+  return launch_cfg<CfgT<32, true, true>>(ctx, tmA, tmB, p, splits, st);
+}
+
+// strided dgrad, GEMM half: col[m][(tap,ci)] = sum_co dY[m][co] * W[co][(tap,ci)]
+int a3d_tc_dgrad_cols_tf32(a3d_ctx* ctx, const a3d_conv_desc* d, const float* dy, const float* w, float* col, cudaStream_t st) {
+  const long long Mpix = (long long)d->N * d->P * d->Q;
+  const int J = d->R * d->S * d->C;
+  if (d->K % 32 || J % 64 || d->ldy % 4) {
+    a3d_set_error("tf32 dgrad cols: needs K %% 32 == 0 and R*S*C %% 64 == 0");
+    return A3D_ENOTSUP;
+  }
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d(ctx, &tmA, dy, Mpix, d->K, d->ldy, 32, 128, 4);
+  if (rc) return rc;
+  rc = make_tmap_2d(ctx, &tmB, w, d->K, J, J, 32, 32, 4, true);
+  if (rc) return rc;
+  tc::Params p{};
+  p.M = (int)Mpix; p.N = J; p.num_kb = d->K / 32; p.kb_per_split = p.num_kb; p.a_mode = tc::A_TILED;
+  p.epi = tc::EPI_ROW_F32; p.out = col; p.ldo = J; p.atomic = 0;
+  if (J % 256 == 0) return launch_cfg<CfgT<256, false, true>>(ctx, tmA, tmB, p, 1, st);
+  if (J % 128 == 0) return launch_cfg<CfgT<128, false, true>>(ctx, tmA, tmB, p, 1, st);
+  return launch_cfg<CfgT<64, false, true>>(ctx, tmA, tmB, p, 1, st);
+}
+
+// dense layers.  acc_ws f32 [M][N] (fwd) / [M][K] (dgrad) receives the split-K partial sums.
+int a3d_tc_dense_fwd_tf32(a3d_ctx* ctx, const float* x, int ldx, const float* w, const float* bias, const uint8_t* mask,
+                          float drop_rate, float* y, float* acc_ws, int M, int N, int K, unsigned flags, cudaStream_t st) {
+  if (K % 32 || ldx % 4 || M > 256 || !acc_ws) {
+    a3d_set_error("tf32 dense fwd: needs K %% 32 == 0, batch <= 256 and an accumulation workspace (K=%d M=%d)", K, M);
+    return A3D_ENOTSUP;
+  }
+  const int bn = M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d(ctx, &tmA, w, N, K, K, 32, 128, 4);
+  if (rc) return rc;
+  rc = make_tmap_2d(ctx, &tmB, x, M, K, ldx, 32, bn, 4);
+  if (rc) return rc;
+  tc::Params p{};
+  p.M = N; p.N = M; p.num_kb = K / 32; p.a_mode = tc::A_TILED;
+  const int tiles = ceil_div(N, 128);
+  int splits = pick_splits(ctx, tiles, p.num_kb, 8);
+  if (splits * tiles < 2 * ctx->sm_count && p.num_kb / (splits * 2) >= 8) splits *= 2;
+  p.kb_per_split = ceil_div(p.num_kb, splits);
+  splits = ceil_div(p.num_kb, p.kb_per_split);
+  p.epi = tc::EPI_COL_F32; p.out = acc_ws; p.ldo = N; p.atomic = 1;
+  A3D_CHECK_CUDA(cudaMemsetAsync(acc_ws, 0, (size_t)M * N * sizeof(float), st));
+  rc = bn == 32 ? launch_cfg<CfgT<32, false, false>>(ctx, tmA, tmB, p, splits, st)
+       : bn == 64 ? launch_cfg<CfgT<64, false, false>>(ctx, tmA, tmB, p, splits, st)
+       : bn == 128 ? launch_cfg<CfgT<128, false, false>>(ctx, tmA, tmB, p, splits, st)
+                   : launch_cfg<CfgT<256, false, false>>(ctx, tmA, tmB, p, splits, st);
+  if (rc) return rc;
+  return finish(ctx, acc_ws, bias, mask, drop_rate, y, 1, (size_t)M, N, N, flags, st);
+}
+
+// dx[b][k] = act'(y_act) * mask/(1-rate) * sum_n dy[b][n] w[n][k]   (y_act / keep_mask nullable)
+int a3d_tc_dense_dgrad_tf32(a3d_ctx* ctx, const float* dy, int lddy, const float* w, float* dx, float* acc_ws, int M, int N,
+                            int K, const float* y_act, const uint8_t* keep_mask, float drop_rate, unsigned flags,
+                            cudaStream_t st) {
+  if (K % 4 || lddy % 4 || M > 128 || !acc_ws) {
+    a3d_set_error("tf32 dense dgrad: needs K %% 4 == 0, lddy %% 4 == 0, batch <= 128, workspace");
+    return A3D_ENOTSUP;
+  }
+  const int bn = M <= 32 ? 32 : M <= 64 ? 64 : 128;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d(ctx, &tmA, w, N, K, K, 32, 32, 4, true);
+  if (rc) return rc;
+  rc = make_tmap_2d(ctx, &tmB, dy, M, N, lddy, 32, bn, 4);
+  if (rc) return rc;
+  tc::Params p{};
+  p.M = K; p.N = M; p.num_kb = ceil_div(N, 32); p.a_mode = tc::A_TILED;
+  const int tiles = ceil_div(K, 128);
+  int splits = pick_splits(ctx, tiles, p.num_kb, 8);
+  if (splits * tiles < 2 * ctx->sm_count && p.num_kb / (splits * 2) >= 8) splits *= 2;
+  p.kb_per_split = ceil_div(p.num_kb, splits);
+  splits = ceil_div(p.num_kb, p.kb_per_split);
+  p.epi = tc::EPI_COL_F32; p.out = acc_ws; p.ldo = K; p.atomic = 1;
+  A3D_CHECK_CUDA(cudaMemsetAsync(acc_ws, 0, (size_t)M * K * sizeof(float), st));
+  rc = bn == 32 ? launch_cfg<CfgT<32, true, false>>(ctx, tmA, tmB, p, splits, st)
+       : bn == 64 ? launch_cfg<CfgT<64, true, false>>(ctx, tmA, tmB, p, splits, st)
+                  : launch_cfg<CfgT<128, true, false>>(ctx, tmA, tmB, p, splits, st);
+  if (rc) return rc;
+  const size_t total = (size_t)M * K;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > (size_t)ctx->sm_count * 16) blocks = (size_t)ctx->sm_count * 16;
+  act_bwd_cast_f32_kernel<<<(int)blocks, 256, 0, st>>>(acc_ws, y_act, keep_mask, 1.f / (1.f - drop_rate), dx, total, flags);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
+// dw[n][k] = sum_b dy[b][n] x[b][k]; both operands MN-major with the batch as the reduction index
+int a3d_tc_dense_wgrad_tf32(a3d_ctx* ctx, const float* x, int ldx, const float* dy, int lddy, float* dw, int M, int N, int K,
+                            cudaStream_t st) {
+  if (K % 32 || ldx % 4 || lddy % 4) {
+    a3d_set_error("tf32 dense wgrad: needs K %% 32 == 0 and 16-byte aligned row pitches");
+    return A3D_ENOTSUP;
+  }
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d(ctx, &tmA, dy, M, N, lddy, 32, 32, 4, true);
+  if (rc) return rc;
+  rc = make_tmap_2d(ctx, &tmB, x, M, K, ldx, 32, 32, 4, true);
+  if (rc) return rc;
+  tc::Params p{};
+  p.M = N; p.N = K; p.num_kb = ceil_div(M, 32); p.kb_per_split = p.num_kb; p.a_mode = tc::A_TILED;
+  p.epi = tc::EPI_ROW_F32; p.out = dw; p.ldo = K; p.atomic = 0;
+  if (K % 128 == 0) return launch_cfg<CfgT<128, true, true>>(ctx, tmA, tmB, p, 1, st);
+  return launch_cfg<CfgT<32, true, true>>(ctx, tmA, tmB, p, 1, st);
+}
+
 // ---- TF32 (kind::tf32) engine test hook: D[M][N] (f32) = A * B^T with f32 operands read as TF32, every combination of
 // operand majors.  K-major operand: [rows][K]; MN-major operand: [K][rows].  kcb: bytes of K per row and stage (K-major).
 extern "C" int a3d_debug_tc_gemm_tf32(a3d_ctx* ctx, const float* A, const float* B, float* D, int M, int N, int K, int bn,

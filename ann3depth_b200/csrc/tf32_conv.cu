@@ -1,0 +1,132 @@
+// tf32_conv.cu -- public entry points of the TF32 precision mode (float32 tensors, tcgen05.mma kind::tf32): convolution
+// and dense forward / dgrad / wgrad.  Mirrors conv.cu; the reference arithmetic these replace is the same TensorFlow
+// float32 Conv2D / MatMul and their gradients (src/models.py:211-251, 228-232).
+#include "common.cuh"
+
+int a3d_tc_conv_fwd_tf32(a3d_ctx*, const a3d_conv_desc*, const float* x, const float* w, const float* bias, float* y,
+                         unsigned flags, void* ws, size_t ws_bytes, cudaStream_t st);
+int a3d_tc_conv_wgrad_tf32(a3d_ctx*, const a3d_conv_desc*, const float* x, const float* dy, float* dw, cudaStream_t st);
+int a3d_tc_dgrad_cols_tf32(a3d_ctx*, const a3d_conv_desc*, const float* dy, const float* w, float* col, cudaStream_t st);
+int a3d_tc_dense_fwd_tf32(a3d_ctx*, const float* x, int ldx, const float* w, const float* bias, const uint8_t* mask,
+                          float drop_rate, float* y, float* acc_ws, int M, int N, int K, unsigned flags, cudaStream_t st);
+int a3d_tc_dense_dgrad_tf32(a3d_ctx*, const float* dy, int lddy, const float* w, float* dx, float* acc_ws, int M, int N,
+                            int K, const float* y_act, const uint8_t* keep_mask, float drop_rate, unsigned flags,
+                            cudaStream_t st);
+int a3d_tc_dense_wgrad_tf32(a3d_ctx*, const float* x, int ldx, const float* dy, int lddy, float* dw, int M, int N, int K,
+                            cudaStream_t st);
+int a3d_flip_filter_f32(a3d_ctx*, const float* w, float* wd, int K, int RS, int C, cudaStream_t st);
+int a3d_col2im_f32(a3d_ctx*, const float* col, float* dx, const a3d_conv_desc* d, cudaStream_t st);
+
+static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+static size_t filt_bytes_f32(const a3d_conv_desc* d) { return al256((size_t)d->K * d->R * d->S * d->C * 4); }
+static bool s1_dgrad_ok(const a3d_conv_desc* d) {
+  return d->stride_h == 1 && d->stride_w == 1 && d->ldy == d->K && d->K % 32 == 0 && d->C % 4 == 0 &&
+         d->R - 1 - d->pad_t >= 0 && d->S - 1 - d->pad_l >= 0;
+}
+
+static int check_desc_tf32(const a3d_conv_desc* d) {
+  A3D_REQUIRE(d, "conv tf32: null descriptor");
+  A3D_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->C > 0 && d->K > 0 && d->R > 0 && d->S > 0, "conv tf32: bad dims");
+  A3D_REQUIRE(d->stride_h > 0 && d->stride_w > 0 && d->pad_t >= 0 && d->pad_l >= 0 && d->P > 0 && d->Q > 0 && d->ldy >= d->K,
+              "conv tf32: bad stride / pad / output dims");
+  return 0;
+}
+
+// scratch sizes: forward = split-K accumulation [N*P*Q][K] f32; dgrad = flipped filter + the same for the transposed
+// problem (stride 1) or the per-output-pixel columns [N*P*Q][R*S*C] (strided)
+extern "C" size_t a3d_conv2d_ws_bytes_tf32(a3d_ctx* ctx, const a3d_conv_desc* d, int op) {
+  if (!d) return 0;
+  // split-K (and its accumulation buffer) is only chosen when the output has far fewer tiles than the GPU has SMs
+  auto splitk = [&](long long rows, int cols) -> size_t {
+    const long long tiles = ((rows + 127) / 128) * ((cols + 127) / 128);
+    return tiles >= (ctx ? ctx->sm_count : 148) * 3 / 4 ? 0 : al256((size_t)rows * cols * 4);
+  };
+  if (op == A3D_OP_FWD) return splitk((long long)d->N * d->P * d->Q, d->K);
+  if (op == A3D_OP_DGRAD) {
+    if (s1_dgrad_ok(d)) return filt_bytes_f32(d) + splitk((long long)d->N * d->H * d->W, d->C);
+    return al256((size_t)d->N * d->P * d->Q * d->R * d->S * d->C * 4);
+  }
+  return 0;
+}
+
+extern "C" int a3d_conv2d_fwd_tf32(a3d_ctx* ctx, const a3d_conv_desc* d, const float* x, const float* w, const float* bias,
+                                   float* y, unsigned flags, void* ws, size_t ws_bytes, void* stream) {
+  A3D_REQUIRE(ctx && x && w && y, "conv fwd tf32: null argument");
+  int rc = check_desc_tf32(d);
+  if (rc) return rc;
+  return a3d_tc_conv_fwd_tf32(ctx, d, x, w, bias, y, flags, ws, ws_bytes, as_stream(stream));
+}
+
+extern "C" int a3d_conv2d_dgrad_tf32(a3d_ctx* ctx, const a3d_conv_desc* d, const float* dy, const float* w, float* dx,
+                                     const float* relu_src, void* ws, size_t ws_bytes, void* stream) {
+  A3D_REQUIRE(ctx && dy && w && dx && ws, "conv dgrad tf32: null argument");
+  int rc = check_desc_tf32(d);
+  if (rc) return rc;
+  cudaStream_t st = as_stream(stream);
+  A3D_REQUIRE(ws_bytes >= a3d_conv2d_ws_bytes_tf32(ctx, d, A3D_OP_DGRAD), "conv dgrad tf32: workspace too small");
+  if (s1_dgrad_ok(d)) {
+    // dgrad of a stride-1 convolution = forward convolution of dY with the spatially flipped, channel-transposed filter
+    float* wd = reinterpret_cast<float*>(ws);
+    rc = a3d_flip_filter_f32(ctx, w, wd, d->K, d->R * d->S, d->C, st);
+    if (rc) return rc;
+    a3d_conv_desc e = *d;
+    e.H = d->P; e.W = d->Q; e.C = d->K;
+    e.K = d->C; e.P = d->H; e.Q = d->W; e.ldy = d->C;
+    e.pad_t = d->R - 1 - d->pad_t; e.pad_l = d->S - 1 - d->pad_l;
+    e.stride_h = e.stride_w = 1;
+    const size_t filt = filt_bytes_f32(d);
+    rc = a3d_tc_conv_fwd_tf32(ctx, &e, dy, wd, nullptr, dx, 0, reinterpret_cast<uint8_t*>(ws) + filt, ws_bytes - filt, st);
+  } else {
+    float* col = reinterpret_cast<float*>(ws);
+    rc = a3d_tc_dgrad_cols_tf32(ctx, d, dy, w, col, st);
+    if (rc) return rc;
+    rc = a3d_col2im_f32(ctx, col, dx, d, st);
+  }
+  if (rc) return rc;
+  if (relu_src)       // ReluGrad of the producer layer, in place
+    return a3d_act_bwd_f32(ctx, dx, d->C, relu_src, nullptr, 0.f, dx, (size_t)d->N * d->H * d->W, d->C, A3D_EPI_RELU, stream);
+  return 0;
+}
+
+extern "C" int a3d_conv2d_wgrad_tf32(a3d_ctx* ctx, const a3d_conv_desc* d, const float* x, const float* dy, float* dw,
+                                     float* db, void* stream) {
+  A3D_REQUIRE(ctx && x && dy && dw, "conv wgrad tf32: null argument");
+  int rc = check_desc_tf32(d);
+  if (rc) return rc;
+  if (db) {
+    rc = a3d_bias_grad_f32(ctx, dy, (size_t)d->N * d->P * d->Q, d->K, d->ldy, db, stream);
+    if (rc) return rc;
+  }
+  return a3d_tc_conv_wgrad_tf32(ctx, d, x, dy, dw, as_stream(stream));
+}
+
+extern "C" int a3d_dense_fwd_tf32(a3d_ctx* ctx, const float* x, int ldx, const float* w, const float* bias,
+                                  const uint8_t* keep_mask, float drop_rate, float* y, float* acc_ws, int M, int N, int K,
+                                  unsigned flags, void* stream) {
+  A3D_REQUIRE(ctx && x && w && y && acc_ws && M > 0 && N > 0 && K > 0 && ldx >= K, "dense fwd tf32: bad argument");
+  cudaStream_t st = as_stream(stream);
+  for (int m0 = 0; m0 < M; m0 += 256) {          // the batch is the UMMA N dimension (<= 256)
+    const int mc = M - m0 < 256 ? M - m0 : 256;
+    int rc = a3d_tc_dense_fwd_tf32(ctx, x + (size_t)m0 * ldx, ldx, w, bias, keep_mask ? keep_mask + (size_t)m0 * N : nullptr,
+                                   drop_rate, y + (size_t)m0 * N, acc_ws + (size_t)m0 * N, mc, N, K, flags, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+extern "C" int a3d_dense_dgrad_tf32(a3d_ctx* ctx, const float* dy, int lddy, const float* w, float* dx, float* acc_ws, int M,
+                                    int N, int K, const float* y_act, const uint8_t* keep_mask, float drop_rate,
+                                    unsigned flags, void* stream) {
+  A3D_REQUIRE(ctx && dy && w && dx && acc_ws && M > 0 && N > 0 && K > 0 && lddy >= N, "dense dgrad tf32: bad argument");
+  return a3d_tc_dense_dgrad_tf32(ctx, dy, lddy, w, dx, acc_ws, M, N, K, y_act, keep_mask, drop_rate, flags, as_stream(stream));
+}
+
+extern "C" int a3d_dense_wgrad_tf32(a3d_ctx* ctx, const float* x, int ldx, const float* dy, int lddy, float* dw, float* db,
+                                    int M, int N, int K, void* stream) {
+  A3D_REQUIRE(ctx && x && dy && dw && M > 0 && N > 0 && K > 0 && lddy >= N && ldx >= K, "dense wgrad tf32: bad argument");
+  if (db) {
+    int rc = a3d_bias_grad_f32(ctx, dy, (size_t)M, N, lddy, db, stream);
+    if (rc) return rc;
+  }
+  return a3d_tc_dense_wgrad_tf32(ctx, x, ldx, dy, lddy, dw, M, N, K, as_stream(stream));
+}

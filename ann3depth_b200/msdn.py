@@ -43,8 +43,20 @@ class MSDNNet:
 
     def __init__(self, ctx: ops.Context, batch: int, in_hw=(480, 640), depth_hw=(55, 73), train=True,
                  beta2=ADAM_BETA2_REFERENCE, impl=L.IMPL_AUTO, dropout_seed=2, comm=None, grad_dtype=torch.float32,
-                 overlap=True, fuse_dense_adam=True):
+                 overlap=True, fuse_dense_adam=True, dtype="bf16"):
         self.ctx, self.B, self.train, self.beta2, self.impl = ctx, batch, train, beta2, impl
+        # dtype = "bf16" (default): BF16 storage of activations / activation gradients / the weight mirror, tcgen05
+        # kind::f16.  dtype = "tf32": everything stays float32 in memory -- the reference's own storage type
+        # (src/models.py:211-251) -- and the contractions run on tcgen05 kind::tf32 (north star: 1e-4 forward agreement).
+        # The TF32 mode runs the sequential schedule with separate wgrad + TF-Adam kernels (the fused / multi-stream
+        # kernels are BF16-storage kernels); single GPU.
+        if dtype not in ("bf16", "tf32"):
+            raise ValueError("dtype must be 'bf16' or 'tf32'")
+        self.tf32 = dtype == "tf32"
+        if self.tf32:
+            if comm is not None:
+                raise ValueError("dtype='tf32' is a single-GPU precision mode")
+            overlap, fuse_dense_adam = False, False
         self.overlap = overlap                # phase-1 step on several streams (see _enqueue_phase1_overlapped)
         # single GPU: the dense weight gradients (32 FMAs per parameter at batch 32) are recomputed on the CUDA cores
         # inside the HBM-bound TF-Adam pass (a3d_dense_wgrad_adam), so the 67 M-element f32 gradient is never written
@@ -63,7 +75,8 @@ class MSDNNet:
         self.adam_t = {g: 0 for g in ADAM_LR}
         self.dropout_seed = dropout_seed
         B = batch
-        bf, f32 = dict(dtype=torch.bfloat16, device=self.dev), dict(dtype=torch.float32, device=self.dev)
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        bf = f32 if self.tf32 else dict(dtype=torch.bfloat16, device=self.dev)        # the activation storage type
         z = torch.zeros
         # ---- static input buffers (the "placeholders" the driver refills each step)
         self.images = z(B, in_hw[0], in_hw[1], 3, **f32)
@@ -142,7 +155,8 @@ class MSDNNet:
         return t[:s.tf_shape[1]] if s.kind == "dense_kernel" else t
 
     def w(self, name):
-        return self._real_rows(self.arena.wb, name)
+        """The operand copy of a kernel: the bf16 mirror, or (TF32 mode) the float32 master itself."""
+        return self._real_rows(self.arena.w if self.tf32 else self.arena.wb, name)
 
     def bias(self, name):
         return self.arena.view(self.arena.w, name + "/bias")
@@ -212,10 +226,11 @@ class MSDNNet:
         c.conv2d_fwd(self.d_f3, self.f2, self.w("fine/third" + K), self.bias("fine/third"), relu=False,
                      out=self.fine.view(B, 55, 74, 1))
         # losses (src/models.py:288-290); the gradient of the active branch is produced in the same pass
+        gk = "dout" if self.tf32 else "dout_bf16"          # the gradient w.r.t. the prediction, in the storage type
         c.silog_loss(self.coarse, self.tar, LAMBDA_OVER_N, want_grad=False, loss_ps=self.lps_coarse,
-                     loss=self.loss_coarse, dout_bf16=self.g_coarse if self.train else None, dout_ld=4096)
+                     loss=self.loss_coarse, dout_ld=4096, **{gk: self.g_coarse if self.train else None})
         c.silog_loss(self.fine, self.tar, LAMBDA_OVER_N, want_grad=False, loss_ps=self.lps_fine, loss=self.loss_fine,
-                     dout_bf16=self.g_fine if self.train else None)
+                     dout_ld=N_PIX, **{gk: self.g_fine if self.train else None})
 
     # ------------------------------------------------------------------ backward
     def _dense_wgrad_adam(self, layer, x, dy):
@@ -291,7 +306,7 @@ class MSDNNet:
         # fine/first: MaxPoolGrad + ReluGrad on the 4 x 64 GEMM columns, wgrad of the embedded filter, then fold its
         # four copies (and the four bias groups) into the canonical variable
         if self.g_f1big is None:
-            self.g_f1big = torch.zeros(self.B * N_PIX, 256, dtype=torch.bfloat16, device=self.dev)
+            self.g_f1big = torch.zeros(self.B * N_PIX, 256, dtype=self.cat.dtype, device=self.dev)
             self.g_wbig = torch.zeros(256 * 3 * 3 * 64 + 256, dtype=torch.float32, device=self.dev)
         c.pool4_bwd(self.g_cat.view(-1, 64), self.cat.view(-1, 64), self.if1, out=self.g_f1big)
         nk = 256 * 3 * 3 * 64

@@ -116,6 +116,10 @@ class Context:
     def resize_bilinear_tf1_s2d(self, src, OH, OW, s, out):
         """Resize + space-to-depth(s): out bf16 [B, OH/s, OW/s, dstC >= s*s*C]."""
         B, H, W, Cc = src.shape
+        if out.dtype == torch.float32:             # TF32 mode: float32 activations
+            L.check(self.lib.a3d_resize_bilinear_tf1_s2d_f32(self.h, _ptr(src), B, H, W, Cc, _ptr(out), OH, OW, s,
+                                                             out.shape[-1], _stream()), "resize_s2d_f32")
+            return out
         if src.dtype == torch.uint8:               # 8-bit wire format: pixel / 255 folded into the kernel
             L.check(self.lib.a3d_resize_bilinear_tf1_s2d_u8(self.h, _ptr(src), B, H, W, Cc, _ptr(out), OH, OW, s,
                                                             out.shape[-1], _stream()), "resize_s2d_u8")
@@ -127,7 +131,17 @@ class Context:
     def conv2d_pool4_fwd(self, d, x, w, bias, relu=True, out=None, idx=None):
         """conv + bias + ReLU + 2x2 max-pool as one GEMM over the pool-embedded filter (K = 4 x 64)."""
         if out is None:
-            out = torch.empty(d.N, d.P, d.Q, d.ldy, dtype=torch.bfloat16, device=x.device)
+            out = torch.empty(d.N, d.P, d.Q, d.ldy, dtype=x.dtype, device=x.device)
+        if x.dtype == torch.float32:
+            # TF32 mode: the pool-embedded GEMM writes its 4 x 64 columns in float32, a second pass takes the group max
+            rows = d.N * d.P * d.Q
+            acc = self.workspace(("pool4_tf32",), rows * 256 * 4).view(torch.float32)[:rows * 256].view(rows, 256)
+            e = ConvDesc.from_buffer_copy(d)
+            e.ldy = 256
+            self.conv2d_fwd(e, x, w, None, relu=False, out=acc.view(d.N, d.P, d.Q, 256))
+            L.check(self.lib.a3d_pool4_reduce_f32(self.h, _ptr(acc), _ptr(bias), _ptr(out), out.shape[-1], _ptr(idx), rows,
+                                                  L.EPI_RELU if relu else 0, _stream()), "pool4_reduce_f32")
+            return out
         ws = None
         if d.impl == L.IMPL_SIMT:
             ws = self.workspace(("pool4_simt",), d.N * d.P * d.Q * 256 * 4)
@@ -139,7 +153,11 @@ class Context:
     def pool4_bwd(self, dy, y, idx, out=None):
         rows = idx.numel() // 64
         if out is None:
-            out = torch.empty(rows, 256, dtype=torch.bfloat16, device=dy.device)
+            out = torch.empty(rows, 256, dtype=dy.dtype, device=dy.device)
+        if dy.dtype == torch.float32:
+            L.check(self.lib.a3d_pool4_bwd_f32(self.h, _ptr(dy), dy.shape[-1], _ptr(y), y.shape[-1], _ptr(idx), _ptr(out),
+                                               rows, _stream()), "pool4_bwd_f32")
+            return out
         L.check(self.lib.a3d_pool4_bwd(self.h, _ptr(dy), dy.shape[-1], _ptr(y), y.shape[-1], _ptr(idx), _ptr(out), rows,
                                        _stream()), "pool4_bwd")
         return out
@@ -151,6 +169,9 @@ class Context:
 
     def scatter_cast_bf16(self, src, idx, dst):
         G, n = idx.shape
+        if dst.dtype == torch.float32:
+            L.check(self.lib.a3d_scatter_f32(self.h, _ptr(src), _ptr(idx), G, n, _ptr(dst), _stream()), "scatter_f32")
+            return dst
         L.check(self.lib.a3d_scatter_cast_bf16(self.h, _ptr(src), _ptr(idx), G, n, _ptr(dst), _stream()), "scatter_cast")
         return dst
 
@@ -176,6 +197,10 @@ class Context:
         ldy = ldy or (out.shape[-1] if out is not None else Cc)
         if out is None:
             out = torch.empty(N, H // 2, W // 2, ldy, dtype=torch.bfloat16, device=x.device)
+        if out.dtype == torch.float32:
+            L.check(self.lib.a3d_maxpool2x2_f32(self.h, _ptr(x), N, H, W, Cc, _ptr(out), ldy, _ptr(idx), _stream()),
+                    "maxpool_f32_f32")
+            return out
         L.check(self.lib.a3d_maxpool2x2_fwd_f32(self.h, _ptr(x), N, H, W, Cc, _ptr(out), ldy, _ptr(idx), _stream()),
                 "maxpool_f32")
         return out
@@ -184,7 +209,11 @@ class Context:
         N, H, W, Cc = shape
         lddy = lddy or dy.shape[-1]
         if out is None:
-            out = torch.empty(N, H, W, Cc, dtype=torch.bfloat16, device=dy.device)
+            out = torch.empty(N, H, W, Cc, dtype=dy.dtype, device=dy.device)
+        if dy.dtype == torch.float32:
+            L.check(self.lib.a3d_maxpool2x2_idx_bwd_f32(self.h, _ptr(idx), _ptr(dy), lddy, N, H, W, Cc, _ptr(out), _stream()),
+                    "maxpool_idx_bwd_f32")
+            return out
         L.check(self.lib.a3d_maxpool2x2_idx_bwd(self.h, _ptr(idx), _ptr(dy), lddy, N, H, W, Cc, _ptr(out), _stream()),
                 "maxpool_idx_bwd")
         return out
@@ -195,12 +224,21 @@ class Context:
         lddy = lddy or dy.shape[-1]
         if out is None:
             out = torch.empty_like(y)
+        if y.dtype == torch.float32:
+            L.check(self.lib.a3d_act_bwd_f32(self.h, _ptr(dy), lddy, _ptr(y), None, 0.0, _ptr(out), rows, Cc, L.EPI_RELU,
+                                             _stream()), "relu_bwd_f32")
+            return out
         L.check(self.lib.a3d_relu_bwd(self.h, _ptr(y), _ptr(dy), lddy, _ptr(out), rows, Cc, _stream()), "relu_bwd")
         return out
 
     def dense_epilogue_bwd(self, g_post, y, keep_mask, drop_rate, flags, out=None):
         if out is None:
             out = torch.empty_like(g_post)
+        if g_post.dtype == torch.float32:
+            Cc = g_post.shape[-1]
+            L.check(self.lib.a3d_act_bwd_f32(self.h, _ptr(g_post), Cc, _ptr(y), _ptr(keep_mask), drop_rate, _ptr(out),
+                                             g_post.numel() // Cc, Cc, flags, _stream()), "act_bwd_f32")
+            return out
         L.check(self.lib.a3d_dense_epilogue_bwd(self.h, _ptr(g_post), _ptr(y), _ptr(keep_mask), drop_rate, _ptr(out),
                                                 g_post.numel(), flags, _stream()), "dense_epilogue_bwd")
         return out
@@ -251,6 +289,10 @@ class Context:
 
     def scatter_channel_bf16(self, src, dst, ch):
         ld = dst.shape[-1]
+        if dst.dtype == torch.float32:
+            L.check(self.lib.a3d_scatter_channel_f32(self.h, _ptr(src), _ptr(dst), src.numel(), ld, ch, _stream()),
+                    "scatter_channel_f32")
+            return
         L.check(self.lib.a3d_scatter_channel_bf16(self.h, _ptr(src), _ptr(dst), src.numel(), ld, ch, _stream()),
                 "scatter_channel")
 
@@ -267,13 +309,25 @@ class Context:
                 "apply_mask")
 
     # ------------------------------------------------------------------ conv / dense
-    def conv_ws(self, d, op):
-        nbytes = self.lib.a3d_conv2d_ws_bytes(self.h, C.byref(d), op)
-        return self.workspace(("conv", op), nbytes), nbytes
+    def conv_ws(self, d, op, tf32=False):
+        fn = self.lib.a3d_conv2d_ws_bytes_tf32 if tf32 else self.lib.a3d_conv2d_ws_bytes
+        nbytes = fn(self.h, C.byref(d), op)
+        return self.workspace(("conv_tf32" if tf32 else "conv", op), nbytes), nbytes
 
     def conv2d_fwd(self, d, x, w, bias, relu=False, out=None, out_dtype=torch.bfloat16):
         if out is None:
-            out = torch.empty(d.N, d.P, d.Q, d.ldy, dtype=out_dtype, device=x.device)
+            out = torch.empty(d.N, d.P, d.Q, d.ldy, dtype=torch.float32 if x.dtype == torch.float32 else out_dtype,
+                              device=x.device)
+        if x.dtype == torch.float32:               # TF32 mode (tcgen05 kind::tf32); K == 1: exact float32 stencil
+            if d.K == 1:
+                L.check(self.lib.a3d_conv_k1_fwd_f32(self.h, C.byref(d), _ptr(x), _ptr(w), _ptr(bias), _ptr(out),
+                                                     L.EPI_RELU if relu else 0, _stream()), "conv_k1_fwd_f32")
+                return out
+            ws, nb = self.conv_ws(d, L.OP_FWD, tf32=True)
+            L.check(self.lib.a3d_conv2d_fwd_tf32(self.h, C.byref(d), _ptr(x), _ptr(w), _ptr(bias), _ptr(out),
+                                                 L.EPI_RELU if relu else 0, _ptr(ws), ws.numel(), _stream()),
+                    "conv2d_fwd_tf32")
+            return out
         ws, nb = self.conv_ws(d, L.OP_FWD)
         code = L.A3D_BF16 if out.dtype == torch.bfloat16 else L.A3D_F32
         L.check(self.lib.a3d_conv2d_fwd(self.h, C.byref(d), _ptr(x), _ptr(w), _ptr(bias), _ptr(out), code,
@@ -294,7 +348,16 @@ class Context:
         """relu_src: post-ReLU activation that was the layer's input -> fused ReluGrad of the producer.
         wflip: filter prepared by conv2d_dgrad_prepare (w is then unused)."""
         if out is None:
-            out = torch.empty(d.N, d.H, d.W, d.C, dtype=torch.bfloat16, device=dy.device)
+            out = torch.empty(d.N, d.H, d.W, d.C, dtype=dy.dtype, device=dy.device)
+        if dy.dtype == torch.float32:
+            if d.K == 1:
+                L.check(self.lib.a3d_conv_k1_dgrad_f32(self.h, C.byref(d), _ptr(dy), _ptr(w), _ptr(out), _ptr(relu_src),
+                                                       _stream()), "conv_k1_dgrad_f32")
+                return out
+            ws, nb = self.conv_ws(d, L.OP_DGRAD, tf32=True)
+            L.check(self.lib.a3d_conv2d_dgrad_tf32(self.h, C.byref(d), _ptr(dy), _ptr(w), _ptr(out), _ptr(relu_src),
+                                                   _ptr(ws), ws.numel(), _stream()), "conv2d_dgrad_tf32")
+            return out
         ws, nb = self.conv_ws(d, L.OP_DGRAD)
         if wflip is not None:
             L.check(self.lib.a3d_conv2d_dgrad_prepared(self.h, C.byref(d), _ptr(dy), _ptr(wflip), _ptr(out), _ptr(relu_src),
@@ -307,6 +370,14 @@ class Context:
     def conv2d_wgrad(self, d, x, dy, dw=None, db=None):
         if dw is None:
             dw = torch.empty(d.K, d.R, d.S, d.C, dtype=torch.float32, device=x.device)
+        if x.dtype == torch.float32:
+            if d.K == 1:
+                L.check(self.lib.a3d_conv_k1_wgrad_f32(self.h, C.byref(d), _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), _stream()),
+                        "conv_k1_wgrad_f32")
+                return dw, db
+            L.check(self.lib.a3d_conv2d_wgrad_tf32(self.h, C.byref(d), _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), _stream()),
+                    "conv2d_wgrad_tf32")
+            return dw, db
         ws, nb = self.conv_ws(d, L.OP_WGRAD)
         L.check(self.lib.a3d_conv2d_wgrad(self.h, C.byref(d), _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), _ptr(ws),
                                           ws.numel(), _stream()), "conv2d_wgrad")
@@ -318,8 +389,12 @@ class Context:
         N, K = w.shape
         ldx = ldx or x.shape[1]
         if out is None:
-            out = torch.empty(M, N, dtype=out_dtype, device=x.device)
+            out = torch.empty(M, N, dtype=torch.float32 if x.dtype == torch.float32 else out_dtype, device=x.device)
         acc = self.workspace(("dense_acc", M, N), M * N * 4)
+        if x.dtype == torch.float32:
+            L.check(self.lib.a3d_dense_fwd_tf32(self.h, _ptr(x), ldx, _ptr(w), _ptr(bias), _ptr(keep_mask), drop_rate,
+                                                _ptr(out), _ptr(acc), M, N, K, flags, _stream()), "dense_fwd_tf32")
+            return out
         code = L.A3D_BF16 if out.dtype == torch.bfloat16 else L.A3D_F32
         L.check(self.lib.a3d_dense_fwd(self.h, _ptr(x), ldx, _ptr(w), _ptr(bias), _ptr(keep_mask), drop_rate,
                                        _ptr(out), code, _ptr(acc), M, N, K, flags, impl, _stream()), "dense_fwd")
@@ -330,8 +405,12 @@ class Context:
         M, lddy = dy.shape
         N, K = w.shape
         if out is None:
-            out = torch.empty(M, K, dtype=torch.bfloat16, device=dy.device)
+            out = torch.empty(M, K, dtype=dy.dtype, device=dy.device)
         acc = self.workspace(("dense_dacc", M, K), M * K * 4)
+        if dy.dtype == torch.float32:
+            L.check(self.lib.a3d_dense_dgrad_tf32(self.h, _ptr(dy), lddy, _ptr(w), _ptr(out), _ptr(acc), M, N, K, None, None,
+                                                  0.0, 0, _stream()), "dense_dgrad_tf32")
+            return out
         L.check(self.lib.a3d_dense_dgrad(self.h, _ptr(dy), lddy, _ptr(w), _ptr(out), _ptr(acc), M, N, K, impl,
                                          _stream()), "dense_dgrad")
         return out
@@ -341,8 +420,13 @@ class Context:
         M, lddy = dy.shape
         N, K = w.shape
         if out is None:
-            out = torch.empty(M, K, dtype=torch.bfloat16, device=dy.device)
+            out = torch.empty(M, K, dtype=dy.dtype, device=dy.device)
         acc = self.workspace(("dense_dacc", M, K), M * K * 4)
+        if dy.dtype == torch.float32:
+            L.check(self.lib.a3d_dense_dgrad_tf32(self.h, _ptr(dy), lddy, _ptr(w), _ptr(out), _ptr(acc), M, N, K,
+                                                  _ptr(y_act), _ptr(keep_mask), drop_rate, flags, _stream()),
+                    "dense_dgrad_tf32")
+            return out
         L.check(self.lib.a3d_dense_dgrad_act(self.h, _ptr(dy), lddy, _ptr(w), _ptr(out), _ptr(acc), M, N, K, impl,
                                              _ptr(y_act), _ptr(keep_mask), drop_rate, flags, _stream()), "dense_dgrad_act")
         return out
@@ -355,6 +439,10 @@ class Context:
         K = x.shape[1]
         if dw is None:
             dw = torch.empty(N, K, dtype=torch.float32, device=x.device)
+        if x.dtype == torch.float32:
+            L.check(self.lib.a3d_dense_wgrad_tf32(self.h, _ptr(x), ldx, _ptr(dy), lddy, _ptr(dw), _ptr(db), M, N, K,
+                                                  _stream()), "dense_wgrad_tf32")
+            return dw, db
         L.check(self.lib.a3d_dense_wgrad(self.h, _ptr(x), ldx, _ptr(dy), lddy, _ptr(dw), _ptr(db), M, N, K, impl,
                                          _stream()), "dense_wgrad")
         return dw, db
@@ -385,6 +473,9 @@ class Context:
     def bias_grad_bf16(self, dy, C_, db, rows=None, ld=None, group_rows=0, group_stride=0):
         if rows is None:
             rows, ld = dy.shape
+        if dy.dtype == torch.float32:
+            L.check(self.lib.a3d_bias_grad_f32(self.h, _ptr(dy), rows, C_, ld, _ptr(db), _stream()), "bias_grad_f32")
+            return db
         L.check(self.lib.a3d_bias_grad_bf16(self.h, _ptr(dy), rows, C_, ld, _ptr(db), group_rows, group_stride,
                                             _stream()), "bias_grad")
         return db

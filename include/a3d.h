@@ -330,6 +330,50 @@ int a3d_allgather(a3d_ctx*, void* buf, size_t chunk, int dtype, void* stream);
 /* n all-gathers as one NCCL group (one launch): bufs[i] = nranks * chunks[i] elements, gathered in place. */
 int a3d_allgather_multi(a3d_ctx*, void* const* bufs, const size_t* chunks, int n, int dtype, void* stream);
 
+/* ---- TF32 precision mode ------------------------------------------------------------------------------------------
+ * models.msdn(images, depths, dtype="tf32"): every activation / activation gradient is a float32 tensor (the reference's
+ * own storage type), the contractions run on tcgen05.mma kind::tf32 with float32 accumulation.  Same operations, layouts
+ * (NHWC, OHWI filters, [out][in] dense kernels) and TF call sites as the bf16 entry points above; C must be a multiple of
+ * 32 for the convolutions (128-byte pixels), K of 32 for the dense layers.  Weights are the float32 master copy itself. */
+size_t a3d_conv2d_ws_bytes_tf32(a3d_ctx*, const a3d_conv_desc*, int op);
+int a3d_conv2d_fwd_tf32(a3d_ctx*, const a3d_conv_desc*, const float* x, const float* w, const float* bias, float* y,
+                        unsigned flags, void* ws, size_t ws_bytes, void* stream);
+int a3d_conv2d_dgrad_tf32(a3d_ctx*, const a3d_conv_desc*, const float* dy, const float* w, float* dx,
+                          const float* relu_src, void* ws, size_t ws_bytes, void* stream);
+int a3d_conv2d_wgrad_tf32(a3d_ctx*, const a3d_conv_desc*, const float* x, const float* dy, float* dw, float* db,
+                          void* stream);
+int a3d_dense_fwd_tf32(a3d_ctx*, const float* x, int ldx, const float* w, const float* bias, const uint8_t* keep_mask,
+                       float drop_rate, float* y, float* acc_ws, int M, int N, int K, unsigned flags, void* stream);
+/* y_act / keep_mask nullable: the producer layer's activation gradient folded into the finishing pass */
+int a3d_dense_dgrad_tf32(a3d_ctx*, const float* dy, int lddy, const float* w, float* dx, float* acc_ws, int M, int N,
+                         int K, const float* y_act, const uint8_t* keep_mask, float drop_rate, unsigned flags,
+                         void* stream);
+int a3d_dense_wgrad_tf32(a3d_ctx*, const float* x, int ldx, const float* dy, int lddy, float* dw, float* db, int M, int N,
+                         int K, void* stream);
+/* float32 counterparts of the memory-bound kernels (f32_ops.cu) */
+int a3d_resize_bilinear_tf1_s2d_f32(a3d_ctx*, const float* src, int B, int H, int W, int C, float* dst, int OH, int OW,
+                                    int s, int dstC, void* stream);
+int a3d_maxpool2x2_f32(a3d_ctx*, const float* x, int N, int H, int W, int C, float* y, int ldy, uint8_t* idx, void* stream);
+int a3d_maxpool2x2_idx_bwd_f32(a3d_ctx*, const uint8_t* idx, const float* dy, int lddy, int N, int H, int W, int C,
+                               float* dx, void* stream);
+int a3d_act_bwd_f32(a3d_ctx*, const float* g_post, int ldg, const float* y, const uint8_t* keep_mask, float drop_rate,
+                    float* g_pre, size_t rows, int C, unsigned flags, void* stream);
+int a3d_scatter_channel_f32(a3d_ctx*, const float* src, float* dst, size_t rows, int ld, int ch, void* stream);
+int a3d_pool4_reduce_f32(a3d_ctx*, const float* acc, const float* bias, float* y, int ldy, uint8_t* idx, size_t rows,
+                         unsigned flags, void* stream);
+int a3d_pool4_bwd_f32(a3d_ctx*, const float* dy, int lddy, const float* y, int ldy, const uint8_t* idx, float* dybig,
+                      size_t rows, void* stream);
+int a3d_bias_grad_f32(a3d_ctx*, const float* dy, size_t rows, int C, int ld, float* db, void* stream);
+int a3d_scatter_f32(a3d_ctx*, const float* src, const int* idx, int G, size_t n, float* dst, void* stream);
+/* single-filter convolution (K == 1: MSDN fine/third, src/models.py:250) in exact float32: forward, dgrad (+ ReluGrad
+ * of relu_src, nullable), wgrad (+ db, nullable).  dy / y row pitch = ldy floats. */
+int a3d_conv_k1_fwd_f32(a3d_ctx*, const a3d_conv_desc*, const float* x, const float* w, const float* bias, float* y,
+                        unsigned flags, void* stream);
+int a3d_conv_k1_dgrad_f32(a3d_ctx*, const a3d_conv_desc*, const float* dy, const float* w, float* dx,
+                          const float* relu_src, void* stream);
+int a3d_conv_k1_wgrad_f32(a3d_ctx*, const a3d_conv_desc*, const float* x, const float* dy, float* dw, float* db,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif
