@@ -15,86 +15,14 @@ int a3d_tc_dense_fwd(a3d_ctx*, const uint16_t* x, int ldx, const uint16_t* w, co
 struct a3d_actbwd_args { const uint16_t* y; const uint8_t* keep_mask; float drop_rate; unsigned flags; };
 int a3d_tc_dense_dgrad(a3d_ctx*, const uint16_t* dy, int lddy, const uint16_t* w, uint16_t* dx, float* acc_ws, int M,
                        int N, int K, cudaStream_t st, const a3d_actbwd_args* ab = nullptr);
-struct a3d_adam_args { float* w; float* m; float* v; uint16_t* wb; float lr_t, beta1, beta2, eps, grad_scale; const float* lr_t_dev; };
 int a3d_tc_dense_wgrad(a3d_ctx*, const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, int M, int N, int K,
-                       cudaStream_t st, const a3d_adam_args* adam = nullptr);
-
-int a3d_simt_dense_wgrad_adam(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* w, float* m,
-                              float* v, uint16_t* wb, int M, int N, int K, float lr_t, float beta1, float beta2, float eps,
-                              float grad_scale, const float* lr_t_dev, cudaStream_t st);
+                       cudaStream_t st);
 
 int a3d_mma_dense_wgrad_adam(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* w, float* m,
                              float* v, uint16_t* wb, int M, int N, int K, float lr_t, float beta1, float beta2, float eps,
                              float grad_scale, const float* lr_t_dev, cudaStream_t st);
 
-// tc_halo.cu
-struct HaloGeom { int Hp, Wp, Cp, need_copy; };
-size_t a3d_halo_ws_bytes(int N, int H, int W, int C, int ld, int K, int R, int S, int pt, int pl, int P, int Q, int flip);
-int a3d_halo_conv_run(a3d_ctx* ctx, const uint16_t* xp, int N, int Hp, int Wp, int Cp, const uint16_t* wpk, int Kout, int R,
-                      int S, int P, int Q, void* out, int out_f32, int OH, int OW, int oph, int opw, long long ldo,
-                      const float* bias, unsigned flags, const uint16_t* relu_src, cudaStream_t st);
-int a3d_halo_pad_copy(a3d_ctx* ctx, const uint16_t* src, int N, int H, int W, int C, int ld, uint16_t* dst, int Hp, int Wp,
-                      int Cp, int pt, int pl, cudaStream_t st);
-int a3d_halo_repack_filter(a3d_ctx* ctx, const uint16_t* w, uint16_t* wd, int K, int RS, int C, int Cp, int flip,
-                           cudaStream_t st);
-
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
-
-// Stride-1 convolution through the shared-memory-halo kernel (tc_halo.cu).  `in` is the tensor the filter
-// slides over ([N,H,W,C], channel stride ld), outputs P x Q, filter [Kout][R][S][C] (flip = 0) or the
-// original OHWI filter of a conv whose dgrad this is (flip = 1: w is [C_conv = Kout][RS][K_conv = C]).
-// A3D_HALO = 0 never (default), 1 the 5x5 forward layers, 2 wherever it fits.  With the TMA-store epilogue the
-// im2col-TMA engine is faster than the halo kernel on every MSDN layer (profiles/sweep_r01_halo.txt):
-// conv2d_1 77 vs 122 us, fine/second 67 vs 91 us; the halo kernel stays as an option and a tested path.
-static int halo_policy() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("A3D_HALO"); v = e ? atoi(e) : 0; }
-  return v;
-}
-static bool halo_ok(int C, int R, int S, int Wp, bool dgrad) {
-  // needs >= 48 channels (padding to 64 wastes < 1/3) and a window that fits shared memory.  Measured on
-  // B200 (profiles/bench_ops_r01_halo.json): a win for the 5x5 forward layers (25 taps share one window);
-  // for 3x3 layers and for dgrad at these small spatial sizes the padded-grid garbage (20-28 % of the
-  // positions) and the extra pad-copy outweigh the saved L2 traffic, so they stay on the im2col-TMA path.
-  if (!(C >= 48 && (128 + (R - 1) * Wp + S - 1) <= 1024)) return false;
-  if (halo_policy() == 0) return false;
-  if (halo_policy() >= 2) return true;
-  return !dgrad && R * S >= 25;
-}
-
-static int halo_conv(a3d_ctx* ctx, const uint16_t* in, int N, int H, int W, int C, int ld, const uint16_t* w, int Kout,
-                     int R, int S, int pt, int pl, int P, int Q, int flip, void* out, int out_f32, long long ldo,
-                     const float* bias, unsigned flags, const uint16_t* relu_src, void* ws, size_t ws_bytes,
-                     cudaStream_t st) {
-  int Hp = P + R - 1; if (Hp < H + pt) Hp = H + pt;
-  int Wp = Q + S - 1; if (Wp < W + pl) Wp = W + pl;
-  const int Cp = (C + 63) / 64 * 64;
-  const bool need_copy = !(pt == 0 && pl == 0 && Hp == H && Wp == W && Cp == C && ld == C);
-  uint8_t* wsb = reinterpret_cast<uint8_t*>(ws);
-  size_t off = 0;
-  const uint16_t* xp = in;
-  if (need_copy) {
-    size_t bytes = al256((size_t)N * Hp * Wp * Cp * 2);
-    if (off + bytes > ws_bytes) { a3d_set_error("halo conv: workspace too small"); return A3D_EINVAL; }
-    int rc = a3d_halo_pad_copy(ctx, in, N, H, W, C, ld, reinterpret_cast<uint16_t*>(wsb + off), Hp, Wp, Cp, pt, pl, st);
-    if (rc) return rc;
-    xp = reinterpret_cast<const uint16_t*>(wsb + off);
-    off += bytes;
-  }
-  const uint16_t* wpk = w;
-  if (flip || Cp != C) {
-    size_t bytes = al256((size_t)Kout * R * S * Cp * 2);
-    if (off + bytes > ws_bytes) { a3d_set_error("halo conv: workspace too small"); return A3D_EINVAL; }
-    // flip: w is [K_conv = C][RS][C_conv = Kout] -> [Kout][RS][Cp]
-    int rc = flip ? a3d_halo_repack_filter(ctx, w, reinterpret_cast<uint16_t*>(wsb + off), C, R * S, Kout, Cp, 1, st)
-                  : a3d_halo_repack_filter(ctx, w, reinterpret_cast<uint16_t*>(wsb + off), Kout, R * S, C, Cp, 0, st);
-    if (rc) return rc;
-    wpk = reinterpret_cast<const uint16_t*>(wsb + off);
-    off += bytes;
-  }
-  return a3d_halo_conv_run(ctx, xp, N, Hp, Wp, Cp, wpk, Kout, R, S, P, Q, out, out_f32, P, Q, 0, 0, ldo, bias, flags,
-                           relu_src, st);
-}
 
 static int check_desc(const a3d_conv_desc* d) {
   A3D_REQUIRE(d, "conv: null descriptor");
@@ -235,19 +163,9 @@ static size_t splitk_bytes(a3d_ctx* ctx, long long rows, int cols) {
 
 extern "C" size_t a3d_conv2d_ws_bytes(a3d_ctx* ctx, const a3d_conv_desc* d, int op) {
   if (!d) return 0;
-  const bool s1 = d->stride_h == 1 && d->stride_w == 1;
-  if (op == A3D_OP_FWD) {
-    size_t a = splitk_bytes(ctx, (long long)d->N * d->P * d->Q, d->K);
-    size_t b = s1 ? a3d_halo_ws_bytes(d->N, d->H, d->W, d->C, d->C, d->K, d->R, d->S, d->pad_t, d->pad_l, d->P, d->Q, 0) : 0;
-    return a > b ? a : b;
-  }
+  if (op == A3D_OP_FWD) return splitk_bytes(ctx, (long long)d->N * d->P * d->Q, d->K);
   if (op == A3D_OP_DGRAD) {
-    if (dgrad_as_fwd_ok(d)) {
-      size_t a = filt_bytes(d) + splitk_bytes(ctx, (long long)d->N * d->H * d->W, d->C);
-      size_t b = a3d_halo_ws_bytes(d->N, d->P, d->Q, d->K, d->ldy, d->C, d->R, d->S, d->R - 1 - d->pad_t,
-                                   d->S - 1 - d->pad_l, d->H, d->W, 1);
-      return a > b ? a : b;
-    }
+    if (dgrad_as_fwd_ok(d)) return filt_bytes(d) + splitk_bytes(ctx, (long long)d->N * d->H * d->W, d->C);
     if (dgrad_as_cols_ok(d)) return (size_t)d->N * d->P * d->Q * d->R * d->S * d->C * sizeof(float);
     return 0;
   }
@@ -262,15 +180,6 @@ extern "C" int a3d_conv2d_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
   if (d->impl == A3D_IMPL_SIMT) return a3d_simt_conv_fwd(ctx, d, x, w, bias, y, y_dtype, flags, st);
-  {
-    int Wp = d->Q + d->S - 1; if (Wp < d->W + d->pad_l) Wp = d->W + d->pad_l;
-    if (d->stride_h == 1 && d->stride_w == 1 && halo_ok(d->C, d->R, d->S, Wp, false) && ws &&
-        ws_bytes >= a3d_halo_ws_bytes(d->N, d->H, d->W, d->C, d->C, d->K, d->R, d->S, d->pad_t, d->pad_l, d->P, d->Q, 0)) {
-      int rc2 = halo_conv(ctx, x, d->N, d->H, d->W, d->C, d->C, w, d->K, d->R, d->S, d->pad_t, d->pad_l, d->P, d->Q, 0, y,
-                          y_dtype == A3D_F32, d->ldy, bias, flags, nullptr, ws, ws_bytes, st);
-      if (rc2 != A3D_ENOTSUP) return rc2;
-    }
-  }
   // single-filter 64-channel convolution (MSDN fine/third): tap products on mma.sync + stencil sum reads the
   // input once; as a BN = 16 tcgen05 GEMM the im2col operand traffic is 25x redundant (49 us vs the input's 17 MB).
   // A3D_K1_TILED=0 keeps the GEMM.
@@ -375,17 +284,6 @@ static int dgrad_impl(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* dy, 
     e.pad_t = d->R - 1 - d->pad_t; e.pad_l = d->S - 1 - d->pad_l;
     e.stride_h = e.stride_w = 1;
     return a3d_tc_conv_fwd(ctx, &e, dy, wflip, nullptr, dx, A3D_BF16, 0, ws, ws_bytes, st);
-  }
-  if (d->impl != A3D_IMPL_SIMT && dgrad_as_fwd_ok(d)) {
-    const int pt2 = d->R - 1 - d->pad_t, pl2 = d->S - 1 - d->pad_l;
-    int Wp = d->W + d->S - 1; if (Wp < d->Q + pl2) Wp = d->Q + pl2;
-    if (halo_ok(d->K, d->R, d->S, Wp, true) && ws &&
-        ws_bytes >= a3d_halo_ws_bytes(d->N, d->P, d->Q, d->K, d->ldy, d->C, d->R, d->S, pt2, pl2, d->H, d->W, 1)) {
-      rc = halo_conv(ctx, dy, d->N, d->P, d->Q, d->K, d->ldy, w, d->C, d->R, d->S, pt2, pl2, d->H, d->W, 1, dx, 0, d->C,
-                     nullptr, 0, relu_src, ws, ws_bytes, st);
-      if (rc == 0) { *relu_done = relu_src != nullptr; return 0; }
-      if (rc != A3D_ENOTSUP) return rc;
-    }
   }
   if (d->impl != A3D_IMPL_SIMT && dgrad_as_fwd_ok(d) && ws && ws_bytes >= filt) {
     uint16_t* wd = reinterpret_cast<uint16_t*>(ws);
@@ -536,26 +434,13 @@ extern "C" int a3d_dense_wgrad_adam(a3d_ctx* ctx, const uint16_t* x, int ldx, co
     int rc = a3d_colsum_bf16(ctx, dy, (size_t)M, N, lddy, db, st);
     if (rc) return rc;
   }
-  // Three implementations (A3D_FUSED_ADAM = mma | simt | tc): the optimizer-shaped streaming kernel that forms the
-  // gradient with warp-level mma.sync (default, batch <= 32), the same with the 32 FMAs per parameter on the CUDA
-  // cores, or the tcgen05 GEMM whose epilogue streams w/m/v through shared-memory-transposed coalesced accesses.
-  static int variant = -1;                   // 0 mma.sync (default), 1 CUDA cores, 2 tcgen05 epilogue
-  if (variant < 0) { const char* e = getenv("A3D_FUSED_ADAM"); variant = !e ? 0 : e[0] == 's' ? 1 : e[0] == 't' ? 2 : 0; }
-  if (variant == 0) {
-    int rc = a3d_mma_dense_wgrad_adam(ctx, x, ldx, dy, lddy, w, m, v, w_bf16, M, N, K, lr_t, beta1, beta2, eps,
-                                      grad_scale, lr_t_dev, st);
-    if (rc != A3D_ENOTSUP) return rc;
-  }
-  if (variant == 1) {
-    int rc = a3d_simt_dense_wgrad_adam(ctx, x, ldx, dy, lddy, w, m, v, w_bf16, M, N, K, lr_t, beta1, beta2, eps,
-                                       grad_scale, lr_t_dev, st);
-    if (rc != A3D_ENOTSUP) return rc;
-  }
-  A3D_REQUIRE(((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0 &&
-                  (!w_bf16 || (reinterpret_cast<uintptr_t>(w_bf16) & 7) == 0),
-              "dense wgrad+adam: w/m/v must be 16-byte aligned");
-  a3d_adam_args a{w, m, v, w_bf16, lr_t, beta1, beta2, eps, grad_scale, lr_t_dev};
-  return a3d_tc_dense_wgrad(ctx, x, ldx, dy, lddy, nullptr, M, N, K, st, &a);
+  // The optimizer-shaped streaming kernel that forms the rank-M gradient with warp-level mma.sync (batch <= 32).  (Two
+  // other forms were measured and removed: the 32 FMAs per parameter on the CUDA cores, 381 us, and a tcgen05 GEMM with
+  // a TF-Adam epilogue, 535 us, against 277 us.)
+  int rc = a3d_mma_dense_wgrad_adam(ctx, x, ldx, dy, lddy, w, m, v, w_bf16, M, N, K, lr_t, beta1, beta2, eps, grad_scale,
+                                    lr_t_dev, st);
+  if (rc == A3D_ENOTSUP) a3d_set_error("dense wgrad+adam: needs batch <= 32, K %% 256 == 0 and 16-byte aligned w/m/v");
+  return rc;
 }
 
 // Convolution + bias + activation + 2x2/2 max-pool in one tcgen05 GEMM.  The caller supplies the "pool-embedded"

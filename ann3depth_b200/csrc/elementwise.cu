@@ -985,114 +985,11 @@ extern "C" int a3d_scatter_cast_bf16(a3d_ctx* ctx, const float* src, const int* 
 // ------------------------------------------------------------------------------------ dense wgrad + TF-Adam, one pass
 // For the batch-32 dense layers the weight gradient dw[n][k] = sum_b dy[b][n] * x[b][k] is 32 FMAs per parameter,
 // while the optimizer moves 26 bytes per parameter: the update is HBM-bound and the gradient is cheap enough to be
-// recomputed from the two small activation matrices on the CUDA cores INSIDE the optimizer pass.  The f32 gradient
-// (4 B written + 4 B read per parameter, 536 MB for MSDN's 67 M dense parameters) then never exists in HBM.
-//
-// Block = 256 threads = 8 warps (4 along n x 2 along k); a warp covers 128 consecutive k (one float4 per lane) of
-// RN = 4 rows, so every w/m/v access of a warp is one contiguous 512-byte segment.  A block owns 256 columns (its
-// x slab [M][256] stays in shared memory as f32) and walks over `rows_per_block` rows in tiles of 16; the w/m/v
-// loads of a tile are issued before the FMA loop so that their latency is hidden behind it.
-// Row tiles are dealt round-robin to the gridDim.y blocks of a column strip and the grid is exactly one resident
-// wave, so at any moment all blocks work on a few neighbouring row tiles: the live footprint is a compact band of
-// w/m/v (DRAM page / TLB locality) instead of 128-row tiles scattered over the whole 200 MB matrix.
-// bf16 x bf16 products are exact in f32 and accumulated in f32, as on the tensor-core path.
-template <int MB>
-__global__ void __launch_bounds__(256, 2)
-dense_wgrad_adam_kernel(const uint16_t* __restrict__ x, int ldx, const uint16_t* __restrict__ dy, int lddy,
-                        float* __restrict__ w, float* __restrict__ m, float* __restrict__ v, uint16_t* __restrict__ wb,
-                        int M, int N, int K, int rows_per_block, float lr_t, float b1, float b2, float eps, float gs,
-                        const float* __restrict__ lr_dev) {
-  __shared__ __align__(16) float xs[MB][256];
-  __shared__ __align__(16) float dys[MB][16];
-  if (lr_dev) lr_t = __ldg(lr_dev);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wn = warp >> 1, wk = warp & 1;
-  const int k0 = blockIdx.x * 256;
-  const int nb1 = N;
-  for (int i = tid; i < MB * 256; i += 256) {
-    const int b = i >> 8, kk = i & 255;
-    xs[b][kk] = b < M ? bf16_bits_to_f32(__ldg(x + (size_t)b * ldx + k0 + kk)) : 0.f;
-  }
-  const int kcol = k0 + wk * 128 + lane * 4;
-  for (int n0 = blockIdx.y * 16; n0 < nb1; n0 += gridDim.y * 16) {
-    // optimizer state of this thread's 4 rows x 4 columns: in flight during the FMA loop
-    float4 W[4], Mo[4], V[4];
-    const int nrow = n0 + wn * 4;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      if (nrow + r < nb1) {
-        const size_t off = (size_t)(nrow + r) * K + kcol;
-        W[r] = *reinterpret_cast<const float4*>(w + off);
-        Mo[r] = *reinterpret_cast<const float4*>(m + off);
-        V[r] = *reinterpret_cast<const float4*>(v + off);
-      }
-    }
-    __syncthreads();                                 // previous tile's readers of dys are done (and xs is written)
-    for (int i = tid; i < MB * 16; i += 256) {
-      const int b = i >> 4, nn = i & 15;
-      dys[b][nn] = (b < M && n0 + nn < nb1) ? bf16_bits_to_f32(__ldg(dy + (size_t)b * lddy + n0 + nn)) : 0.f;
-    }
-    __syncthreads();
-    float acc[4][4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[r][j] = 0.f;
-#pragma unroll 8
-    for (int b = 0; b < MB; ++b) {
-      const float4 xv = *reinterpret_cast<const float4*>(&xs[b][wk * 128 + lane * 4]);
-      const float4 dv = *reinterpret_cast<const float4*>(&dys[b][wn * 4]);
-      const float d[4] = {dv.x, dv.y, dv.z, dv.w};
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        acc[r][0] = fmaf(d[r], xv.x, acc[r][0]);
-        acc[r][1] = fmaf(d[r], xv.y, acc[r][1]);
-        acc[r][2] = fmaf(d[r], xv.z, acc[r][2]);
-        acc[r][3] = fmaf(d[r], xv.w, acc[r][3]);
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      if (nrow + r < nb1) {
-        float* pw = &W[r].x; float* pm = &Mo[r].x; float* pv = &V[r].x;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float gk = acc[r][j] * gs;
-          pm[j] = b1 * pm[j] + (1.f - b1) * gk;
-          pv[j] = b2 * pv[j] + (1.f - b2) * gk * gk;
-          pw[j] = pw[j] - lr_t * pm[j] / (sqrtf(pv[j]) + eps);
-        }
-        const size_t off = (size_t)(nrow + r) * K + kcol;
-        *reinterpret_cast<float4*>(w + off) = W[r];
-        *reinterpret_cast<float4*>(m + off) = Mo[r];
-        *reinterpret_cast<float4*>(v + off) = V[r];
-        if (wb) *reinterpret_cast<uint2*>(wb + off) = make_uint2(pack_bf16x2(W[r].x, W[r].y), pack_bf16x2(W[r].z, W[r].w));
-      }
-    }
-  }
-}
-
-// 0 = launched; A3D_ENOTSUP = shape not covered (caller falls back to the tcgen05 epilogue variant)
-int a3d_simt_dense_wgrad_adam(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* w, float* m,
-                              float* v, uint16_t* wb, int M, int N, int K, float lr_t, float beta1, float beta2, float eps,
-                              float grad_scale, const float* lr_t_dev, cudaStream_t st) {
-  if (M > 32 || K % 256 || !aligned16(w) || !aligned16(m) || !aligned16(v) || (wb && (reinterpret_cast<uintptr_t>(wb) & 7)))
-    return A3D_ENOTSUP;
-  // one resident wave: 2 blocks per SM
-  const int kblocks = K / 256;
-  int gy = 2 * ctx->sm_count / kblocks;
-  if (gy < 1) gy = 1;
-  if (gy > ceil_div(N, 16)) gy = ceil_div(N, 16);
-  const int rows = 0;
-  dim3 grid(kblocks, gy);
-  dense_wgrad_adam_kernel<32><<<grid, 256, 0, st>>>(x, ldx, dy, lddy, w, m, v, wb, M, N, K, rows, lr_t, beta1, beta2, eps,
-                                                   grad_scale, lr_t_dev);
-  A3D_LAUNCH_OK(ctx);
-  return 0;
-}
-
+// recomputed from the two small activation matrices INSIDE the optimizer pass.  The f32 gradient (4 B written + 4 B
+// read per parameter, 536 MB for MSDN's 67 M dense parameters) then never exists in HBM.
 // ------------------------------------------------------------------------------------ dense wgrad + TF-Adam (mma.sync)
-// Same fusion as above with the 32-term dot products on the tensor cores (warp-level mma.sync m16n8k16, bf16 -> f32):
+// The 32-term dot products run on the tensor cores (warp-level mma.sync m16n8k16, bf16 -> f32; on the CUDA cores the
+// same pass was issue-bound at 381 us against 277 us):
 // the kernel keeps the shape of the plain optimizer pass -- many resident warps streaming w/m/v -- and the gradient
 // costs 8 MMAs per 512 parameters instead of 512 FMAs per 16.  No shared memory, no block-level synchronisation.
 //   MMA M = 16 weight rows n, K = batch b (2 steps of 16), N = 8 weight columns k per tile

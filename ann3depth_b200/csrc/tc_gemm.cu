@@ -1,8 +1,6 @@
 // tc_gemm.cu -- host side of the tcgen05 GEMM engine: tensor-map construction, tile/split selection
 // and the launchers used by the convolution / dense entry points.
 #include "tc_gemm.cuh"
-#include "tc_persist.cuh"
-#include "tc_mcast.cuh"
 #include "tc_pair.cuh"
 #include <cuda.h>
 #include <stdlib.h>
@@ -220,65 +218,19 @@ int launch_cfg(a3d_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, con
 //   1  128-row tile, one stage more (long main loops -- conv2d_1 dgrad has 100 k-blocks -- want the deeper pipeline)
 //   2  256-row tile (two accumulators sharing every B stage: less L2->SM operand traffic), default ring
 //   3  256-row tile, three stages
-//   4..6  EXPERIMENTAL persistent kernel (tc_persist.cuh) with 2 / 3 / 4 stages; candidates only with A3D_PERSIST=1
-//   7..10 EXPERIMENTAL cluster kernel (tc_mcast.cuh): weight tile multicast to 2 / 4 CTAs, default ring / one stage
-//         more; candidates only with A3D_MCAST=1.  NOTE: tmB must then have a box of BN / CL rows (mcast_cl()).
+//   4..10 (removed) round-1 experiments that lost on every MSDN layer once measured on hardware: a persistent tile loop
+//         with double-buffered TMEM accumulators, and a cluster kernel that TMA-multicast the weight tile to 2 / 4 CTAs
 //   11,12 CTA-pair kernel (tc_pair.cuh): tcgen05.mma.cta_group::2, 256 x BN tile per pair, each CTA holds half the
 //         weight tile; 11 = short ring (two CTAs per SM), 12 = deep ring (one CTA per SM).  tmB box = BN / 2 rows.
-enum { V_BASE = 0, V_DEEP = 1, V_BM256 = 2, V_BM256_DEEP = 3, V_PERSIST2 = 4, V_PERSIST3 = 5, V_PERSIST4 = 6,
-       V_MC2 = 7, V_MC2_DEEP = 8, V_MC4 = 9, V_MC4_DEEP = 10, V_PAIR = 11, V_PAIR_DEEP = 12, V_COUNT = 13 };
-int mcast_cl(int variant) {
-  return variant == V_MC2 || variant == V_MC2_DEEP || variant == V_PAIR || variant == V_PAIR_DEEP ? 2
-         : variant == V_MC4 || variant == V_MC4_DEEP ? 4 : 1;
-}
+enum { V_BASE = 0, V_DEEP = 1, V_BM256 = 2, V_BM256_DEEP = 3, V_PAIR = 11, V_PAIR_DEEP = 12, V_COUNT = 13 };
+// CTAs that share one B tile: the pair kernel's tensor map for B has a box of BN / 2 rows
+int mcast_cl(int variant) { return variant == V_PAIR || variant == V_PAIR_DEEP ? 2 : 1; }
 // A3D_PAIR: 0 off, 1 deep ring only, 2 (default) both pair variants are tuner candidates
 int pair_mode() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("A3D_PAIR"); v = e ? atoi(e) : 2; }
   return v;
 }
-bool mcast_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("A3D_MCAST"); v = e ? atoi(e) : 0; }
-  return v != 0;
-}
-bool persist_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("A3D_PERSIST"); v = e ? atoi(e) : 0; }
-  return v != 0;
-}
-
-template <class C, int CL>
-int launch_mcast(a3d_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB_slice, const tc::Params& p_in, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    A3D_CHECK_CUDA(cudaFuncSetAttribute(tc::gemm_mcast_kernel<C, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
-  }
-  tc::Params p = p_in;
-  if (p.atomic || p.kb_per_split < p.num_kb) { a3d_set_error("multicast gemm: no split-K"); return A3D_ENOTSUP; }
-  CUtensorMap tmC;
-  bool use_c = false;
-  int rc = maybe_tma_out(ctx, p, &tmC, &use_c);
-  if (rc) return rc;
-  const bool ok = use_c && ((p.epi == tc::EPI_TMA_F32 && C::BN % 32 == 0) || (p.epi == tc::EPI_TMA_BF16 && C::BN % 64 == 0) ||
-                           (p.epi == tc::EPI_POOL4_BF16 && C::BN == 256));
-  if (!ok) { a3d_set_error("multicast gemm: needs a TMA-store epilogue (f32: BN %% 32, bf16: BN %% 64)"); return A3D_ENOTSUP; }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(ceil_div(ceil_div(p.M, 128), CL) * CL, ceil_div(p.N, C::BN), 1);
-  cfg.blockDim = dim3(192, 1, 1);
-  cfg.dynamicSmemBytes = C::SMEM_BYTES;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  A3D_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc::gemm_mcast_kernel<C, CL>, tmA, tmB_slice, tmC, p));
-  A3D_LAUNCH_OK(ctx);
-  return 0;
-}
-
 template <class C>
 int launch_pair(a3d_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB_half, const tc::Params& p_in, cudaStream_t st) {
   static bool attr_set = false;
@@ -310,36 +262,6 @@ int launch_pair(a3d_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB_hal
   return 0;
 }
 
-template <class C, int NSTAGE>
-int launch_persist(a3d_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const tc::Params& p_in, cudaStream_t st) {
-  using P = tc::PersistCfg<C, NSTAGE>;
-  static_assert(P::SMEM_BYTES <= 227 * 1024, "persistent kernel: stage ring + staging exceed shared memory");
-  static int ctas_per_sm = -1;
-  if (ctas_per_sm < 0) {
-    A3D_CHECK_CUDA(cudaFuncSetAttribute(tc::gemm_persist_kernel<C, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        P::SMEM_BYTES));
-    int occ = 0;
-    A3D_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc::gemm_persist_kernel<C, NSTAGE>, 192, P::SMEM_BYTES));
-    const int by_tmem = 512 / P::TMEM_COLS;        // a CTA keeps its TMEM columns for its whole life
-    ctas_per_sm = occ < by_tmem ? occ : by_tmem;
-  }
-  if (ctas_per_sm < 1) { a3d_set_error("persistent gemm: kernel does not fit an SM"); return A3D_ENOTSUP; }
-  tc::Params p = p_in;
-  if (p.atomic || p.kb_per_split < p.num_kb) { a3d_set_error("persistent gemm: no split-K"); return A3D_ENOTSUP; }
-  CUtensorMap tmC;
-  bool use_c = false;
-  int rc = maybe_tma_out(ctx, p, &tmC, &use_c);
-  if (rc) return rc;
-  const bool ok = use_c && ((p.epi == tc::EPI_TMA_F32 && C::BN % 32 == 0) || (p.epi == tc::EPI_TMA_BF16 && C::BN % 64 == 0));
-  if (!ok) { a3d_set_error("persistent gemm: needs a TMA-store epilogue (f32: BN %% 32, bf16: BN %% 64)"); return A3D_ENOTSUP; }
-  const int tiles_m = ceil_div(p.M, 128), tiles_n = ceil_div(p.N, C::BN);
-  int grid = ctx->sm_count * ctas_per_sm;
-  if (grid > tiles_m * tiles_n) grid = tiles_m * tiles_n;
-  tc::gemm_persist_kernel<C, NSTAGE><<<grid, 192, P::SMEM_BYTES, st>>>(tmA, tmB, tmC, p, tiles_m, tiles_n);
-  A3D_LAUNCH_OK(ctx);
-  return 0;
-}
-
 int launch_kk(a3d_ctx* ctx, int bn, int kcb, const CUtensorMap& tmA, const CUtensorMap& tmB, const tc::Params& p,
               int splits, cudaStream_t st, int variant = V_BASE) {
   if (variant == V_BASE) {
@@ -362,26 +284,6 @@ int launch_kk(a3d_ctx* ctx, int bn, int kcb, const CUtensorMap& tmA, const CUten
     A3D_CASEV(V_BM256_DEEP, 64, 3, 256) A3D_CASEV(V_BM256_DEEP, 96, 3, 256) A3D_CASEV(V_BM256_DEEP, 128, 3, 256)
     A3D_CASEV(V_BM256_DEEP, 256, 3, 256)
 #undef A3D_CASEV
-#define A3D_CASEP(BN) \
-  if (bn == BN) { \
-    using C_ = tc::Cfg<BN, 128, false, false>; \
-    if (variant == V_PERSIST2) return launch_persist<C_, 2>(ctx, tmA, tmB, p, st); \
-    if (variant == V_PERSIST3) return launch_persist<C_, 3>(ctx, tmA, tmB, p, st); \
-    if (variant == V_PERSIST4) return launch_persist<C_, 4>(ctx, tmA, tmB, p, st); \
-  }
-    if (variant >= V_PERSIST2 && variant <= V_PERSIST4 && splits == 1) {
-      A3D_CASEP(64) A3D_CASEP(96) A3D_CASEP(128) A3D_CASEP(192) A3D_CASEP(256)
-    }
-#undef A3D_CASEP
-#define A3D_CASEM(BN) \
-  if (bn == BN) { \
-    if (variant == V_MC2) return launch_mcast<tc::Cfg<BN, 128, false, false>, 2>(ctx, tmA, tmB, p, st); \
-    if (variant == V_MC2_DEEP) return launch_mcast<tc::Cfg<BN, 128, false, false, 64, 3>, 2>(ctx, tmA, tmB, p, st); \
-    if (variant == V_MC4) return launch_mcast<tc::Cfg<BN, 128, false, false>, 4>(ctx, tmA, tmB, p, st); \
-    if (variant == V_MC4_DEEP) return launch_mcast<tc::Cfg<BN, 128, false, false, 64, 3>, 4>(ctx, tmA, tmB, p, st); \
-  }
-    if (variant >= V_MC2 && variant <= V_MC4_DEEP && splits == 1) { A3D_CASEM(64) A3D_CASEM(128) A3D_CASEM(256) }
-#undef A3D_CASEM
 #define A3D_CASE2(BN, NS, ND) \
   if (bn == BN) { \
     if (variant == V_PAIR) return launch_pair<tc::PairCfg<BN, 128, NS>>(ctx, tmA, tmB, p, st); \
@@ -401,8 +303,7 @@ bool variant_exists(int bn, int kcb, int variant) {
   if (variant == V_DEEP) return bn == 64 || bn == 96 || bn == 128 || bn == 192 || bn == 256;
   if (variant == V_PAIR) return pair_mode() >= 2 && (bn == 64 || bn == 96 || bn == 128 || bn == 192 || bn == 256);
   if (variant == V_PAIR_DEEP) return pair_mode() >= 1 && (bn == 64 || bn == 96 || bn == 128 || bn == 192 || bn == 256);
-  if (variant >= V_MC2) return mcast_enabled() && (bn == 64 || bn == 128 || bn == 256);
-  if (variant >= V_PERSIST2) return persist_enabled() && (bn == 64 || bn == 96 || bn == 128 || bn == 192 || bn == 256);
+  if (variant > V_BM256_DEEP) return false;
   return bn == 64 || bn == 96 || bn == 128 || bn == 256;
 }
 
@@ -629,14 +530,6 @@ int a3d_tc_conv_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, con
         if (c == 6) return launch_pair<tc::PairCfg<256, 128, 3>>(ctx, tmA, tmBh, p, st);
         return launch_pair<tc::PairCfg<256, 128, 6>>(ctx, tmA, tmBh, p, st);
       }
-      if (c >= 4) {                                // EXPERIMENTAL (A3D_MCAST=1): weight tile multicast to 2 / 4 CTAs
-        const int cl = c == 4 ? 2 : 4;
-        CUtensorMap tmBs;
-        int r = make_tmap_2d(ctx, &tmBs, w, 256, (uint64_t)d->R * d->S * d->C, (uint64_t)d->R * d->S * d->C, 64, 256 / cl);
-        if (r) return r;
-        if (cl == 2) return launch_mcast<tc::Cfg<256, 128, false, false>, 2>(ctx, tmA, tmBs, p, st);
-        return launch_mcast<tc::Cfg<256, 128, false, false>, 4>(ctx, tmA, tmBs, p, st);
-      }
       if (c == 1) return launch_cfg<tc::Cfg<256, 128, false, false, 64, 3>>(ctx, tmA, tmB, p, 1, st);
       if (c == 2) return launch_cfg<tc::Cfg<256, 128, false, false, 64, 2, false, 256>>(ctx, tmA, tmB, p, 1, st);
       if (c == 3) return launch_cfg<tc::Cfg<256, 128, false, false, 64, 3, false, 256>>(ctx, tmA, tmB, p, 1, st);
@@ -647,10 +540,9 @@ int a3d_tc_conv_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, con
     const int kv[16] = {5, d->N, d->H, d->W, d->C, d->K, d->R, d->S, d->stride_h, d->stride_w, d->pad_t, d->pad_l,
                         d->P, d->Q, d->ldy, pool_idx != nullptr};
     memcpy(key.v, kv, sizeof(kv));
-    // candidates 0..3 one-CTA tiles, 4..5 multicast clusters (A3D_MCAST=1 only), 6..7 CTA pairs
+    // candidates 0..3 one-CTA tiles, 6..7 CTA pairs
     int cands[8], nc = 0;
     for (int c = 0; c < 4; ++c) cands[nc++] = c;
-    if (mcast_enabled()) { cands[nc++] = 4; cands[nc++] = 5; }
     if (pair_mode() >= 2) cands[nc++] = 6;
     if (pair_mode() >= 1) cands[nc++] = 7;
     return run(cands[autotune(key, nc, [&](int i) { return run(cands[i]); }, st)]);
@@ -727,10 +619,8 @@ int a3d_tc_conv_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, con
         if (!variant_exists(bn, kcb, variant)) continue;
         // 256-row tiles only unsplit and when they still give every SM about one CTA
         if ((variant == V_BM256 || variant == V_BM256_DEEP) && (sp != 1 || tiles / 2 < ctx->sm_count * 3 / 4)) continue;
-        // persistent kernel: unsplit, and only where a CTA gets more than one tile
-        if (variant >= V_PERSIST2 && variant <= V_PERSIST4 && (sp != 1 || tiles <= ctx->sm_count)) continue;
-        // cluster kernel: unsplit, enough M tiles that sharing the weight tile matters
-        if (variant >= V_MC2 && (sp != 1 || ceil_div(M, 128) < 8)) continue;
+        // pair kernel: unsplit, at least one full pair of M tiles
+        if ((variant == V_PAIR || variant == V_PAIR_DEEP) && (sp != 1 || ceil_div(M, 128) < 2)) continue;
         // pair kernel with an f32 output: 32-column slabs, any BN; with a bf16 output BN % 64 (checked at launch)
         if ((variant == V_PAIR || variant == V_PAIR_DEEP) && y_dtype != A3D_F32 && bn % 64) continue;
         bool dup = false;
@@ -1033,10 +923,8 @@ int a3d_tc_dense_dgrad(a3d_ctx* ctx, const uint16_t* dy, int lddy, const uint16_
 }
 
 // wgrad: dw[n][k] = sum_b dy[b][n] x[b][k]; both operands MN-major with the batch as the reduction index.
-// With `adam` != null the gradient tile is consumed in the epilogue by TF-Adam (see tc::EPI_ADAM).
-struct a3d_adam_args { float* w; float* m; float* v; uint16_t* wb; float lr_t, beta1, beta2, eps, grad_scale; const float* lr_t_dev; };
 int a3d_tc_dense_wgrad(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, int M, int N,
-                       int K, cudaStream_t st, const a3d_adam_args* adam = nullptr) {
+                       int K, cudaStream_t st) {
   if (K % 64 || ldx % 8 || lddy % 8) {
     a3d_set_error("tc dense wgrad: needs K %% 64 == 0 and 16-byte aligned row pitches");
     return A3D_ENOTSUP;
@@ -1049,19 +937,10 @@ int a3d_tc_dense_wgrad(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t*
   tc::Params p{};
   p.M = N; p.N = K; p.num_kb = ceil_div(M, 64); p.kb_per_split = p.num_kb; p.a_mode = tc::A_TILED;
   p.epi = tc::EPI_ROW_F32; p.out = dw; p.ldo = K; p.atomic = 0;
-  if (adam) {
-    p.epi = tc::EPI_ADAM; p.out = adam->w; p.adam_m = adam->m; p.adam_v = adam->v; p.adam_wb = adam->wb;
-    p.lr_t = adam->lr_t; p.beta1 = adam->beta1; p.beta2 = adam->beta2; p.eps = adam->eps; p.grad_scale = adam->grad_scale;
-    p.lr_t_dev = adam->lr_t_dev;
-  }
   // One k-block per CTA: the kernel is all prologue + epilogue.  N tiles of 128 keep the stage ring under
   // 104 KB so that two CTAs share an SM and one's epilogue hides the other's prologue (A3D_DWGRAD_BN overrides).
   static int bn_pref = -1;
   if (bn_pref < 0) { const char* e = getenv("A3D_DWGRAD_BN"); bn_pref = e ? atoi(e) : 128; }
-  if (adam) {
-    if (bn_pref >= 128 && K % 128 == 0) return launch_cfg<tc::Cfg<128, 128, true, true, 64, 3, true>>(ctx, tmA, tmB, p, 1, st);
-    return launch_cfg<tc::Cfg<64, 128, true, true, 64, 3, true>>(ctx, tmA, tmB, p, 1, st);
-  }
   if (bn_pref == 256 && K % 256 == 0) return launch_cfg<tc::Cfg<256, 128, true, true, 64>>(ctx, tmA, tmB, p, 1, st);
   if (bn_pref >= 128 && K % 128 == 0) return launch_cfg<tc::Cfg<128, 128, true, true, 64>>(ctx, tmA, tmB, p, 1, st);
   return launch_cfg<tc::Cfg<64, 128, true, true, 64>>(ctx, tmA, tmB, p, 1, st);

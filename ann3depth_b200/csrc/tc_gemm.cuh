@@ -39,8 +39,8 @@ enum Epi : int {
   EPI_ROW_BF16 = 0,       // out_bf16[row*ldo + col] = act(acc + bias[col])
   EPI_ROW_F32 = 1,        // out_f32 [row*ldo + col] = act(acc + bias[col])   (atomicAdd when split-K)
   EPI_COL_F32 = 2,        // out_f32 [col*ldo + row] (+)= acc                  (transposed; dense layers)
-  EPI_ADAM = 3,           // acc is a weight gradient: TF-Adam applied in place on w/m/v (+ bf16 mirror) at
-                          // [row*ldo + col]; the gradient itself never goes to HBM (dense wgrad, single GPU)
+  // (3: removed -- a TF-Adam epilogue that consumed dense weight-gradient tiles from TMEM lost 535 us vs 277 us to the
+  //  optimizer-shaped mma.sync kernel of elementwise.cu)
   EPI_TMA_F32 = 4,        // out_f32[row*ldo + col] = act(acc + bias[col]) staged through shared memory and written
                           // with TMA (tmC): whole 128-byte lines per row instead of one 64-byte piece per thread;
                           // split-K accumulates with cp.reduce.async.bulk (.add.f32, performed in L2)
@@ -73,11 +73,7 @@ struct Params {
   const float* bias;
   unsigned flags;
   int atomic;               // accumulate with atomicAdd (split-K)
-  // EPI_ADAM: out = w (f32 master)
   uint8_t* pool_idx;        // EPI_POOL4_BF16: routing record (nullable)
-  float* adam_m; float* adam_v; uint16_t* adam_wb;
-  float lr_t, beta1, beta2, eps, grad_scale;
-  const float* lr_t_dev;
 };
 
 // ELT_ = operand element size in bytes: 2 = bf16 (kind::f16), 4 = f32 consumed as TF32 (kind::tf32).  All shared-memory
@@ -97,9 +93,8 @@ struct Cfg {
   // operand traffic per FLOP drops from (128+BN) to (256+BN)/2 rows per k-block -- the 5x5 layers are bound by
   // L2->SM operand bandwidth (conv2d_1: 819 MB per launch at ~13 TB/s), not by the tensor pipe.  K-major A only.
   static constexpr int MT = BM_ / 128;
-  static_assert(BM_ == 128 || (BM_ == 256 && KCB_ != 16 && !ADAM_), "BM = 256: swizzled A, no Adam epilogue");
-  static constexpr bool ADAM = ADAM_;                     // compile the EPI_ADAM epilogue (24 float4 loads in flight:
-                                                          // 168 registers) only into the kernels that use it
+  static_assert(BM_ == 128 || (BM_ == 256 && KCB_ != 16), "BM = 256: swizzled A");
+  static_assert(!ADAM_, "the TF-Adam epilogue was removed (template slot kept so that Cfg<...> argument lists stay valid)");
   static constexpr int B_BW = B_BW_;                     // MN-major B: elements per block (row = B_BW * ELT = 128/64/32 bytes)
   static constexpr int B_BLK_BYTES = KROWS * B_BW_ * ELT_;   // KROWS K-rows x BW elements
   static constexpr int B_NBLK = BN_ / B_BW_;
@@ -389,79 +384,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       c_begin = NCH * 32;
     }
-    if constexpr (C::ADAM) {
-     if (p.epi == EPI_ADAM) {
-      // The accumulator is a weight-gradient tile.  Row-per-thread (the TMEM layout) is the wrong shape for streaming
-      // w/m/v, so each 32 x 32 chunk goes through this warp's swizzled shared-memory slab and is re-read with 8 lanes
-      // per row: every global access of the warp is four full 128-byte lines, and the 24 float4 loads of a chunk are
-      // all in flight before the first one is consumed.  The gradient itself never reaches HBM.
-      uint8_t* slab = smem + quarter * 8192;
-      const int row0 = m0 + quarter * 32;
-      const float lr_t = p.lr_t_dev ? __ldg(p.lr_t_dev) : p.lr_t;
-      const int rsub = lane >> 3, cq = lane & 7;
-      if (row0 < p.M) {
-#pragma unroll 1
-        for (int ch = 0; ch < C::BN / 32; ++ch) {
-          const int col0 = n0 + ch * 32;
-          if (col0 >= p.N) break;
-          {
-            uint32_t ra[16], rb[16];
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ch * 32);
-            __syncwarp();                          // previous chunk's readers of the slab are done
-            ptx::tmem_ld_x16(taddr, ra);
-            ptx::tmem_ld_x16(taddr + 16, rb);
-            ptx::tmem_ld_wait();
-            const uint32_t srow = ptx::smem_u32(slab) + (uint32_t)lane * 128u;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              ptx::st_shared_v4_b32(srow + (uint32_t)((j ^ (lane & 7)) << 4), ra[4 * j], ra[4 * j + 1], ra[4 * j + 2], ra[4 * j + 3]);
-              ptx::st_shared_v4_b32(srow + (uint32_t)(((j + 4) ^ (lane & 7)) << 4), rb[4 * j], rb[4 * j + 1], rb[4 * j + 2],
-                                    rb[4 * j + 3]);
-            }
-          }
-          __syncwarp();
-          const int col = col0 + cq * 4;
-          const bool col_ok = col + 4 <= p.N;
-          float4 W[8], Mo[8], V[8];
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int row = row0 + it * 4 + rsub;
-            if (row < p.M && col_ok) {
-              const long long off = (long long)row * p.ldo + col;
-              W[it] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.out) + off);
-              Mo[it] = *reinterpret_cast<const float4*>(p.adam_m + off);
-              V[it] = *reinterpret_cast<const float4*>(p.adam_v + off);
-            }
-          }
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int rr = it * 4 + rsub;
-            const int row = row0 + rr;
-            if (row < p.M && col_ok) {
-              const float4 G = ptx::ld_shared_v4(ptx::smem_u32(slab) + (uint32_t)rr * 128u + (uint32_t)((cq ^ (rr & 7)) << 4));
-              const float g[4] = {G.x, G.y, G.z, G.w};
-              float* pw = &W[it].x; float* pm = &Mo[it].x; float* pv = &V[it].x;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float gk = g[j] * p.grad_scale;
-                pm[j] = p.beta1 * pm[j] + (1.f - p.beta1) * gk;
-                pv[j] = p.beta2 * pv[j] + (1.f - p.beta2) * gk * gk;
-                pw[j] = pw[j] - lr_t * pm[j] / (sqrtf(pv[j]) + p.eps);
-              }
-              const long long off = (long long)row * p.ldo + col;
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = W[it];
-              *reinterpret_cast<float4*>(p.adam_m + off) = Mo[it];
-              *reinterpret_cast<float4*>(p.adam_v + off) = V[it];
-              if (p.adam_wb)
-                *reinterpret_cast<uint2*>(p.adam_wb + off) =
-                    make_uint2(pack_bf16x2(W[it].x, W[it].y), pack_bf16x2(W[it].z, W[it].w));
-            }
-          }
-        }
-      }
-      c_begin = C::BN;
-     }
-    }
     if (p.epi == EPI_TMA_BF16) {
       // as above with 64 bf16 columns (= 128 bytes) per slab row; a tail of BN % 64 columns takes the register path
       uint8_t* slab0 = smem + quarter * 8192;
@@ -582,9 +504,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       float v[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-      if (p.epi == EPI_ADAM) {
-        // handled above (coalesced pass through shared memory)
-      } else if (p.epi == EPI_COL_F32) {
+      if (p.epi == EPI_COL_F32) {
         float* o = reinterpret_cast<float*>(p.out);
         if (row_ok) {
 #pragma unroll

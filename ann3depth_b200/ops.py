@@ -481,7 +481,8 @@ class Context:
         return db
 
     def debug_tc_gemm(self, A, B, M, N, K, bn, kcb=128, a_mn=False, b_mn=False, splits=1, variant=0):
-        """variant (K-major operands only): 0 default, 1 deeper stage ring, 2 256-row tile, 3 both (tc_gemm.cu)"""
+        """variant (K-major operands only): 0 default, 1 deeper stage ring, 2 256-row tile, 3 both, 11 / 12 CTA pair
+        (tcgen05 cta_group::2) with a short / deep ring (tc_gemm.cu)"""
         D = torch.empty(M, N, dtype=torch.float32, device=A.device)
         L.check(self.lib.a3d_debug_tc_gemm_v(self.h, _ptr(A), _ptr(B), _ptr(D), M, N, K, bn, kcb, int(a_mn), int(b_mn),
                                              splits, variant, _stream()), "debug_tc_gemm")

@@ -216,6 +216,77 @@ def conv_flops(detail):
         return 0.0
 
 
+def other_configs(torch, pk):
+    """BASELINE.json configs 4 and 5 and the TF32 precision mode, as short extra measurements on rank 0 of a single-GPU
+    run (the headline stays config 2: MSDN bs32 phase-1 train step).  CUDA events, inputs resident in HBM."""
+    from ann3depth_b200 import models
+    from ann3depth_b200.init import glorot_params
+    out = {}
+    dev = torch.device("cuda:0")
+
+    def timed(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    # ---- TF32 precision mode: the same phase-1 step with float32 storage and tcgen05 kind::tf32
+    images, depths = synthetic_batch(0, torch)
+    op = models.msdn(images.to(dev), depths.to(dev), train=True, dtype="tf32")
+    op.net.load_params(glorot_params(seed=1))
+    for _ in range(3):
+        op.run()
+    ms = timed(op.run, 20)
+    out["msdn_train_bs32_tf32"] = {"ms_per_step": ms, "images_per_s": BATCH / ms * 1e3,
+                                   "step_tflops_algorithmic": FLOP_PER_IMAGE_PHASE1 * BATCH / ms / 1e9,
+                                   "note": "float32 activations + tcgen05.mma kind::tf32, sequential schedule, CUDA graph"}
+    del op
+    torch.cuda.empty_cache()
+    # ---- config 5: inference-only depth-map throughput (forward of both stacks, dropout off), CUDA graph replay
+    p = glorot_params(seed=1)
+    inf = {}
+    for bs in (1, 32, 512):
+        g = torch.Generator().manual_seed(bs)
+        im = torch.rand(bs, 480, 640, 3, generator=g).to(dev)
+        opi = models.msdn(im, torch.zeros(bs, 55, 73, 1, device=dev), train=False)
+        opi.net.load_params(p)
+        for _ in range(3):
+            opi.run()
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            opi.net.forward()
+        gr.replay()
+        ms = timed(gr.replay, 20)
+        tf = 4.110e9 * bs / ms / 1e9                      # BASELINE.md section 4: 4.110 GFLOP forward per image
+        inf[f"bs{bs}"] = {"latency_ms": ms, "images_per_s": bs / ms * 1e3, "tflops_algorithmic": tf,
+                          "frac_of_bf16_burst": tf / pk["bf16_tflops"]}
+        del opi, gr, im
+        torch.cuda.empty_cache()
+    out["msdn_inference"] = inf
+    # ---- config 4: DCNF train step, batch 16 (768 patches through the unary CNN, 16 CRF graphs, SGD)
+    g = torch.Generator().manual_seed(3)
+    im = torch.rand(16, 480, 640, 3, generator=g).to(dev)
+    dp = (torch.rand(16, 480, 640, 1, generator=g) * 0.95 + 0.05).to(dev)
+    opd = models.dcnf(im, dp, train=True)
+    pp = glorot_params(5, "dcnf")
+    pp["pairwise/pairwise_layers/dense/kernel"].abs_()
+    opd.net.load_params(pp)
+    for _ in range(2):
+        opd.run()
+    ms = timed(opd.run, 5)
+    tf = 3.0 * 2.672e9 * 768 / ms / 1e9                   # unary CNN forward + dgrad + wgrad (BASELINE.md section 4)
+    out["dcnf_train_bs16"] = {"ms_per_step": ms, "images_per_s": 16 / ms * 1e3, "tflops_algorithmic": tf,
+                              "frac_of_bf16_burst": tf / pk["bf16_tflops"], "crf_status_max": int(opd.net.status.max())}
+    del opd
+    torch.cuda.empty_cache()
+    return out
+
+
 def gpu_arm(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -463,6 +534,11 @@ def gpu_arm(args, rank, world, local_rank):
                 "e2e_u8": e2e_u8,
                 "gpu_launches": launches_per_step * args.steps,
                 "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu}
+        if world == 1 and not args.no_extra:
+            try:
+                line["other_configs"] = other_configs(torch, pk)
+            except Exception as e:                                   # never lose the headline line to an extra
+                line["other_configs"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
     if world > 1:
         # Leave without running destructors: NCCL communicator teardown at interpreter exit is collective and
@@ -480,6 +556,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="a3d", choices=["a3d", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the TF32 / inference / DCNF extra measurements")
     ap.add_argument("--ncu", action="store_true", help="profiling hook: cudaProfilerStart/Stop around two steps")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

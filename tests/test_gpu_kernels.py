@@ -187,36 +187,6 @@ def test_conv_fwd(ctx, layer, impl):
 LAYERS_BY_NAME = {l[0]: l for l in LAYERS}
 
 
-@pytest.mark.skipif(__import__("os").environ.get("A3D_TEST_PERSIST") != "1",
-                    reason="experimental persistent GEMM kernel (tc_persist.cuh): set A3D_TEST_PERSIST=1 A3D_PERSIST=1")
-@pytest.mark.parametrize("variant", [4, 5, 6])
-@pytest.mark.parametrize("bn", [64, 96, 128, 192, 256])
-@pytest.mark.parametrize("M", [300, 128 * 160 + 5, 128 * 700])
-def test_tc_gemm_persistent(ctx, variant, bn, M):
-    """persistent tile loop with double-buffered TMEM accumulators: 3 tiles (fewer than CTAs), 161 x n tiles (about one
-    per CTA) and 700 x n tiles (several per CTA: buffer reuse, stage-counter wrap-around across tiles)"""
-    N, K = 2 * bn - 8, 64 * 5
-    A = bf16_rand(M, K, seed=7)
-    B = bf16_rand(N, K, seed=8)
-    D = ctx.debug_tc_gemm(A, B, M, N, K, bn, 128, variant=variant)
-    assert rel_err(D, A.float() @ B.float().t()) < 2e-3
-
-
-@pytest.mark.skipif(__import__("os").environ.get("A3D_TEST_MCAST") != "1",
-                    reason="experimental cluster/multicast GEMM kernel (tc_mcast.cuh): set A3D_TEST_MCAST=1 A3D_MCAST=1")
-@pytest.mark.parametrize("variant", [7, 8, 9, 10])
-@pytest.mark.parametrize("bn", [64, 128, 256])
-@pytest.mark.parametrize("M", [100, 128 * 5 + 7, 128 * 301])
-def test_tc_gemm_multicast(ctx, variant, bn, M):
-    """weight tile multicast across a cluster of 2 / 4 CTAs along M: fewer tiles than one cluster (padding CTAs), a ragged
-    last cluster (6 tiles), many clusters; K = 9 k-blocks > ring depth"""
-    N, K = 2 * bn - 8, 64 * 9
-    A = bf16_rand(M, K, seed=7)
-    B = bf16_rand(N, K, seed=8)
-    D = ctx.debug_tc_gemm(A, B, M, N, K, bn, 128, variant=variant)
-    assert rel_err(D, A.float() @ B.float().t()) < 2e-3
-
-
 @pytest.mark.parametrize("variant", [11, 12])
 @pytest.mark.parametrize("bn", [64, 96, 128, 192, 256])
 @pytest.mark.parametrize("M", [100, 128 * 5 + 7, 128 * 300 + 1])
@@ -684,27 +654,6 @@ def test_conv_pool4_fwd_bwd(ctx, impl):
 @pytest.mark.parametrize("force", ["6", "7"])
 def test_conv_pool4_fwd_cta_pair(ctx, monkeypatch, force):
     """pool-fused fine/first GEMM through the CTA-pair kernel (short / deep ring) == one-CTA kernel, bit for bit"""
-    N, H, W, Cc = 3, 57, 76, 64
-    d = ops.conv_desc(N, H, W, Cc, 256, 3, 3, 1, "valid", ldy=64, impl=L.IMPL_AUTO)
-    x = bf16_rand(N, H, W, Cc, seed=40)
-    w = bf16_rand(256, 3, 3, Cc, seed=41, scale=1.0 / math.sqrt(9 * Cc))
-    bias = (torch.rand(64, generator=torch.Generator().manual_seed(42)) - 0.5).to(DEV) * 0.2
-    res = []
-    for f in ("0", force):
-        monkeypatch.setenv("A3D_POOL4_FORCE", f)
-        y = torch.full((N, d.P, d.Q, 64), 7.0, dtype=torch.bfloat16, device=DEV)
-        idx = torch.full((N, d.P, d.Q, 64), 9, dtype=torch.uint8, device=DEV)
-        ctx.conv2d_pool4_fwd(d, x, w, bias, relu=True, out=y, idx=idx)
-        res.append((y, idx))
-    monkeypatch.delenv("A3D_POOL4_FORCE")
-    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])     # same MMA order: bit-exact
-
-
-@pytest.mark.skipif(__import__("os").environ.get("A3D_TEST_MCAST") != "1",
-                    reason="experimental cluster/multicast GEMM kernel (tc_mcast.cuh): set A3D_TEST_MCAST=1 A3D_MCAST=1")
-@pytest.mark.parametrize("force", ["4", "5"])
-def test_conv_pool4_fwd_multicast(ctx, monkeypatch, force):
-    """pool-fused fine/first GEMM through the cluster kernel (weight tile multicast to 2 / 4 CTAs) == one-CTA kernel"""
     N, H, W, Cc = 3, 57, 76, 64
     d = ops.conv_desc(N, H, W, Cc, 256, 3, 3, 1, "valid", ldy=64, impl=L.IMPL_AUTO)
     x = bf16_rand(N, H, W, Cc, seed=40)
