@@ -54,6 +54,21 @@ SIGNATURES = {
     "a3d_dense_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _i, _vp, _i, _i, _i, _u, _i, _vp]),
     "a3d_dense_dgrad": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "a3d_stamp": (_i, [_vp, _vp, _vp]),
+    "a3d_msdn_workspace_bytes": (_sz, [_vp, _i, _i, _i, _i, _i, _i]),
+    "a3d_msdn_create": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp, C.POINTER(_vp)]),
+    "a3d_msdn_destroy": (_i, [_vp]),
+    "a3d_msdn_configure": (_i, [_vp, _f, C.c_uint64]),
+    "a3d_msdn_segment": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_i * 4)]),
+    "a3d_msdn_arena": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
+                            C.POINTER(_sz)]),
+    "a3d_msdn_sync_weights": (_i, [_vp, _vp]),
+    "a3d_msdn_set_step": (_i, [_vp, C.c_longlong, C.POINTER(_i * 4), _vp]),
+    "a3d_msdn_global_step": (C.c_longlong, [_vp]),
+    "a3d_msdn_step_begin": (_i, [_vp, _vp]),
+    "a3d_msdn_step_enqueue": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
+    "a3d_msdn_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "a3d_msdn_infer": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "a3d_msdn_losses": (_vp, [_vp]),
     "a3d_conv2d_ws_bytes_tf32": (_sz, [_vp, C.POINTER(ConvDesc), _i]),
     "a3d_conv2d_fwd_tf32": (_i, [_vp, C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _u, _vp, _sz, _vp]),
     "a3d_conv2d_dgrad_tf32": (_i, [_vp, C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

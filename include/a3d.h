@@ -374,6 +374,40 @@ int a3d_conv_k1_dgrad_f32(a3d_ctx*, const a3d_conv_desc*, const float* dy, const
 int a3d_conv_k1_wgrad_f32(a3d_ctx*, const a3d_conv_desc*, const float* x, const float* dy, float* dw, float* db,
                           void* stream);
 
+/* ---- model-level entry points: the whole MSDN step behind the C-ABI ---------------------------------
+ * A host in any language drives `session.run(model_op)` (src/ann3depth.py:126-127) for `models.msdn`
+ * (src/models.py:203-367) with these calls alone.  The caller owns ONE device buffer of a3d_msdn_workspace_bytes() that
+ * the net carves into parameter arena (f32 master / gradients / Adam m, v / bf16 mirror; segment table =
+ * a3d_msdn_segment, packed layouts of ann3depth_b200/params.py), activations and scratch.  Sequential single-stream
+ * schedule, BF16 storage; forward of both stacks + both losses, backward + TF-Adam of the active tf.case branch
+ * (phase 1 coarse / 2 fine / 3 idle by global_step, src/models.py:301-364), global_step += 1. */
+typedef struct a3d_msdn a3d_msdn;
+size_t a3d_msdn_workspace_bytes(a3d_ctx*, int batch, int in_h, int in_w, int depth_h, int depth_w, int train);
+int a3d_msdn_create(a3d_ctx*, int batch, int in_h, int in_w, int depth_h, int depth_w, int train, void* workspace,
+                    size_t workspace_bytes, void* stream, a3d_msdn** out);
+int a3d_msdn_destroy(a3d_msdn*);
+/* beta2 of the four AdamOptimizers (src/models.py:309 passes 1: the default) and the dropout seed */
+int a3d_msdn_configure(a3d_msdn*, float adam_beta2, uint64_t dropout_seed);
+/* segment `index` of the arena: TF variable name, element offset, element count, packed shape; returns the segment count */
+int a3d_msdn_segment(const a3d_msdn*, int index, const char** name, size_t* offset, size_t* numel, int shape[4]);
+/* device pointers of the arena buffers (each `total` elements); after writing `w` call a3d_msdn_sync_weights */
+int a3d_msdn_arena(a3d_msdn*, float** w, float** m, float** v, float** g, uint16_t** w_bf16, size_t* total);
+int a3d_msdn_sync_weights(a3d_msdn*, void* stream);
+int a3d_msdn_set_step(a3d_msdn*, long long global_step, const int adam_t[4], void* stream);
+long long a3d_msdn_global_step(const a3d_msdn*);
+/* one step = host half (counters, Adam step sizes -> device scalars; returns the phase, < 0 on error) + device half
+ * (kernel launches only: capturable in a CUDA graph, one graph per phase).  a3d_msdn_step does both and copies the two
+ * losses (coarse, fine) to `losses` (device, nullable).  images f32 [B,in_h,in_w,3], depths f32 [B,depth_h,depth_w,1],
+ * keep_mask u8 [B,4096] or NULL (device RNG, Bernoulli(0.5) per (seed, global_step)). */
+int a3d_msdn_step_begin(a3d_msdn*, void* stream);
+int a3d_msdn_step_enqueue(a3d_msdn*, int phase, const float* images, const float* depths, const uint8_t* keep_mask,
+                          void* stream);
+int a3d_msdn_step(a3d_msdn*, const float* images, const float* depths, const uint8_t* keep_mask, float* losses,
+                  void* stream);
+/* inference (dropout off): fine / coarse depth maps f32 [B,55,74] (device, nullable) */
+int a3d_msdn_infer(a3d_msdn*, const float* images, float* fine, float* coarse, void* stream);
+const float* a3d_msdn_losses(const a3d_msdn*);
+
 #ifdef __cplusplus
 }
 #endif
