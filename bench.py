@@ -82,6 +82,25 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
+def bind_to_gpu_numa(index):
+    """Best effort: run this rank on the CPUs next to its GPU (NVML's ideal affinity), so that the pinned input buffers
+    it allocates afterwards are first-touched on the GPU's own memory node.  Returns the CPU list or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [w * 64 + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        cpus = [c for c in cpus if c < os.cpu_count()]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 def synthetic_batch(rank, torch):
     g = torch.Generator().manual_seed(100 + rank)
     images = torch.rand(BATCH, 480, 640, 3, generator=g)
@@ -296,6 +315,10 @@ def gpu_arm(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
+    if world > 1 and os.environ.get("A3D_NUMA_BIND", "1") != "0":
+        # pinned host batches next to the GPU: e2e at N GPUs is bound by what the host can feed (tools/h2d_ceiling.py).
+        # Single-GPU runs stay unbound: the same process times the CPU baseline on ALL host cores.
+        bind_to_gpu_numa(local_rank)
     comm = None
     ctx = models.get_context(local_rank)
     if world > 1:
