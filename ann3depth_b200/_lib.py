@@ -54,6 +54,19 @@ SIGNATURES = {
     "a3d_dense_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _i, _vp, _i, _i, _i, _u, _i, _vp]),
     "a3d_dense_dgrad": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "a3d_stamp": (_i, [_vp, _vp, _vp]),
+    "a3d_pairwise_dense_act": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _u, _vp]),
+    "a3d_pairwise_dense_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _u, _vp]),
+    "a3d_dcnf_workspace_bytes": (_sz, [_vp, _i, _i, _i, _i, _i, _i]),
+    "a3d_dcnf_create": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp, C.POINTER(_vp)]),
+    "a3d_dcnf_destroy": (_i, [_vp]),
+    "a3d_dcnf_configure": (_i, [_vp, _i]),
+    "a3d_dcnf_segment": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_i * 4)]),
+    "a3d_dcnf_arena": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_sz)]),
+    "a3d_dcnf_sync_weights": (_i, [_vp, _vp]),
+    "a3d_dcnf_global_step": (C.c_longlong, [_vp]),
+    "a3d_dcnf_step": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "a3d_dcnf_infer": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "a3d_dcnf_state": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "a3d_msdn_workspace_bytes": (_sz, [_vp, _i, _i, _i, _i, _i, _i]),
     "a3d_msdn_create": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp, C.POINTER(_vp)]),
     "a3d_msdn_destroy": (_i, [_vp]),

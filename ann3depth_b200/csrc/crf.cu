@@ -323,6 +323,50 @@ extern "C" int a3d_pairwise_dense(a3d_ctx* ctx, const float* sims, const float* 
   return 0;
 }
 
+// ---- beyond the reference: a non-negative pairwise potential (A = I + D - R is SPD for every r >= 0;
+// the reference's unconstrained linear layer, src/models.py:92-93, can leave the SPD cone) and the gradient INTO the
+// pairwise layer (TF 1.3 blocks it at ScatterNdUpdate; the CRF kernel's `dr` output is the gradient w.r.t. r).
+//   fwd: r = act(sims . w + b), act = max(., 0) with A3D_EPI_RELU, identity otherwise
+//   bwd: dw[j] = sum_i dr[i] act'(r[i]) sims[i][j], db = sum_i dr[i] act'(r[i])        (one block, n = B * n_pairs is small)
+__global__ void pairwise_dense_act_kernel(const float* __restrict__ sims, const float* __restrict__ w, const float* __restrict__ b,
+                                          float* __restrict__ r, size_t n, unsigned flags) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float v = sims[2 * i] * w[0] + sims[2 * i + 1] * w[1] + b[0];
+    if (flags & A3D_EPI_RELU) v = fmaxf(v, 0.f);
+    r[i] = v;
+  }
+}
+extern "C" int a3d_pairwise_dense_act(a3d_ctx* ctx, const float* sims, const float* w2, const float* b1, float* r, size_t n,
+                                      unsigned flags, void* stream) {
+  A3D_REQUIRE(ctx && sims && w2 && b1 && r, "pairwise_dense_act: null argument");
+  pairwise_dense_act_kernel<<<ceil_div((long long)n, 256), 256, 0, as_stream(stream)>>>(sims, w2, b1, r, n, flags);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+__global__ void pairwise_dense_bwd_kernel(const float* __restrict__ sims, const float* __restrict__ r, const float* __restrict__ dr,
+                                          float* __restrict__ dw2, float* __restrict__ db1, int n, unsigned flags) {
+  __shared__ float red[32];
+  float s0 = 0.f, s1 = 0.f, sb = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float g = dr[i];
+    if ((flags & A3D_EPI_RELU) && !(r[i] > 0.f)) g = 0.f;
+    s0 += g * sims[2 * i];
+    s1 += g * sims[2 * i + 1];
+    sb += g;
+  }
+  s0 = block_sum(s0, red); __syncthreads();
+  s1 = block_sum(s1, red); __syncthreads();
+  sb = block_sum(sb, red);
+  if (threadIdx.x == 0) { dw2[0] = s0; dw2[1] = s1; db1[0] = sb; }
+}
+extern "C" int a3d_pairwise_dense_bwd(a3d_ctx* ctx, const float* sims, const float* r, const float* dr, float* dw2, float* db1,
+                                      size_t n, unsigned flags, void* stream) {
+  A3D_REQUIRE(ctx && sims && r && dr && dw2 && db1 && n > 0 && n < (1u << 30), "pairwise_dense_bwd: bad argument");
+  pairwise_dense_bwd_kernel<<<1, 256, 0, as_stream(stream)>>>(sims, r, dr, dw2, db1, (int)n, flags);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
 __global__ void mean_f32_kernel(const float* __restrict__ v, int n, float* __restrict__ out) {
   __shared__ float red[32];
   float s = 0.f;

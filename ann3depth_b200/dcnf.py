@@ -31,6 +31,20 @@ def num_superpixels(h=H, w=W):
     return math.ceil(h / SP), math.ceil(w / SP)
 
 
+def grid4_pairs(h=H, w=W):
+    """Beyond the reference: every horizontal and vertical neighbour pair of the tile grid, once each
+    (82 pairs on the 6 x 8 grid: #pairs != #nodes, which the reference's R sizing, src/models.py:149, cannot express)."""
+    rows, cols = num_superpixels(h, w)
+    left, right = [], []
+    for r in range(rows):
+        for c in range(cols):
+            if c + 1 < cols:
+                left.append(r * cols + c); right.append(r * cols + c + 1)
+            if r + 1 < rows:
+                left.append(r * cols + c); right.append((r + 1) * cols + c)
+    return left, right
+
+
 def pair_indices(h=H, w=W):
     """src/models.py:20-30."""
     max_rows, max_cols = num_superpixels(h, w)
@@ -46,16 +60,29 @@ def pair_indices(h=H, w=W):
 
 class DCNFNet:
     def __init__(self, ctx: ops.Context, batch: int, in_hw=(480, 640), depth_hw=(480, 640), train=True,
-                 impl=L.IMPL_AUTO, naive_loss=True, comm=None):
+                 impl=L.IMPL_AUTO, naive_loss=True, comm=None, graph="reference", r_nonneg=False, train_pairwise=False,
+                 predict="unary"):
+        """Beyond-reference options (defaults reproduce the reference):
+             graph="grid4"        every neighbour pair of the tile grid (82 pairs != 48 nodes) instead of the reference's
+                                  checkerboard star graph (src/models.py:20-30);
+             r_nonneg=True        r = max(pairwise_dense(.), 0): A = I + D - R stays SPD whatever the layer learns;
+             train_pairwise=True  the CRF's gradient w.r.t. r flows into `pairwise_layers` (TF 1.3 blocks it at
+                                  ScatterNdUpdate, src/models.py:138-141) and SGD updates that layer too;
+             predict="map"        the output is the CRF's MAP estimate y* = A^-1 z (Liu et al. eq. 12), bilinearly upsampled,
+                                  instead of the unary prediction the reference upsamples (src/models.py:187-191)."""
         self.ctx, self.B, self.train, self.impl, self.naive = ctx, batch, train, impl, naive_loss
+        assert graph in ("reference", "grid4") and predict in ("unary", "map")
+        self.r_nonneg, self.train_pairwise, self.predict = r_nonneg, train_pairwise, predict
         self.dev = torch.device(f"cuda:{ctx.device}")
         self.comm = comm
         self.arena = Arena(dcnf_specs(), self.dev, with_adam=False)
         self.global_step = 0
         rows, cols = num_superpixels()
         self.n = rows * cols
-        pl, pr = pair_indices()
-        assert len(pl) == self.n, "the reference sizes R by #pairs, valid only when #pairs == #nodes (src/models.py:149)"
+        pl, pr = pair_indices() if graph == "reference" else grid4_pairs()
+        if graph == "reference":
+            assert len(pl) == self.n, "the reference sizes R by #pairs, valid only when #pairs == #nodes (src/models.py:149)"
+        self.n_pairs = len(pl)
         self.pl = torch.tensor(pl, dtype=torch.int32, device=self.dev)
         self.pr = torch.tensor(pr, dtype=torch.int32, device=self.dev)
         B, NP = batch, batch * self.n
@@ -85,8 +112,9 @@ class DCNFNet:
         self.h0 = z(NP, 128, **bf)
         self.h1 = z(NP, 16, **bf)
         self.z = z(NP, 1, **f32)
-        self.sims = z(B, self.n, 2, **f32)
-        self.r = z(B, self.n, **f32)
+        self.sims = z(B, self.n_pairs, 2, **f32)
+        self.r = z(B, self.n_pairs, **f32)
+        self.dr = z(B, self.n_pairs, **f32) if (train and train_pairwise) else None
         self.y = z(B, self.n, **f32)
         self.ystar, self.nll, self.logdet = z(B, self.n, **f32), z(B, **f32), z(B, **f32)
         self.status = torch.zeros(B, dtype=torch.int32, device=self.dev)
@@ -150,22 +178,30 @@ class DCNFNet:
         # pairwise part (src/models.py:108-127)
         c.pairwise_features(self.im, self.pl, self.pr, GAMMA, out=self.sims)
         P = "pairwise/pairwise_layers/dense"
-        c.pairwise_dense(self.sims, self.wf(P + K), self.wf(P + "/bias"), out=self.r)
+        if self.r_nonneg:
+            c.pairwise_dense_act(self.sims, self.wf(P + K), self.wf(P + "/bias"), flags=L.EPI_RELU, out=self.r)
+        else:
+            c.pairwise_dense(self.sims, self.wf(P + K), self.wf(P + "/bias"), out=self.r)
         # loss part (src/models.py:129-177)
         c.tile_means(self.dp, out=self.y)
         c.crf(self.z.view(B, self.n), self.y, self.r, self.pl, self.pr, grad_scale=1.0 / B, naive=self.naive,
               out=dict(ystar=self.ystar, nll=self.nll, logdet=self.logdet, dz=self.dz if self.train else None,
-                       status=self.status))
+                       dr=self.dr, status=self.status))
         c.mean_f32(self.nll, self.loss)
         # output (src/models.py:187-191): the unary prediction, upsampled
         rows, cols = num_superpixels()
-        c.resize_bilinear_tf1(self.z.view(B, rows, cols, 1), H, W, out=self.output)
+        src = self.ystar if self.predict == "map" else self.z
+        c.resize_bilinear_tf1(src.view(B, rows, cols, 1), H, W, out=self.output)
 
     # ------------------------------------------------------------------ backward (unary CNN only)
     def backward(self):
         c, NP = self.ctx, self.NP
         U, K = "unary/unary_layers/", "/kernel"
         hook = self.comm.bucket_ready if self.comm else (lambda *_: None)
+        if self.train_pairwise:
+            P = "pairwise/pairwise_layers/dense"
+            c.pairwise_dense_bwd(self.sims, self.r, self.dr, self.gw(P + K), self.gw(P + "/bias"),
+                                 flags=L.EPI_RELU if self.r_nonneg else 0)
         c.scale_cast_bf16(self.dz.view(-1), self.g_z.view(-1), 1.0)
         S = L.IMPL_SIMT
         c.dense_wgrad(self.h1, self.g_z, dw=self.gw(U + "dense_2" + K), db=self.gw(U + "dense_2/bias"), N=1, impl=S)
@@ -204,6 +240,10 @@ class DCNFNet:
             scale = 1.0 / self.comm.world
         lo, hi = self.arena.group_range("SGD")
         self.ctx.sgd(self.arena.w[lo:hi], self.arena.g[lo:hi], self.arena.wb[lo:hi], SGD_LR, scale)
+        if self.train_pairwise:
+            assert not self.comm, "train_pairwise is a single-GPU option"
+            lo, hi = self.arena.group_range("Pairwise")
+            self.ctx.sgd(self.arena.w[lo:hi], self.arena.g[lo:hi], self.arena.wb[lo:hi], SGD_LR, 1.0)
         self.global_step += 1
         return 1
 

@@ -504,6 +504,20 @@ class Context:
                 "pairwise_dense")
         return out
 
+    def pairwise_dense_act(self, sims, w2, b1, flags=0, out=None):
+        """r = act(sims . w + b); flags = EPI_RELU clamps r at 0 (beyond the reference: keeps the CRF matrix SPD)."""
+        n = sims.numel() // 2
+        if out is None:
+            out = torch.empty(sims.shape[:-1], dtype=torch.float32, device=sims.device)
+        L.check(self.lib.a3d_pairwise_dense_act(self.h, _ptr(sims), _ptr(w2), _ptr(b1), _ptr(out), n, flags, _stream()),
+                "pairwise_dense_act")
+        return out
+
+    def pairwise_dense_bwd(self, sims, r, dr, dw2, db1, flags=0):
+        """gradient of the 2 -> 1 pairwise layer from the CRF's dr (beyond the reference)"""
+        L.check(self.lib.a3d_pairwise_dense_bwd(self.h, _ptr(sims), _ptr(r), _ptr(dr), _ptr(dw2), _ptr(db1), r.numel(), flags,
+                                                _stream()), "pairwise_dense_bwd")
+
     def mean_f32(self, v, out):
         L.check(self.lib.a3d_mean_f32(self.h, _ptr(v), v.numel(), _ptr(out), _stream()), "mean")
         return out

@@ -303,6 +303,13 @@ int a3d_pairwise_features(a3d_ctx*, const float* images, int B, int H, int W, co
 /* The 2 -> 1 `pairwise_dense` layer (src/models.py:91-93): r[i] = sims[i,0]*w[0] + sims[i,1]*w[1] + b[0]. */
 int a3d_pairwise_dense(a3d_ctx*, const float* sims, const float* w2, const float* b1, float* r, size_t n,
                        void* stream);
+/* Beyond the reference: r = act(sims . w + b) with act = max(., 0) for A3D_EPI_RELU (keeps A = I + D - R
+ * SPD; the reference's layer is unconstrained, src/models.py:92-93), and the gradient into the pairwise layer from the CRF
+ * kernel's dr (TF 1.3 blocks it): dw2[j] = sum_i dr[i] act'(r[i]) sims[i][j], db1 = sum_i dr[i] act'(r[i]). */
+int a3d_pairwise_dense_act(a3d_ctx*, const float* sims, const float* w2, const float* b1, float* r, size_t n,
+                           unsigned flags, void* stream);
+int a3d_pairwise_dense_bwd(a3d_ctx*, const float* sims, const float* r, const float* dr, float* dw2, float* db1, size_t n,
+                           unsigned flags, void* stream);
 /* out[0] = mean(v[0..n)) (tf.reduce_mean of per-sample losses, src/models.py:174,272). */
 int a3d_mean_f32(a3d_ctx*, const float* v, int n, float* out, void* stream);
 /* f32 -> bf16 with scaling: dst[i] = bf16(scale * src[i]). */
@@ -407,6 +414,26 @@ int a3d_msdn_step(a3d_msdn*, const float* images, const float* depths, const uin
 /* inference (dropout off): fine / coarse depth maps f32 [B,55,74] (device, nullable) */
 int a3d_msdn_infer(a3d_msdn*, const float* images, float* fine, float* coarse, void* stream);
 const float* a3d_msdn_losses(const a3d_msdn*);
+
+/* ---- the whole DCNF step behind the C-ABI (models.dcnf, src/models.py:9-200): counterpart of a3d_msdn_* ---------------
+ * Caller-owned workspace; arena = f32 master / gradients / bf16 mirror (plain SGD: no optimizer slots), segment table and
+ * packed layouts of ann3depth_b200/params.py dcnf_specs().  a3d_dcnf_step = forward (resize, patches, unary CNN on B*48
+ * patches, pairwise features, CRF NLL) + backward through the unary CNN + SGD lr 0.1; kernel launches only (capturable). */
+typedef struct a3d_dcnf a3d_dcnf;
+size_t a3d_dcnf_workspace_bytes(a3d_ctx*, int batch, int in_h, int in_w, int depth_h, int depth_w, int train);
+int a3d_dcnf_create(a3d_ctx*, int batch, int in_h, int in_w, int depth_h, int depth_w, int train, void* workspace,
+                    size_t workspace_bytes, void* stream, a3d_dcnf** out);
+int a3d_dcnf_destroy(a3d_dcnf*);
+int a3d_dcnf_configure(a3d_dcnf*, int naive_loss);   /* 1 (default): the reference's exp(-E)/Z form; 0: stable closed form */
+int a3d_dcnf_segment(const a3d_dcnf*, int index, const char** name, size_t* offset, size_t* numel, int shape[4]);
+int a3d_dcnf_arena(a3d_dcnf*, float** w, float** g, uint16_t** w_bf16, size_t* total);
+int a3d_dcnf_sync_weights(a3d_dcnf*, void* stream);
+long long a3d_dcnf_global_step(const a3d_dcnf*);
+int a3d_dcnf_step(a3d_dcnf*, const float* images, const float* depths, float* loss, void* stream);
+/* output f32 [B,240,320] (upsampled unary prediction), z f32 [B,48], r f32 [B,48]; device, nullable */
+int a3d_dcnf_infer(a3d_dcnf*, const float* images, float* output, float* z, float* r, void* stream);
+/* device pointers into the net: CRF MAP estimate y* = A^-1 z [B,48], per-graph Cholesky status, the loss scalar */
+int a3d_dcnf_state(a3d_dcnf*, const float** ystar, const int32_t** status, const float** loss);
 
 #ifdef __cplusplus
 }

@@ -221,3 +221,70 @@ def test_pure_c_host_runs_a_step():
     print(r.stdout, r.stderr)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     assert "a3d_msdn_step: phase 1 global_step 1" in r.stdout
+
+
+def test_c_dcnf_step_equals_python_step():
+    """a3d_dcnf_create / _step / _infer over ctypes alone == the Python host's DCNF step (same kernels) and the oracle's
+    loss on the same z (src/models.py:129-200)."""
+    from ann3depth_b200.params import dcnf_specs
+    from oracle import dcnf as OD
+    lib = L.load()
+    h = models.get_context(0).h
+    B = 2
+    g = torch.Generator().manual_seed(3)
+    images = torch.rand(B, 480, 640, 3, generator=g).to(DEV)
+    depths = (torch.rand(B, 480, 640, 1, generator=g) * 0.95 + 0.05).to(DEV)
+    p = OD.init_params(5, torch.float32, bias_range=0.05, pairwise_nonneg=True)
+    a = Arena(dcnf_specs(), "cpu", with_adam=False)
+    a.load_tf(p)
+    nbytes = lib.a3d_dcnf_workspace_bytes(h, B, 480, 640, 480, 640, 1)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    net = C.c_void_p()
+    L.check(lib.a3d_dcnf_create(h, B, 480, 640, 480, 640, 1, C.c_void_p(ws.data_ptr()), nbytes, None, C.byref(net)), "dcnf_create")
+    L.check(lib.a3d_dcnf_configure(net, 0), "dcnf_configure")                  # stable loss form
+    # segment table == the Python arena
+    nseg = lib.a3d_dcnf_segment(net, -1, None, None, None, None)
+    names = []
+    for i in range(nseg):
+        name, off, numel, shape = C.c_char_p(), C.c_size_t(), C.c_size_t(), (C.c_int * 4)()
+        lib.a3d_dcnf_segment(net, i, C.byref(name), C.byref(off), C.byref(numel), C.byref(shape))
+        s = a.specs[name.value.decode()]
+        assert (off.value, numel.value, tuple(x for x in shape if x)) == (s.offset, s.numel, tuple(s.packed_shape))
+        names.append(name.value.decode())
+    assert names == list(a.specs)
+    w_ptr, g_ptr, wb_ptr, total = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_size_t()
+    L.check(lib.a3d_dcnf_arena(net, C.byref(w_ptr), C.byref(g_ptr), C.byref(wb_ptr), C.byref(total)), "dcnf_arena")
+    assert total.value == a.total
+
+    def view(ptr):
+        off = ptr.value - ws.data_ptr()
+        return ws[off:off + total.value * 4].view(torch.float32)
+    view(w_ptr).copy_(a.w)
+    L.check(lib.a3d_dcnf_sync_weights(net, None), "sync")
+    loss = torch.zeros(1, device=DEV)
+    L.check(lib.a3d_dcnf_step(net, C.c_void_p(images.data_ptr()), C.c_void_p(depths.data_ptr()), C.c_void_p(loss.data_ptr()),
+                              None), "dcnf_step")
+    torch.cuda.synchronize()
+    assert lib.a3d_dcnf_global_step(net) == 1
+    # Python host, same kernels
+    op = models.dcnf(images.clone(), depths.clone(), train=True, naive_loss=False)
+    op.net.load_params(p)
+    op.run()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(op.net.loss)) <= 1e-4 * max(1.0, abs(float(op.net.loss)))
+    lo, hi = a.group_range("SGD")
+    assert cos(view(g_ptr)[lo:hi], op.net.arena.g[lo:hi]) > 0.9999
+    assert cos(view(w_ptr)[lo:hi] - a.w[lo:hi].to(DEV), op.net.arena.w[lo:hi] - a.w[lo:hi].to(DEV)) > 0.9999
+    lo, hi = a.group_range("Pairwise")
+    assert torch.equal(view(w_ptr)[lo:hi], a.w[lo:hi].to(DEV))                  # no gradient reaches the pairwise layer
+    # inference outputs
+    out = torch.empty(B, 240, 320, device=DEV)
+    z = torch.empty(B, 48, device=DEV)
+    r = torch.empty(B, 48, device=DEV)
+    L.check(lib.a3d_dcnf_infer(net, C.c_void_p(images.data_ptr()), C.c_void_p(out.data_ptr()), C.c_void_p(z.data_ptr()),
+                               C.c_void_p(r.data_ptr()), None), "dcnf_infer")
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(out).all()) and float((r - op.net.r).abs().max()) < 1e-5
+    ref_out = OD.T.resize_bilinear_tf1(z.cpu().double().reshape(B, 6, 8, 1), 240, 320)
+    assert float((out.cpu().double() - ref_out.reshape(B, 240, 320)).abs().max()) < 1e-5
+    lib.a3d_dcnf_destroy(net)

@@ -91,3 +91,57 @@ def test_dcnf_train_step_sgd_and_naive_loss():
     naive = float(OD.nll_naive(A, yy, zz))
     print("naive loss", float(net.loss), "oracle", naive)
     assert abs(float(net.loss) - naive) < 1e-3 * max(1.0, abs(naive))
+
+
+def test_dcnf_beyond_reference_options():
+    """SURVEY.md 8f N4 (none of this exists in the reference, src/models.py:129-191): a grid with #pairs != #nodes, the
+    r >= 0 constraint, the MAP estimate y* = A^-1 z as the prediction, and the gradient INTO the pairwise layer -- against
+    float64 linear algebra / autograd on the same z, y and similarities."""
+    from ann3depth_b200.dcnf import grid4_pairs
+    B = 2
+    images, depths, p = make(B, seed=6)
+    P = "pairwise/pairwise_layers/dense"
+    p[P + "/kernel"] = torch.tensor([[0.8], [-0.9]])            # mixed signs: the clamp at 0 is exercised
+    p[P + "/bias"] = torch.tensor([0.02])
+    op = models.dcnf(images.to(DEV), depths.to(DEV), train=True, naive_loss=False, graph="grid4", r_nonneg=True,
+                     train_pairwise=True, predict="map")
+    net = op.net
+    net.load_params(p)
+    assert net.n_pairs == 82 and net.n == 48
+    net.forward()
+    net.backward()
+    torch.cuda.synchronize()
+    sims = net.sims.cpu().double()                               # [B,82,2]
+    z = net.z.view(B, 48, 1).cpu().double()
+    y = net.y.view(B, 48, 1).cpu().double()
+    w = p[P + "/kernel"].double().reshape(2).requires_grad_(True)
+    b = p[P + "/bias"].double().requires_grad_(True)
+    pl, pr = grid4_pairs()
+
+    def build(rv):
+        R = torch.zeros(B, 48, 48, dtype=torch.float64)
+        R = R.index_put((torch.arange(B)[:, None], torch.tensor(pl)[None], torch.tensor(pr)[None]), rv)
+        R = R.index_put((torch.arange(B)[:, None], torch.tensor(pr)[None], torch.tensor(pl)[None]), rv)
+        return torch.eye(48, dtype=torch.float64) + torch.diag_embed(R.sum(2)) - R
+    r_ref = torch.relu(sims @ w + b)
+    assert float((net.r.cpu().double() - r_ref.detach()).abs().max()) < 1e-6
+    assert float(r_ref.min()) == 0.0 and float(r_ref.max()) > 0.0        # both branches of the clamp occur
+    A = build(r_ref)
+    loss = OD.nll_stable(A, y, z)
+    gw, gb = torch.autograd.grad(loss, [w, b])
+    assert int(net.status.abs().max()) == 0
+    ystar = torch.linalg.solve(A.detach(), z).reshape(B, 48)
+    assert float((net.ystar.cpu().double() - ystar).abs().max()) < 1e-5          # north star: CRF solve 1e-5
+    assert abs(float(net.loss) - float(loss)) < 1e-4 * max(1.0, abs(float(loss)))
+    out = OD.T.resize_bilinear_tf1(ystar.reshape(B, 6, 8, 1), 240, 320)
+    assert float((net.output.cpu().double() - out).abs().max()) < 1e-4           # the prediction is the upsampled MAP
+    got = net.export_grads()
+    print("pairwise grads", got[P + "/kernel"].reshape(-1).tolist(), gw.tolist(), got[P + "/bias"].tolist(), gb.tolist())
+    assert float((got[P + "/kernel"].double().reshape(2) - gw).abs().max()) < 1e-3 * max(1e-3, float(gw.abs().max()))
+    assert abs(float(got[P + "/bias"]) - float(gb)) < 1e-3 * max(1e-3, abs(float(gb)))
+    w0 = net.arena.w.clone()
+    op.run()
+    torch.cuda.synchronize()
+    lo, hi = net.arena.group_range("Pairwise")
+    assert torch.allclose(net.arena.w[lo:hi], w0[lo:hi] - 0.1 * net.arena.g[lo:hi], atol=1e-7)
+    assert not torch.equal(net.arena.w[lo:hi], w0[lo:hi])
