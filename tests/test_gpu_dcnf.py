@@ -100,9 +100,14 @@ def test_dcnf_beyond_reference_options():
     from ann3depth_b200.dcnf import grid4_pairs
     B = 2
     images, depths, p = make(B, seed=6)
+    # tile-wise nearly constant colours: neighbouring tiles differ by ~0.02 per channel, so the colour similarity
+    # exp(-||mean_l - mean_r||_2) over the 1600 tile pixels lands in (0.2, 0.9) instead of underflowing to 0
+    g = torch.Generator().manual_seed(16)
+    tiles = 0.5 + 0.03 * torch.rand(B, 6, 8, 3, generator=g)
+    images = tiles.repeat_interleave(80, 1).repeat_interleave(80, 2).contiguous()
     P = "pairwise/pairwise_layers/dense"
-    p[P + "/kernel"] = torch.tensor([[0.8], [-0.9]])            # mixed signs: the clamp at 0 is exercised
-    p[P + "/bias"] = torch.tensor([0.02])
+    p[P + "/kernel"] = torch.tensor([[0.8], [-0.9]])            # mixed signs ...
+    p[P + "/bias"] = torch.tensor([-0.35])                      # ... and an offset: the clamp at 0 is exercised
     op = models.dcnf(images.to(DEV), depths.to(DEV), train=True, naive_loss=False, graph="grid4", r_nonneg=True,
                      train_pairwise=True, predict="map")
     net = op.net
@@ -125,6 +130,7 @@ def test_dcnf_beyond_reference_options():
         return torch.eye(48, dtype=torch.float64) + torch.diag_embed(R.sum(2)) - R
     r_ref = torch.relu(sims @ w + b)
     assert float((net.r.cpu().double() - r_ref.detach()).abs().max()) < 1e-6
+    print("r range", float(r_ref.min()), float(r_ref.max()), "clamped fraction", float((r_ref == 0).double().mean()))
     assert float(r_ref.min()) == 0.0 and float(r_ref.max()) > 0.0        # both branches of the clamp occur
     A = build(r_ref)
     loss = OD.nll_stable(A, y, z)
