@@ -222,11 +222,12 @@ class DataParallel:
         a, c, n = net.arena, self.ctx, self.world
         publish_now = set(os.environ.get("A3D_DP_PUBLISH_NOW", "dense_1").split(","))
         B = layers[0][2].shape[0]
-        # Gathered batch <= 64 rows: the mma.sync row kernel forms the gradient in registers and applies TF-Adam in the
-        # same pass (26 B/param).  Beyond that its per-row-tile reload of x outweighs the fusion (8 GPUs, batch 256: 0.22
-        # of the HBM roofline, 112 us for this rank's slice of dense_0), so the slice's gradient comes from the tcgen05
-        # GEMM (f32, L2-resident: 25 MB) followed by the streaming TF-Adam pass.
-        use_gemm = n * B > int(os.environ.get("A3D_DP_ROWS_MAX_BATCH", "64"))
+        # The slice's gradient comes from the tcgen05 wgrad GEMM (f32) followed by the streaming TF-Adam pass (34 B/param;
+        # 0.77-0.91 of the HBM roofline at 8 / 4 / 2 GPUs).  The mma.sync row kernel that forms the gradient in registers
+        # and applies TF-Adam in the same pass (a3d_dense_wgrad_adam_rows, 26 B/param) reloads x per row tile: 0.49 of the
+        # roofline at a gathered batch of 64, 0.22 at 256 -- measured slower in the step at every world size (2 GPUs: 1.096 vs
+        # 1.047 ms); A3D_DP_ROWS_MAX_BATCH=<rows> selects it for gathered batches up to that size.
+        use_gemm = n * B > int(os.environ.get("A3D_DP_ROWS_MAX_BATCH", "0"))
         bufs = getattr(self, "_gbufs", None)
         if bufs is None:
             bufs = self._gbufs = {}
