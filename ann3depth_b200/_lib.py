@@ -98,6 +98,11 @@ SIGNATURES = {
     "a3d_pool4_bwd_f32": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     "a3d_bias_grad_f32": (_i, [_vp, _vp, _sz, _i, _i, _vp, _vp]),
     "a3d_scatter_f32": (_i, [_vp, _vp, _vp, _i, _sz, _vp, _vp]),
+    "a3d_split_tf32": (_i, [_vp, _vp, _sz, _i, C.c_longlong, _vp, _vp, _vp]),
+    "a3d_conv2d_ws_bytes_tf32x3": (_sz, [_vp, C.POINTER(ConvDesc)]),
+    "a3d_conv2d_fwd_tf32x3": (_i, [_vp, C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _u, _vp, _sz, _vp]),
+    "a3d_dense_ws_bytes_tf32x3": (_sz, [_i, _i, _i]),
+    "a3d_dense_fwd_tf32x3": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _vp, _sz, _i, _i, _i, _u, _vp]),
     "a3d_conv_k1_fwd_f32": (_i, [_vp, C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _u, _vp]),
     "a3d_conv_k1_dgrad_f32": (_i, [_vp, C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp]),
     "a3d_conv_k1_wgrad_f32": (_i, [_vp, C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp]),

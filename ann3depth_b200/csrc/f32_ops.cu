@@ -461,3 +461,34 @@ extern "C" int a3d_conv_k1_wgrad_f32(a3d_ctx* ctx, const a3d_conv_desc* d, const
   A3D_LAUNCH_OK(ctx);
   return 0;
 }
+
+// ---- 3xTF32 operand split ---------------------------------------------------------------------------------------
+// hi = x rounded to TF32 (10 mantissa bits, cvt.rna), lo = x - hi (exact in float32; |lo| <= 2^-11 |x|).  The tensor core
+// then sees hi unchanged and lo to 10 more bits, so  hi_a.hi_b + hi_a.lo_b + lo_a.hi_b  carries ~21 mantissa bits of a.b.
+// Rows may be pitched (ld floats between rows, `cols` used per row); hi / lo are written densely ([rows][cols]).
+__global__ void split_tf32_kernel(const float* __restrict__ x, size_t rows, int cols, long long ld, float* __restrict__ hi,
+                                  float* __restrict__ lo) {
+  const size_t n = rows * (size_t)cols;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / cols;
+    const int c = (int)(i - r * cols);
+    const float v = x[r * ld + c];
+    uint32_t hb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+    const float h = __uint_as_float(hb);
+    hi[i] = h;
+    lo[i] = v - h;
+  }
+}
+
+extern "C" int a3d_split_tf32(a3d_ctx* ctx, const float* x, size_t rows, int cols, long long ld, float* hi, float* lo,
+                              void* stream) {
+  A3D_REQUIRE(ctx && x && hi && lo && cols > 0 && ld >= cols, "split_tf32: bad argument");
+  if (!rows) return 0;
+  const size_t n = rows * (size_t)cols;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > (size_t)ctx->sm_count * 16) blocks = (size_t)ctx->sm_count * 16;
+  split_tf32_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(x, rows, cols, ld, hi, lo);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}

@@ -374,6 +374,12 @@ int finish(a3d_ctx* ctx, const float* acc, const float* bias, const uint8_t* mas
 
 }  // namespace
 
+// y[r][c] = act(acc[r][c] + bias[c]) (x dropout mask), f32 -- the finishing pass of the 3xTF32 sums (tf32_conv.cu)
+int a3d_tc_finish_f32(a3d_ctx* ctx, const float* acc, const float* bias, const uint8_t* mask, float drop_rate, float* y,
+                      size_t rows, int n, long long ldy, unsigned flags, cudaStream_t st) {
+  return finish(ctx, acc, bias, mask, drop_rate, y, 1, rows, n, ldy, flags, st);
+}
+
 // ---- first-use autotuning -------------------------------------------------------------------------
 // The best tile width / split-K factor of the small MSDN layers depends on how many CTAs end up co-resident
 // and on wave quantisation in ways the closed-form heuristics above miss by up to 1.8x (profiles/sweep_r01_*).
@@ -1014,8 +1020,9 @@ __global__ void act_bwd_cast_f32_kernel(const float* __restrict__ acc, const flo
 }
 }  // namespace
 
+// acc_only: add the raw products into ws ([N*P*Q][K] f32, zeroed by the caller) and stop -- one term of a 3xTF32 sum
 int a3d_tc_conv_fwd_tf32(a3d_ctx* ctx, const a3d_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
-                         unsigned flags, void* ws, size_t ws_bytes, cudaStream_t st) {
+                         unsigned flags, void* ws, size_t ws_bytes, cudaStream_t st, int acc_only) {
   if (d->C % 32 || d->stride_h > 8 || d->stride_w > 8 || d->R > 256 || d->S > 256) {
     a3d_set_error("tf32 conv fwd: needs C %% 32 == 0 (C=%d)", d->C);
     return A3D_ENOTSUP;
@@ -1039,17 +1046,21 @@ int a3d_tc_conv_fwd_tf32(a3d_ctx* ctx, const a3d_conv_desc* d, const float* x, c
   int splits = can_split ? pick_splits(ctx, ceil_div(M, 128) * ceil_div(d->K, bn), num_kb, 8) : 1;
   p.kb_per_split = ceil_div(num_kb, splits);
   splits = ceil_div(num_kb, p.kb_per_split);
-  if (splits == 1) {
+  if (acc_only && !can_split) {
+    a3d_set_error("tf32 conv fwd: the accumulate-only form needs the [N*P*Q][K] f32 workspace");
+    return A3D_EINVAL;
+  }
+  if (splits == 1 && !acc_only) {
     p.epi = tc::EPI_ROW_F32; p.out = y; p.ldo = d->ldy; p.bias = bias; p.flags = flags; p.atomic = 0;
   } else {
-    A3D_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)M * d->K * sizeof(float), st));
+    if (!acc_only) A3D_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)M * d->K * sizeof(float), st));
     p.epi = tc::EPI_ROW_F32; p.out = ws; p.ldo = d->K; p.bias = nullptr; p.flags = 0; p.atomic = 1;
   }
   rc = bn == 16 ? launch_cfg<CfgT<16, false, false>>(ctx, tmA, tmB, p, splits, st)
        : bn == 64 ? launch_cfg<CfgT<64, false, false>>(ctx, tmA, tmB, p, splits, st)
        : bn == 128 ? launch_cfg<CfgT<128, false, false>>(ctx, tmA, tmB, p, splits, st)
                    : launch_cfg<CfgT<256, false, false>>(ctx, tmA, tmB, p, splits, st);
-  if (rc || splits == 1) return rc;
+  if (rc || acc_only || splits == 1) return rc;
   return finish(ctx, reinterpret_cast<const float*>(ws), bias, nullptr, 0.f, y, 1, (size_t)M, d->K, d->ldy, flags, st);
 }
 
@@ -1113,7 +1124,8 @@ int a3d_tc_dgrad_cols_tf32(a3d_ctx* ctx, const a3d_conv_desc* d, const float* dy
 
 // dense layers.  acc_ws f32 [M][N] (fwd) / [M][K] (dgrad) receives the split-K partial sums.
 int a3d_tc_dense_fwd_tf32(a3d_ctx* ctx, const float* x, int ldx, const float* w, const float* bias, const uint8_t* mask,
-                          float drop_rate, float* y, float* acc_ws, int M, int N, int K, unsigned flags, cudaStream_t st) {
+                          float drop_rate, float* y, float* acc_ws, int M, int N, int K, unsigned flags, cudaStream_t st,
+                          int acc_only) {
   if (K % 32 || ldx % 4 || M > 256 || !acc_ws) {
     a3d_set_error("tf32 dense fwd: needs K %% 32 == 0, batch <= 256 and an accumulation workspace (K=%d M=%d)", K, M);
     return A3D_ENOTSUP;
@@ -1132,12 +1144,12 @@ int a3d_tc_dense_fwd_tf32(a3d_ctx* ctx, const float* x, int ldx, const float* w,
   p.kb_per_split = ceil_div(p.num_kb, splits);
   splits = ceil_div(p.num_kb, p.kb_per_split);
   p.epi = tc::EPI_COL_F32; p.out = acc_ws; p.ldo = N; p.atomic = 1;
-  A3D_CHECK_CUDA(cudaMemsetAsync(acc_ws, 0, (size_t)M * N * sizeof(float), st));
+  if (!acc_only) A3D_CHECK_CUDA(cudaMemsetAsync(acc_ws, 0, (size_t)M * N * sizeof(float), st));
   rc = bn == 32 ? launch_cfg<CfgT<32, false, false>>(ctx, tmA, tmB, p, splits, st)
        : bn == 64 ? launch_cfg<CfgT<64, false, false>>(ctx, tmA, tmB, p, splits, st)
        : bn == 128 ? launch_cfg<CfgT<128, false, false>>(ctx, tmA, tmB, p, splits, st)
                    : launch_cfg<CfgT<256, false, false>>(ctx, tmA, tmB, p, splits, st);
-  if (rc) return rc;
+  if (rc || acc_only) return rc;
   return finish(ctx, acc_ws, bias, mask, drop_rate, y, 1, (size_t)M, N, N, flags, st);
 }
 

@@ -4,11 +4,14 @@
 #include "common.cuh"
 
 int a3d_tc_conv_fwd_tf32(a3d_ctx*, const a3d_conv_desc*, const float* x, const float* w, const float* bias, float* y,
-                         unsigned flags, void* ws, size_t ws_bytes, cudaStream_t st);
+                         unsigned flags, void* ws, size_t ws_bytes, cudaStream_t st, int acc_only = 0);
+int a3d_tc_finish_f32(a3d_ctx*, const float* acc, const float* bias, const uint8_t* mask, float drop_rate, float* y,
+                      size_t rows, int n, long long ldy, unsigned flags, cudaStream_t st);
 int a3d_tc_conv_wgrad_tf32(a3d_ctx*, const a3d_conv_desc*, const float* x, const float* dy, float* dw, cudaStream_t st);
 int a3d_tc_dgrad_cols_tf32(a3d_ctx*, const a3d_conv_desc*, const float* dy, const float* w, float* col, cudaStream_t st);
 int a3d_tc_dense_fwd_tf32(a3d_ctx*, const float* x, int ldx, const float* w, const float* bias, const uint8_t* mask,
-                          float drop_rate, float* y, float* acc_ws, int M, int N, int K, unsigned flags, cudaStream_t st);
+                          float drop_rate, float* y, float* acc_ws, int M, int N, int K, unsigned flags, cudaStream_t st,
+                          int acc_only = 0);
 int a3d_tc_dense_dgrad_tf32(a3d_ctx*, const float* dy, int lddy, const float* w, float* dx, float* acc_ws, int M, int N,
                             int K, const float* y_act, const uint8_t* keep_mask, float drop_rate, unsigned flags,
                             cudaStream_t st);
@@ -129,4 +132,78 @@ extern "C" int a3d_dense_wgrad_tf32(a3d_ctx* ctx, const float* x, int ldx, const
     if (rc) return rc;
   }
   return a3d_tc_dense_wgrad_tf32(ctx, x, ldx, dy, lddy, dw, M, N, K, as_stream(stream));
+}
+
+// ---- 3xTF32 forward ("tf32x3"): float32-grade products from three kind::tf32 GEMMs ---------------------------------
+// TF32 keeps 10 mantissa bits of each operand, which leaves the MSDN forward at ~2.6e-4 worst-pixel error against the
+// float32 reference arithmetic (profiles/tf32_parity_r02.log) -- short of the 1e-4 north star.  Splitting both operands
+// into hi + lo (a3d_split_tf32) and summing  lo.hi + hi.lo + hi.hi  in the float32 accumulator recovers ~21 bits at 3x the
+// tensor work; only the forward (the 1e-4 claim) needs it.  Workspace: [acc][x_hi][x_lo][w_hi][w_lo], sizes below.
+static size_t x3_conv_acc(const a3d_conv_desc* d) { return al256((size_t)d->N * d->P * d->Q * d->K * 4); }
+static size_t x3_conv_x(const a3d_conv_desc* d) { return al256((size_t)d->N * d->H * d->W * d->C * 4); }
+
+extern "C" size_t a3d_conv2d_ws_bytes_tf32x3(a3d_ctx*, const a3d_conv_desc* d) {
+  return d ? x3_conv_acc(d) + 2 * x3_conv_x(d) + 2 * filt_bytes_f32(d) : 0;
+}
+
+extern "C" int a3d_conv2d_fwd_tf32x3(a3d_ctx* ctx, const a3d_conv_desc* d, const float* x, const float* w, const float* bias,
+                                     float* y, unsigned flags, void* ws, size_t ws_bytes, void* stream) {
+  A3D_REQUIRE(ctx && x && w && y && ws, "conv fwd tf32x3: null argument");
+  int rc = check_desc_tf32(d);
+  if (rc) return rc;
+  A3D_REQUIRE(ws_bytes >= a3d_conv2d_ws_bytes_tf32x3(ctx, d), "conv fwd tf32x3: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  uint8_t* base = reinterpret_cast<uint8_t*>(ws);
+  const size_t nacc = x3_conv_acc(d), nx = x3_conv_x(d), nw = filt_bytes_f32(d);
+  float* acc = reinterpret_cast<float*>(base);
+  float* xh = reinterpret_cast<float*>(base + nacc);
+  float* xl = reinterpret_cast<float*>(base + nacc + nx);
+  float* wh = reinterpret_cast<float*>(base + nacc + 2 * nx);
+  float* wl = reinterpret_cast<float*>(base + nacc + 2 * nx + nw);
+  rc = a3d_split_tf32(ctx, x, (size_t)d->N * d->H * d->W, d->C, d->C, xh, xl, stream);
+  if (rc) return rc;
+  rc = a3d_split_tf32(ctx, w, (size_t)d->K, d->R * d->S * d->C, d->R * d->S * d->C, wh, wl, stream);
+  if (rc) return rc;
+  A3D_CHECK_CUDA(cudaMemsetAsync(acc, 0, (size_t)d->N * d->P * d->Q * d->K * 4, st));
+  const float* xs[3] = {xl, xh, xh};          // the two small cross terms first, the leading term last
+  const float* wsrc[3] = {wh, wl, wh};
+  for (int t = 0; t < 3; ++t) {
+    rc = a3d_tc_conv_fwd_tf32(ctx, d, xs[t], wsrc[t], nullptr, nullptr, 0, acc, nacc, st, 1);
+    if (rc) return rc;
+  }
+  return a3d_tc_finish_f32(ctx, acc, bias, nullptr, 0.f, y, (size_t)d->N * d->P * d->Q, d->K, d->ldy, flags, st);
+}
+
+extern "C" size_t a3d_dense_ws_bytes_tf32x3(int M, int N, int K) {
+  return al256((size_t)M * N * 4) + 2 * al256((size_t)M * K * 4) + 2 * al256((size_t)N * K * 4);
+}
+
+extern "C" int a3d_dense_fwd_tf32x3(a3d_ctx* ctx, const float* x, int ldx, const float* w, const float* bias,
+                                    const uint8_t* keep_mask, float drop_rate, float* y, void* ws, size_t ws_bytes, int M,
+                                    int N, int K, unsigned flags, void* stream) {
+  A3D_REQUIRE(ctx && x && w && y && ws && M > 0 && N > 0 && K > 0 && ldx >= K, "dense fwd tf32x3: bad argument");
+  A3D_REQUIRE(ws_bytes >= a3d_dense_ws_bytes_tf32x3(M, N, K), "dense fwd tf32x3: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  uint8_t* base = reinterpret_cast<uint8_t*>(ws);
+  const size_t nacc = al256((size_t)M * N * 4), nx = al256((size_t)M * K * 4), nw = al256((size_t)N * K * 4);
+  float* acc = reinterpret_cast<float*>(base);
+  float* xh = reinterpret_cast<float*>(base + nacc);
+  float* xl = reinterpret_cast<float*>(base + nacc + nx);
+  float* wh = reinterpret_cast<float*>(base + nacc + 2 * nx);
+  float* wl = reinterpret_cast<float*>(base + nacc + 2 * nx + nw);
+  int rc = a3d_split_tf32(ctx, x, (size_t)M, K, ldx, xh, xl, stream);
+  if (rc) return rc;
+  rc = a3d_split_tf32(ctx, w, (size_t)N, K, K, wh, wl, stream);
+  if (rc) return rc;
+  A3D_CHECK_CUDA(cudaMemsetAsync(acc, 0, (size_t)M * N * 4, st));
+  const float* xs[3] = {xl, xh, xh};
+  const float* wsrc[3] = {wh, wl, wh};
+  for (int t = 0; t < 3; ++t)
+    for (int m0 = 0; m0 < M; m0 += 256) {
+      const int mc = M - m0 < 256 ? M - m0 : 256;
+      rc = a3d_tc_dense_fwd_tf32(ctx, xs[t] + (size_t)m0 * K, K, wsrc[t], nullptr, nullptr, 0.f, nullptr,
+                                 acc + (size_t)m0 * N, mc, N, K, 0, st, 1);
+      if (rc) return rc;
+    }
+  return a3d_tc_finish_f32(ctx, acc, bias, keep_mask, drop_rate, y, (size_t)M, N, N, flags, st);
 }

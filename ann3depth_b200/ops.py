@@ -67,6 +67,7 @@ class Context:
         self._ws = {}
         self.ws_tag = ""          # set per stream by multi-stream callers: concurrent launches must not share scratch
         self.timeline = None      # StepTimeline when A3D_TIMELINE=1 (stamp() is a no-op otherwise)
+        self.tf32x3 = False       # float32 conv2d_fwd / dense_fwd through the 3xTF32 entry points (set around a forward)
 
     def close(self):
         if getattr(self, "h", None):
@@ -323,6 +324,13 @@ class Context:
                 L.check(self.lib.a3d_conv_k1_fwd_f32(self.h, C.byref(d), _ptr(x), _ptr(w), _ptr(bias), _ptr(out),
                                                      L.EPI_RELU if relu else 0, _stream()), "conv_k1_fwd_f32")
                 return out
+            if self.tf32x3:                        # 3xTF32: hi/lo operand split, float32-grade products
+                nb = self.lib.a3d_conv2d_ws_bytes_tf32x3(self.h, C.byref(d))
+                ws = self.workspace(("conv_tf32x3",), nb)
+                L.check(self.lib.a3d_conv2d_fwd_tf32x3(self.h, C.byref(d), _ptr(x), _ptr(w), _ptr(bias), _ptr(out),
+                                                       L.EPI_RELU if relu else 0, _ptr(ws), ws.numel(), _stream()),
+                        "conv2d_fwd_tf32x3")
+                return out
             ws, nb = self.conv_ws(d, L.OP_FWD, tf32=True)
             L.check(self.lib.a3d_conv2d_fwd_tf32(self.h, C.byref(d), _ptr(x), _ptr(w), _ptr(bias), _ptr(out),
                                                  L.EPI_RELU if relu else 0, _ptr(ws), ws.numel(), _stream()),
@@ -390,6 +398,13 @@ class Context:
         ldx = ldx or x.shape[1]
         if out is None:
             out = torch.empty(M, N, dtype=torch.float32 if x.dtype == torch.float32 else out_dtype, device=x.device)
+        if x.dtype == torch.float32 and self.tf32x3:
+            nb = self.lib.a3d_dense_ws_bytes_tf32x3(M, N, K)
+            ws = self.workspace(("dense_tf32x3",), nb)
+            L.check(self.lib.a3d_dense_fwd_tf32x3(self.h, _ptr(x), ldx, _ptr(w), _ptr(bias), _ptr(keep_mask), drop_rate,
+                                                  _ptr(out), _ptr(ws), ws.numel(), M, N, K, flags, _stream()),
+                    "dense_fwd_tf32x3")
+            return out
         acc = self.workspace(("dense_acc", M, N), M * N * 4)
         if x.dtype == torch.float32:
             L.check(self.lib.a3d_dense_fwd_tf32(self.h, _ptr(x), ldx, _ptr(w), _ptr(bias), _ptr(keep_mask), drop_rate,

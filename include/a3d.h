@@ -372,6 +372,18 @@ int a3d_pool4_bwd_f32(a3d_ctx*, const float* dy, int lddy, const float* y, int l
                       size_t rows, void* stream);
 int a3d_bias_grad_f32(a3d_ctx*, const float* dy, size_t rows, int C, int ld, float* db, void* stream);
 int a3d_scatter_f32(a3d_ctx*, const float* src, const int* idx, int G, size_t n, float* dst, void* stream);
+/* 3xTF32 forward ("tf32x3" precision mode): both operands are split into hi = tf32(x) and lo = x - hi (a3d_split_tf32;
+ * rows x cols floats at pitch ld, outputs dense) and  lo.hi + hi.lo + hi.hi  is summed in the float32 accumulator --
+ * float32-grade Conv2D / MatMul (src/models.py:211-251) at three times the kind::tf32 tensor work.  Same arguments as
+ * a3d_conv2d_fwd_tf32 / a3d_dense_fwd_tf32 except for the workspace, whose size the *_ws_bytes_tf32x3 calls return. */
+int a3d_split_tf32(a3d_ctx*, const float* x, size_t rows, int cols, long long ld, float* hi, float* lo, void* stream);
+size_t a3d_conv2d_ws_bytes_tf32x3(a3d_ctx*, const a3d_conv_desc*);
+int a3d_conv2d_fwd_tf32x3(a3d_ctx*, const a3d_conv_desc*, const float* x, const float* w, const float* bias, float* y,
+                          unsigned flags, void* ws, size_t ws_bytes, void* stream);
+size_t a3d_dense_ws_bytes_tf32x3(int M, int N, int K);
+int a3d_dense_fwd_tf32x3(a3d_ctx*, const float* x, int ldx, const float* w, const float* bias, const uint8_t* keep_mask,
+                         float drop_rate, float* y, void* ws, size_t ws_bytes, int M, int N, int K, unsigned flags,
+                         void* stream);
 /* single-filter convolution (K == 1: MSDN fine/third, src/models.py:250) in exact float32: forward, dgrad (+ ReluGrad
  * of relu_src, nullable), wgrad (+ db, nullable).  dy / y row pitch = ldy floats. */
 int a3d_conv_k1_fwd_f32(a3d_ctx*, const a3d_conv_desc*, const float* x, const float* w, const float* bias, float* y,
