@@ -25,7 +25,8 @@ class A3DError(RuntimeError):
 class ConvDesc(C.Structure):
     """Mirror of `a3d_conv_desc` (include/a3d.h)."""
     _fields_ = [(n, C.c_int) for n in
-                ("N", "H", "W", "C", "K", "R", "S", "stride_h", "stride_w", "pad_t", "pad_l", "P", "Q", "ldy", "impl")]
+                ("N", "H", "W", "C", "K", "R", "S", "stride_h", "stride_w", "pad_t", "pad_l", "P", "Q", "ldy", "impl",
+                 "dil_w", "pix_pitch")]
 
 
 _vp, _i, _f, _sz, _u = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_uint
@@ -138,6 +139,7 @@ SIGNATURES = {
     "a3d_pairwise_ws_bytes": (_sz, [_i, _i, _i]),
     "a3d_tile_means": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "a3d_extract_patches": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "a3d_extract_patches_s2d": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
     "a3d_comm_unique_id": (_i, [C.c_char_p, _vp]),
     "a3d_comm_init": (_i, [_vp, C.c_char_p, _vp, _i, _i]),
     "a3d_comm_destroy": (_i, [_vp]),

@@ -24,8 +24,19 @@ int a3d_mma_dense_wgrad_adam(a3d_ctx* ctx, const uint16_t* x, int ldx, const uin
 
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-static int check_desc(const a3d_conv_desc* d) {
+// overlapped-pixel view (a3d_conv_desc dil_w / pix_pitch): only the pool-fused forward and the weight gradient take it
+static bool is_view(const a3d_conv_desc* d) { return d->dil_w > 1 || (d->pix_pitch && d->pix_pitch != d->C); }
+
+static int check_desc(const a3d_conv_desc* d, bool allow_view = false) {
   A3D_REQUIRE(d, "conv: null descriptor");
+  A3D_REQUIRE(d->dil_w >= 0 && d->pix_pitch >= 0, "conv: negative dil_w / pix_pitch");
+  if (is_view(d)) {
+    A3D_REQUIRE(allow_view, "conv: dil_w / pix_pitch views are taken by a3d_conv2d_pool4_fwd and a3d_conv2d_wgrad only");
+    const int pp = d->pix_pitch ? d->pix_pitch : d->C, dil = d->dil_w > 1 ? d->dil_w : 1;
+    A3D_REQUIRE(pp % 8 == 0 && pp <= d->C && d->C % pp == 0, "conv: pix_pitch must divide C and be a multiple of 8");
+    A3D_REQUIRE(d->pad_l == 0 && (d->Q - 1) * d->stride_w + (d->S - 1) * dil < d->W,
+                "conv: a dilated / overlapped view needs pad_l == 0 and every tap inside the row");
+  }
   A3D_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->C > 0 && d->K > 0 && d->R > 0 && d->S > 0, "conv: bad dims");
   A3D_REQUIRE(d->stride_h > 0 && d->stride_w > 0 && d->pad_t >= 0 && d->pad_l >= 0, "conv: bad stride/pad");
   A3D_REQUIRE(d->P > 0 && d->Q > 0 && d->ldy >= d->K, "conv: bad output dims");
@@ -322,7 +333,7 @@ static int dgrad_impl(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* dy, 
 extern "C" int a3d_conv2d_wgrad(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, const uint16_t* dy, float* dw,
                                 float* db, void* ws, size_t ws_bytes, void* stream) {
   A3D_REQUIRE(ctx && x && dy && dw, "conv wgrad: null argument");
-  int rc = check_desc(d);
+  int rc = check_desc(d, true);
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
   if (db) {
@@ -331,7 +342,7 @@ extern "C" int a3d_conv2d_wgrad(a3d_ctx* ctx, const a3d_conv_desc* d, const uint
   }
   if (d->impl != A3D_IMPL_SIMT) {
     a3d_conv_desc v;
-    const a3d_conv_desc* e = virtualize(d, &v) ? &v : d;
+    const a3d_conv_desc* e = (!is_view(d) && virtualize(d, &v)) ? &v : d;
     if (a3d_tc_conv_wgrad_supported(e)) return a3d_tc_conv_wgrad(ctx, e, x, dy, dw, st);
     if (d->impl == A3D_IMPL_TC) {
       a3d_set_error("conv wgrad: shape not supported by the tcgen05 path (C=%d ldy=%d)", d->C, d->ldy);
@@ -474,7 +485,7 @@ extern "C" int a3d_conv2d_pool4_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const 
   A3D_REQUIRE(d->K == 256 && d->ldy >= 64, "conv pool4 fwd: K must be 4 x 64 and ldy >= 64");
   a3d_conv_desc chk = *d;
   chk.ldy = d->K;                      // ldy describes the POOLED output (64 channels), not the 256 GEMM columns
-  int rc = check_desc(&chk);
+  int rc = check_desc(&chk, true);
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
   if (d->impl == A3D_IMPL_SIMT) {

@@ -255,7 +255,62 @@ __global__ void extract_patches_kernel(const float* __restrict__ img, int B, int
   }
 }
 
+// The same patches after space-to-depth(2): 50 x 50 cells of 16 channels, channel (2a + b) * 3 + c = patch pixel
+// (2Y + a, 2X + b, c), channels 12..15 zero.  fold = 1: out [NP][50][50][16] (one 32-byte cell per position).
+// fold = 4: out [NP][50][50][64], position X holds cells X .. X+3 (zeros beyond the row) -- the materialised form of the
+// overlapped view the first DCNF layer reads (a3d_conv_desc::pix_pitch = 16 over the fold = 1 tensor is the same data).
+__global__ void extract_patches_s2d_kernel(const float* __restrict__ img, int B, int H, int W, int rows, int cols,
+                                           uint16_t* __restrict__ out, int fold) {
+  const int CS = 50, PAD = 30;
+  size_t total = (size_t)B * rows * cols * CS * CS * fold;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % fold);
+    size_t t = i / fold;
+    const int X = (int)(t % CS);
+    t /= CS;
+    const int Y = (int)(t % CS);
+    t /= CS;
+    const int pc = (int)(t % cols);
+    t /= cols;
+    const int prow = (int)(t % rows);
+    const int b = (int)(t / rows);
+    uint32_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int cx = X + k;
+    if (cx < CS) {
+      float f[12];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int bb = 0; bb < 2; ++bb) {
+          const int iy = prow * TILE - PAD + 2 * Y + a, ix = pc * TILE - PAD + 2 * cx + bb;
+          const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+          const float* p = img + (((size_t)b * H + (ok ? iy : 0)) * W + (ok ? ix : 0)) * 3;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) f[(a * 2 + bb) * 3 + c] = ok ? p[c] : 0.f;
+        }
+#pragma unroll
+      for (int j = 0; j < 6; ++j) v[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + i * 16);
+    o[0] = make_uint4(v[0], v[1], v[2], v[3]);
+    o[1] = make_uint4(v[4], v[5], v[6], v[7]);
+  }
+}
+
 }  // namespace
+
+extern "C" int a3d_extract_patches_s2d(a3d_ctx* ctx, const float* images, int B, int H, int W, uint16_t* cells, int fold,
+                                       void* stream) {
+  A3D_REQUIRE(ctx && images && cells && (fold == 1 || fold == 4), "extract_patches_s2d: bad argument (fold is 1 or 4)");
+  A3D_REQUIRE((reinterpret_cast<uintptr_t>(cells) & 15) == 0, "extract_patches_s2d: output must be 16-byte aligned");
+  int rows = (H + TILE - 1) / TILE, cols = (W + TILE - 1) / TILE;
+  size_t total = (size_t)B * rows * cols * 50 * 50 * fold;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > (size_t)ctx->sm_count * 32) blocks = (size_t)ctx->sm_count * 32;
+  extract_patches_s2d_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(images, B, H, W, rows, cols, cells, fold);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
 
 extern "C" int a3d_crf_fwd_bwd(a3d_ctx* ctx, const float* z, const float* y, const float* r, const int32_t* pl,
                                const int32_t* pr, int B, int n, int n_pairs, float grad_scale, int naive, float* ystar,

@@ -2,7 +2,8 @@
 // step / inference behind the C-ABI (a3d_dcnf_create / a3d_dcnf_step / a3d_dcnf_infer), the counterpart of msdn_model.cu.
 // Caller-owned workspace, no allocation or host synchronisation inside a step (CUDA-graph capturable after the first,
 // autotuning, call).  Mirrors ann3depth_b200/dcnf.py launch for launch: resize to 240x320, 100x100 patches around the 6x8
-// grid of 40x40 tiles, the unary CNN on all B*48 patches at once, pairwise colour / histogram similarities through the 2->1
+// grid of 40x40 tiles, the unary CNN on all B*48 patches at once (first layer pool-fused over
+// space-to-depth(2) patches), pairwise colour / histogram similarities through the 2->1
 // dense layer, CRF negative log-likelihood with A = I + D - R (one CTA per graph), plain SGD (lr 0.1).  As in TF 1.3 no
 // gradient reaches `pairwise_layers` (ScatterNdUpdate is not differentiable, src/models.py:138-141).
 #include "common.cuh"
@@ -11,7 +12,8 @@
 namespace {
 constexpr int H = 240, W = 320, SP = 40, ROWS = 6, COLS = 8, NSP = ROWS * COLS;     // src/models.py:16,32-35,180-181
 constexpr float SGD_LR = 0.1f, GAMMA = 1.0f;                                           // src/models.py:17,198
-constexpr int PATCH_C = 16;
+constexpr int C0_NUMEL = 64 * 11 * 11 * 16;       // canonical first-layer filter [64][11][11][16] (3 real channels)
+constexpr int EMB0_K = 256 * 6 * 2 * 64;           // its pool-embedded form [256][6][2][64]
 enum { G_SGD = 0, G_PAIRWISE = 1 };
 
 struct Seg { const char* name; int shape[4]; int ndim; int group; size_t numel, offset, size; };
@@ -46,13 +48,15 @@ struct a3d_dcnf {
   Seg seg[NSEG];
   size_t total, sgd_lo, sgd_hi;
   float *w, *g; uint16_t* wb;
-  float *im, *dp, *c0, *c1, *c4, *z, *sims, *r, *y, *ystar, *nll, *logdet, *loss, *output, *dz, *dense_acc, *pair_ws;
-  uint16_t *patches, *p0, *p1, *c2, *c3, *p4, *h0, *h1;
-  uint8_t *i0, *i1, *i4, *mask_c0;
+  float *im, *dp, *c1, *c4, *z, *sims, *r, *y, *ystar, *nll, *logdet, *loss, *output, *dz, *dense_acc, *pair_ws;
+  uint16_t *cells, *wbig0, *p0, *p1, *c2, *c3, *p4, *h0, *h1, *g_big0;
+  float* g_wbig0;
+  int32_t *emb_k, *emb_b;
+  uint8_t *i0, *i1, *i4;
   int32_t *pl, *pr, *status;
-  uint16_t *g_z, *g_h1a, *g_h1, *g_h0a, *g_h0, *g_p4, *g_c4, *g_c3, *g_c2, *g_p1, *g_c1, *g_p0, *g_c0;
+  uint16_t *g_z, *g_h1a, *g_h1, *g_h0a, *g_h0, *g_p4, *g_c4, *g_c3, *g_c2, *g_p1, *g_c1, *g_p0;
   void* scratch; size_t scratch_bytes;
-  a3d_conv_desc d0, d1, d2, d3, d4;
+  a3d_conv_desc d0, d0w, d1, d2, d3, d4;
 };
 
 namespace {
@@ -67,8 +71,10 @@ size_t carve(a3d_dcnf* n, uint8_t* base) {
   n->w = (float*)take(T * 4); n->g = (float*)take(T * 4); n->wb = (uint16_t*)take(T * 2);
   n->im = (float*)take(B * H * W * 3 * 4);
   n->dp = (float*)take(B * H * W * 4);
-  n->patches = (uint16_t*)take(NP * 100 * 100 * PATCH_C * 2);
-  n->c0 = (float*)take(NP * 90 * 90 * 64 * 4);
+  n->cells = (uint16_t*)take(NP * 50 * 50 * 16 * 2 + 256);       // + slack: the overlapped view reads past the last row
+  n->wbig0 = (uint16_t*)take((size_t)EMB0_K * 2);
+  n->emb_k = (int32_t*)take((size_t)4 * C0_NUMEL * 4);
+  n->emb_b = (int32_t*)take(4 * 64 * 4);
   n->p0 = (uint16_t*)take(NP * 45 * 45 * 64 * 2);
   n->i0 = (uint8_t*)take(NP * 45 * 45 * 64);
   n->c1 = (float*)take(NP * 41 * 41 * 256 * 4);
@@ -93,7 +99,6 @@ size_t carve(a3d_dcnf* n, uint8_t* base) {
   n->output = (float*)take(B * H * W * 4);
   n->pl = (int32_t*)take(NSP * 4);
   n->pr = (int32_t*)take(NSP * 4);
-  n->mask_c0 = (uint8_t*)take((size_t)64 * 11 * 11 * 16);
   n->dense_acc = (float*)take(NP * 12544 * 4);
   n->pair_ws = (float*)take(a3d_pairwise_ws_bytes((int)B, H, W));
   if (n->train) {
@@ -108,10 +113,11 @@ size_t carve(a3d_dcnf* n, uint8_t* base) {
     n->g_p1 = (uint16_t*)take(NP * 20 * 20 * 256 * 2);
     n->g_c1 = (uint16_t*)take(NP * 41 * 41 * 256 * 2);
     n->g_p0 = (uint16_t*)take(NP * 45 * 45 * 64 * 2);
-    n->g_c0 = (uint16_t*)take(NP * 90 * 90 * 64 * 2);
+    n->g_big0 = (uint16_t*)take(NP * 45 * 45 * 256 * 2);
+    n->g_wbig0 = (float*)take(((size_t)EMB0_K + 256) * 4);
   }
   size_t sc = 256;
-  const a3d_conv_desc* ds[] = {&n->d0, &n->d1, &n->d2, &n->d3, &n->d4};
+  const a3d_conv_desc* ds[] = {&n->d0w, &n->d1, &n->d2, &n->d3, &n->d4};
   for (const a3d_conv_desc* d : ds)
     for (int op = A3D_OP_FWD; op <= A3D_OP_WGRAD; ++op) {
       size_t b = a3d_conv2d_ws_bytes(n->ctx, d, op);
@@ -143,7 +149,12 @@ void init_layout(a3d_dcnf* n, a3d_ctx* ctx, int batch, int in_h, int in_w, int d
   }
   n->total = off;
   const int NP = n->NP;
-  n->d0 = valid_desc(NP, 100, 100, PATCH_C, 64, 11);      // src/models.py:64
+  // src/models.py:64-66 (11x11x3 -> 64, ReLU, 2x2 max-pool) as one pool-fused 6x6-cell convolution over the
+  // space-to-depth(2) patches, read through the overlapped-pixel view (a3d_extract_patches_s2d, dcnf.py)
+  n->d0 = valid_desc(NP, 50, 50, 64, 256, 6);
+  n->d0.S = 2; n->d0.P = n->d0.Q = 45; n->d0.ldy = 64; n->d0.dil_w = 4; n->d0.pix_pitch = 16;
+  n->d0w = n->d0;
+  n->d0w.ldy = 256;
   n->d1 = valid_desc(NP, 45, 45, 64, 256, 5);             // :67
   n->d2 = valid_desc(NP, 20, 20, 256, 256, 3);            // :69
   n->d3 = valid_desc(NP, 18, 18, 256, 256, 3);            // :71
@@ -166,10 +177,8 @@ int forward(a3d_dcnf* n, const float* images, const float* depths, void* st) {
   CK(a3d_resize_bilinear_tf1(c, images, B, n->inH, n->inW, 3, n->im, H, W, 3, A3D_F32, st));
   if (depths) CK(a3d_resize_bilinear_tf1(c, depths, B, n->dH, n->dW, 1, n->dp, H, W, 1, A3D_F32, st));
   // unary part (src/models.py:61-89) on all B*48 patches at once
-  CK(a3d_extract_patches(c, n->im, B, H, W, n->patches, PATCH_C, st));
-  CK(a3d_conv2d_fwd(c, &n->d0, n->patches, Wb(U "conv2d/kernel"), Wf(U "conv2d/bias"), n->c0, A3D_F32, A3D_EPI_RELU, n->scratch,
-                    n->scratch_bytes, st));
-  CK(a3d_maxpool2x2_fwd_f32(c, n->c0, NP, 90, 90, 64, n->p0, 64, n->i0, st));
+  CK(a3d_extract_patches_s2d(c, n->im, B, H, W, n->cells, 1, st));
+  CK(a3d_conv2d_pool4_fwd(c, &n->d0, n->cells, n->wbig0, Wf(U "conv2d/bias"), n->p0, n->i0, A3D_EPI_RELU, nullptr, 0, st));
   CK(a3d_conv2d_fwd(c, &n->d1, n->p0, Wb(U "conv2d_1/kernel"), Wf(U "conv2d_1/bias"), n->c1, A3D_F32, A3D_EPI_RELU, n->scratch,
                     n->scratch_bytes, st));
   CK(a3d_maxpool2x2_fwd_f32(c, n->c1, NP, 41, 41, 256, n->p1, 256, n->i1, st));
@@ -227,10 +236,12 @@ int backward(a3d_dcnf* n, void* st) {
   CK(a3d_maxpool2x2_idx_bwd(c, n->i1, n->g_p1, 256, NP, 41, 41, 256, n->g_c1, st));
   CK(a3d_conv2d_wgrad(c, &n->d1, n->p0, n->g_c1, G(U "conv2d_1/kernel"), G(U "conv2d_1/bias"), n->scratch, n->scratch_bytes, st));
   CK(a3d_conv2d_dgrad(c, &n->d1, n->g_c1, Wb(U "conv2d_1/kernel"), n->g_p0, nullptr, n->scratch, n->scratch_bytes, st));
-  CK(a3d_maxpool2x2_idx_bwd(c, n->i0, n->g_p0, 64, NP, 90, 90, 64, n->g_c0, st));
-  CK(a3d_conv2d_wgrad(c, &n->d0, n->patches, n->g_c0, G(U "conv2d/kernel"), G(U "conv2d/bias"), n->scratch, n->scratch_bytes, st));
-  // gradients of the 13 zero channels the 3-channel patches are stored with
-  return a3d_apply_mask_f32(c, G(U "conv2d/kernel"), n->mask_c0, (size_t)64 * 11 * 11 * 16, st);
+  // first layer: MaxPoolGrad + ReluGrad onto the 4 x 64 GEMM columns, weight gradient of the embedded filter, then its
+  // four copies (and the four bias groups) folded into the canonical variable (the 13 padding channels receive 0)
+  CK(a3d_pool4_bwd(c, n->g_p0, 64, n->p0, 64, n->i0, n->g_big0, (size_t)NP * 45 * 45, st));
+  CK(a3d_conv2d_wgrad(c, &n->d0w, n->cells, n->g_big0, n->g_wbig0, n->g_wbig0 + EMB0_K, n->scratch, n->scratch_bytes, st));
+  CK(a3d_gather_sum_f32(c, n->g_wbig0, n->emb_k, 4, C0_NUMEL, G(U "conv2d/kernel"), st));
+  return a3d_gather_sum_f32(c, n->g_wbig0 + EMB0_K, n->emb_b, 4, 64, G(U "conv2d/bias"), st);
 }
 }  // namespace
 
@@ -265,11 +276,33 @@ extern "C" int a3d_dcnf_create(a3d_ctx* ctx, int batch, int in_h, int in_w, int 
       for (int k = 0; k < 4; ++k) { pl[np] = pixel; pr[np] = pixel + add[k]; ++np; }
     }
   if (np != NSP) { delete n; a3d_set_error("dcnf_create: pair graph has %d pairs, expected %d", np, NSP); return A3D_EINVAL; }
-  uint8_t* mk = new uint8_t[64 * 11 * 11 * 16];
-  for (int i = 0; i < 64 * 11 * 11 * 16; ++i) mk[i] = (i & 15) < 3 ? 1 : 0;
+  // index maps canonical [64][11][11][16] -> the four embedded copies inside [256][6][2][64] (params.dcnf_first_embedded)
+  int32_t* mk = new int32_t[4 * C0_NUMEL + 4 * 64];
+  for (int i = 0; i < 4 * C0_NUMEL; ++i) mk[i] = -1;
+  for (int g = 0; g < 4; ++g) {
+    const int dy = g >> 1, dx = g & 1;
+    for (int co = 0; co < 64; ++co)
+      for (int tY = 0; tY < 6; ++tY)
+        for (int a = 0; a < 2; ++a) {
+          const int i = 2 * tY + a - dy;
+          if (i < 0 || i >= 11) continue;
+          for (int tX = 0; tX < 6; ++tX)
+            for (int b = 0; b < 2; ++b) {
+              const int j = 2 * tX + b - dx;
+              if (j < 0 || j >= 11) continue;
+              for (int ch = 0; ch < 3; ++ch) {
+                const int canon = ((co * 11 + i) * 11 + j) * 16 + ch;
+                const int derived = (((g * 64 + co) * 6 + tY) * 2 + tX / 4) * 64 + (tX % 4) * 16 + (2 * a + b) * 3 + ch;
+                mk[g * C0_NUMEL + canon] = derived;
+              }
+            }
+        }
+    for (int co = 0; co < 64; ++co) mk[4 * C0_NUMEL + g * 64 + co] = g * 64 + co;
+  }
   cudaError_t e1 = cudaMemcpyAsync(n->pl, pl, sizeof(pl), cudaMemcpyHostToDevice, st);
   cudaError_t e2 = cudaMemcpyAsync(n->pr, pr, sizeof(pr), cudaMemcpyHostToDevice, st);
-  cudaError_t e3 = cudaMemcpyAsync(n->mask_c0, mk, 64 * 11 * 11 * 16, cudaMemcpyHostToDevice, st);
+  cudaError_t e3 = cudaMemcpyAsync(n->emb_k, mk, (size_t)4 * C0_NUMEL * 4, cudaMemcpyHostToDevice, st);
+  if (e3 == cudaSuccess) e3 = cudaMemcpyAsync(n->emb_b, mk + 4 * C0_NUMEL, 4 * 64 * 4, cudaMemcpyHostToDevice, st);
   cudaStreamSynchronize(st);
   delete[] mk;
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { delete n; a3d_set_error("dcnf_create: upload failed"); return A3D_EINVAL; }
@@ -308,7 +341,8 @@ extern "C" int a3d_dcnf_arena(a3d_dcnf* n, float** w, float** g, uint16_t** w_bf
 
 extern "C" int a3d_dcnf_sync_weights(a3d_dcnf* n, void* stream) {
   A3D_REQUIRE(n, "dcnf_sync_weights: null net");
-  return a3d_cast_f32_bf16(n->ctx, n->w, n->wb, n->total, stream);
+  CK(a3d_cast_f32_bf16(n->ctx, n->w, n->wb, n->total, stream));
+  return a3d_scatter_cast_bf16(n->ctx, n->w + seg_off(n, U "conv2d/kernel"), n->emb_k, 4, C0_NUMEL, n->wbig0, stream);
 }
 
 extern "C" long long a3d_dcnf_global_step(const a3d_dcnf* n) { return n ? n->global_step : -1; }
@@ -321,6 +355,7 @@ extern "C" int a3d_dcnf_step(a3d_dcnf* n, const float* images, const float* dept
   CK(forward(n, images, depths, stream));
   CK(backward(n, stream));
   CK(a3d_sgd(n->ctx, n->w + n->sgd_lo, n->g + n->sgd_lo, n->wb + n->sgd_lo, n->sgd_hi - n->sgd_lo, SGD_LR, 1.0f, stream));
+  CK(a3d_scatter_cast_bf16(n->ctx, n->w + seg_off(n, U "conv2d/kernel"), n->emb_k, 4, C0_NUMEL, n->wbig0, stream));
   n->global_step += 1;
   if (loss) A3D_CHECK_CUDA(cudaMemcpyAsync(loss, n->loss, sizeof(float), cudaMemcpyDeviceToDevice, as_stream(stream)));
   return 0;

@@ -12,15 +12,16 @@ constexpr int TM = 64, TN = 64, TK = 16, NT = 256;
 struct ConvFwdProb {
   const uint16_t* x; const uint16_t* w; const float* bias; void* y;
   int N, H, W, C, K, R, S, sh, sw, pt, pl, P, Q, ldy, y_f32; unsigned flags;
+  int dil, pp;                 // horizontal tap spacing, pixel pitch in elements (a3d_conv_desc dil_w / pix_pitch)
   __device__ int dimM() const { return N * P * Q; }
   __device__ int dimN() const { return K; }
   __device__ int dimK() const { return R * S * C; }
   __device__ float a(int m, int k) const {
     int c = k % C; int t = k / C; int s = t % S; int r = t / S;
     int q = m % Q; int t2 = m / Q; int p = t2 % P; int n = t2 / P;
-    int ih = p * sh - pt + r, iw = q * sw - pl + s;
+    int ih = p * sh - pt + r, iw = q * sw - pl + s * dil;
     if (ih < 0 || ih >= H || iw < 0 || iw >= W) return 0.f;
-    return bf16_bits_to_f32(x[(((size_t)n * H + ih) * W + iw) * C + c]);
+    return bf16_bits_to_f32(x[(((size_t)n * H + ih) * W + iw) * pp + c]);
   }
   __device__ float b(int j, int k) const { return bf16_bits_to_f32(w[(size_t)j * (R * S * C) + k]); }
   __device__ void store(int m, int j, float acc) const {
@@ -56,6 +57,7 @@ struct ConvDgradProb {
 struct ConvWgradProb {
   const uint16_t* x; const uint16_t* dy; float* dw;
   int N, H, W, C, K, R, S, sh, sw, pt, pl, P, Q, ldy;
+  int dil, pp;
   __device__ int dimM() const { return K; }
   __device__ int dimN() const { return R * S * C; }
   __device__ int dimK() const { return N * P * Q; }
@@ -63,9 +65,9 @@ struct ConvWgradProb {
   __device__ float b(int j, int m) const {
     int c = j % C; int t = j / C; int s = t % S; int r = t / S;
     int q = m % Q; int t2 = m / Q; int p = t2 % P; int n = t2 / P;
-    int ih = p * sh - pt + r, iw = q * sw - pl + s;
+    int ih = p * sh - pt + r, iw = q * sw - pl + s * dil;
     if (ih < 0 || ih >= H || iw < 0 || iw >= W) return 0.f;
-    return bf16_bits_to_f32(x[(((size_t)n * H + ih) * W + iw) * C + c]);
+    return bf16_bits_to_f32(x[(((size_t)n * H + ih) * W + iw) * pp + c]);
   }
   __device__ void store(int co, int j, float acc) const { dw[(size_t)co * (R * S * C) + j] = acc; }
 };
@@ -228,7 +230,7 @@ __global__ void colsum_bf16_scalar_kernel(const uint16_t* __restrict__ a, size_t
 int a3d_simt_conv_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, const uint16_t* w, const float* bias,
                       void* y, int y_dtype, unsigned flags, cudaStream_t st) {
   ConvFwdProb p{x, w, bias, y, d->N, d->H, d->W, d->C, d->K, d->R, d->S, d->stride_h, d->stride_w, d->pad_t, d->pad_l,
-                d->P, d->Q, d->ldy, y_dtype == A3D_F32, flags};
+                d->P, d->Q, d->ldy, y_dtype == A3D_F32, flags, d->dil_w > 1 ? d->dil_w : 1, d->pix_pitch ? d->pix_pitch : d->C};
   return launch(ctx, p, (long long)d->N * d->P * d->Q, d->K, st);
 }
 
@@ -242,7 +244,7 @@ int a3d_simt_conv_dgrad(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* dy
 int a3d_simt_conv_wgrad(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, const uint16_t* dy, float* dw,
                         cudaStream_t st) {
   ConvWgradProb p{x, dy, dw, d->N, d->H, d->W, d->C, d->K, d->R, d->S, d->stride_h, d->stride_w, d->pad_t, d->pad_l,
-                  d->P, d->Q, d->ldy};
+                  d->P, d->Q, d->ldy, d->dil_w > 1 ? d->dil_w : 1, d->pix_pitch ? d->pix_pitch : d->C};
   return launch(ctx, p, d->K, (long long)d->R * d->S * d->C, st);
 }
 

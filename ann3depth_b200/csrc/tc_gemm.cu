@@ -82,11 +82,14 @@ int make_tmap_chunked(a3d_ctx* ctx, CUtensorMap* tm, const void* base, uint64_t 
 }
 
 // NHWC activation tensor (bf16, or f32 read as TF32) in im2col mode.  Base pixels run over lower + {0..P-1} * stride per axis.
+// pix_pitch (elements, 0 = C): pixel pitch of an overlapped view -- pixel w's C channels start at w * pix_pitch, so
+// consecutive pixels share C - pix_pitch channels (a3d_conv_desc::pix_pitch); rows and images are W and H*W pitches apart
 int make_tmap_im2col(a3d_ctx* ctx, CUtensorMap* tm, const void* base, int N, int H, int W, int C, int lower_h,
                      int lower_w, int P, int Q, int sh, int sw, uint32_t chan_box, uint32_t pixels, int elt = 2,
-                     bool mn_major = false) {
+                     bool mn_major = false, int pix_pitch = 0) {
+  const cuuint64_t pp = pix_pitch > 0 ? pix_pitch : C;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)C * elt, (cuuint64_t)W * C * elt, (cuuint64_t)H * W * C * elt};
+  cuuint64_t strides[3] = {pp * elt, (cuuint64_t)W * pp * elt, (cuuint64_t)H * W * pp * elt};
   // tightest bounding box that still contains the last base pixel (see DESIGN.md "im2col corners")
   int upper_w = lower_w + (Q - 1) * sw + 1 - W;
   int upper_h = lower_h + (P - 1) * sh + 1 - H;
@@ -516,7 +519,7 @@ int a3d_tc_conv_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, con
     const long long M = (long long)d->N * d->P * d->Q;
     CUtensorMap tmA, tmB;
     int rc = make_tmap_im2col(ctx, &tmA, x, d->N, d->H, d->W, d->C, -d->pad_t, -d->pad_l, d->P, d->Q, d->stride_h,
-                              d->stride_w, 64, 128);
+                              d->stride_w, 64, 128, 2, false, d->pix_pitch);
     if (rc) return rc;
     rc = make_tmap_2d(ctx, &tmB, w, 256, (uint64_t)d->R * d->S * d->C, (uint64_t)d->R * d->S * d->C, 64, 256);
     if (rc) return rc;
@@ -524,7 +527,7 @@ int a3d_tc_conv_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, con
     p.M = (int)M; p.N = 256; p.num_kb = d->R * d->S * cblocks; p.kb_per_split = p.num_kb;
     p.a_mode = tc::A_IM2COL;
     p.PQ = d->P * d->Q; p.Q = d->Q; p.sh = d->stride_h; p.sw = d->stride_w; p.lower_h = -d->pad_t; p.lower_w = -d->pad_l;
-    p.S = d->S; p.cblocks = cblocks;
+    p.S = d->S; p.cblocks = cblocks; p.dil_w = d->dil_w > 1 ? d->dil_w : 1;
     p.epi = tc::EPI_POOL4_BF16; p.out = y; p.ldo = d->ldy; p.bias = bias; p.flags = flags; p.pool_idx = pool_idx;
     // 128-row tiles with two stages of 48 KB (two CTAs per SM, one CTA's epilogue under the other's main loop),
     // the same with three stages, or 256-row tiles (both accumulators fill the 512 TMEM columns)
@@ -544,7 +547,7 @@ int a3d_tc_conv_fwd(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, con
     if (const char* force = getenv("A3D_POOL4_FORCE")) return run(atoi(force));
     TuneKey key{};
     const int kv[16] = {5, d->N, d->H, d->W, d->C, d->K, d->R, d->S, d->stride_h, d->stride_w, d->pad_t, d->pad_l,
-                        d->P, d->Q, d->ldy, pool_idx != nullptr};
+                        d->P, d->Q, d->ldy + 4096 * d->dil_w + 65536 * d->pix_pitch, pool_idx != nullptr};
     memcpy(key.v, kv, sizeof(kv));
     // candidates 0..3 one-CTA tiles, 6..7 CTA pairs
     int cands[8], nc = 0;
@@ -755,13 +758,13 @@ int a3d_tc_conv_wgrad(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, c
   int rc = make_tmap_2d(ctx, &tmA, dy, Mpix, d->K, d->ldy, 64, 64);
   if (rc) return rc;
   rc = make_tmap_im2col(ctx, &tmB, x, d->N, d->H, d->W, d->C, -d->pad_t, -d->pad_l, d->P, d->Q, d->stride_h,
-                        d->stride_w, bw, 64);
+                        d->stride_w, bw, 64, 2, false, d->pix_pitch);
   if (rc) return rc;
   tc::Params p{};
   p.M = d->K; p.N = RS * d->C; p.num_kb = ceil_div(Mpix, 64);
   p.a_mode = tc::A_TILED; p.b_im2col = 1; p.RS = RS;
   p.PQ = d->P * d->Q; p.Q = d->Q; p.sh = d->stride_h; p.sw = d->stride_w; p.lower_h = -d->pad_t; p.lower_w = -d->pad_l;
-  p.S = d->S; p.cblocks = cblocks;
+  p.S = d->S; p.cblocks = cblocks; p.dil_w = d->dil_w > 1 ? d->dil_w : 1;
   p.epi = tc::EPI_ROW_F32; p.out = dw; p.ldo = (long long)RS * d->C;
 
   // bm = 256: 256 filters per CTA, i.e. two accumulators share every im2col stage of X (the expensive operand)
@@ -828,7 +831,7 @@ int a3d_tc_conv_wgrad(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* x, c
   }
   TuneKey key{};
   const int kv[16] = {1, d->N, d->H, d->W, d->C, d->K, d->R, d->S, d->stride_h, d->stride_w, d->pad_t, d->pad_l,
-                      d->P, d->Q, d->ldy, 0};
+                      d->P, d->Q, d->ldy, d->dil_w * 4096 + d->pix_pitch};
   memcpy(key.v, kv, sizeof(kv));
   const int best = autotune(key, nc, [&](int c) { return launch(cand[c].nblk, cand[c].splits, cand[c].bm); }, st);
   return launch(cand[best].nblk, cand[best].splits, cand[best].bm);

@@ -61,6 +61,7 @@ struct Params {
   int a_mode;
   int a_k0;                 // tiled: first K coordinate
   int PQ, Q, sh, sw, lower_h, lower_w, S, cblocks;   // im2col
+  int dil_w = 1;            // im2col: horizontal tap spacing in pixels (a3d_conv_desc::dil_w)
   // B operand addressing: coords (kb*KC, n0) for K-major, (n0, kb*64) for MN-major.
   // b_im2col (wgrad): B is the im2col view of an NHWC tensor, MN-major: K rows = 64 consecutive output
   // pixels, N blocks of BW channels; block jb <-> (tap = jb / cblocks, channel block jb % cblocks).
@@ -203,8 +204,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             int ch = kb * 8 + j;
             int tap = ch / p.cblocks, cb = ch - tap * p.cblocks;
             int r = tap / p.S, sx = tap - r * p.S;      // taps beyond the filter meet zero-filled weights
-            ptx::tma_load_im2col_4d(sA + j * (C::BM * 16), &tmA, &full_bar[stage], cb * 8, w0, h0, n_img, (uint16_t)sx,
-                                    (uint16_t)r);
+            ptx::tma_load_im2col_4d(sA + j * (C::BM * 16), &tmA, &full_bar[stage], cb * 8, w0, h0, n_img,
+                                    (uint16_t)(sx * p.dil_w), (uint16_t)r);
           }
           ptx::tma_load_3d(sB, &tmB, &full_bar[stage], 0, n0, kb * 8);
         } else if constexpr (!C::A_MN) {
@@ -214,11 +215,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           } else {
             int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
             int r = tap / p.S, s = tap - r * p.S;
-            ptx::tma_load_im2col_4d(sA, &tmA, &full_bar[stage], cb * C::KELEMS, w0, h0, n_img, (uint16_t)s,
+            ptx::tma_load_im2col_4d(sA, &tmA, &full_bar[stage], cb * C::KELEMS, w0, h0, n_img, (uint16_t)(s * p.dil_w),
                                     (uint16_t)r);
             if (sub1)
               ptx::tma_load_im2col_4d(sA + C::A_SUB_BYTES, &tmA, &full_bar[stage], cb * C::KELEMS, w01, h01, n_img1,
-                                      (uint16_t)s, (uint16_t)r);
+                                      (uint16_t)(s * p.dil_w), (uint16_t)r);
           }
         } else {
           // MN-major A: global [K rows][M cols]; 128-byte-wide boxes of KROWS K-rows (2 per 128 rows for bf16, 4 for tf32)
@@ -255,7 +256,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (tap >= p.RS) tap = p.RS - 1;              // columns beyond N: loaded but never stored
             int r = tap / p.S, sx = tap - r * p.S;
             ptx::tma_load_im2col_4d(sB + j * C::B_BLK_BYTES, &tmB, &full_bar[stage], cb * C::B_BW, ww, hh, ni,
-                                    (uint16_t)sx, (uint16_t)r);
+                                    (uint16_t)(sx * p.dil_w), (uint16_t)r);
           }
         }
       }

@@ -187,7 +187,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         } else {
           const int tap = i / p.cblocks, cb = i - tap * p.cblocks;
           const int r = tap / p.S, s = tap - r * p.S;
-          pair::tma_load_im2col_4d_2cta(sA, &tmA, full0, cb * C::KELEMS, w0, h0, n_img, (uint16_t)s, (uint16_t)r);
+          pair::tma_load_im2col_4d_2cta(sA, &tmA, full0, cb * C::KELEMS, w0, h0, n_img, (uint16_t)(s * p.dil_w),
+                                        (uint16_t)r);
         }
         pair::tma_load_2d_2cta(sB, &tmB, full0, i * C::KELEMS, n0 + (int)crank * C::HALF_ROWS);
       }

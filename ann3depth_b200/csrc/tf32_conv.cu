@@ -29,6 +29,7 @@ static bool s1_dgrad_ok(const a3d_conv_desc* d) {
 
 static int check_desc_tf32(const a3d_conv_desc* d) {
   A3D_REQUIRE(d, "conv tf32: null descriptor");
+  A3D_REQUIRE(d->dil_w <= 1 && (!d->pix_pitch || d->pix_pitch == d->C), "conv tf32: dil_w / pix_pitch views not supported");
   A3D_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->C > 0 && d->K > 0 && d->R > 0 && d->S > 0, "conv tf32: bad dims");
   A3D_REQUIRE(d->stride_h > 0 && d->stride_w > 0 && d->pad_t >= 0 && d->pad_l >= 0 && d->P > 0 && d->Q > 0 && d->ldy >= d->K,
               "conv tf32: bad stride / pad / output dims");

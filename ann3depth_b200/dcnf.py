@@ -12,12 +12,13 @@ src/models.py:138-141): only the unary CNN trains.
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
 from . import _lib as L
 from . import ops
-from .params import Arena, dcnf_specs
+from .params import DCNF_FIRST_EMBEDDED_SHAPE, Arena, dcnf_first_index_maps, dcnf_specs
 
 H, W = 240, 320            # src/models.py:180-181
 SP = 40                    # src/models.py:16
@@ -94,14 +95,32 @@ class DCNFNet:
         self.depths = z(B, depth_hw[0], depth_hw[1], 1, **f32)
         self.im = z(B, H, W, 3, **f32)
         self.dp = z(B, H, W, 1, **f32)
-        self.patches = z(NP, 100, 100, PATCH_C, **bf)
+        # First layer (src/models.py:64-66: 11x11x3 -> 64, ReLU, 2x2 max-pool) as ONE pool-fused convolution over the
+        # space-to-depth(2) patches: 50 x 50 cells of 16 channels, read 4 cells (128 bytes) per tap through an overlapped
+        # view (params.dcnf_first_embedded).  `first_fold` = 1: the view (pix_pitch 16 over the cell tensor, 61 MB at
+        # B = 16); 4: the same pixels materialised (245 MB).  The 100x100x16 patch tensor, the 1.6 GB float32 conv output
+        # and its separate pool pass of the plain formulation do not exist.
+        self.first_fold = int(os.environ.get("A3D_DCNF_FIRST_FOLD", "1"))
+        assert self.first_fold in (1, 4)
+        ncell = NP * 50 * 50 * 16 * self.first_fold
+        self._cells = z(ncell + 128, **bf)             # + slack: the last positions of the last row read past the end
+        self.cells = self._cells[:ncell].view(NP, 50, 50, 16 * self.first_fold)
         cd = ops.conv_desc
-        self.d0 = cd(NP, 100, 100, PATCH_C, 64, 11, 11, 1, "valid", impl=impl)      # :64
+        d0 = cd(NP, 50, 50, 64, 256, 6, 2, 1, "valid", ldy=64, impl=impl)
+        d0.P = d0.Q = 45
+        d0.dil_w = 4
+        d0.pix_pitch = 16 if self.first_fold == 1 else 0
+        self.d0 = d0
+        self.d0w = L.ConvDesc.from_buffer_copy(d0)   # the weight gradient sees the 4 x 64 GEMM columns
+        self.d0w.ldy = 256
+        self.wbig0 = z(*DCNF_FIRST_EMBEDDED_SHAPE, **bf)
+        km, bm = dcnf_first_index_maps(self.arena.specs["unary/unary_layers/conv2d/kernel"],
+                                       self.arena.specs["unary/unary_layers/conv2d/bias"])
+        self.emb_k, self.emb_b = km.to(self.dev), bm.to(self.dev)
         self.d1 = cd(NP, 45, 45, 64, 256, 5, 5, 1, "valid", impl=impl)              # :67
         self.d2 = cd(NP, 20, 20, 256, 256, 3, 3, 1, "valid", impl=impl)             # :69
         self.d3 = cd(NP, 18, 18, 256, 256, 3, 3, 1, "valid", impl=impl)             # :71
         self.d4 = cd(NP, 16, 16, 256, 256, 3, 3, 1, "valid", impl=impl)             # :72
-        self.c0 = z(NP, 90, 90, 64, **f32)
         self.p0, self.i0 = z(NP, 45, 45, 64, **bf), z(NP, 45, 45, 64, **u8)
         self.c1 = z(NP, 41, 41, 256, **f32)
         self.p1, self.i1 = z(NP, 20, 20, 256, **bf), z(NP, 20, 20, 256, **u8)
@@ -132,7 +151,9 @@ class DCNFNet:
             self.g_p1 = z(NP, 20, 20, 256, **bf)
             self.g_c1 = z(NP, 41, 41, 256, **bf)
             self.g_p0 = z(NP, 45, 45, 64, **bf)
-            self.g_c0 = z(NP, 90, 90, 64, **bf)
+            self.g_big0 = z(NP * 45 * 45, 256, **bf)       # gradient on the 4 x 64 pool-window columns
+            nk = 256 * 6 * 2 * 64
+            self.g_wbig0 = z(nk + 256, **f32)
 
     # ------------------------------------------------------------------ parameters
     def w(self, name):
@@ -146,6 +167,13 @@ class DCNFNet:
 
     def load_params(self, tf_params):
         self.arena.load_tf(tf_params)
+        self.refresh_derived()
+
+    def refresh_derived(self):
+        """Re-embed the canonical first-layer filter into the pool-fused filter the kernels read (after a load or an SGD
+        step); entries outside the four embedded copies stay zero."""
+        s = self.arena.specs["unary/unary_layers/conv2d/kernel"]
+        self.ctx.scatter_cast_bf16(self.arena.w[s.offset:s.offset + s.numel], self.emb_k, self.wbig0)
 
     def export_params(self):
         return self.arena.export_tf()
@@ -160,9 +188,8 @@ class DCNFNet:
         c.resize_bilinear_tf1(self.images, H, W, out=self.im)
         c.resize_bilinear_tf1(self.depths, H, W, out=self.dp)
         # unary part (src/models.py:61-89) on all B*48 patches at once
-        c.extract_patches(self.im, out=self.patches)
-        c.conv2d_fwd(self.d0, self.patches, self.w(U + "conv2d" + K), self.wf(U + "conv2d/bias"), relu=True, out=self.c0)
-        c.maxpool2x2_fwd_f32(self.c0, out=self.p0, idx=self.i0)
+        c.extract_patches_s2d(self.im, self.cells, self.first_fold)
+        c.conv2d_pool4_fwd(self.d0, self.cells, self.wbig0, self.wf(U + "conv2d/bias"), relu=True, out=self.p0, idx=self.i0)
         c.conv2d_fwd(self.d1, self.p0, self.w(U + "conv2d_1" + K), self.wf(U + "conv2d_1/bias"), relu=True, out=self.c1)
         c.maxpool2x2_fwd_f32(self.c1, out=self.p1, idx=self.i1)
         c.conv2d_fwd(self.d2, self.p1, self.w(U + "conv2d_2" + K), self.wf(U + "conv2d_2/bias"), relu=True, out=self.c2)
@@ -223,12 +250,14 @@ class DCNFNet:
         c.maxpool2x2_idx_bwd(self.i1, self.g_p1, (NP, 41, 41, 256), out=self.g_c1)
         c.conv2d_wgrad(self.d1, self.p0, self.g_c1, dw=self.gw(U + "conv2d_1" + K), db=self.gw(U + "conv2d_1/bias"))
         c.conv2d_dgrad(self.d1, self.g_c1, self.w(U + "conv2d_1" + K), out=self.g_p0)
-        c.maxpool2x2_idx_bwd(self.i0, self.g_p0, (NP, 90, 90, 64), out=self.g_c0)
-        c.conv2d_wgrad(self.d0, self.patches, self.g_c0, dw=self.gw(U + "conv2d" + K), db=self.gw(U + "conv2d/bias"))
-        m = self.arena.masks.get(U + "conv2d" + K)
-        if m is not None:
-            s = self.arena.specs[U + "conv2d" + K]
-            c.apply_mask_f32(self.arena.g[s.offset:s.offset + s.numel], m)
+        # first layer: MaxPoolGrad + ReluGrad onto the 4 x 64 GEMM columns, weight gradient of the embedded filter, then
+        # fold its four copies (and the four bias groups) into the canonical variable (padding channels receive 0)
+        c.pool4_bwd(self.g_p0.view(-1, 64), self.p0.view(-1, 64), self.i0, out=self.g_big0)
+        nk = 256 * 6 * 2 * 64
+        c.conv2d_wgrad(self.d0w, self.cells, self.g_big0.view(NP, 45, 45, 256), dw=self.g_wbig0[:nk].view(256, 6, 2, 64),
+                       db=self.g_wbig0[nk:])
+        c.gather_sum_f32(self.g_wbig0[:nk], self.emb_k, self.gw(U + "conv2d" + K))
+        c.gather_sum_f32(self.g_wbig0[nk:], self.emb_b, self.gw(U + "conv2d/bias"))
         hook(self, "SGD")
 
     def train_step(self, use_graph=False):
@@ -244,6 +273,7 @@ class DCNFNet:
             assert not self.comm, "train_pairwise is a single-GPU option"
             lo, hi = self.arena.group_range("Pairwise")
             self.ctx.sgd(self.arena.w[lo:hi], self.arena.g[lo:hi], self.arena.wb[lo:hi], SGD_LR, 1.0)
+        self.refresh_derived()
         self.global_step += 1
         return 1
 

@@ -588,6 +588,13 @@ class Context:
                 "extract_patches")
         return out
 
+    def extract_patches_s2d(self, images, out, fold=1):
+        """DCNF patches after space-to-depth(2): out bf16 [B*n, 50, 50, 16*fold] (a3d_extract_patches_s2d)."""
+        B, H, W, _ = images.shape
+        L.check(self.lib.a3d_extract_patches_s2d(self.h, _ptr(images), B, H, W, _ptr(out), fold, _stream()),
+                "extract_patches_s2d")
+        return out
+
     # ------------------------------------------------------------------ data parallel
     def comm_init(self, id_bytes: bytes, rank: int, nranks: int, nccl_path: str | None = None):
         buf = C.create_string_buffer(id_bytes, 128)

@@ -212,6 +212,61 @@ def fine_first_index_maps(kernel_spec: "VarSpec", bias_spec: "VarSpec"):
     return kmap, bmap
 
 
+DCNF_FIRST_EMBEDDED_SHAPE = (256, 6, 2, 64)
+
+
+def dcnf_first_embedded(t: torch.Tensor) -> torch.Tensor:
+    """DCNF first layer (11x11x3 -> 64, stride 1) + ReLU + 2x2 max-pool (src/models.py:64-66) as ONE convolution over the
+    space-to-depth(2) patch (50 x 50 cells of 16 channels, channel (2a+b)*3+c = patch pixel (2Y+a, 2X+b, c),
+    a3d_extract_patches_s2d): pool-window position (dy, dx) is filter group g = 2*dy + dx, whose 11x11 filter sits at
+    offset (dy, dx) inside the 12x12-pixel = 6x6-cell receptive field.  The layer reads 4 cells (64 channels, 128 bytes)
+    per tap through an overlapped-pixel view, so the 6 horizontal cell taps are 2 taps of 4 cells, 4 pixels apart
+    (a3d_conv_desc dil_w = 4, pix_pitch = 16): [11,11,3,64] -> [256][6][2][64], element
+    [g*64 + co][tY][sv][k*16 + (2a+b)*3 + c] = w[2tY + a - dy][2(4sv + k) + b - dx][c][co]."""
+    kh, kw, ci, co = t.shape
+    assert (kh, kw, ci) == (11, 11, 3) and co <= 64
+    big = torch.zeros(DCNF_FIRST_EMBEDDED_SHAPE, dtype=t.dtype)
+    for dy in range(2):
+        for dx in range(2):
+            g = 2 * dy + dx
+            for tY in range(6):
+                for a in range(2):
+                    i = 2 * tY + a - dy
+                    if not 0 <= i < kh:
+                        continue
+                    for sv in range(2):
+                        for k in range(4):
+                            tX = 4 * sv + k
+                            if tX >= 6:
+                                continue
+                            for b in range(2):
+                                j = 2 * tX + b - dx
+                                if not 0 <= j < kw:
+                                    continue
+                                ch = k * 16 + (2 * a + b) * 3
+                                big[g * 64:g * 64 + co, tY, sv, ch:ch + 3] = t[i, j].t()
+    return big
+
+
+def dcnf_first_index_maps(kernel_spec: "VarSpec", bias_spec: "VarSpec"):
+    """(kernel map int32 [4, numel], bias map int32 [4, 64]) of the embedded DCNF first layer, for a3d_gather_sum_f32 /
+    a3d_scatter_cast_bf16 (same mechanism as fine_first_index_maps)."""
+    def derive(ids):
+        big = dcnf_first_embedded(ids)
+        copies = []
+        for g in range(4):
+            sel = torch.zeros_like(big)
+            sel[g * 64:(g + 1) * 64] = big[g * 64:(g + 1) * 64]
+            copies.append(sel)
+        return copies
+    kmap = embed_index_map(kernel_spec, derive)
+    bmap = torch.full((4, bias_spec.numel), -1, dtype=torch.int32)
+    n_real = bias_spec.tf_shape[0]
+    for g in range(4):
+        bmap[g, :n_real] = torch.arange(n_real, dtype=torch.int32) + g * 64
+    return kmap, bmap
+
+
 def dcnf_specs():
     """DCNF variables (src/models.py:61-93); one SGD group (src/models.py:198)."""
     v = []

@@ -93,6 +93,13 @@ typedef struct a3d_conv_desc {
   int ldy;                 /* channel stride of the output tensor (>= K; lets conv write into a
                               wider concat buffer, src/models.py:246)                           */
   int impl;                /* A3D_IMPL_*                                                        */
+  /* Overlapped-pixel view (0 / 0 = plain tensor; used by the DCNF first layer, see a3d_extract_patches_s2d):
+   * pix_pitch = elements between consecutive pixels when that is LESS than C, i.e. pixel w's C channels are
+   * the pix_pitch-wide cells w .. w + C/pix_pitch - 1 of a row of cells; dil_w = horizontal tap spacing in pixels
+   * (tap s reads pixel q*stride_w + s*dil_w).  Together: a filter S*C/pix_pitch cells wide over a cell image,
+   * consumed in whole 128-byte rows, without materialising the fold.  Honoured by a3d_conv2d_pool4_fwd and
+   * a3d_conv2d_wgrad on the tcgen05 path (and their CUDA-core cross-checks); every other call rejects it. */
+  int dil_w, pix_pitch;
 } a3d_conv_desc;
 
 /* Scratch requirements.  op: 0 = fwd (split-K accumulator), 1 = dgrad (repacked filter + accumulator),
@@ -321,6 +328,13 @@ int a3d_tile_means(a3d_ctx*, const float* depth, int B, int H, int W, float* y, 
  * images f32 [B,H,W,3] -> patches bf16 [B*rows*cols,100,100,dstC]. */
 int a3d_extract_patches(a3d_ctx*, const float* images, int B, int H, int W, uint16_t* patches,
                         int dstC, void* stream);
+/* The same patches after space-to-depth(2), for the pool-fused first layer (11x11 conv + ReLU + 2x2 max-pool as ONE
+ * 6x6-cell convolution with 4 x 64 filters, a3d_conv2d_pool4_fwd): cells bf16 [B*n][50][50][16], channel (2a+b)*3+c =
+ * patch pixel (2Y+a, 2X+b, c), channels 12..15 zero (fold = 1); fold = 4 writes [B*n][50][50][64] with position X
+ * holding cells X..X+3.  The layer reads the fold = 1 tensor through a3d_conv_desc{C = 64, S = 2, dil_w = 4,
+ * pix_pitch = 16}: whole 128-byte rows per TMA load, a quarter of the bytes.  The caller keeps >= 128 zero bytes after
+ * the fold = 1 tensor (the last positions of the last row read past it, against zero weights). */
+int a3d_extract_patches_s2d(a3d_ctx*, const float* images, int B, int H, int W, uint16_t* cells, int fold, void* stream);
 
 /* ---- data parallelism (replaces the PS/gRPC replication of src/ann3depth.py:78-92) ---------- */
 /* NCCL is dlopen()ed at first use (path = NULL -> "libnccl.so.2"). */

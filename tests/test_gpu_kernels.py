@@ -788,3 +788,86 @@ def test_dense_rows_update_with_rank_blocks(ctx):
     db = torch.zeros(N, device=DEV)
     ctx.bias_grad_bf16(gbuf.view(-1)[B * K:], N, db, rows=n * B, ld=lddy, group_rows=B, group_stride=blk)
     assert torch.allclose(db, dy[:, :N].float().sum(0), rtol=1e-5, atol=1e-4)
+
+
+# ---- overlapped-pixel / dilated view (a3d_conv_desc dil_w, pix_pitch): the DCNF first layer ------------------------------
+def _view_reference(cells, w, N, Hc, Wc, P, Q, dil):
+    """cells f64 flat (with slack), w f64 [K,R,S,64]: out[n,p,q,k] = sum_{r,s} w[k,r,s,:] . cells[(n,p+r,q+s*dil) .. +64)."""
+    K, R, S, _ = w.shape
+    out = torch.zeros(N, P, Q, K, dtype=torch.float64)
+    pix = torch.arange(Hc * Wc * N).view(N, Hc, Wc)
+    win = cells.unfold(0, 64, 16)                                   # win[i] = 64 elements starting at cell i
+    for r in range(R):
+        for s in range(S):
+            sel = pix[:, r:r + P, s * dil:s * dil + Q]
+            out += win[sel] @ w[:, r, s, :].t()
+    return out, win, pix
+
+
+@pytest.mark.parametrize("fold", [1, 4])
+@pytest.mark.parametrize("impl", ["tc", "simt"])
+def test_conv_view_pool4_fwd_and_wgrad(ctx, fold, impl):
+    """64-channel pixels that are 4 consecutive 16-channel cells (pix_pitch = 16, or materialised for fold = 4), taps 4
+    pixels apart (dil_w = 4): pool-fused forward and weight gradient against float64 on the same bf16 values."""
+    N, Hc, Wc, R, S, dil = 3, 20, 30, 6, 2, 4
+    P, Q = Hc - R + 1, Wc - 6 + 1
+    g = torch.Generator().manual_seed(60)
+    cells = torch.randn(N * Hc * Wc * 16 + 64, generator=g).to(torch.bfloat16)
+    cells[N * Hc * Wc * 16:] = 0
+    w = (torch.randn(256, R, S, 64, generator=g) / math.sqrt(R * S * 64)).to(torch.bfloat16)
+    bias = (torch.rand(64, generator=g) - 0.5) * 0.2
+    ref, win, pix = _view_reference(cells.double(), w.double(), N, Hc, Wc, P, Q, dil)
+    if fold == 1:
+        x = cells.to(DEV)
+        xv = x[:N * Hc * Wc * 16].view(N, Hc, Wc, 16)
+    else:
+        xv = win[pix].to(torch.bfloat16).to(DEV).contiguous()      # [N,Hc,Wc,64] materialised
+        x = xv
+    d = ops.conv_desc(N, Hc, Wc, 64, 256, R, S, 1, "valid", ldy=64, impl=L.IMPL_SIMT if impl == "simt" else L.IMPL_AUTO)
+    d.P, d.Q, d.dil_w, d.pix_pitch = P, Q, dil, 16 if fold == 1 else 0
+    y = torch.full((N, P, Q, 64), 7.0, dtype=torch.bfloat16, device=DEV)
+    idx = torch.full((N, P, Q, 64), 9, dtype=torch.uint8, device=DEV)
+    ctx.conv2d_pool4_fwd(d, xv, w.to(DEV), bias.to(DEV), relu=True, out=y, idx=idx)
+    r4 = ref.view(N, P, Q, 4, 64)
+    yref = torch.relu(r4.max(3).values + bias.double())
+    assert float((y.cpu().double() - yref).abs().max()) < 2e-2 * float(yref.abs().max())
+    # the routing byte names a group whose value is the maximum (ties aside, within accumulation noise)
+    picked = r4.gather(3, idx.cpu().long().unsqueeze(3)).squeeze(3)
+    assert float((picked - r4.max(3).values).abs().max()) < 1e-3
+    # weight gradient over the 4 x 64 columns
+    dy = (torch.randn(N, P, Q, 256, generator=g) * 0.1).to(torch.bfloat16)
+    dw = torch.empty(256, R, S, 64, dtype=torch.float32, device=DEV)
+    db = torch.empty(256, dtype=torch.float32, device=DEV)
+    dwd = L.ConvDesc.from_buffer_copy(d)
+    dwd.ldy = 256
+    ctx.conv2d_wgrad(dwd, xv, dy.to(DEV), dw=dw, db=db)
+    dwref = torch.zeros(256, R, S, 64, dtype=torch.float64)
+    dyf = dy.double().view(-1, 256)
+    for r in range(R):
+        for s in range(S):
+            sel = pix[:, r:r + P, s * dil:s * dil + Q].reshape(-1)
+            dwref[:, r, s, :] = dyf.t() @ win[sel]
+    assert float((dw.cpu().double() - dwref).abs().max()) < 1e-3 * float(dwref.abs().max())
+    assert float((db.cpu().double() - dyf.sum(0)).abs().max()) < 1e-3 * float(dyf.sum(0).abs().max())
+    # every other convolution call rejects the view
+    with pytest.raises(L.A3DError):
+        ctx.conv2d_fwd(dwd, xv, w.to(DEV), None)
+
+
+def test_extract_patches_s2d(ctx):
+    g = torch.Generator().manual_seed(61)
+    im = torch.rand(2, 240, 320, 3, generator=g)
+    refp = OD.patches(im).reshape(96, 100, 100, 3).to(torch.bfloat16)
+    exp = torch.zeros(96, 50, 50, 16, dtype=torch.bfloat16)
+    for a in range(2):
+        for b in range(2):
+            exp[..., (2 * a + b) * 3:(2 * a + b) * 3 + 3] = refp[:, a::2, b::2, :]
+    c1 = torch.full((96, 50, 50, 16), 5.0, dtype=torch.bfloat16, device=DEV)
+    ctx.extract_patches_s2d(im.to(DEV), c1, 1)
+    assert torch.equal(c1.cpu(), exp)
+    c4 = torch.full((96, 50, 50, 64), 5.0, dtype=torch.bfloat16, device=DEV)
+    ctx.extract_patches_s2d(im.to(DEV), c4, 4)
+    for k in range(4):
+        assert torch.equal(c4[:, :, :50 - k, 16 * k:16 * k + 16].cpu(), exp[:, :, k:, :])
+        if k:
+            assert float(c4[:, :, 50 - k:, 16 * k:16 * k + 16].abs().max()) == 0.0

@@ -77,3 +77,58 @@ def test_fine_first_index_maps_fold_and_embed():
     assert float((P.unpack(ks, fold.view(ks.packed_shape)) - wr.grad).abs().max()) < 1e-12
     assert torch.equal(bmap[:, 63], torch.full((4,), -1, dtype=torch.int32))
     assert torch.equal(bmap[2, :63], torch.arange(63, dtype=torch.int32) + 128)
+
+
+def _cells(patch):
+    """space-to-depth(2) of 100x100x3 patches -> flat cells [N*50*50*16] (+ zero slack), a3d_extract_patches_s2d."""
+    N = patch.shape[0]
+    cells = torch.zeros(N, 50, 50, 16, dtype=patch.dtype)
+    for a in range(2):
+        for b in range(2):
+            cells[..., (2 * a + b) * 3:(2 * a + b) * 3 + 3] = patch[:, a::2, b::2, :]
+    return torch.cat([cells.reshape(-1), torch.zeros(64, dtype=patch.dtype)])
+
+
+def test_dcnf_first_layer_embedding_is_conv_relu_maxpool():
+    """src/models.py:64-66 (11x11x3 -> 64 VALID, ReLU, 2x2 max-pool) == the 6 x 2-tap convolution (taps 4 pixels apart) of
+    the embedded filter over 64-channel pixels that are 4 consecutive 16-channel cells, then the max over the 4 groups."""
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(11, 11, 3, 64, generator=g, dtype=torch.float64)
+    bias = torch.randn(64, generator=g, dtype=torch.float64)
+    patch = torch.randn(2, 100, 100, 3, generator=g, dtype=torch.float64)
+    ref = F.max_pool2d(torch.relu(F.conv2d(patch.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), bias)), 2, 2)   # [2,64,45,45]
+    flat = _cells(patch)
+    win = flat.unfold(0, 64, 16)                      # pixel i = cells i .. i+3 (pix_pitch = 16, C = 64)
+    pix = torch.arange(2 * 50 * 50).view(2, 50, 50)
+    big = P.dcnf_first_embedded(w)
+    assert big.shape == P.DCNF_FIRST_EMBEDDED_SHAPE
+    out = torch.zeros(2, 45, 45, 256, dtype=torch.float64)
+    for tY in range(6):
+        for sv in range(2):
+            out += win[pix[:, tY:tY + 45, 4 * sv:4 * sv + 45]] @ big[:, tY, sv, :].t()
+    got = torch.relu(out.view(2, 45, 45, 4, 64).max(3).values + bias)
+    assert float((got.permute(0, 3, 1, 2) - ref).abs().max()) < 1e-11
+
+
+def test_dcnf_first_index_maps_fold_and_embed():
+    sp = {s.name: s for s in P.dcnf_specs()}
+    ks, bs = sp["unary/unary_layers/conv2d/kernel"], sp["unary/unary_layers/conv2d/bias"]
+    kmap, bmap = P.dcnf_first_index_maps(ks, bs)
+    assert kmap.shape == (4, ks.numel) and bmap.shape == (4, 64)
+    assert [int(x) for x in (kmap >= 0).sum(1)] == [11 * 11 * 3 * 64] * 4
+    w = torch.rand(11, 11, 3, 64, dtype=torch.float64) - 0.5
+    canon = P.pack(ks, w).reshape(-1)
+    big = torch.zeros(256 * 6 * 2 * 64, dtype=torch.float64)
+    for g in range(4):
+        m = kmap[g] >= 0
+        big[kmap[g][m].long()] = canon[m]
+    assert torch.equal(big.view(P.DCNF_FIRST_EMBEDDED_SHAPE), P.dcnf_first_embedded(w))
+    gb = torch.rand(big.numel(), dtype=torch.float64)
+    fold = torch.zeros_like(canon)
+    for g in range(4):
+        m = kmap[g] >= 0
+        fold[m] += gb[kmap[g][m].long()]
+    wr = w.clone().requires_grad_(True)
+    (P.dcnf_first_embedded(wr).reshape(-1) * gb).sum().backward()
+    assert float((P.unpack(ks, fold.view(ks.packed_shape)) - wr.grad).abs().max()) < 1e-12
+    assert torch.equal(bmap[1], torch.arange(64, dtype=torch.int32) + 64)
