@@ -140,6 +140,9 @@ SIGNATURES = {
     "a3d_tile_means": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "a3d_extract_patches": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
     "a3d_extract_patches_s2d": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "a3d_image_cells_s2d": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "a3d_window_gather": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "a3d_window_scatter_sum": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "a3d_comm_unique_id": (_i, [C.c_char_p, _vp]),
     "a3d_comm_init": (_i, [_vp, C.c_char_p, _vp, _i, _i]),
     "a3d_comm_destroy": (_i, [_vp]),

@@ -297,7 +297,130 @@ __global__ void extract_patches_s2d_kernel(const float* __restrict__ img, int B,
   }
 }
 
+// ---- fully convolutional unary network (DCNF): no patches at all ---------------------------------------------------------
+// The reference runs its CNN on 48 overlapping 100x100 patches per image (src/models.py:50-83).  Patches are plain windows
+// (stride 40, zero border 30) and every layer is a VALID convolution or an even-aligned 2x2 pool, so layer L of patch
+// (prow, pcol) IS a window of layer L of the zero-padded whole image: the network is evaluated ONCE per image (a third of
+// the FLOPs) and only the 7x7x256 inputs of the first dense layer are gathered per patch (windows of stride 5).
+// image_cells_s2d: zero-padded image after space-to-depth(2): cells bf16 [B][(H+2pad)/2][(W+2pad)/2][16], channel
+// (2a+b)*3+c = padded pixel (2Y+a, 2X+b, c), channels 12..15 zero.
+__global__ void image_cells_s2d_kernel(const float* __restrict__ img, int B, int H, int W, int pad, int CH, int CW,
+                                       uint16_t* __restrict__ out) {
+  size_t total = (size_t)B * CH * CW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int X = (int)(i % CW);
+    size_t t = i / CW;
+    const int Y = (int)(t % CH);
+    const int b = (int)(t / CH);
+    float f[12];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int bb = 0; bb < 2; ++bb) {
+        const int iy = 2 * Y + a - pad, ix = 2 * X + bb - pad;
+        const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+        const float* p = img + (((size_t)b * H + (ok ? iy : 0)) * W + (ok ? ix : 0)) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) f[(a * 2 + bb) * 3 + c] = ok ? p[c] : 0.f;
+      }
+    uint4* o = reinterpret_cast<uint4*>(out + i * 16);
+    o[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    o[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), 0u, 0u);
+  }
+}
+
+// out[(b, pr, pc)][i][j][:] = src[b][pr*stride + i][pc*stride + j][:]   (16-byte pieces of 8 channels)
+__global__ void window_gather_kernel(const uint4* __restrict__ src, int B, int Hs, int Ws, int C8, int rows, int cols, int win,
+                                     int stride, uint4* __restrict__ out) {
+  size_t total = (size_t)B * rows * cols * win * win * C8;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    size_t t = i / C8;
+    const int j = (int)(t % win); t /= win;
+    const int ii = (int)(t % win); t /= win;
+    const int pc = (int)(t % cols); t /= cols;
+    const int pr = (int)(t % rows);
+    const int b = (int)(t / rows);
+    out[i] = __ldg(src + (((size_t)b * Hs + pr * stride + ii) * Ws + pc * stride + j) * C8 + c);
+  }
+}
+
+// transpose of the gather: g_src[b][h][w][:] = sum over the windows that contain (h, w) of g_out[(b,pr,pc)][h-pr*stride][w-pc*stride][:]
+// (float32 sum, one bf16 rounding; gather form, no atomics)
+__global__ void window_scatter_sum_kernel(const uint4* __restrict__ g_out, int B, int Hs, int Ws, int C8, int rows, int cols,
+                                          int win, int stride, uint4* __restrict__ g_src) {
+  size_t total = (size_t)B * Hs * Ws * C8;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    size_t t = i / C8;
+    const int w = (int)(t % Ws); t /= Ws;
+    const int h = (int)(t % Hs);
+    const int b = (int)(t / Hs);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int pr = 0; pr < rows; ++pr) {
+      const int ii = h - pr * stride;
+      if (ii < 0 || ii >= win) continue;
+      for (int pc = 0; pc < cols; ++pc) {
+        const int j = w - pc * stride;
+        if (j < 0 || j >= win) continue;
+        const uint4 v = __ldg(g_out + ((((size_t)(b * rows + pr) * cols + pc) * win + ii) * win + j) * C8 + c);
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          acc[2 * k] += __uint_as_float(u[k] << 16);
+          acc[2 * k + 1] += __uint_as_float(u[k] & 0xffff0000u);
+        }
+      }
+    }
+    g_src[i] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                          pack_bf16x2(acc[6], acc[7]));
+  }
+}
+
 }  // namespace
+
+extern "C" int a3d_image_cells_s2d(a3d_ctx* ctx, const float* images, int B, int H, int W, int pad, uint16_t* cells,
+                                   void* stream) {
+  A3D_REQUIRE(ctx && images && cells && B > 0 && pad >= 0 && (H + 2 * pad) % 2 == 0 && (W + 2 * pad) % 2 == 0,
+              "image_cells_s2d: bad argument (padded size must be even)");
+  A3D_REQUIRE((reinterpret_cast<uintptr_t>(cells) & 15) == 0, "image_cells_s2d: output must be 16-byte aligned");
+  const int CH = (H + 2 * pad) / 2, CW = (W + 2 * pad) / 2;
+  size_t total = (size_t)B * CH * CW;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > (size_t)ctx->sm_count * 32) blocks = (size_t)ctx->sm_count * 32;
+  image_cells_s2d_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(images, B, H, W, pad, CH, CW, cells);
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
+extern "C" int a3d_window_gather(a3d_ctx* ctx, const uint16_t* src, int B, int Hs, int Ws, int C, int rows, int cols, int win,
+                                 int stride, uint16_t* out, void* stream) {
+  A3D_REQUIRE(ctx && src && out && B > 0 && C % 8 == 0 && rows > 0 && cols > 0 && win > 0 && stride > 0 &&
+                  (rows - 1) * stride + win <= Hs && (cols - 1) * stride + win <= Ws,
+              "window_gather: bad argument (C %% 8 == 0, windows inside the source)");
+  size_t total = (size_t)B * rows * cols * win * win * (C / 8);
+  size_t blocks = (total + 255) / 256;
+  if (blocks > (size_t)ctx->sm_count * 32) blocks = (size_t)ctx->sm_count * 32;
+  window_gather_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint4*>(src), B, Hs, Ws, C / 8, rows,
+                                                                   cols, win, stride, reinterpret_cast<uint4*>(out));
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
+
+extern "C" int a3d_window_scatter_sum(a3d_ctx* ctx, const uint16_t* g_out, int B, int Hs, int Ws, int C, int rows, int cols,
+                                      int win, int stride, uint16_t* g_src, void* stream) {
+  A3D_REQUIRE(ctx && g_out && g_src && B > 0 && C % 8 == 0 && rows > 0 && cols > 0 && win > 0 && stride > 0 &&
+                  (rows - 1) * stride + win <= Hs && (cols - 1) * stride + win <= Ws,
+              "window_scatter_sum: bad argument (C %% 8 == 0, windows inside the source)");
+  size_t total = (size_t)B * Hs * Ws * (C / 8);
+  size_t blocks = (total + 255) / 256;
+  if (blocks > (size_t)ctx->sm_count * 32) blocks = (size_t)ctx->sm_count * 32;
+  window_scatter_sum_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint4*>(g_out), B, Hs, Ws, C / 8,
+                                                                        rows, cols, win, stride,
+                                                                        reinterpret_cast<uint4*>(g_src));
+  A3D_LAUNCH_OK(ctx);
+  return 0;
+}
 
 extern "C" int a3d_extract_patches_s2d(a3d_ctx* ctx, const float* images, int B, int H, int W, uint16_t* cells, int fold,
                                        void* stream) {

@@ -12,6 +12,13 @@
 namespace {
 constexpr int H = 240, W = 320, SP = 40, ROWS = 6, COLS = 8, NSP = ROWS * COLS;     // src/models.py:16,32-35,180-181
 constexpr float SGD_LR = 0.1f, GAMMA = 1.0f;                                           // src/models.py:17,198
+// fully convolutional unary network (dcnf.py, unary = "fullconv"): zero-padded image = 150 x 190 cells of 2x2 pixels; layer
+// sizes per image: pooled first layer S0, conv2d_1 S1, its pool Q1, conv2d_2..4 S2..S4, last pool Q4 = 7x7 windows at stride 5
+constexpr int PAD = 30, CH = (H + 2 * PAD) / 2, CW = (W + 2 * PAD) / 2;
+constexpr int S0H = CH - 5, S0W = CW - 5, S1H = S0H - 4, S1W = S0W - 4, Q1H = S1H / 2, Q1W = S1W / 2;
+constexpr int S2H = Q1H - 2, S2W = Q1W - 2, S3H = S2H - 2, S3W = S2W - 2, S4H = S3H - 2, S4W = S3W - 2;
+constexpr int Q4H = S4H / 2, Q4W = S4W / 2;
+static_assert(Q4H == (ROWS - 1) * 5 + 7 && Q4W == (COLS - 1) * 5 + 7, "7x7 windows at stride 5 tile the last pooled map");
 constexpr int C0_NUMEL = 64 * 11 * 11 * 16;       // canonical first-layer filter [64][11][11][16] (3 real channels)
 constexpr int EMB0_K = 256 * 6 * 2 * 64;           // its pool-embedded form [256][6][2][64]
 enum { G_SGD = 0, G_PAIRWISE = 1 };
@@ -49,7 +56,7 @@ struct a3d_dcnf {
   size_t total, sgd_lo, sgd_hi;
   float *w, *g; uint16_t* wb;
   float *im, *dp, *c1, *c4, *z, *sims, *r, *y, *ystar, *nll, *logdet, *loss, *output, *dz, *dense_acc, *pair_ws;
-  uint16_t *cells, *wbig0, *p0, *p1, *c2, *c3, *p4, *h0, *h1, *g_big0;
+  uint16_t *cells, *wbig0, *p0, *p1, *c2, *c3, *p4, *xd, *h0, *h1, *g_big0, *g_xd;
   float* g_wbig0;
   int32_t *emb_k, *emb_b;
   uint8_t *i0, *i1, *i4;
@@ -71,20 +78,21 @@ size_t carve(a3d_dcnf* n, uint8_t* base) {
   n->w = (float*)take(T * 4); n->g = (float*)take(T * 4); n->wb = (uint16_t*)take(T * 2);
   n->im = (float*)take(B * H * W * 3 * 4);
   n->dp = (float*)take(B * H * W * 4);
-  n->cells = (uint16_t*)take(NP * 50 * 50 * 16 * 2 + 256);       // + slack: the overlapped view reads past the last row
+  n->cells = (uint16_t*)take(B * CH * CW * 16 * 2 + 256);          // + slack: the overlapped view reads past the last row
   n->wbig0 = (uint16_t*)take((size_t)EMB0_K * 2);
   n->emb_k = (int32_t*)take((size_t)4 * C0_NUMEL * 4);
   n->emb_b = (int32_t*)take(4 * 64 * 4);
-  n->p0 = (uint16_t*)take(NP * 45 * 45 * 64 * 2);
-  n->i0 = (uint8_t*)take(NP * 45 * 45 * 64);
-  n->c1 = (float*)take(NP * 41 * 41 * 256 * 4);
-  n->p1 = (uint16_t*)take(NP * 20 * 20 * 256 * 2);
-  n->i1 = (uint8_t*)take(NP * 20 * 20 * 256);
-  n->c2 = (uint16_t*)take(NP * 18 * 18 * 256 * 2);
-  n->c3 = (uint16_t*)take(NP * 16 * 16 * 256 * 2);
-  n->c4 = (float*)take(NP * 14 * 14 * 256 * 4);
-  n->p4 = (uint16_t*)take(NP * 7 * 7 * 256 * 2);
-  n->i4 = (uint8_t*)take(NP * 7 * 7 * 256);
+  n->p0 = (uint16_t*)take(B * S0H * S0W * 64 * 2);
+  n->i0 = (uint8_t*)take(B * S0H * S0W * 64);
+  n->c1 = (float*)take(B * S1H * S1W * 256 * 4);
+  n->p1 = (uint16_t*)take(B * Q1H * Q1W * 256 * 2);
+  n->i1 = (uint8_t*)take(B * Q1H * Q1W * 256);
+  n->c2 = (uint16_t*)take(B * S2H * S2W * 256 * 2);
+  n->c3 = (uint16_t*)take(B * S3H * S3W * 256 * 2);
+  n->c4 = (float*)take(B * S4H * S4W * 256 * 4);
+  n->p4 = (uint16_t*)take(B * Q4H * Q4W * 256 * 2);
+  n->i4 = (uint8_t*)take(B * Q4H * Q4W * 256);
+  n->xd = (uint16_t*)take(NP * 12544 * 2);
   n->h0 = (uint16_t*)take(NP * 128 * 2);
   n->h1 = (uint16_t*)take(NP * 16 * 2);
   n->z = (float*)take(NP * 4);
@@ -106,14 +114,15 @@ size_t carve(a3d_dcnf* n, uint8_t* base) {
     n->g_z = (uint16_t*)take(NP * 2);
     n->g_h1a = (uint16_t*)take(NP * 16 * 2); n->g_h1 = (uint16_t*)take(NP * 16 * 2);
     n->g_h0a = (uint16_t*)take(NP * 128 * 2); n->g_h0 = (uint16_t*)take(NP * 128 * 2);
-    n->g_p4 = (uint16_t*)take(NP * 7 * 7 * 256 * 2);
-    n->g_c4 = (uint16_t*)take(NP * 14 * 14 * 256 * 2);
-    n->g_c3 = (uint16_t*)take(NP * 16 * 16 * 256 * 2);
-    n->g_c2 = (uint16_t*)take(NP * 18 * 18 * 256 * 2);
-    n->g_p1 = (uint16_t*)take(NP * 20 * 20 * 256 * 2);
-    n->g_c1 = (uint16_t*)take(NP * 41 * 41 * 256 * 2);
-    n->g_p0 = (uint16_t*)take(NP * 45 * 45 * 64 * 2);
-    n->g_big0 = (uint16_t*)take(NP * 45 * 45 * 256 * 2);
+    n->g_xd = (uint16_t*)take(NP * 12544 * 2);
+    n->g_p4 = (uint16_t*)take(B * Q4H * Q4W * 256 * 2);
+    n->g_c4 = (uint16_t*)take(B * S4H * S4W * 256 * 2);
+    n->g_c3 = (uint16_t*)take(B * S3H * S3W * 256 * 2);
+    n->g_c2 = (uint16_t*)take(B * S2H * S2W * 256 * 2);
+    n->g_p1 = (uint16_t*)take(B * Q1H * Q1W * 256 * 2);
+    n->g_c1 = (uint16_t*)take(B * S1H * S1W * 256 * 2);
+    n->g_p0 = (uint16_t*)take(B * S0H * S0W * 64 * 2);
+    n->g_big0 = (uint16_t*)take(B * S0H * S0W * 256 * 2);
     n->g_wbig0 = (float*)take(((size_t)EMB0_K + 256) * 4);
   }
   size_t sc = 256;
@@ -148,17 +157,16 @@ void init_layout(a3d_dcnf* n, a3d_ctx* ctx, int batch, int in_h, int in_w, int d
     }
   }
   n->total = off;
-  const int NP = n->NP;
   // src/models.py:64-66 (11x11x3 -> 64, ReLU, 2x2 max-pool) as one pool-fused 6x6-cell convolution over the
-  // space-to-depth(2) patches, read through the overlapped-pixel view (a3d_extract_patches_s2d, dcnf.py)
-  n->d0 = valid_desc(NP, 50, 50, 64, 256, 6);
-  n->d0.S = 2; n->d0.P = n->d0.Q = 45; n->d0.ldy = 64; n->d0.dil_w = 4; n->d0.pix_pitch = 16;
+  // space-to-depth(2) image, read through the overlapped-pixel view (a3d_image_cells_s2d, dcnf.py)
+  n->d0 = valid_desc(batch, CH, CW, 64, 256, 6);
+  n->d0.S = 2; n->d0.P = S0H; n->d0.Q = S0W; n->d0.ldy = 64; n->d0.dil_w = 4; n->d0.pix_pitch = 16;
   n->d0w = n->d0;
   n->d0w.ldy = 256;
-  n->d1 = valid_desc(NP, 45, 45, 64, 256, 5);             // :67
-  n->d2 = valid_desc(NP, 20, 20, 256, 256, 3);            // :69
-  n->d3 = valid_desc(NP, 18, 18, 256, 256, 3);            // :71
-  n->d4 = valid_desc(NP, 16, 16, 256, 256, 3);            // :72
+  n->d1 = valid_desc(batch, S0H, S0W, 64, 256, 5);        // :67
+  n->d2 = valid_desc(batch, Q1H, Q1W, 256, 256, 3);       // :69
+  n->d3 = valid_desc(batch, S2H, S2W, 256, 256, 3);       // :71
+  n->d4 = valid_desc(batch, S3H, S3W, 256, 256, 3);       // :72
 }
 
 size_t seg_off(const a3d_dcnf* n, const char* name) {
@@ -177,20 +185,22 @@ int forward(a3d_dcnf* n, const float* images, const float* depths, void* st) {
   CK(a3d_resize_bilinear_tf1(c, images, B, n->inH, n->inW, 3, n->im, H, W, 3, A3D_F32, st));
   if (depths) CK(a3d_resize_bilinear_tf1(c, depths, B, n->dH, n->dW, 1, n->dp, H, W, 1, A3D_F32, st));
   // unary part (src/models.py:61-89) on all B*48 patches at once
-  CK(a3d_extract_patches_s2d(c, n->im, B, H, W, n->cells, 1, st));
+  CK(a3d_image_cells_s2d(c, n->im, B, H, W, PAD, n->cells, st));
   CK(a3d_conv2d_pool4_fwd(c, &n->d0, n->cells, n->wbig0, Wf(U "conv2d/bias"), n->p0, n->i0, A3D_EPI_RELU, nullptr, 0, st));
   CK(a3d_conv2d_fwd(c, &n->d1, n->p0, Wb(U "conv2d_1/kernel"), Wf(U "conv2d_1/bias"), n->c1, A3D_F32, A3D_EPI_RELU, n->scratch,
                     n->scratch_bytes, st));
-  CK(a3d_maxpool2x2_fwd_f32(c, n->c1, NP, 41, 41, 256, n->p1, 256, n->i1, st));
+  CK(a3d_maxpool2x2_fwd_f32(c, n->c1, B, S1H, S1W, 256, n->p1, 256, n->i1, st));
   CK(a3d_conv2d_fwd(c, &n->d2, n->p1, Wb(U "conv2d_2/kernel"), Wf(U "conv2d_2/bias"), n->c2, A3D_BF16, A3D_EPI_RELU, n->scratch,
                     n->scratch_bytes, st));
   CK(a3d_conv2d_fwd(c, &n->d3, n->c2, Wb(U "conv2d_3/kernel"), Wf(U "conv2d_3/bias"), n->c3, A3D_BF16, A3D_EPI_RELU, n->scratch,
                     n->scratch_bytes, st));
   CK(a3d_conv2d_fwd(c, &n->d4, n->c3, Wb(U "conv2d_4/kernel"), Wf(U "conv2d_4/bias"), n->c4, A3D_F32, A3D_EPI_RELU, n->scratch,
                     n->scratch_bytes, st));
-  CK(a3d_maxpool2x2_fwd_f32(c, n->c4, NP, 14, 14, 256, n->p4, 256, n->i4, st));
+  CK(a3d_maxpool2x2_fwd_f32(c, n->c4, B, S4H, S4W, 256, n->p4, 256, n->i4, st));
+  // patch (prow, pcol) reads the 7x7x256 window at (5 prow, 5 pcol) of the last pooled map
+  CK(a3d_window_gather(c, n->p4, B, Q4H, Q4W, 256, ROWS, COLS, 7, 5, n->xd, st));
   // the 768-row dense layer goes in chunks of 256 rows inside a3d_dense_fwd; the two tiny ones run on the CUDA cores
-  CK(a3d_dense_fwd(c, n->p4, 12544, Wb(U "dense/kernel"), Wf(U "dense/bias"), nullptr, 0.f, n->h0, A3D_BF16, n->dense_acc, NP, 128,
+  CK(a3d_dense_fwd(c, n->xd, 12544, Wb(U "dense/kernel"), Wf(U "dense/bias"), nullptr, 0.f, n->h0, A3D_BF16, n->dense_acc, NP, 128,
                    12544, A3D_EPI_RELU, A3D_IMPL_AUTO, st));
   CK(a3d_dense_fwd(c, n->h0, 128, Wb(U "dense_1/kernel"), Wf(U "dense_1/bias"), nullptr, 0.f, n->h1, A3D_BF16, n->dense_acc, NP, 16,
                    128, A3D_EPI_SIGMOID, A3D_IMPL_SIMT, st));
@@ -224,21 +234,22 @@ int backward(a3d_dcnf* n, void* st) {
   CK(a3d_dense_wgrad(c, n->h0, 128, n->g_h1, 16, G(U "dense_1/kernel"), G(U "dense_1/bias"), NP, 16, 128, S, st));
   CK(a3d_dense_dgrad(c, n->g_h1, 16, Wb(U "dense_1/kernel"), n->g_h0a, n->dense_acc, NP, 16, 128, S, st));
   CK(a3d_dense_epilogue_bwd(c, n->g_h0a, n->h0, nullptr, 0.f, n->g_h0, (size_t)NP * 128, A3D_EPI_RELU, st));
-  CK(a3d_dense_wgrad(c, n->p4, 12544, n->g_h0, 128, G(U "dense/kernel"), G(U "dense/bias"), NP, 128, 12544, A3D_IMPL_AUTO, st));
-  CK(a3d_dense_dgrad(c, n->g_h0, 128, Wb(U "dense/kernel"), n->g_p4, n->dense_acc, NP, 128, 12544, S, st));
-  CK(a3d_maxpool2x2_idx_bwd(c, n->i4, n->g_p4, 256, NP, 14, 14, 256, n->g_c4, st));
+  CK(a3d_dense_wgrad(c, n->xd, 12544, n->g_h0, 128, G(U "dense/kernel"), G(U "dense/bias"), NP, 128, 12544, A3D_IMPL_AUTO, st));
+  CK(a3d_dense_dgrad(c, n->g_h0, 128, Wb(U "dense/kernel"), n->g_xd, n->dense_acc, NP, 128, 12544, S, st));
+  CK(a3d_window_scatter_sum(c, n->g_xd, n->B, Q4H, Q4W, 256, ROWS, COLS, 7, 5, n->g_p4, st));
+  CK(a3d_maxpool2x2_idx_bwd(c, n->i4, n->g_p4, 256, n->B, S4H, S4W, 256, n->g_c4, st));
   CK(a3d_conv2d_wgrad(c, &n->d4, n->c3, n->g_c4, G(U "conv2d_4/kernel"), G(U "conv2d_4/bias"), n->scratch, n->scratch_bytes, st));
   CK(a3d_conv2d_dgrad(c, &n->d4, n->g_c4, Wb(U "conv2d_4/kernel"), n->g_c3, n->c3, n->scratch, n->scratch_bytes, st));
   CK(a3d_conv2d_wgrad(c, &n->d3, n->c2, n->g_c3, G(U "conv2d_3/kernel"), G(U "conv2d_3/bias"), n->scratch, n->scratch_bytes, st));
   CK(a3d_conv2d_dgrad(c, &n->d3, n->g_c3, Wb(U "conv2d_3/kernel"), n->g_c2, n->c2, n->scratch, n->scratch_bytes, st));
   CK(a3d_conv2d_wgrad(c, &n->d2, n->p1, n->g_c2, G(U "conv2d_2/kernel"), G(U "conv2d_2/bias"), n->scratch, n->scratch_bytes, st));
   CK(a3d_conv2d_dgrad(c, &n->d2, n->g_c2, Wb(U "conv2d_2/kernel"), n->g_p1, nullptr, n->scratch, n->scratch_bytes, st));
-  CK(a3d_maxpool2x2_idx_bwd(c, n->i1, n->g_p1, 256, NP, 41, 41, 256, n->g_c1, st));
+  CK(a3d_maxpool2x2_idx_bwd(c, n->i1, n->g_p1, 256, n->B, S1H, S1W, 256, n->g_c1, st));
   CK(a3d_conv2d_wgrad(c, &n->d1, n->p0, n->g_c1, G(U "conv2d_1/kernel"), G(U "conv2d_1/bias"), n->scratch, n->scratch_bytes, st));
   CK(a3d_conv2d_dgrad(c, &n->d1, n->g_c1, Wb(U "conv2d_1/kernel"), n->g_p0, nullptr, n->scratch, n->scratch_bytes, st));
   // first layer: MaxPoolGrad + ReluGrad onto the 4 x 64 GEMM columns, weight gradient of the embedded filter, then its
   // four copies (and the four bias groups) folded into the canonical variable (the 13 padding channels receive 0)
-  CK(a3d_pool4_bwd(c, n->g_p0, 64, n->p0, 64, n->i0, n->g_big0, (size_t)NP * 45 * 45, st));
+  CK(a3d_pool4_bwd(c, n->g_p0, 64, n->p0, 64, n->i0, n->g_big0, (size_t)n->B * S0H * S0W, st));
   CK(a3d_conv2d_wgrad(c, &n->d0w, n->cells, n->g_big0, n->g_wbig0, n->g_wbig0 + EMB0_K, n->scratch, n->scratch_bytes, st));
   CK(a3d_gather_sum_f32(c, n->g_wbig0, n->emb_k, 4, C0_NUMEL, G(U "conv2d/kernel"), st));
   return a3d_gather_sum_f32(c, n->g_wbig0 + EMB0_K, n->emb_b, 4, 64, G(U "conv2d/bias"), st);

@@ -24,7 +24,7 @@ H, W = 240, 320            # src/models.py:180-181
 SP = 40                    # src/models.py:16
 SGD_LR = 0.1               # src/models.py:198
 GAMMA = 1.0                # src/models.py:17
-PATCH_C = 16               # 3 image channels stored as 16 (32-byte pixels: the im2col TMA minimum)
+PATCH_PAD = 30             # zero border of the SAME patch extraction (100x100 windows, stride 40; src/models.py:50-59)
 
 
 def num_superpixels(h=H, w=W):
@@ -62,7 +62,7 @@ def pair_indices(h=H, w=W):
 class DCNFNet:
     def __init__(self, ctx: ops.Context, batch: int, in_hw=(480, 640), depth_hw=(480, 640), train=True,
                  impl=L.IMPL_AUTO, naive_loss=True, comm=None, graph="reference", r_nonneg=False, train_pairwise=False,
-                 predict="unary"):
+                 predict="unary", unary="fullconv"):
         """Beyond-reference options (defaults reproduce the reference):
              graph="grid4"        every neighbour pair of the tile grid (82 pairs != 48 nodes) instead of the reference's
                                   checkerboard star graph (src/models.py:20-30);
@@ -72,7 +72,7 @@ class DCNFNet:
              predict="map"        the output is the CRF's MAP estimate y* = A^-1 z (Liu et al. eq. 12), bilinearly upsampled,
                                   instead of the unary prediction the reference upsamples (src/models.py:187-191)."""
         self.ctx, self.B, self.train, self.impl, self.naive = ctx, batch, train, impl, naive_loss
-        assert graph in ("reference", "grid4") and predict in ("unary", "map")
+        assert graph in ("reference", "grid4") and predict in ("unary", "map") and unary in ("fullconv", "patches")
         self.r_nonneg, self.train_pairwise, self.predict = r_nonneg, train_pairwise, predict
         self.dev = torch.device(f"cuda:{ctx.device}")
         self.comm = comm
@@ -95,39 +95,61 @@ class DCNFNet:
         self.depths = z(B, depth_hw[0], depth_hw[1], 1, **f32)
         self.im = z(B, H, W, 3, **f32)
         self.dp = z(B, H, W, 1, **f32)
-        # First layer (src/models.py:64-66: 11x11x3 -> 64, ReLU, 2x2 max-pool) as ONE pool-fused convolution over the
-        # space-to-depth(2) patches: 50 x 50 cells of 16 channels, read 4 cells (128 bytes) per tap through an overlapped
-        # view (params.dcnf_first_embedded).  `first_fold` = 1: the view (pix_pitch 16 over the cell tensor, 61 MB at
-        # B = 16); 4: the same pixels materialised (245 MB).  The 100x100x16 patch tensor, the 1.6 GB float32 conv output
-        # and its separate pool pass of the plain formulation do not exist.
+        # Unary CNN (src/models.py:61-83).  unary = "fullconv" (default): the patches are plain windows (stride 40, zero
+        # border 30) and every layer is a VALID convolution or an even-aligned 2x2 pool, so each layer of patch
+        # (prow, pcol) IS a window of the same layer of the zero-padded whole image -- the network runs ONCE per image
+        # (N0 = B images of 150 x 190 cells, a third of the FLOPs of 48 overlapping patches, no patch tensor at all) and
+        # only the 7x7x256 inputs of the first dense layer are gathered per patch (windows of stride 5,
+        # a3d_window_gather / a3d_window_scatter_sum).  unary = "patches": the reference's literal formulation (N0 = B*48
+        # patches of 50 x 50 cells) on the same kernels; kept as the cross-check of the fully convolutional form.
+        # First layer (:64-66: 11x11x3 -> 64, ReLU, 2x2 max-pool) in both forms: ONE pool-fused convolution over
+        # space-to-depth(2) cells of 16 channels, read 4 cells (128 bytes) per tap through an overlapped-pixel view
+        # (params.dcnf_first_embedded; a3d_conv_desc dil_w = 4, pix_pitch = 16).  `first_fold` = 4 materialises the view.
+        self.unary = unary
         self.first_fold = int(os.environ.get("A3D_DCNF_FIRST_FOLD", "1"))
-        assert self.first_fold in (1, 4)
-        ncell = NP * 50 * 50 * 16 * self.first_fold
+        assert self.first_fold in (1, 4) and (self.first_fold == 1 or unary == "patches")
+        if unary == "fullconv":
+            N0, ch, cw = B, (H + 2 * PATCH_PAD) // 2, (W + 2 * PATCH_PAD) // 2
+        else:
+            N0, ch, cw = NP, 50, 50
+        self.N0 = N0
+        s0 = (ch - 5, cw - 5)                          # pooled first layer (one output per cell)
+        s1 = (s0[0] - 4, s0[1] - 4)                    # conv2d_1 5x5
+        q1 = (s1[0] // 2, s1[1] // 2)
+        s2 = (q1[0] - 2, q1[1] - 2)
+        s3 = (s2[0] - 2, s2[1] - 2)
+        s4 = (s3[0] - 2, s3[1] - 2)
+        q4 = (s4[0] // 2, s4[1] // 2)
+        self.s1, self.s4, self.q4 = s1, s4, q4
+        assert q4 == (((rows - 1) * 5 + 7, (cols - 1) * 5 + 7) if unary == "fullconv" else (7, 7))
+        ncell = N0 * ch * cw * 16 * self.first_fold
         self._cells = z(ncell + 128, **bf)             # + slack: the last positions of the last row read past the end
-        self.cells = self._cells[:ncell].view(NP, 50, 50, 16 * self.first_fold)
+        self.cells = self._cells[:ncell].view(N0, ch, cw, 16 * self.first_fold)
         cd = ops.conv_desc
-        d0 = cd(NP, 50, 50, 64, 256, 6, 2, 1, "valid", ldy=64, impl=impl)
-        d0.P = d0.Q = 45
+        d0 = cd(N0, ch, cw, 64, 256, 6, 2, 1, "valid", ldy=64, impl=impl)
+        d0.P, d0.Q = s0
         d0.dil_w = 4
         d0.pix_pitch = 16 if self.first_fold == 1 else 0
         self.d0 = d0
-        self.d0w = L.ConvDesc.from_buffer_copy(d0)   # the weight gradient sees the 4 x 64 GEMM columns
+        self.d0w = L.ConvDesc.from_buffer_copy(d0)     # the weight gradient sees the 4 x 64 GEMM columns
         self.d0w.ldy = 256
         self.wbig0 = z(*DCNF_FIRST_EMBEDDED_SHAPE, **bf)
         km, bm = dcnf_first_index_maps(self.arena.specs["unary/unary_layers/conv2d/kernel"],
                                        self.arena.specs["unary/unary_layers/conv2d/bias"])
         self.emb_k, self.emb_b = km.to(self.dev), bm.to(self.dev)
-        self.d1 = cd(NP, 45, 45, 64, 256, 5, 5, 1, "valid", impl=impl)              # :67
-        self.d2 = cd(NP, 20, 20, 256, 256, 3, 3, 1, "valid", impl=impl)             # :69
-        self.d3 = cd(NP, 18, 18, 256, 256, 3, 3, 1, "valid", impl=impl)             # :71
-        self.d4 = cd(NP, 16, 16, 256, 256, 3, 3, 1, "valid", impl=impl)             # :72
-        self.p0, self.i0 = z(NP, 45, 45, 64, **bf), z(NP, 45, 45, 64, **u8)
-        self.c1 = z(NP, 41, 41, 256, **f32)
-        self.p1, self.i1 = z(NP, 20, 20, 256, **bf), z(NP, 20, 20, 256, **u8)
-        self.c2 = z(NP, 18, 18, 256, **bf)
-        self.c3 = z(NP, 16, 16, 256, **bf)
-        self.c4 = z(NP, 14, 14, 256, **f32)
-        self.p4, self.i4 = z(NP, 7, 7, 256, **bf), z(NP, 7, 7, 256, **u8)
+        self.d1 = cd(N0, s0[0], s0[1], 64, 256, 5, 5, 1, "valid", impl=impl)        # :67
+        self.d2 = cd(N0, q1[0], q1[1], 256, 256, 3, 3, 1, "valid", impl=impl)       # :69
+        self.d3 = cd(N0, s2[0], s2[1], 256, 256, 3, 3, 1, "valid", impl=impl)       # :71
+        self.d4 = cd(N0, s3[0], s3[1], 256, 256, 3, 3, 1, "valid", impl=impl)       # :72
+        self.p0, self.i0 = z(N0, *s0, 64, **bf), z(N0, *s0, 64, **u8)
+        self.c1 = z(N0, *s1, 256, **f32)
+        self.p1, self.i1 = z(N0, *q1, 256, **bf), z(N0, *q1, 256, **u8)
+        self.c2 = z(N0, *s2, 256, **bf)
+        self.c3 = z(N0, *s3, 256, **bf)
+        self.c4 = z(N0, *s4, 256, **f32)
+        self.p4, self.i4 = z(N0, *q4, 256, **bf), z(N0, *q4, 256, **u8)
+        # the first dense layer's input: one 7x7x256 window per patch
+        self.xd = z(NP, 12544, **bf) if unary == "fullconv" else self.p4.view(NP, 12544)
         self.h0 = z(NP, 128, **bf)
         self.h1 = z(NP, 16, **bf)
         self.z = z(NP, 1, **f32)
@@ -144,14 +166,15 @@ class DCNFNet:
             self.g_z = z(NP, 1, **bf)
             self.g_h1a, self.g_h1 = z(NP, 16, **bf), z(NP, 16, **bf)
             self.g_h0a, self.g_h0 = z(NP, 128, **bf), z(NP, 128, **bf)
-            self.g_p4 = z(NP, 7, 7, 256, **bf)
-            self.g_c4 = z(NP, 14, 14, 256, **bf)
-            self.g_c3a, self.g_c3 = z(NP, 16, 16, 256, **bf), z(NP, 16, 16, 256, **bf)
-            self.g_c2a, self.g_c2 = z(NP, 18, 18, 256, **bf), z(NP, 18, 18, 256, **bf)
-            self.g_p1 = z(NP, 20, 20, 256, **bf)
-            self.g_c1 = z(NP, 41, 41, 256, **bf)
-            self.g_p0 = z(NP, 45, 45, 64, **bf)
-            self.g_big0 = z(NP * 45 * 45, 256, **bf)       # gradient on the 4 x 64 pool-window columns
+            self.g_p4 = z(N0, *q4, 256, **bf)
+            self.g_xd = z(NP, 12544, **bf) if unary == "fullconv" else self.g_p4.view(NP, 12544)
+            self.g_c4 = z(N0, *s4, 256, **bf)
+            self.g_c3 = z(N0, *s3, 256, **bf)
+            self.g_c2 = z(N0, *s2, 256, **bf)
+            self.g_p1 = z(N0, *q1, 256, **bf)
+            self.g_c1 = z(N0, *s1, 256, **bf)
+            self.g_p0 = z(N0, *s0, 64, **bf)
+            self.g_big0 = z(N0 * s0[0] * s0[1], 256, **bf)   # gradient on the 4 x 64 pool-window columns
             nk = 256 * 6 * 2 * 64
             self.g_wbig0 = z(nk + 256, **f32)
 
@@ -188,7 +211,10 @@ class DCNFNet:
         c.resize_bilinear_tf1(self.images, H, W, out=self.im)
         c.resize_bilinear_tf1(self.depths, H, W, out=self.dp)
         # unary part (src/models.py:61-89) on all B*48 patches at once
-        c.extract_patches_s2d(self.im, self.cells, self.first_fold)
+        if self.unary == "fullconv":
+            c.image_cells_s2d(self.im, PATCH_PAD, self.cells)
+        else:
+            c.extract_patches_s2d(self.im, self.cells, self.first_fold)
         c.conv2d_pool4_fwd(self.d0, self.cells, self.wbig0, self.wf(U + "conv2d/bias"), relu=True, out=self.p0, idx=self.i0)
         c.conv2d_fwd(self.d1, self.p0, self.w(U + "conv2d_1" + K), self.wf(U + "conv2d_1/bias"), relu=True, out=self.c1)
         c.maxpool2x2_fwd_f32(self.c1, out=self.p1, idx=self.i1)
@@ -196,7 +222,10 @@ class DCNFNet:
         c.conv2d_fwd(self.d3, self.c2, self.w(U + "conv2d_3" + K), self.wf(U + "conv2d_3/bias"), relu=True, out=self.c3)
         c.conv2d_fwd(self.d4, self.c3, self.w(U + "conv2d_4" + K), self.wf(U + "conv2d_4/bias"), relu=True, out=self.c4)
         c.maxpool2x2_fwd_f32(self.c4, out=self.p4, idx=self.i4)
-        c.dense_fwd(self.p4.view(NP, 12544), self.w(U + "dense" + K), self.wf(U + "dense/bias"), flags=L.EPI_RELU,
+        if self.unary == "fullconv":                  # patch (prow, pcol) reads the 7x7 window at (5 prow, 5 pcol)
+            rows, cols = num_superpixels()
+            c.window_gather(self.p4, rows, cols, 7, 5, self.xd)
+        c.dense_fwd(self.xd, self.w(U + "dense" + K), self.wf(U + "dense/bias"), flags=L.EPI_RELU,
                     out=self.h0, impl=self.impl)
         c.dense_fwd(self.h0, self.w(U + "dense_1" + K), self.wf(U + "dense_1/bias"), flags=L.EPI_SIGMOID, out=self.h1,
                     impl=L.IMPL_SIMT)
@@ -237,24 +266,27 @@ class DCNFNet:
         c.dense_wgrad(self.h0, self.g_h1, dw=self.gw(U + "dense_1" + K), db=self.gw(U + "dense_1/bias"), impl=S)
         c.dense_dgrad(self.g_h1, self.w(U + "dense_1" + K), out=self.g_h0a, impl=S)
         c.dense_epilogue_bwd(self.g_h0a, self.h0, None, 0.0, L.EPI_RELU, out=self.g_h0)
-        c.dense_wgrad(self.p4.view(NP, 12544), self.g_h0, dw=self.gw(U + "dense" + K), db=self.gw(U + "dense/bias"),
-                      impl=self.impl)
-        c.dense_dgrad(self.g_h0, self.w(U + "dense" + K), out=self.g_p4.view(NP, 12544), impl=S)
-        c.maxpool2x2_idx_bwd(self.i4, self.g_p4, (NP, 14, 14, 256), out=self.g_c4)
+        c.dense_wgrad(self.xd, self.g_h0, dw=self.gw(U + "dense" + K), db=self.gw(U + "dense/bias"), impl=self.impl)
+        c.dense_dgrad(self.g_h0, self.w(U + "dense" + K), out=self.g_xd, impl=S)
+        if self.unary == "fullconv":                  # shared activations: sum over the (up to 4) windows covering them
+            rows, cols = num_superpixels()
+            c.window_scatter_sum(self.g_xd, rows, cols, 7, 5, self.g_p4)
+        N0 = self.N0
+        c.maxpool2x2_idx_bwd(self.i4, self.g_p4, (N0, *self.s4, 256), out=self.g_c4)
         c.conv2d_wgrad(self.d4, self.c3, self.g_c4, dw=self.gw(U + "conv2d_4" + K), db=self.gw(U + "conv2d_4/bias"))
         c.conv2d_dgrad(self.d4, self.g_c4, self.w(U + "conv2d_4" + K), out=self.g_c3, relu_src=self.c3)
         c.conv2d_wgrad(self.d3, self.c2, self.g_c3, dw=self.gw(U + "conv2d_3" + K), db=self.gw(U + "conv2d_3/bias"))
         c.conv2d_dgrad(self.d3, self.g_c3, self.w(U + "conv2d_3" + K), out=self.g_c2, relu_src=self.c2)
         c.conv2d_wgrad(self.d2, self.p1, self.g_c2, dw=self.gw(U + "conv2d_2" + K), db=self.gw(U + "conv2d_2/bias"))
         c.conv2d_dgrad(self.d2, self.g_c2, self.w(U + "conv2d_2" + K), out=self.g_p1)
-        c.maxpool2x2_idx_bwd(self.i1, self.g_p1, (NP, 41, 41, 256), out=self.g_c1)
+        c.maxpool2x2_idx_bwd(self.i1, self.g_p1, (N0, *self.s1, 256), out=self.g_c1)
         c.conv2d_wgrad(self.d1, self.p0, self.g_c1, dw=self.gw(U + "conv2d_1" + K), db=self.gw(U + "conv2d_1/bias"))
         c.conv2d_dgrad(self.d1, self.g_c1, self.w(U + "conv2d_1" + K), out=self.g_p0)
         # first layer: MaxPoolGrad + ReluGrad onto the 4 x 64 GEMM columns, weight gradient of the embedded filter, then
         # fold its four copies (and the four bias groups) into the canonical variable (padding channels receive 0)
         c.pool4_bwd(self.g_p0.view(-1, 64), self.p0.view(-1, 64), self.i0, out=self.g_big0)
         nk = 256 * 6 * 2 * 64
-        c.conv2d_wgrad(self.d0w, self.cells, self.g_big0.view(NP, 45, 45, 256), dw=self.g_wbig0[:nk].view(256, 6, 2, 64),
+        c.conv2d_wgrad(self.d0w, self.cells, self.g_big0.view(N0, self.d0.P, self.d0.Q, 256), dw=self.g_wbig0[:nk].view(256, 6, 2, 64),
                        db=self.g_wbig0[nk:])
         c.gather_sum_f32(self.g_wbig0[:nk], self.emb_k, self.gw(U + "conv2d" + K))
         c.gather_sum_f32(self.g_wbig0[nk:], self.emb_b, self.gw(U + "conv2d/bias"))

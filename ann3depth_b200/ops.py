@@ -595,6 +595,24 @@ class Context:
                 "extract_patches_s2d")
         return out
 
+    def image_cells_s2d(self, images, pad, out):
+        """Zero-padded image after space-to-depth(2): out bf16 [B, (H+2pad)/2, (W+2pad)/2, 16] (a3d_image_cells_s2d)."""
+        B, H, W, _ = images.shape
+        L.check(self.lib.a3d_image_cells_s2d(self.h, _ptr(images), B, H, W, pad, _ptr(out), _stream()), "image_cells_s2d")
+        return out
+
+    def window_gather(self, src, rows, cols, win, stride, out):
+        B, Hs, Ws, Cc = src.shape
+        L.check(self.lib.a3d_window_gather(self.h, _ptr(src), B, Hs, Ws, Cc, rows, cols, win, stride, _ptr(out), _stream()),
+                "window_gather")
+        return out
+
+    def window_scatter_sum(self, g_out, rows, cols, win, stride, g_src):
+        B, Hs, Ws, Cc = g_src.shape
+        L.check(self.lib.a3d_window_scatter_sum(self.h, _ptr(g_out), B, Hs, Ws, Cc, rows, cols, win, stride, _ptr(g_src),
+                                                _stream()), "window_scatter_sum")
+        return g_src
+
     # ------------------------------------------------------------------ data parallel
     def comm_init(self, id_bytes: bytes, rank: int, nranks: int, nccl_path: str | None = None):
         buf = C.create_string_buffer(id_bytes, 128)

@@ -335,6 +335,18 @@ int a3d_extract_patches(a3d_ctx*, const float* images, int B, int H, int W, uint
  * pix_pitch = 16}: whole 128-byte rows per TMA load, a quarter of the bytes.  The caller keeps >= 128 zero bytes after
  * the fold = 1 tensor (the last positions of the last row read past it, against zero weights). */
 int a3d_extract_patches_s2d(a3d_ctx*, const float* images, int B, int H, int W, uint16_t* cells, int fold, void* stream);
+/* Fully convolutional form of the DCNF unary network (src/models.py:50-83): the patches are plain windows (stride 40,
+ * zero border 30) and every layer is a VALID convolution or an even-aligned 2x2 pool, so each layer of patch (prow, pcol)
+ * is a window of the same layer of the zero-padded whole image.  a3d_image_cells_s2d: the padded image after
+ * space-to-depth(2), cells bf16 [B][(H+2pad)/2][(W+2pad)/2][16] (channel (2a+b)*3+c, 12..15 zero; keep >= 128 zero bytes
+ * after it for the overlapped view).  a3d_window_gather: out [B*rows*cols][win][win][C] = the windows of src [B,Hs,Ws,C]
+ * at stride `stride` (the per-patch inputs of the first dense layer: 7x7x256 at stride 5).  a3d_window_scatter_sum: its
+ * transpose for the backward pass (float32 sum over the overlapping windows, one bf16 rounding). */
+int a3d_image_cells_s2d(a3d_ctx*, const float* images, int B, int H, int W, int pad, uint16_t* cells, void* stream);
+int a3d_window_gather(a3d_ctx*, const uint16_t* src, int B, int Hs, int Ws, int C, int rows, int cols, int win, int stride,
+                      uint16_t* out, void* stream);
+int a3d_window_scatter_sum(a3d_ctx*, const uint16_t* g_out, int B, int Hs, int Ws, int C, int rows, int cols, int win,
+                           int stride, uint16_t* g_src, void* stream);
 
 /* ---- data parallelism (replaces the PS/gRPC replication of src/ann3depth.py:78-92) ---------- */
 /* NCCL is dlopen()ed at first use (path = NULL -> "libnccl.so.2"). */

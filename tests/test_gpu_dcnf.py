@@ -151,3 +151,32 @@ def test_dcnf_beyond_reference_options():
     lo, hi = net.arena.group_range("Pairwise")
     assert torch.allclose(net.arena.w[lo:hi], w0[lo:hi] - 0.1 * net.arena.g[lo:hi], atol=1e-7)
     assert not torch.equal(net.arena.w[lo:hi], w0[lo:hi])
+
+
+def test_dcnf_fully_convolutional_equals_patchwise():
+    """The default evaluation runs the unary CNN ONCE per zero-padded image and gathers 7x7 windows for the dense layers;
+    unary="patches" runs the reference's literal formulation (48 overlapping 100x100 patches, src/models.py:50-83) on the
+    same kernels.  Same forward values (each output is the same dot product), same gradients up to the bf16 rounding of
+    activation gradients that the fully convolutional form sums over overlapping patches before rounding."""
+    B = 2
+    images, depths, p = make(B, seed=8)
+    res = {}
+    for mode in ("fullconv", "patches"):
+        op = models.dcnf(images.to(DEV), depths.to(DEV), train=True, naive_loss=False, unary=mode)
+        net = op.net
+        net.load_params(p)
+        net.forward()
+        net.backward()
+        torch.cuda.synchronize()
+        res[mode] = (net.z.clone(), net.h0.clone(), float(net.loss), net.export_grads())
+    zf, zp = res["fullconv"][0], res["patches"][0]
+    print("z max diff", float((zf - zp).abs().max()), "h0 max diff", float((res["fullconv"][1].float() - res["patches"][1].float()).abs().max()))
+    assert float((zf - zp).abs().max()) <= 1e-3 * float(zp.abs().max())
+    assert abs(res["fullconv"][2] - res["patches"][2]) < 1e-3 * max(1.0, abs(res["patches"][2]))
+    for name, g in res["patches"][3].items():
+        if name.startswith("pairwise"):
+            continue
+        c = cos(res["fullconv"][3][name], g)
+        nr = float(res["fullconv"][3][name].double().norm() / (g.double().norm() + 1e-300))
+        print(f"{name:36s} cos={c:.7f} norm ratio={nr:.5f}")
+        assert c >= 0.9999 and 0.99 < nr < 1.01, name

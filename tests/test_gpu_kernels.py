@@ -871,3 +871,34 @@ def test_extract_patches_s2d(ctx):
         assert torch.equal(c4[:, :, :50 - k, 16 * k:16 * k + 16].cpu(), exp[:, :, k:, :])
         if k:
             assert float(c4[:, :, 50 - k:, 16 * k:16 * k + 16].abs().max()) == 0.0
+
+
+def test_image_cells_and_window_gather_scatter(ctx):
+    g = torch.Generator().manual_seed(62)
+    im = torch.rand(2, 240, 320, 3, generator=g)
+    cells = torch.full((2, 150, 190, 16), 5.0, dtype=torch.bfloat16, device=DEV)
+    ctx.image_cells_s2d(im.to(DEV), 30, cells)
+    pad = F.pad(im.permute(0, 3, 1, 2), (30, 30, 30, 30)).permute(0, 2, 3, 1).to(torch.bfloat16)     # [2,300,380,3]
+    exp = torch.zeros(2, 150, 190, 16, dtype=torch.bfloat16)
+    for a in range(2):
+        for b in range(2):
+            exp[..., (2 * a + b) * 3:(2 * a + b) * 3 + 3] = pad[:, a::2, b::2, :]
+    assert torch.equal(cells.cpu(), exp)
+    # the patch-wise cells are windows of it: patch (prow, pcol) = cells[20 prow : +50, 20 pcol : +50]
+    pc = torch.empty(96, 50, 50, 16, dtype=torch.bfloat16, device=DEV)
+    ctx.extract_patches_s2d(im.to(DEV), pc, 1)
+    win = torch.empty(96, 50 * 50 * 16, dtype=torch.bfloat16, device=DEV)
+    ctx.window_gather(cells, 6, 8, 50, 20, win)
+    assert torch.equal(win.view(96, 50, 50, 16), pc)
+    # 7x7 windows at stride 5 and the transpose
+    src = bf16_rand(2, 32, 42, 256, seed=63)
+    out = torch.empty(96, 7, 7, 256, dtype=torch.bfloat16, device=DEV)
+    ctx.window_gather(src, 6, 8, 7, 5, out)
+    ref = src.cpu().unfold(1, 7, 5).unfold(2, 7, 5).permute(0, 1, 2, 4, 5, 3).reshape(96, 7, 7, 256)
+    assert torch.equal(out.cpu(), ref)
+    go = bf16_rand(96, 7, 7, 256, seed=64)
+    gs = torch.full((2, 32, 42, 256), 3.0, dtype=torch.bfloat16, device=DEV)
+    ctx.window_scatter_sum(go, 6, 8, 7, 5, gs)
+    x = src.cpu().double().requires_grad_(True)
+    x.unfold(1, 7, 5).unfold(2, 7, 5).permute(0, 1, 2, 4, 5, 3).reshape(96, 7, 7, 256).backward(go.cpu().double())
+    assert torch.equal(gs.cpu(), x.grad.to(torch.bfloat16))
