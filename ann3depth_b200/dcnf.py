@@ -142,11 +142,14 @@ class DCNFNet:
         self.d3 = cd(N0, s2[0], s2[1], 256, 256, 3, 3, 1, "valid", impl=impl)       # :71
         self.d4 = cd(N0, s3[0], s3[1], 256, 256, 3, 3, 1, "valid", impl=impl)       # :72
         self.p0, self.i0 = z(N0, *s0, 64, **bf), z(N0, *s0, 64, **u8)
-        self.c1 = z(N0, *s1, 256, **f32)
+        # conv outputs that feed a max-pool: f32 + routing record when training; inference pools the bf16 output (the same
+        # values: rounding is monotone) at half the bytes
+        pool_src = f32 if train else bf
+        self.c1 = z(N0, *s1, 256, **pool_src)
         self.p1, self.i1 = z(N0, *q1, 256, **bf), z(N0, *q1, 256, **u8)
         self.c2 = z(N0, *s2, 256, **bf)
         self.c3 = z(N0, *s3, 256, **bf)
-        self.c4 = z(N0, *s4, 256, **f32)
+        self.c4 = z(N0, *s4, 256, **pool_src)
         self.p4, self.i4 = z(N0, *q4, 256, **bf), z(N0, *q4, 256, **u8)
         # the first dense layer's input: one 7x7x256 window per patch
         self.xd = z(NP, 12544, **bf) if unary == "fullconv" else self.p4.view(NP, 12544)
@@ -217,11 +220,17 @@ class DCNFNet:
             c.extract_patches_s2d(self.im, self.cells, self.first_fold)
         c.conv2d_pool4_fwd(self.d0, self.cells, self.wbig0, self.wf(U + "conv2d/bias"), relu=True, out=self.p0, idx=self.i0)
         c.conv2d_fwd(self.d1, self.p0, self.w(U + "conv2d_1" + K), self.wf(U + "conv2d_1/bias"), relu=True, out=self.c1)
-        c.maxpool2x2_fwd_f32(self.c1, out=self.p1, idx=self.i1)
+        if self.train:
+            c.maxpool2x2_fwd_f32(self.c1, out=self.p1, idx=self.i1)
+        else:
+            c.maxpool2x2_fwd(self.c1, out=self.p1)
         c.conv2d_fwd(self.d2, self.p1, self.w(U + "conv2d_2" + K), self.wf(U + "conv2d_2/bias"), relu=True, out=self.c2)
         c.conv2d_fwd(self.d3, self.c2, self.w(U + "conv2d_3" + K), self.wf(U + "conv2d_3/bias"), relu=True, out=self.c3)
         c.conv2d_fwd(self.d4, self.c3, self.w(U + "conv2d_4" + K), self.wf(U + "conv2d_4/bias"), relu=True, out=self.c4)
-        c.maxpool2x2_fwd_f32(self.c4, out=self.p4, idx=self.i4)
+        if self.train:
+            c.maxpool2x2_fwd_f32(self.c4, out=self.p4, idx=self.i4)
+        else:
+            c.maxpool2x2_fwd(self.c4, out=self.p4)
         if self.unary == "fullconv":                  # patch (prow, pcol) reads the 7x7 window at (5 prow, 5 pcol)
             rows, cols = num_superpixels()
             c.window_gather(self.p4, rows, cols, 7, 5, self.xd)

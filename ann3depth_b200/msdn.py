@@ -92,11 +92,14 @@ class MSDNNet:
         # Both first layers are 3x3 stride-1 convolutions on it (coarse 11x11 s4; fine 9x9 s2 + pool = 11x11 s4).
         self.img4 = z(B, IN_H // 4, IN_W // 4, 64, **bf)
         self.tar = z(B, OUT_H, OUT_W, 1, **f32)         # resized target
-        # conv outputs that feed a max-pool stay f32 and the pool records its routing (see a3d.h)
-        self.c0 = z(B, 55, 74, 96, **f32)
+        # conv outputs that feed a max-pool stay f32 and the pool records its routing (see a3d.h).  Inference has no routing
+        # to record: the conv writes bf16 and the pool runs on bf16 -- the same values (rounding is monotone, so
+        # max(bf16(x)) == bf16(max(x))) at half the bytes
+        pool_src = f32 if (train or self.tf32) else bf
+        self.c0 = z(B, 55, 74, 96, **pool_src)
         self.p0 = z(B, 27, 37, 128, **bf)               # 96 channels + 32 zero: 128-byte pixels for conv2d_1
         self.i0 = torch.zeros(B, 27, 37, 96, dtype=torch.uint8, device=self.dev)
-        self.c1 = z(B, 27, 37, 256, **f32)
+        self.c1 = z(B, 27, 37, 256, **pool_src)
         self.p1 = z(B, 13, 18, 256, **bf)
         self.i1 = torch.zeros(B, 13, 18, 256, dtype=torch.uint8, device=self.dev)
         self.c2 = z(B, 13, 18, 384, **bf)
@@ -213,9 +216,15 @@ class MSDNNet:
         # coarse (src/models.py:208-236)
         n = "coarse/conv/conv2d_"
         c.conv2d_fwd(self.d_c0, self.img4, self.w(n + "0" + K), self.bias(n + "0"), relu=True, out=self.c0)
-        c.maxpool2x2_fwd_f32(self.c0, out=self.p0, idx=self.i0)
+        if self.c0.dtype == torch.bfloat16:            # inference: bf16 pool, no routing record
+            c.maxpool2x2_fwd(self.c0, out=self.p0, ldy=self.p0.shape[-1])
+        else:
+            c.maxpool2x2_fwd_f32(self.c0, out=self.p0, idx=self.i0)
         c.conv2d_fwd(self.d_c1, self.p0, self.w(n + "1" + K), self.bias(n + "1"), relu=True, out=self.c1)
-        c.maxpool2x2_fwd_f32(self.c1, out=self.p1, idx=self.i1)
+        if self.c1.dtype == torch.bfloat16:
+            c.maxpool2x2_fwd(self.c1, out=self.p1)
+        else:
+            c.maxpool2x2_fwd_f32(self.c1, out=self.p1, idx=self.i1)
         c.conv2d_fwd(self.d_c2, self.p1, self.w(n + "2" + K), self.bias(n + "2"), relu=True, out=self.c2)
         c.conv2d_fwd(self.d_c3, self.c2, self.w(n + "3" + K), self.bias(n + "3"), relu=True, out=self.c3)
         c.conv2d_fwd(self.d_c4, self.c3, self.w(n + "4" + K), self.bias(n + "4"), relu=True, out=self.c4)

@@ -301,9 +301,16 @@ def other_configs(torch, pk):
     for _ in range(2):
         opd.run()
     ms = timed(opd.run, 5)
-    tf = 3.0 * 2.672e9 * 768 / ms / 1e9                   # unary CNN forward + dgrad + wgrad
+    # The reference formulation (48 overlapping patches per image) is 2.672 GFLOP forward per patch;
+    # the fully convolutional evaluation computes every shared activation once: 46.14 GFLOP forward per IMAGE
+    # (11x11x3 at 290x370, 5x5x64 at 141x181, 3x3x256 at 68x88 / 66x86 / 64x84, the dense layers per patch).
+    # fwd + dgrad + wgrad ~ 3x forward.  `frac_of_bf16_burst` is on the FLOPs actually needed, not the patch-wise count.
+    tf_ref = 3.0 * 2.672e9 * 768 / ms / 1e9
+    tf = 3.0 * 46.14e9 * 16 / ms / 1e9
     out["dcnf_train_bs16"] = {"ms_per_step": ms, "images_per_s": 16 / ms * 1e3, "tflops_algorithmic": tf,
-                              "frac_of_bf16_burst": tf / pk["bf16_tflops"], "crf_status_max": int(opd.net.status.max())}
+                              "tflops_patchwise_equivalent": tf_ref, "frac_of_bf16_burst": tf / pk["bf16_tflops"],
+                              "formulation": "fully convolutional (one pass per padded image, 7x7 windows gathered)",
+                              "crf_status_max": int(opd.net.status.max())}
     del opd
     torch.cuda.empty_cache()
     return out

@@ -180,3 +180,18 @@ def test_dcnf_fully_convolutional_equals_patchwise():
         nr = float(res["fullconv"][3][name].double().norm() / (g.double().norm() + 1e-300))
         print(f"{name:36s} cos={c:.7f} norm ratio={nr:.5f}")
         assert c >= 0.9999 and 0.99 < nr < 1.01, name
+
+
+def test_dcnf_inference_equals_training_forward():
+    """train=False pools the bf16 conv outputs (no routing record): bit-identical predictions (rounding is monotone)."""
+    B = 2
+    images, depths, p = make(B, seed=9)
+    opt = models.dcnf(images.to(DEV), depths.to(DEV), train=True, naive_loss=False)
+    opt.net.load_params(p)
+    opt.net.forward()
+    opi = models.dcnf(images.to(DEV), depths.to(DEV), train=False, naive_loss=False)
+    opi.net.load_params(p)
+    out = opi.run()
+    torch.cuda.synchronize()
+    assert opi.net.c1.dtype == torch.bfloat16 and opt.net.c1.dtype == torch.float32
+    assert torch.equal(opi.net.z, opt.net.z) and torch.equal(out, opt.net.output)
