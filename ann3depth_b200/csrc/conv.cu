@@ -15,6 +15,8 @@ int a3d_tc_dense_fwd(a3d_ctx*, const uint16_t* x, int ldx, const uint16_t* w, co
 struct a3d_actbwd_args { const uint16_t* y; const uint8_t* keep_mask; float drop_rate; unsigned flags; };
 int a3d_tc_dense_dgrad(a3d_ctx*, const uint16_t* dy, int lddy, const uint16_t* w, uint16_t* dx, float* acc_ws, int M,
                        int N, int K, cudaStream_t st, const a3d_actbwd_args* ab = nullptr);
+int a3d_tc_dense_dgrad_rows(a3d_ctx*, const uint16_t* dy, int lddy, const uint16_t* w, uint16_t* dx, int M, int N, int K,
+                            cudaStream_t st);
 int a3d_tc_dense_wgrad(a3d_ctx*, const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, int M, int N, int K,
                        cudaStream_t st);
 
@@ -384,6 +386,8 @@ extern "C" int a3d_dense_dgrad(a3d_ctx* ctx, const uint16_t* dy, int lddy, const
   cudaStream_t st = as_stream(stream);
   bool tc_ok = (K % 8 == 0) && (lddy % 8 == 0) && M <= 128 && acc_ws;
   if (impl != A3D_IMPL_SIMT && tc_ok) return a3d_tc_dense_dgrad(ctx, dy, lddy, w, dx, acc_ws, M, N, K, st);
+  if (impl != A3D_IMPL_SIMT && M > 128 && N % 64 == 0 && K % 64 == 0 && lddy % 8 == 0)
+    return a3d_tc_dense_dgrad_rows(ctx, dy, lddy, w, dx, M, N, K, st);       // long batch (DCNF patches)
   if (impl == A3D_IMPL_TC) {
     a3d_set_error("dense dgrad: shape not supported by the tcgen05 path (M=%d N=%d K=%d lddy=%d)", M, N, K, lddy);
     return A3D_ENOTSUP;

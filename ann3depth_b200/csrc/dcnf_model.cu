@@ -235,7 +235,7 @@ int backward(a3d_dcnf* n, void* st) {
   CK(a3d_dense_dgrad(c, n->g_h1, 16, Wb(U "dense_1/kernel"), n->g_h0a, n->dense_acc, NP, 16, 128, S, st));
   CK(a3d_dense_epilogue_bwd(c, n->g_h0a, n->h0, nullptr, 0.f, n->g_h0, (size_t)NP * 128, A3D_EPI_RELU, st));
   CK(a3d_dense_wgrad(c, n->xd, 12544, n->g_h0, 128, G(U "dense/kernel"), G(U "dense/bias"), NP, 128, 12544, A3D_IMPL_AUTO, st));
-  CK(a3d_dense_dgrad(c, n->g_h0, 128, Wb(U "dense/kernel"), n->g_xd, n->dense_acc, NP, 128, 12544, S, st));
+  CK(a3d_dense_dgrad(c, n->g_h0, 128, Wb(U "dense/kernel"), n->g_xd, n->dense_acc, NP, 128, 12544, A3D_IMPL_AUTO, st));
   CK(a3d_window_scatter_sum(c, n->g_xd, n->B, Q4H, Q4W, 256, ROWS, COLS, 7, 5, n->g_p4, st));
   CK(a3d_maxpool2x2_idx_bwd(c, n->i4, n->g_p4, 256, n->B, S4H, S4W, 256, n->g_c4, st));
   CK(a3d_conv2d_wgrad(c, &n->d4, n->c3, n->g_c4, G(U "conv2d_4/kernel"), G(U "conv2d_4/bias"), n->scratch, n->scratch_bytes, st));

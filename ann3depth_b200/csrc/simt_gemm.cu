@@ -293,8 +293,34 @@ int a3d_simt_dense_dgrad(a3d_ctx* ctx, const uint16_t* dy, int lddy, const uint1
   return launch(ctx, p, M, K, st);
 }
 
+// Tiny weight matrices (DCNF dense_1 16x128, dense_2 1x16) over a long batch (768 patches): the 64x64-tile kernel would
+// run the whole M loop in one or two CTAs (57 / 93 us).  Here the batch is cut into `gridDim.y` slices, every thread owns
+// one dw[n][k] of its slice (x row reads coalesced over k, dy broadcast), slices meet with one atomicAdd per output.
+__global__ void small_dense_wgrad_kernel(const uint16_t* __restrict__ x, int ldx, const uint16_t* __restrict__ dy, int lddy,
+                                         float* __restrict__ dw, int M, int N, int K) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= N * K) return;
+  const int n = o / K, k = o - n * K;
+  const int per = (M + gridDim.y - 1) / gridDim.y;
+  const int m0 = blockIdx.y * per, m1 = min(M, m0 + per);
+  float acc = 0.f;
+  for (int m = m0; m < m1; ++m)
+    acc += bf16_bits_to_f32(__ldg(dy + (size_t)m * lddy + n)) * bf16_bits_to_f32(__ldg(x + (size_t)m * ldx + k));
+  atomicAdd(dw + o, acc);
+}
+
 int a3d_simt_dense_wgrad(a3d_ctx* ctx, const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, int M,
                          int N, int K, cudaStream_t st) {
+  if ((long long)N * K <= 4096 && M >= 256) {
+    A3D_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)N * K * sizeof(float), st));
+    const int bx = (N * K + 127) / 128;
+    int slices = ctx->sm_count * 2 / bx;
+    if (slices < 1) slices = 1;
+    if (slices > M / 16) slices = M / 16;
+    small_dense_wgrad_kernel<<<dim3(bx, slices), 128, 0, st>>>(x, ldx, dy, lddy, dw, M, N, K);
+    A3D_LAUNCH_OK(ctx);
+    return 0;
+  }
   DenseWgradProb p{x, dy, dw, M, N, K, ldx, lddy};
   return launch(ctx, p, N, K, st);
 }

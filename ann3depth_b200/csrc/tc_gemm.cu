@@ -862,6 +862,29 @@ int a3d_tc_dgrad_cols(a3d_ctx* ctx, const a3d_conv_desc* d, const uint16_t* dy, 
   return launch_cfg<tc::Cfg<64, 128, false, true, 64>>(ctx, tmA, tmB, p, 1, st);
 }
 
+// dense dgrad of a LONG batch (DCNF: 768 patches x 128 -> 12544): the batch is the GEMM M dimension, A = dy K-major,
+// B = w MN-major (as in a3d_tc_dgrad_cols), bf16 rows written straight from the epilogue -- one launch, no accumulation
+// buffer.  The weight-streaming form below (batch <= 128 as the UMMA N dimension) is for the batch-32 MSDN layers.
+int a3d_tc_dense_dgrad_rows(a3d_ctx* ctx, const uint16_t* dy, int lddy, const uint16_t* w, uint16_t* dx, int M, int N, int K,
+                            cudaStream_t st) {
+  if (N % 64 || K % 64 || lddy % 8) {
+    a3d_set_error("tc dense dgrad (rows): needs N %% 64 == 0, K %% 64 == 0, lddy %% 8 == 0 (N=%d K=%d)", N, K);
+    return A3D_ENOTSUP;
+  }
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d(ctx, &tmA, dy, M, N, lddy, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d(ctx, &tmB, w, N, K, K, 64, 64);
+  if (rc) return rc;
+  tc::Params p{};
+  p.M = M; p.N = K; p.num_kb = N / 64; p.kb_per_split = p.num_kb; p.a_mode = tc::A_TILED;
+  p.epi = tc::EPI_ROW_BF16; p.out = dx; p.ldo = K; p.atomic = 0;
+  const int bn = K % 256 == 0 ? 256 : K % 128 == 0 ? 128 : 64;
+  if (bn == 256) return launch_cfg<tc::Cfg<256, 128, false, true, 64>>(ctx, tmA, tmB, p, 1, st);
+  if (bn == 128) return launch_cfg<tc::Cfg<128, 128, false, true, 64>>(ctx, tmA, tmB, p, 1, st);
+  return launch_cfg<tc::Cfg<64, 128, false, true, 64>>(ctx, tmA, tmB, p, 1, st);
+}
+
 // ------------------------------------------------------------------------------------------------
 // dense backward.  dgrad: dx[b][k] = sum_n dy[b][n] w[n][k]  -> D^T[k][b], A = w MN-major, B = dy K-major.
 struct a3d_actbwd_args { const uint16_t* y; const uint8_t* keep_mask; float drop_rate; unsigned flags; };

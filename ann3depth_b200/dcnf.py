@@ -276,7 +276,7 @@ class DCNFNet:
         c.dense_dgrad(self.g_h1, self.w(U + "dense_1" + K), out=self.g_h0a, impl=S)
         c.dense_epilogue_bwd(self.g_h0a, self.h0, None, 0.0, L.EPI_RELU, out=self.g_h0)
         c.dense_wgrad(self.xd, self.g_h0, dw=self.gw(U + "dense" + K), db=self.gw(U + "dense/bias"), impl=self.impl)
-        c.dense_dgrad(self.g_h0, self.w(U + "dense" + K), out=self.g_xd, impl=S)
+        c.dense_dgrad(self.g_h0, self.w(U + "dense" + K), out=self.g_xd, impl=self.impl)
         if self.unary == "fullconv":                  # shared activations: sum over the (up to 4) windows covering them
             rows, cols = num_superpixels()
             c.window_scatter_sum(self.g_xd, rows, cols, 7, 5, self.g_p4)

@@ -902,3 +902,23 @@ def test_image_cells_and_window_gather_scatter(ctx):
     x = src.cpu().double().requires_grad_(True)
     x.unfold(1, 7, 5).unfold(2, 7, 5).permute(0, 1, 2, 4, 5, 3).reshape(96, 7, 7, 256).backward(go.cpu().double())
     assert torch.equal(gs.cpu(), x.grad.to(torch.bfloat16))
+
+
+def test_dense_bwd_long_batch(ctx):
+    """DCNF dense layers: 768 patches.  dgrad with the batch as the GEMM M dimension (a3d_tc_dense_dgrad_rows) and the
+    tiny weight gradients (16x128, 1x16) through the sliced CUDA-core kernel, against fp32 on the same bf16 values."""
+    M, N, K = 768, 128, 12544
+    w = bf16_rand(N, K, seed=70, scale=1.0 / math.sqrt(K))
+    dy = bf16_rand(M, N, seed=71)
+    n0 = ctx.launches
+    dx = ctx.dense_dgrad(dy, w, impl=L.IMPL_TC)
+    assert ctx.launches == n0 + 1                                   # one GEMM launch, no memset / finish
+    assert rel_err(dx, dy.float() @ w.float()) < 1e-2
+    assert rel_err(ctx.dense_dgrad(dy, w, impl=L.IMPL_SIMT), dy.float() @ w.float()) < 1e-2
+    for (n, k) in ((16, 128), (1, 16)):
+        x = bf16_rand(M, k, seed=72)
+        g = bf16_rand(M, n, seed=73)
+        db = torch.empty(n, dtype=torch.float32, device=DEV)
+        dw, _ = ctx.dense_wgrad(x, g, db=db, N=n, impl=L.IMPL_SIMT)
+        assert rel_err(dw, g.float().t() @ x.float()) < 1e-4
+        assert rel_err(db, g.float().sum(0)) < 2e-3
