@@ -592,10 +592,11 @@ class MSDNNet:
         # Single GPU: TF-Adam of conv2d_4 .. conv2d_1 (99 % of the group) runs on the idle fine stream next to
         # conv2d_0's weight gradient; only conv2d_0's 55 k parameters are updated in the step's tail.  The group is
         # one contiguous arena range in backward order, so this is the same update as two launches.
-        # DP exchange of the conv stack (4 M parameters, at the very end of the step): from 4 ranks on ONE f32 allreduce
-        # + replicated Adam beats cast + reduce-scatter + sharded Adam + all-gather (4 GPUs: 1.160 vs 1.185 ms; the
-        # collectives are latency-bound at 8-16 MB); at 2 ranks the sharded form was the faster one.
-        conv_allreduce = os.environ.get("A3D_DP_CONV_ALLREDUCE", "1" if (self.comm and self.comm.world >= 4) else "0") == "1"
+        # DP exchange of the conv stack (4 M parameters): f32 allreduce + replicated Adam beats cast + reduce-scatter +
+        # sharded Adam + all-gather at every world size (4 GPUs: 1.160 vs 1.185 ms; 2 GPUs, with the split below:
+        # 0.972 vs 1.015 ms -- the collectives are latency-bound at 8-16 MB and the sharded form needs three of them).
+        # A3D_DP_CONV_ALLREDUCE=0 selects the sharded form (a weight-sharded optimizer, kept for large conv stacks).
+        conv_allreduce = os.environ.get("A3D_DP_CONV_ALLREDUCE", "1" if self.comm else "0") == "1"
         lo_cc, hi_cc = a.group_range("CoarseConv")
         split_cc = a.specs["coarse/conv/conv2d_0/kernel"].offset
         split_ok = (not self.comm) and lo_cc < split_cc < hi_cc and a.specs["coarse/conv/conv2d_0/bias"].offset > split_cc
@@ -606,7 +607,7 @@ class MSDNNet:
         # the GEMMs they overlap with -- so it is off by default.
         dp_split = bool(self.comm) and lo_cc < split_cc < hi_cc and (split_cc - lo_cc) % (self.comm.world * 8) == 0 and \
             os.environ.get("A3D_DP_CONV_SPLIT", "0") == "1" and not conv_allreduce
-        # With the f32-allreduce exchange (4+ ranks) the same cut is ON by default: conv2d_4 .. conv2d_1 (99 % of the bucket)
+        # With the f32-allreduce exchange (the default) the same cut is ON by default: conv2d_4 .. conv2d_1 (99 % of the bucket)
         # are all-reduced and updated behind conv2d_1's weight gradient, under conv2d_1's dgrad, the pool backward and
         # conv2d_0's wgrad; the step's tail exchanges conv2d_0's 55 k parameters only.  (8 GPUs, profiles/
         # step_timeline_r02_n8_rank0.json: the single 16 MB allreduce + Adam was ~150 us of exposed tail.)
