@@ -298,9 +298,10 @@ def other_configs(torch, pk):
     pp = glorot_params(5, "dcnf")
     pp["pairwise/pairwise_layers/dense/kernel"].abs_()
     opd.net.load_params(pp)
+    step = lambda: opd.run(use_graph=True)               # one captured CUDA graph per step (dcnf.py train_step)
     for _ in range(2):
-        opd.run()
-    ms = timed(opd.run, 5)
+        step()
+    ms = timed(step, 10)
     # The reference formulation (48 overlapping patches per image) is 2.672 GFLOP forward per patch;
     # the fully convolutional evaluation computes every shared activation once: 46.14 GFLOP forward per IMAGE
     # (11x11x3 at 290x370, 5x5x64 at 141x181, 3x3x256 at 68x88 / 66x86 / 64x84, the dense layers per patch).

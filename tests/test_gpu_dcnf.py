@@ -195,3 +195,22 @@ def test_dcnf_inference_equals_training_forward():
     torch.cuda.synchronize()
     assert opi.net.c1.dtype == torch.bfloat16 and opt.net.c1.dtype == torch.float32
     assert torch.equal(opi.net.z, opt.net.z) and torch.equal(out, opt.net.output)
+
+
+def test_dcnf_graph_step_equals_eager_step():
+    B = 1
+    images, depths, p = make(B, seed=10)
+    res = {}
+    for use_graph in (False, True):
+        op = models.dcnf(images.to(DEV), depths.to(DEV), train=True, naive_loss=False)
+        op.net.load_params(p)
+        for _ in range(3):
+            op.run(use_graph=use_graph)
+        torch.cuda.synchronize()
+        assert op.global_step == 3
+        res[use_graph] = (op.net.arena.w.clone(), float(op.net.loss))
+    # split-K atomics make two runs differ in the last bits; three SGD steps stay within 1e-5 of the weights' scale
+    d = float((res[True][0] - res[False][0]).abs().max())
+    print("graph vs eager max weight diff", d, "loss", res[True][1], res[False][1])
+    assert d < 1e-4 * float(res[False][0].abs().max())
+    assert abs(res[True][1] - res[False][1]) < 1e-3 * max(1.0, abs(res[False][1]))
