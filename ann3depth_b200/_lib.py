@@ -22,6 +22,9 @@ class A3DError(RuntimeError):
     pass
 
 
+ABI_VERSION = 200          # include/a3d.h A3D_VERSION
+
+
 class ConvDesc(C.Structure):
     """Mirror of `a3d_conv_desc` (include/a3d.h)."""
     _fields_ = [(n, C.c_int) for n in
@@ -172,9 +175,13 @@ def load():
                        "(there is no CPU or PyTorch fallback)")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
-        fn = getattr(lib, name)
+        fn = getattr(lib, name, None)
+        if fn is None:
+            raise A3DError(f"{LIB_PATH} does not export {name}: stale build, run `make -C ann3depth_b200/csrc`")
         fn.restype = res
         fn.argtypes = args
+    if lib.a3d_version() != ABI_VERSION:           # e.g. a3d_conv_desc grew two fields in 200: a stale .so misreads it
+        raise A3DError(f"{LIB_PATH} is ABI version {lib.a3d_version()}, this host code expects {ABI_VERSION}: rebuild")
     _lib = lib
     return lib
 

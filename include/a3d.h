@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define A3D_VERSION 100
+#define A3D_VERSION 200   /* 200: a3d_conv_desc gained dil_w / pix_pitch; TF32, model-level and DCNF fully convolutional entry points */
 
 /* negative error codes */
 #define A3D_EINVAL   (-1)   /* bad argument / unsupported shape */
