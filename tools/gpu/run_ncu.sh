@@ -1,6 +1,7 @@
 #!/bin/bash
 # ncu passes with the tuner's choices of a plain run (A3D_TUNE_CACHE): launch list, then the full set on the GEMMs and the
-# dense update.  Round tag as $1 (default r02).
+# dense update.  Round tag as $1 (default r02).  Budget ~10 GPU-minutes: the full-set pass replays 44 kernels ~40 times each
+# under a Python process that ncu slows down considerably (the DCNF variant, run_ncu_dcnf.sh, takes ~3.5 minutes).
 mkdir -p gpurun_out
 TAG=${1:-r02}
 rm -f gpurun_out/tune_cache.txt
