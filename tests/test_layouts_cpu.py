@@ -132,3 +132,34 @@ def test_dcnf_first_index_maps_fold_and_embed():
     (P.dcnf_first_embedded(wr).reshape(-1) * gb).sum().backward()
     assert float((P.unpack(ks, fold.view(ks.packed_shape)) - wr.grad).abs().max()) < 1e-12
     assert torch.equal(bmap[1], torch.arange(64, dtype=torch.int32) + 64)
+
+
+def test_dcnf_fully_convolutional_equals_patchwise_in_float64():
+    """The claim behind dcnf.py's unary="fullconv" (DESIGN.md 4.2b), checked on the CPU in float64 with the real geometry
+    (240x320 image, 100x100 patches at stride 40 with a zero border of 30, src/models.py:50-83: 11x11 conv, pool, 5x5 conv,
+    pool, three 3x3 convs, pool -- all VALID) and a few channels: every layer of patch (prow, pcol) is a window of the same
+    layer of the zero-padded whole image, and the 7x7 input of the dense layers is the window at (5 prow, 5 pcol)."""
+    from oracle import dcnf as OD
+    g = torch.Generator().manual_seed(5)
+    img = torch.rand(1, 240, 320, 3, generator=g, dtype=torch.float64)
+    chans = [3, 4, 5, 5, 5, 6]
+    ks = [11, 5, 3, 3, 3]
+    ws = [torch.randn(chans[i + 1], chans[i], ks[i], ks[i], generator=g, dtype=torch.float64) / ks[i] for i in range(5)]
+    bs = [torch.randn(chans[i + 1], generator=g, dtype=torch.float64) * 0.1 for i in range(5)]
+
+    def cnn(x):                                        # x [N,3,H,W] -> last pooled map
+        t = F.max_pool2d(torch.relu(F.conv2d(x, ws[0], bs[0])), 2, 2)
+        t = F.max_pool2d(torch.relu(F.conv2d(t, ws[1], bs[1])), 2, 2)
+        t = torch.relu(F.conv2d(t, ws[2], bs[2]))
+        t = torch.relu(F.conv2d(t, ws[3], bs[3]))
+        return F.max_pool2d(torch.relu(F.conv2d(t, ws[4], bs[4])), 2, 2)
+
+    patches = OD.patches(img).reshape(48, 100, 100, 3).permute(0, 3, 1, 2)            # the reference's formulation
+    per_patch = cnn(patches)                                                          # [48, 6, 7, 7]
+    assert per_patch.shape[-2:] == (7, 7)
+    full = cnn(F.pad(img.permute(0, 3, 1, 2), (30, 30, 30, 30)))                       # once, on the padded image
+    assert full.shape[-2:] == (32, 42)
+    win = full.unfold(2, 7, 5).unfold(3, 7, 5)                                         # [1, C, 6, 8, 7, 7]
+    assert win.shape[2:4] == (6, 8)
+    gathered = win.permute(0, 2, 3, 1, 4, 5).reshape(48, chans[-1], 7, 7)
+    assert float((gathered - per_patch).abs().max()) < 1e-12
