@@ -4,7 +4,9 @@ Mirrors `_DistributedConvolutionalNeuralFields` of the reference (src/models.py:
 240x320, 100x100 patches around the 6x8 grid of 40x40 tiles, unary CNN on every patch, pairwise
 colour / histogram similarities through a 2->1 dense layer, CRF negative log-likelihood with
 A = I + D - R, plain SGD (lr 0.1).  The hard-coded worker devices of the reference (:63-79) and its
-serial `map_fn`s are gone: all B*48 patches form one batch and every CRF graph gets its own CTA.
+serial `map_fn`s are gone: the unary CNN runs once per zero-padded image (fully convolutional -- its patches
+are windows of that pass; `unary="patches"` keeps the literal B*48-patch batch), and every CRF graph gets
+its own CTA.
 
 As in TF 1.3, no gradient reaches `pairwise_layers` (ScatterNdUpdate is not differentiable,
 src/models.py:138-141): only the unary CNN trains.
