@@ -1,10 +1,11 @@
 // dcnf_model.cu -- model-level entry points for DCNF (Liu et al.; `models.dcnf`, src/models.py:9-200): the whole train
 // step / inference behind the C-ABI (a3d_dcnf_create / a3d_dcnf_step / a3d_dcnf_infer), the counterpart of msdn_model.cu.
 // Caller-owned workspace, no allocation or host synchronisation inside a step (CUDA-graph capturable after the first,
-// autotuning, call).  Mirrors ann3depth_b200/dcnf.py launch for launch: resize to 240x320, 100x100 patches around the 6x8
-// grid of 40x40 tiles, the unary CNN on all B*48 patches at once (first layer pool-fused over
-// space-to-depth(2) patches), pairwise colour / histogram similarities through the 2->1
-// dense layer, CRF negative log-likelihood with A = I + D - R (one CTA per graph), plain SGD (lr 0.1).  As in TF 1.3 no
+// autotuning, call).  Mirrors ann3depth_b200/dcnf.py (unary = "fullconv") launch for launch: resize to 240x320, the unary
+// CNN ONCE per zero-padded image (the reference's 100x100 patches around the 6x8 grid of 40x40 tiles are windows of that
+// pass; first layer pool-fused over space-to-depth(2) cells), one 7x7x256 window per patch into the dense layers,
+// pairwise colour / histogram similarities through the 2->1 dense layer, CRF negative log-likelihood with
+// A = I + D - R (one CTA per graph), plain SGD (lr 0.1).  As in TF 1.3 no
 // gradient reaches `pairwise_layers` (ScatterNdUpdate is not differentiable, src/models.py:138-141).
 #include "common.cuh"
 #include <string.h>
